@@ -1,0 +1,93 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE — build the UNCHANGED reference CPU path into oracle/_ref/.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may use
+anything under oracle/.  This recipe compiles the reference sources *where they lie* under
+/root/reference (nothing is copied into the repo), against the declaration-only headers in
+oracle/stubinc/, the link stubs in oracle/stubs.c and the clean-room GSL subset oracle/minigsl.c.
+Outputs go ONLY to oracle/_ref/ (git-ignored, travels to the GPU box with gpurun):
+
+    oracle/_ref/libodexp_ref.a          main.c methods_odexp.c datastruct.c loader.c options.c
+                                        rand_gen.c utils_odexp.c lrexp.c + stubs + minigsl
+    oracle/_ref/<fixture>/model.out     reference `perl src/odexp -d -q` output for the fixture, compiled -O3
+    oracle/_ref/<fixture>/.odexp/       equations.pop / parameters.pop the binary re-reads at run time
+
+The reference's own build system (cmake, macOS dylibs, libgsl) is NOT used; see DESIGN.md §oracle.
+"""
+import os, shutil, subprocess, sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("ODX_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+LIB_SRCS = ["main", "methods_odexp", "datastruct", "loader", "options", "rand_gen", "utils_odexp", "lrexp"]
+CFLAGS = ["-std=gnu99", "-O3", "-D_GNU_SOURCE", "-w", "-I" + os.path.join(HERE, "stubinc"),
+          "-I" + os.path.join(REF, "src"), "-include", "errno.h", "-include", "gsl/gsl_errno.h"]
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, "src", "methods_odexp.c")) and shutil.which("perl") and shutil.which("gcc")
+
+
+def fixtures():
+    fx = {}
+    d = os.path.join(HERE, "fixtures")
+    for f in sorted(os.listdir(d)):
+        if f.endswith(".pop"):
+            fx[f[:-4]] = os.path.join(d, f)
+    shipped = os.path.join(REF, "examples", "kuramoto.pop")   # BASELINE config 1: "as shipped"
+    if os.path.isfile(shipped):
+        fx["kuramoto_shipped"] = shipped
+    return fx
+
+
+def build(force=False, verbose=False):
+    if not available():
+        return False
+    os.makedirs(os.path.join(OUT, "obj"), exist_ok=True)
+    lib = os.path.join(OUT, "libodexp_ref.a")
+    objs = []
+    for s in LIB_SRCS:
+        src, obj = os.path.join(REF, "src", s + ".c"), os.path.join(OUT, "obj", s + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
+            run(["gcc"] + CFLAGS + ["-c", src, "-o", obj])
+        objs.append(obj)
+    for s in ["stubs", "minigsl", "rand_hook"]:
+        src, obj = os.path.join(HERE, s + ".c"), os.path.join(OUT, "obj", s + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
+            run(["gcc", "-std=gnu99", "-O3", "-Wall", "-I" + os.path.join(HERE, "stubinc"), "-c", src, "-o", obj])
+        objs.append(obj)
+    if os.path.exists(lib):
+        os.remove(lib)
+    run(["ar", "rcs", lib] + objs)
+    for name, pop in fixtures().items():
+        d = os.path.join(OUT, name)
+        exe = os.path.join(d, "model.out")
+        if not force and os.path.exists(exe) and os.path.getmtime(exe) > os.path.getmtime(pop) \
+                and os.path.getmtime(exe) > os.path.getmtime(lib) - 1e9:
+            # relink is cheap, but keep incremental builds quick
+            pass
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        local = os.path.join(d, os.path.basename(pop))
+        shutil.copy(pop, local)
+        # reference generator: -d generate only, -q quiet (appends `OPT loudness quiet`)
+        run(["perl", os.path.join(REF, "src", "odexp"), "-d", "-q", os.path.basename(pop)], cwd=d)
+        # link order: model + whole archive objects first so rand()/srand() from rand_hook.o win over libc
+        run(["gcc"] + CFLAGS + ["-I" + os.path.join(d, ".odexp"), os.path.join(d, ".odexp", "model.c")]
+            + objs + ["-lm", "-o", exe])
+        os.remove(local)
+        if verbose:
+            print("built", exe)
+    return True
+
+
+if __name__ == "__main__":
+    ok = build(force="--force" in sys.argv, verbose=True)
+    print("oracle/_ref:", "built" if ok else "reference or toolchain not present; skipped")

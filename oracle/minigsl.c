@@ -1,0 +1,268 @@
+/* TEST INFRASTRUCTURE — clean-room restatement of the parts of the GNU Scientific Library that the
+ * reference's population path calls.  PARITY WITH REAL GSL IS UNPINNED: GSL (version unpinned by
+ * the reference: CMakeLists.txt:35 `find_package(GSL REQUIRED)`) is not under /root/reference and is
+ * not installed here, and the reference ships no golden outputs.  The algorithms below restate GSL's
+ * published behaviour (gsl-2.x doc, "Ordinary Differential Equations" and "Chebyshev Approximations"):
+ *
+ *   gsl_odeiv2_step_{rk4,rkf45,rkck}  call sites  src/methods_odexp.c:154-183,445-447,698-701
+ *   gsl_odeiv2_control_y_new          call site   src/methods_odexp.c:446
+ *   gsl_odeiv2_evolve_apply           call site   src/methods_odexp.c:619
+ *   gsl_cheb_{alloc,init,coeffs,eval_n_err,free}, gsl_sf_choose, gsl_pow_int
+ *                                     call sites  src/lrexp.c:116-165,191-245,296-353,407-468
+ *
+ * What pins them here: order-of-convergence, the embedded-pair identities and closed forms
+ * (tests/test_oracle_minigsl.py).  rk2, rk8pd and bsimp are not restated (abort if selected).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#include <gsl/gsl_errno.h>
+#include <gsl/gsl_odeiv2.h>
+#include <gsl/gsl_math.h>
+#include <gsl/gsl_chebyshev.h>
+#include <gsl/gsl_sf.h>
+
+/* ------------------------------------------------------------------ steppers */
+enum { MG_RK2, MG_RK4, MG_RKF45, MG_RKCK, MG_RK8PD, MG_BSIMP };
+struct gsl_odeiv2_step_type_struct { int kind; unsigned order; const char *name; };
+static const gsl_odeiv2_step_type t_rk2 = {MG_RK2, 2, "rk2"}, t_rk4 = {MG_RK4, 4, "rk4"},
+    t_rkf45 = {MG_RKF45, 5, "rkf45"}, t_rkck = {MG_RKCK, 5, "rkck"}, t_rk8pd = {MG_RK8PD, 8, "rk8pd"},
+    t_bsimp = {MG_BSIMP, 2, "bsimp"};
+const gsl_odeiv2_step_type *gsl_odeiv2_step_rk2 = &t_rk2;
+const gsl_odeiv2_step_type *gsl_odeiv2_step_rk4 = &t_rk4;
+const gsl_odeiv2_step_type *gsl_odeiv2_step_rkf45 = &t_rkf45;
+const gsl_odeiv2_step_type *gsl_odeiv2_step_rkck = &t_rkck;
+const gsl_odeiv2_step_type *gsl_odeiv2_step_rk8pd = &t_rk8pd;
+const gsl_odeiv2_step_type *gsl_odeiv2_step_bsimp = &t_bsimp;
+
+struct gsl_odeiv2_step_struct { const gsl_odeiv2_step_type *type; size_t dim; double *k[6], *y0, *ytmp, *yone; };
+struct gsl_odeiv2_control_struct { double eps_abs, eps_rel, a_y, a_dydt; };
+struct gsl_odeiv2_evolve_struct { size_t dim; double *y0, *yerr, *dydt_in, *dydt_out; double last_step; unsigned long count, failed_steps; };
+
+gsl_odeiv2_step *gsl_odeiv2_step_alloc(const gsl_odeiv2_step_type *T, size_t dim) {
+  gsl_odeiv2_step *s = calloc(1, sizeof *s);
+  size_t n = dim ? dim : 1;
+  s->type = T; s->dim = dim;
+  for (int i = 0; i < 6; i++) s->k[i] = calloc(n, sizeof(double));
+  s->y0 = calloc(n, sizeof(double)); s->ytmp = calloc(n, sizeof(double)); s->yone = calloc(n, sizeof(double));
+  return s;
+}
+void gsl_odeiv2_step_free(gsl_odeiv2_step *s) {
+  if (!s) return;
+  for (int i = 0; i < 6; i++) free(s->k[i]);
+  free(s->y0); free(s->ytmp); free(s->yone); free(s);
+}
+gsl_odeiv2_control *gsl_odeiv2_control_y_new(double eps_abs, double eps_rel) {
+  gsl_odeiv2_control *c = calloc(1, sizeof *c);
+  c->eps_abs = eps_abs; c->eps_rel = eps_rel; c->a_y = 1.0; c->a_dydt = 0.0; return c;
+}
+void gsl_odeiv2_control_free(gsl_odeiv2_control *c) { free(c); }
+gsl_odeiv2_evolve *gsl_odeiv2_evolve_alloc(size_t dim) {
+  gsl_odeiv2_evolve *e = calloc(1, sizeof *e);
+  size_t n = dim ? dim : 1;
+  e->dim = dim; e->y0 = calloc(n, sizeof(double)); e->yerr = calloc(n, sizeof(double));
+  e->dydt_in = calloc(n, sizeof(double)); e->dydt_out = calloc(n, sizeof(double));
+  return e;
+}
+void gsl_odeiv2_evolve_free(gsl_odeiv2_evolve *e) { if (!e) return; free(e->y0); free(e->yerr); free(e->dydt_in); free(e->dydt_out); free(e); }
+
+#define FEVAL(sys, t, y, f) do { int s_ = (sys)->function((t), (y), (f), (sys)->params); if (s_ != GSL_SUCCESS) return s_; } while (0)
+
+/* Embedded 4(5) pairs share one driver: 6 stages, k1 = dydt_in, propagate the 5th-order solution. */
+typedef struct { double ah[5]; double b[5][5]; double c[6]; double ec[6]; } tableau;
+static const tableau TAB_RKF45 = {
+  {1.0/4.0, 3.0/8.0, 12.0/13.0, 1.0, 1.0/2.0},
+  {{1.0/4.0},
+   {3.0/32.0, 9.0/32.0},
+   {1932.0/2197.0, -7200.0/2197.0, 7296.0/2197.0},
+   {8341.0/4104.0, -32832.0/4104.0, 29440.0/4104.0, -845.0/4104.0},
+   {-6080.0/20520.0, 41040.0/20520.0, -28352.0/20520.0, 9295.0/20520.0, -5643.0/20520.0}},
+  {902880.0/7618050.0, 0.0, 3953664.0/7618050.0, 3855735.0/7618050.0, -1371249.0/7618050.0, 277020.0/7618050.0},
+  {1.0/360.0, 0.0, -128.0/4275.0, -2197.0/75240.0, 1.0/50.0, 2.0/55.0}};
+static const tableau TAB_RKCK = {
+  {1.0/5.0, 3.0/10.0, 3.0/5.0, 1.0, 7.0/8.0},
+  {{1.0/5.0},
+   {3.0/40.0, 9.0/40.0},
+   {0.3, -0.9, 1.2},
+   {-11.0/54.0, 2.5, -70.0/27.0, 35.0/27.0},
+   {1631.0/55296.0, 175.0/512.0, 575.0/13824.0, 44275.0/110592.0, 253.0/4096.0}},
+  {37.0/378.0, 0.0, 250.0/621.0, 125.0/594.0, 0.0, 512.0/1771.0},
+  {37.0/378.0 - 2825.0/27648.0, 0.0, 250.0/621.0 - 18575.0/48384.0, 125.0/594.0 - 13525.0/55296.0,
+   -277.0/14336.0, 512.0/1771.0 - 0.25}};
+
+static int embedded_apply(gsl_odeiv2_step *s, const tableau *T, double t, double h, double y[], double yerr[],
+                          const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
+  const size_t n = s->dim; size_t i; int st, j;
+  double **k = s->k, *y0 = s->y0, *ytmp = s->ytmp;
+  memcpy(y0, y, n * sizeof(double));
+  if (dydt_in) memcpy(k[0], dydt_in, n * sizeof(double)); else FEVAL(sys, t, y, k[0]);
+  for (st = 1; st < 6; st++) {
+    for (i = 0; i < n; i++) {
+      double acc = 0.0;
+      for (j = 0; j < st; j++) acc += T->b[st-1][j] * k[j][i];
+      ytmp[i] = y[i] + h * acc;
+    }
+    FEVAL(sys, t + T->ah[st-1] * h, ytmp, k[st]);
+  }
+  for (i = 0; i < n; i++) {
+    double d = 0.0;
+    for (j = 0; j < 6; j++) if (T->c[j] != 0.0) d += T->c[j] * k[j][i];
+    y[i] += h * d;
+  }
+  if (dydt_out) {
+    int s_ = sys->function(t + h, y, dydt_out, sys->params);
+    if (s_ != GSL_SUCCESS) { memcpy(y, y0, n * sizeof(double)); return s_; }
+  }
+  for (i = 0; i < n; i++) {
+    double e = 0.0;
+    for (j = 0; j < 6; j++) if (T->ec[j] != 0.0) e += T->ec[j] * k[j][i];
+    yerr[i] = h * e;
+  }
+  return GSL_SUCCESS;
+}
+
+/* classic RK4 substep on (y, y0=s->y0, k=s->k[0] holding k1 on entry) */
+static int rk4_substep(gsl_odeiv2_step *s, double y[], double h, double t, const gsl_odeiv2_system *sys) {
+  const size_t n = s->dim; size_t i; double *k = s->k[0], *y0 = s->y0, *ytmp = s->ytmp;
+  for (i = 0; i < n; i++) { y[i] += h / 6.0 * k[i]; ytmp[i] = y0[i] + 0.5 * h * k[i]; }
+  FEVAL(sys, t + 0.5 * h, ytmp, k);
+  for (i = 0; i < n; i++) { y[i] += h / 3.0 * k[i]; ytmp[i] = y0[i] + 0.5 * h * k[i]; }
+  FEVAL(sys, t + 0.5 * h, ytmp, k);
+  for (i = 0; i < n; i++) { y[i] += h / 3.0 * k[i]; ytmp[i] = y0[i] + h * k[i]; }
+  FEVAL(sys, t + h, ytmp, k);
+  for (i = 0; i < n; i++) y[i] += h / 6.0 * k[i];
+  return GSL_SUCCESS;
+}
+/* GSL "rk4": step doubling, 11 RHS evaluations, yerr = 4 (y_two_halves - y_one) / 15 */
+static int rk4_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
+                     const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
+  const size_t n = s->dim; size_t i; int st;
+  double *k = s->k[0], *k1 = s->k[1], *y0 = s->y0, *yone = s->yone, *ysave = s->k[2];
+  memcpy(y0, y, n * sizeof(double)); memcpy(ysave, y, n * sizeof(double));
+  if (dydt_in) memcpy(k, dydt_in, n * sizeof(double)); else FEVAL(sys, t, y0, k);
+  memcpy(k1, k, n * sizeof(double));
+  memcpy(yone, y, n * sizeof(double));
+  if ((st = rk4_substep(s, yone, h, t, sys)) != GSL_SUCCESS) return st;
+  memcpy(k, k1, n * sizeof(double));
+  if ((st = rk4_substep(s, y, h / 2.0, t, sys)) != GSL_SUCCESS) { memcpy(y, ysave, n * sizeof(double)); return st; }
+  { int s_ = sys->function(t + h / 2.0, y, k, sys->params); if (s_ != GSL_SUCCESS) { memcpy(y, ysave, n * sizeof(double)); return s_; } }
+  memcpy(y0, y, n * sizeof(double));
+  if ((st = rk4_substep(s, y, h / 2.0, t + h / 2.0, sys)) != GSL_SUCCESS) { memcpy(y, ysave, n * sizeof(double)); return st; }
+  if (dydt_out) { int s_ = sys->function(t + h, y, dydt_out, sys->params); if (s_ != GSL_SUCCESS) { memcpy(y, ysave, n * sizeof(double)); return s_; } }
+  for (i = 0; i < n; i++) yerr[i] = 4.0 * (y[i] - yone[i]) / 15.0;
+  return GSL_SUCCESS;
+}
+
+static int step_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
+                      const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
+  switch (s->type->kind) {
+    case MG_RKF45: return embedded_apply(s, &TAB_RKF45, t, h, y, yerr, dydt_in, dydt_out, sys);
+    case MG_RKCK:  return embedded_apply(s, &TAB_RKCK, t, h, y, yerr, dydt_in, dydt_out, sys);
+    case MG_RK4:   return rk4_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
+    default:
+      fprintf(stderr, "minigsl: stepper '%s' is not restated (no GSL source offline)\n", s->type->name);
+      abort();
+  }
+}
+
+/* standard control, a_y = 1, a_dydt = 0 (gsl_odeiv2_control_y_new) */
+enum { HADJ_DEC = -1, HADJ_NIL = 0, HADJ_INC = 1 };
+static int hadjust(const gsl_odeiv2_control *c, size_t dim, unsigned ord, const double y[], const double yerr[],
+                   const double yp[], double *h) {
+  const double S = 0.9, h_old = *h; double rmax = DBL_MIN; size_t i;
+  for (i = 0; i < dim; i++) {
+    const double D0 = c->eps_rel * (c->a_y * fabs(y[i]) + c->a_dydt * fabs(h_old * yp[i])) + c->eps_abs;
+    const double r = fabs(yerr[i]) / fabs(D0);
+    rmax = r > rmax ? r : rmax;   /* GSL_MAX_DBL(r, rmax): a NaN r is dropped */
+  }
+  if (rmax > 1.1) {
+    double r = S / pow(rmax, 1.0 / ord);
+    if (r < 0.2) r = 0.2;
+    *h = r * h_old; return HADJ_DEC;
+  } else if (rmax < 0.5) {
+    double r = S / pow(rmax, 1.0 / (ord + 1.0));
+    if (r > 5.0) r = 5.0;
+    if (r < 1.0) r = 1.0;
+    *h = r * h_old; return HADJ_INC;
+  }
+  return HADJ_NIL;
+}
+
+int gsl_odeiv2_evolve_apply(gsl_odeiv2_evolve *e, gsl_odeiv2_control *con, gsl_odeiv2_step *step,
+                            const gsl_odeiv2_system *dydt, double *t, double t1, double *h, double y[]) {
+  const double t0 = *t; double h0 = *h; int step_status, final_step = 0; const double dt = t1 - t0;
+  if (e->dim != step->dim) return GSL_EINVAL;
+  if ((dt < 0.0 && h0 > 0.0) || (dt > 0.0 && h0 < 0.0)) return GSL_EINVAL;
+  memcpy(e->y0, y, e->dim * sizeof(double));
+  if (e->count == 0) { int s_ = dydt->function(t0, y, e->dydt_in, dydt->params); if (s_) return s_; }
+  else memcpy(e->dydt_in, e->dydt_out, e->dim * sizeof(double));
+try_step:
+  if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) { h0 = dt; final_step = 1; } else final_step = 0;
+  step_status = step_apply(step, t0, h0, y, e->yerr, e->dydt_in, e->dydt_out, dydt);
+  if (step_status == GSL_EFAULT || step_status == GSL_EBADFUNC) return step_status;
+  if (step_status != GSL_SUCCESS) {
+    const double h_old = h0; h0 *= 0.5;
+    { volatile double t_curr = *t, t_next = (*t) + h0;
+      if (fabs(h0) < fabs(h_old) && t_next != t_curr) { memcpy(y, e->y0, dydt->dimension * sizeof(double)); e->failed_steps++; goto try_step; }
+      else { *h = h0; *t = t0; return step_status; } }
+  }
+  e->count++; e->last_step = h0;
+  *t = final_step ? t1 : t0 + h0;
+  if (con != NULL) {
+    const double h_old = h0;
+    const int hs = hadjust(con, step->dim, step->type->order, y, e->yerr, e->dydt_out, &h0);
+    if (hs == HADJ_DEC) {
+      volatile double t_curr = *t, t_next = (*t) + h0;
+      if (fabs(h0) < fabs(h_old) && t_next != t_curr) { memcpy(y, e->y0, dydt->dimension * sizeof(double)); e->failed_steps++; goto try_step; }
+      else { *h = h0; return GSL_FAILURE; }
+    }
+  }
+  if (final_step == 0) *h = h0;
+  return step_status;
+}
+
+/* ------------------------------------------------------------------ cheb / sf / pow_int */
+gsl_cheb_series *gsl_cheb_alloc(const size_t order) {
+  gsl_cheb_series *cs = calloc(1, sizeof *cs);
+  cs->order = order; cs->order_sp = order; cs->c = calloc(order + 1, sizeof(double)); cs->f = calloc(order + 1, sizeof(double));
+  return cs;
+}
+void gsl_cheb_free(gsl_cheb_series *cs) { if (!cs) return; free(cs->c); free(cs->f); free(cs); }
+double *gsl_cheb_coeffs(const gsl_cheb_series *cs) { return cs->c; }
+int gsl_cheb_init(gsl_cheb_series *cs, const gsl_function *func, const double a, const double b) {
+  size_t k, j; const double bma = 0.5 * (b - a), bpa = 0.5 * (b + a), fac = 2.0 / (cs->order + 1.0);
+  if (a >= b) return GSL_EDOM;
+  cs->a = a; cs->b = b;
+  for (k = 0; k <= cs->order; k++) { double y = cos(M_PI * (k + 0.5) / (cs->order + 1)); cs->f[k] = GSL_FN_EVAL(func, (y * bma + bpa)); }
+  for (j = 0; j <= cs->order; j++) {
+    double sum = 0.0;
+    for (k = 0; k <= cs->order; k++) sum += cs->f[k] * cos(M_PI * j * (k + 0.5) / (cs->order + 1));
+    cs->c[j] = fac * sum;
+  }
+  return GSL_SUCCESS;
+}
+int gsl_cheb_eval_n_err(const gsl_cheb_series *cs, const size_t order, const double x, double *result, double *abserr) {
+  size_t i; double d1 = 0.0, d2 = 0.0, absc = 0.0;
+  const double y = (2.0 * x - cs->a - cs->b) / (cs->b - cs->a), y2 = 2.0 * y;
+  const size_t eo = order < cs->order ? order : cs->order;
+  for (i = eo; i >= 1; i--) { double temp = d1; d1 = y2 * d1 - d2 + cs->c[i]; d2 = temp; }
+  *result = y * d1 - d2 + 0.5 * cs->c[0];
+  for (i = 0; i <= eo; i++) absc += fabs(cs->c[i]);
+  *abserr = fabs(cs->c[eo]) + absc * GSL_DBL_EPSILON;
+  return GSL_SUCCESS;
+}
+double gsl_sf_choose(unsigned int n, unsigned int m) {
+  double r = 1.0; unsigned int k;
+  if (m > n) return 0.0;
+  if (m > n - m) m = n - m;
+  for (k = 1; k <= m; k++) r = r * (double)(n - m + k) / (double)k;   /* exact for the n <= 51 used by lrexp */
+  return floor(r + 0.5);
+}
+double gsl_pow_int(double x, int n) {
+  double value = 1.0; unsigned int u;
+  if (n < 0) { x = 1.0 / x; u = (unsigned int)(-n); } else u = (unsigned int)n;
+  do { if (u & 1) value *= x; u >>= 1; x *= x; } while (u);
+  return value;
+}
