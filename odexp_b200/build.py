@@ -1,0 +1,64 @@
+"""Build a model library: .pop -> model.cu (cudagen) -> libodx_<name>.so (nvcc, sm_100a) in-tree.
+
+Counterpart of the reference's `compile_model` (src/odexp:1699-1705: gcc model.c -lgsl -lodexp).  The shared object
+holds the generated model, the engine kernels instantiated for it, the C-ABI of include/odx.h and the C host driver
+(csrc/odx_host.c).  Built files live in odexp_b200/_build/ (git-ignored, shipped to the GPU box by gpurun).
+"""
+import hashlib, os, shutil, subprocess
+from . import popfile, cudagen
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+BUILD = os.path.join(HERE, "_build")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177,550,2361", "-shared"]
+
+
+def _digest(text):
+    h = hashlib.sha1(text.encode("utf8"))
+    for f in sorted(os.listdir(CSRC)) + ["../../include/odx.h"]:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p):
+            h.update(open(p, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def lib_path(name):
+    return os.path.join(BUILD, "libodx_%s.so" % name)
+
+
+def build_model(pop_path=None, text=None, name=None, force=False, verbose=False, extra_flags=()):
+    """Generate + compile; returns the path of the shared library.  Raises if nvcc is missing or fails."""
+    if text is None:
+        with open(pop_path, encoding="utf8") as f:
+            text = f.read()
+    if name is None:
+        name = os.path.splitext(os.path.basename(pop_path))[0]
+    model = popfile.parse(text, name=name)
+    cu = cudagen.emit_cuda(model)
+    os.makedirs(BUILD, exist_ok=True)
+    so, cu_path, stamp = lib_path(name), os.path.join(BUILD, "model_%s.cu" % name), os.path.join(BUILD, "model_%s.stamp" % name)
+    dg = _digest(cu + " ".join(extra_flags))
+    if not force and os.path.exists(so) and os.path.exists(stamp) and open(stamp).read().strip() == dg:
+        return so
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        if os.path.exists(so):
+            return so           # prebuilt library shipped with the tree (GPU box without a changed source)
+        raise RuntimeError("nvcc not found and no prebuilt %s" % so)
+    with open(cu_path, "w") as f:
+        f.write(cu)
+    host_o = os.path.join(BUILD, "odx_host_%s.o" % name)
+    subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-Wall", "-I" + INCLUDE, "-c", os.path.join(CSRC, "odx_host.c"), "-o", host_o],
+                   check=True)
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I" + CSRC, "-I" + INCLUDE, cu_path, host_o, "-o", so, "-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for model %s:\n%s" % (name, r.stdout))
+    with open(stamp, "w") as f:
+        f.write(dg)
+    return so

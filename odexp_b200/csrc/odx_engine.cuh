@@ -1,0 +1,477 @@
+/* odx_engine.cuh — B200 (sm_100a) population engine, instantiated once per generated model.
+ *
+ * Included at the end of a generated model.cu, after `struct OdxModel` (per-particle RHS, %M terms,
+ * %C terms, rates, initial conditions as inlinable __host__ __device__ functions with compile-time
+ * dimensions).  Everything here is templated on that struct, so the model code is inlined into the
+ * stage kernels and all column indices are compile-time constants (the reference resolves every
+ * MY()/MU()/... by a run-time strncmp search, src/odexp.h:218-364).
+ *
+ * Data layout (HBM): structure of arrays, FP64, one column per variable, column stride = capacity:
+ *   Y[nvar][cap]   state at the start of the step          (reference: y[] AoS + p->y, methods_odexp.c:290)
+ *   YS[nvar][cap]  current stage state                      (reference: k[] in dde_apply, ytmp in GSL)
+ *   ACC[nvar][cap] running sum of weighted stage slopes     (chain methods: fe, dde)
+ *   KS[7][nvar][cap] stage slopes k1..k6 + dydt_out         (embedded pairs rkf45 / rkck)
+ *   E[nexpr][cap], AUX[naux][cap], PSI[npsi][cap], DEATH[cap], REPLI[cap], ID[cap] (int32)
+ *
+ * One RHS evaluation of the reference (generated pop_rhs, src/odexp:801-858) is
+ *   pass 1 (aux with zeroed mean fields) -> one list walk per %M -> pass 2 (N^2 %C walk + ode_rhs).
+ * Here a mean-field barrier is one grid-wide reduction, so a Runge-Kutta stage s is split at the
+ * barrier: kernel s finishes stage s-1 (k_{s-1} = ode_rhs(y_{s-1}, mfd_{s-1})), forms y_s and
+ * accumulates the %M terms of y_s (warp shuffle + block partials + last-block fixed-order sum).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "odx.h"
+#include "odx_rng.h"
+
+#ifdef ODX_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace odx {
+
+typedef OdxModel M;
+constexpr int NVAR = M::NVAR, NEXPR = M::NEXPR, NAUX = M::NAUX, NPSI = M::NPSI, NMFD = M::NMFD, NPAR = M::NPAR;
+constexpr int A1(int n) { return n > 0 ? n : 1; }      /* array extent that is never zero */
+constexpr int NRED = NMFD + 2;                          /* [%M sums..., %BIRTH sum, sum(death+repli)] */
+constexpr int RED_BIRTH = NMFD, RED_RATES = NMFD + 1;
+constexpr int BLOCK = 256;
+constexpr int MAXSTAGE = 7;
+
+/* ------------------------------------------------------------------------------------------------
+ * evaluation context handed to the generated model code
+ * ---------------------------------------------------------------------------------------------- */
+struct DevCtx {
+  const double *mu;
+  double pop_size;          /* POP_SIZE */
+  double h;                 /* *SIM->h (DWDT = randN(0,1)/sqrt(h), src/odexp.h:384) */
+  PhiloxStream rng;
+  int32_t id, oid;          /* ID / OID */
+  int atbirth, atrepli;     /* ATBIRTH / ATREPLI (src/odexp.h:366-367) */
+  const double *sis_y, *sis_e, *sis_aux;   /* sister particle (valid only during replication ICs) */
+  int has_sister;
+  int stop;                 /* STOPIF */
+  ODX_HD double rand01() { return rng.rand01(); }
+  ODX_HD double randN(double m, double s) { return rng.randN(m, s); }
+  ODX_HD double exprand(double r) { return rng.exprand(r); }
+  ODX_HD long poisson(double l) { return rng.poisson(l); }
+  ODX_HD double dwdt() { return rng.randN(0.0, 1.0) / sqrt(h); }
+};
+
+/* host context for replayed initial conditions: draws through the serial libc stream */
+struct HostCtx {
+  const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli;
+  const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop;
+  ODX_HD double rand01() { return hr->rand01(); }
+  ODX_HD double randN(double m, double s) { return hr->randN(m, s); }
+  ODX_HD double exprand(double r) { return hr->exprand(r); }
+  ODX_HD long poisson(double l) { return hr->poisson(l); }
+  ODX_HD double dwdt() { return hr->randN(0.0, 1.0) / sqrt(h); }
+};
+
+/* device view of the population */
+struct Pop {
+  double *Y, *YS, *ACC, *E, *AUX, *PSI, *DEATH, *REPLI, *KS;
+  int32_t *ID;
+  int64_t stride;           /* column stride = capacity */
+  int64_t n;                /* particles on this GPU */
+  double n_global;          /* POP_SIZE across all GPUs */
+  const double *mu;
+  uint32_t k0, k1;          /* Philox key */
+};
+
+struct Red {                /* grid reduction scratch */
+  double *partial;          /* [grid][NRED] */
+  unsigned int *counter;
+  double *sums;             /* [NRED] raw sums (divided by POP_SIZE by the consumer) */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * helpers
+ * ---------------------------------------------------------------------------------------------- */
+template <int NC>
+__device__ __forceinline__ void load_cols(const double *__restrict__ base, int64_t stride, int64_t i, double (&out)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) out[c] = base[(int64_t)c * stride + i];
+}
+template <int NC>
+__device__ __forceinline__ void store_cols(double *__restrict__ base, int64_t stride, int64_t i, const double (&v)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) base[(int64_t)c * stride + i] = v[c];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* Block-level sum of red[0..NRED) followed by a deterministic grid-level sum: every block writes its
+ * partials, the last block to arrive adds them in a fixed order (independent of arrival order). */
+template <int NR>
+__device__ __forceinline__ void grid_reduce(double (&red)[NR], const Red &r) {
+  __shared__ double s_part[BLOCK / 32][NR];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    const double v = warp_sum(red[k]);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NR) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) v += s_part[w][threadIdx.x];
+    r.partial[(size_t)blockIdx.x * NR + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(r.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) acc[k] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {
+#pragma unroll
+      for (int k = 0; k < NR; k++) acc[k] += __ldcg(&r.partial[(size_t)b * NR + k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; w++) v += s_part[w][threadIdx.x];
+      r.sums[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *r.counter = 0u;
+  }
+}
+
+/* mean fields from raw sums: SIM->meanfield[k] /= POP_SIZE (src/odexp:897) */
+__device__ __forceinline__ void load_mfd(const double *__restrict__ sums, double n_global, double (&mfd)[A1(NMFD)]) {
+#pragma unroll
+  for (int k = 0; k < NMFD; k++) mfd[k] = (sums != nullptr) ? sums[k] / n_global : 0.0;
+}
+
+__device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
+  DevCtx c;
+  c.mu = p.mu; c.pop_size = p.n_global; c.h = h;
+  c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
+  c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0;
+  return c;
+}
+
+/* %M terms of one particle state.  Pass-1 semantics of the reference: when a %M expression reads an
+ * auxiliary variable (MA), that value comes from ode_rhs evaluated with zeroed mean fields and the
+ * previous psi (src/odexp:820-833). */
+__device__ __forceinline__ void particle_terms(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                               const double (&psi)[A1(NPSI)], double (&red)[NRED]) {
+  double aux[A1(NAUX)];
+  if (M::TERMS_USE_AUX) {
+    double f[A1(NVAR)], mz[A1(NMFD)], d = 0.0, r = 0.0;
+#pragma unroll
+    for (int k = 0; k < A1(NMFD); k++) mz[k] = 0.0;
+    DevCtx c1 = c;
+    M::rhs(c1, t, y, e, psi, mz, f, aux, d, r);
+  }
+  double m[A1(NMFD)];
+  if (NMFD > 0) {
+    M::mfd_terms(c, t, y, e, aux, m);
+#pragma unroll
+    for (int k = 0; k < NMFD; k++) red[k] += m[k];
+  }
+  if (M::HAS_BIRTH) red[RED_BIRTH] += M::birth_term(c, t, y, e, aux);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * kernels
+ * ---------------------------------------------------------------------------------------------- */
+/* moments of a state (start of a step when the previous kernel did not provide them) */
+__global__ void __launch_bounds__(BLOCK) k_moments(Pop p, const double *__restrict__ ysrc, double t, Red r) {
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)];
+    load_cols<NVAR>(ysrc, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    if (M::TERMS_USE_AUX) load_cols<NPSI>(p.PSI, p.stride, i, psi);
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, p.ID[i]);
+    particle_terms(c, t, y, e, psi, red);
+  }
+  grid_reduce<NRED>(red, r);
+}
+
+struct ChainArgs {
+  const double *sums_in;    /* raw %M sums of the state the RHS is evaluated at */
+  double t_eval;            /* time of that state */
+  double t_next;            /* time of the state formed by this kernel (for its %M terms) */
+  double h;                 /* step size (DWDT) */
+  double a;                 /* mid: y_s = y0 + a * k         | last: y_new = y0 + a * (acc + w * k) */
+  double w;                 /* weight of k in the accumulator */
+  uint32_t eval_index;      /* RHS evaluation counter (Philox stream) */
+  int want_out;             /* write aux / rates (last step before an output or event) */
+};
+
+/* chain methods (Euler, classic RK4): stage state depends on the previous slope only.
+ * FIRST: the RHS is evaluated at Y itself (k1).  LAST: apply the step to Y and produce the %M sums of the
+ * new state, which are exactly what the first stage of the next step needs. */
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(BLOCK) k_chain(Pop p, ChainArgs a, Red r) {
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] = 0.0;
+  double mfd[A1(NMFD)];
+  load_mfd(a.sums_in, p.n_global, mfd);
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y0[A1(NVAR)], yc[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], acc[A1(NVAR)], f[A1(NVAR)], aux[A1(NAUX)];
+    double death = 0.0, repli = 0.0;
+    load_cols<NVAR>(p.Y, p.stride, i, y0);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
+    if (FIRST) {
+#pragma unroll
+      for (int v = 0; v < NVAR; v++) yc[v] = y0[v];
+    } else {
+      load_cols<NVAR>(p.YS, p.stride, i, yc);
+      load_cols<NVAR>(p.ACC, p.stride, i, acc);
+    }
+    const int32_t id = p.ID[i];
+    DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+    M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+    double yn[A1(NVAR)];
+    if (LAST) {
+#pragma unroll
+      for (int v = 0; v < NVAR; v++) yn[v] = y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
+      store_cols<NVAR>(p.Y, p.stride, i, yn);
+      if (a.want_out) {
+        store_cols<NAUX>(p.AUX, p.stride, i, aux);
+        if (M::HAS_DEATH) p.DEATH[i] = death;
+        if (M::HAS_REPLI) p.REPLI[i] = repli;
+      }
+      red[RED_RATES] += death + repli;
+    } else {
+#pragma unroll
+      for (int v = 0; v < NVAR; v++) {
+        acc[v] = FIRST ? a.w * f[v] : acc[v] + a.w * f[v];
+        yn[v] = y0[v] + a.a * f[v];
+      }
+      store_cols<NVAR>(p.ACC, p.stride, i, acc);
+      store_cols<NVAR>(p.YS, p.stride, i, yn);
+    }
+    if (NMFD > 0 || M::HAS_BIRTH) {
+      DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
+      particle_terms(c2, a.t_next, yn, e, psi, red);
+    }
+  }
+  if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
+}
+
+/* full RHS evaluation with outputs: aux, rates and (optionally) f into fout[nvar][cap] */
+struct RhsArgs { const double *sums_in; double t; double h; uint32_t eval_index; double *fout; };
+__global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restrict__ ysrc, RhsArgs a, Red r) {
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] = 0.0;
+  double mfd[A1(NMFD)];
+  load_mfd(a.sums_in, p.n_global, mfd);
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)];
+    double death = 0.0, repli = 0.0;
+    load_cols<NVAR>(ysrc, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
+    DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, p.ID[i]);
+    M::rhs(c, a.t, y, e, psi, mfd, f, aux, death, repli);
+    store_cols<NAUX>(p.AUX, p.stride, i, aux);
+    if (M::HAS_DEATH) p.DEATH[i] = death;
+    if (M::HAS_REPLI) p.REPLI[i] = repli;
+    if (a.fout) store_cols<NVAR>(a.fout, p.stride, i, f);
+    red[RED_RATES] += death + repli;
+  }
+  if (M::HAS_DEATH || M::HAS_REPLI) grid_reduce<NRED>(red, r);
+}
+
+/* O(N^2) %C coupling: psi_k(i) = (1/POP_SIZE) sum_j expr_k(i,j), j in list order (src/odexp:922-950).
+ * i-particles live in registers (one per thread), j-particles are staged through shared memory in tiles
+ * of TJ and broadcast to the whole block; arithmetic is FP64 on the CUDA cores. */
+constexpr int PAIR_TJ = 256;
+constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);
+__global__ void __launch_bounds__(BLOCK) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
+                                                const double *__restrict__ je, const int32_t *__restrict__ jid,
+                                                int64_t jstride, int64_t nj, double t, double *__restrict__ psi_out) {
+  __shared__ double s_col[A1(PAIR_NCOL)][PAIR_TJ];
+  __shared__ int32_t s_id[PAIR_TJ];
+  for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < p.n; base += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = base + threadIdx.x;
+    const bool live = i < p.n;
+    const int64_t ii = live ? i : p.n - 1;
+    double y[A1(NVAR)], e[A1(NEXPR)], aux[A1(NAUX)], acc[A1(NPSI)];
+    load_cols<NVAR>(ysrc, p.stride, ii, y);
+    load_cols<NEXPR>(p.E, p.stride, ii, e);
+#pragma unroll
+    for (int k = 0; k < A1(NPSI); k++) acc[k] = 0.0;
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, p.ID[ii]);
+    for (int64_t j0 = 0; j0 < nj; j0 += PAIR_TJ) {
+      const int tj = (int)((nj - j0) < PAIR_TJ ? (nj - j0) : PAIR_TJ);
+      __syncthreads();
+      for (int jj = threadIdx.x; jj < tj; jj += BLOCK) {
+#pragma unroll
+        for (int v = 0; v < NVAR; v++) s_col[v][jj] = jy[(int64_t)v * jstride + j0 + jj];
+        if (M::CPL_USES_EXPR) {
+#pragma unroll
+          for (int v = 0; v < NEXPR; v++) s_col[NVAR + v][jj] = je[(int64_t)v * jstride + j0 + jj];
+        }
+        s_id[jj] = jid[j0 + jj];
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int jj = 0; jj < tj; jj++) {
+        double oy[A1(NVAR)], oe[A1(NEXPR)];
+#pragma unroll
+        for (int v = 0; v < NVAR; v++) oy[v] = s_col[v][jj];
+        if (M::CPL_USES_EXPR) {
+#pragma unroll
+          for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
+        }
+        c.oid = s_id[jj];
+        M::cpl_terms(c, t, y, e, aux, oy, oe, aux, acc);
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < NPSI; k++) psi_out[(int64_t)k * p.stride + i] = acc[k] / p.n_global;
+    }
+  }
+}
+
+/* embedded Runge-Kutta pairs (GSL rkf45 / rkck semantics), general tableau with stored slopes.
+ * Kernel for stage s (2..6): k_{s-1} = rhs(y_{s-1}); y_s = y0 + h sum_{j<s} b_{s,j} k_j; %M terms of y_s.
+ * Kernel s = 7 ("final"): k_6; y_new = y0 + h sum c_j k_j (into YS); yerr = h sum ec_j k_j;
+ *   r_i = |yerr_i| / (eps_abs + eps_rel |y_new,i|), grid max -> rmax (gsl_odeiv2_control standard, a_y=1, a_dydt=0). */
+struct TabArgs {
+  const double *sums_in; double t_eval, t_next, h; int s; /* index of the slope computed here, 1-based */
+  double b[6];          /* weights of k_1..k_s for the state formed here */
+  double ec[6];         /* error weights (final only) */
+  double eps_abs, eps_rel; int final_; uint32_t eval_index; unsigned long long *rmax_bits;
+  const double *ycur;   /* state the RHS is evaluated at (Y for s == 1, else YS) */
+  double *K1;           /* slope k_1 (= dydt_in of gsl_odeiv2_evolve_apply); k_2..k_6 live in Pop::KS */
+  int skip_rhs;         /* s == 1 only: k_1 is already in K1 (reused dydt_out of the previous step, or a retry) */
+};
+__device__ __forceinline__ double *slope_ptr(const Pop &p, const TabArgs &a, int j) {   /* j 0-based */
+  return j == 0 ? a.K1 : p.KS + (int64_t)(j - 1) * NVAR * p.stride;
+}
+__global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] = 0.0;
+  double mfd[A1(NMFD)];
+  load_mfd(a.sums_in, p.n_global, mfd);
+  double rloc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y0[A1(NVAR)], yc[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)];
+    double death = 0.0, repli = 0.0;
+    load_cols<NVAR>(p.Y, p.stride, i, y0);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
+    load_cols<NVAR>(a.ycur, p.stride, i, yc);
+    const int32_t id = p.ID[i];
+    if (a.skip_rhs) {
+      load_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
+    } else {
+      DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+      M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+      store_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
+    }
+    double yn[A1(NVAR)];
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) {
+      double sacc = 0.0, eacc = 0.0;
+      for (int j = 0; j < a.s - 1; j++) {
+        const double kj = slope_ptr(p, a, j)[(int64_t)v * p.stride + i];
+        if (a.b[j] != 0.0) sacc += a.b[j] * kj;
+        if (a.final_ && a.ec[j] != 0.0) eacc += a.ec[j] * kj;
+      }
+      if (a.b[a.s - 1] != 0.0) sacc += a.b[a.s - 1] * f[v];
+      yn[v] = y0[v] + a.h * sacc;
+      if (a.final_) {
+        if (a.ec[a.s - 1] != 0.0) eacc += a.ec[a.s - 1] * f[v];
+        const double yerr = a.h * eacc;
+        const double D0 = a.eps_rel * fabs(yn[v]) + a.eps_abs;
+        const double rr = fabs(yerr) / fabs(D0);
+        if (rr > rloc) rloc = rr;          /* GSL_MAX_DBL: a NaN ratio is dropped */
+      }
+    }
+    store_cols<NVAR>(p.YS, p.stride, i, yn);
+    if (NMFD > 0 || M::HAS_BIRTH) {
+      DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
+      particle_terms(c2, a.t_next, yn, e, psi, red);
+    }
+  }
+  if (a.final_) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_down_sync(0xffffffffu, rloc, o); if (other > rloc) rloc = other; }
+    if ((threadIdx.x & 31) == 0) atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(rloc));
+  }
+  if (NMFD > 0 || M::HAS_BIRTH) grid_reduce<NRED>(red, r);
+}
+
+/* AoS <-> SoA transposes for upload / download (host arrays are particle-major like the reference's y[]) */
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int ncol, int64_t n, int64_t stride, int64_t first) {
+  const int64_t total = n * ncol;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / ncol; const int c = (int)(q % ncol);
+    soa[(int64_t)c * stride + first + i] = aos[q];
+  }
+}
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, int ncol, int64_t n, int64_t stride, int64_t first) {
+  const int64_t total = n * ncol;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / ncol; const int c = (int)(q % ncol);
+    aos[q] = soa[(int64_t)c * stride + first + i];
+  }
+}
+__global__ void k_iota_ids(int32_t *id, int64_t n, int32_t first) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) id[i] = first + (int32_t)i;
+}
+/* ode_init_conditions on the device (keyed Philox), particles [first, first+count) */
+__global__ void __launch_bounds__(BLOCK) k_init(Pop p, int64_t first, int64_t count, double t, uint32_t stream, int atbirth) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = first + q;
+    double y[A1(NVAR)], e[A1(NEXPR)];
+    load_cols<NVAR>(p.Y, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    DevCtx c = make_ctx(p, 0.0, stream, DOM_IC, p.ID[i]);
+    c.atbirth = atbirth;
+    M::ic(c, t, y, e);
+    store_cols<NVAR>(p.Y, p.stride, i, y);
+    store_cols<NEXPR>(p.E, p.stride, i, e);
+    if (NPSI > 0) { for (int k = 0; k < NPSI; k++) p.PSI[(int64_t)k * p.stride + i] = 0.0; }
+    if (NAUX > 0) { for (int k = 0; k < NAUX; k++) p.AUX[(int64_t)k * p.stride + i] = 0.0; }
+    p.DEATH[i] = 0.0; p.REPLI[i] = 0.0;
+  }
+}
+
+}  // namespace odx
+
+#include "odx_runtime.cuh"

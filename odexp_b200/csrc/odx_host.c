@@ -1,0 +1,222 @@
+/* odx_host.c — host-side simulation driver in C: the GPU branch of the reference's odesolver().
+ *
+ * Mirrors src/methods_odexp.c:83-763 for `popmode population`: output grid dt = (t1-t0)/(res-1), one loop iteration per
+ * output interval or birth/death event, SSA / tau-leaping choice, stepper dispatch, and the two binary outputs the
+ * reference's UI reads afterwards (.odexp/stats.dat, .odexp/traj.dat; record layouts src/datastruct.c:643-674).
+ * The population itself never leaves the GPU between outputs: this file only talks to the C-ABI of include/odx.h.
+ *
+ * Differences from the reference that are deliberate and documented in DESIGN.md:
+ *   - stopping times inside TIMESPAN (STOP_TSPAN re-initialisation) and STOPIF are not handled here (status ODX_EUNSUP);
+ *   - traj.dat can be thinned (traj_stride) or switched off: at N = 2^24 one frame is 1.2 GB;
+ *   - current.plot (the 3-column quick buffer of the gnuplot UI) is not written.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "odx.h"
+
+static double now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+typedef struct {
+  FILE *fstats, *ftraj;
+  unsigned int nbrsteps;
+  int nmfd, nvar, naux, npsi, nexpr;
+  double *mfd;
+  /* download buffers */
+  double *y, *e, *aux, *psi;
+  int32_t *ids;
+  int64_t bufcap;
+} out_state;
+
+/* fwrite_SIM (src/datastruct.c:643-653): t, meanfield[nmfd], N, stop_flag, event[3] */
+static void write_stats_row(out_state *os, double t, int n, int stop_flag, const int event[3]) {
+  fwrite(&t, sizeof(double), 1, os->fstats);
+  fwrite(os->mfd, sizeof(double), os->nmfd, os->fstats);
+  fwrite(&n, sizeof(int), 1, os->fstats);
+  fwrite(&stop_flag, sizeof(int), 1, os->fstats);
+  fwrite(event, sizeof(int), 3, os->fstats);
+}
+
+static int ensure_buffers(out_state *os, int64_t n) {
+  if (n <= os->bufcap) return 0;
+  int64_t cap = n + n / 4 + 16;
+  free(os->y); free(os->e); free(os->aux); free(os->psi); free(os->ids);
+  os->y = malloc(sizeof(double) * cap * (os->nvar > 0 ? os->nvar : 1));
+  os->e = malloc(sizeof(double) * cap * (os->nexpr > 0 ? os->nexpr : 1));
+  os->aux = malloc(sizeof(double) * cap * (os->naux > 0 ? os->naux : 1));
+  os->psi = malloc(sizeof(double) * cap * (os->npsi > 0 ? os->npsi : 1));
+  os->ids = malloc(sizeof(int32_t) * cap);
+  os->bufcap = cap;
+  return (os->y && os->e && os->aux && os->psi && os->ids) ? 0 : ODX_ENOMEM;
+}
+
+/* fwrite_all_particles (src/datastruct.c:655-674): per particle: step, id, t, y, aux, psi, meanfield, expr */
+static int write_traj_frame(odx_handle *h, out_state *os, double t, int stride) {
+  int64_t n = 0, i;
+  int st;
+  if (!os->ftraj || stride <= 0) { os->nbrsteps++; return 0; }
+  odx_pop_size(h, &n, NULL, NULL);
+  if ((st = ensure_buffers(os, n)) != 0) return st;
+  if ((st = odx_pop_download(h, 0, n, os->y, os->e, os->aux, os->psi, os->ids, NULL, NULL)) != 0) return st;
+  for (i = 0; i < n; i += stride) {
+    fwrite(&os->nbrsteps, sizeof(unsigned int), 1, os->ftraj);
+    fwrite(&os->ids[i], sizeof(int), 1, os->ftraj);
+    fwrite(&t, sizeof(double), 1, os->ftraj);
+    fwrite(os->y + i * os->nvar, sizeof(double), os->nvar, os->ftraj);
+    fwrite(os->aux + i * os->naux, sizeof(double), os->naux, os->ftraj);
+    fwrite(os->psi + i * os->npsi, sizeof(double), os->npsi, os->ftraj);
+    fwrite(os->mfd, sizeof(double), os->nmfd, os->ftraj);
+    fwrite(os->e + i * os->nexpr, sizeof(double), os->nexpr, os->ftraj);
+  }
+  os->nbrsteps++;
+  return 0;
+}
+
+static int cmp_double(const void *a, const void *b) {
+  const double x = *(const double *)a, y = *(const double *)b;
+  return (x > y) - (x < y);
+}
+
+int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *rep) {
+  const odx_model_info *mi = odx_model();
+  const double t_start = now_ms();
+  double tot_solver = 0.0;
+  double t, t1, dt, tnext, dt_ssa, dt_leaping, dt_dyn, dt_next, sum_rates = 0.0, birth_rate = 0.0, expected_dt_ssa;
+  double hstep = o->h0;
+  int status = ODX_SUCCESS, stop_flag, event[3] = {0, 0, 0};
+  int64_t n = 0, steps = 0, i;
+  double particle_steps = 0.0;
+  enum { SSA, TAU_LEAPING } bd_meth = SSA;
+  out_state os;
+  char path[4096];
+  odx_event_row *rows = NULL;
+  int64_t rows_cap = 0, nrows = 0;
+  uint64_t leap_index = 0;
+  (void)cmp_double;
+
+  memset(&os, 0, sizeof os);
+  if (rep) memset(rep, 0, sizeof *rep);
+  if (o->tspan_len < 2 || o->res < 2) return ODX_EINVAL;
+  if (o->tspan_len > 2) return ODX_EUNSUP;        /* stopping times: host-only feature of the reference UI */
+  os.nmfd = mi->nmfd; os.nvar = mi->nvar; os.naux = mi->naux; os.npsi = mi->npsi; os.nexpr = mi->nexpr;
+  os.mfd = calloc(os.nmfd > 0 ? os.nmfd : 1, sizeof(double));
+
+  t = o->tspan[0];
+  t1 = o->tspan[o->tspan_len - 1];
+  stop_flag = ODX_EVENT_T0;
+  dt = (t1 - t) / (double)(o->res - 1);
+
+  snprintf(path, sizeof path, "%s/stats.dat", o->outdir ? o->outdir : ".odexp");
+  if ((os.fstats = fopen(path, "w")) == NULL) { status = ODX_EFAILED; goto done; }
+  if (o->traj_stride > 0) {
+    snprintf(path, sizeof path, "%s/traj.dat", o->outdir ? o->outdir : ".odexp");
+    if ((os.ftraj = fopen(path, "w")) == NULL) { status = ODX_EFAILED; goto done; }
+  }
+
+  if (o->mu && (status = odx_set_params(h, o->mu, mi->npar)) != 0) goto done;
+  if ((status = odx_set_tolerances(h, o->abstol, o->reltol)) != 0) goto done;
+  if ((status = odx_set_seed(h, o->seed)) != 0) goto done;
+  /* population initialisation: par_birth() x popsize, event = {-1, 1, .}, ode_ic (methods_odexp.c:315-337) */
+  if ((status = odx_pop_init(h, o->popsize, t, o->seed, o->replay_ic)) != 0) goto done;
+  /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364) */
+  if ((status = odx_rhs(h, t)) != 0) goto done;
+  if ((status = odx_meanfields(h, os.mfd)) != 0) goto done;
+  odx_pop_size(h, NULL, &n, NULL);
+  for (i = 0; i < o->popsize; i++) {              /* one stats row per initial particle (methods_odexp.c:372-376) */
+    event[0] = -1; event[1] = 1; event[2] = (int)i;
+    write_stats_row(&os, t, (int)n, stop_flag, event);
+  }
+  memset(event, 0, sizeof event);
+  stop_flag = ODX_EVENT_NONE;
+  if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) goto done;
+  if ((status = odx_evolve_reset(h)) != 0) goto done;
+
+  while (t < t1 && n > 0) {
+    double u;
+    dt_dyn = fmin(dt, t1 - t);
+    /* SSA_timestep (methods_odexp.c:1528-1553): always consumes one uniform */
+    if ((status = odx_rates(h, &sum_rates, &birth_rate)) != 0) break;
+    u = odx_draw_uniform(h, o->replay_ic);
+    dt_ssa = log(1 / (1 - u)) / sum_rates;
+    expected_dt_ssa = 1.0 / sum_rates;
+    bd_meth = (expected_dt_ssa > (dt_dyn * o->ssahmin)) ? SSA : TAU_LEAPING;
+    if (bd_meth == SSA) {
+      if (dt_ssa < dt_dyn) { dt_next = dt_ssa; stop_flag = ODX_STOP_BIRTH | ODX_STOP_DEATH | ODX_STOP_REPLI; }
+      else dt_next = dt_dyn;
+    } else {
+      stop_flag = ODX_STOP_BIRTH | ODX_STOP_DEATH | ODX_STOP_REPLI;
+      dt_leaping = fmax(1, o->aleap * (double)n) * expected_dt_ssa;
+      dt_next = fmin(dt_leaping, dt_dyn);
+    }
+    tnext = t + dt_next;
+
+    {
+      const double c0 = now_ms();
+      while (t < tnext) {
+        const int64_t n_step = n;
+        if (o->method == ODX_METH_FE || o->method == ODX_METH_DDE) {
+          const int last = hstep > ((tnext - t) - o->hmin);     /* this step lands on tnext: keep aux / rates */
+          status = (o->method == ODX_METH_FE) ? odx_fe_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last)
+                                              : odx_dde_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last);
+        } else {
+          status = odx_evolve_apply(h, o->method, &t, tnext, &hstep);
+        }
+        if (status != ODX_SUCCESS) { stop_flag = ODX_EVENT_GSL; break; }
+        steps++; particle_steps += (double)n_step;
+        if (hstep < o->hmin) hstep = o->hmin;
+      }
+      if (t >= t1) stop_flag = ODX_EVENT_TFINAL;
+      if (odx_meanfields(h, os.mfd) != 0 && status == 0) status = ODX_ECUDA;
+      write_stats_row(&os, t, (int)n, stop_flag, event);
+      if (status != ODX_SUCCESS && status != ODX_EBADFUNC) break;
+      tot_solver += now_ms() - c0;
+    }
+    if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) break;
+
+    if (stop_flag & (ODX_STOP_BIRTH | ODX_STOP_DEATH | ODX_STOP_REPLI)) {
+      if (bd_meth == SSA) {
+        odx_event_row row;
+        const double uu = odx_draw_uniform(h, o->replay_ic);
+        if ((status = odx_ssa_apply(h, t, uu, &row)) != 0) break;
+        if (row.event[1] != 0) {      /* sum of rates > 0: one event happened, one stats row (methods_odexp.c:1654) */
+          write_stats_row(&os, t, row.n, row.stop_flag, row.event);
+        }
+      } else {
+        if (rows_cap < 3 * n + 1024) {
+          rows_cap = 3 * n + 1024 + (int64_t)(4.0 * birth_rate * dt_next);
+          free(rows);
+          rows = malloc(sizeof(odx_event_row) * rows_cap);
+          if (!rows) { status = ODX_ENOMEM; break; }
+        }
+        if ((status = odx_tauleap_apply(h, t, dt_next, leap_index++, rows, rows_cap, &nrows)) != 0) break;
+        for (i = 0; i < nrows; i++) write_stats_row(&os, t, rows[i].n, rows[i].stop_flag, rows[i].event);
+      }
+      odx_pop_size(h, NULL, &n, NULL);
+      if (n > 0) {
+        if ((status = odx_rhs(h, t)) != 0) break;                 /* methods_odexp.c:687 */
+        if ((status = odx_meanfields(h, os.mfd)) != 0) break;
+      }
+      if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) break;
+      memset(event, 0, sizeof event);
+      odx_evolve_reset(h);                                         /* gsl step / evolve re-allocated: count = 0 */
+    }
+    stop_flag = ODX_EVENT_NONE;
+  }
+  if (status == ODX_SUCCESS) status = odx_sync(h);
+
+done:
+  if (os.fstats) fclose(os.fstats);
+  if (os.ftraj) fclose(os.ftraj);
+  free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids); free(rows);
+  if (rep) {
+    rep->total_ms = now_ms() - t_start; rep->solver_ms = tot_solver; rep->steps = steps; rep->particle_steps = particle_steps;
+    rep->status = status; rep->final_n = n;
+  }
+  return status;
+}

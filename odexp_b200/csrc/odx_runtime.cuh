@@ -1,0 +1,703 @@
+/* odx_runtime.cuh — host side of the engine: device buffers, launch sequencing, and the extern "C"
+ * entry points declared in include/odx.h.  Included by odx_engine.cuh (one instantiation per model). */
+#pragma once
+#include <dlfcn.h>
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#define ODX_HAVE_NCCL_H 1
+#endif
+
+namespace odx {
+
+enum { SLOT_Y0 = 0, SLOT_Y1 = 1, SLOT_STAGE = 2, SLOT_RATES = 10, NSLOT = 11 };
+
+#ifdef ODX_HAVE_NCCL_H
+/* NCCL is bound at run time (dlopen) so that the model library has no link-time dependency and shares the
+ * libnccl.so.2 already loaded by the host process (e.g. the one bundled with torch). */
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString;
+  }
+};
+static NcclApi g_nccl;
+#endif
+
+}  // namespace odx
+
+using namespace odx;
+
+struct odx_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t cap = 0, n = 0;
+  int32_t max_id = 0;
+  double *Y = nullptr, *YS = nullptr, *ACC = nullptr, *E = nullptr, *AUX = nullptr, *PSI = nullptr, *DEATH = nullptr,
+         *REPLI = nullptr, *KS = nullptr, *K1 = nullptr, *DOUT = nullptr;
+  int32_t *ID = nullptr;
+  double *d_mu = nullptr;
+  double h_mu[A1(NPAR)];
+  double *partial = nullptr; unsigned int *counter = nullptr; double *sums = nullptr; unsigned long long *rmax = nullptr;
+  double *h_pin = nullptr;                 /* pinned scratch: NSLOT*NRED doubles + 8 */
+  double *stage_dev = nullptr; size_t stage_bytes = 0;   /* AoS staging for upload / download */
+  double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
+  int sm_count = 148, grid_cap = 148 * 8;
+  uint32_t k0 = 3141592u, k1 = 0u;
+  uint32_t eval_index = 0;
+  int y_slot = SLOT_Y0; bool ymoments_valid = false;
+  int report_slot = SLOT_Y0, rates_slot = SLOT_RATES;
+  double eps_abs = 1e-6, eps_rel = 1e-6;
+  uint64_t ev_count = 0, ev_failed = 0, rhs_evals = 0; bool k1_valid = false;
+  int rank = 0, nranks = 1; double n_global = 0.0; int64_t n_before = 0;   /* particles on lower ranks */
+#ifdef ODX_HAVE_NCCL_H
+  ncclComm_t comm = nullptr;
+#endif
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t launches = 0;
+  HostRand hr; bool hr_seeded = false; uint32_t host_draws = 0;   /* serial stream of the host loop (replay mode) */
+  std::string err;
+};
+
+namespace odx {
+
+#define ODX_CUDA(h, call)                                                                            \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      char b_[512];                                                                                  \
+      snprintf(b_, sizeof b_, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      (h)->err = b_;                                                                                 \
+      return ODX_ECUDA;                                                                              \
+    }                                                                                                \
+  } while (0)
+#define ODX_TRY(expr) do { int s_ = (expr); if (s_ != ODX_SUCCESS) return s_; } while (0)
+
+static inline Pop pop_view(const odx_handle *h) {
+  Pop p;
+  p.Y = h->Y; p.YS = h->YS; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
+  p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
+  return p;
+}
+static inline Red red_view(const odx_handle *h, int slot) {
+  Red r; r.partial = h->partial; r.counter = h->counter; r.sums = h->sums + (size_t)slot * NRED; return r;
+}
+static inline int grid_for(const odx_handle *h, int64_t n) {
+  int64_t g = (n + BLOCK - 1) / BLOCK;
+  if (g < 1) g = 1;
+  if (g > h->grid_cap) g = h->grid_cap;
+  return (int)g;
+}
+constexpr bool NEEDS_MOMENTS = (NMFD > 0) || M::HAS_BIRTH;
+
+/* cross-GPU sum of the raw %M sums (and birth / rate sums): allreduce(SUM) of NRED doubles per RHS evaluation */
+static int post_reduce(odx_handle *h, int slot) {
+  if (h->nranks <= 1) return ODX_SUCCESS;
+#ifdef ODX_HAVE_NCCL_H
+  double *s = h->sums + (size_t)slot * NRED;
+  ncclResult_t r = g_nccl.AllReduce(s, s, NRED, ncclDouble, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  return ODX_SUCCESS;
+#else
+  h->err = "built without nccl.h"; return ODX_ENCCL;
+#endif
+}
+
+static int launch_check(odx_handle *h) {
+  h->launches++;
+  ODX_CUDA(h, cudaGetLastError());
+  return ODX_SUCCESS;
+}
+
+/* psi for the state in ysrc (all-pairs %C).  Multi-GPU: allgather of the coupled columns first. */
+static int compute_psi(odx_handle *h, const double *ysrc, double t) {
+  if (!M::HAS_PAIR) return ODX_SUCCESS;
+  Pop p = pop_view(h);
+  const double *jy = ysrc, *je = h->E; const int32_t *jid = h->ID; int64_t jstride = h->cap, nj = h->n;
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {
+    /* equal shards are required for the gathered layout [rank][col][n] -> handled as nranks j-segments */
+    const int64_t n = h->n; const int ncol = PAIR_NCOL;
+    if (h->gather_cap < n) { h->err = "gather buffer too small"; return ODX_EFAILED; }
+    /* pack local columns contiguously [ncol][n] then allgather -> [rank][ncol][n] */
+    double *sendbuf = h->gather + (size_t)h->nranks * ncol * h->gather_cap;
+    for (int c = 0; c < NVAR; c++)
+      ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)c * n, ysrc + (size_t)c * h->cap, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (M::CPL_USES_EXPR)
+      for (int c = 0; c < NEXPR; c++)
+        ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)(NVAR + c) * n, h->E + (size_t)c * h->cap, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllGather(sendbuf, h->gather, (size_t)ncol * n, ncclDouble, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    r = g_nccl.AllGather(h->ID, h->gather_id, (size_t)n, ncclInt32, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    /* accumulate rank segments in rank order = global list order */
+    ODX_CUDA(h, cudaMemsetAsync(h->PSI, 0, sizeof(double) * A1(NPSI) * h->cap, h->stream));
+    h->err = "multi-GPU %C: segment accumulation not implemented in this build"; return ODX_EUNSUP;
+  }
+#endif
+  k_pair<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, jy, je, jid, jstride, nj, t, h->PSI);
+  return launch_check(h);
+}
+
+static int ensure_moments_Y(odx_handle *h, double t) {
+  if (!NEEDS_MOMENTS || h->ymoments_valid) return ODX_SUCCESS;
+  k_moments<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(pop_view(h), h->Y, t, red_view(h, h->y_slot));
+  ODX_TRY(launch_check(h));
+  ODX_TRY(post_reduce(h, h->y_slot));
+  h->ymoments_valid = true;
+  return ODX_SUCCESS;
+}
+static inline const double *sums_ptr(const odx_handle *h, int slot) { return NEEDS_MOMENTS ? h->sums + (size_t)slot * NRED : nullptr; }
+
+/* generated pop_rhs once, with outputs (reference call sites methods_odexp.c:364, 687, 709) */
+static int eval_rhs_out(odx_handle *h, const double *ysrc, int sums_slot, double t, double hcur, double *fout) {
+  RhsArgs a; a.sums_in = sums_ptr(h, sums_slot); a.t = t; a.h = hcur; a.eval_index = h->eval_index; a.fout = fout;
+  h->eval_index += 2; h->rhs_evals++;
+  k_rhs_out<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(pop_view(h), ysrc, a, red_view(h, SLOT_RATES));
+  ODX_TRY(launch_check(h));
+  if (M::HAS_DEATH || M::HAS_REPLI) ODX_TRY(post_reduce(h, SLOT_RATES));
+  h->report_slot = sums_slot; h->rates_slot = SLOT_RATES;
+  return ODX_SUCCESS;
+}
+
+static int do_rhs(odx_handle *h, double t, double hcur) {
+  if (h->n <= 0) return ODX_SUCCESS;
+  ODX_TRY(ensure_moments_Y(h, t));
+  ODX_TRY(compute_psi(h, h->Y, t));
+  return eval_rhs_out(h, h->Y, h->y_slot, t, hcur, nullptr);
+}
+
+/* one step of a chain method.  nst = 1: Euler (fe_apply); nst = 4: classic RK4 (dde_apply) */
+static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out) {
+  if (h->n <= 0) return ODX_SUCCESS;
+  ODX_TRY(ensure_moments_Y(h, t));
+  const int g = grid_for(h, h->n);
+  Pop p = pop_view(h);
+  const int new_slot = h->y_slot ^ 1;
+  ChainArgs a; a.h = hh; a.want_out = want_out;
+  if (nst == 1) {
+    ODX_TRY(compute_psi(h, h->Y, t));
+    a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + hh; a.a = hh; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
+    ODX_TRY(launch_check(h));
+    h->report_slot = h->y_slot; h->rhs_evals += 1;
+  } else {
+    /* k[i] = y[i] + (*h)/2.0*k1[i]; ...; y[i] += (*h)/6.0*(k1 + 2.0*(k2+k3) + k4)   (methods_odexp.c:1846-1863) */
+    const double half = hh / 2.0;
+    ODX_TRY(compute_psi(h, h->Y, t));
+    a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + half; a.a = half; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    k_chain<true, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 0));
+    ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 0));
+    ODX_TRY(compute_psi(h, h->YS, t + half));
+    a.sums_in = sums_ptr(h, SLOT_STAGE + 0); a.t_eval = t + half; a.t_next = t + half; a.a = half; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 1));
+    ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 1));
+    ODX_TRY(compute_psi(h, h->YS, t + half));
+    a.sums_in = sums_ptr(h, SLOT_STAGE + 1); a.t_eval = t + half; a.t_next = t + hh; a.a = hh; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 2));
+    ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 2));
+    ODX_TRY(compute_psi(h, h->YS, t + hh));
+    a.sums_in = sums_ptr(h, SLOT_STAGE + 2); a.t_eval = t + hh; a.t_next = t + hh; a.a = hh / 6.0; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    k_chain<false, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
+    ODX_TRY(launch_check(h));
+    h->report_slot = SLOT_STAGE + 2; h->rhs_evals += 4;
+  }
+  if (NEEDS_MOMENTS || M::HAS_DEATH || M::HAS_REPLI) ODX_TRY(post_reduce(h, new_slot));
+  h->rates_slot = new_slot;
+  h->y_slot = new_slot; h->ymoments_valid = NEEDS_MOMENTS;
+  h->k1_valid = false;
+  return ODX_SUCCESS;
+}
+
+/* embedded pairs: coefficient tables as published for GSL's rkf45 / rkck steppers */
+struct Tableau { double ah[5]; double b[5][5]; double c[6]; double ec[6]; unsigned order; };
+static const Tableau TAB_RKF45 = {
+    {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0},
+    {{1.0 / 4.0},
+     {3.0 / 32.0, 9.0 / 32.0},
+     {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0},
+     {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0},
+     {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0}},
+    {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0, 277020.0 / 7618050.0},
+    {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0}, 5};
+static const Tableau TAB_RKCK = {
+    {1.0 / 5.0, 3.0 / 10.0, 3.0 / 5.0, 1.0, 7.0 / 8.0},
+    {{1.0 / 5.0},
+     {3.0 / 40.0, 9.0 / 40.0},
+     {0.3, -0.9, 1.2},
+     {-11.0 / 54.0, 2.5, -70.0 / 27.0, 35.0 / 27.0},
+     {1631.0 / 55296.0, 175.0 / 512.0, 575.0 / 13824.0, 44275.0 / 110592.0, 253.0 / 4096.0}},
+    {37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0},
+    {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0, 125.0 / 594.0 - 13525.0 / 55296.0,
+     -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5};
+
+/* one attempted embedded step of size hh from (t, Y): leaves y_new in YS, dydt_out in DOUT, returns rmax */
+static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh, double *rmax_out) {
+  const int g = grid_for(h, h->n);
+  Pop p = pop_view(h);
+  ODX_CUDA(h, cudaMemsetAsync(h->rmax, 0, sizeof(unsigned long long), h->stream));
+  if (!h->k1_valid) {
+    ODX_TRY(ensure_moments_Y(h, t));
+    ODX_TRY(compute_psi(h, h->Y, t));
+  }
+  for (int s = 1; s <= 6; s++) {
+    TabArgs a;
+    memset(&a, 0, sizeof a);
+    a.s = s; a.h = hh; a.K1 = h->K1; a.eps_abs = h->eps_abs; a.eps_rel = h->eps_rel; a.rmax_bits = h->rmax;
+    a.final_ = (s == 6);
+    a.skip_rhs = (s == 1 && h->k1_valid) ? 1 : 0;
+    a.ycur = (s == 1) ? h->Y : h->YS;
+    a.sums_in = sums_ptr(h, s == 1 ? h->y_slot : SLOT_STAGE + (s - 2));
+    a.t_eval = (s == 1) ? t : t + T.ah[s - 2] * hh;
+    a.t_next = (s == 6) ? t + hh : t + T.ah[s - 1] * hh;
+    if (s < 6) { for (int j = 0; j < s; j++) a.b[j] = T.b[s - 1][j]; }
+    else { for (int j = 0; j < 6; j++) { a.b[j] = T.c[j]; a.ec[j] = T.ec[j]; } }
+    a.eval_index = h->eval_index; h->eval_index += 2;
+    if (!a.skip_rhs) h->rhs_evals++;
+    const int out_slot = SLOT_STAGE + (s - 1);
+    k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, out_slot));
+    ODX_TRY(launch_check(h));
+    if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, out_slot));
+    ODX_TRY(compute_psi(h, h->YS, a.t_next));
+  }
+  h->k1_valid = true;   /* K1 now holds f(t, Y) whatever happens to this attempt */
+  /* dydt_out = f(t + h, y_new): also refreshes aux / rates / reported mean fields like every reference RHS call */
+  ODX_TRY(eval_rhs_out(h, h->YS, SLOT_STAGE + 5, t + hh, hh, h->DOUT));
+  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  double rmax; memcpy(&rmax, h->h_pin, sizeof rmax);
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {
+    /* allreduce(MAX) of one double per attempted step: every rank takes the same accept / reject decision */
+    ODX_CUDA(h, cudaMemcpyAsync(h->rmax, &rmax, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllReduce(h->rmax, h->rmax, 1, ncclDouble, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce(MAX): ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(&rmax, h->h_pin, sizeof rmax);
+  }
+#endif
+  *rmax_out = rmax;
+  return ODX_SUCCESS;
+}
+
+static int alloc_cols(odx_handle *h, double **ptr, int ncol) {
+  ODX_CUDA(h, cudaMalloc((void **)ptr, sizeof(double) * (size_t)A1(ncol) * h->cap));
+  ODX_CUDA(h, cudaMemsetAsync(*ptr, 0, sizeof(double) * (size_t)A1(ncol) * h->cap, h->stream));
+  return ODX_SUCCESS;
+}
+static int ensure_stage(odx_handle *h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return ODX_SUCCESS;
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  h->stage_dev = nullptr; h->stage_bytes = 0;
+  ODX_CUDA(h, cudaMalloc((void **)&h->stage_dev, bytes));
+  h->stage_bytes = bytes;
+  return ODX_SUCCESS;
+}
+static void invalidate_state(odx_handle *h) { h->ymoments_valid = false; h->k1_valid = false; h->ev_count = 0; }
+
+static int upload_cols(odx_handle *h, const double *aos, double *soa, int ncol, int64_t n, int64_t first) {
+  if (ncol == 0 || n == 0 || aos == nullptr) return ODX_SUCCESS;
+  const size_t bytes = sizeof(double) * (size_t)ncol * n;
+  ODX_TRY(ensure_stage(h, bytes));
+  ODX_CUDA(h, cudaMemcpyAsync(h->stage_dev, aos, bytes, cudaMemcpyHostToDevice, h->stream));
+  k_aos_to_soa<<<h->sm_count * 4, 256, 0, h->stream>>>(h->stage_dev, soa, ncol, n, h->cap, first);
+  ODX_TRY(launch_check(h));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+static int download_cols(odx_handle *h, const double *soa, double *aos, int ncol, int64_t n, int64_t first) {
+  if (ncol == 0 || n == 0 || aos == nullptr) return ODX_SUCCESS;
+  const size_t bytes = sizeof(double) * (size_t)ncol * n;
+  ODX_TRY(ensure_stage(h, bytes));
+  k_soa_to_aos<<<h->sm_count * 4, 256, 0, h->stream>>>(soa, h->stage_dev, ncol, n, h->cap, first);
+  ODX_TRY(launch_check(h));
+  ODX_CUDA(h, cudaMemcpyAsync(aos, h->stage_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+
+}  // namespace odx
+
+/* =================================================================================================
+ * C ABI
+ * =============================================================================================== */
+extern "C" {
+
+const odx_model_info *odx_model(void) { return &OdxModel::info(); }
+
+const char *odx_last_error(const odx_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int odx_create(odx_handle **out, int device, int64_t capacity) {
+  if (!out || capacity <= 0) return ODX_EINVAL;
+  odx_handle *h = new (std::nothrow) odx_handle();
+  if (!h) return ODX_ENOMEM;
+  *out = h;
+  h->device = device;
+  h->cap = (capacity + 31) / 32 * 32;      /* columns start 256-byte aligned */
+  ODX_CUDA(h, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ODX_CUDA(h, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) { h->err = "this library is built for sm_100a (B200) only"; return ODX_EUNSUP; }
+  h->sm_count = prop.multiProcessorCount;
+  ODX_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  int occ = 1;
+  ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<false, false>, BLOCK, 0));
+  if (occ < 1) occ = 1;
+  h->grid_cap = h->sm_count * occ;
+  ODX_TRY(alloc_cols(h, &h->Y, NVAR)); ODX_TRY(alloc_cols(h, &h->YS, NVAR)); ODX_TRY(alloc_cols(h, &h->ACC, NVAR));
+  ODX_TRY(alloc_cols(h, &h->E, NEXPR)); ODX_TRY(alloc_cols(h, &h->AUX, NAUX)); ODX_TRY(alloc_cols(h, &h->PSI, NPSI));
+  ODX_TRY(alloc_cols(h, &h->DEATH, 1)); ODX_TRY(alloc_cols(h, &h->REPLI, 1));
+  ODX_CUDA(h, cudaMalloc((void **)&h->ID, sizeof(int32_t) * h->cap));
+  ODX_CUDA(h, cudaMalloc((void **)&h->d_mu, sizeof(double) * A1(NPAR)));
+  const odx_model_info *mi = odx_model();
+  for (int k = 0; k < NPAR; k++) h->h_mu[k] = mi->par_defaults[k];
+  ODX_CUDA(h, cudaMemcpyAsync(h->d_mu, h->h_mu, sizeof(double) * A1(NPAR), cudaMemcpyHostToDevice, h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * (h->grid_cap + 8)));
+  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * 4));
+  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * 4, h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->sums, sizeof(double) * NSLOT * NRED));
+  ODX_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * NSLOT * NRED, h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->rmax, sizeof(unsigned long long) * 2));
+  ODX_CUDA(h, cudaMallocHost((void **)&h->h_pin, sizeof(double) * (NSLOT * NRED + 16)));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+
+void odx_destroy(odx_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+#ifdef ODX_HAVE_NCCL_H
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+#endif
+  double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
+                    h->sums, h->stage_dev, h->gather};
+  for (double *b : bufs) if (b) cudaFree(b);
+  if (h->ID) cudaFree(h->ID);
+  if (h->gather_id) cudaFree(h->gather_id);
+  if (h->counter) cudaFree(h->counter);
+  if (h->rmax) cudaFree(h->rmax);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int odx_sync(odx_handle *h) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+
+int odx_set_params(odx_handle *h, const double *mu, int npar) {
+  if (npar != NPAR) { h->err = "odx_set_params: wrong number of parameters"; return ODX_EINVAL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  for (int k = 0; k < NPAR; k++) h->h_mu[k] = mu[k];
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  ODX_CUDA(h, cudaMemcpyAsync(h->d_mu, h->h_mu, sizeof(double) * A1(NPAR), cudaMemcpyHostToDevice, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  invalidate_state(h);
+  return ODX_SUCCESS;
+}
+int odx_set_seed(odx_handle *h, uint64_t seed) { h->k0 = (uint32_t)seed; h->k1 = (uint32_t)(seed >> 32); h->eval_index = 0; return ODX_SUCCESS; }
+int odx_set_tolerances(odx_handle *h, double eps_abs, double eps_rel) { h->eps_abs = eps_abs; h->eps_rel = eps_rel; return ODX_SUCCESS; }
+
+int odx_comm_unique_id(void *uid128) {
+#ifdef ODX_HAVE_NCCL_H
+  if (!g_nccl.load()) return ODX_ENCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ODX_ENCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(uid128, &id, 128);
+  return ODX_SUCCESS;
+#else
+  (void)uid128; return ODX_ENCCL;
+#endif
+}
+int odx_comm_init(odx_handle *h, int rank, int nranks, const void *uid128) {
+  if (nranks <= 1) { h->rank = 0; h->nranks = 1; return ODX_SUCCESS; }
+#ifdef ODX_HAVE_NCCL_H
+  if (!g_nccl.load()) { h->err = "libnccl.so.2 not found"; return ODX_ENCCL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId id; memcpy(&id, uid128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  h->rank = rank; h->nranks = nranks;
+  return ODX_SUCCESS;
+#else
+  (void)rank; (void)uid128; h->err = "built without nccl.h"; return ODX_ENCCL;
+#endif
+}
+
+/* global population size / offsets after any change of the local size (allreduce over ranks) */
+static int refresh_global_n(odx_handle *h) {
+  h->n_global = (double)h->n; h->n_before = 0;
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {
+    /* allgather of the per-rank sizes through a tiny device buffer */
+    double *d = h->sums + (size_t)SLOT_RATES * NRED;   /* scratch, rewritten by the next evaluation */
+    (void)d;
+    unsigned long long *buf = nullptr;
+    ODX_CUDA(h, cudaMalloc((void **)&buf, sizeof(unsigned long long) * (h->nranks + 1)));
+    unsigned long long mine = (unsigned long long)h->n;
+    ODX_CUDA(h, cudaMemcpyAsync(buf + h->nranks, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllGather(buf + h->nranks, buf, 1, ncclUint64, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); cudaFree(buf); return ODX_ENCCL; }
+    std::vector<unsigned long long> all(h->nranks);
+    ODX_CUDA(h, cudaMemcpyAsync(all.data(), buf, sizeof(unsigned long long) * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(buf);
+    double tot = 0; int64_t before = 0;
+    for (int r2 = 0; r2 < h->nranks; r2++) { tot += (double)all[r2]; if (r2 < h->rank) before += (int64_t)all[r2]; }
+    h->n_global = tot; h->n_before = before;
+  }
+#endif
+  return ODX_SUCCESS;
+}
+
+int odx_pop_upload(odx_handle *h, int64_t n, const double *y, const double *expr, const int32_t *ids, int32_t max_id) {
+  if (n < 0 || n > h->cap) { h->err = "odx_pop_upload: n exceeds capacity"; return ODX_EINVAL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  h->n = n;
+  ODX_TRY(upload_cols(h, y, h->Y, NVAR, n, 0));
+  ODX_TRY(upload_cols(h, expr, h->E, NEXPR, n, 0));
+  if (ids) {
+    ODX_CUDA(h, cudaMemcpyAsync(h->ID, ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else if (n > 0) {
+    k_iota_ids<<<h->sm_count * 4, 256, 0, h->stream>>>(h->ID, n, max_id - (int32_t)n);
+    ODX_TRY(launch_check(h));
+  }
+  h->max_id = max_id;
+  ODX_CUDA(h, cudaMemsetAsync(h->PSI, 0, sizeof(double) * A1(NPSI) * h->cap, h->stream));
+  ODX_CUDA(h, cudaMemsetAsync(h->AUX, 0, sizeof(double) * A1(NAUX) * h->cap, h->stream));
+  ODX_CUDA(h, cudaMemsetAsync(h->DEATH, 0, sizeof(double) * h->cap, h->stream));
+  ODX_CUDA(h, cudaMemsetAsync(h->REPLI, 0, sizeof(double) * h->cap, h->stream));
+  invalidate_state(h);
+  return refresh_global_n(h);
+}
+
+int odx_pop_download(odx_handle *h, int64_t first, int64_t count, double *y, double *expr, double *aux, double *psi,
+                     int32_t *ids, double *death_rate, double *repli_rate) {
+  if (first < 0 || count < 0 || first + count > h->n) { h->err = "odx_pop_download: range outside the population"; return ODX_EINVAL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_TRY(download_cols(h, h->Y, y, NVAR, count, first));
+  ODX_TRY(download_cols(h, h->E, expr, NEXPR, count, first));
+  ODX_TRY(download_cols(h, h->AUX, aux, NAUX, count, first));
+  ODX_TRY(download_cols(h, h->PSI, psi, NPSI, count, first));
+  if (ids && count) ODX_CUDA(h, cudaMemcpyAsync(ids, h->ID + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream));
+  if (death_rate && count) ODX_CUDA(h, cudaMemcpyAsync(death_rate, h->DEATH + first, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  if (repli_rate && count) ODX_CUDA(h, cudaMemcpyAsync(repli_rate, h->REPLI + first, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+
+int odx_pop_size(odx_handle *h, int64_t *n_local, int64_t *n_global, int32_t *max_id) {
+  if (n_local) *n_local = h->n;
+  if (n_global) *n_global = (int64_t)h->n_global;
+  if (max_id) *max_id = h->max_id;
+  return ODX_SUCCESS;
+}
+
+int odx_pop_init(odx_handle *h, int64_t n, double t, uint32_t seed, int replay) {
+  if (n < 0 || n > h->cap) { h->err = "odx_pop_init: n exceeds capacity"; return ODX_EINVAL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  const odx_model_info *mi = odx_model(); (void)mi;
+  if (replay) {
+    /* reference order (src/odexp:1045-1069, methods_odexp.c:315-337): srand(seed) (main.c:403), then per particle in
+     * list order the EXPR expressions followed by the INIT expressions, all drawing from the one serial stream */
+    if (h->nranks > 1) { h->err = "replayed initial conditions are single-GPU (serial stream)"; return ODX_EUNSUP; }
+    std::vector<double> y((size_t)A1(NVAR) * n), e((size_t)A1(NEXPR) * n);
+    HostRand &hr = h->hr; hr.seed(seed); h->hr_seeded = true;
+    for (int64_t i = 0; i < n; i++) {
+      HostCtx c; memset(&c, 0, sizeof c);
+      c.mu = h->h_mu; c.pop_size = (double)n; c.h = 0.0; c.hr = &hr; c.id = (int32_t)i; c.oid = (int32_t)i; c.atbirth = 1;
+      double yy[A1(NVAR)], ee[A1(NEXPR)];
+      for (int v = 0; v < A1(NVAR); v++) yy[v] = 0.0;
+      for (int v = 0; v < A1(NEXPR); v++) ee[v] = 0.0;
+      OdxModel::ic(c, t, yy, ee);
+      for (int v = 0; v < NVAR; v++) y[(size_t)i * NVAR + v] = yy[v];
+      for (int v = 0; v < NEXPR; v++) e[(size_t)i * NEXPR + v] = ee[v];
+    }
+    return odx_pop_upload(h, n, y.data(), e.data(), nullptr, (int32_t)n);
+  }
+  h->n = n;
+  ODX_TRY(refresh_global_n(h));
+  h->max_id = (int32_t)h->n_global;
+  h->k0 = seed; h->k1 = 0;
+  if (n > 0) {
+    k_iota_ids<<<h->sm_count * 4, 256, 0, h->stream>>>(h->ID, n, (int32_t)h->n_before);
+    ODX_TRY(launch_check(h));
+    k_init<<<grid_for(h, n), BLOCK, 0, h->stream>>>(pop_view(h), 0, n, t, 0u, 1);
+    ODX_TRY(launch_check(h));
+  }
+  invalidate_state(h);
+  return ODX_SUCCESS;
+}
+
+int odx_event_record(odx_handle *h, int slot) {
+  if (slot < 0 || slot >= 8) return ODX_EINVAL;
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (!h->ev[slot]) ODX_CUDA(h, cudaEventCreate(&h->ev[slot]));
+  ODX_CUDA(h, cudaEventRecord(h->ev[slot], h->stream));
+  return ODX_SUCCESS;
+}
+int odx_event_elapsed_ms(odx_handle *h, int a, int b, double *ms) {
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !h->ev[a] || !h->ev[b]) return ODX_EINVAL;
+  ODX_CUDA(h, cudaEventSynchronize(h->ev[b]));
+  float f = 0.f;
+  ODX_CUDA(h, cudaEventElapsedTime(&f, h->ev[a], h->ev[b]));
+  *ms = (double)f;
+  return ODX_SUCCESS;
+}
+uint64_t odx_launch_count(const odx_handle *h) { return h->launches; }
+
+double odx_draw_uniform(odx_handle *h, int replay) {
+  if (replay) { if (!h->hr_seeded) { h->hr.seed(3141592u); h->hr_seeded = true; } return h->hr.rand01(); }
+  PhiloxStream ps; ps.k0 = h->k0; ps.k1 = h->k1; ps.id = 0xFFFFFFFFu; ps.stream = h->host_draws++; ps.dom = 0x484f5354u; ps.slot = 0;
+  return ps.rand01();
+}
+long odx_draw_poisson(odx_handle *h, double lambda, int replay) {
+  if (replay) { if (!h->hr_seeded) { h->hr.seed(3141592u); h->hr_seeded = true; } return h->hr.poisson(lambda); }
+  PhiloxStream ps; ps.k0 = h->k0; ps.k1 = h->k1; ps.id = 0xFFFFFFFEu; ps.stream = h->host_draws++; ps.dom = 0x484f5354u; ps.slot = 0;
+  return ps.poisson(lambda);
+}
+
+int odx_rhs(odx_handle *h, double t) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  h->ymoments_valid = false;
+  return do_rhs(h, t, 0.0);
+}
+
+int odx_meanfields(odx_handle *h, double *mfd) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->sums, sizeof(double) * NSLOT * NRED, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < NMFD; k++) mfd[k] = h->h_pin[(size_t)h->report_slot * NRED + k] / h->n_global;
+  return ODX_SUCCESS;
+}
+
+int odx_rates(odx_handle *h, double *sum_rates, double *pop_birth_rate) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->sums, sizeof(double) * NSLOT * NRED, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  /* SIM->pop_birth_rate = (sum of %BIRTH over particles) / POP_SIZE  (src/odexp:829-846) */
+  const double birth = M::HAS_BIRTH && h->n_global > 0 ? h->h_pin[(size_t)h->report_slot * NRED + RED_BIRTH] / h->n_global : 0.0;
+  const double rates = (M::HAS_DEATH || M::HAS_REPLI) ? h->h_pin[(size_t)h->rates_slot * NRED + RED_RATES] : 0.0;
+  if (pop_birth_rate) *pop_birth_rate = birth;
+  if (sum_rates) *sum_rates = birth + rates;       /* SSA_timestep: r = pop_birth_rate + sum(death + repli) */
+  return ODX_SUCCESS;
+}
+
+/* fe_apply (src/methods_odexp.c:1790-1814): h is raised / clipped to land on tnext, then reset to h0 */
+int odx_fe_apply(odx_handle *h, double *t, double tnext, double *hstep, double hmin, double h0, int want_outputs) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  const double dt = tnext - *t;
+  if (*hstep > (dt - hmin)) *hstep = dt;
+  ODX_TRY(chain_step(h, 1, *t, *hstep, want_outputs));
+  *t += *hstep;
+  *hstep = h0;
+  return ODX_SUCCESS;
+}
+/* dde_apply (src/methods_odexp.c:1825-1874): classic RK4 with the same clipping / reset of h */
+int odx_dde_apply(odx_handle *h, double *t, double tnext, double *hstep, double hmin, double h0, int want_outputs) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  const double dt = tnext - *t;
+  if (*hstep > (dt - hmin)) *hstep = dt;
+  ODX_TRY(chain_step(h, 4, *t, *hstep, want_outputs));
+  *t += *hstep;
+  *hstep = h0;
+  return ODX_SUCCESS;
+}
+
+int odx_run_fixed(odx_handle *h, int method, double *t, double hstep, int64_t nsteps) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (method != ODX_METH_FE && method != ODX_METH_DDE) { h->err = "odx_run_fixed: fixed-step methods are fe and dde"; return ODX_EINVAL; }
+  for (int64_t s = 0; s < nsteps; s++) {
+    ODX_TRY(chain_step(h, method == ODX_METH_FE ? 1 : 4, *t, hstep, s == nsteps - 1));
+    *t += hstep;
+  }
+  return ODX_SUCCESS;
+}
+
+int odx_evolve_reset(odx_handle *h) { h->ev_count = 0; h->k1_valid = false; return ODX_SUCCESS; }
+int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uint64_t *rhs_evals) {
+  if (count) *count = h->ev_count;
+  if (failed_steps) *failed_steps = h->ev_failed;
+  if (rhs_evals) *rhs_evals = h->rhs_evals;
+  return ODX_SUCCESS;
+}
+
+/* gsl_odeiv2_evolve_apply + standard control (a_y = 1, a_dydt = 0), restated for the resident population.
+ * Behaviour follows GSL's documented driver: reuse dydt_out as the next dydt_in, clip the step to reach t1,
+ * on rmax > 1.1 shrink by max(0.2, 0.9 rmax^(-1/ord)) and retry, on rmax < 0.5 grow by min(5, max(1, 0.9 rmax^(-1/(ord+1)))). */
+int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK) { h->err = "odx_evolve_apply: method must be rkf45 or rkck"; return ODX_EUNSUP; }
+  if (h->n <= 0) { *t = t1; return ODX_SUCCESS; }
+  const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : TAB_RKCK;
+  if (!h->KS) {
+    ODX_TRY(alloc_cols(h, &h->KS, 5 * A1(NVAR))); ODX_TRY(alloc_cols(h, &h->K1, NVAR)); ODX_TRY(alloc_cols(h, &h->DOUT, NVAR));
+  }
+  const double t0 = *t; double h0 = *hstep; const double dt = t1 - t0; int final_step = 0;
+  if ((dt < 0.0 && h0 > 0.0) || (dt > 0.0 && h0 < 0.0)) { h->err = "step direction must match interval direction"; return ODX_EINVAL; }
+  if (h->ev_count == 0) h->k1_valid = false;     /* first call: evaluate dydt_in = f(t0, y) */
+  for (;;) {
+    if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) { h0 = dt; final_step = 1; } else final_step = 0;
+    double rmax = 0.0;
+    ODX_TRY(embedded_attempt(h, T, t0, h0, &rmax));
+    if (rmax < DBL_MIN) rmax = DBL_MIN;
+    const double h_old = h0; const double S = 0.9; int dec = 0;
+    if (rmax > 1.1) {
+      double r = S / pow(rmax, 1.0 / T.order);
+      if (r < 0.2) r = 0.2;
+      h0 = r * h_old; dec = 1;
+    } else if (rmax < 0.5) {
+      double r = S / pow(rmax, 1.0 / (T.order + 1.0));
+      if (r > 5.0) r = 5.0;
+      if (r < 1.0) r = 1.0;
+      h0 = r * h_old;
+    }
+    const double tnew = final_step ? t1 : t0 + h_old;
+    if (dec) {
+      volatile double t_curr = tnew, t_next = tnew + h0;
+      if (fabs(h0) < fabs(h_old) && t_next != t_curr) { h->ev_failed++; continue; }   /* y0 = Y is untouched: retry */
+      *hstep = h0; h->err = "evolve: cannot reach the requested tolerance"; return ODX_FAILURE;
+    }
+    /* accept: y_new (YS) becomes the state, dydt_out becomes the next dydt_in */
+    std::swap(h->Y, h->YS); std::swap(h->K1, h->DOUT);
+    h->ev_count++;
+    *t = tnew;
+    if (!final_step) *hstep = h0;
+    /* moments of the new Y were produced by the final stage kernel (slot STAGE+5) */
+    if (NEEDS_MOMENTS) {
+      ODX_CUDA(h, cudaMemcpyAsync(h->sums + (size_t)h->y_slot * NRED, h->sums + (size_t)(SLOT_STAGE + 5) * NRED, sizeof(double) * NRED,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+      h->ymoments_valid = true; h->report_slot = h->y_slot;
+    }
+    return ODX_SUCCESS;
+  }
+}
+
+int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row);
+int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows);
+
+}  // extern "C"
+
+#include "odx_events.cuh"

@@ -1,0 +1,300 @@
+"""CUDA emitter: PopModel -> model.cu (device + host functions of one population model).
+
+Counterpart of the reference generator's C emitter (`src/odexp`: print_ode_rhs :981-1043, set_population_meanfields
+:874-903, set_population_coupling :905-954, set_population_birth_rate :860-872, print_ode_init_cond :1045-1069,
+print_header_defines :1071-1195).  Instead of a CPU `model.c` whose macros search variable names at run time
+(src/odexp.h:218-364), it emits `struct OdxModel` with compile-time dimensions and fully inlinable
+`__host__ __device__` functions; `odx_engine.cuh` instantiates the stage kernels around it.
+
+Scope rules follow the reference:
+  * inside D/DT, AUX, %DEATH, %REPLI: parameters (unless {impl}/{init}), EXPR, %C, %M, AUX and the dynamical variables
+    are local names; everything else is reached through MU()/MY()/ME()/MA()/MF()/MC().
+  * inside %M, %C, %BIRTH: only the macros exist (MY/ME/MA/MU/MF, OY/OE for the other particle).
+  * inside EXPR / INIT (initial conditions): parameters tagged {init}/{ever}, previously defined EXPR, SY/SE (sister).
+"""
+import re
+from .popfile import PopModel, PopError, IDENT
+
+_C_KEYWORDS = {"double", "int", "float", "long", "return", "if", "else", "for", "while", "const", "static", "void", "char"}
+
+
+def mangle(name: str) -> str:
+    """ASCII-safe identifier (nvcc device code does not take the UTF-8 identifiers gcc accepts)"""
+    out = []
+    for ch in name:
+        out.append(ch if (ch.isascii() and (ch.isalnum() or ch == "_")) else "_u%04x" % ord(ch))
+    s = "".join(out)
+    return s
+
+
+def _mangle_expr(expr: str) -> str:
+    return re.sub(IDENT, lambda m: mangle(m.group(0)), expr)
+
+
+def _find_call(expr, fname, start=0):
+    """yield (begin, end, [args]) for calls fname(...) with balanced parentheses"""
+    pat = re.compile(r"\b%s\s*\(" % re.escape(fname))
+    pos = start
+    while True:
+        m = pat.search(expr, pos)
+        if not m:
+            return
+        i = m.end()
+        depth, args, cur = 1, [], []
+        while i < len(expr) and depth:
+            ch = expr[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            if ch == "," and depth == 1:
+                args.append("".join(cur)); cur = []
+            else:
+                cur.append(ch)
+            i += 1
+        if depth:
+            raise PopError("unbalanced parentheses in '%s'" % expr)
+        args.append("".join(cur))
+        yield m.start(), i + 1, [a.strip() for a in args]
+        pos = i + 1
+
+
+def _pow_peephole(expr: str) -> str:
+    """pow(x, c) with a literal c in {0.5, 1.5, 2, 3} -> multiplications / sqrt (FP64 pow costs ~100 instructions)"""
+    table = {"0.5": "odx_pow05", "1.5": "odx_pow15", "2": "odx_pow2", "2.0": "odx_pow2", "3": "odx_pow3", "3.0": "odx_pow3"}
+    changed = True
+    while changed:
+        changed = False
+        for b, e, args in _find_call(expr, "pow"):
+            if len(args) == 2 and args[1] in table:
+                expr = expr[:b] + "%s(%s)" % (table[args[1]], args[0]) + expr[e:]
+                changed = True
+                break
+    return expr
+
+
+class Emitter:
+    def __init__(self, m: PopModel, fast_pow: bool = True):
+        self.m = m
+        self.fast_pow = fast_pow
+        self.var_idx = {n: i for i, n in enumerate(e.name for e in m.eqs)}
+        self.par_idx = {e.name: i for i, e in enumerate(m.pars)}
+        self.mfd_idx = {e.name: i for i, e in enumerate(m.mfds)}
+        self.psi_idx = {c.name: i for i, c in enumerate(m.cpls)}
+        self.aux_idx = {e.name: i for i, e in enumerate(m.auxs)}
+        self.expr_base = {}
+        k = 0
+        for e in m.exprs:
+            self.expr_base[e.name] = k
+            k += max(1, e.length)
+
+    # ---- macro translation ---------------------------------------------------------------------
+    def _macro(self, kind, name, where):
+        name = name.strip()
+        def need(d, what):
+            if name not in d:
+                raise PopError("%s(%s) in %s: '%s' is not a declared %s" % (kind, name, where, name, what))
+            return d[name]
+        if kind == "MU":
+            return "(odx_c.mu[%d])" % need(self.par_idx, "parameter")
+        if kind == "MF":
+            return "(odx_mfd[%d])" % need(self.mfd_idx, "mean field")
+        if kind == "MC":
+            return "(odx_psi[%d])" % need(self.psi_idx, "coupling")
+        if kind in ("MY", "OY", "SY"):
+            i = need(self.var_idx, "dynamical variable")
+            return {"MY": "(odx_y[%d])", "OY": "(odx_oy[%d])", "SY": "(odx_c.has_sister ? odx_c.sis_y[%d] : 0.0)"}[kind] % i
+        if kind in ("ME", "OE", "SE"):
+            i = need(self.expr_base, "parametric expression")
+            return {"ME": "(odx_e[%d])", "OE": "(odx_oe[%d])", "SE": "(odx_c.has_sister ? odx_c.sis_e[%d] : 0.0)"}[kind] % i
+        if kind in ("MA", "OA", "SA"):
+            i = need(self.aux_idx, "auxiliary variable")
+            return {"MA": "(odx_aux[%d])", "OA": "(odx_oaux[%d])", "SA": "(odx_c.has_sister ? odx_c.sis_aux[%d] : 0.0)"}[kind] % i
+        raise PopError("unknown macro %s" % kind)
+
+    def tr(self, expr: str, where: str) -> str:
+        """translate one model expression to C++"""
+        e = expr.strip().rstrip(";")
+        e = re.sub(r"\b(MU|MF|MC|MY|OY|SY|ME|OE|SE|MA|OA|SA)\(\s*(%s)\s*\)" % IDENT,
+                   lambda mm: self._macro(mm.group(1), mm.group(2), where), e)
+        if re.search(r"\bKY\s*\(", e):
+            raise PopError("KY() ring neighbours are not supported on the device yet (%s)" % where)
+        if re.search(r"\b(delay|interp)\s*\(", e):
+            raise PopError("delay()/interp() history stacks are host-only (%s)" % where)
+        e = re.sub(r"\bDWDT\b", "odx_c.dwdt()", e)
+        e = re.sub(r"\b(rand01|randN|exprand|poisson)\s*\(", lambda mm: "odx_c.%s(" % mm.group(1), e)
+        e = re.sub(r"\bPOP_SIZE\b", "odx_c.pop_size", e)
+        e = re.sub(r"\bATBIRTH\b", "(odx_c.atbirth)", e)
+        e = re.sub(r"\bATREPLI\b", "(odx_c.atrepli)", e)
+        e = re.sub(r"\bISDAUGHTER\b", "(odx_c.has_sister)", e)
+        e = re.sub(r"\bISMOTHER\b", "(!odx_c.has_sister)", e)
+        e = re.sub(r"\bOID\b", "(odx_c.oid)", e)
+        e = re.sub(r"\b(MID|ID)\b", "(odx_c.id)", e)
+        for b, en, args in list(_find_call(e, "BR"))[::-1]:
+            if len(args) == 2:
+                e = e[:b] + "(odx_c.atbirth ? (%s) : (%s))" % (args[0], args[1]) + e[en:]
+        for b, en, args in list(_find_call(e, "STOPIF"))[::-1]:
+            e = e[:b] + "odx_stopif(odx_c, (%s))" % args[0] + e[en:]
+        if self.fast_pow:
+            e = _pow_peephole(e)
+        return _mangle_expr(e)
+
+    def uses(self, exprs, pat):
+        return any(re.search(pat, x or "") for x in exprs)
+
+    # ---- emit ------------------------------------------------------------------------------------
+    def emit(self) -> str:
+        m = self.m
+        pair_cpls = [c for c in m.cpls if c.lowrank is None]
+        lr_cpls = [c for c in m.cpls if c.lowrank is not None]
+        term_exprs = [e.rhs for e in m.mfds] + ([m.birth] if m.birth else [])
+        cpl_exprs = [c.rhs for c in pair_cpls]
+        rhs_exprs = [e.rhs for e in m.auxs] + [e.rhs for e in m.eqs] + [m.death, m.repli]
+        if self.uses(cpl_exprs + term_exprs, r"\b(OA|SA)\("):
+            raise PopError("OA()/SA() inside %M / %C is not supported (needs the pass-1 auxiliary values of other particles)")
+        if self.uses(cpl_exprs, r"\bMA\("):
+            raise PopError("MA() inside %C is not supported yet")
+        if self.uses(term_exprs, r"\b(OY|OE)\("):
+            raise PopError("OY()/OE() are only meaningful inside %C")
+        terms_use_aux = self.uses(term_exprs, r"\bMA\(")
+        cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
+        rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
+        L = []
+        w = L.append
+        w("/* generated by odexp_b200.cudagen from model '%s' — do not edit */" % m.name)
+        w('#include <math.h>\n#include <stdint.h>\n#include "odx.h"\n#include "odx_rng.h"\n#include "odx_model_prelude.cuh"\n')
+        for name, val in m.macros:
+            w("#define %s %s" % (mangle(name), _mangle_expr(val)))
+        w("")
+        for f in m.funs:
+            args = ", ".join("double %s" % mangle(a) for a in f.args)
+            body = _mangle_expr(_pow_peephole(f.body) if self.fast_pow else f.body)
+            w("ODX_HD double %s(%s) { return %s; }" % (mangle(f.name), args, body))
+        w("")
+        w("struct OdxModel {")
+        w("  static constexpr int NVAR = %d, NEXPR = %d, NAUX = %d, NPSI = %d, NMFD = %d, NPAR = %d;" %
+          (m.nvar, m.nexpr, m.naux, m.npsi, m.nmfd, m.npar))
+        w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
+          tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
+        w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s;" %
+          tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr)))
+        w("")
+        # ---- ode_rhs
+        w("  /* per-particle right-hand side: AUX, D/DT, %DEATH, %REPLI (reference: generated ode_rhs) */")
+        w("  template <class C> ODX_HD static void rhs(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli) {")
+        w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e;")
+        for i, p in enumerate(m.pars):
+            if not re.search(r"\b(init|impl)\b", p.attr, flags=re.I):
+                ctype = "double"
+                mt = re.search(r"\b(int|long|double)\b", p.attr)
+                if mt:
+                    ctype = mt.group(1)
+                w("    const %s %s = (%s)odx_c.mu[%d];" % (ctype, mangle(p.name), ctype, i))
+        for e in m.exprs:
+            b = self.expr_base[e.name]
+            if e.length:
+                w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
+                  (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
+            else:
+                w("    const double %s = odx_e[%d];" % (mangle(e.name), b))
+        for e in m.eqs:
+            w("    const double %s = odx_y[%d];" % (mangle(e.name), self.var_idx[e.name]))
+        for c in m.cpls:
+            w("    const double %s = odx_psi[%d];" % (mangle(c.name), self.psi_idx[c.name]))
+        for e in m.mfds:
+            w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
+        for e in m.auxs:
+            w("    const double %s = %s;" % (mangle(e.name), self.tr(e.rhs, "aux " + e.name)))
+        for e in m.eqs:
+            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "d%s/dt" % e.name)))
+        for e in m.auxs:
+            w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
+        if m.death:
+            w("    odx_death = %s;" % self.tr(m.death, "%DEATH"))
+        if m.repli:
+            w("    odx_repli = %s;" % self.tr(m.repli, "%REPLI"))
+        w("  }\n")
+        # ---- %M terms
+        w("  /* per-particle %M expressions (summed over the population, then divided by POP_SIZE) */")
+        w("  template <class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_aux, double *odx_m) {")
+        w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m;")
+        for e in m.mfds:
+            w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.tr(e.rhs, "%M " + e.name)))
+        w("  }\n")
+        w("  template <class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_aux) {")
+        w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c;")
+        w("    return %s;" % (self.tr(m.birth, "%BIRTH") if m.birth else "0.0"))
+        w("  }\n")
+        # ---- %C terms
+        w("  /* pairwise %C expressions: odx_p[k] += expr_k(me, other) */")
+        w("  template <class C> ODX_HD static void cpl_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_aux, const double *odx_oy, const double *odx_oe, const double *odx_oaux, double *odx_p) {")
+        w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_oy; (void)odx_oe; (void)odx_oaux; (void)odx_c; (void)odx_p;")
+        for c in pair_cpls:
+            w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.tr(c.rhs, "%C " + c.name)))
+        w("  }\n")
+        # ---- initial conditions
+        w("  /* ode_init_conditions: EXPR in file order, then INIT in file order (draw order matters for replay) */")
+        w("  template <class C> ODX_HD static void ic(C &odx_c, double t, double *odx_y, double *odx_e) {")
+        w("    (void)t; (void)odx_e;")
+        for i, p in enumerate(m.pars):
+            if re.search(r"\b(init|ever)\b", p.attr, flags=re.I):
+                w("    const double %s = odx_c.mu[%d];" % (mangle(p.name), i))
+        for e in m.exprs:
+            b = self.expr_base[e.name]
+            if e.length:
+                it = mangle(e.iterator)
+                w("    double %s[%d];" % (mangle(e.name), e.start + e.length))
+                w("    for (int %s = %d; %s < %d; %s++) { %s[%s] = %s; odx_e[%d + %s - %d] = %s[%s]; }" %
+                  (it, e.start, it, e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "expr " + e.name), b, it, e.start,
+                   mangle(e.name), it))
+            else:
+                w("    const double %s = %s; odx_e[%d] = %s;" % (mangle(e.name), self.tr(e.rhs, "expr " + e.name), b, mangle(e.name)))
+        for e in m.inits:
+            w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name)))
+        w("  }\n")
+        # ---- low-rank coupling descriptors
+        w("  static constexpr int NLOWRANK = %d;" % len(lr_cpls))
+        for k, c in enumerate(lr_cpls):
+            d = c.lowrank
+            var = d.get("var")
+            if var not in self.var_idx:
+                raise PopError("low-rank coupling %s: var=%s is not a dynamical variable" % (c.name, var))
+            fun = d.get("fun", "sin")
+            rank = int(d.get("rank", "1")) if d["kind"] == "lrwexp" else 0
+            ub = self.expr_base.get(d.get("U", ""), -1) if d["kind"] == "lrwexp" else -1
+            vb = self.expr_base.get(d.get("V", ""), -1) if d["kind"] == "lrwexp" else -1
+            if d["kind"] == "lrwexp" and (ub < 0 or vb < 0):
+                raise PopError("low-rank coupling %s: U/V must name EXPR arrays" % c.name)
+            w("  static constexpr int LR%d_PSI = %d, LR%d_VAR = %d, LR%d_RANK = %d, LR%d_U = %d, LR%d_V = %d;" %
+              (k, self.psi_idx[c.name], k, self.var_idx[var], k, rank, k, ub, k, vb))
+            w("  ODX_HD static double lr%d_fun(double x) { return %s(x); }" % (k, mangle(fun)))
+        w("")
+        # ---- static info
+        def cstr_list(names):
+            return "{" + ", ".join('"%s"' % n.replace('"', "") for n in names) + (", " if names else "") + "nullptr}"
+        w("  static const odx_model_info &info() {")
+        w("    static const char *const vn[] = %s;" % cstr_list(m.flat_names(m.eqs)))
+        w("    static const char *const en[] = %s;" % cstr_list(m.flat_names(m.exprs)))
+        w("    static const char *const an[] = %s;" % cstr_list(m.flat_names(m.auxs)))
+        w("    static const char *const pn[] = %s;" % cstr_list([c.name for c in m.cpls]))
+        w("    static const char *const mn[] = %s;" % cstr_list([e.name for e in m.mfds]))
+        w("    static const char *const qn[] = %s;" % cstr_list([e.name for e in m.pars]))
+        vals = ", ".join(repr(float(p.rhs)) for p in m.pars) or "0.0"
+        w("    static const double pd[] = {%s};" % vals)
+        w('    static const odx_model_info mi = {"%s", NVAR, NEXPR, NAUX, NPSI, NMFD, NPAR, HAS_BIRTH, HAS_DEATH, HAS_REPLI, RHS_RNG,' % m.name)
+        w("                                      HAS_PAIR, HAS_LOWRANK, vn, en, an, pn, mn, qn, pd};")
+        w("    return mi;")
+        w("  }")
+        w("};\n")
+        w('#include "odx_engine.cuh"')
+        return "\n".join(L) + "\n"
+
+
+def emit_cuda(model: PopModel, fast_pow: bool = True) -> str:
+    return Emitter(model, fast_pow).emit()

@@ -1,0 +1,289 @@
+"""Parser for odexp model files (.pop) — the model-file front end of the B200 population integrator.
+
+Written from the language description in the reference's manual (README.md "MODEL FILE" section) and
+the behaviour of its generator `src/odexp` (prescan :311-402, regexes :26-142): keywords are matched
+case-insensitively by prefix (PAR, EXPR, AUX, D<var>/DT, INIT, LET, MACRO, TIMESPAN, OPT, FUN, %M, %C,
+%BIRTH, %DEATH, %REPLI), `#` starts a comment, `{...}` carries attributes, LET constants are substituted
+textually, `;` separates several PAR / OPT entries on one line, a bare `name value` line is a parameter.
+
+Only what the population path needs is accepted; constructs outside it (CONST/DECL arrays, FILE, LAG,
+multi-line FUN bodies with control flow, multi-dimensional iterators) raise PopError with the line.
+"""
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+IDENT = r"[^\W\d][\w]*"            # unicode letters allowed, like the reference's $re_identifier
+
+
+class PopError(ValueError):
+    pass
+
+
+@dataclass
+class Entry:
+    name: str
+    rhs: str
+    attr: str = ""
+    length: int = 0          # 0 = scalar, >0 = 1-D array of that many elements
+    iterator: str = ""       # iterator name of an array entry
+    start: int = 0
+
+
+@dataclass
+class Fun:
+    name: str
+    args: List[str]
+    body: str                # expression (one-liner) — `return` is added by the emitters
+
+
+@dataclass
+class Coupling:
+    name: str
+    rhs: str
+    attr: str = ""
+    lowrank: Optional[Dict[str, str]] = None    # {var, fun, U, V, rank} for lrwexp / {var, fun} for lrexp
+
+
+@dataclass
+class PopModel:
+    name: str
+    pars: List[Entry] = field(default_factory=list)
+    macros: List[Tuple[str, str]] = field(default_factory=list)
+    exprs: List[Entry] = field(default_factory=list)
+    auxs: List[Entry] = field(default_factory=list)
+    eqs: List[Entry] = field(default_factory=list)
+    inits: List[Entry] = field(default_factory=list)
+    mfds: List[Entry] = field(default_factory=list)
+    cpls: List[Coupling] = field(default_factory=list)
+    funs: List[Fun] = field(default_factory=list)
+    birth: Optional[str] = None
+    death: Optional[str] = None
+    repli: Optional[str] = None
+    options: Dict[str, str] = field(default_factory=dict)
+    timespan: List[float] = field(default_factory=list)
+
+    # flattened dimensions (arrays count element-wise, as in the reference's nbr_expr etc.)
+    @staticmethod
+    def _count(entries):
+        return sum(max(1, e.length) for e in entries)
+
+    @property
+    def nvar(self): return self._count(self.eqs)
+    @property
+    def nexpr(self): return self._count(self.exprs)
+    @property
+    def naux(self): return self._count(self.auxs)
+    @property
+    def npsi(self): return len(self.cpls)
+    @property
+    def nmfd(self): return len(self.mfds)
+    @property
+    def npar(self): return len(self.pars)
+
+    def flat_names(self, entries):
+        out = []
+        for e in entries:
+            if e.length:
+                out += ["%s[%d]" % (e.name, e.start + k) for k in range(e.length)]
+            else:
+                out.append(e.name)
+        return out
+
+    def index_of(self, entries, name):
+        """flattened base index of entry `name`"""
+        k = 0
+        for e in entries:
+            if e.name == name:
+                return k
+            k += max(1, e.length)
+        raise KeyError(name)
+
+
+# option abbreviations -> long names (reference src/options.c:6-79), restricted to the ones the path reads
+OPT_ABBREV = {"r": "res", "meth": "solver", "ps": "popsize", "pm": "popmode", "pr": "progress", "ld": "loudness",
+              "rs": "reseed", "p": "particle"}
+OPT_DEFAULTS = {"res": "201", "hmin": "1e-5", "h0": "1e-1", "abstol": "1e-6", "reltol": "1e-6", "solver": "rkck",
+                "lrabstol": "1e-6", "lrreltol": "1e-6", "lrmax": "31", "popmode": "population", "popsize": "1",
+                "ssahmin": "0.0", "aleap": "0.01", "seed": "3141592", "reseed": "1", "init": "0"}
+
+_RE_ARRAY = re.compile(r"^(%s)\s*\[\s*(\w+)\s*=\s*(\d+)\s*:\s*(\d+)\s*\]$" % IDENT)
+
+
+def _strip_comment(line):
+    # '#' starts a comment (model expressions never contain '#')
+    i = line.find("#")
+    return line if i < 0 else line[:i]
+
+
+def _split_attr(s):
+    m = re.search(r"\{(.*?)\}\s*$", s)
+    if m:
+        return s[:m.start()].rstrip(), m.group(1).strip()
+    return s.rstrip(), ""
+
+
+def _name_and_rhs(rest, lineno, raw):
+    """`name[iter=a:b] rhs {attr}` -> Entry"""
+    rest, attr = _split_attr(rest)
+    m = re.match(r"^(%s(?:\s*\[[^\]]*\])?)\s+(.*)$" % IDENT, rest, flags=re.S)
+    if not m:
+        raise PopError("line %d: cannot parse '%s'" % (lineno, raw.strip()))
+    lhs, rhs = m.group(1).replace(" ", ""), m.group(2).strip()
+    ma = _RE_ARRAY.match(lhs)
+    if ma:
+        a, b = int(ma.group(3)), int(ma.group(4))
+        if b <= a:
+            raise PopError("line %d: empty iterator range in '%s'" % (lineno, raw.strip()))
+        return Entry(ma.group(1), rhs, attr, length=b - a, iterator=ma.group(2), start=a)
+    if "[" in lhs:
+        raise PopError("line %d: unsupported index expression '%s'" % (lineno, lhs))
+    return Entry(lhs, rhs, attr)
+
+
+def parse(text: str, name: str = "model") -> PopModel:
+    m = PopModel(name=name)
+    # pass 1: join continuation lines, collect LET constants
+    lines, cont = [], ""
+    for raw in text.splitlines():
+        s = raw.rstrip("\n")
+        if re.search(r"(\\|\.\.\.)\s*$", s) and not s.lstrip().startswith("#"):
+            cont += re.sub(r"(\\|\.\.\.)\s*$", " ", s)
+            continue
+        lines.append(cont + s)
+        cont = ""
+    if cont:
+        lines.append(cont)
+    lets = []
+    for s in lines:
+        f = _strip_comment(s).split()
+        if f and f[0].lower().startswith("let"):
+            if len(f) < 3:
+                raise PopError("LET needs a name and a value: '%s'" % s.strip())
+            lets.append((f[1], " ".join(f[2:])))
+    # pass 2: substitute LETs, split PAR/OPT at ';', dispatch on keyword
+    for lineno, raw in enumerate(lines, 1):
+        s = _strip_comment(raw).strip()
+        if not s:
+            continue
+        if s.lower().startswith("let"):
+            continue
+        for k, v in lets:
+            s = re.sub(r"\b%s\b" % re.escape(k), v, s)
+        if re.match(r"^%s\s+[-+]?[0-9]*\.?[0-9]+([eE][-+]?[0-9]+)?\s*(\{.*\})?$" % IDENT, s) and \
+                not re.match(r"^(par|expr|aux|init|mac|time|opt|fun|lag|cmd|const|decl|file|fi)\w*\s", s, flags=re.I):
+            s = "par " + s                                    # naked parameter
+        kw = s.split()[0]
+        kwl = kw.lower()
+        rest = s[len(kw):].strip()
+        if kwl.startswith("par") or kwl.startswith("opt"):
+            parts = [p.strip() for p in rest.split(";") if p.strip()]
+        else:
+            parts = [rest]
+        for rest in parts:
+            _dispatch(m, kwl, kw, rest, lineno, raw)
+    _validate(m)
+    return m
+
+
+def _dispatch(m, kwl, kw, rest, lineno, raw):
+    if kwl.startswith("par"):
+        e = _name_and_rhs(rest, lineno, raw)
+        if e.length:
+            raise PopError("line %d: array parameters are not supported" % lineno)
+        m.pars.append(e)
+    elif kwl.startswith("expr"):
+        m.exprs.append(_name_and_rhs(rest, lineno, raw))
+    elif kwl.startswith("aux"):
+        e = _name_and_rhs(rest, lineno, raw)
+        if e.length:
+            raise PopError("line %d: array auxiliary variables are not supported yet" % lineno)
+        m.auxs.append(e)
+    elif kwl.startswith("init"):
+        e = _name_and_rhs(rest, lineno, raw)
+        if e.length:
+            raise PopError("line %d: array dynamical variables are not supported yet" % lineno)
+        m.inits.append(e)
+    elif kwl.startswith("mac"):
+        f = rest.split(None, 1)
+        if len(f) != 2:
+            raise PopError("line %d: MACRO needs a name and a value" % lineno)
+        m.macros.append((f[0], f[1].strip()))
+    elif kwl.startswith("time"):
+        try:
+            m.timespan = [float(x) for x in rest.split()]
+        except ValueError:
+            raise PopError("line %d: TIMESPAN must be numeric here (array mini-language is host-only)" % lineno)
+    elif kwl.startswith("opt"):
+        f = rest.split(None, 1)
+        if len(f) != 2:
+            raise PopError("line %d: OPT needs a name and a value" % lineno)
+        m.options[OPT_ABBREV.get(f[0], f[0])] = f[1].strip()
+    elif kwl.startswith("fun"):
+        mm = re.match(r"^(%s)\s*\(([^)]*)\)\s*=\s*(.*?);?\s*$" % IDENT, rest, flags=re.S)
+        if not mm:
+            raise PopError("line %d: only one-line functions `fun f(a,b) = expr` are supported" % lineno)
+        body = mm.group(3).strip()
+        if re.search(r"\b(for|while|if|return)\b", body) or ";" in body:
+            raise PopError("line %d: function bodies with statements are not supported" % lineno)
+        m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body))
+    elif kwl == "%m" or kwl.startswith("%m"):
+        e = _name_and_rhs(rest, lineno, raw)
+        if re.search(r"\b(vect|noloop)\b", e.attr):
+            raise PopError("line %d: %%M {vect} is not supported" % lineno)
+        m.mfds.append(e)
+    elif kwl.startswith("%c"):
+        rest2, attr = _split_attr(rest)
+        f = rest2.split(None, 1)
+        lr = None
+        if re.search(r"\blrw?exp\b", rest2) or re.search(r"\blrw?exp\b", attr):
+            d = dict((k.strip(), v.strip()) for k, v in (kv.split("=") for kv in attr.split(",") if "=" in kv))
+            d["kind"] = "lrwexp" if re.search(r"\blrwexp\b", rest2 + " " + attr) else "lrexp"
+            lr = d
+            m.cpls.append(Coupling(f[0], "", attr, lr))
+        else:
+            if len(f) != 2:
+                raise PopError("line %d: %%C needs a name and an expression" % lineno)
+            m.cpls.append(Coupling(f[0], f[1].strip(), attr, None))
+    elif kwl.startswith("%birth"):
+        m.birth = _split_attr(rest)[0]
+    elif kwl.startswith("%death"):
+        m.death = _split_attr(rest)[0]
+    elif kwl.startswith("%repli"):
+        m.repli = _split_attr(rest)[0]
+    elif kwl.startswith("cmd") or kwl.startswith("end"):
+        return
+    elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):
+        var = re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I).group(1)
+        rhs, attr = _split_attr(rest)
+        rhs = rhs.lstrip("=").strip()
+        m.eqs.append(Entry(var, rhs, attr))
+        mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)
+        if mi:
+            m.inits.append(Entry(var, mi.group(1).strip()))
+    else:
+        mm = re.match(r"^d(%s)/dt\s*=?\s*(.*)$" % IDENT, (kw + " " + rest), flags=re.I | re.S)
+        if mm:
+            rhs, attr = _split_attr(mm.group(2))
+            m.eqs.append(Entry(mm.group(1), rhs.strip(), attr))
+            return
+        raise PopError("line %d: unknown or unsupported keyword '%s' in '%s'" % (lineno, kw, raw.strip()))
+
+
+def _validate(m):
+    if not m.eqs:
+        raise PopError("model has no dynamical variable (d<name>/dt = ...)")
+    dyn = [e.name for e in m.eqs]
+    ini = [e.name for e in m.inits]
+    if dyn != ini:
+        raise PopError("initial conditions must be declared for, and in the order of, the dynamical variables: %s vs %s" % (dyn, ini))
+    for k, v in OPT_DEFAULTS.items():
+        m.options.setdefault(k, v)
+    if not m.timespan:
+        m.timespan = [0.0, 1.0]
+
+
+def parse_file(path: str) -> PopModel:
+    import os
+    with open(path, encoding="utf8") as f:
+        return parse(f.read(), name=os.path.splitext(os.path.basename(path))[0])

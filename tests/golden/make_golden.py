@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Generate the committed golden vectors from the UNCHANGED reference binary (oracle/_ref, built by
+oracle/build_ref.py from /root/reference).  Run in the build container only; the .npz files travel.
+
+    python tests/golden/make_golden.py
+"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refrun  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+KUR = dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1)
+NBD = dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0)
+VDP = dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0)
+
+CASES = {
+    # name: (fixture, opts, timespan, dims)
+    "kuramoto_dde_n64": ("kuramoto", {"meth": "dde", "h0": 0.1, "res": 5, "ps": 64}, (0, 0.8), KUR),
+    "kuramoto_dde_n1000": ("kuramoto", {"meth": "dde", "h0": 0.1, "res": 11, "ps": 1000}, (0, 2.0), KUR),
+    "kuramoto_dde_h003_n257": ("kuramoto", {"meth": "dde", "h0": 0.03, "res": 4, "ps": 257}, (0, 0.5), KUR),  # ragged: h does not divide dt
+    "kuramoto_fe_n100": ("kuramoto", {"meth": "fe", "h0": 0.05, "res": 3, "ps": 100}, (0, 0.5), KUR),
+    "kuramoto_rkck_n200": ("kuramoto", {"meth": "rkck", "res": 6, "ps": 200}, (0, 5.0), KUR),
+    "kuramoto_rkf45_n200": ("kuramoto", {"meth": "rkf45", "res": 6, "ps": 200, "abstol": 1e-9, "reltol": 1e-9}, (0, 5.0), KUR),
+    "nbody_dde_n64": ("nbody", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 64}, (0, 0.4), NBD),
+    "nbody_rkf45_n96": ("nbody", {"meth": "rkf45", "h0": 0.1, "res": 2, "ps": 96, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 0.4), NBD),
+}
+
+
+def main():
+    for name, (fx, opts, ts, dims) in CASES.items():
+        r = refrun.run(fx, opts, timespan=ts, dims=dims)
+        st, tr = r["stats"], r["traj"]
+        last = tr[tr["step"] == tr["step"].max()]
+        first = tr[tr["step"] == 0]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            stats_t=st["t"], stats_mfd=st["mfd"], stats_n=st["n"], stats_flag=st["stop_flag"], stats_event=st["event"],
+                            first_id=first["id"], first_cols=first["cols"], last_id=last["id"], last_cols=last["cols"], last_t=last["t"],
+                            nframes=np.array([tr["step"].max() + 1]),
+                            meta=np.array([repr(dict(fixture=fx, opts=opts, timespan=ts, dims=dims))]))
+        print(name, "stats rows", len(st), "frames", tr["step"].max() + 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+"""CPU-side tests: model-file parser, CUDA emitter, C-ABI export table, libc rand restatement."""
+import ctypes, os, re, subprocess, sys
+import numpy as np
+import pytest
+from conftest import ROOT, fixture_path
+
+
+def test_parse_kuramoto():
+    from odexp_b200 import popfile
+    m = popfile.parse_file(fixture_path("kuramoto"))
+    assert (m.nvar, m.nexpr, m.naux, m.npsi, m.nmfd, m.npar) == (1, 1, 2, 0, 3, 1)
+    assert m.options["solver"] == "rkck" and m.options["popsize"] == "1000" and m.options["res"] == "801"
+    assert m.timespan == [0.0, 160.0]
+    assert [e.name for e in m.mfds] == ["A1", "A2", "OMEGA"]
+
+
+def test_parse_nbody_and_sde():
+    from odexp_b200 import popfile
+    m = popfile.parse_file(fixture_path("nbody"))
+    assert (m.nvar, m.npsi, m.npar) == (6, 3, 1) and len(m.funs) == 2
+    assert "impl" in m.pars[0].attr
+    s = popfile.parse_file(fixture_path("vdp_sde"))
+    assert s.birth == "0.5" and s.death == "MU(d)" and s.repli == "b*(x>0)"
+    assert [p.name for p in s.pars] == ["mu", "sigma", "d", "b"]
+
+
+def test_parse_features():
+    from odexp_b200 import popfile
+    txt = """
+    let R 4
+    a 1.5 {impl}     # naked parameter
+    par b 2; c 3
+    expr U[i=0:R] i*rand01()
+    dx/dt = -a*x {init = 1.0}
+    opt ps 7; meth dde
+    times 0 2
+    """
+    m = popfile.parse(txt)
+    assert [p.name for p in m.pars] == ["a", "b", "c"] and m.exprs[0].length == 4
+    assert m.inits[0].rhs == "1.0" and m.options["popsize"] == "7" and m.options["solver"] == "dde"
+    with pytest.raises(popfile.PopError):
+        popfile.parse("dx/dt = 1\n")           # no initial condition
+    with pytest.raises(popfile.PopError):
+        popfile.parse("const a[3] 1 2 3\ndx/dt=1\ninit x 0\n")
+
+
+def test_emit_translates_macros():
+    from odexp_b200 import popfile, cudagen
+    cu = cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto")))
+    assert "odx_m[0] = sin((odx_y[0]));" in cu and "odx_m[2] = (odx_e[0]);" in cu
+    assert "NVAR = 1, NEXPR = 1, NAUX = 2, NPSI = 0, NMFD = 3" in cu
+    nb = cudagen.emit_cuda(popfile.parse_file(fixture_path("nbody")))
+    assert "odx_pow15(" in nb and "pow(" not in nb.replace("odx_pow", "")
+    sde = cudagen.emit_cuda(popfile.parse_file(fixture_path("vdp_sde")))
+    assert "odx_c.dwdt()" in sde and "odx_c.atbirth" in sde and "HAS_BIRTH = true" in sde
+
+
+def test_emit_rejects_unsupported():
+    from odexp_b200 import popfile, cudagen
+    m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")
+    with pytest.raises(popfile.PopError):
+        cudagen.emit_cuda(m)
+
+
+def test_unicode_identifiers_are_mangled():
+    from odexp_b200 import popfile, cudagen
+    cu = cudagen.emit_cuda(popfile.parse("par ω 1\ndθ/dt = ω\ninit θ 0\n"))
+    assert "ω" not in cu.split("struct OdxModel")[1].split("info()")[0]
+
+
+def test_library_exports_full_abi(model_lib):
+    """the C-ABI library loads without a GPU and exports every symbol include/odx.h declares"""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    hdr = open(os.path.join(ROOT, "include", "odx.h")).read()
+    declared = set(re.findall(r"\b(odx_[a-z0-9_]+)\s*\(", hdr)) - {"odx_handle"}
+    assert declared == set(capi.ABI_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib.lib, s), s
+    assert lib.dims() == dict(nvar=1, nexpr=1, naux=2, npsi=0, nmfd=3)
+
+
+def test_no_gpu_fails_loudly(model_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from odexp_b200 import capi
+    with pytest.raises(capi.OdxError):
+        capi.Population(model_lib("kuramoto"), 128)
+
+
+def test_libc_rand_restatement_matches_this_libc():
+    """oracle/rand_hook.c and csrc/odx_rng.h restate glibc rand(); check against the libc we run on"""
+    libc = ctypes.CDLL("libc.so.6")
+    src = r'''
+    #include <stdio.h>
+    #include "odx_rng.h"
+    int main() { odx::HostRand h; h.seed(3141592u); for (int i = 0; i < 1000; i++) printf("%d\n", h.next()); return 0; }
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(src)
+        subprocess.run(["g++", "-O1", "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), os.path.join(d, "t.cpp"), "-o", os.path.join(d, "t")], check=True)
+        mine = [int(x) for x in subprocess.run([os.path.join(d, "t")], stdout=subprocess.PIPE, check=True).stdout.split()]
+    libc.srand(3141592)
+    ref = [libc.rand() for _ in range(1000)]
+    assert mine == ref
