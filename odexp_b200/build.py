@@ -12,7 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 BUILD = os.path.join(HERE, "_build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "177,550,2361", "-shared"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-fno-gnu-unique", "-Xlinker", "-Bsymbolic", "-diag-suppress", "177,550,2361",
+              "-shared"]
 
 
 def _digest(text):
@@ -51,7 +52,7 @@ def build_model(pop_path=None, text=None, name=None, force=False, verbose=False,
     with open(cu_path, "w") as f:
         f.write(cu)
     host_o = os.path.join(BUILD, "odx_host_%s.o" % name)
-    subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-Wall", "-I" + INCLUDE, "-c", os.path.join(CSRC, "odx_host.c"), "-o", host_o],
+    subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I" + INCLUDE, "-c", os.path.join(CSRC, "odx_host.c"), "-o", host_o],
                    check=True)
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I" + CSRC, "-I" + INCLUDE, cu_path, host_o, "-o", so, "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -9,6 +9,41 @@ ODX_HD double odx_pow15(double x) { return x * sqrt(x); }
 ODX_HD double odx_pow2(double x) { return x * x; }
 ODX_HD double odx_pow3(double x) { return x * x * x; }
 
+/* sin and cos of one argument with a single Cody-Waite range reduction and constant-bank polynomial coefficients
+ * (fdlibm __kernel_sin / __kernel_cos minimax sets on [-pi/4, pi/4], error < 2^-58 before the final rounding).
+ * nvcc does not merge sin(x) and cos(x) of the same x, and each libdevice call re-reduces the argument and loads its
+ * coefficient table through LDG; the emitter therefore hoists every sin(A) / cos(A) pair into one odx_sincos(A).
+ * Outside |x| < 105615 (where three-term reduction stops being exact) it defers to the library. */
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+static void odx_sincos_library(double x, double *sp, double *cp) { sincos(x, sp, cp); }
+ODX_HD void odx_sincos(double x, double *sp, double *cp) {
+  if (!(fabs(x) < 105615.0)) { odx_sincos_library(x, sp, cp); return; }
+  const double q = rint(x * 0.63661977236758134308);
+  const int n = (int)q;
+  double r = fma(-q, 0x1.921fb54442d18p+0, x);
+  r = fma(-q, 0x1.1a62633145c00p-54, r);
+  r = fma(-q, 0x1.b839a252049c0p-104, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double hz = 0.5 * z, w = 1.0 - hz;
+  const double c = w + (((1.0 - w) - hz) + z * (z * pc));
+  const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+  *sp = (n & 2) ? -a : a;
+  *cp = ((n + 1) & 2) ? -b : b;
+}
+
 /* STOPIF(cond): raise the stop flag, value is the condition (src/odexp.h:400-406) */
 template <class C> ODX_HD int odx_stopif(C &c, int cond) { if (cond) c.stop = 1; return cond; }
 

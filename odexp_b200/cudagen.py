@@ -141,6 +141,28 @@ class Emitter:
             e = _pow_peephole(e)
         return _mangle_expr(e)
 
+    def cse(self, e, cache, out):
+        """hoist sin(A) / cos(A) into one odx_sincos(A) per distinct argument (innermost calls first)"""
+        while True:
+            found = None
+            for fn in ("sin", "cos"):
+                for b, en, args in _find_call(e, fn):
+                    if len(args) == 1 and not re.search(r"\b(sin|cos)\s*\(", args[0]):
+                        found = (b, en, fn, args[0])
+                        break
+                if found:
+                    break
+            if not found:
+                return e
+            b, en, fn, arg = found
+            key = re.sub(r"\s+", "", arg)
+            if key not in cache:
+                cache[key] = len(cache)
+                k = cache[key]
+                out("    double odx_sn%d, odx_cs%d; odx_sincos(%s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
+            k = cache[key]
+            e = e[:b] + ("odx_sn%d" % k if fn == "sin" else "odx_cs%d" % k) + e[en:]
+
     def uses(self, exprs, pat):
         return any(re.search(pat, x or "") for x in exprs)
 
@@ -206,24 +228,26 @@ class Emitter:
             w("    const double %s = odx_psi[%d];" % (mangle(c.name), self.psi_idx[c.name]))
         for e in m.mfds:
             w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
+        tc = {}
         for e in m.auxs:
-            w("    const double %s = %s;" % (mangle(e.name), self.tr(e.rhs, "aux " + e.name)))
+            w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w)))
         for e in m.eqs:
-            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "d%s/dt" % e.name)))
+            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w)))
         for e in m.auxs:
             w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
         if m.death:
-            w("    odx_death = %s;" % self.tr(m.death, "%DEATH"))
+            w("    odx_death = %s;" % self.cse(self.tr(m.death, "%DEATH"), tc, w))
         if m.repli:
-            w("    odx_repli = %s;" % self.tr(m.repli, "%REPLI"))
+            w("    odx_repli = %s;" % self.cse(self.tr(m.repli, "%REPLI"), tc, w))
         w("  }\n")
         # ---- %M terms
         w("  /* per-particle %M expressions (summed over the population, then divided by POP_SIZE) */")
         w("  template <class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, double *odx_m) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m;")
+        tc = {}
         for e in m.mfds:
-            w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.tr(e.rhs, "%M " + e.name)))
+            w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w)))
         w("  }\n")
         w("  template <class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux) {")
@@ -235,8 +259,9 @@ class Emitter:
         w("  template <class C> ODX_HD static void cpl_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, const double *odx_oy, const double *odx_oe, const double *odx_oaux, double *odx_p) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_oy; (void)odx_oe; (void)odx_oaux; (void)odx_c; (void)odx_p;")
+        tc = {}
         for c in pair_cpls:
-            w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.tr(c.rhs, "%C " + c.name)))
+            w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.cse(self.tr(c.rhs, "%C " + c.name), tc, w)))
         w("  }\n")
         # ---- initial conditions
         w("  /* ode_init_conditions: EXPR in file order, then INIT in file order (draw order matters for replay) */")

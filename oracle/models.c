@@ -1,0 +1,85 @@
+/* TEST INFRASTRUCTURE — the fixture models of oracle/fixtures/ (.pop files) written out by hand as plain C, the way the
+ * reference's generator lays out ode_rhs / %M / %C / ode_init_conditions (src/odexp:981-1069, 874-954; a concrete
+ * instance is quoted in SURVEY.md Appendix B).  Hand-written on purpose: the oracle must not share the product's
+ * code generator. */
+#include <math.h>
+#include <string.h>
+#include "odx_oracle.h"
+
+/* ---------------------------------------------------------------- kuramoto.pop */
+#define KPI 3.141592
+static const double kur_pars[] = {0.1};
+static void kur_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                    double *aux, double *death, double *repli) {
+  const double K = c->mu[0], omega = e[0], theta = y_[0], A1 = mfd[0], A2 = mfd[1];
+  const double y = sin(theta);
+  const double coupling = (A1 * cos(theta) - A2 * sin(theta));
+  (void)t; (void)psi; (void)death; (void)repli;
+  f[0] = omega + K * coupling;
+  aux[0] = y; aux[1] = coupling;
+}
+static double kur_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)aux; (void)mfd;
+  return k == 0 ? sin(y[0]) : (k == 1 ? cos(y[0]) : e[0]);
+}
+static void kur_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = orc_randN(c, 2 * KPI / 10.0, 0.1);
+  y[0] = 2 * KPI * orc_rand01(c);
+}
+
+/* ---------------------------------------------------------------- nbody.pop */
+#define NB_G 6.674e-11
+static const double nb_pars[] = {1e+09};
+static double normCube(double x, double y, double z) { return pow(x * x + y * y + z * z, 1.5); }
+static double grav(double numx, double numxi, double x, double y, double z, double xi, double yi, double zi) {
+  return (numx == numxi) ? 0.0 : (numx - numxi) / normCube(x - xi, y - yi, z - zi);
+}
+static void nb_rhs(orc_ctx *c, double t, const double *y, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  (void)c; (void)t; (void)e; (void)mfd; (void)aux; (void)death; (void)repli;
+  f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+  f[3] = psi[0]; f[4] = psi[1]; f[5] = psi[2];
+}
+static void nb_cpl(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi) {
+  const double mass = c->mu[0];
+  (void)e; (void)oe;
+  psi[0] += -NB_G * mass * grav(y[0], oy[0], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+  psi[1] += -NB_G * mass * grav(y[1], oy[1], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+  psi[2] += -NB_G * mass * grav(y[2], oy[2], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+}
+static void nb_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t; (void)e;
+  y[0] = orc_rand01(c); y[1] = orc_rand01(c); y[2] = orc_rand01(c);
+  y[3] = 0.0; y[4] = 0.0; y[5] = 0.0;
+}
+
+/* ---------------------------------------------------------------- vdp_sde.pop */
+static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
+static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                    double *aux, double *death, double *repli) {
+  const double mu = c->mu[0], sigma = c->mu[1], b = c->mu[3];      /* d is {impl}: reached through MU(d) only */
+  const double y = y_[0], x = y_[1];
+  (void)t; (void)e; (void)psi; (void)mfd; (void)aux;
+  f[0] = mu * ((1 - x * x) * y - x) + sigma * orc_dwdt(c);
+  f[1] = y;
+  *death = c->mu[2];
+  *repli = b * (x > 0);
+}
+static double vdp_birth(orc_ctx *c, const double *y, const double *e, const double *aux) { (void)c; (void)y; (void)e; (void)aux; return 0.5; }
+static void vdp_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t; (void)e;
+  y[0] = 0.0;
+  y[1] = c->atbirth ? 2.0 : (c->sister == NULL ? 0.0 : c->sister->y[1]);      /* BR(2.0, SY(x)) */
+}
+
+static const orc_model MODELS[] = {
+  {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic},
+  {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic},
+  {"vdp_sde", 2, 0, 0, 0, 0, 4, vdp_pars, vdp_rhs, NULL, vdp_birth, NULL, vdp_ic},
+};
+const orc_model *orc_find_model(const char *name) {
+  unsigned i;
+  for (i = 0; i < sizeof MODELS / sizeof MODELS[0]; i++) if (strcmp(MODELS[i].name, name) == 0) return &MODELS[i];
+  return NULL;
+}

@@ -105,3 +105,10 @@ def test_libc_rand_restatement_matches_this_libc():
     libc.srand(3141592)
     ref = [libc.rand() for _ in range(1000)]
     assert mine == ref
+
+
+def test_two_model_libraries_coexist(model_lib):
+    """regression: inline statics / same-named symbols of two model libraries must not be merged by the loader"""
+    a, b = model_lib("kuramoto"), model_lib("nbody")
+    assert a.name == "kuramoto" and b.name == "nbody"
+    assert (a.nvar, a.nmfd, a.npsi) == (1, 3, 0) and (b.nvar, b.nmfd, b.npsi) == (6, 0, 3)
