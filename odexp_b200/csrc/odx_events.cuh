@@ -1,10 +1,463 @@
-/* odx_events.cuh — stochastic birth / death on the resident population (SSA single event, tau-leaping). */
+/* odx_events.cuh — stochastic birth / death on the resident SoA population.
+ *
+ * Reference behaviour restated for a parallel machine (src/methods_odexp.c:1556-1762, src/datastruct.c:416-563):
+ *
+ *  tau-leaping  one sweep over the list in order.  Per particle: u1 < death*dt flags DEATH, u2 < repli*dt flags REPLI;
+ *               as coded in the reference ANY flag draws u3, u3 < death/(death+repli) kills the particle, otherwise the
+ *               particle is cloned (daughter appended at the end of the list, copying state and rates, new id = max_id++,
+ *               initial conditions run on the mother then on the daughter with the mother as `sister`) and THEN the mother
+ *               is deleted.  Daughters appended during the sweep are visited later in the same sweep.  Finally
+ *               poisson(birth_rate*dt) de-novo births are appended.  Every event writes one stats row.
+ *               Here: one flag kernel + exclusive scan + spawn kernel per generation of daughters, then a stable
+ *               prefix-scan compaction that preserves list order, ids by exclusive scan on max_id, and the event rows
+ *               reconstructed in sweep order from two more scans.  Draws are keyed Philox: (particle id, slot 0..2,
+ *               stream = event index, domain LEAP), so the outcome does not depend on the traversal.
+ *  SSA          one event per call.  The normalised cumulative sum over [death_0..N-1, repli_0..N-1, birth] and the linear
+ *               search `while (u > r[k]) k++` are done on the host from the downloaded rate columns, in the reference's
+ *               summation order, so the chosen event is identical to the reference for the same u; the list edit
+ *               (delete / clone / append, initial conditions) runs on the device.
+ */
 #pragma once
+
+namespace odx {
+
+constexpr int SCAN_ITEMS = 4;                      /* items per thread */
+constexpr int SCAN_TILE = BLOCK * SCAN_ITEMS;      /* items per block */
+enum { OUT_NONE = 0, OUT_DIE = 1, OUT_REPL_DIE = 2, OUT_REPL_KEEP = 3 };
+
+/* ---- three-phase exclusive scan of NCH interleaved int32 channels ----------------------------------------------- */
+template <int NCH>
+__global__ void __launch_bounds__(BLOCK) k_scan_tiles(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                       int32_t *__restrict__ tile_tot, int64_t n) {
+  __shared__ int32_t s_warp[BLOCK / 32][NCH];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t v[SCAN_ITEMS][NCH], tsum[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) tsum[c] = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) { v[k][c] = (base + k < n) ? in[(base + k) * NCH + c] : 0; tsum[c] += v[k][c]; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t incl[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    int32_t x = tsum[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    incl[c] = x;
+    if (lane == 31) s_warp[warp][c] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    int32_t woff = 0;
+    for (int w2 = 0; w2 < warp; w2++) woff += s_warp[w2][c];
+    int32_t run = woff + incl[c] - tsum[c];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[(base + k) * NCH + c] = run; run += v[k][c]; }
+    if (threadIdx.x == BLOCK - 1) tile_tot[(int64_t)blockIdx.x * NCH + c] = woff + incl[c];
+  }
+}
+template <int NCH>
+__global__ void __launch_bounds__(BLOCK) k_scan_totals(int32_t *tile_tot, int ntiles, int32_t *grand) {
+  /* one block: exclusive scan of the tile totals in place, grand totals to grand[NCH] */
+  __shared__ int32_t s_warp[BLOCK / 32][NCH];
+  __shared__ int32_t s_carry[NCH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < NCH) s_carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < ntiles; b0 += BLOCK) {
+    const int i = b0 + threadIdx.x;
+    int32_t mine[NCH], incl[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      mine[c] = (i < ntiles) ? tile_tot[(int64_t)i * NCH + c] : 0;
+      int32_t x = mine[c];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      incl[c] = x;
+      if (lane == 31) s_warp[warp][c] = x;
+    }
+    __syncthreads();
+    int32_t tot[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      int32_t woff = 0, all = 0;
+      for (int w2 = 0; w2 < BLOCK / 32; w2++) { if (w2 < warp) woff += s_warp[w2][c]; all += s_warp[w2][c]; }
+      if (i < ntiles) tile_tot[(int64_t)i * NCH + c] = s_carry[c] + woff + incl[c] - mine[c];
+      tot[c] = all;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) s_carry[c] += tot[c];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < NCH) grand[threadIdx.x] = s_carry[threadIdx.x];
+}
+template <int NCH>
+__global__ void __launch_bounds__(BLOCK) k_scan_add(int32_t *__restrict__ out, const int32_t *__restrict__ tile_off, int64_t n) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) out[(base + k) * NCH + c] += tile_off[(int64_t)blockIdx.x * NCH + c];
+    }
+  }
+}
+
+/* ---- tau-leap kernels ----------------------------------------------------------------------------------------- */
+/* per-particle outcome for particles [first, first+count); flags3[i] = {replicates, rows, dies} for the scans */
+__global__ void __launch_bounds__(BLOCK) k_leap_flags(Pop p, int64_t first, int64_t count, double dt, uint32_t stream,
+                                                       int32_t *__restrict__ outcome, int32_t *__restrict__ repl_flag) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = first + q;
+    const double death = p.DEATH[i], repli = p.REPLI[i];
+    PhiloxStream rng; rng.k0 = p.k0; rng.k1 = p.k1; rng.id = (uint32_t)p.ID[i]; rng.stream = stream; rng.dom = DOM_LEAP; rng.slot = 0;
+    const double u1 = rng.rand01(), u2 = rng.rand01();
+    int o = OUT_NONE;
+    if ((u1 < death * dt) || (u2 < repli * dt)) {
+      const double u3 = rng.rand01();
+      o = (u3 < death / (death + repli)) ? OUT_DIE : OUT_REPL_DIE;
+    }
+    outcome[i] = o;
+    repl_flag[q] = (o == OUT_REPL_DIE) ? 1 : 0;
+  }
+}
+
+/* clone + initial conditions for every replicating particle of [first, first+count): daughter slot = dst0 + off,
+ * daughter id = id0 + off.  keep_mother: SSA replication (the mother stays, with her initial conditions re-run). */
+__global__ void __launch_bounds__(BLOCK) k_spawn(Pop p, int64_t first, int64_t count, const int32_t *__restrict__ outcome,
+                                                  const int32_t *__restrict__ off, int64_t dst0, int32_t id0, double t, uint32_t stream,
+                                                  int32_t *__restrict__ child_id) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = first + q;
+    const int o = outcome[i];
+    if (o != OUT_REPL_DIE && o != OUT_REPL_KEEP) continue;
+    const int64_t j = dst0 + off[q];
+    const int32_t cid = id0 + off[q], mid = p.ID[i];
+    double my[A1(NVAR)], me[A1(NEXPR)], maux[A1(NAUX)], dy[A1(NVAR)], de[A1(NEXPR)];
+    load_cols<NVAR>(p.Y, p.stride, i, my);
+    load_cols<NEXPR>(p.E, p.stride, i, me);
+    load_cols<NAUX>(p.AUX, p.stride, i, maux);
+#pragma unroll
+    for (int v = 0; v < A1(NVAR); v++) dy[v] = my[v];
+#pragma unroll
+    for (int v = 0; v < A1(NEXPR); v++) de[v] = me[v];
+    /* mother first (sister == NULL), then the daughter with the mother as sister */
+    DevCtx cm = make_ctx(p, 0.0, stream, DOM_IC + 1, mid);
+    cm.atbirth = 0; cm.atrepli = 1; cm.has_sister = 0;
+    M::ic(cm, t, my, me);
+    DevCtx cd = make_ctx(p, 0.0, stream, DOM_IC + 2, cid);
+    cd.atbirth = 0; cd.atrepli = 1; cd.has_sister = 1; cd.sis_y = my; cd.sis_e = me; cd.sis_aux = maux;
+    M::ic(cd, t, dy, de);
+    store_cols<NVAR>(p.Y, p.stride, j, dy);
+    store_cols<NEXPR>(p.E, p.stride, j, de);
+    store_cols<NAUX>(p.AUX, p.stride, j, maux);
+    if (NPSI > 0) { double ps[A1(NPSI)]; load_cols<NPSI>(p.PSI, p.stride, i, ps); store_cols<NPSI>(p.PSI, p.stride, j, ps); }
+    p.DEATH[j] = p.DEATH[i]; p.REPLI[j] = p.REPLI[i];
+    p.ID[j] = cid;
+    child_id[i] = cid;
+    if (o == OUT_REPL_KEEP) { store_cols<NVAR>(p.Y, p.stride, i, my); store_cols<NEXPR>(p.E, p.stride, i, me); }
+  }
+}
+
+/* de-novo births: slots [dst0, dst0+count), ids id0.. ; par_birth defaults then ode_init_conditions at birth */
+__global__ void __launch_bounds__(BLOCK) k_births(Pop p, int64_t dst0, int64_t count, int32_t id0, double t, uint32_t stream) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t j = dst0 + q;
+    double y[A1(NVAR)], e[A1(NEXPR)], z[A1(NAUX)], zp[A1(NPSI)];
+#pragma unroll
+    for (int v = 0; v < A1(NVAR); v++) y[v] = 0.0;
+#pragma unroll
+    for (int v = 0; v < A1(NEXPR); v++) e[v] = 0.0;
+#pragma unroll
+    for (int v = 0; v < A1(NAUX); v++) z[v] = 0.0;
+#pragma unroll
+    for (int v = 0; v < A1(NPSI); v++) zp[v] = 0.0;
+    DevCtx c = make_ctx(p, 0.0, stream, DOM_IC + 3, id0 + (int32_t)q);
+    c.atbirth = 1;
+    M::ic(c, t, y, e);
+    store_cols<NVAR>(p.Y, p.stride, j, y);
+    store_cols<NEXPR>(p.E, p.stride, j, e);
+    store_cols<NAUX>(p.AUX, p.stride, j, z);
+    store_cols<NPSI>(p.PSI, p.stride, j, zp);
+    p.DEATH[j] = 0.0; p.REPLI[j] = 0.0; p.ID[j] = id0 + (int32_t)q;
+  }
+}
+
+/* scan inputs over the whole sweep: ch0 = keep, ch1 = rows written, ch2 = net deaths before (outcome DIE) */
+__global__ void __launch_bounds__(BLOCK) k_sweep_flags(const int32_t *__restrict__ outcome, int32_t *__restrict__ f3, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * BLOCK) {
+    const int o = outcome[i];
+    f3[i * 3 + 0] = (o == OUT_NONE || o == OUT_REPL_KEEP) ? 1 : 0;
+    f3[i * 3 + 1] = (o == OUT_DIE) ? 1 : ((o == OUT_REPL_DIE) ? 2 : (o == OUT_REPL_KEEP ? 1 : 0));
+    f3[i * 3 + 2] = (o == OUT_DIE) ? 1 : 0;
+  }
+}
+
+/* event rows in sweep order (fwrite_SIM rows of tau_leaping_apply_birthdeath) */
+__global__ void __launch_bounds__(BLOCK) k_event_rows(const int32_t *__restrict__ outcome, const int32_t *__restrict__ s3,
+                                                       const int32_t *__restrict__ ids, const int32_t *__restrict__ child_id,
+                                                       int64_t n, int32_t n0, odx_event_row *__restrict__ rows, int64_t max_rows) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * BLOCK) {
+    const int o = outcome[i];
+    if (o == OUT_NONE) continue;
+    const int64_t r = s3[i * 3 + 1];
+    const int32_t nbefore = n0 - s3[i * 3 + 2];        /* replicate-then-die is net zero */
+    if (o == OUT_DIE) {
+      if (r < max_rows) { odx_event_row e = {nbefore - 1, ODX_STOP_DEATH, {ids[i], -1, -1}}; rows[r] = e; }
+    } else {
+      if (r < max_rows) { odx_event_row e = {nbefore + 1, ODX_STOP_REPLI, {ids[i], 1, child_id[i]}}; rows[r] = e; }
+      if (o == OUT_REPL_DIE && r + 1 < max_rows) { odx_event_row e = {nbefore, ODX_STOP_DEATH, {ids[i], -1, -1}}; rows[r + 1] = e; }
+    }
+  }
+}
+
+/* stable compaction: survivor i moves to position s3[i].keep in the alternate buffers */
+struct AltBufs { double *Y, *E, *AUX, *PSI, *DEATH, *REPLI; int32_t *ID; };
+__global__ void __launch_bounds__(BLOCK) k_compact(Pop p, AltBufs a, const int32_t *__restrict__ outcome, const int32_t *__restrict__ s3,
+                                                    int64_t nsweep, int64_t ntotal, int32_t kept_in_sweep) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < ntotal; i += (int64_t)gridDim.x * BLOCK) {
+    int64_t j;
+    if (i < nsweep) {
+      const int o = outcome[i];
+      if (!(o == OUT_NONE || o == OUT_REPL_KEEP)) continue;
+      j = s3[i * 3 + 0];
+    } else {
+      j = (int64_t)kept_in_sweep + (i - nsweep);       /* de-novo births stay behind the sweep survivors */
+    }
+#pragma unroll
+    for (int c = 0; c < NVAR; c++) a.Y[(int64_t)c * p.stride + j] = p.Y[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NEXPR; c++) a.E[(int64_t)c * p.stride + j] = p.E[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NAUX; c++) a.AUX[(int64_t)c * p.stride + j] = p.AUX[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NPSI; c++) a.PSI[(int64_t)c * p.stride + j] = p.PSI[(int64_t)c * p.stride + i];
+    a.DEATH[j] = p.DEATH[i]; a.REPLI[j] = p.REPLI[i]; a.ID[j] = p.ID[i];
+  }
+}
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+/* ---- host side -------------------------------------------------------------------------------------------------- */
+struct EventBufs {
+  int32_t *outcome = nullptr, *flag = nullptr, *scan = nullptr, *tile = nullptr, *grand = nullptr, *child = nullptr, *f3 = nullptr, *s3 = nullptr;
+  odx_event_row *rows = nullptr; int64_t rows_cap = 0;
+  AltBufs alt = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ready = false;
+};
+
+template <int NCH>
+static int exclusive_scan(odx_handle *h, const int32_t *in, int32_t *out, int64_t n, int32_t *tile, int32_t *grand, int32_t *grand_host) {
+  const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  if (n > 0) {
+    k_scan_tiles<NCH><<<ntiles, BLOCK, 0, h->stream>>>(in, out, tile, n);
+    ODX_TRY(launch_check(h));
+  }
+  k_scan_totals<NCH><<<1, BLOCK, 0, h->stream>>>(tile, n > 0 ? ntiles : 0, grand);
+  ODX_TRY(launch_check(h));
+  if (n > 0) {
+    k_scan_add<NCH><<<ntiles, BLOCK, 0, h->stream>>>(out, tile, n);
+    ODX_TRY(launch_check(h));
+  }
+  ODX_CUDA(h, cudaMemcpyAsync(grand_host, grand, sizeof(int32_t) * NCH, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+
+}  // namespace odx
+
+struct odx_event_state { odx::EventBufs b; uint32_t event_index = 0; };
+static odx_event_state *event_state(odx_handle *h) {
+  if (!h->ev_state) h->ev_state = new odx_event_state();
+  return h->ev_state;
+}
+static void odx_events_free(odx_handle *h) {
+  if (!h->ev_state) return;
+  odx::EventBufs &b = h->ev_state->b;
+  void *ptrs[] = {b.outcome, b.flag, b.scan, b.tile, b.grand, b.child, b.f3, b.s3, b.rows, b.alt.Y, b.alt.E, b.alt.AUX, b.alt.PSI,
+                  b.alt.DEATH, b.alt.REPLI, b.alt.ID};
+  for (void *q : ptrs) if (q) cudaFree(q);
+  delete h->ev_state;
+  h->ev_state = nullptr;
+}
+
+namespace odx {
+
+static int ensure_event_bufs(odx_handle *h, EventBufs &b) {
+  if (b.ready) return ODX_SUCCESS;
+  const int64_t cap = h->cap;
+  const int64_t ntile = (cap + SCAN_TILE - 1) / SCAN_TILE + 1;
+  ODX_CUDA(h, cudaMalloc((void **)&b.outcome, sizeof(int32_t) * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.flag, sizeof(int32_t) * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.scan, sizeof(int32_t) * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.child, sizeof(int32_t) * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.f3, sizeof(int32_t) * 3 * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.s3, sizeof(int32_t) * 3 * cap));
+  ODX_CUDA(h, cudaMalloc((void **)&b.tile, sizeof(int32_t) * 3 * ntile));
+  ODX_CUDA(h, cudaMalloc((void **)&b.grand, sizeof(int32_t) * 4));
+  ODX_TRY(alloc_cols(h, &b.alt.Y, NVAR)); ODX_TRY(alloc_cols(h, &b.alt.E, NEXPR)); ODX_TRY(alloc_cols(h, &b.alt.AUX, NAUX));
+  ODX_TRY(alloc_cols(h, &b.alt.PSI, NPSI)); ODX_TRY(alloc_cols(h, &b.alt.DEATH, 1)); ODX_TRY(alloc_cols(h, &b.alt.REPLI, 1));
+  ODX_CUDA(h, cudaMalloc((void **)&b.alt.ID, sizeof(int32_t) * cap));
+  b.ready = true;
+  return ODX_SUCCESS;
+}
+
+/* compaction + bookkeeping shared by tau-leap and SSA.  nsweep = particles covered by `outcome`, nbirth appended after. */
+static int finish_events(odx_handle *h, EventBufs &b, int64_t nsweep, int64_t nbirth, int32_t n0, odx_event_row *rows, int64_t max_rows,
+                         int64_t *nrows_out, int32_t *g3) {
+  Pop p = pop_view(h);
+  const int g = grid_for(h, nsweep > 0 ? nsweep : 1);
+  if (nsweep > 0) { k_sweep_flags<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.f3, nsweep); ODX_TRY(launch_check(h)); }
+  ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3));
+  const int32_t kept = g3[0], nrows = g3[1];
+  int64_t written = 0;
+  if (rows && max_rows > 0 && nrows > 0) {
+    if (b.rows_cap < nrows) {
+      if (b.rows) cudaFree(b.rows);
+      b.rows = nullptr; b.rows_cap = 0;
+      ODX_CUDA(h, cudaMalloc((void **)&b.rows, sizeof(odx_event_row) * (size_t)(nrows + 1024)));
+      b.rows_cap = nrows + 1024;
+    }
+    k_event_rows<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.s3, h->ID, b.child, nsweep, n0, b.rows, b.rows_cap);
+    ODX_TRY(launch_check(h));
+    written = nrows < max_rows ? nrows : max_rows;
+    ODX_CUDA(h, cudaMemcpyAsync(rows, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  /* births: rows {n+1.., STOP_BIRTH, {-1, +1, id}} follow the sweep rows */
+  const int32_t n_after_sweep = n0 - g3[2];
+  const int32_t first_birth_id = h->max_id - (int32_t)nbirth;
+  for (int64_t k = 0; k < nbirth; k++) {
+    if (rows && written < max_rows) {
+      odx_event_row e = {n_after_sweep + (int32_t)k + 1, ODX_STOP_BIRTH, {-1, 1, first_birth_id + (int32_t)k}};
+      rows[written++] = e;
+    }
+  }
+  if (nrows_out) *nrows_out = written;
+  const int64_t ntotal = nsweep + nbirth;
+  if (ntotal > 0) {
+    k_compact<<<grid_for(h, ntotal), BLOCK, 0, h->stream>>>(p, b.alt, b.outcome, b.s3, nsweep, ntotal, kept);
+    ODX_TRY(launch_check(h));
+  }
+  std::swap(h->Y, b.alt.Y); std::swap(h->E, b.alt.E); std::swap(h->AUX, b.alt.AUX); std::swap(h->PSI, b.alt.PSI);
+  std::swap(h->DEATH, b.alt.DEATH); std::swap(h->REPLI, b.alt.REPLI); std::swap(h->ID, b.alt.ID);
+  h->n = kept + nbirth;
+  invalidate_state(h);
+  return refresh_global_n(h);
+}
+
+}  // namespace odx
+
 extern "C" {
-int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {
-  (void)t; (void)u; (void)row; h->err = "odx_ssa_apply: not built yet"; return ODX_EUNSUP;
-}
+
 int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows) {
-  (void)t; (void)dt; (void)leap_index; (void)rows; (void)max_rows; (void)nrows; h->err = "odx_tauleap_apply: not built yet"; return ODX_EUNSUP;
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (h->nranks > 1) { h->err = "odx_tauleap_apply: multi-GPU birth/death is not built yet"; return ODX_EUNSUP; }
+  odx_event_state *es = event_state(h);
+  EventBufs &b = es->b;
+  ODX_TRY(ensure_event_bufs(h, b));
+  const uint32_t stream = (leap_index == UINT64_MAX) ? es->event_index : (uint32_t)leap_index;
+  const int32_t n0 = (int32_t)h->n;
+  double birth_rate = 0.0;
+  ODX_TRY(odx_rates(h, nullptr, &birth_rate));
+  /* generations of the sweep: [first, end) -> daughters appended at [end, end + nd) */
+  int64_t first = 0, end = h->n;
+  int32_t g1[4];
+  while (end > first) {
+    const int64_t count = end - first;
+    Pop p = pop_view(h);
+    k_leap_flags<<<grid_for(h, count), BLOCK, 0, h->stream>>>(p, first, count, dt, stream, b.outcome, b.flag);
+    ODX_TRY(launch_check(h));
+    ODX_TRY(exclusive_scan<1>(h, b.flag, b.scan, count, b.tile, b.grand, g1));
+    const int64_t nd = g1[0];
+    if (nd > 0) {
+      if (end + nd > h->cap) { h->err = "odx_tauleap_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+      k_spawn<<<grid_for(h, count), BLOCK, 0, h->stream>>>(p, first, count, b.outcome, b.scan, end, h->max_id, t, stream, b.child);
+      ODX_TRY(launch_check(h));
+      h->max_id += (int32_t)nd;
+    }
+    first = end; end += nd;
+  }
+  const int64_t nsweep = end;
+  /* de-novo births: poisson(pop_birth_rate * dt), drawn by the host loop's stream */
+  long nnew = M::HAS_BIRTH ? odx_draw_poisson(h, birth_rate * dt, h->hr_seeded ? 1 : 0) : 0;
+  if (nnew < 0) nnew = 0;
+  if (nsweep + nnew > h->cap) { h->err = "odx_tauleap_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+  if (nnew > 0) {
+    k_births<<<grid_for(h, nnew), BLOCK, 0, h->stream>>>(pop_view(h), nsweep, nnew, h->max_id, t, stream);
+    ODX_TRY(launch_check(h));
+    h->max_id += (int32_t)nnew;
+  }
+  int32_t g3[4];
+  ODX_TRY(finish_events(h, b, nsweep, nnew, n0, rows, max_rows, nrows, g3));
+  es->event_index++;
+  return ODX_SUCCESS;
 }
+
+int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (h->nranks > 1) { h->err = "odx_ssa_apply: multi-GPU birth/death is not built yet"; return ODX_EUNSUP; }
+  odx_event_state *es = event_state(h);
+  EventBufs &b = es->b;
+  ODX_TRY(ensure_event_bufs(h, b));
+  const int64_t N = h->n;
+  if (row) { row->n = (int32_t)N; row->stop_flag = 0; row->event[0] = row->event[1] = row->event[2] = 0; }
+  double birth_rate = 0.0;
+  ODX_TRY(odx_rates(h, nullptr, &birth_rate));
+  /* normalised cumulative sum and linear search exactly as SSA_apply_birthdeath / ncumsum (host, reference order) */
+  std::vector<double> r((size_t)(2 * N + 1));
+  if (N > 0) {
+    ODX_CUDA(h, cudaMemcpyAsync(r.data(), h->DEATH, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(r.data() + N, h->REPLI, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  r[2 * N] = birth_rate;
+  for (int64_t i = 1; i < 2 * N + 1; i++) r[i] += r[i - 1];
+  const double sumr = r[2 * N];
+  for (int64_t i = 0; i < 2 * N + 1; i++) r[i] /= r[2 * N];
+  if (!(sumr > 0.0)) return ODX_SUCCESS;
+  int64_t idx = 0;
+  while (u > r[idx]) idx++;
+  const uint32_t stream = es->event_index;
+  int64_t nbirth = 0;
+  if (N > 0) { k_fill_i32<<<grid_for(h, N), BLOCK, 0, h->stream>>>(b.outcome, N, OUT_NONE); ODX_TRY(launch_check(h)); }
+  int32_t one;
+  if (idx < N) {
+    one = OUT_DIE;
+    ODX_CUDA(h, cudaMemcpyAsync(b.outcome + idx, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+  } else if (idx < 2 * N) {
+    const int64_t k = idx - N;
+    if (N + 1 > h->cap) { h->err = "odx_ssa_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+    one = OUT_REPL_KEEP;
+    ODX_CUDA(h, cudaMemcpyAsync(b.outcome + k, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+    ODX_CUDA(h, cudaMemsetAsync(b.scan, 0, sizeof(int32_t) * N, h->stream));
+    k_spawn<<<grid_for(h, N), BLOCK, 0, h->stream>>>(pop_view(h), 0, N, b.outcome, b.scan, N, h->max_id, t, stream, b.child);
+    ODX_TRY(launch_check(h));
+    h->max_id += 1;
+    /* the daughter sits at slot N: treat it as an appended particle that is kept */
+    nbirth = 1;
+  } else {
+    if (N + 1 > h->cap) { h->err = "odx_ssa_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+    k_births<<<1, BLOCK, 0, h->stream>>>(pop_view(h), N, 1, h->max_id, t, stream);
+    ODX_TRY(launch_check(h));
+    h->max_id += 1;
+    nbirth = 1;
+  }
+  odx_event_row tmp[2]; int64_t nr = 0; int32_t g3[4];
+  const bool repl = (idx >= N && idx < 2 * N);
+  /* for a replication the appended slot is not a de-novo birth: no birth row, the sweep row carries the child id */
+  ODX_TRY(finish_events(h, b, N, nbirth, (int32_t)N, repl ? tmp : tmp, repl ? 1 : 2, &nr, g3));
+  if (row && nr > 0) *row = tmp[0];
+  es->event_index++;
+  return ODX_SUCCESS;
 }
+
+}  // extern "C"

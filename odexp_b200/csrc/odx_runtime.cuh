@@ -43,7 +43,11 @@ static NcclApi g_nccl;
 
 using namespace odx;
 
+struct odx_event_state;
+static void odx_events_free(odx_handle *h);
+
 struct odx_handle {
+  odx_event_state *ev_state = nullptr;       /* birth / death scratch (odx_events.cuh), allocated on first use */
   int device = 0;
   cudaStream_t stream = nullptr;
   int64_t cap = 0, n = 0;
@@ -386,6 +390,7 @@ void odx_destroy(odx_handle *h) {
 #ifdef ODX_HAVE_NCCL_H
   if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
+  odx_events_free(h);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
                     h->sums, h->stage_dev, h->gather};
   for (double *b : bufs) if (b) cudaFree(b);

@@ -1,0 +1,102 @@
+"""GPU parity for the stochastic paths: Euler-Maruyama (DWDT) and birth / death (SSA, tau-leaping), through the C-ABI,
+against the CPU restatement run with the SAME keyed Philox draws (oracle rng_mode 1; the restatement itself is pinned
+bit-for-bit to the unchanged reference with the serial libc stream, tests/test_oracle_port.py).
+
+Required: identical event logs (N, stop flag, parent id, +-1, child id per stats row) and identical particle ids in
+every trajectory frame; states within 1e-10 relative (libm vs device log/sqrt/cos in Box-Muller)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(model_lib, model, opts, ts, capacity=None):
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib(model)
+    pop = capi.Population(lib, capacity=capacity or max(4096, 4 * opts["ps"]))
+    out = capi.odesolver(pop, ts, meth=opts["meth"], res=opts["res"], popsize=opts["ps"], h0=opts.get("h0", 0.1),
+                         hmin=opts.get("hmin", 1e-5), ssahmin=opts.get("ssahmin", 0.0), aleap=opts.get("aleap", 0.01),
+                         seed=opts.get("seed", 3141592), replay_ic=False)
+    pop.close()
+    ref = port.run(model, opts, ts, rng_mode=1)
+    return out, ref
+
+
+def compare(out, ref, rtol=1e-10, atol=1e-12):
+    sa, sb, ta, tb = out["stats"], ref["stats"], out["traj"], ref["traj"]
+    assert len(sa) == len(sb), (len(sa), len(sb))
+    np.testing.assert_array_equal(sa["n"], sb["n"])
+    np.testing.assert_array_equal(sa["stop_flag"], sb["stop_flag"])
+    np.testing.assert_array_equal(sa["event"], sb["event"])
+    np.testing.assert_allclose(sa["t"], sb["t"], rtol=1e-12, atol=1e-13)
+    assert len(ta) == len(tb)
+    np.testing.assert_array_equal(ta["id"], tb["id"])
+    np.testing.assert_array_equal(ta["step"], tb["step"])
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=rtol, atol=atol)
+
+
+def test_kuramoto_device_initial_conditions(model_lib):
+    """ode_init_conditions on the device (keyed Philox randN / rand01) == restatement with the same keys"""
+    out, ref = run_both(model_lib, "kuramoto", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 777}, (0, 0.4))
+    compare(out, ref, rtol=1e-11, atol=1e-13)
+
+
+def test_sde_euler_maruyama_no_events(model_lib):
+    out, ref = run_both(model_lib, "vdp_sde", {"meth": "fe", "h0": 0.01, "res": 6, "ps": 300, "ssahmin": 0.0, "seed": 11}, (0, 0.05))
+    compare(out, ref)
+
+
+@pytest.mark.parametrize("ps,seed", [(100, 3141592), (1000, 5), (1, 7), (3000, 9)])
+def test_tau_leaping(model_lib, ps, seed):
+    opts = {"meth": "fe", "h0": 0.01, "res": 41, "ps": ps, "ssahmin": 1.0, "seed": seed}
+    out, ref = run_both(model_lib, "vdp_sde", opts, (0, 4))
+    ev = out["stats"]["event"][:, 1]
+    assert (ev == 1).sum() > ps                               # births / replications beyond the initial rows
+    if ps >= 100:
+        assert (ev == -1).sum() > 0                           # and deaths
+    compare(out, ref)
+
+
+@pytest.mark.parametrize("ps,seed", [(50, 3141592), (200, 21)])
+def test_ssa_single_events(model_lib, ps, seed):
+    opts = {"meth": "fe", "h0": 0.01, "res": 11, "ps": ps, "ssahmin": 0.0, "seed": seed}
+    out, ref = run_both(model_lib, "vdp_sde", opts, (0, 2))
+    compare(out, ref)
+
+
+def test_population_can_die_out(model_lib):
+    """edge: every particle dies (huge death rate, no births): the loop stops with an empty population"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("vdp_sde")
+    mu = [1.0, 0.1, 50.0, 0.0]
+    opts = {"meth": "fe", "h0": 0.01, "res": 11, "ps": 64, "ssahmin": 1.0, "aleap": 1.0}
+    pop = capi.Population(lib, capacity=1024)
+    out = capi.odesolver(pop, (0, 2), meth="fe", res=11, popsize=64, h0=0.01, ssahmin=1.0, aleap=1.0, replay_ic=False, mu=mu)
+    ref = port.run("vdp_sde", opts, (0, 2), rng_mode=1, mu=mu)
+    pop.close()
+    np.testing.assert_array_equal(out["stats"]["n"], ref["stats"]["n"])
+    np.testing.assert_array_equal(out["stats"]["event"], ref["stats"]["event"])
+
+
+def test_exclusive_scan_and_compaction_large(model_lib):
+    """size-independent property at a population larger than one scan tile grid: ids stay sorted (stable compaction
+    preserves list order), are unique, and N matches the event log arithmetic"""
+    from odexp_b200 import capi
+    lib = model_lib("vdp_sde")
+    n = 1 << 18
+    pop = capi.Population(lib, capacity=2 * n)
+    pop.set_seed(5)
+    pop.init(n, replay=False, seed=5)
+    pop.rhs(0.0)
+    rows = pop.tauleap_apply(0.0, 2.0, 0)
+    n_local, _, max_id = pop.size()
+    d = pop.download()
+    ids = d["id"]
+    assert np.all(np.diff(ids) > 0) and len(ids) == n_local
+    deaths = sum(1 for r in rows if r[2][1] == -1)
+    births = sum(1 for r in rows if r[2][1] == 1)
+    assert n_local == n - deaths + births and rows[-1][0] == n_local
+    assert max_id == n + births
+    pop.close()

@@ -47,7 +47,9 @@ def test_parse_features():
 def test_emit_translates_macros():
     from odexp_b200 import popfile, cudagen
     cu = cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto")))
-    assert "odx_m[0] = sin((odx_y[0]));" in cu and "odx_m[2] = (odx_e[0]);" in cu
+    # sin / cos of the same argument are hoisted into one odx_sincos
+    assert "odx_sincos((odx_y[0]), &odx_sn0, &odx_cs0);" in cu and "odx_m[0] = odx_sn0;" in cu and "odx_m[1] = odx_cs0;" in cu
+    assert "odx_m[2] = (odx_e[0]);" in cu and cu.count("odx_sincos(") == 2
     assert "NVAR = 1, NEXPR = 1, NAUX = 2, NPSI = 0, NMFD = 3" in cu
     nb = cudagen.emit_cuda(popfile.parse_file(fixture_path("nbody")))
     assert "odx_pow15(" in nb and "pow(" not in nb.replace("odx_pow", "")
