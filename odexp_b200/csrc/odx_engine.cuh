@@ -46,6 +46,9 @@ constexpr int NRED = NMFD + 2;                          /* [%M sums..., %BIRTH s
 constexpr int RED_BIRTH = NMFD, RED_RATES = NMFD + 1;
 constexpr int BLOCK = 256;
 constexpr int MAXSTAGE = 7;
+#ifndef CHAIN_MIN_BLOCKS
+#define CHAIN_MIN_BLOCKS 4
+#endif
 
 /* ------------------------------------------------------------------------------------------------
  * evaluation context handed to the generated model code
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(BLOCK) k_moments(Pop p, const double *__restri
     load_cols<NVAR>(ysrc, p.stride, i, y);
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (M::TERMS_USE_AUX) load_cols<NPSI>(p.PSI, p.stride, i, psi);
-    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, p.ID[i]);
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
     particle_terms(c, t, y, e, psi, red);
   }
   grid_reduce<NRED>(red, r);
@@ -235,53 +238,90 @@ struct ChainArgs {
 
 /* chain methods (Euler, classic RK4): stage state depends on the previous slope only.
  * FIRST: the RHS is evaluated at Y itself (k1).  LAST: apply the step to Y and produce the %M sums of the
- * new state, which are exactly what the first stage of the next step needs. */
+ * new state, which are exactly what the first stage of the next step needs.
+ * Each thread carries two adjacent particles per iteration: every column is moved with 128-bit accesses and the two
+ * independent dependency chains hide the FP64 latency of the per-particle model code. */
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(BLOCK) k_chain(Pop p, ChainArgs a, Red r) {
+__device__ __forceinline__ void chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id,
+                                           const double (&y0)[A1(NVAR)], const double (&yc)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                           const double (&psi)[A1(NPSI)], double (&acc)[A1(NVAR)], double (&yn)[A1(NVAR)],
+                                           double (&aux)[A1(NAUX)], double &death, double &repli, double (&red)[NRED], bool live) {
+  double f[A1(NVAR)];
+  DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+  M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+  if (LAST) {
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) yn[v] = y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
+    if (live) red[RED_RATES] += death + repli;
+  } else {
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) {
+      acc[v] = FIRST ? a.w * f[v] : acc[v] + a.w * f[v];
+      yn[v] = y0[v] + a.a * f[v];
+    }
+  }
+  if (NMFD > 0 || M::HAS_BIRTH) {
+    if (live) {
+      DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
+      particle_terms(c2, a.t_next, yn, e, psi, red);
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_cols2(const double *__restrict__ base, int64_t stride, int64_t i, bool two,
+                                           double (&o0)[A1(NC)], double (&o1)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (two) { const double2 v = *reinterpret_cast<const double2 *>(base + (int64_t)c * stride + i); o0[c] = v.x; o1[c] = v.y; }
+    else { o0[c] = base[(int64_t)c * stride + i]; o1[c] = o0[c]; }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t stride, int64_t i, bool two,
+                                            const double (&v0)[A1(NC)], const double (&v1)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (two) *reinterpret_cast<double2 *>(base + (int64_t)c * stride + i) = make_double2(v0[c], v1[c]);
+    else base[(int64_t)c * stride + i] = v0[c];
+  }
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainArgs a, Red r) {
   double red[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
   load_mfd(a.sums_in, p.n_global, mfd);
-  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
-    double y0[A1(NVAR)], yc[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], acc[A1(NVAR)], f[A1(NVAR)], aux[A1(NAUX)];
-    double death = 0.0, repli = 0.0;
-    load_cols<NVAR>(p.Y, p.stride, i, y0);
-    load_cols<NEXPR>(p.E, p.stride, i, e);
-    if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
+  for (int64_t i = 2 * ((int64_t)blockIdx.x * BLOCK + threadIdx.x); i < p.n; i += 2 * (int64_t)gridDim.x * BLOCK) {
+    const bool two = (i + 1 < p.n);
+    double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)], yn[2][A1(NVAR)], aux[2][A1(NAUX)];
+    double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
+    load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
+    load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
+    if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
     if (FIRST) {
 #pragma unroll
-      for (int v = 0; v < NVAR; v++) yc[v] = y0[v];
+      for (int v = 0; v < NVAR; v++) { yc[0][v] = y0[0][v]; yc[1][v] = y0[1][v]; }
     } else {
-      load_cols<NVAR>(p.YS, p.stride, i, yc);
-      load_cols<NVAR>(p.ACC, p.stride, i, acc);
+      load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
+      load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
     }
-    const int32_t id = p.ID[i];
-    DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
-    M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
-    double yn[A1(NVAR)];
+    int32_t id0 = 0, id1 = 0;
+    if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
+    chain_lane<FIRST, LAST>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], yn[0], aux[0], death[0], repli[0], red, true);
+    chain_lane<FIRST, LAST>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], yn[1], aux[1], death[1], repli[1], red, two);
     if (LAST) {
-#pragma unroll
-      for (int v = 0; v < NVAR; v++) yn[v] = y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
-      store_cols<NVAR>(p.Y, p.stride, i, yn);
+      store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
       if (a.want_out) {
-        store_cols<NAUX>(p.AUX, p.stride, i, aux);
-        if (M::HAS_DEATH) p.DEATH[i] = death;
-        if (M::HAS_REPLI) p.REPLI[i] = repli;
+        store_cols2<NAUX>(p.AUX, p.stride, i, two, aux[0], aux[1]);
+        if (M::HAS_DEATH) { p.DEATH[i] = death[0]; if (two) p.DEATH[i + 1] = death[1]; }
+        if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
       }
-      red[RED_RATES] += death + repli;
     } else {
-#pragma unroll
-      for (int v = 0; v < NVAR; v++) {
-        acc[v] = FIRST ? a.w * f[v] : acc[v] + a.w * f[v];
-        yn[v] = y0[v] + a.a * f[v];
-      }
-      store_cols<NVAR>(p.ACC, p.stride, i, acc);
-      store_cols<NVAR>(p.YS, p.stride, i, yn);
-    }
-    if (NMFD > 0 || M::HAS_BIRTH) {
-      DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
-      particle_terms(c2, a.t_next, yn, e, psi, red);
+      store_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
     }
   }
   if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
@@ -301,7 +341,7 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
     load_cols<NVAR>(ysrc, p.stride, i, y);
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
-    DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, p.ID[i]);
+    DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
     M::rhs(c, a.t, y, e, psi, mfd, f, aux, death, repli);
     store_cols<NAUX>(p.AUX, p.stride, i, aux);
     if (M::HAS_DEATH) p.DEATH[i] = death;
@@ -331,7 +371,7 @@ __global__ void __launch_bounds__(BLOCK) k_pair(Pop p, const double *__restrict_
     load_cols<NEXPR>(p.E, p.stride, ii, e);
 #pragma unroll
     for (int k = 0; k < A1(NPSI); k++) acc[k] = 0.0;
-    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, p.ID[ii]);
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[ii] : 0);
     for (int64_t j0 = 0; j0 < nj; j0 += PAIR_TJ) {
       const int tj = (int)((nj - j0) < PAIR_TJ ? (nj - j0) : PAIR_TJ);
       __syncthreads();
@@ -395,7 +435,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
     load_cols<NVAR>(a.ycur, p.stride, i, yc);
-    const int32_t id = p.ID[i];
+    const int32_t id = M::NEEDS_ID ? p.ID[i] : 0;
     if (a.skip_rhs) {
       load_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     } else {

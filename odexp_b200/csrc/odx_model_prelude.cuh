@@ -18,25 +18,41 @@ ODX_HD double odx_pow3(double x) { return x * x * x; }
 __host__ __device__ __noinline__
 #endif
 static void odx_sincos_library(double x, double *sp, double *cp) { sincos(x, sp, cp); }
+/* coefficients live in the constant bank on the device: a 64-bit literal would be rebuilt from two 32-bit uniform
+ * moves in front of every DFMA (three issue slots per term instead of one) */
+#define ODX_SC_TABLE { 0.63661977236758134308, 0x1.921fb54442d18p+0, 0x1.1a62633145c00p-54, 0x1.b839a252049c0p-104, \
+  1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, \
+  8.33333333332248946124e-03, -1.66666666666666324348e-01, \
+  -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05, \
+  -1.38888888888741095749e-03, 4.16666666666666019037e-02 }
+#if defined(__CUDACC__)
+__constant__ double odx_sc_dev[16] = ODX_SC_TABLE;
+#endif
+static const double odx_sc_host[16] = ODX_SC_TABLE;
 ODX_HD void odx_sincos(double x, double *sp, double *cp) {
+#if defined(__CUDA_ARCH__)
+  const double *T = odx_sc_dev;
+#else
+  const double *T = odx_sc_host;
+#endif
   if (!(fabs(x) < 105615.0)) { odx_sincos_library(x, sp, cp); return; }
-  const double q = rint(x * 0.63661977236758134308);
+  const double q = rint(x * T[0]);
   const int n = (int)q;
-  double r = fma(-q, 0x1.921fb54442d18p+0, x);
-  r = fma(-q, 0x1.1a62633145c00p-54, r);
-  r = fma(-q, 0x1.b839a252049c0p-104, r);
+  double r = fma(-q, T[1], x);
+  r = fma(-q, T[2], r);
+  r = fma(-q, T[3], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, T[4], T[5]);
+  ps = fma(z, ps, T[6]);
+  ps = fma(z, ps, T[7]);
+  ps = fma(z, ps, T[8]);
+  ps = fma(z, ps, T[9]);
   const double s = fma(r * z, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double pc = fma(z, T[10], T[11]);
+  pc = fma(z, pc, T[12]);
+  pc = fma(z, pc, T[13]);
+  pc = fma(z, pc, T[14]);
+  pc = fma(z, pc, T[15]);
   const double hz = 0.5 * z, w = 1.0 - hz;
   const double c = w + (((1.0 - w) - hz) + z * (z * pc));
   const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;

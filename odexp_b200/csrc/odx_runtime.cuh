@@ -107,6 +107,12 @@ static inline int grid_for(const odx_handle *h, int64_t n) {
   if (g > h->grid_cap) g = h->grid_cap;
   return (int)g;
 }
+static inline int grid_chain(const odx_handle *h, int64_t n) {      /* two particles per thread */
+  int64_t g = (n + 2 * BLOCK - 1) / (2 * BLOCK);
+  if (g < 1) g = 1;
+  if (g > h->grid_cap) g = h->grid_cap;
+  return (int)g;
+}
 constexpr bool NEEDS_MOMENTS = (NMFD > 0) || M::HAS_BIRTH;
 
 /* cross-GPU sum of the raw %M sums (and birth / rate sums): allreduce(SUM) of NRED doubles per RHS evaluation */
@@ -190,7 +196,7 @@ static int do_rhs(odx_handle *h, double t, double hcur) {
 static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out) {
   if (h->n <= 0) return ODX_SUCCESS;
   ODX_TRY(ensure_moments_Y(h, t));
-  const int g = grid_for(h, h->n);
+  const int g = grid_chain(h, h->n);
   Pop p = pop_view(h);
   const int new_slot = h->y_slot ^ 1;
   ChainArgs a; a.h = hh; a.want_out = want_out;

@@ -183,6 +183,8 @@ class Emitter:
         terms_use_aux = self.uses(term_exprs, r"\bMA\(")
         cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
         rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
+        # the particle id column is only read by the stage kernels when something can observe it
+        needs_id = rhs_rng or self.uses(rhs_exprs + term_exprs + cpl_exprs, r"\b(ID|OID|MID|rand01|randN|exprand|poisson|DWDT)\b")
         L = []
         w = L.append
         w("/* generated by odexp_b200.cudagen from model '%s' — do not edit */" % m.name)
@@ -200,8 +202,8 @@ class Emitter:
           (m.nvar, m.nexpr, m.naux, m.npsi, m.nmfd, m.npar))
         w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
-        w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s;" %
-          tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr)))
+        w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %
+          tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr, needs_id)))
         w("")
         # ---- ode_rhs
         w("  /* per-particle right-hand side: AUX, D/DT, %DEATH, %REPLI (reference: generated ode_rhs) */")
