@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_TOTAL)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-peers", action="store_true", help="per-stage sums through NCCL allreduce instead of NVLink peer mailboxes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -158,9 +159,8 @@ def main():
     n_local = n_total // world
     pop = capi.Population(lib, capacity=n_local, device=local)
     if world > 1:
-        uid = [pop.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        pop.comm_init(rank, world, uid[0])
+        from odexp_b200 import dist as odist
+        odist.connect(pop, use_nccl=True, use_peers=not args.no_peers)
     # synthetic population: theta0 = 2*PI*u, omega ~ N(2*PI/10, 0.1), keyed Philox on the device (ode_init_conditions)
     pop.init(n_local, t=0.0, seed=3141592, replay=False)
     pop.sync()
@@ -222,7 +222,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "Kuramoto mean-field (oracle/fixtures/kuramoto.pop), N=%d oscillators, classic RK4 (meth dde) h=%g, FP64" % (n_total, H_STEP),
                            "n_particles": n_total, "per_gpu_particles": n_local, "l2": "inputs larger than L2 (%.0f MB state per GPU)" % (n_local * 32 / 1e6),
-                           "parallelism": "particle sharding x%d, allreduce of %%M sums per stage" % world, "mean_fields_after": [float(x) for x in mfd]},
+                           "parallelism": "particle sharding x%d, %%M sums per stage through %s" % (world, "NCCL allreduce" if args.no_peers else "in-kernel NVLink peer mailboxes"), "mean_fields_after": [float(x) for x in mfd]},
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(8 * lib.nmfd),
                         "steps": ne2e, "what": "odx_pop_upload(host theta, omega) + odx_run_fixed(dde, 1 step) + odx_meanfields per step"},
                 "gpu_launches": int(launches), "clocks": clocks,

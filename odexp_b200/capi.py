@@ -49,7 +49,8 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_set_tolerances", "odx_comm_unique_id", "odx_comm_init", "odx_pop_upload", "odx_pop_download", "odx_pop_size",
                "odx_pop_init", "odx_rhs", "odx_meanfields", "odx_rates", "odx_fe_apply", "odx_dde_apply", "odx_evolve_reset",
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
-               "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count"]
+               "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
+               "odx_set_option", "odx_peer_export", "odx_peer_attach"]
 
 
 def _dp(a):
@@ -73,6 +74,9 @@ class ModelLib:
         L.odx_set_params.argtypes = [H, C.POINTER(C.c_double), C.c_int]
         L.odx_set_seed.argtypes = [H, C.c_uint64]
         L.odx_set_tolerances.argtypes = [H, C.c_double, C.c_double]
+        L.odx_set_option.argtypes = [H, C.c_char_p, C.c_double]
+        L.odx_peer_export.argtypes = [H, C.c_void_p]
+        L.odx_peer_attach.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
         L.odx_comm_unique_id.argtypes = [C.c_void_p]
         L.odx_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
         L.odx_pop_upload.argtypes = [H, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]
@@ -149,6 +153,18 @@ class Population:
 
     def set_tolerances(self, abstol, reltol):
         self._ck(self.L.odx_set_tolerances(self.h, abstol, reltol), "odx_set_tolerances")
+
+    def set_option(self, name, value):
+        self._ck(self.L.odx_set_option(self.h, name.encode(), float(value)), "odx_set_option")
+
+    def peer_export(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.odx_peer_export(self.h, buf), "odx_peer_export")
+        return bytes(buf.raw)
+
+    def peer_attach(self, rank, nranks, handles):
+        buf = C.create_string_buffer(b"".join(handles), 64 * nranks)
+        self._ck(self.L.odx_peer_attach(self.h, rank, nranks, buf), "odx_peer_attach")
 
     def comm_init(self, rank, nranks, uid):
         buf = C.create_string_buffer(bytes(uid), 128)

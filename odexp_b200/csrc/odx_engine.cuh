@@ -287,14 +287,10 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
   }
 }
 
+/* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread) */
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainArgs a, Red r) {
-  double red[NRED];
-#pragma unroll
-  for (int k = 0; k < NRED; k++) red[k] = 0.0;
-  double mfd[A1(NMFD)];
-  load_mfd(a.sums_in, p.n_global, mfd);
-  for (int64_t i = 2 * ((int64_t)blockIdx.x * BLOCK + threadIdx.x); i < p.n; i += 2 * (int64_t)gridDim.x * BLOCK) {
+__device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED]) {
+  for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < p.n; i += 2 * (int64_t)gridDim.x * blockDim.x) {
     const bool two = (i + 1 < p.n);
     double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)], yn[2][A1(NVAR)], aux[2][A1(NAUX)];
     double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
@@ -324,7 +320,260 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
       store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
     }
   }
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainArgs a, Red r) {
+  double red[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] = 0.0;
+  double mfd[A1(NMFD)];
+  load_mfd(a.sums_in, p.n_global, mfd);
+  chain_sweep<FIRST, LAST>(p, a, mfd, red);
   if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistent step kernel: `nsteps` whole steps of a chain method in ONE cooperative launch.
+ *
+ * The mean-field barrier between stages is a grid barrier inside the kernel (arrive counter + generation word in
+ * global memory, all CTAs co-resident) instead of a kernel boundary, and across GPUs it is an exchange of the NRED
+ * partial sums through peer memory: after the local barrier CTA 0 adds the block partials in a fixed order and
+ * stores the result, tagged with the epoch, straight into every peer's mailbox over NVLink (plain st.global on
+ * IPC-mapped pointers, __threadfence_system, then the flag); every CTA then waits for the flags of all ranks in its
+ * own GPU's mailbox and adds the rank sums in rank order.  No NCCL call, no host round trip per stage: the fused
+ * compute + collective the latency-bound per-stage allreduce (24-40 bytes) needs.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int MAX_RANKS = 8;
+struct PersistArgs {
+  int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0;
+  const double *sums_y;            /* global raw sums of the %M terms of Y at entry */
+  double *partial;                 /* [2][grid][NRED] */
+  unsigned int *bar;               /* [2][PERSIST_MAX_CTAS] epoch tags of the published block partials */
+  double *totals;                  /* unused */
+  double *sums_new, *sums_report;  /* out: sums of the new Y (+ rates) / sums used by the last RHS evaluation */
+  int rank, nranks; uint32_t epoch0;
+  double *mailbox; uint32_t *mailflag;                 /* local: [2][MAX_RANKS][NRED], [2][MAX_RANKS] */
+  double *peer_box[MAX_RANKS]; uint32_t *peer_flag[MAX_RANKS];
+  int *abort_flag;
+};
+
+/* Grid barrier fused with the reduction (all CTAs co-resident: cooperative launch).  Arrival is two-level to keep the
+ * atomics off a single L2 line: CTAs arrive on one of BAR_GROUPS padded counters, the last of each group arrives on the
+ * top counter, and the globally last CTA returns true: it alone adds the block partials (and talks to the peers)
+ * before it releases the others by bumping the generation word. */
+constexpr int BAR_GROUPS = 16;
+constexpr int BAR_PAD = 32;                         /* one 128-byte line per counter */
+constexpr int BAR_WORDS = (BAR_GROUPS + 2) * BAR_PAD;
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+/* returns true in exactly one CTA (the last to arrive); that CTA must call barrier_release afterwards */
+__device__ __forceinline__ bool barrier_arrive(unsigned int *bar, unsigned int nblocks, unsigned int &gen0) {
+  __shared__ int s_is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *top = bar + BAR_GROUPS * BAR_PAD, *gen = bar + (BAR_GROUPS + 1) * BAR_PAD;
+    gen0 = ld_acquire_u32(gen);
+    const unsigned int ng = nblocks < BAR_GROUPS ? nblocks : BAR_GROUPS;
+    const unsigned int grp = blockIdx.x % ng;
+    const unsigned int gsize = nblocks / ng + ((grp < nblocks % ng) ? 1u : 0u);
+    __threadfence();
+    int last = 0;
+    if (atomicAdd(bar + grp * BAR_PAD, 1u) == gsize - 1) {
+      bar[grp * BAR_PAD] = 0u;
+      __threadfence();
+      if (atomicAdd(top, 1u) == ng - 1) { *top = 0u; last = 1; }
+    }
+    s_is_last = last;
+  }
+  __syncthreads();
+  const bool last = s_is_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+__device__ __forceinline__ void barrier_release(unsigned int *bar, unsigned int gen0) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); st_release_u32(bar + (BAR_GROUPS + 1) * BAR_PAD, gen0 + 1u); }
+}
+__device__ __forceinline__ void barrier_wait(unsigned int *bar, unsigned int gen0) {
+  if (threadIdx.x == 0) {
+    const unsigned int *gen = bar + (BAR_GROUPS + 1) * BAR_PAD;
+    while (ld_acquire_u32(gen) == gen0) { }
+  }
+  __syncthreads();
+}
+
+/* block partial of red[] -> partial[blockIdx][*] */
+template <int NT>
+__device__ __forceinline__ void block_partial(const double (&red)[NRED], double *__restrict__ partial) {
+  __shared__ double s_part[NT / 32][NRED];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    const double v = warp_sum(red[k]);
+    if (lane == 0) s_part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) v += s_part[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * NRED + threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+/* fixed-order sum of all block partials, result in s_tot[NRED] (every CTA computes the same bits) */
+template <int NT>
+__device__ __forceinline__ void sum_partials(const double *__restrict__ partial, unsigned int nblocks, double *s_tot) {
+  __shared__ double s_part2[NT / 32][NRED];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+  for (unsigned int b = threadIdx.x; b < nblocks; b += NT) {
+#pragma unroll
+    for (int k = 0; k < NRED; k++) acc[k] += __ldcg(&partial[(size_t)b * NRED + k]);
+  }
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_part2[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) v += s_part2[w][threadIdx.x];
+    s_tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+/* fixed-order block sum of per-thread accumulators into s_tot[NRED] */
+template <int NT>
+__device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s_tot) {
+  __shared__ double s_part3[NT / 32][NRED];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_part3[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) v += s_part3[w][threadIdx.x];
+    s_tot[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+constexpr int PERSIST_MAX_CTAS = 1024;
+#ifndef PERSIST_THREADS
+#define PERSIST_THREADS 1024
+#endif
+constexpr int PT = PERSIST_THREADS;
+__global__ void __launch_bounds__(PT, 4096 / PT / (4 / CHAIN_MIN_BLOCKS > 0 ? 4 / CHAIN_MIN_BLOCKS : 1)) k_chain_persist(Pop p, PersistArgs g) {
+  __shared__ double s_tot[NRED];
+  double mfd[A1(NMFD)];
+  if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
+  __syncthreads();
+  uint32_t epoch = g.epoch0;
+  uint32_t eval = g.eval_index0;
+  for (long long step = 0; step < g.nsteps; step++) {
+    const double t = g.t0 + (double)step * g.h;
+    for (int s = 0; s < g.nst; s++) {
+#pragma unroll
+      for (int k = 0; k < NMFD; k++) mfd[k] = s_tot[k] / p.n_global;
+      const bool last_stage = (s == g.nst - 1);
+      if (last_stage && step == g.nsteps - 1 && blockIdx.x == 0 && threadIdx.x < NRED) g.sums_report[threadIdx.x] = s_tot[threadIdx.x];
+      __syncthreads();
+      ChainArgs a;
+      a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2;
+      a.want_out = (last_stage && step == g.nsteps - 1) ? g.want_out_last : 0;
+      double red[NRED];
+#pragma unroll
+      for (int k = 0; k < NRED; k++) red[k] = 0.0;
+      if (g.nst == 1) {                                   /* Euler */
+        a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
+        chain_sweep<true, true>(p, a, mfd, red);
+      } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */
+        a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0;
+        chain_sweep<true, false>(p, a, mfd, red);
+      } else if (s == 1) {
+        a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0;
+        chain_sweep<false, false>(p, a, mfd, red);
+      } else if (s == 2) {
+        a.t_eval = t + g.h / 2.0; a.t_next = t + g.h; a.a = g.h; a.w = 2.0;
+        chain_sweep<false, false>(p, a, mfd, red);
+      } else {
+        a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
+        chain_sweep<false, true>(p, a, mfd, red);
+      }
+      /* ---- mean-field barrier without a barrier: every CTA publishes (partial sums, epoch tag) and every CTA waits for
+       * the tags of all CTAs, then adds the partials itself in a fixed order: three dependent L2 round trips, no atomics,
+       * and identical bits in every CTA.  Buffers alternate with the epoch parity (a CTA can be one epoch ahead at most). */
+      const size_t par = (size_t)(epoch & 1u);
+      const uint32_t tag = epoch + 1u;
+      double *part = g.partial + par * gridDim.x * NRED;
+      unsigned int *tags = g.bar + par * PERSIST_MAX_CTAS;
+      block_partial<PT>(red, part);                /* threads < NRED stored part[blockIdx][*] */
+      if (threadIdx.x < NRED) __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(tags + blockIdx.x, tag);
+      {
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+        for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += PT) {
+          unsigned long long spins = 0;
+          while (ld_acquire_u32(tags + b2) != tag) { if (++spins > (1ull << 28)) { if (g.abort_flag) *g.abort_flag = 1; break; } }
+#pragma unroll
+          for (int k = 0; k < NRED; k++) acc[k] += __ldcg(&part[(size_t)b2 * NRED + k]);
+        }
+        block_total<PT>(acc, s_tot);
+      }
+      if (g.nranks > 1) {
+        /* cross-GPU: CTA 0 stores this rank's sums and the tag straight into every peer's mailbox over NVLink; every CTA
+         * waits for the other ranks' tags in its own GPU's mailbox and adds the rank sums in rank order */
+        if (blockIdx.x == 0) {
+          if (threadIdx.x < NRED) {
+            for (int r = 0; r < g.nranks; r++)
+              if (r != g.rank) g.peer_box[r][(par * MAX_RANKS + g.rank) * NRED + threadIdx.x] = s_tot[threadIdx.x];
+            __threadfence_system();
+          }
+          __syncthreads();
+          if (threadIdx.x < g.nranks && threadIdx.x != g.rank) {
+            volatile uint32_t *f = g.peer_flag[threadIdx.x] + par * MAX_RANKS + g.rank;
+            *f = tag;
+          }
+        }
+        if (threadIdx.x < g.nranks && threadIdx.x != g.rank) {
+          volatile uint32_t *w = g.mailflag + par * MAX_RANKS + threadIdx.x;
+          unsigned long long spins = 0;
+          while (*w != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+          __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x < NRED) {
+          double v = 0.0;
+          for (int r = 0; r < g.nranks; r++)
+            v += (r == g.rank) ? s_tot[threadIdx.x] : __ldcv(&g.mailbox[(par * MAX_RANKS + r) * NRED + threadIdx.x]);
+          s_tot[threadIdx.x] = v;
+        }
+        __syncthreads();
+      }
+      epoch++;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < NRED) g.sums_new[threadIdx.x] = s_tot[threadIdx.x];
 }
 
 /* full RHS evaluation with outputs: aux, rates and (optionally) f into fout[nvar][cap] */

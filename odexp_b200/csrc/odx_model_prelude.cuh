@@ -53,11 +53,16 @@ ODX_HD void odx_sincos(double x, double *sp, double *cp) {
   pc = fma(z, pc, T[13]);
   pc = fma(z, pc, T[14]);
   pc = fma(z, pc, T[15]);
-  const double hz = 0.5 * z, w = 1.0 - hz;
-  const double c = w + (((1.0 - w) - hz) + z * (z * pc));
+  const double c = fma(z, fma(z, pc, -0.5), 1.0);
+  /* quadrant: swap for odd n, flip signs through the sign bit (integer pipe, not DADD on the FP64 pipe) */
   const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+#if defined(__CUDA_ARCH__)
+  *sp = __hiloint2double(__double2hiint(a) ^ ((n & 2) << 30), __double2loint(a));
+  *cp = __hiloint2double(__double2hiint(b) ^ (((n + 1) & 2) << 30), __double2loint(b));
+#else
   *sp = (n & 2) ? -a : a;
   *cp = ((n + 1) & 2) ? -b : b;
+#endif
 }
 
 /* STOPIF(cond): raise the stop flag, value is the condition (src/odexp.h:400-406) */

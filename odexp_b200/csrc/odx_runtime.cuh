@@ -72,6 +72,12 @@ struct odx_handle {
 #ifdef ODX_HAVE_NCCL_H
   ncclComm_t comm = nullptr;
 #endif
+  /* persistent step kernel + peer-memory exchange */
+  int use_persistent = 1, coop_ok = 0, coop_blocks = 0;
+  uint32_t epoch = 0;
+  void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
+  void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peers_attached = false;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   HostRand hr; bool hr_seeded = false; uint32_t host_draws = 0;   /* serial stream of the host loop (replay mode) */
@@ -116,8 +122,19 @@ static inline int grid_chain(const odx_handle *h, int64_t n) {      /* two parti
 constexpr bool NEEDS_MOMENTS = (NMFD > 0) || M::HAS_BIRTH;
 
 /* cross-GPU sum of the raw %M sums (and birth / rate sums): allreduce(SUM) of NRED doubles per RHS evaluation */
+static void fill_peer_args(odx_handle *h, struct odx::PersistArgs &g);
+__global__ void k_peer_allreduce(double *sums, int rank, int nranks, uint32_t epoch, double *mailbox, uint32_t *mailflag, PersistArgs g);
 static int post_reduce(odx_handle *h, int slot) {
   if (h->nranks <= 1) return ODX_SUCCESS;
+  if (h->peers_attached) {
+    PersistArgs g; memset(&g, 0, sizeof g);
+    fill_peer_args(h, g);
+    k_peer_allreduce<<<1, 64, 0, h->stream>>>(h->sums + (size_t)slot * NRED, h->rank, h->nranks, h->epoch, g.mailbox, g.mailflag, g);
+    h->launches++;
+    ODX_CUDA(h, cudaGetLastError());
+    h->epoch += 1;
+    return ODX_SUCCESS;
+  }
 #ifdef ODX_HAVE_NCCL_H
   double *s = h->sums + (size_t)slot * NRED;
   ncclResult_t r = g_nccl.AllReduce(s, s, NRED, ncclDouble, ncclSum, h->comm, h->stream);
@@ -192,9 +209,86 @@ static int do_rhs(odx_handle *h, double t, double hcur) {
   return eval_rhs_out(h, h->Y, h->y_slot, t, hcur, nullptr);
 }
 
+constexpr size_t MAIL_BOX_BYTES = sizeof(double) * 2 * MAX_RANKS * NRED;
+constexpr size_t MAIL_FLAG_BYTES = sizeof(uint32_t) * 2 * MAX_RANKS;
+constexpr size_t MAIL_BYTES = ((MAIL_BOX_BYTES + MAIL_FLAG_BYTES + sizeof(int) + 255) / 256) * 256;
+static inline double *mail_box(void *m) { return (double *)m; }
+static inline uint32_t *mail_flag(void *m) { return (uint32_t *)((char *)m + MAIL_BOX_BYTES); }
+static inline int *mail_abort(void *m) { return (int *)((char *)m + MAIL_BOX_BYTES + MAIL_FLAG_BYTES); }
+static int ensure_mail(odx_handle *h) {
+  if (h->mail) return ODX_SUCCESS;
+  ODX_CUDA(h, cudaMalloc(&h->mail, MAIL_BYTES));
+  ODX_CUDA(h, cudaMemset(h->mail, 0, MAIL_BYTES));
+  h->peer_mail[0] = h->mail;
+  return ODX_SUCCESS;
+}
+
+/* allreduce(SUM) of one sums slot through the peer mailboxes (same protocol and epoch counter as the persistent kernel) */
+__global__ void k_peer_allreduce(double *sums, int rank, int nranks, uint32_t epoch, double *mailbox, uint32_t *mailflag,
+                                 PersistArgs g) {
+  const uint32_t tag = epoch + 1u; const size_t par = (size_t)(epoch & 1u);
+  if (threadIdx.x < NRED) {
+    for (int r = 0; r < nranks; r++) g.peer_box[r][(par * MAX_RANKS + rank) * NRED + threadIdx.x] = sums[threadIdx.x];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < nranks) { volatile uint32_t *f = g.peer_flag[threadIdx.x] + par * MAX_RANKS + rank; *f = tag; }
+  __threadfence_system();
+  if (threadIdx.x < nranks) {
+    volatile uint32_t *f = mailflag + par * MAX_RANKS + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*f != tag) { __nanosleep(64); if (++spins > (1ull << 26)) { *g.abort_flag = 1; break; } }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+    for (int r = 0; r < nranks; r++) v += __ldcv(&mailbox[(par * MAX_RANKS + r) * NRED + threadIdx.x]);
+    sums[threadIdx.x] = v;
+  }
+}
+
+static void fill_peer_args(odx_handle *h, PersistArgs &g) {
+  g.rank = h->rank; g.nranks = h->nranks; g.epoch0 = h->epoch;
+  g.mailbox = h->mail ? mail_box(h->mail) : nullptr; g.mailflag = h->mail ? mail_flag(h->mail) : nullptr;
+  g.abort_flag = h->mail ? mail_abort(h->mail) : nullptr;
+  for (int r = 0; r < MAX_RANKS; r++) {
+    void *m = (r < h->nranks) ? (r == h->rank ? h->mail : h->peer_mail[r]) : nullptr;
+    g.peer_box[r] = m ? mail_box(m) : nullptr; g.peer_flag[r] = m ? mail_flag(m) : nullptr;
+  }
+}
+
+/* nsteps whole steps in one cooperative launch (see k_chain_persist) */
+static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64_t nsteps, int want_out_last) {
+  ODX_TRY(ensure_moments_Y(h, t0));
+  const int new_slot = h->y_slot ^ 1;
+  Pop p = pop_view(h);
+  PersistArgs g; memset(&g, 0, sizeof g);
+  g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index;
+  g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32 + BAR_WORDS; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
+  g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
+  fill_peer_args(h, g);
+  int64_t grid = (h->n + 2 * PT - 1) / (2 * PT);
+  if (grid > h->coop_blocks) grid = h->coop_blocks;
+  if (grid > PERSIST_MAX_CTAS) grid = PERSIST_MAX_CTAS;
+  if (grid < 1) grid = 1;
+  void *args[] = {(void *)&p, (void *)&g};
+  ODX_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_chain_persist, dim3((unsigned)grid), dim3(PT), args, 0, h->stream));
+  h->launches++;
+  h->epoch += (uint32_t)(nst * nsteps);
+  h->eval_index += (uint32_t)(2 * nst * nsteps); h->rhs_evals += (uint64_t)nst * nsteps;
+  h->report_slot = SLOT_STAGE;
+  h->rates_slot = new_slot; h->y_slot = new_slot; h->ymoments_valid = NEEDS_MOMENTS; h->k1_valid = false;
+  return ODX_SUCCESS;
+}
+static inline bool can_persist(const odx_handle *h) {
+  return h->use_persistent && h->coop_ok && !M::HAS_PAIR && !M::HAS_LOWRANK && (h->nranks == 1 || h->peers_attached);
+}
+
 /* one step of a chain method.  nst = 1: Euler (fe_apply); nst = 4: classic RK4 (dde_apply) */
 static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out) {
   if (h->n <= 0) return ODX_SUCCESS;
+  if (can_persist(h)) return chain_run_persist(h, nst, t, hh, 1, want_out);
   ODX_TRY(ensure_moments_Y(h, t));
   const int g = grid_chain(h, h->n);
   Pop p = pop_view(h);
@@ -370,6 +464,12 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chain<false, false>, BLOCK, 0));
   if (occ < 1) occ = 1;
   h->grid_cap = h->sm_count * occ;
+  {
+    int coop = 0, occp = 0;
+    ODX_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_chain_persist, PT, 0));
+    h->coop_ok = coop && occp > 0; h->coop_blocks = h->sm_count * occp;
+  }
   ODX_TRY(alloc_cols(h, &h->Y, NVAR)); ODX_TRY(alloc_cols(h, &h->YS, NVAR)); ODX_TRY(alloc_cols(h, &h->ACC, NVAR));
   ODX_TRY(alloc_cols(h, &h->E, NEXPR)); ODX_TRY(alloc_cols(h, &h->AUX, NAUX)); ODX_TRY(alloc_cols(h, &h->PSI, NPSI));
   ODX_TRY(alloc_cols(h, &h->DEATH, 1)); ODX_TRY(alloc_cols(h, &h->REPLI, 1));
@@ -378,9 +478,9 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   const odx_model_info *mi = odx_model();
   for (int k = 0; k < NPAR; k++) h->h_mu[k] = mi->par_defaults[k];
   ODX_CUDA(h, cudaMemcpyAsync(h->d_mu, h->h_mu, sizeof(double) * A1(NPAR), cudaMemcpyHostToDevice, h->stream));
-  ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * (h->grid_cap + 8)));
-  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * 4));
-  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * 4, h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * 2 * (h->grid_cap + h->coop_blocks + 8)));
+  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS)));
+  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS), h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->sums, sizeof(double) * NSLOT * NRED));
   ODX_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * NSLOT * NRED, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->rmax, sizeof(unsigned long long) * 2));
@@ -397,6 +497,8 @@ void odx_destroy(odx_handle *h) {
   if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
   odx_events_free(h);
+  for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
+  if (h->mail) cudaFree(h->mail);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
                     h->sums, h->stage_dev, h->gather};
   for (double *b : bufs) if (b) cudaFree(b);
@@ -413,6 +515,43 @@ void odx_destroy(odx_handle *h) {
 int odx_sync(odx_handle *h) {
   ODX_CUDA(h, cudaSetDevice(h->device));
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->mail) {
+    int ab = 0;
+    ODX_CUDA(h, cudaMemcpy(&ab, mail_abort(h->mail), sizeof ab, cudaMemcpyDeviceToHost));
+    if (ab) { h->err = "peer exchange timed out: a rank did not reach the mean-field barrier"; return ODX_EFAILED; }
+  }
+  return ODX_SUCCESS;
+}
+
+int odx_set_option(odx_handle *h, const char *name, double value) {
+  if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
+  h->err = std::string("odx_set_option: unknown option ") + name;
+  return ODX_EINVAL;
+}
+
+/* peer-memory exchange: every rank exports its mailbox, the caller distributes the 64-byte handles (all ranks, rank
+ * order) and every rank attaches to the others (cudaIpcOpenMemHandle; NVLink peer access is enabled lazily) */
+int odx_peer_export(odx_handle *h, void *handle64) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_TRY(ensure_mail(h));
+  cudaIpcMemHandle_t mh;
+  ODX_CUDA(h, cudaIpcGetMemHandle(&mh, h->mail));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  memcpy(handle64, &mh, 64);
+  return ODX_SUCCESS;
+}
+int odx_peer_attach(odx_handle *h, int rank, int nranks, const void *handles64) {
+  if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { h->err = "odx_peer_attach: bad rank / nranks"; return ODX_EINVAL; }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_TRY(ensure_mail(h));
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) { h->peer_mail[r] = h->mail; continue; }
+    cudaIpcMemHandle_t mh; memcpy(&mh, (const char *)handles64 + (size_t)r * 64, 64);
+    void *ptr = nullptr;
+    ODX_CUDA(h, cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mail[r] = ptr;
+  }
+  h->rank = rank; h->nranks = nranks; h->peers_attached = nranks > 1;
   return ODX_SUCCESS;
 }
 
@@ -640,6 +779,11 @@ int odx_dde_apply(odx_handle *h, double *t, double tnext, double *hstep, double 
 int odx_run_fixed(odx_handle *h, int method, double *t, double hstep, int64_t nsteps) {
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (method != ODX_METH_FE && method != ODX_METH_DDE) { h->err = "odx_run_fixed: fixed-step methods are fe and dde"; return ODX_EINVAL; }
+  if (can_persist(h) && h->n > 0 && nsteps > 0) {
+    ODX_TRY(chain_run_persist(h, method == ODX_METH_FE ? 1 : 4, *t, hstep, nsteps, 1));
+    *t += hstep * (double)nsteps;
+    return ODX_SUCCESS;
+  }
   for (int64_t s = 0; s < nsteps; s++) {
     ODX_TRY(chain_step(h, method == ODX_METH_FE ? 1 : 4, *t, hstep, s == nsteps - 1));
     *t += hstep;

@@ -20,16 +20,19 @@ def run(n=1 << 24, steps=100):
     from odexp_b200 import capi, build as b
     for tag in VARIANTS:
         lib = capi.ModelLib(b.lib_path("kuramoto_" + tag))
-        pop = capi.Population(lib, capacity=n)
-        pop.init(n, replay=False)
-        t = pop.run_fixed("dde", 0.0, 0.05, 10)
-        pop.sync()
-        best = 1e9
-        for rep in range(3):
-            pop.event_record(0); t = pop.run_fixed("dde", t, 0.05, steps); pop.event_record(1)
-            best = min(best, pop.event_elapsed_ms(0, 1) / steps)
-        print("%-8s %.4f ms/step  %.3e particle-steps/s  frac72=%.3f  mfd=%s" % (tag, best, n / (best * 1e-3), 72.0 * n / (best * 1e-3) / 6550.4e9, pop.meanfields()))
-        pop.close()
+        for persistent in (1, 0):
+            pop = capi.Population(lib, capacity=n)
+            pop.set_option("persistent", persistent)
+            pop.init(n, replay=False)
+            t = pop.run_fixed("dde", 0.0, 0.05, 10)
+            pop.sync()
+            best = 1e9
+            for rep in range(3):
+                pop.event_record(0); t = pop.run_fixed("dde", t, 0.05, steps); pop.event_record(1)
+                best = min(best, pop.event_elapsed_ms(0, 1) / steps)
+            print("%-8s persistent=%d %.4f ms/step  %.3e particle-steps/s  frac72=%.3f  mfd=%s" % (
+                tag, persistent, best, n / (best * 1e-3), 72.0 * n / (best * 1e-3) / 6550.4e9, pop.meanfields()))
+            pop.close()
 
 
 if __name__ == "__main__":
