@@ -156,7 +156,9 @@ def main():
 
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop"))
     n_total = args.n
-    n_local = n_total // world
+    from odexp_b200.dist import shard_range
+    lo, hi = shard_range(n_total, rank, world)
+    n_local = hi - lo
     pop = capi.Population(lib, capacity=n_local, device=local)
     if world > 1:
         from odexp_b200 import dist as odist
@@ -226,9 +228,14 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(8 * lib.nmfd),
                         "steps": ne2e, "what": "odx_pop_upload(host theta, omega) + odx_run_fixed(dde, 1 step) + odx_meanfields per step"},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             # dram__bytes_read.sum + dram__bytes_write.sum of k_chain_persist from the ncu --set full capture
+                             # profiles/r1_k_chain_persist_kuramoto_n16M.txt: 56.60 GB for 20 steps at N=2^24 = 168.7 B per particle-step
+                             "traffic": (168.7 * n_local * args.steps) if (world == 1 and n_total == N_TOTAL) else None,
+                             "traffic_unit": "bytes per launch (one cooperative launch = all timed steps)",
                              "peak_source": how, "algorithmic_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP,
-                             "kernel": "k_chain<*> (4 stage launches per RK4 step; bytes and time are per step)"}}
+                             "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_local * args.steps,
+                             "kernel": "k_chain_persist (one cooperative launch runs all timed RK4 steps: 4 stages per step, in-kernel mean-field exchange)"}}
         if world == 1 and not args.no_cpu:
             v, info = cpu_reference_sample(1 << 20, 16)
             line["cpu_baseline"] = dict(info, value=v, unit="particle-steps/s")

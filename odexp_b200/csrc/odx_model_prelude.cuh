@@ -65,6 +65,9 @@ ODX_HD void odx_sincos(double x, double *sp, double *cp) {
 #endif
 }
 
+/* branch-free conditional emitted for `c ? a : b` in model functions (both arms are pure) */
+ODX_HD double odx_sel(bool c, double a, double b) { return c ? a : b; }
+
 /* STOPIF(cond): raise the stop flag, value is the condition (src/odexp.h:400-406) */
 template <class C> ODX_HD int odx_stopif(C &c, int cond) { if (cond) c.stop = 1; return cond; }
 

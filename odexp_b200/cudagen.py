@@ -75,6 +75,54 @@ def _pow_peephole(expr: str) -> str:
     return expr
 
 
+def _strip_outer_parens(e):
+    e = e.strip()
+    while e.startswith("(") and e.endswith(")"):
+        depth = 0
+        for i, ch in enumerate(e):
+            depth += ch == "("
+            depth -= ch == ")"
+            if depth == 0 and i < len(e) - 1:
+                return e
+        e = e[1:-1].strip()
+    return e
+
+
+def _ternary_to_select(expr: str) -> str:
+    """`c ? a : b` (whole expression) -> odx_sel(c, a, b): both arms are evaluated, the result is a select.
+    On the GPU this removes a divergent branch per use and lets the compiler share sub-expressions between several
+    guarded terms (the N-body fixture guards each force component separately around the same r^3).  Only applied when
+    neither arm draws random numbers or raises STOPIF (evaluating those eagerly would change behaviour)."""
+    e = _strip_outer_parens(expr)
+    depth, q = 0, -1
+    for i, ch in enumerate(e):
+        depth += ch in "(["
+        depth -= ch in ")]"
+        if ch == "?" and depth == 0:
+            q = i
+            break
+    if q < 0:
+        return expr
+    depth, nest, c = 0, 0, -1
+    for i in range(q + 1, len(e)):
+        ch = e[i]
+        depth += ch in "(["
+        depth -= ch in ")]"
+        if depth == 0 and ch == "?":
+            nest += 1
+        elif depth == 0 and ch == ":":
+            if nest == 0:
+                c = i
+                break
+            nest -= 1
+    if c < 0:
+        return expr
+    cond, a, b = e[:q].strip(), e[q + 1:c].strip(), e[c + 1:].strip()
+    if re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF)\b", a + " " + b):
+        return expr
+    return "odx_sel(%s, %s, %s)" % (cond, _ternary_to_select(a), _ternary_to_select(b))
+
+
 class Emitter:
     def __init__(self, m: PopModel, fast_pow: bool = True):
         self.m = m
@@ -194,7 +242,7 @@ class Emitter:
         w("")
         for f in m.funs:
             args = ", ".join("double %s" % mangle(a) for a in f.args)
-            body = _mangle_expr(_pow_peephole(f.body) if self.fast_pow else f.body)
+            body = _mangle_expr(_ternary_to_select(_pow_peephole(f.body) if self.fast_pow else f.body))
             w("ODX_HD double %s(%s) { return %s; }" % (mangle(f.name), args, body))
         w("")
         w("struct OdxModel {")
