@@ -480,7 +480,7 @@ constexpr int PERSIST_MAX_CTAS = 1024;
 #define PERSIST_THREADS 1024
 #endif
 constexpr int PT = PERSIST_THREADS;
-__global__ void __launch_bounds__(PT, 4096 / PT / (4 / CHAIN_MIN_BLOCKS > 0 ? 4 / CHAIN_MIN_BLOCKS : 1)) k_chain_persist(Pop p, PersistArgs g) {
+__global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_persist(Pop p, PersistArgs g) {
   __shared__ double s_tot[NRED];
   double mfd[A1(NMFD)];
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;

@@ -2,6 +2,9 @@
  * entry points declared in include/odx.h.  Included by odx_engine.cuh (one instantiation per model). */
 #pragma once
 #include <dlfcn.h>
+#ifdef ODX_MODEL_HAS_LOWRANK
+#include "odx_lowrank.cuh"
+#endif
 #if __has_include(<nccl.h>)
 #include <nccl.h>
 #define ODX_HAVE_NCCL_H 1
@@ -78,6 +81,9 @@ struct odx_handle {
   void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_attached = false;
+  /* low-rank coupling scratch + options (opt lrmax / lrabstol / lrreltol) */
+  void *lr_plan = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr;
+  int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   HostRand hr; bool hr_seeded = false; uint32_t host_draws = 0;   /* serial stream of the host loop (replay mode) */
@@ -151,8 +157,42 @@ static int launch_check(odx_handle *h) {
   return ODX_SUCCESS;
 }
 
+#ifdef ODX_MODEL_HAS_LOWRANK
+/* lrwpkern on the device (see odx_lowrank.cuh); writes PSI[LR0_PSI] */
+static int compute_lowrank(odx_handle *h, const double *ysrc) {
+  if (h->nranks > 1) { h->err = "low-rank %C coupling is single-GPU in this build"; return ODX_EUNSUP; }
+  const int64_t n = h->n;
+  if (n <= 0) return ODX_SUCCESS;
+  int nblk = (int)((n + LR_MTILE - 1) / LR_MTILE);
+  if (nblk > h->grid_cap) nblk = h->grid_cap;
+  if (!h->lr_plan) {
+    ODX_CUDA(h, cudaMalloc(&h->lr_plan, sizeof(LrPlan)));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 4));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_spart, sizeof(double) * 3 * (h->grid_cap + 1)));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (h->grid_cap + 1)));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
+  }
+  const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
+  k_lr_stats<<<grid_for(h, n), BLOCK, 0, h->stream>>>(x, n, h->lr_spart, h->counter + 1, h->lr_stats);
+  ODX_TRY(launch_check(h));
+  k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, (LrPlan *)h->lr_plan);
+  ODX_TRY(launch_check(h));
+  k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
+  ODX_TRY(launch_check(h));
+  k_lr_moments_sum<<<(LR_R * LR_P1 + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(h->lr_apart, nblk, h->lr_A);
+  ODX_TRY(launch_check(h));
+  int ga = (int)((n + 127) / 128); if (ga > 4 * h->sm_count) ga = 4 * h->sm_count;
+  k_lr_apply<<<ga, 128, 0, h->stream>>>(x, h->E + (size_t)M::LR0_U * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_A,
+                                        h->PSI + (size_t)M::LR0_PSI * h->cap);
+  return launch_check(h);
+}
+#endif
+
 /* psi for the state in ysrc (all-pairs %C).  Multi-GPU: allgather of the coupled columns first. */
 static int compute_psi(odx_handle *h, const double *ysrc, double t) {
+#ifdef ODX_MODEL_HAS_LOWRANK
+  ODX_TRY(compute_lowrank(h, ysrc));
+#endif
   if (!M::HAS_PAIR) return ODX_SUCCESS;
   Pop p = pop_view(h);
   const double *jy = ysrc, *je = h->E; const int32_t *jid = h->ID; int64_t jstride = h->cap, nj = h->n;
@@ -497,6 +537,8 @@ void odx_destroy(odx_handle *h) {
   if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
   odx_events_free(h);
+  if (h->lr_plan) cudaFree(h->lr_plan);
+  { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
@@ -525,6 +567,9 @@ int odx_sync(odx_handle *h) {
 
 int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
+  if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }
+  if (strcmp(name, "lrabstol") == 0) { h->lr_abstol = value; return ODX_SUCCESS; }
+  if (strcmp(name, "lrreltol") == 0) { h->lr_reltol = value; return ODX_SUCCESS; }
   h->err = std::string("odx_set_option: unknown option ") + name;
   return ODX_EINVAL;
 }

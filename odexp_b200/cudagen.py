@@ -367,6 +367,12 @@ class Emitter:
         w("    return mi;")
         w("  }")
         w("};\n")
+        if lr_cpls:
+            if len(lr_cpls) > 1:
+                raise PopError("only one low-rank coupling per model is supported")
+            if lr_cpls[0].lowrank["kind"] != "lrwexp":
+                raise PopError("%C ... lrexp (unweighted) is not supported yet; use lrwexp with U = V = 1")
+            w("#define ODX_MODEL_HAS_LOWRANK 1")
         w('#include "odx_engine.cuh"')
         return "\n".join(L) + "\n"
 

@@ -20,7 +20,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("ODX_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 LIB_SRCS = ["main", "methods_odexp", "datastruct", "loader", "options", "rand_gen", "utils_odexp", "lrexp"]
-CFLAGS = ["-std=gnu99", "-O3", "-D_GNU_SOURCE", "-w", "-I" + os.path.join(HERE, "stubinc"),
+# _FORTIFY_SOURCE off: the reference's loader passes over-stated buffer lengths to snprintf/strncat for array entries
+# (`expr U[i=0:R] ...`); harmless on its macOS target, aborted by glibc's fortified variants
+CFLAGS = ["-std=gnu99", "-O3", "-D_GNU_SOURCE", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-w", "-I" + os.path.join(HERE, "stubinc"),
           "-I" + os.path.join(REF, "src"), "-include", "errno.h", "-include", "gsl/gsl_errno.h"]
 
 

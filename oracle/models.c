@@ -73,10 +73,37 @@ static void vdp_ic(orc_ctx *c, double t, double *y, double *e) {
   y[1] = c->atbirth ? 2.0 : (c->sister == NULL ? 0.0 : c->sister->y[1]);      /* BR(2.0, SY(x)) */
 }
 
+/* ---------------------------------------------------------------- kuramoto_lowrank.pop (LET R 8, LET N 256) */
+#define LPI 3.141592653589793
+#define LR_R 8
+static const double klr_pars[] = {0.5};
+static void klr_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                    double *aux, double *death, double *repli) {
+  const double K = c->mu[0], omega = e[0], theta = y_[0], CPL = psi[0];
+  const double y = sin(theta);
+  const double cpl = CPL;
+  (void)t; (void)mfd; (void)death; (void)repli;
+  f[0] = omega + K / 256 * CPL;
+  aux[0] = y; aux[1] = cpl;
+}
+static double klr_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)e; (void)aux; (void)mfd;
+  return k == 0 ? sin(y[0]) : cos(y[0]);
+}
+static void klr_ic(orc_ctx *c, double t, double *y, double *e) {
+  int i;
+  (void)t;
+  e[0] = orc_randN(c, 2 * LPI / 10.0, 0.1);
+  for (i = 0; i < LR_R; i++) e[1 + i] = orc_rand01(c);
+  for (i = 0; i < LR_R; i++) e[1 + LR_R + i] = orc_rand01(c);
+  y[0] = 2 * LPI * orc_rand01(c);
+}
+
 static const orc_model MODELS[] = {
-  {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic},
-  {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic},
-  {"vdp_sde", 2, 0, 0, 0, 0, 4, vdp_pars, vdp_rhs, NULL, vdp_birth, NULL, vdp_ic},
+  {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic, 0, 0, 0, 0, 0, NULL},
+  {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic, 0, 0, 0, 0, 0, NULL},
+  {"vdp_sde", 2, 0, 0, 0, 0, 4, vdp_pars, vdp_rhs, NULL, vdp_birth, NULL, vdp_ic, 0, 0, 0, 0, 0, NULL},
+  {"kuramoto_lowrank", 1, 1 + 2 * LR_R, 2, 1, 2, 1, klr_pars, klr_rhs, klr_mfd, NULL, NULL, klr_ic, LR_R, 0, 0, 1, 1 + LR_R, sin},
 };
 const orc_model *orc_find_model(const char *name) {
   unsigned i;

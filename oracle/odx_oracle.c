@@ -164,6 +164,7 @@ int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
     memcpy(p->y, y_ + (size_t)i * m->nvar, sizeof(double) * m->nvar);
     if (m->birth_term) s->pop_birth_rate += m->birth_term(&c, p->y, p->expr, p->aux);
   }
+  if (m->lr_rank > 0) orc_lowrank_apply(s);      /* low-rank coupling between pass 1 and the mean fields (src/odexp:841) */
   /* one walk per mean field, summed in list order, then divided by POP_SIZE */
   for (k = 0; k < m->nmfd; k++) {
     for (i = 0; i < s->n; i++) { orc_par *p = s->p[i]; rhs_ctx(s, &c, p); s->mfd[k] += m->mfd_term(&c, k, p->y, p->expr, p->aux, s->mfd); }

@@ -42,6 +42,9 @@ typedef struct {
   double (*birth_term)(orc_ctx *c, const double *y, const double *e, const double *aux);
   void (*cpl_terms)(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi);
   void (*ic)(orc_ctx *c, double t, double *y, double *e);
+  /* low-rank %C ... lrwexp {var, fun, U, V, rank}: lr_rank == 0 means none */
+  int lr_rank, lr_psi, lr_var, lr_iu, lr_iv;
+  double (*lr_fun)(double);
 } orc_model;
 
 typedef struct {
@@ -68,7 +71,9 @@ typedef struct orc_sim {
   FILE *fstats, *ftraj;
   int rng_mode; orc_hostrand hr; uint32_t k0, k1, eval_index, host_draws, event_index;
   uint64_t rhs_evals; int64_t steps; double particle_steps, function_ms;
+  int lr_last_p;
 } orc_sim;
+void orc_lowrank_apply(orc_sim *s);
 
 double orc_rand01(orc_ctx *c);
 double orc_randN(orc_ctx *c, double mu, double sigma);

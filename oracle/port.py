@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4}
 DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0),
-        "vdp_sde": dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0)}
+        "vdp_sde": dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0),
+        "kuramoto_lowrank": dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=17)}
 
 
 class Opts(C.Structure):
@@ -29,11 +30,11 @@ class Report(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("odx_oracle.c", "models.c", "minigsl.c", "odx_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("odx_oracle.c", "models.c", "minigsl.c", "lowrank.c", "odx_oracle.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.run(["gcc", "-std=gnu99", "-O3", "-fPIC", "-Wall", "-Wno-unused-parameter", "-I" + os.path.join(HERE, "stubinc"),
-                    "-I" + HERE, "-shared"] + srcs[:3] + ["-lm", "-o", LIB], check=True)
+                    "-I" + HERE, "-shared"] + srcs[:4] + ["-lm", "-o", LIB], check=True)
     return LIB
 
 

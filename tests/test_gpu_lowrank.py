@@ -1,0 +1,50 @@
+"""GPU parity for the low-rank %C coupling (config 3) against the CPU restatement of src/lrexp.c (oracle/lowrank.c,
+itself bit-identical to the unchanged reference binary on this fixture, tests/test_oracle_port.py).
+
+Tolerance: the expansion converts a Chebyshev fit to the monomial basis (integer coefficients up to ~1e11 at the order
+selected here, alternating signs), so round-off differences between the serial CPU sums and the blocked GPU sums are
+amplified; psi agrees to 1e-8 relative to its scale, the state to 1e-10."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("meth,ps,ts,res", [("dde", 256, (0, 0.4), 3), ("fe", 1000, (0, 0.2), 2), ("rkck", 300, (0, 1.0), 3)])
+def test_lowrank_matches_restatement(model_lib, meth, ps, ts, res):
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto_lowrank")
+    opts = {"meth": meth, "h0": 0.05 if meth == "fe" else 0.1, "res": res, "ps": ps}
+    pop = capi.Population(lib, capacity=max(1024, ps))
+    out = capi.odesolver(pop, ts, meth=meth, res=res, popsize=ps, h0=opts["h0"], replay_ic=True)
+    pop.close()
+    ref = port.run("kuramoto_lowrank", opts, ts)
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb)
+    np.testing.assert_array_equal(ta["id"], tb["id"])
+    first_a, first_b = ta[ta["step"] == 0]["cols"], tb[tb["step"] == 0]["cols"]
+    np.testing.assert_array_equal(first_a[:, 0], first_b[:, 0])              # theta0: replayed libc stream
+    np.testing.assert_array_equal(first_a[:, 6:], first_b[:, 6:])            # omega, U[0:8], V[0:8]
+    psi_a, psi_b = ta["cols"][:, 3], tb["cols"][:, 3]
+    scale = np.abs(psi_b).max()
+    print("max |dpsi|/scale", np.abs(psi_a - psi_b).max() / scale, "max rel dtheta", (np.abs(ta["cols"][:, 0] - tb["cols"][:, 0]) / np.abs(tb["cols"][:, 0])).max())
+    assert np.abs(psi_a - psi_b).max() <= 1e-8 * scale
+    np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)
+
+
+def test_lowrank_matches_direct_sum(model_lib):
+    """independent check of the expansion itself: psi_i vs the O(N^2) sum_j (U_i.V_j) sin(x_j - x_i) in numpy"""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto_lowrank")
+    n = 512
+    pop = capi.Population(lib, capacity=1024)
+    pop.init(n, replay=True)
+    pop.rhs(0.0)
+    d = pop.download()
+    x, U, V, psi = d["y"][:, 0], d["expr"][:, 1:9], d["expr"][:, 9:17], d["psi"][:, 0]
+    direct = ((U @ V.T) * np.sin(x[None, :] - x[:, None])).sum(axis=1)
+    pop.close()
+    # lrabstol / lrreltol = 1e-6 of the reference bound the truncation error of the expansion
+    assert np.abs(psi - direct).max() <= 1e-4 * np.abs(direct).max()

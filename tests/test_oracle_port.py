@@ -37,6 +37,9 @@ REF_CASES = [
     ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 21, "ps": 50, "ssahmin": 0.0}, (0, 4)),
     ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 51, "ps": 100, "ssahmin": 1.0}, (0, 5)),
     ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 11, "ps": 1, "ssahmin": 1.0, "seed": 7}, (0, 5)),     # tiny population
+    # low-rank %C coupling (src/lrexp.c): restated lrexpars / lrexprank / lrexpwp
+    ("kuramoto_lowrank", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 256}, (0, 0.4)),
+    ("kuramoto_lowrank", {"meth": "rkck", "res": 3, "ps": 300}, (0, 1.0)),
 ]
 
 
