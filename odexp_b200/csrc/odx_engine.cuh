@@ -601,55 +601,77 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
   if (M::HAS_DEATH || M::HAS_REPLI) grid_reduce<NRED>(red, r);
 }
 
-/* O(N^2) %C coupling: psi_k(i) = (1/POP_SIZE) sum_j expr_k(i,j), j in list order (src/odexp:922-950).
- * i-particles live in registers (one per thread), j-particles are staged through shared memory in tiles
- * of TJ and broadcast to the whole block; arithmetic is FP64 on the CUDA cores. */
-constexpr int PAIR_TJ = 256;
+/* O(N^2) %C coupling: psi_k(i) = (1/POP_SIZE) sum_j expr_k(i,j) (src/odexp:922-950).
+ * Grid = (i-tiles of 256 particles) x (j-segments).  Two i-particles per thread live in registers (two independent FP64
+ * dependency chains), j-particles are staged through shared memory in tiles of PAIR_TJ and broadcast to the CTA.  Every
+ * CTA writes the raw partial sums of its (i-tile, j-segment); k_pair_finish adds the segments in ascending j order and
+ * divides by POP_SIZE, so the result is deterministic and the j-segments of other GPUs (allgathered columns) are just
+ * more segments.  Arithmetic is FP64 FMA on the CUDA cores. */
+constexpr int PAIR_THREADS = 128, PAIR_ITILE = 256, PAIR_TJ = 128;
 constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);
-__global__ void __launch_bounds__(BLOCK) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
-                                                const double *__restrict__ je, const int32_t *__restrict__ jid,
-                                                int64_t jstride, int64_t nj, double t, double *__restrict__ psi_out) {
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
+                                                       const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
+                                                       int64_t nj, double t, double *__restrict__ part, int seg_base) {
   __shared__ double s_col[A1(PAIR_NCOL)][PAIR_TJ];
   __shared__ int32_t s_id[PAIR_TJ];
-  for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < p.n; base += (int64_t)gridDim.x * BLOCK) {
-    const int64_t i = base + threadIdx.x;
-    const bool live = i < p.n;
-    const int64_t ii = live ? i : p.n - 1;
-    double y[A1(NVAR)], e[A1(NEXPR)], aux[A1(NAUX)], acc[A1(NPSI)];
-    load_cols<NVAR>(ysrc, p.stride, ii, y);
-    load_cols<NEXPR>(p.E, p.stride, ii, e);
+  /* this CTA's j-range: segment blockIdx.y of gridDim.y, boundaries aligned to the j-tile */
+  const int64_t tiles = (nj + PAIR_TJ - 1) / PAIR_TJ;
+  const int64_t tps = (tiles + gridDim.y - 1) / gridDim.y;
+  const int64_t jbeg = (int64_t)blockIdx.y * tps * PAIR_TJ;
+  int64_t jend = jbeg + tps * PAIR_TJ; if (jend > nj) jend = nj;
+  const int64_t ia = (int64_t)blockIdx.x * PAIR_ITILE + threadIdx.x, ib = ia + PAIR_THREADS;
+  const bool la = ia < p.n, lb = ib < p.n;
+  const int64_t ja = la ? ia : p.n - 1, jb = lb ? ib : p.n - 1;
+  double ya[A1(NVAR)], ea[A1(NEXPR)], yb[A1(NVAR)], eb[A1(NEXPR)], aux[A1(NAUX)], acca[A1(NPSI)], accb[A1(NPSI)];
+  load_cols<NVAR>(ysrc, p.stride, ja, ya); load_cols<NEXPR>(p.E, p.stride, ja, ea);
+  load_cols<NVAR>(ysrc, p.stride, jb, yb); load_cols<NEXPR>(p.E, p.stride, jb, eb);
 #pragma unroll
-    for (int k = 0; k < A1(NPSI); k++) acc[k] = 0.0;
-    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[ii] : 0);
-    for (int64_t j0 = 0; j0 < nj; j0 += PAIR_TJ) {
-      const int tj = (int)((nj - j0) < PAIR_TJ ? (nj - j0) : PAIR_TJ);
-      __syncthreads();
-      for (int jj = threadIdx.x; jj < tj; jj += BLOCK) {
+  for (int k = 0; k < A1(NPSI); k++) { acca[k] = 0.0; accb[k] = 0.0; }
+  DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[ja] : 0);
+  DevCtx cb = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[jb] : 0);
+  for (int64_t j0 = jbeg; j0 < jend; j0 += PAIR_TJ) {
+    const int tj = (int)((jend - j0) < PAIR_TJ ? (jend - j0) : PAIR_TJ);
+    __syncthreads();
+    for (int jj = threadIdx.x; jj < tj; jj += PAIR_THREADS) {
 #pragma unroll
-        for (int v = 0; v < NVAR; v++) s_col[v][jj] = jy[(int64_t)v * jstride + j0 + jj];
-        if (M::CPL_USES_EXPR) {
+      for (int v = 0; v < NVAR; v++) s_col[v][jj] = jy[(int64_t)v * jstride + j0 + jj];
+      if (M::CPL_USES_EXPR) {
 #pragma unroll
-          for (int v = 0; v < NEXPR; v++) s_col[NVAR + v][jj] = je[(int64_t)v * jstride + j0 + jj];
-        }
-        s_id[jj] = jid[j0 + jj];
+        for (int v = 0; v < NEXPR; v++) s_col[NVAR + v][jj] = je[(int64_t)v * jstride + j0 + jj];
       }
-      __syncthreads();
-#pragma unroll 4
-      for (int jj = 0; jj < tj; jj++) {
-        double oy[A1(NVAR)], oe[A1(NEXPR)];
-#pragma unroll
-        for (int v = 0; v < NVAR; v++) oy[v] = s_col[v][jj];
-        if (M::CPL_USES_EXPR) {
-#pragma unroll
-          for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
-        }
-        c.oid = s_id[jj];
-        M::cpl_terms(c, t, y, e, aux, oy, oe, aux, acc);
-      }
+      if (M::NEEDS_ID) s_id[jj] = jid[j0 + jj];
     }
-    if (live) {
+    __syncthreads();
+#pragma unroll 2
+    for (int jj = 0; jj < tj; jj++) {
+      double oy[A1(NVAR)], oe[A1(NEXPR)];
 #pragma unroll
-      for (int k = 0; k < NPSI; k++) psi_out[(int64_t)k * p.stride + i] = acc[k] / p.n_global;
+      for (int v = 0; v < NVAR; v++) oy[v] = s_col[v][jj];
+      if (M::CPL_USES_EXPR) {
+#pragma unroll
+        for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
+      }
+      if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
+      M::cpl_terms(ca, t, ya, ea, aux, oy, oe, aux, acca);
+      M::cpl_terms(cb, t, yb, eb, aux, oy, oe, aux, accb);
+    }
+  }
+  double *dst = part + (size_t)(seg_base + blockIdx.y) * A1(NPSI) * p.stride;
+#pragma unroll
+  for (int k = 0; k < NPSI; k++) {
+    if (la) dst[(int64_t)k * p.stride + ia] = acca[k];
+    if (lb) dst[(int64_t)k * p.stride + ib] = accb[k];
+  }
+}
+/* psi = (sum over segments, ascending j) / POP_SIZE; only the pairwise couplings are touched (a low-rank psi keeps its column) */
+__global__ void __launch_bounds__(BLOCK) k_pair_finish(Pop p, const double *__restrict__ part, int nseg, double *__restrict__ psi) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+#pragma unroll
+    for (int k = 0; k < NPSI; k++) {
+      if (!M::psi_is_pairwise(k)) continue;
+      double a = 0.0;
+      for (int s2 = 0; s2 < nseg; s2++) a += part[((size_t)s2 * A1(NPSI) + k) * p.stride + i];
+      psi[(int64_t)k * p.stride + i] = a / p.n_global;
     }
   }
 }

@@ -64,6 +64,8 @@ struct odx_handle {
   double *h_pin = nullptr;                 /* pinned scratch: NSLOT*NRED doubles + 8 */
   double *stage_dev = nullptr; size_t stage_bytes = 0;   /* AoS staging for upload / download */
   double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
+  double *pair_part = nullptr; size_t pair_part_len = 0;                             /* [segment][npsi][cap] raw partial sums of k_pair */
+  int64_t all_n[MAX_RANKS] = {0, 0, 0, 0, 0, 0, 0, 0};                               /* particles per rank */
   int sm_count = 148, grid_cap = 148 * 8;
   uint32_t k0 = 3141592u, k1 = 0u;
   uint32_t eval_index = 0;
@@ -194,30 +196,63 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
   ODX_TRY(compute_lowrank(h, ysrc));
 #endif
   if (!M::HAS_PAIR) return ODX_SUCCESS;
+  if (h->n <= 0) return ODX_SUCCESS;
   Pop p = pop_view(h);
-  const double *jy = ysrc, *je = h->E; const int32_t *jid = h->ID; int64_t jstride = h->cap, nj = h->n;
+  const int itiles = (int)((h->n + PAIR_ITILE - 1) / PAIR_ITILE);
+  /* enough CTAs to fill the GPU about 8 deep: split the j-range of every source segment */
+  int js = (8 * h->sm_count + itiles - 1) / itiles;
+  if (js < 1) js = 1;
+  if (js > 64) js = 64;
+  const int nsrc = h->nranks > 1 ? h->nranks : 1;
+  const size_t need = (size_t)nsrc * js * A1(NPSI) * h->cap;
+  if (h->pair_part_len < need) {
+    if (h->pair_part) cudaFree(h->pair_part);
+    h->pair_part = nullptr; h->pair_part_len = 0;
+    ODX_CUDA(h, cudaMalloc((void **)&h->pair_part, sizeof(double) * need));
+    h->pair_part_len = need;
+  }
+  if (h->nranks <= 1) {
+    k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, ysrc, h->E, h->ID, h->cap, h->n, t, h->pair_part, 0);
+    ODX_TRY(launch_check(h));
+  } else {
 #ifdef ODX_HAVE_NCCL_H
-  if (h->nranks > 1) {
-    /* equal shards are required for the gathered layout [rank][col][n] -> handled as nranks j-segments */
-    const int64_t n = h->n; const int ncol = PAIR_NCOL;
-    if (h->gather_cap < n) { h->err = "gather buffer too small"; return ODX_EFAILED; }
-    /* pack local columns contiguously [ncol][n] then allgather -> [rank][ncol][n] */
-    double *sendbuf = h->gather + (size_t)h->nranks * ncol * h->gather_cap;
+    /* allgather of the coupled columns (nvar[+nexpr] x N doubles per RHS evaluation) into [rank][col][nmax] + ids, then one
+     * launch per source rank in rank order = global list order */
+    if (!h->comm) { h->err = "multi-GPU %C needs odx_comm_init (NCCL allgather)"; return ODX_ENCCL; }
+    int64_t nmax = 0;
+    for (int r = 0; r < h->nranks; r++) nmax = h->all_n[r] > nmax ? h->all_n[r] : nmax;
+    const int ncol = PAIR_NCOL;
+    if (h->gather_cap < nmax) {
+      if (h->gather) cudaFree(h->gather);
+      if (h->gather_id) cudaFree(h->gather_id);
+      h->gather = nullptr; h->gather_id = nullptr; h->gather_cap = 0;
+      ODX_CUDA(h, cudaMalloc((void **)&h->gather, sizeof(double) * (size_t)(h->nranks + 1) * ncol * nmax));
+      ODX_CUDA(h, cudaMalloc((void **)&h->gather_id, sizeof(int32_t) * (size_t)(h->nranks + 1) * nmax));
+      h->gather_cap = nmax;
+    }
+    double *sendbuf = h->gather + (size_t)h->nranks * ncol * nmax;
+    int32_t *sendid = h->gather_id + (size_t)h->nranks * nmax;
     for (int c = 0; c < NVAR; c++)
-      ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)c * n, ysrc + (size_t)c * h->cap, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)c * nmax, ysrc + (size_t)c * h->cap, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (M::CPL_USES_EXPR)
       for (int c = 0; c < NEXPR; c++)
-        ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)(NVAR + c) * n, h->E + (size_t)c * h->cap, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    ncclResult_t r = g_nccl.AllGather(sendbuf, h->gather, (size_t)ncol * n, ncclDouble, h->comm, h->stream);
+        ODX_CUDA(h, cudaMemcpyAsync(sendbuf + (size_t)(NVAR + c) * nmax, h->E + (size_t)c * h->cap, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(sendid, h->ID, h->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllGather(sendbuf, h->gather, (size_t)ncol * nmax, ncclDouble, h->comm, h->stream);
     if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
-    r = g_nccl.AllGather(h->ID, h->gather_id, (size_t)n, ncclInt32, h->comm, h->stream);
+    r = g_nccl.AllGather(sendid, h->gather_id, (size_t)nmax, ncclInt32, h->comm, h->stream);
     if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
-    /* accumulate rank segments in rank order = global list order */
-    ODX_CUDA(h, cudaMemsetAsync(h->PSI, 0, sizeof(double) * A1(NPSI) * h->cap, h->stream));
-    h->err = "multi-GPU %C: segment accumulation not implemented in this build"; return ODX_EUNSUP;
-  }
+    for (int src = 0; src < h->nranks; src++) {
+      const double *gy = h->gather + (size_t)src * ncol * nmax;
+      k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, gy, gy + (size_t)NVAR * nmax, h->gather_id + (size_t)src * nmax, nmax,
+                                                               h->all_n[src], t, h->pair_part, src * js);
+      ODX_TRY(launch_check(h));
+    }
+#else
+    h->err = "built without nccl.h"; return ODX_ENCCL;
 #endif
-  k_pair<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, jy, je, jid, jstride, nj, t, h->PSI);
+  }
+  k_pair_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, h->pair_part, nsrc * js, h->PSI);
   return launch_check(h);
 }
 
@@ -542,7 +577,7 @@ void odx_destroy(odx_handle *h) {
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
-                    h->sums, h->stage_dev, h->gather};
+                    h->sums, h->stage_dev, h->gather, h->pair_part};
   for (double *b : bufs) if (b) cudaFree(b);
   if (h->ID) cudaFree(h->ID);
   if (h->gather_id) cudaFree(h->gather_id);
@@ -642,7 +677,7 @@ int odx_comm_init(odx_handle *h, int rank, int nranks, const void *uid128) {
 
 /* global population size / offsets after any change of the local size (allreduce over ranks) */
 static int refresh_global_n(odx_handle *h) {
-  h->n_global = (double)h->n; h->n_before = 0;
+  h->n_global = (double)h->n; h->n_before = 0; h->all_n[0] = h->n;
 #ifdef ODX_HAVE_NCCL_H
   if (h->nranks > 1) {
     /* allgather of the per-rank sizes through a tiny device buffer */
@@ -659,7 +694,7 @@ static int refresh_global_n(odx_handle *h) {
     ODX_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaFree(buf);
     double tot = 0; int64_t before = 0;
-    for (int r2 = 0; r2 < h->nranks; r2++) { tot += (double)all[r2]; if (r2 < h->rank) before += (int64_t)all[r2]; }
+    for (int r2 = 0; r2 < h->nranks; r2++) { tot += (double)all[r2]; if (r2 < h->rank) before += (int64_t)all[r2]; if (r2 < MAX_RANKS) h->all_n[r2] = (int64_t)all[r2]; }
     h->n_global = tot; h->n_before = before;
   }
 #endif

@@ -333,6 +333,8 @@ class Emitter:
         for e in m.inits:
             w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name)))
         w("  }\n")
+        w("  ODX_HD static constexpr bool psi_is_pairwise(int k) { return %s; }\n" %
+          (" || ".join("k == %d" % self.psi_idx[c.name] for c in pair_cpls) or "false"))
         # ---- low-rank coupling descriptors
         w("  static constexpr int NLOWRANK = %d;" % len(lr_cpls))
         for k, c in enumerate(lr_cpls):
