@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(BLOCK) k_lr_stats(const double *__restrict__ x
       const double p0 = __ldcg(&partial[3 * k]), p1 = __ldcg(&partial[3 * k + 1]), p2 = __ldcg(&partial[3 * k + 2]);
       a = p0 < a ? p0 : a; b = p1 > b ? p1 : b; c += p2;
     }
-    stats[0] = a; stats[1] = b; stats[2] = c;
+    stats[0] = a; stats[1] = b; stats[2] = c; stats[3] = -a;     /* [3] = -min so that one MAX allreduce covers min and max */
     *counter = 0u;
   }
 }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ st
   __shared__ long long s_tc[LR_P1][LR_P1];
   __shared__ int s_p, s_pstep, s_go;
   const double meanx = stats[2] / n_global;
-  double range = stats[1] - stats[0];
+  double range = stats[1] - (-stats[3]);
   if (range == 0.0) range = 1.0;
   /* Chebyshev polynomials in the monomial basis: T_{n+1} = 2 x T_n - T_{n-1} (exact in 64-bit integers up to n = 50) */
   if (threadIdx.x == 0) {

@@ -65,6 +65,9 @@ ODX_HD void odx_sincos(double x, double *sp, double *cp) {
 #endif
 }
 
+/* reciprocal emitted for `x / f(...)` (a pure call the compiler can share between terms) */
+ODX_HD double odx_rcp(double x) { return 1.0 / x; }
+
 /* branch-free conditional emitted for `c ? a : b` in model functions (both arms are pure) */
 ODX_HD double odx_sel(bool c, double a, double b) { return c ? a : b; }
 

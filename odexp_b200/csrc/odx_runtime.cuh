@@ -162,14 +162,17 @@ static int launch_check(odx_handle *h) {
 #ifdef ODX_MODEL_HAS_LOWRANK
 /* lrwpkern on the device (see odx_lowrank.cuh); writes PSI[LR0_PSI] */
 static int compute_lowrank(odx_handle *h, const double *ysrc) {
-  if (h->nranks > 1) { h->err = "low-rank %C coupling is single-GPU in this build"; return ODX_EUNSUP; }
   const int64_t n = h->n;
-  if (n <= 0) return ODX_SUCCESS;
+  if (n <= 0 && h->nranks <= 1) return ODX_SUCCESS;
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1 && !h->comm) { h->err = "multi-GPU low-rank %C needs odx_comm_init"; return ODX_ENCCL; }
+#endif
   int nblk = (int)((n + LR_MTILE - 1) / LR_MTILE);
   if (nblk > h->grid_cap) nblk = h->grid_cap;
+  if (nblk < 1) nblk = 1;
   if (!h->lr_plan) {
     ODX_CUDA(h, cudaMalloc(&h->lr_plan, sizeof(LrPlan)));
-    ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 4));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 8));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_spart, sizeof(double) * 3 * (h->grid_cap + 1)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (h->grid_cap + 1)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
@@ -177,13 +180,31 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
   k_lr_stats<<<grid_for(h, n), BLOCK, 0, h->stream>>>(x, n, h->lr_spart, h->counter + 1, h->lr_stats);
   ODX_TRY(launch_check(h));
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {      /* mean / range over all GPUs: SUM of the sums, MAX of {max, -min} */
+    ncclResult_t r = g_nccl.AllReduce(h->lr_stats + 2, h->lr_stats + 2, 1, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r == ncclSuccess) { double *mm = h->lr_stats + 1; (void)mm; }
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    /* stats layout [min, max, sum, -min]: reduce {max} and {-min} with MAX (two one-element calls keep the layout simple) */
+    r = g_nccl.AllReduce(h->lr_stats + 1, h->lr_stats + 1, 1, ncclDouble, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    r = g_nccl.AllReduce(h->lr_stats + 3, h->lr_stats + 3, 1, ncclDouble, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  }
+#endif
   k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, (LrPlan *)h->lr_plan);
   ODX_TRY(launch_check(h));
   k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
   ODX_TRY(launch_check(h));
   k_lr_moments_sum<<<(LR_R * LR_P1 + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(h->lr_apart, nblk, h->lr_A);
   ODX_TRY(launch_check(h));
-  int ga = (int)((n + 127) / 128); if (ga > 4 * h->sm_count) ga = 4 * h->sm_count;
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {      /* moments are sums over particles: allreduce(SUM) of r x (p+1) doubles */
+    ncclResult_t r = g_nccl.AllReduce(h->lr_A, h->lr_A, (size_t)LR_R * LR_P1, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  }
+#endif
+  int ga = (int)((n + 127) / 128); if (ga > 4 * h->sm_count) ga = 4 * h->sm_count; if (ga < 1) ga = 1;
   k_lr_apply<<<ga, 128, 0, h->stream>>>(x, h->E + (size_t)M::LR0_U * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_A,
                                         h->PSI + (size_t)M::LR0_PSI * h->cap);
   return launch_check(h);

@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 for model, n, meth, nsteps, tol in [("kuramoto", 100003, "dde", 20, 1e-12), ("nbody", 3001, "dde", 2, 1e-12), ("nbody", 2048, "rkf45", 3, 1e-9),
-                                    ("vdp_sde", 50001, "fe", 10, 1e-12)]:
+                                    ("vdp_sde", 50001, "fe", 10, 1e-12), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10)]:
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
     pop = capi.Population(lib, capacity=hi - lo + 64, device=local)
