@@ -356,11 +356,102 @@ static int finish_events(odx_handle *h, EventBufs &b, int64_t nsweep, int64_t nb
 
 }  // namespace odx
 
+/* ---- multi-GPU birth / death: gather -> replicated sweep -> re-shard -----------------------------------------------------
+ * The sweep is O(N) light work next to the steps between events, and its semantics are those of ONE ordered list (ids by
+ * sweep order, daughters visited later in the same sweep).  Every rank therefore assembles the whole ordered population
+ * (allgather of all columns, rank order = list order), runs the single-GPU sweep on it — keyed draws make the result
+ * identical on every rank — and keeps the contiguous shard [lo, hi) of the new list that the balanced partition assigns to
+ * it.  Counts, ids and event rows are those of the single-GPU run by construction, and the population is rebalanced across
+ * the GPUs after every sweep. */
+namespace odx {
+#ifdef ODX_HAVE_NCCL_H
+static int gather_column(odx_handle *h, const void *src, void *dst, size_t elem, int64_t nmax, ncclDataType_t dt) {
+  char *sendbuf = (char *)h->gcol + (size_t)h->nranks * nmax * 8;
+  ODX_CUDA(h, cudaMemcpyAsync(sendbuf, src, (size_t)h->n * elem, cudaMemcpyDeviceToDevice, h->stream));
+  ncclResult_t r = g_nccl.AllGather(sendbuf, h->gcol, (size_t)nmax, dt, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  int64_t off = 0;
+  for (int q = 0; q < h->nranks; q++) {
+    if (h->all_n[q] > 0)
+      ODX_CUDA(h, cudaMemcpyAsync((char *)dst + (size_t)off * elem, (char *)h->gcol + (size_t)q * nmax * elem, (size_t)h->all_n[q] * elem,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    off += h->all_n[q];
+  }
+  return ODX_SUCCESS;
+}
+static int replica_gather(odx_handle *h) {
+  if (!h->comm) { h->err = "multi-GPU birth/death needs odx_comm_init (NCCL allgather)"; return ODX_ENCCL; }
+  const int64_t N = (int64_t)h->n_global;
+  int64_t nmax = 1;
+  for (int q = 0; q < h->nranks; q++) nmax = h->all_n[q] > nmax ? h->all_n[q] : nmax;
+  const int64_t want = 2 * N + 4096;
+  if (!h->replica || h->replica->cap < N + N / 4 + 1024) {
+    if (h->replica) odx_destroy(h->replica);
+    h->replica = nullptr;
+    int st = odx_create(&h->replica, h->device, want);
+    if (st != ODX_SUCCESS) { h->err = std::string("replica: ") + (h->replica ? h->replica->err : "allocation failed"); return st; }
+  }
+  if (h->gcol_cap < nmax) {
+    if (h->gcol) cudaFree(h->gcol);
+    h->gcol = nullptr; h->gcol_cap = 0;
+    ODX_CUDA(h, cudaMalloc(&h->gcol, (size_t)(h->nranks + 1) * nmax * 8));
+    h->gcol_cap = nmax;
+  }
+  odx_handle *g = h->replica;
+  ODX_CUDA(h, cudaStreamSynchronize(g->stream));
+  for (int c = 0; c < NVAR; c++) ODX_TRY(gather_column(h, h->Y + (size_t)c * h->cap, g->Y + (size_t)c * g->cap, 8, nmax, ncclDouble));
+  for (int c = 0; c < NEXPR; c++) ODX_TRY(gather_column(h, h->E + (size_t)c * h->cap, g->E + (size_t)c * g->cap, 8, nmax, ncclDouble));
+  for (int c = 0; c < NAUX; c++) ODX_TRY(gather_column(h, h->AUX + (size_t)c * h->cap, g->AUX + (size_t)c * g->cap, 8, nmax, ncclDouble));
+  for (int c = 0; c < NPSI; c++) ODX_TRY(gather_column(h, h->PSI + (size_t)c * h->cap, g->PSI + (size_t)c * g->cap, 8, nmax, ncclDouble));
+  ODX_TRY(gather_column(h, h->DEATH, g->DEATH, 8, nmax, ncclDouble));
+  ODX_TRY(gather_column(h, h->REPLI, g->REPLI, 8, nmax, ncclDouble));
+  ODX_TRY(gather_column(h, h->ID, g->ID, 4, nmax, ncclInt32));
+  ODX_CUDA(h, cudaMemcpyAsync(g->sums, h->sums, sizeof(double) * NSLOT * NRED, cudaMemcpyDeviceToDevice, h->stream));
+  ODX_CUDA(h, cudaMemcpyAsync(g->d_mu, h->d_mu, sizeof(double) * A1(NPAR), cudaMemcpyDeviceToDevice, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  g->n = N; g->n_global = (double)N; g->all_n[0] = N; g->max_id = h->max_id; g->k0 = h->k0; g->k1 = h->k1;
+  g->report_slot = h->report_slot; g->rates_slot = h->rates_slot;
+  g->hr = h->hr; g->hr_seeded = h->hr_seeded; g->host_draws = h->host_draws;
+  for (int k = 0; k < NPAR; k++) g->h_mu[k] = h->h_mu[k];
+  return ODX_SUCCESS;
+}
+static int replica_scatter(odx_handle *h) {
+  odx_handle *g = h->replica;
+  ODX_CUDA(h, cudaStreamSynchronize(g->stream));
+  const int64_t Nn = g->n, base = Nn / h->nranks, extra = Nn % h->nranks;
+  const int64_t lo = h->rank * base + (h->rank < extra ? h->rank : extra), cnt = base + (h->rank < extra ? 1 : 0);
+  if (cnt > h->cap) { h->err = "birth/death: this rank's shard exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+  if (cnt > 0) {
+    for (int c = 0; c < NVAR; c++) ODX_CUDA(h, cudaMemcpyAsync(h->Y + (size_t)c * h->cap, g->Y + (size_t)c * g->cap + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int c = 0; c < NEXPR; c++) ODX_CUDA(h, cudaMemcpyAsync(h->E + (size_t)c * h->cap, g->E + (size_t)c * g->cap + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int c = 0; c < NAUX; c++) ODX_CUDA(h, cudaMemcpyAsync(h->AUX + (size_t)c * h->cap, g->AUX + (size_t)c * g->cap + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int c = 0; c < NPSI; c++) ODX_CUDA(h, cudaMemcpyAsync(h->PSI + (size_t)c * h->cap, g->PSI + (size_t)c * g->cap + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(h->DEATH, g->DEATH + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(h->REPLI, g->REPLI + lo, cnt * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(h->ID, g->ID + lo, cnt * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n = cnt; h->max_id = g->max_id; h->hr = g->hr; h->hr_seeded = g->hr_seeded; h->host_draws = g->host_draws;
+  invalidate_state(h);
+  return refresh_global_n(h);
+}
+#endif
+}  // namespace odx
+
 extern "C" {
 
 int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows) {
   ODX_CUDA(h, cudaSetDevice(h->device));
-  if (h->nranks > 1) { h->err = "odx_tauleap_apply: multi-GPU birth/death is not built yet"; return ODX_EUNSUP; }
+  if (h->nranks > 1) {
+#ifdef ODX_HAVE_NCCL_H
+    ODX_TRY(replica_gather(h));
+    int st = odx_tauleap_apply(h->replica, t, dt, leap_index, rows, max_rows, nrows);
+    if (st != ODX_SUCCESS) { h->err = std::string("replicated sweep: ") + h->replica->err; return st; }
+    return replica_scatter(h);
+#else
+    h->err = "built without nccl.h"; return ODX_ENCCL;
+#endif
+  }
   odx_event_state *es = event_state(h);
   EventBufs &b = es->b;
   ODX_TRY(ensure_event_bufs(h, b));
@@ -404,7 +495,16 @@ int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, o
 
 int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {
   ODX_CUDA(h, cudaSetDevice(h->device));
-  if (h->nranks > 1) { h->err = "odx_ssa_apply: multi-GPU birth/death is not built yet"; return ODX_EUNSUP; }
+  if (h->nranks > 1) {
+#ifdef ODX_HAVE_NCCL_H
+    ODX_TRY(replica_gather(h));
+    int st = odx_ssa_apply(h->replica, t, u, row);
+    if (st != ODX_SUCCESS) { h->err = std::string("replicated SSA event: ") + h->replica->err; return st; }
+    return replica_scatter(h);
+#else
+    h->err = "built without nccl.h"; return ODX_ENCCL;
+#endif
+  }
   odx_event_state *es = event_state(h);
   EventBufs &b = es->b;
   ODX_TRY(ensure_event_bufs(h, b));

@@ -122,8 +122,16 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   if (o->mu && (status = odx_set_params(h, o->mu, mi->npar)) != 0) goto done;
   if ((status = odx_set_tolerances(h, o->abstol, o->reltol)) != 0) goto done;
   if ((status = odx_set_seed(h, o->seed)) != 0) goto done;
-  /* population initialisation: par_birth() x popsize, event = {-1, 1, .}, ode_ic (methods_odexp.c:315-337) */
-  if ((status = odx_pop_init(h, o->popsize, t, o->seed, o->replay_ic)) != 0) goto done;
+  /* population initialisation: par_birth() x popsize, event = {-1, 1, .}, ode_ic (methods_odexp.c:315-337).
+   * Multi-GPU: every rank runs this same loop on its contiguous shard of the ordered population. */
+  {
+    int rank = 0, nranks = 1;
+    int64_t base, extra, local;
+    odx_comm_rank(h, &rank, &nranks);
+    base = o->popsize / nranks; extra = o->popsize % nranks;
+    local = base + (rank < extra ? 1 : 0);
+    if ((status = odx_pop_init(h, local, t, o->seed, o->replay_ic)) != 0) goto done;
+  }
   /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364) */
   if ((status = odx_rhs(h, t)) != 0) goto done;
   if ((status = odx_meanfields(h, os.mfd)) != 0) goto done;

@@ -51,6 +51,8 @@ static void odx_events_free(odx_handle *h);
 
 struct odx_handle {
   odx_event_state *ev_state = nullptr;       /* birth / death scratch (odx_events.cuh), allocated on first use */
+  odx_handle *replica = nullptr;             /* multi-GPU birth/death: whole ordered population, rebuilt per sweep */
+  void *gcol = nullptr; int64_t gcol_cap = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
   int64_t cap = 0, n = 0;
@@ -593,6 +595,8 @@ void odx_destroy(odx_handle *h) {
   if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
   odx_events_free(h);
+  if (h->replica) { odx_destroy(h->replica); h->replica = nullptr; cudaSetDevice(h->device); }
+  if (h->gcol) cudaFree(h->gcol);
   if (h->lr_plan) cudaFree(h->lr_plan);
   { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
@@ -694,6 +698,12 @@ int odx_comm_init(odx_handle *h, int rank, int nranks, const void *uid128) {
 #else
   (void)rank; (void)uid128; h->err = "built without nccl.h"; return ODX_ENCCL;
 #endif
+}
+
+int odx_comm_rank(const odx_handle *h, int *rank, int *nranks) {
+  if (rank) *rank = h->rank;
+  if (nranks) *nranks = h->nranks;
+  return ODX_SUCCESS;
 }
 
 /* global population size / offsets after any change of the local size (allreduce over ranks) */

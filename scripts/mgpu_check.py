@@ -56,6 +56,29 @@ for model, n, meth, nsteps, tol in [("kuramoto", 100003, "dde", 20, 1e-12), ("nb
         solo.close()
     dist.barrier()
     pop.close()
+# ---- whole simulation with birth / death through the C host driver: every rank's stats.dat must equal the solo run's
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "vdp_sde.pop"))
+for ssahmin, ps, res, T in [(1.0, 2000, 21, 2.0), (0.0, 60, 6, 1.0)]:
+    pop = capi.Population(lib, capacity=4 * ps + 1024, device=local)
+    odist.connect(pop)
+    out = capi.odesolver(pop, (0, T), meth="fe", res=res, popsize=ps, h0=0.01, ssahmin=ssahmin, seed=123, replay_ic=False)
+    ids_mine = out["traj"]["id"][out["traj"]["step"] == out["traj"]["step"].max()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ids_mine)
+    if rank == 0:
+        solo = capi.Population(lib, capacity=4 * ps + 1024, device=local)
+        ref = capi.odesolver(solo, (0, T), meth="fe", res=res, popsize=ps, h0=0.01, ssahmin=ssahmin, seed=123, replay_ic=False)
+        sa, sb = out["stats"], ref["stats"]
+        same = len(sa) == len(sb) and all(np.array_equal(sa[k], sb[k]) for k in ("n", "stop_flag", "event")) and np.allclose(sa["t"], sb["t"], rtol=1e-12)
+        ids_ref = ref["traj"]["id"][ref["traj"]["step"] == ref["traj"]["step"].max()]
+        ids_all = np.concatenate(gathered)
+        good = bool(same and np.array_equal(ids_all, ids_ref) and max(len(g) for g in gathered) - min(len(g) for g in gathered) <= 1)
+        ok &= good
+        print("vdp_sde odesolver ssahmin=%g ps=%d world=%d: stats rows %d (solo %d) events %d final N %d shards %s -> %s" % (
+            ssahmin, ps, world, len(sa), len(sb), int((sb["event"][:, 1] != 0).sum()) - ps, int(sb["n"][-1]), [len(g) for g in gathered], "OK" if good else "MISMATCH"), flush=True)
+        solo.close()
+    dist.barrier()
+    pop.close()
 if rank == 0:
     print("MGPU_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
