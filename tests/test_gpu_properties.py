@@ -1,0 +1,128 @@
+"""Size-independent properties at the BASELINE sizes (where the oracle would take hours) and edge cases of the C-ABI.
+All through the C-ABI on cuda:0."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kuramoto_full_size_invariants(model_lib):
+    """N = 2^24 (config 2): (a) OMEGA = mean(omega) is a conserved mean field; (b) with K = 0 classic RK4 is exact:
+    theta(t) = theta0 + omega t; (c) k steps in one persistent launch == k single-step calls == per-stage kernels."""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    n = 1 << 24
+    pop = capi.Population(lib, capacity=n)
+    pop.init(n, replay=False, seed=42)
+    pop.rhs(0.0)
+    m0 = pop.meanfields()
+    s0 = pop.download(12345, 4096)
+    t = pop.run_fixed("dde", 0.0, 0.05, 8)
+    m1 = pop.meanfields()
+    assert abs(m1[2] - m0[2]) < 1e-14 and abs(m0[2] - 2 * 3.141592 / 10.0) < 1e-3
+    assert abs(t - 0.4) < 1e-15
+    a = pop.download(12345, 4096)["y"][:, 0]
+    # (c) same 8 steps as single calls, and with the persistent kernel switched off
+    for persistent in (1, 0):
+        q = capi.Population(lib, capacity=n)
+        q.set_option("persistent", persistent)
+        q.init(n, replay=False, seed=42)
+        tt, hh = 0.0, 0.05
+        for _ in range(8):
+            tt, hh = q.dde_apply(tt, 10.0, hh, hmin=1e-9, h0=0.05)
+        b = q.download(12345, 4096)["y"][:, 0]
+        np.testing.assert_allclose(a, b, rtol=1e-13, atol=0)
+        np.testing.assert_allclose(q.meanfields(), m1, rtol=0, atol=1e-15)
+        q.close()
+    # (b) K = 0
+    pop.set_params([0.0])
+    pop.init(n, replay=False, seed=42)
+    pop.run_fixed("dde", 0.0, 0.05, 8)
+    f = pop.download(12345, 4096)
+    np.testing.assert_allclose(f["y"][:, 0], s0["y"][:, 0] + s0["expr"][:, 0] * 0.4, rtol=1e-14)
+    pop.close()
+
+
+def test_nbody_full_size_momentum(model_lib):
+    """N = 2^17 (config 4): equal masses and antisymmetric pair forces => sum_i psi_i = 0 up to round-off, and psi is
+    invariant under a permutation-free re-evaluation (determinism)."""
+    from odexp_b200 import capi
+    lib = model_lib("nbody")
+    n = 1 << 17
+    pop = capi.Population(lib, capacity=n)
+    pop.init(n, replay=False, seed=3)
+    pop.rhs(0.0)
+    p1 = pop.download()["psi"]
+    pop.rhs(0.0)
+    p2 = pop.download()["psi"]
+    np.testing.assert_array_equal(p1, p2)
+    scale = np.abs(p1).sum(axis=0)
+    assert np.all(np.abs(p1.sum(axis=0)) <= 1e-9 * scale)
+    pop.close()
+
+
+def test_sde_full_size_leap(model_lib):
+    """N = 2^22 (config 5): one Euler-Maruyama burst + one tau-leap sweep: ids stay sorted and unique (stable compaction),
+    N matches the event arithmetic, noise has the right scale (Var[y] ~ sigma^2 t for small t)."""
+    from odexp_b200 import capi
+    lib = model_lib("vdp_sde")
+    n = 1 << 22
+    pop = capi.Population(lib, capacity=n + n // 2)
+    pop.init(n, replay=False, seed=8)
+    t = pop.run_fixed("fe", 0.0, 0.001, 10)
+    d = pop.download(0, 1 << 16)
+    y = d["y"][:, 0]
+    # dy = mu((1-x^2)y - x)dt + sigma dW, x0 = 2, y0 = 0: drift mean ~ -2 t, noise variance ~ sigma^2 t
+    assert abs(y.var() / (0.1 ** 2 * t) - 1.0) < 0.05 and abs(y.mean() + 2.0 * t) < 2e-3
+    pop.rhs(t)
+    rows = pop.tauleap_apply(t, 1.0, 0, max_rows=1 << 20)
+    nl, ng, max_id = pop.size()
+    ids = pop.download()["id"]
+    assert len(ids) == nl and np.all(np.diff(ids) > 0)
+    deaths = sum(1 for r in rows if r[2][1] == -1)
+    births = sum(1 for r in rows if r[2][1] == 1)
+    assert nl == n - deaths + births and max_id == n + births and rows[-1][0] == nl
+    pop.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 257, 2049])
+def test_ragged_sizes(model_lib, n):
+    """empty / tiny / odd populations: the two-particles-per-thread kernels, tails and reductions"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto")
+    pop = capi.Population(lib, capacity=4096)
+    if n == 0:
+        pop.init(0, replay=True)
+        pop.rhs(0.0)
+        assert pop.size()[0] == 0
+        assert pop.run_fixed("dde", 0.0, 0.1, 3) == pytest.approx(0.3)
+        pop.close()
+        return
+    out = capi.odesolver(pop, (0, 0.3), meth="dde", h0=0.1, res=2, popsize=n, replay_ic=True)
+    ref = port.run("kuramoto", {"meth": "dde", "h0": 0.1, "res": 2, "ps": n}, (0, 0.3))
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_array_equal(out["traj"]["id"], ref["traj"]["id"])
+    pop.close()
+
+
+def test_error_paths(model_lib):
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    pop = capi.Population(lib, capacity=64)
+    with pytest.raises(capi.OdxError):
+        pop.init(1000)                         # exceeds capacity
+    with pytest.raises(capi.OdxError):
+        pop.set_params([1.0, 2.0])             # wrong number of parameters
+    with pytest.raises(capi.OdxError):
+        pop.evolve_apply("dde", 0.0, 1.0, 0.1)  # not an embedded method
+    with pytest.raises(capi.OdxError):
+        capi.odesolver(pop, (0, 0.5, 1.0), meth="dde", popsize=8)   # stopping times are host-only
+    pop.close()
+    sde = capi.Population(model_lib("vdp_sde"), capacity=64)
+    sde.init(60, replay=False)
+    sde.rhs(0.0)
+    with pytest.raises(capi.OdxError):
+        for k in range(50):                    # births + replications overflow the capacity: reported, not fatal
+            sde.tauleap_apply(0.0, 5.0, k)
+    sde.close()
