@@ -234,6 +234,11 @@ struct ChainArgs {
   double w;                 /* weight of k in the accumulator */
   uint32_t eval_index;      /* RHS evaluation counter (Philox stream) */
   int want_out;             /* write aux / rates (last step before an output or event) */
+  int reverse;              /* sweep direction of this stage */
+  double recon;             /* != 0: this is the stage after FIRST and the accumulator w1*k1 is rebuilt from the stage state,
+                               acc = (ys - y0) * recon with recon = w1 / a1, instead of being stored and re-read (16 B per
+                               particle-step less traffic; the rebuilt slope is exact to <= 1 ulp of y0 / (a1 h)) */
+  int skip_acc_store;       /* FIRST stage: the next stage reconstructs the accumulator */
 };
 
 /* chain methods (Euler, classic RK4): stage state depends on the previous slope only.
@@ -290,7 +295,14 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
 /* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread) */
 template <bool FIRST, bool LAST>
 __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED]) {
-  for (int64_t i = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < p.n; i += 2 * (int64_t)gridDim.x * blockDim.x) {
+  /* the grid sweeps the columns as a moving window of gridDim.x tiles; alternate stages sweep in opposite directions so that
+   * the tail of one stage (still resident in the 126 MB L2) is the head of the next */
+  const int64_t per_iter = 2 * (int64_t)gridDim.x * blockDim.x;
+  const int64_t niter = (p.n + per_iter - 1) / per_iter;
+  for (int64_t k = 0; k < niter; k++) {
+    const int64_t kk = a.reverse ? (niter - 1 - k) : k;
+    const int64_t i = kk * per_iter + 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= p.n) continue;
     const bool two = (i + 1 < p.n);
     double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)], yn[2][A1(NVAR)], aux[2][A1(NAUX)];
     double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
@@ -302,7 +314,12 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
       for (int v = 0; v < NVAR; v++) { yc[0][v] = y0[0][v]; yc[1][v] = y0[1][v]; }
     } else {
       load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
-      load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      if (a.recon == 0.0) {
+        load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NVAR; v++) { acc[0][v] = (yc[0][v] - y0[0][v]) * a.recon; acc[1][v] = (yc[1][v] - y0[1][v]) * a.recon; }
+      }
     }
     int32_t id0 = 0, id1 = 0;
     if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
@@ -316,7 +333,7 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
         if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
       }
     } else {
-      store_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
       store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
     }
   }
@@ -346,11 +363,11 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
  * ---------------------------------------------------------------------------------------------- */
 constexpr int MAX_RANKS = 8;
 struct PersistArgs {
-  int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0;
+  int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0; int recon;
   const double *sums_y;            /* global raw sums of the %M terms of Y at entry */
   double *partial;                 /* [2][grid][NRED] */
-  unsigned int *bar;               /* [2][PERSIST_MAX_CTAS] epoch tags of the published block partials */
-  double *totals;                  /* unused */
+  unsigned int *bar;               /* [2][PERSIST_MAX_CTAS] epoch tags of the published block partials, then [2] global-sum flags */
+  double *totals;                  /* [2][NRED] global sums published by CTA 0 (multi-GPU) */
   double *sums_new, *sums_report;  /* out: sums of the new Y (+ rates) / sums used by the last RHS evaluation */
   int rank, nranks; uint32_t epoch0;
   double *mailbox; uint32_t *mailflag;                 /* local: [2][MAX_RANKS][NRED], [2][MAX_RANKS] */
@@ -369,6 +386,14 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -496,7 +521,8 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       if (last_stage && step == g.nsteps - 1 && blockIdx.x == 0 && threadIdx.x < NRED) g.sums_report[threadIdx.x] = s_tot[threadIdx.x];
       __syncthreads();
       ChainArgs a;
-      a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2;
+      a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2; a.reverse = (int)(epoch & 1u);
+      a.recon = 0.0; a.skip_acc_store = 0;
       a.want_out = (last_stage && step == g.nsteps - 1) ? g.want_out_last : 0;
       double red[NRED];
 #pragma unroll
@@ -505,10 +531,10 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
         chain_sweep<true, true>(p, a, mfd, red);
       } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */
-        a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0;
+        a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0; a.skip_acc_store = g.recon ? 1 : 0;
         chain_sweep<true, false>(p, a, mfd, red);
       } else if (s == 1) {
-        a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0;
+        a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0; a.recon = g.recon ? 1.0 / (g.h / 2.0) : 0.0;
         chain_sweep<false, false>(p, a, mfd, red);
       } else if (s == 2) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h; a.a = g.h; a.w = 2.0;
@@ -541,8 +567,12 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
         block_total<PT>(acc, s_tot);
       }
       if (g.nranks > 1) {
-        /* cross-GPU: CTA 0 stores this rank's sums and the tag straight into every peer's mailbox over NVLink; every CTA
-         * waits for the other ranks' tags in its own GPU's mailbox and adds the rank sums in rank order */
+        /* cross-GPU: CTA 0 stores this rank's sums and the epoch tag straight into every peer's mailbox over NVLink
+         * (st.release.sys on IPC-mapped pointers), waits for the other ranks' tags in its own GPU's mailbox, adds the rank
+         * sums in rank order and publishes the global sums to the other CTAs of this GPU (one more local round trip, but
+         * only one CTA polls the lines the peers write to) */
+        double *gtot = g.totals + par * NRED;
+        unsigned int *gflag = g.bar + 2 * PERSIST_MAX_CTAS + par;
         if (blockIdx.x == 0) {
           if (threadIdx.x < NRED) {
             for (int r = 0; r < g.nranks; r++)
@@ -551,22 +581,29 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
           }
           __syncthreads();
           if (threadIdx.x < g.nranks && threadIdx.x != g.rank) {
-            volatile uint32_t *f = g.peer_flag[threadIdx.x] + par * MAX_RANKS + g.rank;
-            *f = tag;
+            st_release_sys_u32(g.peer_flag[threadIdx.x] + par * MAX_RANKS + g.rank, tag);
+            const uint32_t *w = g.mailflag + par * MAX_RANKS + threadIdx.x;
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u32(w) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
           }
-        }
-        if (threadIdx.x < g.nranks && threadIdx.x != g.rank) {
-          volatile uint32_t *w = g.mailflag + par * MAX_RANKS + threadIdx.x;
-          unsigned long long spins = 0;
-          while (*w != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
-          __threadfence_system();
-        }
-        __syncthreads();
-        if (threadIdx.x < NRED) {
-          double v = 0.0;
-          for (int r = 0; r < g.nranks; r++)
-            v += (r == g.rank) ? s_tot[threadIdx.x] : __ldcv(&g.mailbox[(par * MAX_RANKS + r) * NRED + threadIdx.x]);
-          s_tot[threadIdx.x] = v;
+          __syncthreads();
+          if (threadIdx.x < NRED) {
+            double v = 0.0;
+            for (int r = 0; r < g.nranks; r++)
+              v += (r == g.rank) ? s_tot[threadIdx.x] : __ldcv(&g.mailbox[(par * MAX_RANKS + r) * NRED + threadIdx.x]);
+            s_tot[threadIdx.x] = v;
+            gtot[threadIdx.x] = v;
+            __threadfence();
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) st_release_u32(gflag, tag);
+        } else {
+          if (threadIdx.x == 0) {
+            unsigned long long spins = 0;
+            while (ld_acquire_u32(gflag) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+          }
+          __syncthreads();
+          if (threadIdx.x < NRED) s_tot[threadIdx.x] = __ldcg(&gtot[threadIdx.x]);
         }
         __syncthreads();
       }

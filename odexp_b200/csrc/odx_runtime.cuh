@@ -80,7 +80,7 @@ struct odx_handle {
   ncclComm_t comm = nullptr;
 #endif
   /* persistent step kernel + peer-memory exchange */
-  int use_persistent = 1, coop_ok = 0, coop_blocks = 0;
+  int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
   uint32_t epoch = 0;
   void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -362,7 +362,7 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   const int new_slot = h->y_slot ^ 1;
   Pop p = pop_view(h);
   PersistArgs g; memset(&g, 0, sizeof g);
-  g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index;
+  g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index; g.recon = h->use_recon;
   g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32 + BAR_WORDS; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
   g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
   fill_peer_args(h, g);
@@ -391,10 +391,11 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out)
   const int g = grid_chain(h, h->n);
   Pop p = pop_view(h);
   const int new_slot = h->y_slot ^ 1;
-  ChainArgs a; a.h = hh; a.want_out = want_out;
+  ChainArgs a; a.h = hh; a.want_out = want_out; a.reverse = 0; a.recon = 0.0; a.skip_acc_store = 0;
   if (nst == 1) {
     ODX_TRY(compute_psi(h, h->Y, t));
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + hh; a.a = hh; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    a.reverse = (h->sweep_dir ^= 1);
     k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
     ODX_TRY(launch_check(h));
     h->report_slot = h->y_slot; h->rhs_evals += 1;
@@ -403,18 +404,24 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out)
     const double half = hh / 2.0;
     ODX_TRY(compute_psi(h, h->Y, t));
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + half; a.a = half; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    a.reverse = (h->sweep_dir ^= 1); a.skip_acc_store = h->use_recon;
     k_chain<true, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 0));
+    a.skip_acc_store = 0;
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 0));
     ODX_TRY(compute_psi(h, h->YS, t + half));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 0); a.t_eval = t + half; a.t_next = t + half; a.a = half; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    a.reverse = (h->sweep_dir ^= 1); a.recon = h->use_recon ? 1.0 / half : 0.0;
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 1));
+    a.recon = 0.0;
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 1));
     ODX_TRY(compute_psi(h, h->YS, t + half));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 1); a.t_eval = t + half; a.t_next = t + hh; a.a = hh; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    a.reverse = (h->sweep_dir ^= 1);
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 2));
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 2));
     ODX_TRY(compute_psi(h, h->YS, t + hh));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 2); a.t_eval = t + hh; a.t_next = t + hh; a.a = hh / 6.0; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
+    a.reverse = (h->sweep_dir ^= 1);
     k_chain<false, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
     ODX_TRY(launch_check(h));
     h->report_slot = SLOT_STAGE + 2; h->rhs_evals += 4;
@@ -515,6 +522,10 @@ static void invalidate_state(odx_handle *h) { h->ymoments_valid = false; h->k1_v
 
 static int upload_cols(odx_handle *h, const double *aos, double *soa, int ncol, int64_t n, int64_t first) {
   if (ncol == 0 || n == 0 || aos == nullptr) return ODX_SUCCESS;
+  if (ncol == 1) {          /* a single column is already in device layout: straight into place, no staging pass */
+    ODX_CUDA(h, cudaMemcpyAsync(soa + first, aos, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    return ODX_SUCCESS;
+  }
   const size_t bytes = sizeof(double) * (size_t)ncol * n;
   ODX_TRY(ensure_stage(h, bytes));
   ODX_CUDA(h, cudaMemcpyAsync(h->stage_dev, aos, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -525,6 +536,11 @@ static int upload_cols(odx_handle *h, const double *aos, double *soa, int ncol, 
 }
 static int download_cols(odx_handle *h, const double *soa, double *aos, int ncol, int64_t n, int64_t first) {
   if (ncol == 0 || n == 0 || aos == nullptr) return ODX_SUCCESS;
+  if (ncol == 1) {
+    ODX_CUDA(h, cudaMemcpyAsync(aos, soa + first, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ODX_SUCCESS;
+  }
   const size_t bytes = sizeof(double) * (size_t)ncol * n;
   ODX_TRY(ensure_stage(h, bytes));
   k_soa_to_aos<<<h->sm_count * 4, 256, 0, h->stream>>>(soa, h->stage_dev, ncol, n, h->cap, first);
@@ -577,8 +593,8 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   for (int k = 0; k < NPAR; k++) h->h_mu[k] = mi->par_defaults[k];
   ODX_CUDA(h, cudaMemcpyAsync(h->d_mu, h->h_mu, sizeof(double) * A1(NPAR), cudaMemcpyHostToDevice, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * 2 * (h->grid_cap + h->coop_blocks + 8)));
-  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS)));
-  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS), h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS + 8)));
+  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS + 8), h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->sums, sizeof(double) * NSLOT * NRED));
   ODX_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * NSLOT * NRED, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->rmax, sizeof(unsigned long long) * 2));
@@ -627,6 +643,7 @@ int odx_sync(odx_handle *h) {
 
 int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
+  if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }
   if (strcmp(name, "lrabstol") == 0) { h->lr_abstol = value; return ODX_SUCCESS; }
   if (strcmp(name, "lrreltol") == 0) { h->lr_reltol = value; return ODX_SUCCESS; }
@@ -751,6 +768,7 @@ int odx_pop_upload(odx_handle *h, int64_t n, const double *y, const double *expr
   ODX_CUDA(h, cudaMemsetAsync(h->DEATH, 0, sizeof(double) * h->cap, h->stream));
   ODX_CUDA(h, cudaMemsetAsync(h->REPLI, 0, sizeof(double) * h->cap, h->stream));
   invalidate_state(h);
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));      /* the caller's host buffers may be reused as soon as we return */
   return refresh_global_n(h);
 }
 
