@@ -375,13 +375,7 @@ struct PersistArgs {
   int *abort_flag;
 };
 
-/* Grid barrier fused with the reduction (all CTAs co-resident: cooperative launch).  Arrival is two-level to keep the
- * atomics off a single L2 line: CTAs arrive on one of BAR_GROUPS padded counters, the last of each group arrives on the
- * top counter, and the globally last CTA returns true: it alone adds the block partials (and talks to the peers)
- * before it releases the others by bumping the generation word. */
-constexpr int BAR_GROUPS = 16;
-constexpr int BAR_PAD = 32;                         /* one 128-byte line per counter */
-constexpr int BAR_WORDS = (BAR_GROUPS + 2) * BAR_PAD;
+/* acquire / release accesses used by the in-kernel mean-field exchange (gpu scope inside one GPU, sys scope across NVLink) */
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -398,42 +392,6 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-/* returns true in exactly one CTA (the last to arrive); that CTA must call barrier_release afterwards */
-__device__ __forceinline__ bool barrier_arrive(unsigned int *bar, unsigned int nblocks, unsigned int &gen0) {
-  __shared__ int s_is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int *top = bar + BAR_GROUPS * BAR_PAD, *gen = bar + (BAR_GROUPS + 1) * BAR_PAD;
-    gen0 = ld_acquire_u32(gen);
-    const unsigned int ng = nblocks < BAR_GROUPS ? nblocks : BAR_GROUPS;
-    const unsigned int grp = blockIdx.x % ng;
-    const unsigned int gsize = nblocks / ng + ((grp < nblocks % ng) ? 1u : 0u);
-    __threadfence();
-    int last = 0;
-    if (atomicAdd(bar + grp * BAR_PAD, 1u) == gsize - 1) {
-      bar[grp * BAR_PAD] = 0u;
-      __threadfence();
-      if (atomicAdd(top, 1u) == ng - 1) { *top = 0u; last = 1; }
-    }
-    s_is_last = last;
-  }
-  __syncthreads();
-  const bool last = s_is_last != 0;
-  if (last) __threadfence();
-  return last;
-}
-__device__ __forceinline__ void barrier_release(unsigned int *bar, unsigned int gen0) {
-  __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); st_release_u32(bar + (BAR_GROUPS + 1) * BAR_PAD, gen0 + 1u); }
-}
-__device__ __forceinline__ void barrier_wait(unsigned int *bar, unsigned int gen0) {
-  if (threadIdx.x == 0) {
-    const unsigned int *gen = bar + (BAR_GROUPS + 1) * BAR_PAD;
-    while (ld_acquire_u32(gen) == gen0) { }
-  }
-  __syncthreads();
-}
-
 /* block partial of red[] -> partial[blockIdx][*] */
 template <int NT>
 __device__ __forceinline__ void block_partial(const double (&red)[NRED], double *__restrict__ partial) {
@@ -453,33 +411,6 @@ __device__ __forceinline__ void block_partial(const double (&red)[NRED], double 
   }
   __syncthreads();
 }
-/* fixed-order sum of all block partials, result in s_tot[NRED] (every CTA computes the same bits) */
-template <int NT>
-__device__ __forceinline__ void sum_partials(const double *__restrict__ partial, unsigned int nblocks, double *s_tot) {
-  __shared__ double s_part2[NT / 32][NRED];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double acc[NRED];
-#pragma unroll
-  for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-  for (unsigned int b = threadIdx.x; b < nblocks; b += NT) {
-#pragma unroll
-    for (int k = 0; k < NRED; k++) acc[k] += __ldcg(&partial[(size_t)b * NRED + k]);
-  }
-#pragma unroll
-  for (int k = 0; k < NRED; k++) {
-    const double v = warp_sum(acc[k]);
-    if (lane == 0) s_part2[warp][k] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < NRED) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; w++) v += s_part2[w][threadIdx.x];
-    s_tot[threadIdx.x] = v;
-  }
-  __syncthreads();
-}
-
 /* fixed-order block sum of per-thread accumulators into s_tot[NRED] */
 template <int NT>
 __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s_tot) {

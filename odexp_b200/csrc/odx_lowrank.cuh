@@ -81,22 +81,17 @@ __global__ void __launch_bounds__(BLOCK) k_lr_stats(const double *__restrict__ x
   }
 }
 
-/* one CTA: lrexpars tail + lrexprank + the coefficient part of lrexpwp */
-__global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ stats, double n_global, int pmax, double abstol, double reltol,
-                                                    LrPlan *plan) {
-  __shared__ double s_f[LR_P1], s_c[LR_P1], s_red[2][BLOCK / 32];
-  __shared__ long long s_tc[LR_P1][LR_P1];
-  __shared__ int s_p, s_pstep, s_go;
-  const double meanx = stats[2] / n_global;
+/* lrexprank, part 1 (one CTA): Chebyshev fit of f at the maximal order on [-range, range], parity of f, candidate orders */
+constexpr int LR_NCAND = 12;
+struct LrRank {
+  double c[LR_P1];            /* fit at order pmax */
+  int p0, pstep, ncand;       /* candidates p0 + pstep * (1..ncand), capped at pmax */
+  double spe[LR_NCAND];       /* sum_i |series_p(x_i)| over the errn sample points, per candidate (filled by k_lr_rank_spe) */
+};
+__global__ void __launch_bounds__(BLOCK) k_lr_rank_fit(const double *__restrict__ stats, int pmax, LrRank *rk) {
+  __shared__ double s_f[LR_P1], s_c[LR_P1];
   double range = stats[1] - (-stats[3]);
   if (range == 0.0) range = 1.0;
-  /* Chebyshev polynomials in the monomial basis: T_{n+1} = 2 x T_n - T_{n-1} (exact in 64-bit integers up to n = 50) */
-  if (threadIdx.x == 0) {
-    for (int a = 0; a < LR_P1; a++) for (int b = 0; b < LR_P1; b++) s_tc[a][b] = 0;
-    s_tc[0][0] = 1; s_tc[1][1] = 1;
-    for (int n = 1; n + 1 < LR_P1; n++)
-      for (int l = 0; l <= n + 1; l++) s_tc[n + 1][l] = (l > 0 ? 2 * s_tc[n][l - 1] : 0) - s_tc[n - 1][l];
-  }
   lr_cheb_init(pmax, range, s_f, s_c);
   if (threadIdx.x == 0) {
     double sc = 0.0; int oddity = 2;
@@ -104,43 +99,91 @@ __global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ st
     if (sc < (double)pmax / 2 * 1e-8) oddity = 1;
     for (int i = 1; i < pmax + 1; i += 2) sc += fabs(s_c[i]);
     if (sc < (double)pmax / 2 * 1e-8) oddity = 0;
-    s_pstep = 4;
-    if (oddity == 0) s_p = 0; else if (oddity == 1) s_p = -1; else { s_p = -1; s_pstep = 3; }
+    int pstep = 4, p0;
+    if (oddity == 0) p0 = 0; else if (oddity == 1) p0 = -1; else { p0 = -1; pstep = 3; }
+    rk->p0 = p0; rk->pstep = pstep;
+    int nc = 0;
+    for (int p = p0 + pstep; nc < LR_NCAND; p += pstep) { nc++; if (p >= pmax) break; }
+    rk->ncand = nc;
+    for (int i = 0; i < LR_NCAND; i++) rk->spe[i] = 0.0;
+    for (int i = 0; i <= pmax; i++) rk->c[i] = s_c[i];
   }
+}
+/* part 2 (whole grid): spe_p = sum over the errn sample points of |series truncated at order p|, for every candidate p at once.
+ * The reference walks the candidates one after the other and stops at the first that passes; evaluating all of them costs
+ * errn * sum(p) FMAs spread over the GPU instead of a serial loop on one CTA. */
+__global__ void __launch_bounds__(BLOCK) k_lr_rank_spe(const double *__restrict__ stats, double n_global, int pmax, LrRank *rk) {
+  __shared__ double s_c[LR_P1];
+  __shared__ double s_red[BLOCK / 32][LR_NCAND];
+  if (threadIdx.x <= pmax) s_c[threadIdx.x] = rk->c[threadIdx.x];
   __syncthreads();
+  double range = stats[1] - (-stats[3]);
+  if (range == 0.0) range = 1.0;
   const long long ng = (long long)n_global;
   const long long errn = (ng / 10 > 10) ? ng / 10 : 10;
+  const int ncand = rk->ncand, p0 = rk->p0, pstep = rk->pstep;
+  double spe[LR_NCAND];
+#pragma unroll
+  for (int q = 0; q < LR_NCAND; q++) spe[q] = 0.0;
+  for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < errn; i += (long long)gridDim.x * BLOCK) {
+    const double x = -1.0 + (double)i / (errn - 1) * 2.0;
+    const double y = (2.0 * x - (-range) - range) / (range - (-range)), y2 = 2.0 * y;
+#pragma unroll
+    for (int q = 0; q < LR_NCAND; q++) {
+      if (q < ncand) {
+        const int p = p0 + pstep * (q + 1);
+        const int eo = p < pmax ? p : pmax;
+        double d1 = 0.0, d2 = 0.0;
+        for (int k = eo; k >= 1; k--) { const double tmp = d1; d1 = y2 * d1 - d2 + s_c[k]; d2 = tmp; }
+        spe[q] += fabs(y * d1 - d2 + 0.5 * s_c[0]);
+      }
+    }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  do {
-    if (threadIdx.x == 0) s_p += s_pstep;
-    __syncthreads();
-    const int p = s_p;
-    const int eo = p < pmax ? p : pmax;
-    double absc = 0.0;
-    for (int i = 0; i <= eo; i++) absc += fabs(s_c[i]);
-    const double abserr = fabs(s_c[eo]) + absc * 2.2204460492503131e-16;
-    double spe = 0.0;
-    for (long long i = threadIdx.x; i < errn; i += BLOCK) {
-      /* gsl_cheb_eval_n_err at x = -1 + 2 i/(errn-1) on the series fitted on [-range, range] (as coded in the reference) */
-      const double x = -1.0 + (double)i / (errn - 1) * 2.0;
-      const double y = (2.0 * x - (-range) - range) / (range - (-range)), y2 = 2.0 * y;
-      double d1 = 0.0, d2 = 0.0;
-      for (int k = eo; k >= 1; k--) { const double tmp = d1; d1 = y2 * d1 - d2 + s_c[k]; d2 = tmp; }
-      spe += fabs(y * d1 - d2 + 0.5 * s_c[0]);
+#pragma unroll
+  for (int q = 0; q < LR_NCAND; q++) {
+    const double v = warp_sum(spe[q]);
+    if (lane == 0) s_red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < LR_NCAND) {
+    double v = 0.0;
+    for (int w = 0; w < BLOCK / 32; w++) v += s_red[w][threadIdx.x];
+    atomicAdd(&rk->spe[threadIdx.x], v);
+  }
+}
+/* part 3 (one CTA): first candidate that passes err/errn <= abstol + reltol * spe (or the last one), then lrexpwp's
+ * coefficient work: refit at order p, cc[0] /= 2, B[l] = sum_{k>=l} cc[k] TC[k][l], BC[l][k] = B[l] C(l,k) */
+__global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ stats, double n_global, int pmax, double abstol, double reltol,
+                                                    const LrRank *__restrict__ rk, LrPlan *plan) {
+  __shared__ double s_f[LR_P1], s_c[LR_P1];
+  __shared__ long long s_tc[LR_P1][LR_P1];
+  __shared__ int s_p;
+  const double meanx = stats[2] / n_global;
+  double range = stats[1] - (-stats[3]);
+  if (range == 0.0) range = 1.0;
+  if (threadIdx.x == 0) {
+    /* Chebyshev polynomials in the monomial basis: T_{n+1} = 2 x T_n - T_{n-1} (exact in 64-bit integers up to n = 50) */
+    for (int a = 0; a < LR_P1; a++) for (int b = 0; b < LR_P1; b++) s_tc[a][b] = 0;
+    s_tc[0][0] = 1; s_tc[1][1] = 1;
+    for (int n = 1; n + 1 < LR_P1; n++)
+      for (int l = 0; l <= n + 1; l++) s_tc[n + 1][l] = (l > 0 ? 2 * s_tc[n][l - 1] : 0) - s_tc[n - 1][l];
+    const long long ng = (long long)n_global;
+    const long long errn = (ng / 10 > 10) ? ng / 10 : 10;
+    int p = rk->p0;
+    for (int q = 0; q < rk->ncand; q++) {
+      p = rk->p0 + rk->pstep * (q + 1);
+      const int eo = p < pmax ? p : pmax;
+      double absc = 0.0;
+      for (int i = 0; i <= eo; i++) absc += fabs(rk->c[i]);
+      const double abserr = fabs(rk->c[eo]) + absc * 2.2204460492503131e-16;
+      const double err = abserr * (double)errn;               /* abserr does not depend on the sample point */
+      if (!((err / errn > (abstol + reltol * rk->spe[q])) & (p < pmax))) break;
     }
-    spe = warp_sum(spe);
-    if (lane == 0) s_red[0][warp] = spe;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot = 0.0;
-      for (int w = 0; w < BLOCK / 32; w++) tot += s_red[0][w];
-      const double err = abserr * (double)errn;            /* abserr does not depend on x */
-      s_go = ((err / errn > (abstol + reltol * tot)) & (p < pmax)) ? 1 : 0;
-    }
-    __syncthreads();
-  } while (s_go);
+    s_p = p;
+  }
+  __syncthreads();
   const int p = s_p;
-  /* lrexpwp: refit at order p, cc[0] /= 2, B[l] = sum_{k>=l} cc[k] TC[k][l], BC[l][k] = B[l] * C(l,k) */
   lr_cheb_init(p, range, s_f, s_c);
   if (threadIdx.x == 0) {
     s_c[0] /= 2;
@@ -157,16 +200,21 @@ __global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ st
   }
 }
 
-/* block partials of A[m][k] = sum_j V_jm xi_j^k over this block's particles */
-__global__ void __launch_bounds__(BLOCK) k_lr_moments(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride, int64_t n,
+/* block partials of A[m][k] = sum_j V_jm xi_j^k over this block's particles: a skinny FP64 GEMM (K = particles).
+ * Register tiling when the output fits 8 accumulators per thread (r = 64, p+1 <= 32): thread t owns the 4 x 2 tile
+ * m0 = 4 (t % (r/4)), k0 = 2 (t / (r/4)); per particle it reads 4 V values and 2 powers from shared memory (LDS.128 / broadcast)
+ * for 8 DFMA, i.e. 0.6 shared-memory wavefronts per FMA instead of 3 for the scalar mapping used for small ranks. */
+constexpr bool LR_TILED = (LR_R % 4 == 0) && ((LR_R / 4) * (LR_P1 / 2) == BLOCK);
+__global__ void __launch_bounds__(BLOCK, 5) k_lr_moments(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride, int64_t n,
                                                        const LrPlan *__restrict__ plan, double *__restrict__ partial) {
-  __shared__ double s_v[LR_MTILE][LR_R + 1];
-  __shared__ double s_pw[LR_MTILE][LR_P1];
+  __shared__ __align__(16) double s_v[LR_MTILE][LR_TILED ? LR_R : LR_R + 1];
+  __shared__ __align__(16) double s_pw[LR_MTILE][LR_P1];
   const int p1 = plan->p + 1;
   const double meanx = plan->meanx, range = plan->range;
-  double acc[LR_NACC];
+  double acc[LR_TILED ? 8 : LR_NACC];
 #pragma unroll
-  for (int s = 0; s < LR_NACC; s++) acc[s] = 0.0;
+  for (int s = 0; s < (LR_TILED ? 8 : LR_NACC); s++) acc[s] = 0.0;
+  const int m0 = LR_TILED ? 4 * (threadIdx.x % (LR_R / 4)) : 0, k0 = LR_TILED ? 2 * (threadIdx.x / (LR_R / 4)) : 0;
   for (int64_t base = (int64_t)blockIdx.x * LR_MTILE; base < n; base += (int64_t)gridDim.x * LR_MTILE) {
     const int cnt = (int)((n - base) < LR_MTILE ? (n - base) : LR_MTILE);
     __syncthreads();
@@ -178,23 +226,43 @@ __global__ void __launch_bounds__(BLOCK) k_lr_moments(const double *__restrict__
       const int jj = threadIdx.x;
       const double xi = (jj < cnt) ? (x[base + jj] - meanx) / range : 0.0;
       double pw = 1.0;
-      for (int k = 0; k < p1; k++) { s_pw[jj][k] = (jj < cnt) ? pw : 0.0; pw *= xi; }
+      for (int k = 0; k < LR_P1; k++) { s_pw[jj][k] = (jj < cnt && k < p1) ? pw : 0.0; pw *= xi; }
     }
     __syncthreads();
+    if (LR_TILED) {
+      if (k0 < p1) {
+#pragma unroll 4
+        for (int jj = 0; jj < LR_MTILE; jj++) {
+          const double2 va = *reinterpret_cast<const double2 *>(&s_v[jj][m0]), vb = *reinterpret_cast<const double2 *>(&s_v[jj][m0 + 2]);
+          const double2 pk = *reinterpret_cast<const double2 *>(&s_pw[jj][k0]);
+          acc[0] = fma(va.x, pk.x, acc[0]); acc[1] = fma(va.y, pk.x, acc[1]); acc[2] = fma(vb.x, pk.x, acc[2]); acc[3] = fma(vb.y, pk.x, acc[3]);
+          acc[4] = fma(va.x, pk.y, acc[4]); acc[5] = fma(va.y, pk.y, acc[5]); acc[6] = fma(vb.x, pk.y, acc[6]); acc[7] = fma(vb.y, pk.y, acc[7]);
+        }
+      }
+    } else {
 #pragma unroll
-    for (int s = 0; s < LR_NACC; s++) {
-      const int q = threadIdx.x + s * BLOCK, m = q % LR_R, k = q / LR_R;
-      if (q < LR_R * LR_P1 && k < p1) {
-        double a = acc[s];
-        for (int jj = 0; jj < LR_MTILE; jj++) a = fma(s_v[jj][m], s_pw[jj][k], a);
-        acc[s] = a;
+      for (int s = 0; s < LR_NACC; s++) {
+        const int q = threadIdx.x + s * BLOCK, m = q % LR_R, k = q / LR_R;
+        if (q < LR_R * LR_P1 && k < p1) {
+          double a = acc[s];
+          for (int jj = 0; jj < LR_MTILE; jj++) a = fma(s_v[jj][m], s_pw[jj][k], a);
+          acc[s] = a;
+        }
       }
     }
   }
+  double *dst = partial + (size_t)blockIdx.x * LR_R * LR_P1;             /* layout q = k * LR_R + m */
+  if (LR_TILED) {
 #pragma unroll
-  for (int s = 0; s < LR_NACC; s++) {
-    const int q = threadIdx.x + s * BLOCK;
-    if (q < LR_R * LR_P1) partial[(size_t)blockIdx.x * LR_R * LR_P1 + q] = acc[s];
+    for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+      for (int mm = 0; mm < 4; mm++) dst[(k0 + kk) * LR_R + m0 + mm] = acc[kk * 4 + mm];
+  } else {
+#pragma unroll
+    for (int s = 0; s < LR_NACC; s++) {
+      const int q = threadIdx.x + s * BLOCK;
+      if (q < LR_R * LR_P1) dst[q] = acc[s];
+    }
   }
 }
 __global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ A) {
@@ -205,33 +273,42 @@ __global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restri
   A[q] = a;                                                             /* q = k * LR_R + m */
 }
 
+/* psi_i for the particles of this GPU.  P1T = p + 1 rounded up to a multiple of 8: the host launches the four
+ * instantiations and the three that do not match the order chosen on the device return at once (no host round trip). */
+template <int P1T>
 __global__ void __launch_bounds__(128) k_lr_apply(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride, int64_t n,
                                                    const LrPlan *__restrict__ plan, const double *__restrict__ A, double *__restrict__ psi) {
-  __shared__ double s_A[LR_P1][LR_R];
-  __shared__ double s_BC[LR_P1][LR_P1];
+  __shared__ double s_A[P1T][LR_R];
+  __shared__ double s_BC[P1T][P1T];
   const int p1 = plan->p + 1;
-  for (int q = threadIdx.x; q < LR_P1 * LR_R; q += 128) s_A[q / LR_R][q % LR_R] = A[q];
-  for (int q = threadIdx.x; q < LR_P1 * LR_P1; q += 128) s_BC[q / LR_P1][q % LR_P1] = plan->BC[q / LR_P1][q % LR_P1];
+  if ((p1 + 7) / 8 * 8 != P1T) return;
+  for (int q = threadIdx.x; q < P1T * LR_R; q += 128) s_A[q / LR_R][q % LR_R] = A[q];
+  for (int q = threadIdx.x; q < P1T * P1T; q += 128) s_BC[q / P1T][q % P1T] = plan->BC[q / P1T][q % P1T];
   __syncthreads();
   const double meanx = plan->meanx, range = plan->range;
   for (int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 128) {
-    double ua[LR_P1], pw[LR_P1];
+    double ua[P1T];
     const double nxi = -(x[i] - meanx) / range;
-    double w = 1.0;
 #pragma unroll
-    for (int k = 0; k < LR_P1; k++) { ua[k] = 0.0; pw[k] = w; w *= nxi; }
-    for (int m = 0; m < LR_R; m++) {
-      const double u = U[(int64_t)m * ustride + i];
+    for (int k = 0; k < P1T; k++) ua[k] = 0.0;
+    constexpr int UB = (LR_R % 8 == 0) ? 8 : 1;              /* U values fetched ahead of their FMAs */
+    for (int m = 0; m < LR_R; m += UB) {
+      double u[UB];
 #pragma unroll
-      for (int k = 0; k < LR_P1; k++) ua[k] = fma(u, s_A[k][m], ua[k]);
+      for (int q = 0; q < UB; q++) u[q] = U[(int64_t)(m + q) * ustride + i];
+#pragma unroll
+      for (int q = 0; q < UB; q++) {
+#pragma unroll
+        for (int k = 0; k < P1T; k++) ua[k] = fma(u[q], s_A[k][m + q], ua[k]);
+      }
     }
+    /* phi_k(nxi) = sum_{l>=k} B[l] C(l,k) nxi^(l-k): Horner in nxi (no table of powers in registers) */
     double y = 0.0;
 #pragma unroll
-    for (int k = 0; k < LR_P1; k++) {
+    for (int k = 0; k < P1T; k++) {
       if (k < p1) {
         double phi = 0.0;
-#pragma unroll
-        for (int l = 0; l < LR_P1; l++) if (l >= k && l < p1) phi = fma(s_BC[l][k], pw[l - k], phi);
+        for (int l = p1 - 1; l >= k; l--) phi = fma(phi, nxi, s_BC[l][k]);
         y = fma(phi, ua[k], y);
       }
     }

@@ -86,7 +86,7 @@ struct odx_handle {
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_attached = false;
   /* low-rank coupling scratch + options (opt lrmax / lrabstol / lrreltol) */
-  void *lr_plan = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr;
+  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr;
   int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
@@ -170,13 +170,14 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   if (h->nranks > 1 && !h->comm) { h->err = "multi-GPU low-rank %C needs odx_comm_init"; return ODX_ENCCL; }
 #endif
   int nblk = (int)((n + LR_MTILE - 1) / LR_MTILE);
-  if (nblk > h->grid_cap) nblk = h->grid_cap;
+  if (nblk > 8 * h->sm_count) nblk = 8 * h->sm_count;
   if (nblk < 1) nblk = 1;
   if (!h->lr_plan) {
     ODX_CUDA(h, cudaMalloc(&h->lr_plan, sizeof(LrPlan)));
+    ODX_CUDA(h, cudaMalloc(&h->lr_rank, sizeof(LrRank)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 8));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_spart, sizeof(double) * 3 * (h->grid_cap + 1)));
-    ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (h->grid_cap + 1)));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (8 * h->sm_count + 1)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
   }
   const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
@@ -194,7 +195,12 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
   }
 #endif
-  k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, (LrPlan *)h->lr_plan);
+  LrRank *rk = (LrRank *)h->lr_rank;
+  k_lr_rank_fit<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->lr_pmax, rk);
+  ODX_TRY(launch_check(h));
+  k_lr_rank_spe<<<2 * h->sm_count, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, rk);
+  ODX_TRY(launch_check(h));
+  k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, rk, (LrPlan *)h->lr_plan);
   ODX_TRY(launch_check(h));
   k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
   ODX_TRY(launch_check(h));
@@ -206,9 +212,13 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
   }
 #endif
-  int ga = (int)((n + 127) / 128); if (ga > 4 * h->sm_count) ga = 4 * h->sm_count; if (ga < 1) ga = 1;
-  k_lr_apply<<<ga, 128, 0, h->stream>>>(x, h->E + (size_t)M::LR0_U * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_A,
-                                        h->PSI + (size_t)M::LR0_PSI * h->cap);
+  int ga = (int)((n + 127) / 128); if (ga > 64 * h->sm_count) ga = 64 * h->sm_count; if (ga < 1) ga = 1;
+  const double *Uc = h->E + (size_t)M::LR0_U * h->cap; double *psi = h->PSI + (size_t)M::LR0_PSI * h->cap;
+  const LrPlan *pl = (const LrPlan *)h->lr_plan;
+  k_lr_apply<8><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+  k_lr_apply<16><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+  k_lr_apply<24><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+  k_lr_apply<32><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi);
   return launch_check(h);
 }
 #endif
@@ -363,7 +373,7 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   Pop p = pop_view(h);
   PersistArgs g; memset(&g, 0, sizeof g);
   g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index; g.recon = h->use_recon;
-  g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32 + BAR_WORDS; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
+  g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
   g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
   fill_peer_args(h, g);
   int64_t grid = (h->n + 2 * PT - 1) / (2 * PT);
@@ -593,8 +603,8 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   for (int k = 0; k < NPAR; k++) h->h_mu[k] = mi->par_defaults[k];
   ODX_CUDA(h, cudaMemcpyAsync(h->d_mu, h->h_mu, sizeof(double) * A1(NPAR), cudaMemcpyHostToDevice, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * 2 * (h->grid_cap + h->coop_blocks + 8)));
-  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS + 8)));
-  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + BAR_WORDS + 2 * PERSIST_MAX_CTAS + 8), h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + 2 * PERSIST_MAX_CTAS + 8)));
+  ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + 2 * PERSIST_MAX_CTAS + 8), h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->sums, sizeof(double) * NSLOT * NRED));
   ODX_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * NSLOT * NRED, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->rmax, sizeof(unsigned long long) * 2));
@@ -614,6 +624,7 @@ void odx_destroy(odx_handle *h) {
   if (h->replica) { odx_destroy(h->replica); h->replica = nullptr; cudaSetDevice(h->device); }
   if (h->gcol) cudaFree(h->gcol);
   if (h->lr_plan) cudaFree(h->lr_plan);
+  if (h->lr_rank) cudaFree(h->lr_rank);
   { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
