@@ -65,6 +65,16 @@ ODX_HD void odx_sincos(double x, double *sp, double *cp) {
 #endif
 }
 
+/* x^(-3/2) and x^(-1/2) emitted for 1 / pow(x, 1.5) and 1 / sqrt(x) */
+ODX_HD double odx_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+ODX_HD double odx_rpow15(double x) { const double r = odx_rsqrt(x); return r * r * r; }
+
 /* reciprocal emitted for `x / f(...)` (a pure call the compiler can share between terms) */
 ODX_HD double odx_rcp(double x) { return 1.0 / x; }
 

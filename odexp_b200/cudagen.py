@@ -123,13 +123,34 @@ def _ternary_to_select(expr: str) -> str:
     return "odx_sel(%s, %s, %s)" % (cond, _ternary_to_select(a), _ternary_to_select(b))
 
 
+def _ternary_to_select_nested(expr: str) -> str:
+    """apply _ternary_to_select to every parenthesised sub-expression that is a whole ternary (after function inlining the
+    guards of the model functions sit inside parentheses)"""
+    out, i = [], 0
+    while i < len(expr):
+        if expr[i] == "(":
+            depth, j = 1, i + 1
+            while j < len(expr) and depth:
+                depth += expr[j] == "("
+                depth -= expr[j] == ")"
+                j += 1
+            inner = _ternary_to_select_nested(expr[i + 1:j - 1])
+            conv = _ternary_to_select(inner)
+            out.append("(" + conv + ")")
+            i = j
+        else:
+            out.append(expr[i])
+            i += 1
+    return "".join(out)
+
+
 def _div_peephole(expr: str) -> str:
     """`x / f(args)` -> `x * odx_rcp(f(args))` for divisions by a function call.
     A double division costs ~20 instructions on the GPU; as a reciprocal it becomes a pure call the compiler can share
     between terms that divide by the same quantity (the three force components of the N-body fixture divide by one r^3).
     Result differs from the IEEE quotient by at most 1.5 ulp."""
     out, pos = [], 0
-    pat = re.compile(r"/\s*(%s)\s*\(" % IDENT)
+    pat = re.compile(r"/\s*(%s)?\s*\(" % IDENT)
     while True:
         m = pat.search(expr, pos)
         if not m:
@@ -143,8 +164,53 @@ def _div_peephole(expr: str) -> str:
         if depth:
             out.append(expr[pos:])
             return "".join(out)
-        out.append(expr[pos:m.start()] + "* odx_rcp(" + m.group(1) + "(" + _div_peephole(expr[m.end():i - 1]) + "))")
+        out.append(expr[pos:m.start()] + "* odx_rcp(" + (m.group(1) or "") + "(" + _div_peephole(expr[m.end():i - 1]) + "))")
         pos = i
+
+
+def _inline_funs(expr: str, funs) -> str:
+    """substitute one-line model functions textually (arguments parenthesised), innermost definitions last, so that the
+    peepholes below see through `grav(...)` / `normCube(...)`; the functions are still emitted for host use"""
+    for _ in range(8):                      # bounded nesting depth
+        changed = False
+        for f in funs:
+            for b, e, args in _find_call(expr, f.name):
+                if len(args) != len(f.args):
+                    continue
+                body = f.body
+                # two-phase substitution so that an argument text cannot be captured by a later parameter name
+                for k, a in enumerate(f.args):
+                    body = re.sub(r"\b%s\b" % re.escape(a), "\x00%d\x00" % k, body)
+                for k, a in enumerate(args):
+                    body = body.replace("\x00%d\x00" % k, "(" + a + ")")
+                expr = expr[:b] + "(" + body + ")" + expr[e:]
+                changed = True
+                break
+            if changed:
+                break
+        if not changed:
+            return expr
+    return expr
+
+
+def _rpow_peephole(expr: str) -> str:
+    """odx_rcp(odx_pow15(x)) -> odx_rpow15(x) = rsqrt(x)^3 (one MUFU.RSQ64H + Newton instead of an IEEE sqrt and an IEEE
+    reciprocal; <= 3 ulp), likewise odx_rcp(odx_pow05(x)) -> odx_rsqrt(x)"""
+    for inner, repl in (("odx_pow15", "odx_rpow15"), ("odx_pow05", "odx_rsqrt")):
+        changed = True
+        while changed:
+            changed = False
+            for b, e, args in _find_call(expr, "odx_rcp"):
+                if len(args) == 1:
+                    a = _strip_outer_parens(args[0])
+                    m = re.match(r"^%s\s*\(" % inner, a)
+                    if m:
+                        calls = list(_find_call(a, inner))
+                        if calls and calls[0][0] == 0 and calls[0][1] == len(a):
+                            expr = expr[:b] + "%s(%s)" % (repl, calls[0][2][0]) + expr[e:]
+                            changed = True
+                            break
+    return expr
 
 
 class Emitter:
@@ -187,9 +253,12 @@ class Emitter:
             return {"MA": "(odx_aux[%d])", "OA": "(odx_oaux[%d])", "SA": "(odx_c.has_sister ? odx_c.sis_aux[%d] : 0.0)"}[kind] % i
         raise PopError("unknown macro %s" % kind)
 
-    def tr(self, expr: str, where: str) -> str:
-        """translate one model expression to C++"""
+    def tr(self, expr: str, where: str, exact: bool = False) -> str:
+        """translate one model expression to C++.  exact = True (initial conditions): no arithmetic peepholes, so that replayed
+        initial conditions stay bit-identical to the reference's"""
         e = expr.strip().rstrip(";")
+        if self.fast_div and self.m.funs and not exact:
+            e = _inline_funs(e, self.m.funs)
         e = re.sub(r"\b(MU|MF|MC|MY|OY|SY|ME|OE|SE|MA|OA|SA)\(\s*(%s)\s*\)" % IDENT,
                    lambda mm: self._macro(mm.group(1), mm.group(2), where), e)
         if re.search(r"\bKY\s*\(", e):
@@ -210,10 +279,11 @@ class Emitter:
                 e = e[:b] + "(odx_c.atbirth ? (%s) : (%s))" % (args[0], args[1]) + e[en:]
         for b, en, args in list(_find_call(e, "STOPIF"))[::-1]:
             e = e[:b] + "odx_stopif(odx_c, (%s))" % args[0] + e[en:]
-        if self.fast_pow:
+        if self.fast_pow and not exact:
             e = _pow_peephole(e)
-        if self.fast_div:
-            e = _div_peephole(e)
+        if self.fast_div and not exact:
+            e = _rpow_peephole(_div_peephole(e))
+            e = _ternary_to_select_nested(e)
         return _mangle_expr(e)
 
     def cse(self, e, cache, out):
@@ -355,12 +425,12 @@ class Emitter:
                 it = mangle(e.iterator)
                 w("    double %s[%d];" % (mangle(e.name), e.start + e.length))
                 w("    for (int %s = %d; %s < %d; %s++) { %s[%s] = %s; odx_e[%d + %s - %d] = %s[%s]; }" %
-                  (it, e.start, it, e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "expr " + e.name), b, it, e.start,
+                  (it, e.start, it, e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "expr " + e.name, exact=True), b, it, e.start,
                    mangle(e.name), it))
             else:
-                w("    const double %s = %s; odx_e[%d] = %s;" % (mangle(e.name), self.tr(e.rhs, "expr " + e.name), b, mangle(e.name)))
+                w("    const double %s = %s; odx_e[%d] = %s;" % (mangle(e.name), self.tr(e.rhs, "expr " + e.name, exact=True), b, mangle(e.name)))
         for e in m.inits:
-            w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name)))
+            w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name, exact=True)))
         w("  }\n")
         w("  ODX_HD static constexpr bool psi_is_pairwise(int k) { return %s; }\n" %
           (" || ".join("k == %d" % self.psi_idx[c.name] for c in pair_cpls) or "false"))
