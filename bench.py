@@ -230,8 +230,9 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of k_chain_persist from the ncu --set full capture
-                             # profiles/r1_k_chain_persist_kuramoto_n16M.txt: 56.60 GB for 20 steps at N=2^24 = 168.7 B per particle-step
-                             "traffic": (168.7 * n_local * args.steps) if (world == 1 and n_total == N_TOTAL) else None,
+                             # profiles/r1_k_chain_persist_kuramoto_n16M.txt: 44.54 GB for 20 steps at N=2^24 = 132.7 B per particle-step
+                             # (152 B by construction, minus what the alternating sweep direction finds in L2)
+                             "traffic": (132.7 * n_local * args.steps) if (world == 1 and n_total == N_TOTAL) else None,
                              "traffic_unit": "bytes per launch (one cooperative launch = all timed steps)",
                              "peak_source": how, "algorithmic_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_local * args.steps,
