@@ -370,8 +370,12 @@ struct PersistArgs {
   double *totals;                  /* [2][NRED] global sums published by CTA 0 (multi-GPU) */
   double *sums_new, *sums_report;  /* out: sums of the new Y (+ rates) / sums used by the last RHS evaluation */
   int rank, nranks; uint32_t epoch0;
-  double *mailbox; uint32_t *mailflag;                 /* local: [2][MAX_RANKS][NRED], [2][MAX_RANKS] */
+  double *mailbox; uint32_t *mailflag;                 /* local: [2][MAX_RANKS][NRED], [2][MAX_RANKS] (k_peer_allreduce) */
   double *peer_box[MAX_RANKS]; uint32_t *peer_flag[MAX_RANKS];
+  unsigned long long *ll_part;     /* [2][PERSIST_MAX_CTAS][LLW] block partials as LL words */
+  unsigned long long *ll_gtot;     /* [2][LLW] global sums republished by CTA 0 (multi-GPU) */
+  unsigned long long *mail_ll;     /* local mailbox [2][MAX_RANKS][LLW] written by the peers */
+  unsigned long long *peer_ll[MAX_RANKS];
   int *abort_flag;
 };
 
@@ -411,6 +415,52 @@ __device__ __forceinline__ void block_partial(const double (&red)[NRED], double 
   }
   __syncthreads();
 }
+/* low-latency words: {tag:32 | data:32}; a double is two words (low half, high half) */
+constexpr int LLW = 2 * NRED;
+__device__ __forceinline__ unsigned long long ll_pack(double v, int half, uint32_t tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const uint32_t d = half ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+  return ((unsigned long long)tag << 32) | d;
+}
+__device__ __forceinline__ double ll_unpack(uint32_t lo, uint32_t hi) {
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__device__ __forceinline__ void ll_store_gpu(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load_gpu(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ll_store_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+/* block sum of red[] into shared s_bp[NRED] */
+template <int NT>
+__device__ __forceinline__ void block_partial_smem(const double (&red)[NRED], double *s_bp) {
+  __shared__ double s_part4[NT / 32][NRED];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    const double v = warp_sum(red[k]);
+    if (lane == 0) s_part4[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) v += s_part4[w][threadIdx.x];
+    s_bp[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
 /* fixed-order block sum of per-thread accumulators into s_tot[NRED] */
 template <int NT>
 __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s_tot) {
@@ -431,13 +481,14 @@ __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s
   }
   __syncthreads();
 }
-constexpr int PERSIST_MAX_CTAS = 1024;
+constexpr int PERSIST_MAX_CTAS = 256;
 #ifndef PERSIST_THREADS
 #define PERSIST_THREADS 1024
 #endif
 constexpr int PT = PERSIST_THREADS;
 __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_persist(Pop p, PersistArgs g) {
-  __shared__ double s_tot[NRED];
+  __shared__ double s_tot[NRED], s_bp[NRED];
+  __shared__ uint32_t s_words[PERSIST_MAX_CTAS * LLW];
   double mfd[A1(NMFD)];
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
   __syncthreads();
@@ -474,67 +525,71 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
         chain_sweep<false, true>(p, a, mfd, red);
       }
-      /* ---- mean-field barrier without a barrier: every CTA publishes (partial sums, epoch tag) and every CTA waits for
-       * the tags of all CTAs, then adds the partials itself in a fixed order: three dependent L2 round trips, no atomics,
-       * and identical bits in every CTA.  Buffers alternate with the epoch parity (a CTA can be one epoch ahead at most). */
+      /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
+       * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence
+       * or separate flag round trip is needed (the LL idea of NCCL's small-message protocol).  Every CTA publishes its
+       * block partials as such words, every CTA polls the words of all CTAs and adds the partials itself in a fixed order
+       * (identical bits everywhere, no atomics).  Buffers alternate with the epoch parity: a CTA is one epoch ahead at most. */
       const size_t par = (size_t)(epoch & 1u);
       const uint32_t tag = epoch + 1u;
-      double *part = g.partial + par * gridDim.x * NRED;
-      unsigned int *tags = g.bar + par * PERSIST_MAX_CTAS;
-      block_partial<PT>(red, part);                /* threads < NRED stored part[blockIdx][*] */
-      if (threadIdx.x < NRED) __threadfence();
+      unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
+      block_partial_smem<PT>(red, s_bp);
+      if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
+      for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += PT) {
+        unsigned long long w; unsigned long long spins = 0;
+        while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (++spins > (1ull << 28)) { if (g.abort_flag) *g.abort_flag = 1; break; } }
+        s_words[idx] = (uint32_t)w;
+      }
       __syncthreads();
-      if (threadIdx.x == 0) st_release_u32(tags + blockIdx.x, tag);
       {
         double acc[NRED];
 #pragma unroll
         for (int k = 0; k < NRED; k++) acc[k] = 0.0;
         for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += PT) {
-          unsigned long long spins = 0;
-          while (ld_acquire_u32(tags + b2) != tag) { if (++spins > (1ull << 28)) { if (g.abort_flag) *g.abort_flag = 1; break; } }
 #pragma unroll
-          for (int k = 0; k < NRED; k++) acc[k] += __ldcg(&part[(size_t)b2 * NRED + k]);
+          for (int k = 0; k < NRED; k++) acc[k] += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
         }
         block_total<PT>(acc, s_tot);
       }
       if (g.nranks > 1) {
-        /* cross-GPU: CTA 0 stores this rank's sums and the epoch tag straight into every peer's mailbox over NVLink
-         * (st.release.sys on IPC-mapped pointers), waits for the other ranks' tags in its own GPU's mailbox, adds the rank
-         * sums in rank order and publishes the global sums to the other CTAs of this GPU (one more local round trip, but
-         * only one CTA polls the lines the peers write to) */
-        double *gtot = g.totals + par * NRED;
-        unsigned int *gflag = g.bar + 2 * PERSIST_MAX_CTAS + par;
+        /* cross-GPU: CTA 0 stores this rank's sums as LL words straight into every peer's mailbox over NVLink (8-byte
+         * st.relaxed.sys on IPC-mapped pointers), polls the words of the other ranks in its own GPU's mailbox, adds the rank
+         * sums in rank order and republishes the global sums to the other CTAs of this GPU, again as LL words */
+        unsigned long long *gt = g.ll_gtot + par * LLW;
         if (blockIdx.x == 0) {
-          if (threadIdx.x < NRED) {
+          if (threadIdx.x < LLW) {
+            const unsigned long long w = ll_pack(s_tot[threadIdx.x >> 1], threadIdx.x & 1, tag);
             for (int r = 0; r < g.nranks; r++)
-              if (r != g.rank) g.peer_box[r][(par * MAX_RANKS + g.rank) * NRED + threadIdx.x] = s_tot[threadIdx.x];
-            __threadfence_system();
+              if (r != g.rank) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + threadIdx.x, w);
           }
-          __syncthreads();
-          if (threadIdx.x < g.nranks && threadIdx.x != g.rank) {
-            st_release_sys_u32(g.peer_flag[threadIdx.x] + par * MAX_RANKS + g.rank, tag);
-            const uint32_t *w = g.mailflag + par * MAX_RANKS + threadIdx.x;
-            unsigned long long spins = 0;
-            while (ld_acquire_sys_u32(w) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+          if (threadIdx.x < (unsigned)(g.nranks * LLW)) {
+            const int r = threadIdx.x / LLW, k = threadIdx.x % LLW;
+            if (r != g.rank) {
+              unsigned long long w; unsigned long long spins = 0;
+              while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + k)) >> 32) != tag) {
+                if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; }
+              }
+              s_words[threadIdx.x] = (uint32_t)w;
+            }
           }
           __syncthreads();
           if (threadIdx.x < NRED) {
             double v = 0.0;
             for (int r = 0; r < g.nranks; r++)
-              v += (r == g.rank) ? s_tot[threadIdx.x] : __ldcv(&g.mailbox[(par * MAX_RANKS + r) * NRED + threadIdx.x]);
-            s_tot[threadIdx.x] = v;
-            gtot[threadIdx.x] = v;
-            __threadfence();
+              v += (r == g.rank) ? s_tot[threadIdx.x] : ll_unpack(s_words[r * LLW + 2 * threadIdx.x], s_words[r * LLW + 2 * threadIdx.x + 1]);
+            s_bp[threadIdx.x] = v;
           }
           __syncthreads();
-          if (threadIdx.x == 0) st_release_u32(gflag, tag);
+          if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
+          if (threadIdx.x < LLW) ll_store_gpu(gt + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
         } else {
-          if (threadIdx.x == 0) {
-            unsigned long long spins = 0;
-            while (ld_acquire_u32(gflag) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+          if (threadIdx.x < LLW) {
+            unsigned long long w; unsigned long long spins = 0;
+            while ((uint32_t)((w = ll_load_gpu(gt + threadIdx.x)) >> 32) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+            s_words[threadIdx.x] = (uint32_t)w;
           }
           __syncthreads();
-          if (threadIdx.x < NRED) s_tot[threadIdx.x] = __ldcg(&gtot[threadIdx.x]);
+          if (threadIdx.x < NRED) s_tot[threadIdx.x] = ll_unpack(s_words[2 * threadIdx.x], s_words[2 * threadIdx.x + 1]);
         }
         __syncthreads();
       }

@@ -80,6 +80,7 @@ struct odx_handle {
   ncclComm_t comm = nullptr;
 #endif
   /* persistent step kernel + peer-memory exchange */
+  unsigned long long *ll_words = nullptr;     /* LL exchange words of the persistent kernel (zero-initialised) */
   int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
   uint32_t epoch = 0;
   void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
@@ -319,7 +320,10 @@ static int do_rhs(odx_handle *h, double t, double hcur) {
 
 constexpr size_t MAIL_BOX_BYTES = sizeof(double) * 2 * MAX_RANKS * NRED;
 constexpr size_t MAIL_FLAG_BYTES = sizeof(uint32_t) * 2 * MAX_RANKS;
-constexpr size_t MAIL_BYTES = ((MAIL_BOX_BYTES + MAIL_FLAG_BYTES + sizeof(int) + 255) / 256) * 256;
+constexpr size_t MAIL_LL_OFF = ((MAIL_BOX_BYTES + MAIL_FLAG_BYTES + sizeof(int) + 255) / 256) * 256;
+constexpr size_t MAIL_LL_BYTES = sizeof(unsigned long long) * 2 * MAX_RANKS * LLW;
+constexpr size_t MAIL_BYTES = ((MAIL_LL_OFF + MAIL_LL_BYTES + 255) / 256) * 256;
+static inline unsigned long long *mail_ll(void *m) { return (unsigned long long *)((char *)m + MAIL_LL_OFF); }
 static inline double *mail_box(void *m) { return (double *)m; }
 static inline uint32_t *mail_flag(void *m) { return (uint32_t *)((char *)m + MAIL_BOX_BYTES); }
 static inline int *mail_abort(void *m) { return (int *)((char *)m + MAIL_BOX_BYTES + MAIL_FLAG_BYTES); }
@@ -363,7 +367,9 @@ static void fill_peer_args(odx_handle *h, PersistArgs &g) {
   for (int r = 0; r < MAX_RANKS; r++) {
     void *m = (r < h->nranks) ? (r == h->rank ? h->mail : h->peer_mail[r]) : nullptr;
     g.peer_box[r] = m ? mail_box(m) : nullptr; g.peer_flag[r] = m ? mail_flag(m) : nullptr;
+    g.peer_ll[r] = m ? mail_ll(m) : nullptr;
   }
+  g.mail_ll = h->mail ? mail_ll(h->mail) : nullptr;
 }
 
 /* nsteps whole steps in one cooperative launch (see k_chain_persist) */
@@ -374,6 +380,7 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   PersistArgs g; memset(&g, 0, sizeof g);
   g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index; g.recon = h->use_recon;
   g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
+  g.ll_part = h->ll_words; g.ll_gtot = h->ll_words + (size_t)2 * PERSIST_MAX_CTAS * LLW;
   g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
   fill_peer_args(h, g);
   int64_t grid = (h->n + 2 * PT - 1) / (2 * PT);
@@ -605,6 +612,8 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   ODX_CUDA(h, cudaMalloc((void **)&h->partial, sizeof(double) * (size_t)NRED * 2 * (h->grid_cap + h->coop_blocks + 8)));
   ODX_CUDA(h, cudaMalloc((void **)&h->counter, sizeof(unsigned int) * (32 + 2 * PERSIST_MAX_CTAS + 8)));
   ODX_CUDA(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * (32 + 2 * PERSIST_MAX_CTAS + 8), h->stream));
+  ODX_CUDA(h, cudaMalloc((void **)&h->ll_words, sizeof(unsigned long long) * ((size_t)2 * PERSIST_MAX_CTAS * LLW + 2 * LLW + 8)));
+  ODX_CUDA(h, cudaMemsetAsync(h->ll_words, 0, sizeof(unsigned long long) * ((size_t)2 * PERSIST_MAX_CTAS * LLW + 2 * LLW + 8), h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->sums, sizeof(double) * NSLOT * NRED));
   ODX_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * NSLOT * NRED, h->stream));
   ODX_CUDA(h, cudaMalloc((void **)&h->rmax, sizeof(unsigned long long) * 2));
@@ -628,6 +637,7 @@ void odx_destroy(odx_handle *h) {
   { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
+  if (h->ll_words) cudaFree(h->ll_words);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
                     h->sums, h->stage_dev, h->gather, h->pair_part};
   for (double *b : bufs) if (b) cudaFree(b);
