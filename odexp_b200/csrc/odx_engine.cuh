@@ -710,6 +710,7 @@ struct TabArgs {
   double eps_abs, eps_rel; int final_; uint32_t eval_index; unsigned long long *rmax_bits;
   const double *ycur;   /* state the RHS is evaluated at (Y for s == 1, else YS) */
   double *K1;           /* slope k_1 (= dydt_in of gsl_odeiv2_evolve_apply); k_2..k_6 live in Pop::KS */
+  const double *y0src;  /* state at the start of the (sub)step (Y, or the half-step state of the step-doubling rk4) */
   int skip_rhs;         /* s == 1 only: k_1 is already in K1 (reused dydt_out of the previous step, or a retry) */
 };
 __device__ __forceinline__ double *slope_ptr(const Pop &p, const TabArgs &a, int j) {   /* j 0-based */
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
   for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
     double y0[A1(NVAR)], yc[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)];
     double death = 0.0, repli = 0.0;
-    load_cols<NVAR>(p.Y, p.stride, i, y0);
+    load_cols<NVAR>(a.y0src, p.stride, i, y0);
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
     load_cols<NVAR>(a.ycur, p.stride, i, yc);
@@ -768,6 +769,24 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
     if ((threadIdx.x & 31) == 0) atomicMax(a.rmax_bits, (unsigned long long)__double_as_longlong(rloc));
   }
   if (NMFD > 0 || M::HAS_BIRTH) grid_reduce<NRED>(red, r);
+}
+
+/* step-doubling error of GSL's rk4: yerr = 4 (y_two_halves - y_one_full) / 15, rmax = max |yerr| / (eps_abs + eps_rel |y|) */
+__global__ void __launch_bounds__(BLOCK) k_err_doubling(Pop p, const double *__restrict__ ytwo, const double *__restrict__ yone,
+                                                         double eps_abs, double eps_rel, unsigned long long *rmax_bits) {
+  double rloc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) {
+      const double y = ytwo[(int64_t)v * p.stride + i], y1 = yone[(int64_t)v * p.stride + i];
+      const double yerr = 4.0 * (y - y1) / 15.0;
+      const double rr = fabs(yerr) / fabs(eps_rel * fabs(y) + eps_abs);
+      if (rr > rloc) rloc = rr;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_down_sync(0xffffffffu, rloc, o); if (other > rloc) rloc = other; }
+  if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(rloc));
 }
 
 /* AoS <-> SoA transposes for upload / download (host arrays are particle-major like the reference's y[]) */

@@ -58,7 +58,7 @@ struct odx_handle {
   int64_t cap = 0, n = 0;
   int32_t max_id = 0;
   double *Y = nullptr, *YS = nullptr, *ACC = nullptr, *E = nullptr, *AUX = nullptr, *PSI = nullptr, *DEATH = nullptr,
-         *REPLI = nullptr, *KS = nullptr, *K1 = nullptr, *DOUT = nullptr;
+         *REPLI = nullptr, *KS = nullptr, *K1 = nullptr, *DOUT = nullptr, *YONE = nullptr, *YH = nullptr, *K1B = nullptr;
   int32_t *ID = nullptr;
   double *d_mu = nullptr;
   double h_mu[A1(NPAR)];
@@ -472,6 +472,24 @@ static const Tableau TAB_RKCK = {
     {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0, 125.0 / 594.0 - 13525.0 / 55296.0,
      -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5};
 
+static int read_rmax(odx_handle *h, double *rmax_out) {
+  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  double rmax; memcpy(&rmax, h->h_pin, sizeof rmax);
+#ifdef ODX_HAVE_NCCL_H
+  if (h->nranks > 1) {
+    ODX_CUDA(h, cudaMemcpyAsync(h->rmax, &rmax, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = g_nccl.AllReduce(h->rmax, h->rmax, 1, ncclDouble, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce(MAX): ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+    ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(&rmax, h->h_pin, sizeof rmax);
+  }
+#endif
+  *rmax_out = rmax;
+  return ODX_SUCCESS;
+}
+
 /* one attempted embedded step of size hh from (t, Y): leaves y_new in YS, dydt_out in DOUT, returns rmax */
 static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh, double *rmax_out) {
   const int g = grid_for(h, h->n);
@@ -487,7 +505,7 @@ static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh
     a.s = s; a.h = hh; a.K1 = h->K1; a.eps_abs = h->eps_abs; a.eps_rel = h->eps_rel; a.rmax_bits = h->rmax;
     a.final_ = (s == 6);
     a.skip_rhs = (s == 1 && h->k1_valid) ? 1 : 0;
-    a.ycur = (s == 1) ? h->Y : h->YS;
+    a.ycur = (s == 1) ? h->Y : h->YS; a.y0src = h->Y;
     a.sums_in = sums_ptr(h, s == 1 ? h->y_slot : SLOT_STAGE + (s - 2));
     a.t_eval = (s == 1) ? t : t + T.ah[s - 2] * hh;
     a.t_next = (s == 6) ? t + hh : t + T.ah[s - 1] * hh;
@@ -504,22 +522,55 @@ static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh
   h->k1_valid = true;   /* K1 now holds f(t, Y) whatever happens to this attempt */
   /* dydt_out = f(t + h, y_new): also refreshes aux / rates / reported mean fields like every reference RHS call */
   ODX_TRY(eval_rhs_out(h, h->YS, SLOT_STAGE + 5, t + hh, hh, h->DOUT));
-  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
-  double rmax; memcpy(&rmax, h->h_pin, sizeof rmax);
-#ifdef ODX_HAVE_NCCL_H
-  if (h->nranks > 1) {
-    /* allreduce(MAX) of one double per attempted step: every rank takes the same accept / reject decision */
-    ODX_CUDA(h, cudaMemcpyAsync(h->rmax, &rmax, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    ncclResult_t r = g_nccl.AllReduce(h->rmax, h->rmax, 1, ncclDouble, ncclMax, h->comm, h->stream);
-    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce(MAX): ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
-    ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(&rmax, h->h_pin, sizeof rmax);
+  return read_rmax(h, rmax_out);
+}
+
+/* one classic RK4 (sub)step of size hh from y0src through the tableau kernel: result in YS, its %M sums in out_slot.
+ * k1buf holds (or receives) the slope at y0src. */
+static int rk4_tab_step(odx_handle *h, const double *y0src, double *k1buf, bool k1_valid, int y0_slot, double t, double hh, int out_slot) {
+  static const double cnode[5] = {0.0, 0.5, 0.5, 1.0, 1.0};
+  const int g = grid_for(h, h->n);
+  Pop p = pop_view(h);
+  if (!k1_valid) ODX_TRY(compute_psi(h, y0src, t));
+  for (int s = 1; s <= 4; s++) {
+    TabArgs a; memset(&a, 0, sizeof a);
+    a.s = s; a.h = hh; a.K1 = k1buf; a.y0src = y0src; a.eps_abs = h->eps_abs; a.eps_rel = h->eps_rel; a.rmax_bits = h->rmax;
+    a.final_ = 0; a.skip_rhs = (s == 1 && k1_valid) ? 1 : 0;
+    a.ycur = (s == 1) ? y0src : h->YS;
+    a.sums_in = sums_ptr(h, s == 1 ? y0_slot : SLOT_STAGE + (s - 2));
+    a.t_eval = t + cnode[s - 1] * hh; a.t_next = t + cnode[s] * hh;
+    if (s == 1) a.b[0] = 0.5;
+    else if (s == 2) a.b[1] = 0.5;
+    else if (s == 3) a.b[2] = 1.0;
+    else { a.b[0] = 1.0 / 6.0; a.b[1] = 1.0 / 3.0; a.b[2] = 1.0 / 3.0; a.b[3] = 1.0 / 6.0; }
+    a.eval_index = h->eval_index; h->eval_index += 2;
+    if (!a.skip_rhs) h->rhs_evals++;
+    const int slot = (s == 4) ? out_slot : SLOT_STAGE + (s - 1);
+    k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, slot));
+    ODX_TRY(launch_check(h));
+    if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, slot));
+    ODX_TRY(compute_psi(h, h->YS, a.t_next));
   }
-#endif
-  *rmax_out = rmax;
   return ODX_SUCCESS;
+}
+
+/* one attempted step of GSL's rk4 (step doubling, 11 RHS evaluations): y_one = RK4(h), y = RK4(h/2) o RK4(h/2),
+ * yerr = 4 (y - y_one) / 15.  Leaves y in YS and dydt_out in DOUT like embedded_attempt. */
+static int rk4_doubling_attempt(odx_handle *h, double t, double hh, double *rmax_out) {
+  const size_t colbytes = sizeof(double) * (size_t)A1(NVAR) * h->cap;
+  ODX_CUDA(h, cudaMemsetAsync(h->rmax, 0, sizeof(unsigned long long), h->stream));
+  if (!h->k1_valid) ODX_TRY(ensure_moments_Y(h, t));
+  ODX_TRY(rk4_tab_step(h, h->Y, h->K1, h->k1_valid, h->y_slot, t, hh, SLOT_STAGE + 3));
+  h->k1_valid = true;
+  ODX_CUDA(h, cudaMemcpyAsync(h->YONE, h->YS, colbytes, cudaMemcpyDeviceToDevice, h->stream));
+  ODX_TRY(rk4_tab_step(h, h->Y, h->K1, true, h->y_slot, t, hh / 2.0, SLOT_STAGE + 4));
+  ODX_CUDA(h, cudaMemcpyAsync(h->YH, h->YS, colbytes, cudaMemcpyDeviceToDevice, h->stream));
+  ODX_TRY(eval_rhs_out(h, h->YH, SLOT_STAGE + 4, t + hh / 2.0, hh, h->K1B));
+  ODX_TRY(rk4_tab_step(h, h->YH, h->K1B, true, SLOT_STAGE + 4, t + hh / 2.0, hh / 2.0, SLOT_STAGE + 5));
+  ODX_TRY(eval_rhs_out(h, h->YS, SLOT_STAGE + 5, t + hh, hh, h->DOUT));
+  k_err_doubling<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(pop_view(h), h->YS, h->YONE, h->eps_abs, h->eps_rel, h->rmax);
+  ODX_TRY(launch_check(h));
+  return read_rmax(h, rmax_out);
 }
 
 static int alloc_cols(odx_handle *h, double **ptr, int ncol) {
@@ -638,7 +689,7 @@ void odx_destroy(odx_handle *h) {
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   if (h->ll_words) cudaFree(h->ll_words);
-  double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->d_mu, h->partial,
+  double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->YONE, h->YH, h->K1B, h->d_mu, h->partial,
                     h->sums, h->stage_dev, h->gather, h->pair_part};
   for (double *b : bufs) if (b) cudaFree(b);
   if (h->ID) cudaFree(h->ID);
@@ -954,11 +1005,17 @@ int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uin
  * on rmax > 1.1 shrink by max(0.2, 0.9 rmax^(-1/ord)) and retry, on rmax < 0.5 grow by min(5, max(1, 0.9 rmax^(-1/(ord+1)))). */
 int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
   ODX_CUDA(h, cudaSetDevice(h->device));
-  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK) { h->err = "odx_evolve_apply: method must be rkf45 or rkck"; return ODX_EUNSUP; }
+  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4) {
+    h->err = "odx_evolve_apply: method must be rkf45, rkck or rk4"; return ODX_EUNSUP;
+  }
   if (h->n <= 0) { *t = t1; return ODX_SUCCESS; }
   const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : TAB_RKCK;
+  const unsigned order = (method == ODX_METH_RK4) ? 4u : T.order;
   if (!h->KS) {
     ODX_TRY(alloc_cols(h, &h->KS, 5 * A1(NVAR))); ODX_TRY(alloc_cols(h, &h->K1, NVAR)); ODX_TRY(alloc_cols(h, &h->DOUT, NVAR));
+  }
+  if (method == ODX_METH_RK4 && !h->YONE) {
+    ODX_TRY(alloc_cols(h, &h->YONE, NVAR)); ODX_TRY(alloc_cols(h, &h->YH, NVAR)); ODX_TRY(alloc_cols(h, &h->K1B, NVAR));
   }
   const double t0 = *t; double h0 = *hstep; const double dt = t1 - t0; int final_step = 0;
   if ((dt < 0.0 && h0 > 0.0) || (dt > 0.0 && h0 < 0.0)) { h->err = "step direction must match interval direction"; return ODX_EINVAL; }
@@ -966,15 +1023,16 @@ int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hs
   for (;;) {
     if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) { h0 = dt; final_step = 1; } else final_step = 0;
     double rmax = 0.0;
-    ODX_TRY(embedded_attempt(h, T, t0, h0, &rmax));
+    if (method == ODX_METH_RK4) ODX_TRY(rk4_doubling_attempt(h, t0, h0, &rmax));
+    else ODX_TRY(embedded_attempt(h, T, t0, h0, &rmax));
     if (rmax < DBL_MIN) rmax = DBL_MIN;
     const double h_old = h0; const double S = 0.9; int dec = 0;
     if (rmax > 1.1) {
-      double r = S / pow(rmax, 1.0 / T.order);
+      double r = S / pow(rmax, 1.0 / order);
       if (r < 0.2) r = 0.2;
       h0 = r * h_old; dec = 1;
     } else if (rmax < 0.5) {
-      double r = S / pow(rmax, 1.0 / (T.order + 1.0));
+      double r = S / pow(rmax, 1.0 / (order + 1.0));
       if (r > 5.0) r = 5.0;
       if (r < 1.0) r = 1.0;
       h0 = r * h_old;

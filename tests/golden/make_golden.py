@@ -23,6 +23,9 @@ CASES = {
     "kuramoto_fe_n100": ("kuramoto", {"meth": "fe", "h0": 0.05, "res": 3, "ps": 100}, (0, 0.5), KUR),
     "kuramoto_rkck_n200": ("kuramoto", {"meth": "rkck", "res": 6, "ps": 200}, (0, 5.0), KUR),
     "kuramoto_rkf45_n200": ("kuramoto", {"meth": "rkf45", "res": 6, "ps": 200, "abstol": 1e-9, "reltol": 1e-9}, (0, 5.0), KUR),
+    # BASELINE config 1: examples/kuramoto.pop exactly as shipped (N=1000, meth rkck, res 801, t in [0,160]), no overrides
+    "kuramoto_shipped_rkck": ("kuramoto_shipped", {}, None, KUR),
+    "kuramoto_rk4_n50": ("kuramoto", {"meth": "rk4", "res": 6, "ps": 50}, (0, 5.0), KUR),      # GSL step-doubling rk4
     "nbody_dde_n64": ("nbody", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 64}, (0, 0.4), NBD),
     # short horizon: at T=0.4 a close encounter makes the reference itself change by 7e-6 under a 1e-7 relative change of the tolerance
     "nbody_rkf45_n96": ("nbody", {"meth": "rkf45", "h0": 0.02, "res": 3, "ps": 96, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 0.2), NBD),
@@ -32,6 +35,8 @@ CASES = {
 def main():
     for name, (fx, opts, ts, dims) in CASES.items():
         r = refrun.run(fx, opts, timespan=ts, dims=dims)
+        if name == "kuramoto_shipped_rkck":
+            opts, ts = {"meth": "rkck", "res": 801, "ps": 1000}, (0, 160)     # what the shipped file sets itself
         st, tr = r["stats"], r["traj"]
         last = tr[tr["step"] == tr["step"].max()]
         first = tr[tr["step"] == 0]

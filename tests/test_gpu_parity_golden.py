@@ -17,7 +17,7 @@ def run_case(model_lib, name):
     g = load_golden(name)
     meta = ast.literal_eval(str(g["meta"][0]))
     o = meta["opts"]
-    lib = model_lib(meta["fixture"])
+    lib = model_lib("kuramoto" if meta["fixture"] == "kuramoto_shipped" else meta["fixture"])
     pop = capi.Population(lib, capacity=max(1024, int(o["ps"])))
     kw = dict(meth=o["meth"], res=o["res"], popsize=o["ps"], h0=o.get("h0", 0.1), hmin=o.get("hmin", 1e-5),
               abstol=o.get("abstol", 1e-6), reltol=o.get("reltol", 1e-6))
@@ -59,7 +59,7 @@ def test_kuramoto_fixed_step(model_lib, name):
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=RTOL_STATE, atol=1e-13)
 
 
-@pytest.mark.parametrize("name", ["kuramoto_rkck_n200", "kuramoto_rkf45_n200"])
+@pytest.mark.parametrize("name", ["kuramoto_rkck_n200", "kuramoto_rkf45_n200", "kuramoto_rk4_n50"])
 def test_kuramoto_adaptive(model_lib, name):
     g, out, meta = run_case(model_lib, name)
     first, last = check(g, out, atol_mfd=1e-11)
@@ -78,3 +78,18 @@ def test_nbody_rkf45(model_lib):
     g, out, meta = run_case(model_lib, "nbody_rkf45_n96")
     first, last = check(g, out)
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-8, atol=1e-12)
+
+
+def test_config1_kuramoto_as_shipped(model_lib):
+    """BASELINE config 1: the reference's examples/kuramoto.pop as shipped (N=1000, rkck, 801 output points over [0,160]);
+    golden = the unchanged reference binary built from the shipped file.  160 time units of adaptive stepping: the GPU and
+    CPU runs take the same accept/reject decisions, so the trajectories stay within 1e-8."""
+    g, out, meta = run_case(model_lib, "kuramoto_shipped_rkck")
+    st = out["stats"]
+    assert len(st) == len(g["stats_t"])          # 1000 birth rows + one row per loop iteration (incl. the round-off sliver at t1)
+    np.testing.assert_array_equal(st["stop_flag"], g["stats_flag"])
+    np.testing.assert_allclose(st["t"], g["stats_t"], rtol=1e-13, atol=1e-12)
+    np.testing.assert_allclose(st["mfd"], g["stats_mfd"], rtol=0, atol=1e-9)
+    tr = out["traj"]
+    last = tr[tr["step"] == tr["step"].max()]
+    np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-8, atol=1e-9)

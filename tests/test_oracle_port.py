@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 from conftest import load_golden
 
-GOLDEN_CASES = ["kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
-                "kuramoto_rkf45_n200", "nbody_dde_n64", "nbody_rkf45_n96"]
+GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
+                "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -17,7 +17,7 @@ def test_port_matches_golden(name):
     from oracle import port
     g = load_golden(name)
     meta = ast.literal_eval(str(g["meta"][0]))
-    out = port.run(meta["fixture"], meta["opts"], meta["timespan"])
+    out = port.run("kuramoto" if meta["fixture"] == "kuramoto_shipped" else meta["fixture"], meta["opts"], meta["timespan"])
     st, tr = out["stats"], out["traj"]
     np.testing.assert_array_equal(st["n"], g["stats_n"])
     np.testing.assert_array_equal(st["stop_flag"], g["stats_flag"])
