@@ -12,7 +12,7 @@ import numpy as np
 from . import build as _build
 from . import popfile
 
-METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4}
+METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5}
 
 
 class OdxError(RuntimeError):
@@ -50,7 +50,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_pop_init", "odx_rhs", "odx_meanfields", "odx_rates", "odx_fe_apply", "odx_dde_apply", "odx_evolve_reset",
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
-               "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank"]
+               "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply"]
 
 
 def _dp(a):
@@ -89,6 +89,7 @@ class ModelLib:
         L.odx_rates.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         for f in (L.odx_fe_apply, L.odx_dde_apply):
             f.argtypes = [H, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int]
+        L.odx_iteration_apply.argtypes = [H, C.POINTER(C.c_double), C.c_int]
         L.odx_evolve_reset.argtypes = [H]
         L.odx_evolve_apply.argtypes = [H, C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
         L.odx_evolve_stats.argtypes = [H] + [C.POINTER(C.c_uint64)] * 3

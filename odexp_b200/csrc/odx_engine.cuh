@@ -239,6 +239,7 @@ struct ChainArgs {
                                acc = (ys - y0) * recon with recon = w1 / a1, instead of being stored and re-read (16 B per
                                particle-step less traffic; the rebuilt slope is exact to <= 1 ulp of y0 / (a1 h)) */
   int skip_acc_store;       /* FIRST stage: the next stage reconstructs the accumulator */
+  int iterate;              /* iteration_apply (src/methods_odexp.c:1816-1823): y <- f(y) instead of y <- y + h f(y) */
 };
 
 /* chain methods (Euler, classic RK4): stage state depends on the previous slope only.
@@ -256,7 +257,7 @@ __device__ __forceinline__ void chain_lane(const Pop &p, const ChainArgs &a, con
   M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
   if (LAST) {
 #pragma unroll
-    for (int v = 0; v < NVAR; v++) yn[v] = y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
+    for (int v = 0; v < NVAR; v++) yn[v] = a.iterate ? f[v] : y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
     if (live) red[RED_RATES] += death + repli;
   } else {
 #pragma unroll
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
  * ---------------------------------------------------------------------------------------------- */
 constexpr int MAX_RANKS = 8;
 struct PersistArgs {
-  int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0; int recon;
+  int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0; int recon; int iterate;
   const double *sums_y;            /* global raw sums of the %M terms of Y at entry */
   double *partial;                 /* [2][grid][NRED] */
   unsigned int *bar;               /* [2][PERSIST_MAX_CTAS] epoch tags of the published block partials, then [2] global-sum flags */
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       __syncthreads();
       ChainArgs a;
       a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2; a.reverse = (int)(epoch & 1u);
-      a.recon = 0.0; a.skip_acc_store = 0;
+      a.recon = 0.0; a.skip_acc_store = 0; a.iterate = g.iterate;
       a.want_out = (last_stage && step == g.nsteps - 1) ? g.want_out_last : 0;
       double red[NRED];
 #pragma unroll

@@ -89,6 +89,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   double tot_solver = 0.0;
   double t, t1, dt, tnext, dt_ssa, dt_leaping, dt_dyn, dt_next, sum_rates = 0.0, birth_rate = 0.0, expected_dt_ssa;
   double hstep = o->h0;
+  int res = o->res;
   int status = ODX_SUCCESS, stop_flag, event[3] = {0, 0, 0};
   int64_t n = 0, steps = 0, i;
   double particle_steps = 0.0;
@@ -102,7 +103,12 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
 
   memset(&os, 0, sizeof os);
   if (rep) memset(rep, 0, sizeof *rep);
-  if (o->tspan_len < 2 || o->res < 2) return ODX_EINVAL;
+  if (o->tspan_len < 2) return ODX_EINVAL;
+  if (o->method == ODX_METH_ITERATION) {          /* set_dou("h0", 1.0); set_int("res", (int)(t1 - t0) + 1) */
+    hstep = 1.0;
+    res = (int)(o->tspan[o->tspan_len - 1] - o->tspan[0]) + 1;
+  }
+  if (res < 2) return ODX_EINVAL;
   if (o->tspan_len > 2) return ODX_EUNSUP;        /* stopping times: host-only feature of the reference UI */
   os.nmfd = mi->nmfd; os.nvar = mi->nvar; os.naux = mi->naux; os.npsi = mi->npsi; os.nexpr = mi->nexpr;
   os.mfd = calloc(os.nmfd > 0 ? os.nmfd : 1, sizeof(double));
@@ -110,7 +116,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   t = o->tspan[0];
   t1 = o->tspan[o->tspan_len - 1];
   stop_flag = ODX_EVENT_T0;
-  dt = (t1 - t) / (double)(o->res - 1);
+  dt = (t1 - t) / (double)(res - 1);
 
   snprintf(path, sizeof path, "%s/stats.dat", o->outdir ? o->outdir : ".odexp");
   if ((os.fstats = fopen(path, "w")) == NULL) { status = ODX_EFAILED; goto done; }
@@ -168,7 +174,9 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
       const double c0 = now_ms();
       while (t < tnext) {
         const int64_t n_step = n;
-        if (o->method == ODX_METH_FE || o->method == ODX_METH_DDE) {
+        if (o->method == ODX_METH_ITERATION) {
+          status = odx_iteration_apply(h, &t, 1);
+        } else if (o->method == ODX_METH_FE || o->method == ODX_METH_DDE) {
           const int last = hstep > ((tnext - t) - o->hmin);     /* this step lands on tnext: keep aux / rates */
           status = (o->method == ODX_METH_FE) ? odx_fe_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last)
                                               : odx_dde_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last);

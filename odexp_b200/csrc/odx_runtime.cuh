@@ -373,12 +373,12 @@ static void fill_peer_args(odx_handle *h, PersistArgs &g) {
 }
 
 /* nsteps whole steps in one cooperative launch (see k_chain_persist) */
-static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64_t nsteps, int want_out_last) {
+static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64_t nsteps, int want_out_last, int iterate = 0) {
   ODX_TRY(ensure_moments_Y(h, t0));
   const int new_slot = h->y_slot ^ 1;
   Pop p = pop_view(h);
   PersistArgs g; memset(&g, 0, sizeof g);
-  g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index; g.recon = h->use_recon;
+  g.nst = nst; g.nsteps = nsteps; g.t0 = t0; g.h = hh; g.want_out_last = want_out_last; g.eval_index0 = h->eval_index; g.recon = h->use_recon; g.iterate = iterate;
   g.sums_y = sums_ptr(h, h->y_slot); g.partial = h->partial; g.bar = h->counter + 32; g.totals = h->sums + (size_t)(SLOT_STAGE + 6) * NRED;
   g.ll_part = h->ll_words; g.ll_gtot = h->ll_words + (size_t)2 * PERSIST_MAX_CTAS * LLW;
   g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
@@ -401,14 +401,14 @@ static inline bool can_persist(const odx_handle *h) {
 }
 
 /* one step of a chain method.  nst = 1: Euler (fe_apply); nst = 4: classic RK4 (dde_apply) */
-static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out) {
+static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out, int iterate = 0) {
   if (h->n <= 0) return ODX_SUCCESS;
-  if (can_persist(h)) return chain_run_persist(h, nst, t, hh, 1, want_out);
+  if (can_persist(h)) return chain_run_persist(h, nst, t, hh, 1, want_out, iterate);
   ODX_TRY(ensure_moments_Y(h, t));
   const int g = grid_chain(h, h->n);
   Pop p = pop_view(h);
   const int new_slot = h->y_slot ^ 1;
-  ChainArgs a; a.h = hh; a.want_out = want_out; a.reverse = 0; a.recon = 0.0; a.skip_acc_store = 0;
+  ChainArgs a; a.h = hh; a.want_out = want_out; a.reverse = 0; a.recon = 0.0; a.skip_acc_store = 0; a.iterate = iterate;
   if (nst == 1) {
     ODX_TRY(compute_psi(h, h->Y, t));
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + hh; a.a = hh; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
@@ -974,6 +974,34 @@ int odx_dde_apply(odx_handle *h, double *t, double tnext, double *hstep, double 
   ODX_TRY(chain_step(h, 4, *t, *hstep, want_outputs));
   *t += *hstep;
   *hstep = h0;
+  return ODX_SUCCESS;
+}
+
+/* iteration_apply (src/methods_odexp.c:1816-1823) calls pop_rhs(t, y, y): input and output alias.  In the generated pop_rhs
+ * that makes pass 1 overwrite y with f(y) evaluated at ZERO mean fields before the state is copied into the particles, the
+ * %M walks then see those values, and pass 2 applies the map again with these mean fields.  Reproduced as two sweeps:
+ *   y1 = f(y; mfd = 0),  mfd = mean(terms(y1)),  y <- f(y1; mfd). */
+int odx_iteration_apply(odx_handle *h, double *t, int want_outputs) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (h->n > 0) {
+    if (M::HAS_PAIR || M::HAS_LOWRANK) { h->err = "meth iteration with %C coupling is not supported"; return ODX_EUNSUP; }
+    const int g = grid_chain(h, h->n);
+    Pop p = pop_view(h);
+    ChainArgs a; memset(&a, 0, sizeof a);
+    a.h = 1.0; a.a = 1.0; a.w = 1.0; a.iterate = 1; a.t_eval = *t; a.t_next = *t; a.eval_index = h->eval_index;
+    a.sums_in = nullptr; a.want_out = 0;
+    k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 0));
+    ODX_TRY(launch_check(h));
+    if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 0));
+    a.sums_in = sums_ptr(h, SLOT_STAGE + 0); a.want_out = want_outputs;
+    const int new_slot = h->y_slot ^ 1;
+    k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
+    ODX_TRY(launch_check(h));
+    if (NEEDS_MOMENTS || M::HAS_DEATH || M::HAS_REPLI) ODX_TRY(post_reduce(h, new_slot));
+    h->eval_index += 2; h->rhs_evals += 1;
+    h->report_slot = SLOT_STAGE + 0; h->rates_slot = new_slot; h->y_slot = new_slot; h->ymoments_valid = NEEDS_MOMENTS; h->k1_valid = false;
+  }
+  *t += 1;
   return ODX_SUCCESS;
 }
 

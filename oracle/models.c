@@ -99,7 +99,29 @@ static void klr_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = 2 * LPI * orc_rand01(c);
 }
 
+/* ---------------------------------------------------------------- logistic_map.pop */
+static const double lm_pars[] = {3.7, 0.1};
+static void lm_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double eps = c->mu[1], r_i = e[0], x = y_[0], XBAR = mfd[0];
+  const double local = r_i * x * (1 - x);
+  (void)t; (void)psi; (void)death; (void)repli;
+  f[0] = (1 - eps) * local + eps * XBAR;
+  aux[0] = local;
+}
+static double lm_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void lm_ic(orc_ctx *c, double t, double *y, double *e) {
+  const double r = c->mu[0];
+  (void)t;
+  e[0] = r + 0.05 * (orc_rand01(c) - 0.5);
+  y[0] = 0.1 + 0.8 * orc_rand01(c);
+}
+
 static const orc_model MODELS[] = {
+  {"logistic_map", 1, 1, 1, 0, 1, 2, lm_pars, lm_rhs, lm_mfd, NULL, NULL, lm_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic, 0, 0, 0, 0, 0, NULL},
   {"vdp_sde", 2, 0, 0, 0, 0, 4, vdp_pars, vdp_rhs, NULL, vdp_birth, NULL, vdp_ic, 0, 0, 0, 0, 0, NULL},

@@ -221,6 +221,13 @@ static int orc_dde_apply(orc_sim *s, double *t, double tnext, double *h, double 
   return GSL_SUCCESS;
 }
 
+/* iteration_apply, src/methods_odexp.c:1816-1823: y = f(y) written in place (the RHS reads y_ and writes f_ == y_) */
+static int orc_iteration_apply(orc_sim *s, double *t, double *y) {
+  orc_pop_rhs(*t, y, y, s);
+  *t += 1;
+  return GSL_SUCCESS;
+}
+
 /* ------------------------------------------------------------------ initial conditions */
 static void run_ic(orc_sim *s, orc_par *p, double t, uint32_t dom, uint32_t stream) {
   orc_ctx c;
@@ -368,9 +375,15 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   char path[4096];
   clock_t start = clock(), c0;
   if (!m) return GSL_EINVAL;
-  if (o->tspan_len != 2 || o->res < 2) return GSL_EINVAL;
+  if (o->tspan_len != 2) return GSL_EINVAL;
   memset(s, 0, sizeof *s);
-  s->model = m; s->o = *o; s->rng_mode = o->rng_mode; s->k0 = o->seed; s->k1 = 0;
+  s->model = m; s->o = *o;
+  if (o->method == ORC_METH_ITERATION) {         /* src/methods_odexp.c:187-193 */
+    s->o.h0 = 1.0; s->o.res = (int)(o->tspan[1] - o->tspan[0]) + 1;
+  }
+  o = &s->o;
+  if (o->res < 2) return GSL_EINVAL;
+  s->rng_mode = o->rng_mode; s->k0 = o->seed; s->k1 = 0;
   s->mu = malloc(sizeof(double) * (m->npar > 0 ? m->npar : 1));
   for (i = 0; i < m->npar; i++) s->mu[i] = o->mu ? o->mu[i] : m->par_defaults[i];
   s->mfd = calloc(m->nmfd > 0 ? m->nmfd : 1, sizeof(double));
@@ -416,7 +429,8 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
       gsl_odeiv2_system sys = {orc_pop_rhs, NULL, (size_t)dim, s};
       while (t < tnext) {
         const int nstep = s->size;
-        if (o->method == ORC_METH_FE) status = orc_fe_apply(s, &t, tnext, &h, y, dim);
+        if (o->method == ORC_METH_ITERATION) status = orc_iteration_apply(s, &t, y);
+        else if (o->method == ORC_METH_FE) status = orc_fe_apply(s, &t, tnext, &h, y, dim);
         else if (o->method == ORC_METH_DDE) status = orc_dde_apply(s, &t, tnext, &h, y, dim);
         else status = gsl_odeiv2_evolve_apply(ge, gc, gs, &sys, &t, tnext, &h, y);
         if (status != GSL_SUCCESS) { s->stop_flag = ORC_EVENT_GSL; break; }

@@ -100,3 +100,20 @@ def test_exclusive_scan_and_compaction_large(model_lib):
     assert n_local == n - deaths + births and rows[-1][0] == n_local
     assert max_id == n + births
     pop.close()
+
+
+def test_iteration_method(model_lib):
+    """meth iteration (discrete map population, reference iteration_apply incl. its in-place two-pass behaviour)"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("logistic_map")
+    pop = capi.Population(lib, capacity=1024)
+    out = capi.odesolver(pop, (0, 20), meth="iteration", popsize=333, replay_ic=True)
+    pop.close()
+    ref = port.run("logistic_map", {"meth": "iteration", "ps": 333}, (0, 20))
+    assert len(out["stats"]) == len(ref["stats"]) and len(out["traj"]) == len(ref["traj"])
+    np.testing.assert_allclose(out["stats"]["t"], ref["stats"]["t"], rtol=0, atol=0)
+    # the logistic map at r = 3.7 is chaotic (Lyapunov exponent ~0.35 per iteration): round-off grows e^(0.35 n)
+    first = out["traj"]["step"] <= 5
+    np.testing.assert_allclose(out["traj"]["cols"][first], ref["traj"]["cols"][first], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=0, atol=1e-9)
