@@ -36,17 +36,18 @@ def peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """samples nvidia-smi clocks / throttle reasons of the GPUs in use during the timed region (all ranks' GPUs: in a
+    strong-scaling run every stage waits for the slowest GPU, so one power-capped GPU sets the pace)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, ngpus):
+        self.ngpus, self.rows, self.proc = ngpus, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -65,19 +66,22 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        per, mx, reasons = {}, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                idx = int(r[0])
+                if idx >= self.ngpus:
+                    continue
+                per.setdefault(idx, []).append(float(r[1])); mx.append(float(r[2]))
                 for k, nme in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
+                    if r[4 + k].lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        med = {i: sorted(v)[len(v) // 2] for i, v in per.items() if v}
+        return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": sum(len(v) for v in per.values()), "per_gpu_sm_mhz": [med[i] for i in sorted(med)]}
 
 
 def cpu_reference_sample(n, nsteps, meth="dde"):
@@ -176,7 +180,7 @@ def main():
     t = 0.0
     t = pop.run_fixed("dde", t, H_STEP, args.warmup)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(world)
     if rank == 0:
         sampler.start()
     l0 = pop.launch_count()

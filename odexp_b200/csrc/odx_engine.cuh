@@ -483,6 +483,9 @@ __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s
   __syncthreads();
 }
 constexpr int PERSIST_MAX_CTAS = 256;
+#ifndef PEER_POLL_ALL
+#define PEER_POLL_ALL 1
+#endif
 #ifndef PERSIST_THREADS
 #define PERSIST_THREADS 1024
 #endif
@@ -556,6 +559,33 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
         /* cross-GPU: CTA 0 stores this rank's sums as LL words straight into every peer's mailbox over NVLink (8-byte
          * st.relaxed.sys on IPC-mapped pointers), polls the words of the other ranks in its own GPU's mailbox, adds the rank
          * sums in rank order and republishes the global sums to the other CTAs of this GPU, again as LL words */
+#if PEER_POLL_ALL
+        /* every CTA polls the peers' words itself (no local republish hop) */
+        if (blockIdx.x == 0 && threadIdx.x < LLW) {
+          const unsigned long long w = ll_pack(s_tot[threadIdx.x >> 1], threadIdx.x & 1, tag);
+          for (int r = 0; r < g.nranks; r++)
+            if (r != g.rank) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + threadIdx.x, w);
+        }
+        if (threadIdx.x < (unsigned)(g.nranks * LLW)) {
+          const int r = threadIdx.x / LLW, k = threadIdx.x % LLW;
+          if (r != g.rank) {
+            unsigned long long w; unsigned long long spins = 0;
+            while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + k)) >> 32) != tag) {
+              if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; }
+            }
+            s_words[threadIdx.x] = (uint32_t)w;
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x < NRED) {
+          double v = 0.0;
+          for (int r = 0; r < g.nranks; r++)
+            v += (r == g.rank) ? s_tot[threadIdx.x] : ll_unpack(s_words[r * LLW + 2 * threadIdx.x], s_words[r * LLW + 2 * threadIdx.x + 1]);
+          s_bp[threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
+#else
         unsigned long long *gt = g.ll_gtot + par * LLW;
         if (blockIdx.x == 0) {
           if (threadIdx.x < LLW) {
@@ -592,6 +622,7 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
           __syncthreads();
           if (threadIdx.x < NRED) s_tot[threadIdx.x] = ll_unpack(s_words[2 * threadIdx.x], s_words[2 * threadIdx.x + 1]);
         }
+#endif
         __syncthreads();
       }
       epoch++;
