@@ -227,7 +227,10 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "Kuramoto mean-field (oracle/fixtures/kuramoto.pop), N=%d oscillators, classic RK4 (meth dde) h=%g, FP64" % (n_total, H_STEP),
-                           "n_particles": n_total, "per_gpu_particles": n_local, "l2": "inputs larger than L2 (%.0f MB state per GPU)" % (n_local * 32 / 1e6),
+                           "n_particles": n_total, "per_gpu_particles": n_local, "l2": ("state larger than L2 (%.0f MB per GPU vs 126 MB): every stage streams it from HBM" % (n_local * 32 / 1e6)) if n_local * 32 > 126e6
+                                 else ("state fits in L2 (%.0f MB per GPU): consecutive steps of one simulation reuse the resident population by construction, "
+                                       "no flush between steps (a flush would not be part of the workload)" % (n_local * 32 / 1e6)),
+                           "stage_sweeps_in_timed_region": int(4 * args.steps),
                            "parallelism": "particle sharding x%d, %%M sums per stage through %s" % (world, "NCCL allreduce" if args.no_peers else "in-kernel NVLink peer mailboxes"), "mean_fields_after": [float(x) for x in mfd]},
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(8 * lib.nmfd),
                         "steps": ne2e, "what": "odx_pop_upload(host theta, omega) + odx_run_fixed(dde, 1 step) + odx_meanfields per step"},
