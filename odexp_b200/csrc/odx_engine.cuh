@@ -293,34 +293,90 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
   }
 }
 
-/* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread) */
-template <bool FIRST, bool LAST>
-__device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED]) {
+/* cp.async staging of the next iteration's columns (16 B per thread and column) into the thread's own shared-memory slots:
+ * the loads of iteration k+1 are in flight while iteration k computes, without holding registers and without a CTA barrier
+ * (every thread reads back only what it staged itself). */
+constexpr int PF_NCOL = 3 * NVAR + NEXPR + NPSI;                 /* y0, e, psi, ys, acc */
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NC>
+__device__ __forceinline__ void stage_cols(double2 *slot, int nthreads, const double *__restrict__ base, int64_t stride, int64_t i) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) cp_async16(slot + (size_t)c * nthreads, base + (int64_t)c * stride + i);
+}
+template <int NC>
+__device__ __forceinline__ void unstage_cols(const double2 *slot, int nthreads, double (&o0)[A1(NC)], double (&o1)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) { const double2 v = slot[(size_t)c * nthreads]; o0[c] = v.x; o1[c] = v.y; }
+}
+
+/* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread).
+ * PF: stage the input columns of the next iteration through shared memory with cp.async (sbuf = [2][PF_NCOL][blockDim] double2). */
+template <bool FIRST, bool LAST, bool PF>
+__device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED],
+                                            double2 *sbuf = nullptr) {
   /* the grid sweeps the columns as a moving window of gridDim.x tiles; alternate stages sweep in opposite directions so that
    * the tail of one stage (still resident in the 126 MB L2) is the head of the next */
   const int64_t per_iter = 2 * (int64_t)gridDim.x * blockDim.x;
   const int64_t niter = (p.n + per_iter - 1) / per_iter;
-  for (int64_t k = 0; k < niter; k++) {
+  const int nt = blockDim.x;
+  const int64_t toff = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  auto issue = [&](int64_t k) {
     const int64_t kk = a.reverse ? (niter - 1 - k) : k;
-    const int64_t i = kk * per_iter + 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const int64_t i = kk * per_iter + toff;
+    if (i < p.n) {
+      double2 *slot = sbuf + (size_t)(k & 1) * PF_NCOL * nt + threadIdx.x;
+      stage_cols<NVAR>(slot, nt, p.Y, p.stride, i);
+      stage_cols<NEXPR>(slot + (size_t)NVAR * nt, nt, p.E, p.stride, i);
+      stage_cols<NPSI>(slot + (size_t)(NVAR + NEXPR) * nt, nt, p.PSI, p.stride, i);
+      if (!FIRST) {
+        stage_cols<NVAR>(slot + (size_t)(NVAR + NEXPR + NPSI) * nt, nt, p.YS, p.stride, i);
+        if (a.recon == 0.0) stage_cols<NVAR>(slot + (size_t)(2 * NVAR + NEXPR + NPSI) * nt, nt, p.ACC, p.stride, i);
+      }
+    }
+    cp_async_commit();
+  };
+  if (PF && niter > 0) issue(0);
+  for (int64_t k = 0; k < niter; k++) {
+    if (PF) {
+      if (k + 1 < niter) issue(k + 1); else cp_async_commit();
+      cp_async_wait<1>();
+    }
+    const int64_t kk = a.reverse ? (niter - 1 - k) : k;
+    const int64_t i = kk * per_iter + toff;
     if (i >= p.n) continue;
     const bool two = (i + 1 < p.n);
     double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)], yn[2][A1(NVAR)], aux[2][A1(NAUX)];
     double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
-    load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
-    load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
-    if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
+    if (PF) {
+      const double2 *slot = sbuf + (size_t)(k & 1) * PF_NCOL * nt + threadIdx.x;
+      unstage_cols<NVAR>(slot, nt, y0[0], y0[1]);
+      unstage_cols<NEXPR>(slot + (size_t)NVAR * nt, nt, e[0], e[1]);
+      if (NPSI > 0) unstage_cols<NPSI>(slot + (size_t)(NVAR + NEXPR) * nt, nt, psi[0], psi[1]);
+      if (!FIRST) {
+        unstage_cols<NVAR>(slot + (size_t)(NVAR + NEXPR + NPSI) * nt, nt, yc[0], yc[1]);
+        if (a.recon == 0.0) unstage_cols<NVAR>(slot + (size_t)(2 * NVAR + NEXPR + NPSI) * nt, nt, acc[0], acc[1]);
+      }
+    } else {
+      load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
+      load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
+      if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
+      if (!FIRST) {
+        load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
+        if (a.recon == 0.0) load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      }
+    }
     if (FIRST) {
 #pragma unroll
       for (int v = 0; v < NVAR; v++) { yc[0][v] = y0[0][v]; yc[1][v] = y0[1][v]; }
-    } else {
-      load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
-      if (a.recon == 0.0) {
-        load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
-      } else {
+    } else if (a.recon != 0.0) {
 #pragma unroll
-        for (int v = 0; v < NVAR; v++) { acc[0][v] = (yc[0][v] - y0[0][v]) * a.recon; acc[1][v] = (yc[1][v] - y0[1][v]) * a.recon; }
-      }
+      for (int v = 0; v < NVAR; v++) { acc[0][v] = (yc[0][v] - y0[0][v]) * a.recon; acc[1][v] = (yc[1][v] - y0[1][v]) * a.recon; }
     }
     int32_t id0 = 0, id1 = 0;
     if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
@@ -338,6 +394,7 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
       store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
     }
   }
+  if (PF) cp_async_wait<0>();
 }
 
 template <bool FIRST, bool LAST>
@@ -347,7 +404,7 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
   load_mfd(a.sums_in, p.n_global, mfd);
-  chain_sweep<FIRST, LAST>(p, a, mfd, red);
+  chain_sweep<FIRST, LAST, false>(p, a, mfd, red);
   if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
 }
 
@@ -490,9 +547,16 @@ constexpr int PERSIST_MAX_CTAS = 256;
 #define PERSIST_THREADS 1024
 #endif
 constexpr int PT = PERSIST_THREADS;
+#ifndef PERSIST_PREFETCH
+#define PERSIST_PREFETCH 0   /* measured on B200: cp.async staging is 14% SLOWER than direct 128-bit loads here (0.507 vs 0.443 ms/step at N=2^24) */
+#endif
+constexpr size_t PF_BYTES = (size_t)2 * PF_NCOL * PT * sizeof(double2);
+constexpr bool PF_ON = PERSIST_PREFETCH && (PF_BYTES <= 160 * 1024);
 __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_persist(Pop p, PersistArgs g) {
   __shared__ double s_tot[NRED], s_bp[NRED];
   __shared__ uint32_t s_words[PERSIST_MAX_CTAS * LLW];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double2 *sbuf = reinterpret_cast<double2 *>(s_dyn);
   double mfd[A1(NMFD)];
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
   __syncthreads();
@@ -515,19 +579,19 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       for (int k = 0; k < NRED; k++) red[k] = 0.0;
       if (g.nst == 1) {                                   /* Euler */
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
-        chain_sweep<true, true>(p, a, mfd, red);
+        chain_sweep<true, true, PF_ON>(p, a, mfd, red, sbuf);
       } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */
         a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0; a.skip_acc_store = g.recon ? 1 : 0;
-        chain_sweep<true, false>(p, a, mfd, red);
+        chain_sweep<true, false, PF_ON>(p, a, mfd, red, sbuf);
       } else if (s == 1) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0; a.recon = g.recon ? 1.0 / (g.h / 2.0) : 0.0;
-        chain_sweep<false, false>(p, a, mfd, red);
+        chain_sweep<false, false, PF_ON>(p, a, mfd, red, sbuf);
       } else if (s == 2) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h; a.a = g.h; a.w = 2.0;
-        chain_sweep<false, false>(p, a, mfd, red);
+        chain_sweep<false, false, PF_ON>(p, a, mfd, red, sbuf);
       } else {
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
-        chain_sweep<false, true>(p, a, mfd, red);
+        chain_sweep<false, true, PF_ON>(p, a, mfd, red, sbuf);
       }
       /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
        * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence

@@ -388,7 +388,7 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   if (grid > PERSIST_MAX_CTAS) grid = PERSIST_MAX_CTAS;
   if (grid < 1) grid = 1;
   void *args[] = {(void *)&p, (void *)&g};
-  ODX_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_chain_persist, dim3((unsigned)grid), dim3(PT), args, 0, h->stream));
+  ODX_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_chain_persist, dim3((unsigned)grid), dim3(PT), args, PF_ON ? PF_BYTES : 0, h->stream));
   h->launches++;
   h->epoch += (uint32_t)(nst * nsteps);
   h->eval_index += (uint32_t)(2 * nst * nsteps); h->rhs_evals += (uint64_t)nst * nsteps;
@@ -649,7 +649,8 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   {
     int coop = 0, occp = 0;
     ODX_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_chain_persist, PT, 0));
+    if (PF_ON) ODX_CUDA(h, cudaFuncSetAttribute(k_chain_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_BYTES));
+    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_chain_persist, PT, PF_ON ? PF_BYTES : 0));
     h->coop_ok = coop && occp > 0; h->coop_blocks = h->sm_count * occp;
   }
   ODX_TRY(alloc_cols(h, &h->Y, NVAR)); ODX_TRY(alloc_cols(h, &h->YS, NVAR)); ODX_TRY(alloc_cols(h, &h->ACC, NVAR));
