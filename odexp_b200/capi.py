@@ -50,7 +50,8 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_pop_init", "odx_rhs", "odx_meanfields", "odx_rates", "odx_fe_apply", "odx_dde_apply", "odx_evolve_reset",
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
-               "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply"]
+               "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
+               "odx_pop_download_strided"]
 
 
 def _dp(a):
@@ -82,6 +83,7 @@ class ModelLib:
         L.odx_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
         L.odx_pop_upload.argtypes = [H, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int32]
         L.odx_pop_download.argtypes = [H, C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 2
+        L.odx_pop_download_strided.argtypes = [H, C.c_int64, C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)]
         L.odx_pop_size.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.odx_pop_init.argtypes = [H, C.c_int64, C.c_double, C.c_uint32, C.c_int]
         L.odx_rhs.argtypes = [H, C.c_double]

@@ -900,6 +900,18 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
     aos[q] = soa[(int64_t)c * stride + first + i];
   }
 }
+/* every stride-th particle of [first, first + m*stride) -> AoS rows (thinned trajectory output) */
+__global__ void k_soa_to_aos_strided(const double *__restrict__ soa, double *__restrict__ aos, int ncol, int64_t m, int64_t stride_cols,
+                                     int64_t first, int64_t step) {
+  const int64_t total = m * ncol;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = q / ncol; const int c = (int)(q % ncol);
+    aos[q] = soa[(int64_t)c * stride_cols + first + i * step];
+  }
+}
+__global__ void k_gather_ids(const int32_t *__restrict__ id, int32_t *__restrict__ out, int64_t m, int64_t first, int64_t step) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) out[i] = id[first + i * step];
+}
 __global__ void k_iota_ids(int32_t *id, int64_t n, int32_t first) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) id[i] = first + (int32_t)i;
 }

@@ -58,13 +58,16 @@ static int ensure_buffers(out_state *os, int64_t n) {
 
 /* fwrite_all_particles (src/datastruct.c:655-674): per particle: step, id, t, y, aux, psi, meanfield, expr */
 static int write_traj_frame(odx_handle *h, out_state *os, double t, int stride) {
-  int64_t n = 0, i;
+  int64_t n = 0, m, i;
   int st;
   if (!os->ftraj || stride <= 0) { os->nbrsteps++; return 0; }
   odx_pop_size(h, &n, NULL, NULL);
-  if ((st = ensure_buffers(os, n)) != 0) return st;
-  if ((st = odx_pop_download(h, 0, n, os->y, os->e, os->aux, os->psi, os->ids, NULL, NULL)) != 0) return st;
-  for (i = 0; i < n; i += stride) {
+  m = (n + stride - 1) / stride;                  /* particles 0, stride, 2*stride, ... */
+  if ((st = ensure_buffers(os, m)) != 0) return st;
+  if (stride == 1) st = odx_pop_download(h, 0, n, os->y, os->e, os->aux, os->psi, os->ids, NULL, NULL);
+  else st = odx_pop_download_strided(h, 0, stride, m, os->y, os->e, os->aux, os->psi, os->ids);
+  if (st != 0) return st;
+  for (i = 0; i < m; i++) {
     fwrite(&os->nbrsteps, sizeof(unsigned int), 1, os->ftraj);
     fwrite(&os->ids[i], sizeof(int), 1, os->ftraj);
     fwrite(&t, sizeof(double), 1, os->ftraj);

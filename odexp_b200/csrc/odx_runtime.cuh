@@ -860,6 +860,38 @@ int odx_pop_download(odx_handle *h, int64_t first, int64_t count, double *y, dou
   return ODX_SUCCESS;
 }
 
+/* thinned download for trajectory output at scale: particles first, first+step, ... (m of them); only the selected rows cross
+ * PCIe (at N = 2^24 a full traj.dat frame is 1.2 GB, src/datastruct.c:655-674) */
+static int download_cols_strided(odx_handle *h, const double *soa, double *aos, int ncol, int64_t m, int64_t first, int64_t step) {
+  if (ncol == 0 || m == 0 || aos == nullptr) return ODX_SUCCESS;
+  const size_t bytes = sizeof(double) * (size_t)ncol * m;
+  ODX_TRY(ensure_stage(h, bytes));
+  k_soa_to_aos_strided<<<h->sm_count * 4, 256, 0, h->stream>>>(soa, h->stage_dev, ncol, m, h->cap, first, step);
+  ODX_TRY(launch_check(h));
+  ODX_CUDA(h, cudaMemcpyAsync(aos, h->stage_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ODX_SUCCESS;
+}
+int odx_pop_download_strided(odx_handle *h, int64_t first, int64_t step, int64_t m, double *y, double *expr, double *aux, double *psi,
+                             int32_t *ids) {
+  if (first < 0 || step < 1 || m < 0 || (m > 0 && first + (m - 1) * step >= h->n)) {
+    h->err = "odx_pop_download_strided: selection outside the population"; return ODX_EINVAL;
+  }
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  ODX_TRY(download_cols_strided(h, h->Y, y, NVAR, m, first, step));
+  ODX_TRY(download_cols_strided(h, h->E, expr, NEXPR, m, first, step));
+  ODX_TRY(download_cols_strided(h, h->AUX, aux, NAUX, m, first, step));
+  ODX_TRY(download_cols_strided(h, h->PSI, psi, NPSI, m, first, step));
+  if (ids && m > 0) {
+    ODX_TRY(ensure_stage(h, sizeof(int32_t) * (size_t)m));
+    k_gather_ids<<<h->sm_count * 4, 256, 0, h->stream>>>(h->ID, (int32_t *)h->stage_dev, m, first, step);
+    ODX_TRY(launch_check(h));
+    ODX_CUDA(h, cudaMemcpyAsync(ids, h->stage_dev, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return ODX_SUCCESS;
+}
+
 int odx_pop_size(odx_handle *h, int64_t *n_local, int64_t *n_global, int32_t *max_id) {
   if (n_local) *n_local = h->n;
   if (n_global) *n_global = (int64_t)h->n_global;

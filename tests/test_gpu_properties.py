@@ -126,3 +126,20 @@ def test_error_paths(model_lib):
         for k in range(50):                    # births + replications overflow the capacity: reported, not fatal
             sde.tauleap_apply(0.0, 5.0, k)
     sde.close()
+
+
+def test_strided_trajectory_output(model_lib):
+    """traj_stride = k writes particles 0, k, 2k, ... of every frame (thinned traj.dat for large populations); the rows must
+    equal the corresponding rows of the full output"""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    kw = dict(meth="dde", h0=0.1, res=3, popsize=1001, replay_ic=True)
+    p1 = capi.Population(lib, capacity=2048); full = capi.odesolver(p1, (0, 0.4), traj_stride=1, **kw); p1.close()
+    p2 = capi.Population(lib, capacity=2048); thin = capi.odesolver(p2, (0, 0.4), traj_stride=7, **kw); p2.close()
+    np.testing.assert_array_equal(full["stats"], thin["stats"])
+    for step in range(3):
+        a = full["traj"][full["traj"]["step"] == step][::7]
+        b = thin["traj"][thin["traj"]["step"] == step]
+        assert len(b) == (1001 + 6) // 7
+        np.testing.assert_array_equal(a["id"], b["id"])
+        np.testing.assert_array_equal(a["cols"], b["cols"])
