@@ -63,6 +63,7 @@ struct DevCtx {
   const double *sis_y, *sis_e, *sis_aux;   /* sister particle (valid only during replication ICs) */
   int has_sister;
   int stop;                 /* STOPIF */
+  int slow;                 /* a fast-path sincos saw an out-of-range argument: redo this particle with the library path */
   ODX_HD double rand01() { return rng.rand01(); }
   ODX_HD double randN(double m, double s) { return rng.randN(m, s); }
   ODX_HD double exprand(double r) { return rng.exprand(r); }
@@ -73,7 +74,7 @@ struct DevCtx {
 /* host context for replayed initial conditions: draws through the serial libc stream */
 struct HostCtx {
   const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli;
-  const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop;
+  const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop; int slow;
   ODX_HD double rand01() { return hr->rand01(); }
   ODX_HD double randN(double m, double s) { return hr->randN(m, s); }
   ODX_HD double exprand(double r) { return hr->exprand(r); }
@@ -180,30 +181,52 @@ __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stre
   DevCtx c;
   c.mu = p.mu; c.pop_size = p.n_global; c.h = h;
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
-  c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0;
+  c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   return c;
 }
 
 /* %M terms of one particle state.  Pass-1 semantics of the reference: when a %M expression reads an
  * auxiliary variable (MA), that value comes from ode_rhs evaluated with zeroed mean fields and the
  * previous psi (src/odexp:820-833). */
-__device__ __forceinline__ void particle_terms(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
-                                               const double (&psi)[A1(NPSI)], double (&red)[NRED]) {
+template <bool EXACT>
+__device__ __forceinline__ void particle_terms_x(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                                 const double (&psi)[A1(NPSI)], double (&tm)[NRED]) {
   double aux[A1(NAUX)];
   if (M::TERMS_USE_AUX) {
     double f[A1(NVAR)], mz[A1(NMFD)], d = 0.0, r = 0.0;
 #pragma unroll
     for (int k = 0; k < A1(NMFD); k++) mz[k] = 0.0;
     DevCtx c1 = c;
-    M::rhs(c1, t, y, e, psi, mz, f, aux, d, r);
+    M::template rhs<EXACT>(c1, t, y, e, psi, mz, f, aux, d, r);
+    c.slow |= c1.slow;
   }
   double m[A1(NMFD)];
   if (NMFD > 0) {
-    M::mfd_terms(c, t, y, e, aux, m);
+    M::template mfd_terms<EXACT>(c, t, y, e, aux, m);
 #pragma unroll
-    for (int k = 0; k < NMFD; k++) red[k] += m[k];
+    for (int k = 0; k < NMFD; k++) tm[k] = m[k];
   }
-  if (M::HAS_BIRTH) red[RED_BIRTH] += M::birth_term(c, t, y, e, aux);
+  if (M::HAS_BIRTH) tm[RED_BIRTH] = M::template birth_term<EXACT>(c, t, y, e, aux);
+}
+/* accumulating form with the rare redo (kernels that carry one particle per thread) */
+__device__ __forceinline__ void particle_terms(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                               const double (&psi)[A1(NPSI)], double (&red)[NRED]) {
+  double tm[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) tm[k] = 0.0;
+  DevCtx c0 = c;
+  particle_terms_x<false>(c, t, y, e, psi, tm);
+  if (c.slow) { c = c0; particle_terms_x<true>(c, t, y, e, psi, tm); }
+#pragma unroll
+  for (int k = 0; k < NRED; k++) red[k] += tm[k];
+}
+/* ode_rhs with the rare redo */
+__device__ __forceinline__ void rhs_checked(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                            const double (&psi)[A1(NPSI)], const double (&mfd)[A1(NMFD)], double (&f)[A1(NVAR)],
+                                            double (&aux)[A1(NAUX)], double &death, double &repli) {
+  DevCtx c0 = c;
+  M::template rhs<false>(c, t, y, e, psi, mfd, f, aux, death, repli);
+  if (c.slow) { c = c0; M::template rhs<true>(c, t, y, e, psi, mfd, f, aux, death, repli); }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -247,31 +270,34 @@ struct ChainArgs {
  * new state, which are exactly what the first stage of the next step needs.
  * Each thread carries two adjacent particles per iteration: every column is moved with 128-bit accesses and the two
  * independent dependency chains hide the FP64 latency of the per-particle model code. */
-template <bool FIRST, bool LAST>
-__device__ __forceinline__ void chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id,
-                                           const double (&y0)[A1(NVAR)], const double (&yc)[A1(NVAR)], const double (&e)[A1(NEXPR)],
-                                           const double (&psi)[A1(NPSI)], double (&acc)[A1(NVAR)], double (&yn)[A1(NVAR)],
-                                           double (&aux)[A1(NAUX)], double &death, double &repli, double (&red)[NRED], bool live) {
+template <bool FIRST, bool LAST, bool EXACT>
+__device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id,
+                                          const double (&y0)[A1(NVAR)], const double (&yc)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                          const double (&psi)[A1(NPSI)], const double (&acc_in)[A1(NVAR)], double (&acc)[A1(NVAR)],
+                                          double (&yn)[A1(NVAR)], double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
   double f[A1(NVAR)];
   DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
-  M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+  M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+  int slow = c.slow;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) tm[k] = 0.0;
   if (LAST) {
 #pragma unroll
-    for (int v = 0; v < NVAR; v++) yn[v] = a.iterate ? f[v] : y0[v] + a.a * ((FIRST ? 0.0 : acc[v]) + a.w * f[v]);
-    if (live) red[RED_RATES] += death + repli;
+    for (int v = 0; v < NVAR; v++) yn[v] = a.iterate ? f[v] : y0[v] + a.a * ((FIRST ? 0.0 : acc_in[v]) + a.w * f[v]);
+    tm[RED_RATES] = death + repli;
   } else {
 #pragma unroll
     for (int v = 0; v < NVAR; v++) {
-      acc[v] = FIRST ? a.w * f[v] : acc[v] + a.w * f[v];
+      acc[v] = FIRST ? a.w * f[v] : acc_in[v] + a.w * f[v];
       yn[v] = y0[v] + a.a * f[v];
     }
   }
   if (NMFD > 0 || M::HAS_BIRTH) {
-    if (live) {
-      DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
-      particle_terms(c2, a.t_next, yn, e, psi, red);
-    }
+    DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
+    particle_terms_x<EXACT>(c2, a.t_next, yn, e, psi, tm);
+    slow |= c2.slow;
   }
+  return slow;
 }
 
 template <int NC>
@@ -380,8 +406,15 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
     }
     int32_t id0 = 0, id1 = 0;
     if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
-    chain_lane<FIRST, LAST>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], yn[0], aux[0], death[0], repli[0], red, true);
-    chain_lane<FIRST, LAST>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], yn[1], aux[1], death[1], repli[1], red, two);
+    double acco[2][A1(NVAR)], tm[2][NRED];
+    const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+    if (s0 | s1) {          /* rare: an argument outside the fast sincos range -> library path for this pair */
+      chain_lane<FIRST, LAST, true>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+      chain_lane<FIRST, LAST, true>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+    }
+#pragma unroll
+    for (int k = 0; k < NRED; k++) red[k] += tm[0][k] + (two ? tm[1][k] : 0.0);
     if (LAST) {
       store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
       if (a.want_out) {
@@ -390,7 +423,7 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
         if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
       }
     } else {
-      if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acco[0], acco[1]);
       store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
     }
   }
@@ -710,7 +743,7 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
     DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
-    M::rhs(c, a.t, y, e, psi, mfd, f, aux, death, repli);
+    rhs_checked(c, a.t, y, e, psi, mfd, f, aux, death, repli);
     store_cols<NAUX>(p.AUX, p.stride, i, aux);
     if (M::HAS_DEATH) p.DEATH[i] = death;
     if (M::HAS_REPLI) p.REPLI[i] = repli;
@@ -728,26 +761,17 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
  * more segments.  Arithmetic is FP64 FMA on the CUDA cores. */
 constexpr int PAIR_THREADS = 128, PAIR_ITILE = 256, PAIR_TJ = 128;
 constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);
-__global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
-                                                       const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
-                                                       int64_t nj, double t, double *__restrict__ part, int seg_base) {
-  __shared__ double s_col[A1(PAIR_NCOL)][PAIR_TJ];
-  __shared__ int32_t s_id[PAIR_TJ];
-  /* this CTA's j-range: segment blockIdx.y of gridDim.y, boundaries aligned to the j-tile */
-  const int64_t tiles = (nj + PAIR_TJ - 1) / PAIR_TJ;
-  const int64_t tps = (tiles + gridDim.y - 1) / gridDim.y;
-  const int64_t jbeg = (int64_t)blockIdx.y * tps * PAIR_TJ;
-  int64_t jend = jbeg + tps * PAIR_TJ; if (jend > nj) jend = nj;
-  const int64_t ia = (int64_t)blockIdx.x * PAIR_ITILE + threadIdx.x, ib = ia + PAIR_THREADS;
-  const bool la = ia < p.n, lb = ib < p.n;
-  const int64_t ja = la ? ia : p.n - 1, jb = lb ? ib : p.n - 1;
-  double ya[A1(NVAR)], ea[A1(NEXPR)], yb[A1(NVAR)], eb[A1(NEXPR)], aux[A1(NAUX)], acca[A1(NPSI)], accb[A1(NPSI)];
-  load_cols<NVAR>(ysrc, p.stride, ja, ya); load_cols<NEXPR>(p.E, p.stride, ja, ea);
-  load_cols<NVAR>(ysrc, p.stride, jb, yb); load_cols<NEXPR>(p.E, p.stride, jb, eb);
+template <bool EXACT>
+__device__ __forceinline__ int pair_rows(const Pop &p, const double *__restrict__ jy, const double *__restrict__ je,
+                                         const int32_t *__restrict__ jid, int64_t jstride, int64_t jbeg, int64_t jend, double t,
+                                         const double (&ya)[A1(NVAR)], const double (&ea)[A1(NEXPR)], const double (&yb)[A1(NVAR)],
+                                         const double (&eb)[A1(NEXPR)], int32_t ida, int32_t idb, double (&acca)[A1(NPSI)],
+                                         double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id) {
+  double aux[A1(NAUX)];
 #pragma unroll
   for (int k = 0; k < A1(NPSI); k++) { acca[k] = 0.0; accb[k] = 0.0; }
-  DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[ja] : 0);
-  DevCtx cb = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[jb] : 0);
+  DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida);
+  DevCtx cb = make_ctx(p, 0.0, 0, DOM_RHS, idb);
   for (int64_t j0 = jbeg; j0 < jend; j0 += PAIR_TJ) {
     const int tj = (int)((jend - j0) < PAIR_TJ ? (jend - j0) : PAIR_TJ);
     __syncthreads();
@@ -771,10 +795,32 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__re
         for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
       }
       if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
-      M::cpl_terms(ca, t, ya, ea, aux, oy, oe, aux, acca);
-      M::cpl_terms(cb, t, yb, eb, aux, oy, oe, aux, accb);
+      M::template cpl_terms<EXACT>(ca, t, ya, ea, aux, oy, oe, aux, acca);
+      M::template cpl_terms<EXACT>(cb, t, yb, eb, aux, oy, oe, aux, accb);
     }
   }
+  return ca.slow | cb.slow;
+}
+__global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
+                                                       const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
+                                                       int64_t nj, double t, double *__restrict__ part, int seg_base) {
+  __shared__ double s_col[A1(PAIR_NCOL)][PAIR_TJ];
+  __shared__ int32_t s_id[PAIR_TJ];
+  /* this CTA's j-range: segment blockIdx.y of gridDim.y, boundaries aligned to the j-tile */
+  const int64_t tiles = (nj + PAIR_TJ - 1) / PAIR_TJ;
+  const int64_t tps = (tiles + gridDim.y - 1) / gridDim.y;
+  const int64_t jbeg = (int64_t)blockIdx.y * tps * PAIR_TJ;
+  int64_t jend = jbeg + tps * PAIR_TJ; if (jend > nj) jend = nj;
+  const int64_t ia = (int64_t)blockIdx.x * PAIR_ITILE + threadIdx.x, ib = ia + PAIR_THREADS;
+  const bool la = ia < p.n, lb = ib < p.n;
+  const int64_t ja = la ? ia : p.n - 1, jb = lb ? ib : p.n - 1;
+  double ya[A1(NVAR)], ea[A1(NEXPR)], yb[A1(NVAR)], eb[A1(NEXPR)], acca[A1(NPSI)], accb[A1(NPSI)];
+  load_cols<NVAR>(ysrc, p.stride, ja, ya); load_cols<NEXPR>(p.E, p.stride, ja, ea);
+  load_cols<NVAR>(ysrc, p.stride, jb, yb); load_cols<NEXPR>(p.E, p.stride, jb, eb);
+  const int32_t ida = M::NEEDS_ID ? p.ID[ja] : 0, idb = M::NEEDS_ID ? p.ID[jb] : 0;
+  const int slow = pair_rows<false>(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
+  if (__syncthreads_or(slow))        /* rare: a fast-path sincos argument out of range somewhere in this CTA */
+    pair_rows<true>(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
   double *dst = part + (size_t)(seg_base + blockIdx.y) * A1(NPSI) * p.stride;
 #pragma unroll
   for (int k = 0; k < NPSI; k++) {
@@ -831,7 +877,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
       load_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     } else {
       DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
-      M::rhs(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+      rhs_checked(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
       store_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     }
     double yn[A1(NVAR)];

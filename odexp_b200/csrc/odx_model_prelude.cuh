@@ -29,13 +29,18 @@ static void odx_sincos_library(double x, double *sp, double *cp) { sincos(x, sp,
 __constant__ double odx_sc_dev[16] = ODX_SC_TABLE;
 #endif
 static const double odx_sc_host[16] = ODX_SC_TABLE;
-ODX_HD void odx_sincos(double x, double *sp, double *cp) {
+/* EXACT = false: straight-line fast path for every argument; out-of-range arguments only raise c.slow, and the caller redoes
+ * the particle with EXACT = true.  (A branch to the library inside the fast path splits the basic block and keeps the compiler
+ * from interleaving the two particles a thread carries: measured 135 -> ~100 issued instructions per particle-stage.) */
+template <bool EXACT, class C>
+ODX_HD void odx_sincos(C &ctx, double x, double *sp, double *cp) {
 #if defined(__CUDA_ARCH__)
   const double *T = odx_sc_dev;
 #else
   const double *T = odx_sc_host;
 #endif
-  if (!(fabs(x) < 105615.0)) { odx_sincos_library(x, sp, cp); return; }
+  if (EXACT) { odx_sincos_library(x, sp, cp); return; }
+  ctx.slow |= !(fabs(x) < 105615.0);
   const double q = rint(x * T[0]);
   const int n = (int)q;
   double r = fma(-q, T[1], x);

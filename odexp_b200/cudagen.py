@@ -304,7 +304,7 @@ class Emitter:
             if key not in cache:
                 cache[key] = len(cache)
                 k = cache[key]
-                out("    double odx_sn%d, odx_cs%d; odx_sincos(%s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
+                out("    double odx_sn%d, odx_cs%d; odx_sincos<ODX_EXACT>(odx_c, %s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
             k = cache[key]
             e = e[:b] + ("odx_sn%d" % k if fn == "sin" else "odx_cs%d" % k) + e[en:]
 
@@ -354,7 +354,9 @@ class Emitter:
         w("")
         # ---- ode_rhs
         w("  /* per-particle right-hand side: AUX, D/DT, %DEATH, %REPLI (reference: generated ode_rhs) */")
-        w("  template <class C> ODX_HD static void rhs(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("  /* ODX_EXACT = false: range-limited fast sincos, the context records when an argument was out of range and the engine")
+        w("   * redoes the particle with ODX_EXACT = true (library sincos); keeps the hot code free of branches */")
+        w("  template <bool ODX_EXACT, class C> ODX_HD static void rhs(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli) {")
         w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e;")
         for i, p in enumerate(m.pars):
@@ -391,21 +393,21 @@ class Emitter:
         w("  }\n")
         # ---- %M terms
         w("  /* per-particle %M expressions (summed over the population, then divided by POP_SIZE) */")
-        w("  template <class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("  template <bool ODX_EXACT, class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, double *odx_m) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m;")
         tc = {}
         for e in m.mfds:
             w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w)))
         w("  }\n")
-        w("  template <class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("  template <bool ODX_EXACT, class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c;")
         w("    return %s;" % (self.tr(m.birth, "%BIRTH") if m.birth else "0.0"))
         w("  }\n")
         # ---- %C terms
         w("  /* pairwise %C expressions: odx_p[k] += expr_k(me, other) */")
-        w("  template <class C> ODX_HD static void cpl_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("  template <bool ODX_EXACT, class C> ODX_HD static void cpl_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, const double *odx_oy, const double *odx_oe, const double *odx_oaux, double *odx_p) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_oy; (void)odx_oe; (void)odx_oaux; (void)odx_c; (void)odx_p;")
         tc = {}

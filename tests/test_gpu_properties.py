@@ -143,3 +143,30 @@ def test_strided_trajectory_output(model_lib):
         assert len(b) == (1001 + 6) // 7
         np.testing.assert_array_equal(a["id"], b["id"])
         np.testing.assert_array_equal(a["cols"], b["cols"])
+
+
+def test_sincos_out_of_range_takes_library_path(model_lib):
+    """phases beyond the fast sincos range (|x| >= 105615) must be redone with the library sincos: compare a few RK4 steps of
+    an uploaded population with theta ~ 1e6 against a float64 numpy RK4 of the same model (two-pass pop_rhs semantics)"""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    rng = np.random.default_rng(5)
+    n = 4097
+    theta = 1.0e6 + 50.0 * rng.random(n)
+    theta[::3] = 2 * np.pi * rng.random(len(theta[::3]))       # mix of in-range and out-of-range particles
+    omega = 0.6283184 + 0.1 * rng.standard_normal(n)
+    pop = capi.Population(lib, capacity=8192)
+    pop.upload(theta.reshape(-1, 1), omega.reshape(-1, 1))
+    pop.run_fixed("dde", 0.0, 0.05, 5)
+    got = pop.download()["y"][:, 0]
+    pop.close()
+    K, h = 0.1, 0.05
+
+    def f(th):
+        a1, a2 = np.sin(th).sum() / n, np.cos(th).sum() / n
+        return omega + K * (a1 * np.cos(th) - a2 * np.sin(th))
+    y = theta.copy()
+    for _ in range(5):
+        k1 = f(y); k2 = f(y + h / 2.0 * k1); k3 = f(y + h / 2.0 * k2); k4 = f(y + h * k3)
+        y = y + h / 6.0 * (k1 + 2.0 * (k2 + k3) + k4)
+    np.testing.assert_allclose(got, y, rtol=1e-12, atol=1e-9)
