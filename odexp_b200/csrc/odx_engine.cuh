@@ -46,6 +46,12 @@ constexpr int NRED = NMFD + 2;                          /* [%M sums..., %BIRTH s
 constexpr int RED_BIRTH = NMFD, RED_RATES = NMFD + 1;
 constexpr int BLOCK = 256;
 constexpr int MAXSTAGE = 7;
+#ifndef STAGE_LOAD_CS
+#define STAGE_LOAD_CS 0
+#endif
+#ifndef STAGE_STORE_CS
+#define STAGE_STORE_CS 1   /* streaming stores: neutral at N=2^24, +5% at N=2^22 (measured) */
+#endif
 #ifndef CHAIN_MIN_BLOCKS
 #define CHAIN_MIN_BLOCKS 4
 #endif
@@ -305,7 +311,11 @@ __device__ __forceinline__ void load_cols2(const double *__restrict__ base, int6
                                            double (&o0)[A1(NC)], double (&o1)[A1(NC)]) {
 #pragma unroll
   for (int c = 0; c < NC; c++) {
+#if STAGE_LOAD_CS
+    if (two) { const double2 v = __ldcs(reinterpret_cast<const double2 *>(base + (int64_t)c * stride + i)); o0[c] = v.x; o1[c] = v.y; }
+#else
     if (two) { const double2 v = *reinterpret_cast<const double2 *>(base + (int64_t)c * stride + i); o0[c] = v.x; o1[c] = v.y; }
+#endif
     else { o0[c] = base[(int64_t)c * stride + i]; o1[c] = o0[c]; }
   }
 }
@@ -314,7 +324,11 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
                                             const double (&v0)[A1(NC)], const double (&v1)[A1(NC)]) {
 #pragma unroll
   for (int c = 0; c < NC; c++) {
+#if STAGE_STORE_CS
+    if (two) __stcs(reinterpret_cast<double2 *>(base + (int64_t)c * stride + i), make_double2(v0[c], v1[c]));
+#else
     if (two) *reinterpret_cast<double2 *>(base + (int64_t)c * stride + i) = make_double2(v0[c], v1[c]);
+#endif
     else base[(int64_t)c * stride + i] = v0[c];
   }
 }

@@ -38,6 +38,24 @@ def connect(pop, use_nccl=True, use_peers=True):
         uid = broadcast_bytes(pop.unique_id() if rank == 0 else None, src=0)
         pop.comm_init(rank, world, uid)
     if use_peers:
-        handles = all_gather_bytes(pop.peer_export())
-        pop.peer_attach(rank, world, handles)
+        # every rank must take the same decision: attach only if the export / attach succeeded everywhere
+        try:
+            mine = pop.peer_export()
+        except Exception:
+            mine = None
+        handles = all_gather_bytes(mine)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                pop.peer_attach(rank, world, handles)
+            except Exception:
+                ok = False
+        if not all(all_gather_bytes(ok)):
+            # no peer access on this box: the library falls back to ncclAllReduce for the per-stage sums
+            try:
+                pop.peer_attach(rank, 1, [mine or b"\0" * 64])
+                if use_nccl:
+                    pop.comm_init(rank, world, uid)
+            except Exception:
+                pass
     dist.barrier()
