@@ -170,6 +170,11 @@ class Population:
         buf = C.create_string_buffer(b"".join(handles), 64 * nranks)
         self._ck(self.L.odx_peer_attach(self.h, rank, nranks, buf), "odx_peer_attach")
 
+    def peer_detach(self):
+        r, n = C.c_int(), C.c_int()
+        self.L.odx_comm_rank(self.h, C.byref(r), C.byref(n))
+        self._ck(self.L.odx_peer_attach(self.h, r.value, n.value, None), "odx_peer_attach(detach)")
+
     def comm_init(self, rank, nranks, uid):
         buf = C.create_string_buffer(bytes(uid), 128)
         self._ck(self.L.odx_comm_init(self.h, rank, nranks, buf), "odx_comm_init")

@@ -737,6 +737,7 @@ int odx_peer_export(odx_handle *h, void *handle64) {
 }
 int odx_peer_attach(odx_handle *h, int rank, int nranks, const void *handles64) {
   if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks) { h->err = "odx_peer_attach: bad rank / nranks"; return ODX_EINVAL; }
+  if (handles64 == nullptr) { h->peers_attached = false; return ODX_SUCCESS; }      /* detach: back to the NCCL exchange */
   ODX_CUDA(h, cudaSetDevice(h->device));
   ODX_TRY(ensure_mail(h));
   for (int r = 0; r < nranks; r++) {

@@ -51,11 +51,5 @@ def connect(pop, use_nccl=True, use_peers=True):
             except Exception:
                 ok = False
         if not all(all_gather_bytes(ok)):
-            # no peer access on this box: the library falls back to ncclAllReduce for the per-stage sums
-            try:
-                pop.peer_attach(rank, 1, [mine or b"\0" * 64])
-                if use_nccl:
-                    pop.comm_init(rank, world, uid)
-            except Exception:
-                pass
+            pop.peer_detach()       # no peer access on this box: per-stage sums go through ncclAllReduce instead
     dist.barrier()

@@ -19,6 +19,7 @@ def _worker(rank, world, port, q):
         def comm_init(self, r, w, u): self.comm = (r, w, u)
         def peer_export(self): return bytes([rank + 65]) * 64
         def peer_attach(self, r, w, h): self.peers = (r, w, h)
+        def peer_detach(self): self.peers = None
     fp = FakePop()
     odist.connect(fp)
     q.put((rank, uid, handles, lo, hi, fp.comm, fp.peers))
