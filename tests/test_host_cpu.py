@@ -48,11 +48,13 @@ def test_emit_translates_macros():
     from odexp_b200 import popfile, cudagen
     cu = cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto")))
     # sin / cos of the same argument are hoisted into one odx_sincos
-    assert "odx_sincos((odx_y[0]), &odx_sn0, &odx_cs0);" in cu and "odx_m[0] = odx_sn0;" in cu and "odx_m[1] = odx_cs0;" in cu
-    assert "odx_m[2] = (odx_e[0]);" in cu and cu.count("odx_sincos(") == 2
+    assert "odx_sincos<ODX_EXACT>(odx_c, (odx_y[0]), &odx_sn0, &odx_cs0);" in cu and "odx_m[0] = odx_sn0;" in cu and "odx_m[1] = odx_cs0;" in cu
+    assert "odx_m[2] = (odx_e[0]);" in cu and cu.count("odx_sincos<ODX_EXACT>(") == 2
     assert "NVAR = 1, NEXPR = 1, NAUX = 2, NPSI = 0, NMFD = 3" in cu
     nb = cudagen.emit_cuda(popfile.parse_file(fixture_path("nbody")))
-    assert "odx_pow15(" in nb and "pow(" not in nb.replace("odx_pow", "")
+    # pow(x,1.5) -> x*sqrt(x) in the emitted helper function; inlined + 1/pow(x,1.5) -> rsqrt(x)^3 in the %C terms
+    assert "odx_pow15(" in nb and "odx_rpow15(" in nb and "odx_sel(" in nb
+    assert "pow(" not in nb.replace("odx_pow", "").replace("odx_rpow", "")
     sde = cudagen.emit_cuda(popfile.parse_file(fixture_path("vdp_sde")))
     assert "odx_c.dwdt()" in sde and "odx_c.atbirth" in sde and "HAS_BIRTH = true" in sde
 
