@@ -265,12 +265,80 @@ __global__ void __launch_bounds__(BLOCK, 5) k_lr_moments(const double *__restric
     }
   }
 }
-__global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restrict__ partial, int nblocks, double *__restrict__ A) {
-  const int q = blockIdx.x * BLOCK + threadIdx.x;
+/* rank-64 path: warp-split moment GEMM.  4 warps per CTA share a staged tile of 32 particles; every warp takes 8 of them and
+ * every lane owns the column pair m = 2*lane, 2*lane+1 for ALL orders k: one 16-byte shared-memory read of V per particle feeds
+ * 2 x P1T DFMAs (the powers are broadcast reads), so the kernel is bound by the FP64 pipe, not by shared memory.  The tile is
+ * stored pair-swizzled (pair index XOR particle index) so the transposing stores of the staging phase spread over the banks. */
+constexpr bool LR_WSPLIT = (LR_R == 64);
+constexpr int LR_WS_THREADS = 128, LR_WS_WARPS = 4, LR_WS_TILE = 32;
+template <int P1T>
+__global__ void __launch_bounds__(LR_WS_THREADS, 3) k_lr_moments_ws(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
+                                                                    int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
+  __shared__ __align__(16) double s_v[LR_WS_TILE][64];
+  __shared__ __align__(16) double s_pw[LR_WS_TILE][P1T];
+  const int p1 = plan->p + 1;
+  if ((p1 + 7) / 8 * 8 != P1T) return;
+  const double meanx = plan->meanx, range = plan->range;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[2][P1T];
+#pragma unroll
+  for (int k = 0; k < P1T; k++) { acc[0][k] = 0.0; acc[1][k] = 0.0; }
+  for (int64_t base = (int64_t)blockIdx.x * LR_WS_TILE; base < n; base += (int64_t)gridDim.x * LR_WS_TILE) {
+    const int cnt = (int)((n - base) < LR_WS_TILE ? (n - base) : LR_WS_TILE);
+    __syncthreads();
+#pragma unroll 4
+    for (int q = threadIdx.x; q < LR_WS_TILE * 64; q += LR_WS_THREADS) {
+      const int jj = q % LR_WS_TILE, m = q / LR_WS_TILE;                  /* coalesced along particles */
+      const double v = (jj < cnt) ? V[(int64_t)m * vstride + base + jj] : 0.0;
+      s_v[jj][(((m >> 1) ^ jj) << 1) | (m & 1)] = v;
+    }
+    if (threadIdx.x < LR_WS_TILE) {
+      const int jj = threadIdx.x;
+      const double xi = (jj < cnt) ? (x[base + jj] - meanx) / range : 0.0;
+      double pw = 1.0;
+#pragma unroll
+      for (int k = 0; k < P1T; k++) { s_pw[jj][k] = (jj < cnt && k < p1) ? pw : 0.0; pw *= xi; }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int tq = 0; tq < LR_WS_TILE / LR_WS_WARPS; tq++) {
+      const int jj = warp * (LR_WS_TILE / LR_WS_WARPS) + tq;
+      const double2 va = *reinterpret_cast<const double2 *>(&s_v[jj][(lane ^ jj) << 1]);
+#pragma unroll
+      for (int k = 0; k < P1T; k += 2) {
+        const double2 pk = *reinterpret_cast<const double2 *>(&s_pw[jj][k]);
+        acc[0][k] = fma(va.x, pk.x, acc[0][k]); acc[1][k] = fma(va.y, pk.x, acc[1][k]);
+        acc[0][k + 1] = fma(va.x, pk.y, acc[0][k + 1]); acc[1][k + 1] = fma(va.y, pk.y, acc[1][k + 1]);
+      }
+    }
+  }
+  /* the four warps add their accumulators in warp order through shared memory (the staged tile is dead by now), then the CTA
+   * writes ONE partial, layout q = k * 64 + m; orders >= P1T stay zero (the buffer is cleared by the host) */
+  double *s_red = &s_v[0][0];                       /* LR_WS_TILE * 64 = 2048 doubles >= P1T * 64 */
+  for (int w = 0; w < LR_WS_WARPS; w++) {
+    __syncthreads();
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < P1T; k++) {
+        double2 *slot = reinterpret_cast<double2 *>(&s_red[k * 64 + 2 * lane]);
+        if (w == 0) *slot = make_double2(acc[0][k], acc[1][k]);
+        else { const double2 o = *slot; *slot = make_double2(o.x + acc[0][k], o.y + acc[1][k]); }
+      }
+    }
+  }
+  __syncthreads();
+  double *dst = partial + (size_t)blockIdx.x * LR_R * LR_P1;
+  for (int q = threadIdx.x; q < P1T * 64; q += LR_WS_THREADS) dst[q] = s_red[q];
+}
+
+/* fixed-order sum of groups of partials: out[g][q] = sum_{b in group g} in[b][q]; called twice (groups of 32, then all) */
+__global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restrict__ in, int nin, int group, double *__restrict__ out) {
+  const int q = blockIdx.x * BLOCK + threadIdx.x, g = blockIdx.y;
   if (q >= LR_R * LR_P1) return;
+  const int b0 = g * group, b1 = (b0 + group < nin) ? b0 + group : nin;
   double a = 0.0;
-  for (int b = 0; b < nblocks; b++) a += partial[(size_t)b * LR_R * LR_P1 + q];
-  A[q] = a;                                                             /* q = k * LR_R + m */
+  for (int b = b0; b < b1; b++) a += in[(size_t)b * LR_R * LR_P1 + q];
+  out[(size_t)g * LR_R * LR_P1 + q] = a;                                 /* q = k * LR_R + m */
 }
 
 /* psi_i for the particles of this GPU.  P1T = p + 1 rounded up to a multiple of 8: the host launches the four
@@ -278,11 +346,11 @@ __global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restri
 template <int P1T>
 __global__ void __launch_bounds__(128) k_lr_apply(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride, int64_t n,
                                                    const LrPlan *__restrict__ plan, const double *__restrict__ A, double *__restrict__ psi) {
-  __shared__ double s_A[P1T][LR_R];
+  __shared__ __align__(16) double s_A[LR_R][P1T];          /* [m][k]: two orders per 16-byte broadcast read */
   __shared__ double s_BC[P1T][P1T];
   const int p1 = plan->p + 1;
   if ((p1 + 7) / 8 * 8 != P1T) return;
-  for (int q = threadIdx.x; q < P1T * LR_R; q += 128) s_A[q / LR_R][q % LR_R] = A[q];
+  for (int q = threadIdx.x; q < P1T * LR_R; q += 128) s_A[q % LR_R][q / LR_R] = A[q];
   for (int q = threadIdx.x; q < P1T * P1T; q += 128) s_BC[q / P1T][q % P1T] = plan->BC[q / P1T][q % P1T];
   __syncthreads();
   const double meanx = plan->meanx, range = plan->range;
@@ -299,7 +367,10 @@ __global__ void __launch_bounds__(128) k_lr_apply(const double *__restrict__ x, 
 #pragma unroll
       for (int q = 0; q < UB; q++) {
 #pragma unroll
-        for (int k = 0; k < P1T; k++) ua[k] = fma(u[q], s_A[k][m + q], ua[k]);
+        for (int k = 0; k < P1T; k += 2) {
+          const double2 a2 = *reinterpret_cast<const double2 *>(&s_A[m + q][k]);
+          ua[k] = fma(u[q], a2.x, ua[k]); ua[k + 1] = fma(u[q], a2.y, ua[k + 1]);
+        }
       }
     }
     /* phi_k(nxi) = sum_{l>=k} B[l] C(l,k) nxi^(l-k): Horner in nxi (no table of powers in registers) */

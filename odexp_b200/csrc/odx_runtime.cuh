@@ -178,7 +178,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     ODX_CUDA(h, cudaMalloc(&h->lr_rank, sizeof(LrRank)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 8));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_spart, sizeof(double) * 3 * (h->grid_cap + 1)));
-    ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (8 * h->sm_count + 1)));
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (24 * h->sm_count + 24 * h->sm_count / 32 + 2)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
   }
   const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
@@ -203,10 +203,30 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   ODX_TRY(launch_check(h));
   k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, rk, (LrPlan *)h->lr_plan);
   ODX_TRY(launch_check(h));
-  k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
-  ODX_TRY(launch_check(h));
-  k_lr_moments_sum<<<(LR_R * LR_P1 + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(h->lr_apart, nblk, h->lr_A);
-  ODX_TRY(launch_check(h));
+  int npart = nblk;
+  if (LR_WSPLIT) {
+    nblk = (int)((n + LR_WS_TILE - 1) / LR_WS_TILE);
+    if (nblk > 6 * h->sm_count) nblk = 6 * h->sm_count;
+    if (nblk < 1) nblk = 1;
+    npart = nblk;
+    const double *Vc = h->E + (size_t)M::LR0_V * h->cap; const LrPlan *plm = (const LrPlan *)h->lr_plan;
+    ODX_CUDA(h, cudaMemsetAsync(h->lr_apart, 0, sizeof(double) * (size_t)LR_R * LR_P1 * npart, h->stream));
+    k_lr_moments_ws<8><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<16><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<24><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<32><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+  } else {
+    k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
+    ODX_TRY(launch_check(h));
+  }
+  {
+    const int qb = (LR_R * LR_P1 + BLOCK - 1) / BLOCK, ng = (npart + 31) / 32;
+    double *stage2 = h->lr_apart + (size_t)LR_R * LR_P1 * (24 * h->sm_count);      /* tail of the partial buffer */
+    k_lr_moments_sum<<<dim3(qb, ng), BLOCK, 0, h->stream>>>(h->lr_apart, npart, 32, stage2);
+    ODX_TRY(launch_check(h));
+    k_lr_moments_sum<<<dim3(qb, 1), BLOCK, 0, h->stream>>>(stage2, ng, ng, h->lr_A);
+    ODX_TRY(launch_check(h));
+  }
 #ifdef ODX_HAVE_NCCL_H
   if (h->nranks > 1) {      /* moments are sums over particles: allreduce(SUM) of r x (p+1) doubles */
     ncclResult_t r = g_nccl.AllReduce(h->lr_A, h->lr_A, (size_t)LR_R * LR_P1, ncclDouble, ncclSum, h->comm, h->stream);
