@@ -92,6 +92,16 @@ static const tableau TAB_RKCK = {
   {37.0/378.0 - 2825.0/27648.0, 0.0, 250.0/621.0 - 18575.0/48384.0, 125.0/594.0 - 13525.0/55296.0,
    -277.0/14336.0, 512.0/1771.0 - 0.25}};
 
+/* test hook: copy a tableau out (kind: 2 = rkf45, 3 = rkck); ah[5], b[25] row-major, c[6], ec[6] */
+int minigsl_tableau(int kind, double *ah, double *b, double *c, double *ec) {
+  const tableau *T = kind == 2 ? &TAB_RKF45 : (kind == 3 ? &TAB_RKCK : NULL);
+  int i, j;
+  if (!T) return -1;
+  for (i = 0; i < 5; i++) { ah[i] = T->ah[i]; for (j = 0; j < 5; j++) b[5 * i + j] = T->b[i][j]; }
+  for (i = 0; i < 6; i++) { c[i] = T->c[i]; ec[i] = T->ec[i]; }
+  return 0;
+}
+
 static int embedded_apply(gsl_odeiv2_step *s, const tableau *T, double t, double h, double y[], double yerr[],
                           const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
   const size_t n = s->dim; size_t i; int st, j;
