@@ -23,7 +23,7 @@ LIB_SRCS = ["main", "methods_odexp", "datastruct", "loader", "options", "rand_ge
 # _FORTIFY_SOURCE off: the reference's loader passes over-stated buffer lengths to snprintf/strncat for array entries
 # (`expr U[i=0:R] ...`); harmless on its macOS target, aborted by glibc's fortified variants
 CFLAGS = ["-std=gnu99", "-O3", "-D_GNU_SOURCE", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-w", "-I" + os.path.join(HERE, "stubinc"),
-          "-I" + os.path.join(REF, "src"), "-include", "errno.h", "-include", "gsl/gsl_errno.h"]
+          "-I" + os.path.join(REF, "src"), "-include", "errno.h", "-include", "gsl/gsl_errno.h", "-include", "bsd_compat.h"]
 
 
 def run(cmd, **kw):

@@ -120,7 +120,28 @@ static void lm_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = 0.1 + 0.8 * orc_rand01(c);
 }
 
+/* ---------------------------------------------------------------- reset_decay.pop */
+static const double rd_pars[] = {0.5, 0.35};
+static void rd_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double k = c->mu[0], xmin = c->mu[1], x = y_[0];
+  const double low = orc_stopif(c, x < xmin);
+  (void)t; (void)e; (void)psi; (void)mfd; (void)death; (void)repli;
+  f[0] = -k * x;
+  aux[0] = low;
+}
+static double rd_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void rd_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = 0.5 + orc_rand01(c);
+  y[0] = c->ist0 ? e[0] : 2.0 * e[0];          /* IST0(x0, 2.0*x0) */
+}
+
 static const orc_model MODELS[] = {
+  {"reset_decay", 1, 1, 1, 0, 1, 2, rd_pars, rd_rhs, rd_mfd, NULL, NULL, rd_ic, 0, 0, 0, 0, 0, NULL},
   {"logistic_map", 1, 1, 1, 0, 1, 2, lm_pars, lm_rhs, lm_mfd, NULL, NULL, lm_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic, 0, 0, 0, 0, 0, NULL},

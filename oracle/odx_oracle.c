@@ -104,6 +104,7 @@ long orc_poisson(orc_ctx *c, double lambda) {
   return --k;
 }
 double orc_dwdt(orc_ctx *c) { return orc_randN(c, 0, 1) / sqrt(c->h); }
+int orc_stopif(orc_ctx *c, int cond) { if (cond) c->sim->stop_flag = ORC_STOP_COND; return cond; }
 
 static void host_ctx(orc_sim *s, orc_ctx *c, uint32_t kid) {     /* draws made by the solver loop itself */
   memset(c, 0, sizeof *c);
@@ -234,6 +235,7 @@ static void run_ic(orc_sim *s, orc_par *p, double t, uint32_t dom, uint32_t stre
   memset(&c, 0, sizeof c);
   c.sim = s; c.mu = s->mu; c.pop_size = (double)s->size; c.id = p->id; c.oid = p->id;
   c.atbirth = (s->event[0] == -1); c.atrepli = (s->event[0] >= 0 && s->event[1] == 1);
+  c.ist0 = (s->stop_flag == ORC_EVENT_T0);
   c.sister = p->sister;
   c.kid = (uint32_t)p->id; c.kstream = stream; c.kdom = dom; c.kslot = 0;
   s->model->ic(&c, t, p->y, p->expr);
@@ -371,15 +373,16 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   orc_sim S, *s = &S;
   double t, t1, dt, tnext, dt_ssa, dt_dyn, dt_next, sum_rates, expected, h, *y = NULL, *f = NULL, tot_solver = 0.0;
   const gsl_odeiv2_step_type *odeT = NULL; gsl_odeiv2_step *gs = NULL; gsl_odeiv2_control *gc = NULL; gsl_odeiv2_evolve *ge = NULL;
-  int status = GSL_SUCCESS, i, dim, tau = 0;
+  int status = GSL_SUCCESS, i, dim, tau = 0, nstops = 0, idx_stop = 0;
+  double *tstops = NULL, nextstop = INFINITY;
   char path[4096];
   clock_t start = clock(), c0;
   if (!m) return GSL_EINVAL;
-  if (o->tspan_len != 2) return GSL_EINVAL;
+  if (o->tspan_len < 2) return GSL_EINVAL;
   memset(s, 0, sizeof *s);
   s->model = m; s->o = *o;
   if (o->method == ORC_METH_ITERATION) {         /* src/methods_odexp.c:187-193 */
-    s->o.h0 = 1.0; s->o.res = (int)(o->tspan[1] - o->tspan[0]) + 1;
+    s->o.h0 = 1.0; s->o.res = (int)(o->tspan[o->tspan_len - 1] - o->tspan[0]) + 1;
   }
   o = &s->o;
   if (o->res < 2) return GSL_EINVAL;
@@ -392,7 +395,16 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   if (o->method == ORC_METH_RKF45) odeT = gsl_odeiv2_step_rkf45;
   else if (o->method == ORC_METH_RKCK) odeT = gsl_odeiv2_step_rkck;
   else if (o->method == ORC_METH_RK4) odeT = gsl_odeiv2_step_rk4;
-  t = o->tspan[0]; t1 = o->tspan[1];
+  t = o->tspan[0]; t1 = o->tspan[o->tspan_len - 1];
+  /* stopping times = interior TIMESPAN values, sorted (src/methods_odexp.c:222-236); past the last one the reference reads
+   * beyond its array, restated as "no further stop" */
+  if (o->tspan_len > 2) {
+    nstops = o->tspan_len - 2;
+    tstops = malloc(sizeof(double) * nstops);
+    for (i = 0; i < nstops; i++) tstops[i] = o->tspan[i + 1];
+    for (i = 1; i < nstops; i++) { double v = tstops[i]; int j2 = i - 1; while (j2 >= 0 && tstops[j2] > v) { tstops[j2 + 1] = tstops[j2]; j2--; } tstops[j2 + 1] = v; }
+    nextstop = tstops[idx_stop++];
+  }
   s->stop_flag = ORC_EVENT_T0;
   dt = (t1 - t) / (double)(o->res - 1);
   snprintf(path, sizeof path, "%s/stats.dat", o->outdir);
@@ -414,6 +426,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
 
   while (t < t1 && s->size > 0) {
     dt_dyn = fmin(dt, t1 - t);
+    if ((t <= nextstop) && (dt_dyn >= (nextstop - t))) { dt_dyn = nextstop - t; s->stop_flag = ORC_STOP_TSPAN; }
     dt_ssa = orc_ssa_timestep(s, &sum_rates);
     expected = 1.0 / sum_rates;
     tau = !(expected > (dt_dyn * o->ssahmin));
@@ -433,8 +446,9 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
         else if (o->method == ORC_METH_FE) status = orc_fe_apply(s, &t, tnext, &h, y, dim);
         else if (o->method == ORC_METH_DDE) status = orc_dde_apply(s, &t, tnext, &h, y, dim);
         else status = gsl_odeiv2_evolve_apply(ge, gc, gs, &sys, &t, tnext, &h, y);
-        if (status != GSL_SUCCESS) { s->stop_flag = ORC_EVENT_GSL; break; }
         s->steps++; s->particle_steps += nstep;
+        if (s->stop_flag & ORC_STOP_COND) break;
+        if (status != GSL_SUCCESS) { s->stop_flag = ORC_EVENT_GSL; break; }
         if (h < o->hmin) h = o->hmin;
       }
     }
@@ -454,8 +468,18 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
       memset(s->event, 0, sizeof s->event);
       if (odeT) { gsl_odeiv2_evolve_free(ge); gsl_odeiv2_step_free(gs); gs = gsl_odeiv2_step_alloc(odeT, dim); ge = gsl_odeiv2_evolve_alloc(dim); }
     }
+    if (s->stop_flag & (ORC_STOP_COND | ORC_STOP_TSPAN)) {
+      /* reset: pop_init_conditions for every particle, then a full RHS evaluation and a trajectory frame (:704-714) */
+      for (i = 0; i < s->n; i++) run_ic(s, s->p[i], t, ORC_DOM_IC + 4, s->reinit_index);
+      s->reinit_index++;
+      fill_y(s, y);
+      orc_pop_rhs(t, y, f, s);
+      write_traj(s, t);
+    }
+    if (s->stop_flag & ORC_STOP_TSPAN) nextstop = (idx_stop < nstops) ? tstops[idx_stop++] : INFINITY;
     s->stop_flag = ORC_EVENT_NONE;
   }
+  free(tstops);
   if (rep) {
     rep->total_ms = (clock() - start) * 1000.0 / CLOCKS_PER_SEC; rep->solver_ms = tot_solver; rep->function_ms = s->function_ms;
     rep->steps = s->steps; rep->particle_steps = s->particle_steps; rep->final_n = s->size; rep->status = status;

@@ -6,7 +6,7 @@
 #include <stdio.h>
 
 enum { ORC_METH_FE = 0, ORC_METH_DDE = 1, ORC_METH_RKF45 = 2, ORC_METH_RKCK = 3, ORC_METH_RK4 = 4, ORC_METH_ITERATION = 5 };
-enum { ORC_EVENT_NONE = 0x00, ORC_EVENT_T0 = 0x01, ORC_EVENT_TFINAL = 0x02, ORC_STOP_BIRTH = 0x10, ORC_STOP_DEATH = 0x20,
+enum { ORC_EVENT_NONE = 0x00, ORC_EVENT_T0 = 0x01, ORC_EVENT_TFINAL = 0x02, ORC_STOP_TSPAN = 0x04, ORC_STOP_COND = 0x08, ORC_STOP_BIRTH = 0x10, ORC_STOP_DEATH = 0x20,
        ORC_STOP_REPLI = 0x40, ORC_POP_MASK = 0x70, ORC_EVENT_GSL = 0x100 };
 /* Philox domain tags, identical to odexp_b200/csrc/odx_rng.h (rng_mode 1 only) */
 #define ORC_DOM_RHS  0x52485300u
@@ -27,7 +27,7 @@ struct orc_sim;
 typedef struct orc_ctx {
   struct orc_sim *sim;
   const double *mu; double pop_size, h;
-  int id, oid, atbirth, atrepli;
+  int id, oid, atbirth, atrepli, ist0;
   const orc_par *sister;
   uint32_t kid, kstream, kdom, kslot;      /* keyed-Philox address of the next draw (rng_mode 1) */
 } orc_ctx;
@@ -71,7 +71,7 @@ typedef struct orc_sim {
   FILE *fstats, *ftraj;
   int rng_mode; orc_hostrand hr; uint32_t k0, k1, eval_index, host_draws, event_index;
   uint64_t rhs_evals; int64_t steps; double particle_steps, function_ms;
-  int lr_last_p;
+  int lr_last_p; uint32_t reinit_index;
 } orc_sim;
 void orc_lowrank_apply(orc_sim *s);
 
@@ -80,6 +80,7 @@ double orc_randN(orc_ctx *c, double mu, double sigma);
 double orc_exprand(orc_ctx *c, double r);
 long   orc_poisson(orc_ctx *c, double lambda);
 double orc_dwdt(orc_ctx *c);
+int    orc_stopif(orc_ctx *c, int cond);      /* STOPIF(cond), src/odexp.h:400-406 */
 
 const orc_model *orc_find_model(const char *name);
 int orc_pop_rhs(double t, const double *y, double *f, void *sim);
