@@ -25,7 +25,7 @@ class ModelInfo(C.Structure):
                 ("rhs_uses_rng", C.c_int), ("has_pairwise", C.c_int), ("has_lowrank", C.c_int),
                 ("var_names", C.POINTER(C.c_char_p)), ("expr_names", C.POINTER(C.c_char_p)), ("aux_names", C.POINTER(C.c_char_p)),
                 ("psi_names", C.POINTER(C.c_char_p)), ("mfd_names", C.POINTER(C.c_char_p)), ("par_names", C.POINTER(C.c_char_p)),
-                ("par_defaults", C.POINTER(C.c_double))]
+                ("par_defaults", C.POINTER(C.c_double)), ("has_stopif", C.c_int)]
 
 
 class EventRow(C.Structure):
@@ -47,7 +47,7 @@ class SolverReport(C.Structure):
 # every symbol include/odx.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_sync", "odx_set_params", "odx_set_seed",
                "odx_set_tolerances", "odx_comm_unique_id", "odx_comm_init", "odx_pop_upload", "odx_pop_download", "odx_pop_size",
-               "odx_pop_init", "odx_rhs", "odx_meanfields", "odx_rates", "odx_fe_apply", "odx_dde_apply", "odx_evolve_reset",
+               "odx_pop_init", "odx_pop_reinit", "odx_stop_flag", "odx_rhs", "odx_meanfields", "odx_rates", "odx_fe_apply", "odx_dde_apply", "odx_evolve_reset",
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
@@ -86,6 +86,8 @@ class ModelLib:
         L.odx_pop_download_strided.argtypes = [H, C.c_int64, C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)]
         L.odx_pop_size.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.odx_pop_init.argtypes = [H, C.c_int64, C.c_double, C.c_uint32, C.c_int]
+        L.odx_pop_reinit.argtypes = [H, C.c_double, C.c_int]
+        L.odx_stop_flag.argtypes = [H, C.POINTER(C.c_int)]
         L.odx_rhs.argtypes = [H, C.c_double]
         L.odx_meanfields.argtypes = [H, C.POINTER(C.c_double)]
         L.odx_rates.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double)]

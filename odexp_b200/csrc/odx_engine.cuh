@@ -66,6 +66,7 @@ struct DevCtx {
   PhiloxStream rng;
   int32_t id, oid;          /* ID / OID */
   int atbirth, atrepli;     /* ATBIRTH / ATREPLI (src/odexp.h:366-367) */
+  int ist0;                 /* IST0: initial conditions of the very first population (EVENT_TYPE == EVENT_T0) */
   const double *sis_y, *sis_e, *sis_aux;   /* sister particle (valid only during replication ICs) */
   int has_sister;
   int stop;                 /* STOPIF */
@@ -79,7 +80,7 @@ struct DevCtx {
 
 /* host context for replayed initial conditions: draws through the serial libc stream */
 struct HostCtx {
-  const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli;
+  const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli, ist0;
   const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop; int slow;
   ODX_HD double rand01() { return hr->rand01(); }
   ODX_HD double randN(double m, double s) { return hr->randN(m, s); }
@@ -97,6 +98,7 @@ struct Pop {
   double n_global;          /* POP_SIZE across all GPUs */
   const double *mu;
   uint32_t k0, k1;          /* Philox key */
+  int *stop;                /* sticky STOPIF flag of the whole population (models with STOPIF only) */
 };
 
 struct Red {                /* grid reduction scratch */
@@ -187,8 +189,15 @@ __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stre
   DevCtx c;
   c.mu = p.mu; c.pop_size = p.n_global; c.h = h;
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
-  c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
+  c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   return c;
+}
+
+/* STOPIF (src/odexp.h:400-406): the reference sets the global EVENT_TYPE from inside ode_rhs; here the full (second-pass)
+ * evaluation of a particle raises one sticky device flag that the time loop reads after the step.  Compiled out for models
+ * without STOPIF.  A fast-path evaluation that is about to be redone (c.slow) does not count. */
+__device__ __forceinline__ void note_stop(const Pop &p, const DevCtx &c) {
+  if (M::HAS_STOPIF) { if (c.stop && !c.slow) atomicOr(p.stop, 1); }
 }
 
 /* %M terms of one particle state.  Pass-1 semantics of the reference: when a %M expression reads an
@@ -233,6 +242,12 @@ __device__ __forceinline__ void rhs_checked(DevCtx &c, double t, const double (&
   DevCtx c0 = c;
   M::template rhs<false>(c, t, y, e, psi, mfd, f, aux, death, repli);
   if (c.slow) { c = c0; M::template rhs<true>(c, t, y, e, psi, mfd, f, aux, death, repli); }
+}
+__device__ __forceinline__ void rhs_checked(const Pop &p, DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                            const double (&psi)[A1(NPSI)], const double (&mfd)[A1(NMFD)], double (&f)[A1(NVAR)],
+                                            double (&aux)[A1(NAUX)], double &death, double &repli) {
+  rhs_checked(c, t, y, e, psi, mfd, f, aux, death, repli);
+  note_stop(p, c);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -284,6 +299,7 @@ __device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, cons
   double f[A1(NVAR)];
   DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
   M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+  note_stop(p, c);
   int slow = c.slow;
 #pragma unroll
   for (int k = 0; k < NRED; k++) tm[k] = 0.0;
@@ -757,7 +773,7 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
     DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
-    rhs_checked(c, a.t, y, e, psi, mfd, f, aux, death, repli);
+    rhs_checked(p, c, a.t, y, e, psi, mfd, f, aux, death, repli);
     store_cols<NAUX>(p.AUX, p.stride, i, aux);
     if (M::HAS_DEATH) p.DEATH[i] = death;
     if (M::HAS_REPLI) p.REPLI[i] = repli;
@@ -891,7 +907,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
       load_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     } else {
       DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
-      rhs_checked(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+      rhs_checked(p, c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
       store_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     }
     double yn[A1(NVAR)];
@@ -976,17 +992,20 @@ __global__ void k_iota_ids(int32_t *id, int64_t n, int32_t first) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) id[i] = first + (int32_t)i;
 }
 /* ode_init_conditions on the device (keyed Philox), particles [first, first+count) */
-__global__ void __launch_bounds__(BLOCK) k_init(Pop p, int64_t first, int64_t count, double t, uint32_t stream, int atbirth) {
+/* mode 1: the first population (ATBIRTH, IST0, coupling / aux / rate columns cleared); mode 0: re-initialisation at a stopping
+ * time (pop_init_conditions on the living particles, src/methods_odexp.c:704-714): only Y and E are rewritten */
+__global__ void __launch_bounds__(BLOCK) k_init(Pop p, int64_t first, int64_t count, double t, uint32_t stream, int first_pop) {
   for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
     const int64_t i = first + q;
     double y[A1(NVAR)], e[A1(NEXPR)];
     load_cols<NVAR>(p.Y, p.stride, i, y);
     load_cols<NEXPR>(p.E, p.stride, i, e);
-    DevCtx c = make_ctx(p, 0.0, stream, DOM_IC, p.ID[i]);
-    c.atbirth = atbirth;
+    DevCtx c = make_ctx(p, 0.0, stream, first_pop ? DOM_IC : DOM_IC + 4, p.ID[i]);
+    c.atbirth = first_pop; c.ist0 = first_pop;
     M::ic(c, t, y, e);
     store_cols<NVAR>(p.Y, p.stride, i, y);
     store_cols<NEXPR>(p.E, p.stride, i, e);
+    if (!first_pop) continue;
     if (NPSI > 0) { for (int k = 0; k < NPSI; k++) p.PSI[(int64_t)k * p.stride + i] = 0.0; }
     if (NAUX > 0) { for (int k = 0; k < NAUX; k++) p.AUX[(int64_t)k * p.stride + i] = 0.0; }
     p.DEATH[i] = 0.0; p.REPLI[i] = 0.0;

@@ -6,7 +6,8 @@
  * The population itself never leaves the GPU between outputs: this file only talks to the C-ABI of include/odx.h.
  *
  * Differences from the reference that are deliberate and documented in DESIGN.md:
- *   - stopping times inside TIMESPAN (STOP_TSPAN re-initialisation) and STOPIF are not handled here (status ODX_EUNSUP);
+ *   - stopping times inside TIMESPAN (STOP_TSPAN) and STOPIF (STOP_COND) end the current output interval and re-initialise
+ *     the living particles (src/methods_odexp.c:222-236, 453-459, 704-720);
  *   - traj.dat can be thinned (traj_stride) or switched off: at N = 2^24 one frame is 1.2 GB;
  *   - current.plot (the 3-column quick buffer of the gnuplot UI) is not written.
  */
@@ -102,7 +103,8 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   odx_event_row *rows = NULL;
   int64_t rows_cap = 0, nrows = 0;
   uint64_t leap_index = 0;
-  (void)cmp_double;
+  double *tstops = NULL, nextstop = INFINITY;
+  int nstops = 0, idx_stop = 0;
 
   memset(&os, 0, sizeof os);
   if (rep) memset(rep, 0, sizeof *rep);
@@ -112,7 +114,13 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
     res = (int)(o->tspan[o->tspan_len - 1] - o->tspan[0]) + 1;
   }
   if (res < 2) return ODX_EINVAL;
-  if (o->tspan_len > 2) return ODX_EUNSUP;        /* stopping times: host-only feature of the reference UI */
+  if (o->tspan_len > 2) {                         /* interior TIMESPAN values are stopping times, sorted (:222-236) */
+    nstops = o->tspan_len - 2;
+    if ((tstops = malloc(sizeof(double) * nstops)) == NULL) return ODX_ENOMEM;
+    memcpy(tstops, o->tspan + 1, sizeof(double) * nstops);
+    qsort(tstops, nstops, sizeof(double), cmp_double);
+    nextstop = tstops[idx_stop++];
+  }
   os.nmfd = mi->nmfd; os.nvar = mi->nvar; os.naux = mi->naux; os.npsi = mi->npsi; os.nexpr = mi->nexpr;
   os.mfd = calloc(os.nmfd > 0 ? os.nmfd : 1, sizeof(double));
 
@@ -144,6 +152,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364) */
   if ((status = odx_rhs(h, t)) != 0) goto done;
   if ((status = odx_meanfields(h, os.mfd)) != 0) goto done;
+  if (mi->has_stopif) odx_stop_flag(h, NULL);      /* EVENT_TYPE = EVENT_NONE after the initial evaluation (:380) */
   odx_pop_size(h, NULL, &n, NULL);
   for (i = 0; i < o->popsize; i++) {              /* one stats row per initial particle (methods_odexp.c:372-376) */
     event[0] = -1; event[1] = 1; event[2] = (int)i;
@@ -157,6 +166,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   while (t < t1 && n > 0) {
     double u;
     dt_dyn = fmin(dt, t1 - t);
+    if ((t <= nextstop) && (dt_dyn >= (nextstop - t))) { dt_dyn = nextstop - t; stop_flag = ODX_STOP_TSPAN; }
     /* SSA_timestep (methods_odexp.c:1528-1553): always consumes one uniform */
     if ((status = odx_rates(h, &sum_rates, &birth_rate)) != 0) break;
     u = odx_draw_uniform(h, o->replay_ic);
@@ -180,11 +190,19 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
         if (o->method == ODX_METH_ITERATION) {
           status = odx_iteration_apply(h, &t, 1);
         } else if (o->method == ODX_METH_FE || o->method == ODX_METH_DDE) {
-          const int last = hstep > ((tnext - t) - o->hmin);     /* this step lands on tnext: keep aux / rates */
+          /* this step lands on tnext: keep aux / rates (always when a STOPIF may end the interval at any step) */
+          const int last = mi->has_stopif || hstep > ((tnext - t) - o->hmin);
           status = (o->method == ODX_METH_FE) ? odx_fe_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last)
                                               : odx_dde_apply(h, &t, tnext, &hstep, o->hmin, o->h0, last);
         } else {
           status = odx_evolve_apply(h, o->method, &t, tnext, &hstep);
+        }
+        if (mi->has_stopif && status == ODX_SUCCESS) {            /* EVENT_TYPE = STOP_COND from inside the RHS (:453-459) */
+          int raised = 0;
+          if ((status = odx_stop_flag(h, &raised)) == ODX_SUCCESS && raised) {
+            stop_flag = ODX_STOP_COND; steps++; particle_steps += (double)n_step;
+            break;
+          }
         }
         if (status != ODX_SUCCESS) { stop_flag = ODX_EVENT_GSL; break; }
         steps++; particle_steps += (double)n_step;
@@ -225,6 +243,14 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
       memset(event, 0, sizeof event);
       odx_evolve_reset(h);                                         /* gsl step / evolve re-allocated: count = 0 */
     }
+    if (stop_flag & (ODX_STOP_COND | ODX_STOP_TSPAN)) {            /* reset the dynamical variables (:704-714) */
+      if ((status = odx_pop_reinit(h, t, o->replay_ic)) != 0) break;
+      if ((status = odx_rhs(h, t)) != 0) break;
+      if ((status = odx_meanfields(h, os.mfd)) != 0) break;
+      if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) break;
+    }
+    if (stop_flag & ODX_STOP_TSPAN) nextstop = (idx_stop < nstops) ? tstops[idx_stop++] : INFINITY;
+    if (mi->has_stopif) odx_stop_flag(h, NULL);                     /* EVENT_TYPE = EVENT_NONE */
     stop_flag = ODX_EVENT_NONE;
   }
   if (status == ODX_SUCCESS) status = odx_sync(h);
@@ -232,6 +258,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
 done:
   if (os.fstats) fclose(os.fstats);
   if (os.ftraj) fclose(os.ftraj);
+  free(tstops);
   free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids); free(rows);
   if (rep) {
     rep->total_ms = now_ms() - t_start; rep->solver_ms = tot_solver; rep->steps = steps; rep->particle_steps = particle_steps;

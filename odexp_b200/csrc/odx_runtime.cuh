@@ -63,7 +63,8 @@ struct odx_handle {
   double *d_mu = nullptr;
   double h_mu[A1(NPAR)];
   double *partial = nullptr; unsigned int *counter = nullptr; double *sums = nullptr; unsigned long long *rmax = nullptr;
-  double *h_pin = nullptr;                 /* pinned scratch: NSLOT*NRED doubles + 8 */
+  double *h_pin = nullptr;                 /* pinned scratch: NSLOT*NRED doubles + 16 */
+  uint32_t reinit_index = 0;               /* resets at stopping times so far (Philox stream of the re-drawn ICs) */
   double *stage_dev = nullptr; size_t stage_bytes = 0;   /* AoS staging for upload / download */
   double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
   double *pair_part = nullptr; size_t pair_part_len = 0;                             /* [segment][npsi][cap] raw partial sums of k_pair */
@@ -113,6 +114,7 @@ static inline Pop pop_view(const odx_handle *h) {
   Pop p;
   p.Y = h->Y; p.YS = h->YS; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
   p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
+  p.stop = reinterpret_cast<int *>(h->counter + 8);
   return p;
 }
 static inline Red red_view(const odx_handle *h, int slot) {
@@ -932,7 +934,7 @@ int odx_pop_init(odx_handle *h, int64_t n, double t, uint32_t seed, int replay) 
     HostRand &hr = h->hr; hr.seed(seed); h->hr_seeded = true;
     for (int64_t i = 0; i < n; i++) {
       HostCtx c; memset(&c, 0, sizeof c);
-      c.mu = h->h_mu; c.pop_size = (double)n; c.h = 0.0; c.hr = &hr; c.id = (int32_t)i; c.oid = (int32_t)i; c.atbirth = 1;
+      c.mu = h->h_mu; c.pop_size = (double)n; c.h = 0.0; c.hr = &hr; c.id = (int32_t)i; c.oid = (int32_t)i; c.atbirth = 1; c.ist0 = 1;
       double yy[A1(NVAR)], ee[A1(NEXPR)];
       for (int v = 0; v < A1(NVAR); v++) yy[v] = 0.0;
       for (int v = 0; v < A1(NEXPR); v++) ee[v] = 0.0;
@@ -953,6 +955,60 @@ int odx_pop_init(odx_handle *h, int64_t n, double t, uint32_t seed, int replay) 
     ODX_TRY(launch_check(h));
   }
   invalidate_state(h);
+  return ODX_SUCCESS;
+}
+
+int odx_pop_reinit(odx_handle *h, double t, int replay) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  const int64_t n = h->n;
+  if (replay) {
+    /* pop_init_conditions over the list in order, drawing from the running serial stream; ids, aux, psi and rates stay */
+    if (h->nranks > 1) { h->err = "replayed initial conditions are single-GPU (serial stream)"; return ODX_EUNSUP; }
+    if (!h->hr_seeded) { h->hr.seed(3141592u); h->hr_seeded = true; }
+    std::vector<double> y((size_t)A1(NVAR) * n), e((size_t)A1(NEXPR) * n);
+    std::vector<int32_t> ids((size_t)n + 1);
+    ODX_TRY(download_cols(h, h->Y, y.data(), NVAR, n, 0));
+    ODX_TRY(download_cols(h, h->E, e.data(), NEXPR, n, 0));
+    if (n) ODX_CUDA(h, cudaMemcpyAsync(ids.data(), h->ID, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < n; i++) {
+      HostCtx c; memset(&c, 0, sizeof c);
+      c.mu = h->h_mu; c.pop_size = h->n_global; c.h = 0.0; c.hr = &h->hr; c.id = ids[i]; c.oid = ids[i];
+      double yy[A1(NVAR)], ee[A1(NEXPR)];
+      for (int v = 0; v < A1(NVAR); v++) yy[v] = v < NVAR ? y[(size_t)i * NVAR + v] : 0.0;
+      for (int v = 0; v < A1(NEXPR); v++) ee[v] = v < NEXPR ? e[(size_t)i * NEXPR + v] : 0.0;
+      OdxModel::ic(c, t, yy, ee);
+      for (int v = 0; v < NVAR; v++) y[(size_t)i * NVAR + v] = yy[v];
+      for (int v = 0; v < NEXPR; v++) e[(size_t)i * NEXPR + v] = ee[v];
+    }
+    ODX_TRY(upload_cols(h, y.data(), h->Y, NVAR, n, 0));
+    ODX_TRY(upload_cols(h, e.data(), h->E, NEXPR, n, 0));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  } else if (n > 0) {
+    k_init<<<grid_for(h, n), BLOCK, 0, h->stream>>>(pop_view(h), 0, n, t, h->reinit_index, 0);
+    ODX_TRY(launch_check(h));
+  }
+  h->reinit_index++;
+  /* the reference does not re-allocate its gsl evolve object here, so the next embedded step still starts from the
+   * derivative left by the previous one (dydt_in <- dydt_out); keep that state, drop only the cached moments */
+  const bool k1 = h->k1_valid; const uint64_t count = h->ev_count;
+  invalidate_state(h);
+  h->k1_valid = k1; h->ev_count = count;
+  return ODX_SUCCESS;
+}
+
+int odx_stop_flag(odx_handle *h, int *raised) {
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  int *flag = reinterpret_cast<int *>(h->counter + 8);
+  int *pin = reinterpret_cast<int *>(h->h_pin + NSLOT * NRED + 8);
+  if (h->nranks > 1) {
+    ncclResult_t r = g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce(MAX): ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+  }
+  ODX_CUDA(h, cudaMemcpyAsync(pin, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (raised) *raised = *pin;
   return ODX_SUCCESS;
 }
 

@@ -277,6 +277,9 @@ class Emitter:
         for b, en, args in list(_find_call(e, "BR"))[::-1]:
             if len(args) == 2:
                 e = e[:b] + "(odx_c.atbirth ? (%s) : (%s))" % (args[0], args[1]) + e[en:]
+        for b, en, args in list(_find_call(e, "IST0"))[::-1]:     # IST0(at t0, afterwards), src/odexp.h:369
+            if len(args) == 2:
+                e = e[:b] + "(odx_c.ist0 ? (%s) : (%s))" % (args[0], args[1]) + e[en:]
         for b, en, args in list(_find_call(e, "STOPIF"))[::-1]:
             e = e[:b] + "odx_stopif(odx_c, (%s))" % args[0] + e[en:]
         if self.fast_pow and not exact:
@@ -328,6 +331,7 @@ class Emitter:
         terms_use_aux = self.uses(term_exprs, r"\bMA\(")
         cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
         rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
+        has_stopif = self.uses(rhs_exprs, r"\bSTOPIF\s*\(")
         # the particle id column is only read by the stage kernels when something can observe it
         needs_id = rhs_rng or self.uses(rhs_exprs + term_exprs + cpl_exprs, r"\b(ID|OID|MID|rand01|randN|exprand|poisson|DWDT)\b")
         L = []
@@ -349,6 +353,7 @@ class Emitter:
           (m.nvar, m.nexpr, m.naux, m.npsi, m.nmfd, m.npar))
         w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
+        w("  static constexpr bool HAS_STOPIF = %s;" % ("true" if has_stopif else "false"))
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %
           tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr, needs_id)))
         w("")
@@ -466,7 +471,7 @@ class Emitter:
         vals = ", ".join(repr(float(p.rhs)) for p in m.pars) or "0.0"
         w("    static const double pd[] = {%s};" % vals)
         w('    static const odx_model_info mi = {"%s", NVAR, NEXPR, NAUX, NPSI, NMFD, NPAR, HAS_BIRTH, HAS_DEATH, HAS_REPLI, RHS_RNG,' % m.name)
-        w("                                      HAS_PAIR, HAS_LOWRANK, vn, en, an, pn, mn, qn, pd};")
+        w("                                      HAS_PAIR, HAS_LOWRANK, vn, en, an, pn, mn, qn, pd, HAS_STOPIF};")
         w("    return mi;")
         w("  }")
         w("};\n")

@@ -117,3 +117,47 @@ def test_iteration_method(model_lib):
     first = out["traj"]["step"] <= 5
     np.testing.assert_allclose(out["traj"]["cols"][first], ref["traj"]["cols"][first], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("meth,opts,ts,tol", [
+    ("dde", dict(h0=0.05, res=25, popsize=20), (0, 1.5, 3.25, 6), 1e-12),
+    ("rkck", dict(h0=0.1, res=13, popsize=7), (0, 0.5, 2.0, 2.1, 4), 1e-9),
+    ("fe", dict(h0=0.01, res=9, popsize=1000), (0, 2.5, 1.0, 4), 1e-11),          # unsorted stops
+])
+@pytest.mark.parametrize("replay", [True, False])
+def test_stopping_times_stopif_ist0(model_lib, meth, opts, ts, tol, replay):
+    """interior TIMESPAN values (STOP_TSPAN) and STOPIF (STOP_COND) cut the interval and re-initialise the living particles,
+    IST0 selects the afterwards arm (src/methods_odexp.c:222-236, 453-459, 704-720).  replay: the serial libc stream of the
+    reference; keyed: the same Philox draws in the restatement (rng_mode 1)."""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("reset_decay")
+    assert lib.info.has_stopif == 1
+    pop = capi.Population(lib, capacity=2048)
+    out = capi.odesolver(pop, ts, meth=meth, replay_ic=replay, **opts)
+    pop.close()
+    o = {"meth": meth, "h0": opts["h0"], "res": opts["res"], "ps": opts["popsize"]}
+    ref = port.run("reset_decay", o, ts, rng_mode=0 if replay else 1)
+    assert len(out["stats"]) == len(ref["stats"]) and len(out["traj"]) == len(ref["traj"])
+    np.testing.assert_array_equal(out["stats"]["stop_flag"], ref["stats"]["stop_flag"])
+    assert (ref["stats"]["stop_flag"] & 8).any() and (ref["stats"]["stop_flag"] & 4).any()
+    np.testing.assert_allclose(out["stats"]["t"], ref["stats"]["t"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=tol, atol=tol)
+    np.testing.assert_array_equal(out["traj"]["id"], ref["traj"]["id"])
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=tol, atol=tol)
+
+
+def test_stopping_time_keeps_evolve_state(model_lib):
+    """the reference does not re-allocate its gsl evolve object at a stopping time: the first embedded step after the reset
+    starts from the derivative of the state before the reset (dydt_in <- dydt_out); same here"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto")
+    pop = capi.Population(lib, capacity=256)
+    out = capi.odesolver(pop, (0, 0.7, 2.0), meth="rkf45", h0=0.1, res=6, popsize=30, replay_ic=True)
+    pop.close()
+    ref = port.run("kuramoto", {"meth": "rkf45", "h0": 0.1, "res": 6, "ps": 30}, (0, 0.7, 2.0))
+    assert len(out["stats"]) == len(ref["stats"]) and len(out["traj"]) == len(ref["traj"])
+    np.testing.assert_array_equal(out["stats"]["stop_flag"], ref["stats"]["stop_flag"])
+    np.testing.assert_allclose(out["stats"]["t"], ref["stats"]["t"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-9, atol=1e-9)

@@ -42,6 +42,10 @@ REF_CASES = [
     ("kuramoto_lowrank", {"meth": "rkck", "res": 3, "ps": 300}, (0, 1.0)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
+    # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
+    ("reset_decay", {"meth": "dde", "h0": 0.05, "res": 25, "ps": 20}, (0, 1.5, 3.25, 6)),
+    ("reset_decay", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 7}, (0, 0.5, 2.0, 2.1, 4)),
+    ("kuramoto", {"meth": "rkf45", "h0": 0.1, "res": 6, "ps": 30}, (0, 0.7, 2.0)),
 ]
 
 
@@ -60,6 +64,8 @@ def test_port_matches_reference_binary(model, opts, ts):
     np.testing.assert_array_equal(ta["step"], tb["step"])
     np.testing.assert_allclose(sa["t"], sb["t"], rtol=0, atol=1e-14)
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-13, atol=1e-15)
+    if model == "reset_decay":
+        assert (sa["stop_flag"] & 8).any() and (sa["stop_flag"] & 4).any(), "case must contain STOP_COND and STOP_TSPAN"
     if model == "vdp_sde":
         assert (sa["event"][:, 1] != 0).sum() > opts["ps"], "case must contain birth/death events"
 
