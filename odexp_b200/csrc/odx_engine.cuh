@@ -90,6 +90,8 @@ struct HostCtx {
 };
 
 /* device view of the population */
+constexpr int MUV_MAX = 48;                                   /* parameters carried by value in the kernel arguments */
+constexpr int MUV_N = (NPAR >= 1 && NPAR <= MUV_MAX) ? NPAR : 1;
 struct Pop {
   double *Y, *YS, *ACC, *E, *AUX, *PSI, *DEATH, *REPLI, *KS;
   int32_t *ID;
@@ -97,6 +99,7 @@ struct Pop {
   int64_t n;                /* particles on this GPU */
   double n_global;          /* POP_SIZE across all GPUs */
   const double *mu;
+  double muv[MUV_N];        /* the parameters by value: kernel-argument (constant bank) operands instead of a load per use */
   uint32_t k0, k1;          /* Philox key */
   int *stop;                /* sticky STOPIF flag of the whole population (models with STOPIF only) */
 };
@@ -187,7 +190,7 @@ __device__ __forceinline__ void load_mfd(const double *__restrict__ sums, double
 
 __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
   DevCtx c;
-  c.mu = p.mu; c.pop_size = p.n_global; c.h = h;
+  c.mu = (NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu; c.pop_size = p.n_global; c.h = h;
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
   c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   return c;
@@ -349,115 +352,225 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
   }
 }
 
-/* cp.async staging of the next iteration's columns (16 B per thread and column) into the thread's own shared-memory slots:
- * the loads of iteration k+1 are in flight while iteration k computes, without holding registers and without a CTA barrier
- * (every thread reads back only what it staged itself). */
-constexpr int PF_NCOL = 3 * NVAR + NEXPR + NPSI;                 /* y0, e, psi, ys, acc */
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+/* ------------------------------------------------------------------------------------------------
+ * TMA staging for the persistent kernel.  A CTA consumes one contiguous tile of 2 x 736 particles per iteration, i.e. one
+ * contiguous 11.5 KB run per column: one elected thread fetches the runs of the next tiles with cp.async.bulk (the TMA unit, no
+ * registers and no issue slots of the consumer warps) into a ring of shared-memory buffers, mbarrier complete_tx tells the
+ * consumers when a tile has landed, and a second mbarrier per buffer (one arrival per warp) tells the producer when every
+ * warp has copied its two particles out.  Compared with plain 128-bit loads this multiplies the bytes in flight per SM
+ * (ring depth x tile instead of what the stalled warps hold), which is what a latency-bound HBM stream needs.
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef PERSIST_TMA
+#define PERSIST_TMA 1
+#endif
+#ifndef PERSIST_THREADS_TMA
+#define PERSIST_THREADS_TMA 768    /* 23 consumer warps + 1 producer warp, 80 registers: measured best of 512 / 640 / 768 / 896 / 1024 */
+#endif
+#ifndef PERSIST_THREADS
+#define PERSIST_THREADS 1024       /* without the ring: 32 warps x 64 registers hide the load latency best */
+#endif
+#ifndef TMA_MAXBUF_N
+#define TMA_MAXBUF_N 8   /* <= 16 (state word of tma_produce) */
+#endif
+constexpr int TMA_MAXBUF = TMA_MAXBUF_N;
+constexpr int TMA_NCOL_MAX = 3 * NVAR + NEXPR + NPSI;                       /* y0, e, psi, ys, acc */
+constexpr size_t TMA_SMEM = 192 * 1024;
+/* the ring is used when at least two tiles of the widest stage fit */
+constexpr bool TMA_ON = PERSIST_TMA && ((size_t)TMA_NCOL_MAX * 2 * (PERSIST_THREADS_TMA - 32) * sizeof(double) * 2 <= TMA_SMEM);
+constexpr int PT_TMA = PERSIST_THREADS_TMA, PT_LD = PERSIST_THREADS;       /* CTA size of the two kernel variants */
+constexpr int TMA_CONS = PT_TMA - 32;                                      /* consumer threads (the last warp produces) */
+constexpr size_t TMA_COL_BYTES = (size_t)2 * TMA_CONS * sizeof(double);    /* one column of one tile */
+/* barrier over the NT computing threads of the CTA: all of it (NT = PT_LD), or all but the TMA producer warp, which never joins */
+template <int NT>
+__device__ __forceinline__ void cta_sync() {
+  if (NT != TMA_CONS) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+/* ring geometry of one stage: columns in ring order Y, E, PSI, [YS], [ACC] */
+__device__ __forceinline__ void tma_geometry(bool first, bool use_acc, int &ncol, uint32_t &tile_bytes, int &nbuf) {
+  ncol = NVAR + NEXPR + NPSI + (first ? 0 : NVAR) + (use_acc ? NVAR : 0);
+  tile_bytes = (uint32_t)ncol * (uint32_t)TMA_COL_BYTES;
+  nbuf = (int)(TMA_SMEM / tile_bytes);
+  if (nbuf > TMA_MAXBUF) nbuf = TMA_MAXBUF;
+}
+struct TmaRing {
+  unsigned char *buf;            /* TMA_SMEM bytes, 128-byte aligned */
+  uint32_t base;                 /* the same as a 32-bit shared-window address */
+  uint64_t *full, *empty;        /* [TMA_MAXBUF] each */
+  uint32_t full_par;             /* bit b: parity of the next phase of full[b] this thread will wait for */
+};
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+/* one thread waits */
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+/* a whole (converged) warp waits: the vote keeps the loop warp-uniform, so the compiler may go on using the uniform datapath
+ * (constant-bank coefficients in uniform registers) in the code that follows */
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+/* this thread's pair out of column c of a ring slot (slot = 32-bit shared address of the thread's pair in column 0) */
+template <int NC>
+__device__ __forceinline__ void unstage_cols(uint32_t slot, double (&o0)[A1(NC)], double (&o1)[A1(NC)]) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o0[c]), "=d"(o1[c]) : "r"(slot + (uint32_t)(c * TMA_COL_BYTES)) : "memory");
+  }
+}
 
-template <int NC>
-__device__ __forceinline__ void stage_cols(double2 *slot, int nthreads, const double *__restrict__ base, int64_t stride, int64_t i) {
-#pragma unroll
-  for (int c = 0; c < NC; c++) cp_async16(slot + (size_t)c * nthreads, base + (int64_t)c * stride + i);
+/* the producer lane of the TMA ring: fetches the column runs of every tile of one sweep, never more than nbuf tiles ahead of
+ * the slowest consumer warp.  Called from ONE place, the producer branch at the top of the persistent kernel: instantiated
+ * inside every stage sweep (or called out of line from there) it made ptxas park the sincos coefficient table on the stack of
+ * every consumer thread.
+ * state: bits 0-15 parity of the number of tiles issued into slot b, bits 16-31 slot b used at all. */
+__device__ __forceinline__ uint32_t tma_produce(const double *Y, const double *E, const double *PSI, const double *YS, const double *ACC,
+                                             int64_t stride, int64_t n, int64_t per_iter, int64_t cta_off, int niter, int reverse,
+                                             int nbuf, uint32_t tile_bytes, unsigned char *buf, uint64_t *full, uint64_t *empty,
+                                             uint32_t state) {
+  const int ncol = NVAR + NEXPR + NPSI + (YS ? NVAR : 0) + (ACC ? NVAR : 0);
+  int b = 0;
+  for (int k = 0; k < niter; k++) {
+    const int kk = reverse ? (niter - 1 - k) : k;
+    const int64_t start = (int64_t)kk * per_iter + cta_off;
+    int64_t cnt = n - start;
+    if (cnt > 2 * (int64_t)TMA_CONS) cnt = 2 * (int64_t)TMA_CONS;
+    if (cnt < 0) cnt = 0;
+    cnt = (cnt + 1) & ~(int64_t)1;                      /* whole pairs: the partner of a trailing single particle lies inside the
+                                                           (32-particle padded) column and is ignored by the consumer */
+    const uint32_t bytes = (uint32_t)(cnt * sizeof(double));
+    if ((state >> (16 + b)) & 1u) mbar_wait(empty + b, ((state >> b) & 1u) ^ 1u);
+    state |= 1u << (16 + b); state ^= 1u << b;
+    mbar_expect_tx(full + b, bytes * (uint32_t)ncol);
+    if (bytes) {
+      unsigned char *dst = buf + (size_t)b * tile_bytes;
+      for (int c = 0; c < NVAR; c++, dst += TMA_COL_BYTES) bulk_g2s(dst, Y + (int64_t)c * stride + start, bytes, full + b);
+      for (int c = 0; c < NEXPR; c++, dst += TMA_COL_BYTES) bulk_g2s(dst, E + (int64_t)c * stride + start, bytes, full + b);
+      for (int c = 0; c < NPSI; c++, dst += TMA_COL_BYTES) bulk_g2s(dst, PSI + (int64_t)c * stride + start, bytes, full + b);
+      if (YS) for (int c = 0; c < NVAR; c++, dst += TMA_COL_BYTES) bulk_g2s(dst, YS + (int64_t)c * stride + start, bytes, full + b);
+      if (ACC) for (int c = 0; c < NVAR; c++, dst += TMA_COL_BYTES) bulk_g2s(dst, ACC + (int64_t)c * stride + start, bytes, full + b);
+    }
+    if (++b == nbuf) b = 0;
+  }
+  return state;
 }
-template <int NC>
-__device__ __forceinline__ void unstage_cols(const double2 *slot, int nthreads, double (&o0)[A1(NC)], double (&o1)[A1(NC)]) {
+
+/* the arithmetic and the stores of one thread's pair of particles.  FULL: the pair lies inside the population (known per
+ * tile, so the tail predicates vanish from the hot path) */
+template <bool FIRST, bool LAST, bool FULL>
+__device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int64_t i, bool two_rt,
+                                           double (&y0)[2][A1(NVAR)], double (&yc)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)],
+                                           double (&psi)[2][A1(NPSI)], double (&acc)[2][A1(NVAR)], double (&red)[NRED]) {
+  const bool two = FULL ? true : two_rt;
+  double yn[2][A1(NVAR)], aux[2][A1(NAUX)];
+  double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
+  if (FIRST) {
 #pragma unroll
-  for (int c = 0; c < NC; c++) { const double2 v = slot[(size_t)c * nthreads]; o0[c] = v.x; o1[c] = v.y; }
+    for (int v = 0; v < NVAR; v++) { yc[0][v] = y0[0][v]; yc[1][v] = y0[1][v]; }
+  } else if (a.recon != 0.0) {
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) { acc[0][v] = (yc[0][v] - y0[0][v]) * a.recon; acc[1][v] = (yc[1][v] - y0[1][v]) * a.recon; }
+  }
+  int32_t id0 = 0, id1 = 0;
+  if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
+  double acco[2][A1(NVAR)], tm[2][NRED];
+  const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+  const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  if (s0 | s1) {          /* rare: an argument outside the fast sincos range -> library path for this pair */
+    chain_lane<FIRST, LAST, true>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    chain_lane<FIRST, LAST, true>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  }
+#pragma unroll
+  for (int k2 = 0; k2 < NRED; k2++) red[k2] += tm[0][k2] + (two ? tm[1][k2] : 0.0);
+  if (LAST) {
+    store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
+    if (a.want_out) {
+      store_cols2<NAUX>(p.AUX, p.stride, i, two, aux[0], aux[1]);
+      if (M::HAS_DEATH) { p.DEATH[i] = death[0]; if (two) p.DEATH[i + 1] = death[1]; }
+      if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
+    }
+  } else {
+    if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acco[0], acco[1]);
+    store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
+  }
 }
 
 /* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread).
- * PF: stage the input columns of the next iteration through shared memory with cp.async (sbuf = [2][PF_NCOL][blockDim] double2). */
-template <bool FIRST, bool LAST, bool PF>
+ * TMA: warp-specialised.  The last warp of the CTA is the producer (one lane issues the bulk copies and runs ahead as far as
+ * the ring allows); the other warps consume.  Its registers do not add to the consumers' live state. */
+template <bool FIRST, bool LAST, bool TMA>
 __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED],
-                                            double2 *sbuf = nullptr) {
+                                            TmaRing &ring) {
   /* the grid sweeps the columns as a moving window of gridDim.x tiles; alternate stages sweep in opposite directions so that
    * the tail of one stage (still resident in the 126 MB L2) is the head of the next */
-  const int64_t per_iter = 2 * (int64_t)gridDim.x * blockDim.x;
-  const int64_t niter = (p.n + per_iter - 1) / per_iter;
-  const int nt = blockDim.x;
-  const int64_t toff = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
-  auto issue = [&](int64_t k) {
-    const int64_t kk = a.reverse ? (niter - 1 - k) : k;
-    const int64_t i = kk * per_iter + toff;
-    if (i < p.n) {
-      double2 *slot = sbuf + (size_t)(k & 1) * PF_NCOL * nt + threadIdx.x;
-      stage_cols<NVAR>(slot, nt, p.Y, p.stride, i);
-      stage_cols<NEXPR>(slot + (size_t)NVAR * nt, nt, p.E, p.stride, i);
-      stage_cols<NPSI>(slot + (size_t)(NVAR + NEXPR) * nt, nt, p.PSI, p.stride, i);
-      if (!FIRST) {
-        stage_cols<NVAR>(slot + (size_t)(NVAR + NEXPR + NPSI) * nt, nt, p.YS, p.stride, i);
-        if (a.recon == 0.0) stage_cols<NVAR>(slot + (size_t)(2 * NVAR + NEXPR + NPSI) * nt, nt, p.ACC, p.stride, i);
-      }
-    }
-    cp_async_commit();
-  };
-  if (PF && niter > 0) issue(0);
-  for (int64_t k = 0; k < niter; k++) {
-    if (PF) {
-      if (k + 1 < niter) issue(k + 1); else cp_async_commit();
-      cp_async_wait<1>();
-    }
-    const int64_t kk = a.reverse ? (niter - 1 - k) : k;
-    const int64_t i = kk * per_iter + toff;
-    if (i >= p.n) continue;
+  const int ncons = TMA ? TMA_CONS : (int)blockDim.x;
+  const int64_t per_iter = 2 * (int64_t)gridDim.x * ncons;
+  const int niter = (int)((p.n + per_iter - 1) / per_iter);
+  const bool use_acc = !FIRST && a.recon == 0.0;
+  int ncol, nbuf; uint32_t tile_bytes;
+  tma_geometry(FIRST, use_acc, ncol, tile_bytes, nbuf);
+  const int64_t toff = 2 * ((int64_t)blockIdx.x * ncons + threadIdx.x);
+  int bcur = 0;
+  for (int k = 0; k < niter; k++) {
+    const int kk = a.reverse ? (niter - 1 - k) : k;
+    const int64_t i = (int64_t)kk * per_iter + toff;
     const bool two = (i + 1 < p.n);
-    double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)], yn[2][A1(NVAR)], aux[2][A1(NAUX)];
-    double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
-    if (PF) {
-      const double2 *slot = sbuf + (size_t)(k & 1) * PF_NCOL * nt + threadIdx.x;
-      unstage_cols<NVAR>(slot, nt, y0[0], y0[1]);
-      unstage_cols<NEXPR>(slot + (size_t)NVAR * nt, nt, e[0], e[1]);
-      if (NPSI > 0) unstage_cols<NPSI>(slot + (size_t)(NVAR + NEXPR) * nt, nt, psi[0], psi[1]);
+    double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)];
+    if (TMA) {
+      mbar_wait_warp(ring.full + bcur, (ring.full_par >> bcur) & 1u);
+      ring.full_par ^= 1u << bcur;
+      const uint32_t slot = ring.base + (uint32_t)bcur * tile_bytes + threadIdx.x * (uint32_t)sizeof(double2);
+      unstage_cols<NVAR>(slot, y0[0], y0[1]);
+      unstage_cols<NEXPR>(slot + (uint32_t)(NVAR * TMA_COL_BYTES), e[0], e[1]);
+      if (NPSI > 0) unstage_cols<NPSI>(slot + (uint32_t)((NVAR + NEXPR) * TMA_COL_BYTES), psi[0], psi[1]);
       if (!FIRST) {
-        unstage_cols<NVAR>(slot + (size_t)(NVAR + NEXPR + NPSI) * nt, nt, yc[0], yc[1]);
-        if (a.recon == 0.0) unstage_cols<NVAR>(slot + (size_t)(2 * NVAR + NEXPR + NPSI) * nt, nt, acc[0], acc[1]);
+        unstage_cols<NVAR>(slot + (uint32_t)((NVAR + NEXPR + NPSI) * TMA_COL_BYTES), yc[0], yc[1]);
+        if (use_acc) unstage_cols<NVAR>(slot + (uint32_t)((2 * NVAR + NEXPR + NPSI) * TMA_COL_BYTES), acc[0], acc[1]);
       }
+      /* the slot is refilled through the async proxy: order this thread's generic-proxy reads of it before the release below
+       * (without this fence a refill was observed to overtake the reads once in a few 10^5 tiles) */
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(ring.empty + bcur);
+      if (++bcur == nbuf) bcur = 0;
     } else {
+      if (i >= p.n) continue;
       load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
       load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
       if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
       if (!FIRST) {
         load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
-        if (a.recon == 0.0) load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+        if (use_acc) load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
       }
     }
-    if (FIRST) {
-#pragma unroll
-      for (int v = 0; v < NVAR; v++) { yc[0][v] = y0[0][v]; yc[1][v] = y0[1][v]; }
-    } else if (a.recon != 0.0) {
-#pragma unroll
-      for (int v = 0; v < NVAR; v++) { acc[0][v] = (yc[0][v] - y0[0][v]) * a.recon; acc[1][v] = (yc[1][v] - y0[1][v]) * a.recon; }
-    }
-    int32_t id0 = 0, id1 = 0;
-    if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
-    double acco[2][A1(NVAR)], tm[2][NRED];
-    const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-    const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
-    if (s0 | s1) {          /* rare: an argument outside the fast sincos range -> library path for this pair */
-      chain_lane<FIRST, LAST, true>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-      chain_lane<FIRST, LAST, true>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
-    }
-#pragma unroll
-    for (int k = 0; k < NRED; k++) red[k] += tm[0][k] + (two ? tm[1][k] : 0.0);
-    if (LAST) {
-      store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
-      if (a.want_out) {
-        store_cols2<NAUX>(p.AUX, p.stride, i, two, aux[0], aux[1]);
-        if (M::HAS_DEATH) { p.DEATH[i] = death[0]; if (two) p.DEATH[i + 1] = death[1]; }
-        if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
-      }
-    } else {
-      if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acco[0], acco[1]);
-      store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
-    }
+    const bool full_tile = TMA && ((int64_t)kk * per_iter + 2 * (int64_t)(blockIdx.x + 1) * ncons <= p.n);   /* CTA-uniform */
+    if (full_tile) chain_pair<FIRST, LAST, true>(p, a, mfd, i, true, y0, yc, e, psi, acc, red);
+    else if (i < p.n) chain_pair<FIRST, LAST, false>(p, a, mfd, i, two, y0, yc, e, psi, acc, red);
   }
-  if (PF) cp_async_wait<0>();
+  /* the next stage fetches what this one stored through the async proxy (TMA), which reads L2 directly: the stores must have
+   * reached gpu scope (a CTA-scope release could leave them in flight between the SM and L2), then cross the proxy boundary */
+  if (TMA) {
+    __threadfence();
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+  }
 }
 
 template <bool FIRST, bool LAST>
@@ -467,7 +580,8 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
   load_mfd(a.sums_in, p.n_global, mfd);
-  chain_sweep<FIRST, LAST, false>(p, a, mfd, red);
+  TmaRing none{};
+  chain_sweep<FIRST, LAST, false>(p, a, mfd, red, none);
   if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
 }
 
@@ -567,62 +681,93 @@ template <int NT>
 __device__ __forceinline__ void block_partial_smem(const double (&red)[NRED], double *s_bp) {
   __shared__ double s_part4[NT / 32][NRED];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
+  cta_sync<NT>();
 #pragma unroll
   for (int k = 0; k < NRED; k++) {
     const double v = warp_sum(red[k]);
     if (lane == 0) s_part4[warp][k] = v;
   }
-  __syncthreads();
+  cta_sync<NT>();
   if (threadIdx.x < NRED) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) v += s_part4[w][threadIdx.x];
     s_bp[threadIdx.x] = v;
   }
-  __syncthreads();
+  cta_sync<NT>();
 }
 /* fixed-order block sum of per-thread accumulators into s_tot[NRED] */
 template <int NT>
 __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s_tot) {
   __shared__ double s_part3[NT / 32][NRED];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
+  cta_sync<NT>();
 #pragma unroll
   for (int k = 0; k < NRED; k++) {
     const double v = warp_sum(acc[k]);
     if (lane == 0) s_part3[warp][k] = v;
   }
-  __syncthreads();
+  cta_sync<NT>();
   if (threadIdx.x < NRED) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; w++) v += s_part3[w][threadIdx.x];
     s_tot[threadIdx.x] = v;
   }
-  __syncthreads();
+  cta_sync<NT>();
 }
 constexpr int PERSIST_MAX_CTAS = 256;
 #ifndef PEER_POLL_ALL
 #define PEER_POLL_ALL 1
 #endif
-#ifndef PERSIST_THREADS
-#define PERSIST_THREADS 1024
-#endif
-constexpr int PT = PERSIST_THREADS;
-#ifndef PERSIST_PREFETCH
-#define PERSIST_PREFETCH 0   /* measured on B200: cp.async staging is 14% SLOWER than direct 128-bit loads here (0.507 vs 0.443 ms/step at N=2^24) */
-#endif
-constexpr size_t PF_BYTES = (size_t)2 * PF_NCOL * PT * sizeof(double2);
-constexpr bool PF_ON = PERSIST_PREFETCH && (PF_BYTES <= 160 * 1024);
-__global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_persist(Pop p, PersistArgs g) {
+constexpr size_t PF_BYTES = TMA_SMEM + 128;
+/* PF_ON: the TMA-ring variant (768 threads, HBM-resident populations); otherwise plain 128-bit loads (1024 threads), which is
+ * faster while the working set sits in L2 (measured crossover: 5-6 M Kuramoto particles per GPU) */
+template <bool PF_ON>
+__global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, (PF_ON || 1024 / PT_LD < 1) ? 1 : 1024 / PT_LD) k_chain_persist(Pop p, PersistArgs g) {
   __shared__ double s_tot[NRED], s_bp[NRED];
   __shared__ uint32_t s_words[PERSIST_MAX_CTAS * LLW];
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  double2 *sbuf = reinterpret_cast<double2 *>(s_dyn);
+  __shared__ __align__(8) uint64_t s_full[TMA_MAXBUF], s_empty[TMA_MAXBUF], s_go;
+  constexpr int NTC = PF_ON ? TMA_CONS : PT_LD;    /* threads that compute (all but the producer warp) */
+  TmaRing ring_;
+  ring_.buf = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);
+  ring_.base = smem_u32(ring_.buf); ring_.full = s_full; ring_.empty = s_empty; ring_.full_par = 0;
+  if (PF_ON && threadIdx.x == 0) {
+    for (int b = 0; b < TMA_MAXBUF; b++) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, TMA_CONS / 32); }
+    mbar_init(&s_go, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   double mfd[A1(NMFD)];
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
   __syncthreads();
+  /* role by warp index, broadcast from lane 0 so that the compiler knows the branch is warp-uniform */
+  const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (PF_ON && warp_id >= NTC / 32) {
+    /* ---- producer warp: walks the same (step, stage) sequence as the consumers and keeps the ring full.  A stage may only be
+     * fetched once this CTA's consumers have stored the previous one (same CTA, same particle ranges in every stage): s_go. */
+    if (threadIdx.x == NTC) {
+      const int64_t per_iter = 2 * (int64_t)gridDim.x * TMA_CONS;
+      const int niter = (int)((p.n + per_iter - 1) / per_iter);
+      uint32_t state = 0, go_par = 0, ep = g.epoch0;
+      for (long long step = 0; step < g.nsteps; step++) {
+        for (int s = 0; s < g.nst; s++) {
+          const bool first = (s == 0);
+          const bool use_acc = !first && !(s == 1 && g.recon);
+          int ncol, nbuf; uint32_t tile_bytes;
+          tma_geometry(first, use_acc, ncol, tile_bytes, nbuf);
+          if (step != 0 || s != 0) { mbar_wait(&s_go, go_par); go_par ^= 1u; }
+          asm volatile("fence.proxy.async;" ::: "memory");
+
+          state = tma_produce(p.Y, p.E, p.PSI, first ? nullptr : p.YS, use_acc ? p.ACC : nullptr, p.stride, p.n, per_iter,
+                              2 * (int64_t)blockIdx.x * TMA_CONS, niter, (int)(ep & 1u), nbuf, tile_bytes, ring_.buf, s_full, s_empty, state);
+          ep++;
+        }
+      }
+    }
+    return;
+  }
   uint32_t epoch = g.epoch0;
   uint32_t eval = g.eval_index0;
   for (long long step = 0; step < g.nsteps; step++) {
@@ -632,7 +777,7 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       for (int k = 0; k < NMFD; k++) mfd[k] = s_tot[k] / p.n_global;
       const bool last_stage = (s == g.nst - 1);
       if (last_stage && step == g.nsteps - 1 && blockIdx.x == 0 && threadIdx.x < NRED) g.sums_report[threadIdx.x] = s_tot[threadIdx.x];
-      __syncthreads();
+      cta_sync<NTC>();
       ChainArgs a;
       a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2; a.reverse = (int)(epoch & 1u);
       a.recon = 0.0; a.skip_acc_store = 0; a.iterate = g.iterate;
@@ -642,19 +787,19 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       for (int k = 0; k < NRED; k++) red[k] = 0.0;
       if (g.nst == 1) {                                   /* Euler */
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
-        chain_sweep<true, true, PF_ON>(p, a, mfd, red, sbuf);
+        chain_sweep<true, true, PF_ON>(p, a, mfd, red, ring_);
       } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */
         a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0; a.skip_acc_store = g.recon ? 1 : 0;
-        chain_sweep<true, false, PF_ON>(p, a, mfd, red, sbuf);
+        chain_sweep<true, false, PF_ON>(p, a, mfd, red, ring_);
       } else if (s == 1) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0; a.recon = g.recon ? 1.0 / (g.h / 2.0) : 0.0;
-        chain_sweep<false, false, PF_ON>(p, a, mfd, red, sbuf);
+        chain_sweep<false, false, PF_ON>(p, a, mfd, red, ring_);
       } else if (s == 2) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h; a.a = g.h; a.w = 2.0;
-        chain_sweep<false, false, PF_ON>(p, a, mfd, red, sbuf);
+        chain_sweep<false, false, PF_ON>(p, a, mfd, red, ring_);
       } else {
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
-        chain_sweep<false, true, PF_ON>(p, a, mfd, red, sbuf);
+        chain_sweep<false, true, PF_ON>(p, a, mfd, red, ring_);
       }
       /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
        * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence
@@ -664,23 +809,24 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
       const size_t par = (size_t)(epoch & 1u);
       const uint32_t tag = epoch + 1u;
       unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
-      block_partial_smem<PT>(red, s_bp);
+      block_partial_smem<NTC>(red, s_bp);
+      if (PF_ON && threadIdx.x == 0) mbar_arrive(&s_go);     /* every consumer has stored (and fenced) this stage */
       if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
-      for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += PT) {
+      for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
         unsigned long long w; unsigned long long spins = 0;
         while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (++spins > (1ull << 28)) { if (g.abort_flag) *g.abort_flag = 1; break; } }
         s_words[idx] = (uint32_t)w;
       }
-      __syncthreads();
+      cta_sync<NTC>();
       {
         double acc[NRED];
 #pragma unroll
         for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-        for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += PT) {
+        for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += NTC) {
 #pragma unroll
           for (int k = 0; k < NRED; k++) acc[k] += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
         }
-        block_total<PT>(acc, s_tot);
+        block_total<NTC>(acc, s_tot);
       }
       if (g.nranks > 1) {
         /* cross-GPU: CTA 0 stores this rank's sums as LL words straight into every peer's mailbox over NVLink (8-byte
@@ -703,14 +849,14 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
             s_words[threadIdx.x] = (uint32_t)w;
           }
         }
-        __syncthreads();
+        cta_sync<NTC>();
         if (threadIdx.x < NRED) {
           double v = 0.0;
           for (int r = 0; r < g.nranks; r++)
             v += (r == g.rank) ? s_tot[threadIdx.x] : ll_unpack(s_words[r * LLW + 2 * threadIdx.x], s_words[r * LLW + 2 * threadIdx.x + 1]);
           s_bp[threadIdx.x] = v;
         }
-        __syncthreads();
+        cta_sync<NTC>();
         if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
 #else
         unsigned long long *gt = g.ll_gtot + par * LLW;
@@ -730,14 +876,14 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
               s_words[threadIdx.x] = (uint32_t)w;
             }
           }
-          __syncthreads();
+          cta_sync<NTC>();
           if (threadIdx.x < NRED) {
             double v = 0.0;
             for (int r = 0; r < g.nranks; r++)
               v += (r == g.rank) ? s_tot[threadIdx.x] : ll_unpack(s_words[r * LLW + 2 * threadIdx.x], s_words[r * LLW + 2 * threadIdx.x + 1]);
             s_bp[threadIdx.x] = v;
           }
-          __syncthreads();
+          cta_sync<NTC>();
           if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
           if (threadIdx.x < LLW) ll_store_gpu(gt + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
         } else {
@@ -746,11 +892,11 @@ __global__ void __launch_bounds__(PT, (1024 / PT > 0 ? 1024 / PT : 1)) k_chain_p
             while ((uint32_t)((w = ll_load_gpu(gt + threadIdx.x)) >> 32) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
             s_words[threadIdx.x] = (uint32_t)w;
           }
-          __syncthreads();
+          cta_sync<NTC>();
           if (threadIdx.x < NRED) s_tot[threadIdx.x] = ll_unpack(s_words[2 * threadIdx.x], s_words[2 * threadIdx.x + 1]);
         }
 #endif
-        __syncthreads();
+        cta_sync<NTC>();
       }
       epoch++;
     }

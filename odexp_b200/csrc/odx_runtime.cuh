@@ -83,6 +83,8 @@ struct odx_handle {
   /* persistent step kernel + peer-memory exchange */
   unsigned long long *ll_words = nullptr;     /* LL exchange words of the persistent kernel (zero-initialised) */
   int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
+  int coop_blocks_tma = 0, tma_mode = -1;     /* tma_mode: -1 choose by size, 0 never, 1 always (option "tma") */
+  double l2_bytes = 0.0;
   uint32_t epoch = 0;
   void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -115,6 +117,7 @@ static inline Pop pop_view(const odx_handle *h) {
   p.Y = h->Y; p.YS = h->YS; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
   p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
   p.stop = reinterpret_cast<int *>(h->counter + 8);
+  for (int k = 0; k < MUV_N; k++) p.muv[k] = (k < NPAR) ? h->h_mu[k] : 0.0;
   return p;
 }
 static inline Red red_view(const odx_handle *h, int slot) {
@@ -405,12 +408,17 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   g.ll_part = h->ll_words; g.ll_gtot = h->ll_words + (size_t)2 * PERSIST_MAX_CTAS * LLW;
   g.sums_new = h->sums + (size_t)new_slot * NRED; g.sums_report = h->sums + (size_t)SLOT_STAGE * NRED;
   fill_peer_args(h, g);
-  int64_t grid = (h->n + 2 * PT - 1) / (2 * PT);
-  if (grid > h->coop_blocks) grid = h->coop_blocks;
+  /* TMA-ring variant for populations that stream from HBM, plain loads while the working set is L2-resident */
+  const bool ring = TMA_ON && h->coop_blocks_tma > 0 &&
+                    (h->tma_mode == 1 || (h->tma_mode < 0 && (double)h->n * TMA_NCOL_MAX * sizeof(double) > 1.5 * h->l2_bytes));
+  const int pt = ring ? PT_TMA : PT_LD, per_cta = ring ? 2 * TMA_CONS : 2 * PT_LD;
+  int64_t grid = (h->n + per_cta - 1) / per_cta;
+  if (grid > (ring ? h->coop_blocks_tma : h->coop_blocks)) grid = ring ? h->coop_blocks_tma : h->coop_blocks;
   if (grid > PERSIST_MAX_CTAS) grid = PERSIST_MAX_CTAS;
   if (grid < 1) grid = 1;
   void *args[] = {(void *)&p, (void *)&g};
-  ODX_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_chain_persist, dim3((unsigned)grid), dim3(PT), args, PF_ON ? PF_BYTES : 0, h->stream));
+  ODX_CUDA(h, cudaLaunchCooperativeKernel(ring ? (const void *)k_chain_persist<TMA_ON> : (const void *)k_chain_persist<false>, dim3((unsigned)grid),
+                                          dim3(pt), args, ring ? PF_BYTES : 0, h->stream));
   h->launches++;
   h->epoch += (uint32_t)(nst * nsteps);
   h->eval_index += (uint32_t)(2 * nst * nsteps); h->rhs_evals += (uint64_t)nst * nsteps;
@@ -671,9 +679,15 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   {
     int coop = 0, occp = 0;
     ODX_CUDA(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    if (PF_ON) ODX_CUDA(h, cudaFuncSetAttribute(k_chain_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_BYTES));
-    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_chain_persist, PT, PF_ON ? PF_BYTES : 0));
+    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_chain_persist<false>, PT_LD, 0));
     h->coop_ok = coop && occp > 0; h->coop_blocks = h->sm_count * occp;
+    if (TMA_ON) {
+      int occt = 0;
+      ODX_CUDA(h, cudaFuncSetAttribute(k_chain_persist<TMA_ON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_BYTES));
+      ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occt, k_chain_persist<TMA_ON>, PT_TMA, PF_BYTES));
+      h->coop_blocks_tma = h->sm_count * occt;
+    }
+    h->l2_bytes = (double)prop.l2CacheSize;
   }
   ODX_TRY(alloc_cols(h, &h->Y, NVAR)); ODX_TRY(alloc_cols(h, &h->YS, NVAR)); ODX_TRY(alloc_cols(h, &h->ACC, NVAR));
   ODX_TRY(alloc_cols(h, &h->E, NEXPR)); ODX_TRY(alloc_cols(h, &h->AUX, NAUX)); ODX_TRY(alloc_cols(h, &h->PSI, NPSI));
@@ -738,6 +752,7 @@ int odx_sync(odx_handle *h) {
 
 int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
+  if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }
   if (strcmp(name, "lrabstol") == 0) { h->lr_abstol = value; return ODX_SUCCESS; }
