@@ -206,9 +206,10 @@ __device__ __forceinline__ void note_stop(const Pop &p, const DevCtx &c) {
 /* %M terms of one particle state.  Pass-1 semantics of the reference: when a %M expression reads an
  * auxiliary variable (MA), that value comes from ode_rhs evaluated with zeroed mean fields and the
  * previous psi (src/odexp:820-833). */
+constexpr bool USE_HINTS = (M::NHINT > 0) && !M::TERMS_USE_AUX;     /* stage-to-stage sincos increments (odx_sincos_inc) */
 template <bool EXACT>
 __device__ __forceinline__ void particle_terms_x(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
-                                                 const double (&psi)[A1(NPSI)], double (&tm)[NRED]) {
+                                                 const double (&psi)[A1(NPSI)], double (&tm)[NRED], const OdxHint *hint = nullptr) {
   double aux[A1(NAUX)];
   if (M::TERMS_USE_AUX) {
     double f[A1(NVAR)], mz[A1(NMFD)], d = 0.0, r = 0.0;
@@ -220,7 +221,8 @@ __device__ __forceinline__ void particle_terms_x(DevCtx &c, double t, const doub
   }
   double m[A1(NMFD)];
   if (NMFD > 0) {
-    M::template mfd_terms<EXACT>(c, t, y, e, aux, m);
+    if (USE_HINTS && hint != nullptr) M::template mfd_terms_inc<EXACT>(c, t, y, e, aux, m, *hint);
+    else M::template mfd_terms<EXACT>(c, t, y, e, aux, m);
 #pragma unroll
     for (int k = 0; k < NMFD; k++) tm[k] = m[k];
   }
@@ -301,7 +303,8 @@ __device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, cons
                                           double (&yn)[A1(NVAR)], double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
   double f[A1(NVAR)];
   DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
-  M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
+  OdxHint hint;
+  M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli, USE_HINTS ? &hint : nullptr);
   note_stop(p, c);
   int slow = c.slow;
 #pragma unroll
@@ -319,7 +322,7 @@ __device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, cons
   }
   if (NMFD > 0 || M::HAS_BIRTH) {
     DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
-    particle_terms_x<EXACT>(c2, a.t_next, yn, e, psi, tm);
+    particle_terms_x<EXACT>(c2, a.t_next, yn, e, psi, tm, USE_HINTS ? &hint : nullptr);
     slow |= c2.slow;
   }
   return slow;

@@ -289,8 +289,11 @@ class Emitter:
             e = _ternary_to_select_nested(e)
         return _mangle_expr(e)
 
-    def cse(self, e, cache, out):
-        """hoist sin(A) / cos(A) into one odx_sincos(A) per distinct argument (innermost calls first)"""
+    def cse(self, e, cache, out, record=None, hinted=None):
+        """hoist sin(A) / cos(A) into one odx_sincos(A) per distinct argument (innermost calls first).
+        record: {canonical argument: hint slot} -- after the sincos of such an argument, store (A, sin A, cos A) in *odx_h
+        (the RHS side of the stage-to-stage increment); hinted: the same map on the %M side, where sincos(A') is then formed
+        from the recorded triple and the small difference A' - A"""
         while True:
             found = None
             for fn in ("sin", "cos"):
@@ -307,9 +310,59 @@ class Emitter:
             if key not in cache:
                 cache[key] = len(cache)
                 k = cache[key]
-                out("    double odx_sn%d, odx_cs%d; odx_sincos<ODX_EXACT>(odx_c, %s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
+                canon = self.canon_arg(arg)
+                if hinted is not None and canon in hinted:
+                    j = hinted[canon]
+                    out("    double odx_sn%d, odx_cs%d; odx_sincos_inc<ODX_EXACT>(odx_c, %s, odx_h.a[%d], odx_h.s[%d], odx_h.c[%d], &odx_sn%d, &odx_cs%d);"
+                        % (k, k, arg, j, j, j, k, k))
+                else:
+                    out("    double odx_sn%d, odx_cs%d; odx_sincos<ODX_EXACT>(odx_c, %s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
+                    if record is not None and canon in record:
+                        j = record[canon]
+                        out("    if (odx_h) { odx_h->a[%d] = %s; odx_h->s[%d] = odx_sn%d; odx_h->c[%d] = odx_cs%d; }" % (j, arg, j, k, j, k))
             k = cache[key]
             e = e[:b] + ("odx_sn%d" % k if fn == "sin" else "odx_cs%d" % k) + e[en:]
+
+    def canon_arg(self, arg):
+        """canonical text of a sincos argument in terms of odx_y[] / odx_e[] only, or None when it reads anything else
+        (mean fields, auxiliaries, couplings, time, parameters, random numbers): only such arguments are functions of the
+        particle state alone, so that the %M side of a stage sees the RHS side's argument shifted by a small step"""
+        a = re.sub(r"\s+", "", arg)
+        for e in self.m.eqs:
+            a = re.sub(r"(?<![\w\]])%s(?![\w\[(])" % re.escape(mangle(e.name)), "odx_y[%d]" % self.var_idx[e.name], a)
+        for e in self.m.exprs:
+            if not e.length:
+                a = re.sub(r"(?<![\w\]])%s(?![\w\[(])" % re.escape(mangle(e.name)), "odx_e[%d]" % self.expr_base[e.name], a)
+        while True:
+            b = re.sub(r"\((odx_[ye]\[\d+\])\)", r"\1", a)
+            if b.startswith("(") and b.endswith(")"):
+                depth, ok = 0, True
+                for i, ch in enumerate(b):
+                    depth += ch == "("
+                    depth -= ch == ")"
+                    if depth == 0 and i < len(b) - 1:
+                        ok = False
+                        break
+                if ok:
+                    b = b[1:-1]
+            if b == a:
+                break
+            a = b
+        rest = re.sub(r"odx_[ye]\[\d+\]|\d+\.?\d*(?:[eE][-+]?\d+)?|[-+*/()]", "", a)
+        return a if rest == "" and "odx_y[" in a else None
+
+    def sincos_args(self, exprs, where):
+        """canonical sincos arguments the given expressions would hoist"""
+        seen, lines = {}, []
+        for x in exprs:
+            if x:
+                self.cse(self.tr(x, where), seen, lines.append)
+        out = set()
+        for ln in lines:
+            mm = re.search(r"odx_sincos<ODX_EXACT>\(odx_c, (.*), &odx_sn\d+, &odx_cs\d+\);", ln)
+            if mm and self.canon_arg(mm.group(1)):
+                out.add(self.canon_arg(mm.group(1)))
+        return out
 
     def uses(self, exprs, pat):
         return any(re.search(pat, x or "") for x in exprs)
@@ -348,12 +401,23 @@ class Emitter:
             body = _mangle_expr(_ternary_to_select(body))
             w("ODX_HD double %s(%s) { return %s; }" % (mangle(f.name), args, body))
         w("")
+        # sincos arguments shared by the RHS and the %M terms: candidates for the stage-to-stage increment
+        hint_slots = {}
+        if not terms_use_aux and not rhs_rng:
+            shared = self.sincos_args([e.rhs for e in m.auxs] + [e.rhs for e in m.eqs], "rhs") & \
+                     self.sincos_args([e.rhs for e in m.mfds], "%M")
+            hint_slots = {a: i for i, a in enumerate(sorted(shared))}
+        self.hint_slots = hint_slots
+        w("/* (argument, sin, cos) of the sincos arguments the RHS shares with the %M terms */")
+        w("#define ODX_NHINT %d" % len(hint_slots))
+        w("struct OdxHint { double a[%d], s[%d], c[%d]; };" % ((max(1, len(hint_slots)),) * 3))
         w("struct OdxModel {")
         w("  static constexpr int NVAR = %d, NEXPR = %d, NAUX = %d, NPSI = %d, NMFD = %d, NPAR = %d;" %
           (m.nvar, m.nexpr, m.naux, m.npsi, m.nmfd, m.npar))
         w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
         w("  static constexpr bool HAS_STOPIF = %s;" % ("true" if has_stopif else "false"))
+        w("  static constexpr int NHINT = ODX_NHINT;")
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %
           tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr, needs_id)))
         w("")
@@ -362,8 +426,9 @@ class Emitter:
         w("  /* ODX_EXACT = false: range-limited fast sincos, the context records when an argument was out of range and the engine")
         w("   * redoes the particle with ODX_EXACT = true (library sincos); keeps the hot code free of branches */")
         w("  template <bool ODX_EXACT, class C> ODX_HD static void rhs(C &odx_c, double t, const double *odx_y, const double *odx_e,")
-        w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli) {")
-        w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e;")
+        w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli,")
+        w("      OdxHint *odx_h = nullptr) {")
+        w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e; (void)odx_h;")
         for i, p in enumerate(m.pars):
             if not re.search(r"\b(init|impl)\b", p.attr, flags=re.I):
                 ctype = "double"
@@ -386,9 +451,9 @@ class Emitter:
             w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
         tc = {}
         for e in m.auxs:
-            w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w)))
+            w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots)))
         for e in m.eqs:
-            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w)))
+            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots)))
         for e in m.auxs:
             w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
         if m.death:
@@ -404,6 +469,15 @@ class Emitter:
         tc = {}
         for e in m.mfds:
             w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w)))
+        w("  }\n")
+        w("  /* the same terms for the state one stage after the one the RHS was evaluated at: sin / cos of an argument the RHS has")
+        w("   * already reduced come from its (argument, sin, cos) triple and the small difference (angle addition) */")
+        w("  template <bool ODX_EXACT, class C> ODX_HD static void mfd_terms_inc(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_aux, double *odx_m, const OdxHint &odx_h) {")
+        w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m; (void)odx_h;")
+        tc = {}
+        for e in m.mfds:
+            w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w, hinted=hint_slots)))
         w("  }\n")
         w("  template <bool ODX_EXACT, class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux) {")
