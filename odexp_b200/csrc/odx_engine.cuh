@@ -938,14 +938,29 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
  * CTA writes the raw partial sums of its (i-tile, j-segment); k_pair_finish adds the segments in ascending j order and
  * divides by POP_SIZE, so the result is deterministic and the j-segments of other GPUs (allgathered columns) are just
  * more segments.  Arithmetic is FP64 FMA on the CUDA cores. */
-constexpr int PAIR_THREADS = 128, PAIR_ITILE = 256, PAIR_TJ = 128;
+#ifndef PAIR_THREADS_N
+#define PAIR_THREADS_N 128
+#endif
+#ifndef PAIR_TJ_N
+#define PAIR_TJ_N 128
+#endif
+#ifndef PAIR_UNROLL_N
+#define PAIR_UNROLL_N 4
+#endif
+#ifndef PAIR_WAVES
+#define PAIR_WAVES 16      /* CTAs per resident slot: the tail of the last wave costs <= 1 / PAIR_WAVES of the launch */
+#endif
+constexpr int PAIR_THREADS = PAIR_THREADS_N, PAIR_ITILE = 2 * PAIR_THREADS_N, PAIR_TJ = PAIR_TJ_N, PAIR_UNROLL = PAIR_UNROLL_N;
 constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);
-template <bool EXACT>
-__device__ __forceinline__ int pair_rows(const Pop &p, const double *__restrict__ jy, const double *__restrict__ je,
-                                         const int32_t *__restrict__ jid, int64_t jstride, int64_t jbeg, int64_t jend, double t,
-                                         const double (&ya)[A1(NVAR)], const double (&ea)[A1(NEXPR)], const double (&yb)[A1(NVAR)],
-                                         const double (&eb)[A1(NEXPR)], int32_t ida, int32_t idb, double (&acca)[A1(NPSI)],
-                                         double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id) {
+/* Fast path + tile-local redo: the straight-line fast forms of the model code only signal when they cannot represent a term
+ * (range-limited sincos: the context's slow flag; odx_zmul: a non-finite sum); the thread then discards what this j-tile added
+ * to its sums and repeats the tile with the exact forms.  The self term of a 1/r^n kernel does this once per i-particle (1 tile
+ * in N / PAIR_TJ). */
+__device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict__ jy, const double *__restrict__ je,
+                                          const int32_t *__restrict__ jid, int64_t jstride, int64_t jbeg, int64_t jend, double t,
+                                          const double (&ya)[A1(NVAR)], const double (&ea)[A1(NEXPR)], const double (&yb)[A1(NVAR)],
+                                          const double (&eb)[A1(NEXPR)], int32_t ida, int32_t idb, double (&acca)[A1(NPSI)],
+                                          double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id) {
   double aux[A1(NAUX)];
 #pragma unroll
   for (int k = 0; k < A1(NPSI); k++) { acca[k] = 0.0; accb[k] = 0.0; }
@@ -964,7 +979,11 @@ __device__ __forceinline__ int pair_rows(const Pop &p, const double *__restrict_
       if (M::NEEDS_ID) s_id[jj] = jid[j0 + jj];
     }
     __syncthreads();
-#pragma unroll 2
+    double sava[A1(NPSI)], savb[A1(NPSI)];
+#pragma unroll
+    for (int k = 0; k < A1(NPSI); k++) { sava[k] = acca[k]; savb[k] = accb[k]; }
+    ca.slow = 0; cb.slow = 0;
+#pragma unroll PAIR_UNROLL
     for (int jj = 0; jj < tj; jj++) {
       double oy[A1(NVAR)], oe[A1(NEXPR)];
 #pragma unroll
@@ -974,11 +993,33 @@ __device__ __forceinline__ int pair_rows(const Pop &p, const double *__restrict_
         for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
       }
       if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
-      M::template cpl_terms<EXACT>(ca, t, ya, ea, aux, oy, oe, aux, acca);
-      M::template cpl_terms<EXACT>(cb, t, yb, eb, aux, oy, oe, aux, accb);
+      M::template cpl_terms<false>(ca, t, ya, ea, aux, oy, oe, aux, acca);
+      M::template cpl_terms<false>(cb, t, yb, eb, aux, oy, oe, aux, accb);
+    }
+    int redo = ca.slow | cb.slow;
+    if (M::CPL_POISON) {
+#pragma unroll
+      for (int k = 0; k < NPSI; k++)
+        redo |= ((__double2hiint(acca[k]) & 0x7ff00000) == 0x7ff00000) | ((__double2hiint(accb[k]) & 0x7ff00000) == 0x7ff00000);
+    }
+    if (redo) {
+#pragma unroll
+      for (int k = 0; k < A1(NPSI); k++) { acca[k] = sava[k]; accb[k] = savb[k]; }
+#pragma unroll 1
+      for (int jj = 0; jj < tj; jj++) {
+        double oy[A1(NVAR)], oe[A1(NEXPR)];
+#pragma unroll
+        for (int v = 0; v < NVAR; v++) oy[v] = s_col[v][jj];
+        if (M::CPL_USES_EXPR) {
+#pragma unroll
+          for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
+        }
+        if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
+        M::template cpl_terms<true>(ca, t, ya, ea, aux, oy, oe, aux, acca);
+        M::template cpl_terms<true>(cb, t, yb, eb, aux, oy, oe, aux, accb);
+      }
     }
   }
-  return ca.slow | cb.slow;
 }
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
                                                        const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
@@ -997,9 +1038,15 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__re
   load_cols<NVAR>(ysrc, p.stride, ja, ya); load_cols<NEXPR>(p.E, p.stride, ja, ea);
   load_cols<NVAR>(ysrc, p.stride, jb, yb); load_cols<NEXPR>(p.E, p.stride, jb, eb);
   const int32_t ida = M::NEEDS_ID ? p.ID[ja] : 0, idb = M::NEEDS_ID ? p.ID[jb] : 0;
-  const int slow = pair_rows<false>(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
-  if (__syncthreads_or(slow))        /* rare: a fast-path sincos argument out of range somewhere in this CTA */
-    pair_rows<true>(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
+  pair_rows(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
+  if (M::CPL_SCALED) {      /* factors that do not depend on the other particle, hoisted out of the sum by the emitter */
+    double aux[A1(NAUX)], sa[A1(NPSI)], sb[A1(NPSI)];
+    DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida), cb = make_ctx(p, 0.0, 0, DOM_RHS, idb);
+    M::template cpl_scale<true>(ca, t, ya, ea, aux, sa);
+    M::template cpl_scale<true>(cb, t, yb, eb, aux, sb);
+#pragma unroll
+    for (int k = 0; k < NPSI; k++) { acca[k] *= sa[k]; accb[k] *= sb[k]; }
+  }
   double *dst = part + (size_t)(seg_base + blockIdx.y) * A1(NPSI) * p.stride;
 #pragma unroll
   for (int k = 0; k < NPSI; k++) {

@@ -111,6 +111,42 @@ ODX_HD double odx_rsqrt(double x) {
 }
 ODX_HD double odx_rpow15(double x) { const double r = odx_rsqrt(x); return r * r * r; }
 
+/* x^(-3/2) for the guarded product below: one MUFU.RSQ64H seed y0 (>= 20 good bits), then x^(-3/2) = y0^3 (1 - e)^(-3/2) with
+ * e = 1 - x y0^2 expanded to second order (truncation 2.2 e^3 < 2e-18): 6 FP64 operations instead of the 7 of rsqrt(x)^3, no
+ * special-case branch.  x = 0, subnormal or huge gives NaN / inf / 0; every non-finite value sends the j-tile through the exact
+ * forms (see odx_zmul), which is why this form is only emitted as odx_zmul's third argument. */
+template <bool EXACT>
+ODX_HD double odx_rpow15_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  if (EXACT) return odx_rpow15(x);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double t = y0 * y0;
+  const double e = fma(-x, t, 1.0);
+  const double c = t * y0;
+  const double p = fma(e, 1.875, 1.5);
+  return fma(p, c * e, c);
+#else
+  return odx_rpow15(x);
+#endif
+}
+
+/* (a == b) ? 0.0 : (a - b) * r, emitted for that pattern inside %C terms (the per-component guard of a 1/r^n kernel).
+ * Fast path: for a finite r the product is already +-0 when a == b, so neither the FP64 compare nor the select is needed and
+ * the product fuses into the accumulation.  A non-finite r (the self term: r = 1/0) makes the product inf or NaN, which
+ * poisons the running sum it is added to: the pair kernel checks its sums after every j-tile, and on a non-finite sum
+ * restores the values from before the tile and repeats the tile with the exact form (OdxModel::CPL_POISON; once per
+ * i-particle for a self term; coincident or overflowing particles, where the reference itself produces inf / NaN, take the
+ * same route).  With a finite r, a = b = +-inf gives NaN instead of the reference's 0. */
+template <bool EXACT, class C>
+ODX_HD double odx_zmul(C &ctx, double a, double b, double r) {
+  (void)ctx;
+#if defined(__CUDA_ARCH__)
+  if (!EXACT) return (a - b) * r;
+#endif
+  return (a == b) ? 0.0 : (a - b) * r;
+}
+
 /* reciprocal emitted for `x / f(...)` (a pure call the compiler can share between terms) */
 ODX_HD double odx_rcp(double x) { return 1.0 / x; }
 

@@ -258,8 +258,15 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
   if (h->n <= 0) return ODX_SUCCESS;
   Pop p = pop_view(h);
   const int itiles = (int)((h->n + PAIR_ITILE - 1) / PAIR_ITILE);
-  /* enough CTAs to fill the GPU about 8 deep: split the j-range of every source segment */
-  int js = (8 * h->sm_count + itiles - 1) / itiles;
+  /* split the j-range of every source segment until the grid is PAIR_WAVES waves of resident CTAs deep: with ~1.5 waves (the
+   * first version at N = 2^17) the half-empty last wave idles a quarter of the GPU */
+  static int resident = 0;
+  if (!resident) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_pair, PAIR_THREADS, 0) != cudaSuccess || resident < 1) resident = 8;
+  }
+  int js = (PAIR_WAVES * resident * h->sm_count + itiles - 1) / itiles;
+  const int64_t jtiles = (h->n + PAIR_TJ - 1) / PAIR_TJ;
+  if (js > jtiles) js = (int)jtiles;
   if (js < 1) js = 1;
   if (js > 64) js = 64;
   const int nsrc = h->nranks > 1 ? h->nranks : 1;

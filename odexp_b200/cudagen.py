@@ -213,6 +213,116 @@ def _rpow_peephole(expr: str) -> str:
     return expr
 
 
+def _split_top(e: str, ops: str):
+    """split e at the depth-0 occurrences of the single-character binary operators in `ops`; returns (parts, seps).
+    A '+' / '-' counts as binary only when it follows an operand (not at the start, after another operator or inside a
+    floating-point exponent)."""
+    parts, seps, cur, depth = [], [], [], 0
+    prev = ""                                   # previous non-space character at any depth
+    for i, ch in enumerate(e):
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if depth == 0 and ch in ops:
+            binary = True
+            if ch in "+-":
+                if prev == "" or prev in "*/(,+-?:<>=!&|":
+                    binary = False
+                elif prev in "eE" and re.search(r"(\d\.?|\.\d+)[eE]$", "".join(cur).rstrip()) and not re.search(r"[A-Za-z_]\w*$", "".join(cur).rstrip()[:-1] or " "):
+                    binary = False
+            if binary:
+                parts.append("".join(cur)); seps.append(ch); cur = []
+                prev = ch
+                continue
+        cur.append(ch)
+        if not ch.isspace():
+            prev = ch
+    parts.append("".join(cur))
+    return parts, seps
+
+
+def _is_pure_product(e: str):
+    """factors of e when e is a depth-0 product `[-]f1 * f2 * ...` (no depth-0 '+', binary '-', '/', '?', comparison), else None"""
+    e = _strip_outer_parens(e)
+    depth = 0
+    for i, ch in enumerate(e):
+        depth += ch in "(["
+        depth -= ch in ")]"
+        if depth == 0 and ch in "?:<>=!&|/%":
+            return None
+    parts, seps = _split_top(e, "+-")
+    if len(parts) != 1:
+        return None
+    factors, _ = _split_top(e, "*")
+    factors = [f.strip() for f in factors]
+    if any(f == "" for f in factors):
+        return None
+    return factors
+
+
+_J_DEPENDENT = re.compile(r"odx_oy|odx_oe|odx_oaux|odx_c\.oid|odx_c\.(rand01|randN|exprand|poisson|dwdt)|odx_stopif|\b(sin|cos)\s*\(")
+
+
+def _hoist_invariant_factors(e: str):
+    """%C term `a(i) * b(i,j)`: the factors that do not read the other particle leave the O(N^2) sum,
+    psi_k(i) = a(i) * sum_j b(i,j) (one multiplication per particle instead of one per pair; the result differs from the
+    reference's term-by-term product by the rounding of the distributive law).  Returns (scale or None, variant)."""
+    factors = _is_pure_product(e)
+    if not factors or len(factors) < 2:
+        return None, e
+    inv = [f for f in factors if not _J_DEPENDENT.search(f)]
+    var = [f for f in factors if _J_DEPENDENT.search(f)]
+    if not inv or not var:
+        return None, e
+    return " * ".join("(%s)" % f for f in inv), " * ".join(var)
+
+
+def _norm(x: str) -> str:
+    x = re.sub(r"\s+", "", x)
+    while True:
+        y = _strip_outer_parens(x)
+        y = re.sub(r"\(\((odx_\w+\[\d+\])\)\)", r"(\1)", y)
+        y = re.sub(r"\((odx_\w+\[\d+\])\)", r"\1", y)
+        if y == x:
+            return x
+        x = y
+
+
+def _zmul_peephole(expr: str) -> str:
+    """odx_sel(A == B, 0.0, (A - B) * R) -> odx_zmul<ODX_EXACT>(odx_c, A, B, R).
+    For a finite R the guarded product equals (A - B) * R (it is +-0 when A == B), so the FP64 compare and the select leave
+    the hot path; R = inf / NaN (the self term of a 1/r^n kernel) is replaced by 0 on the integer pipe, and the rare case of a
+    non-finite R with A != B raises the context's slow flag: the engine redoes that tile with the exact form."""
+    pos = 0
+    while True:
+        calls = [c for c in _find_call(expr, "odx_sel", pos)]
+        if not calls:
+            return expr
+        b, en, args = calls[0]
+        done = False
+        if len(args) == 3 and args[1].strip() in ("0.0", "0", "0."):
+            cond = _strip_outer_parens(args[0])
+            cparts = re.split(r"==", cond)
+            factors = _is_pure_product(args[2])
+            if len(cparts) == 2 and factors and len(factors) >= 2 and not re.search(r"[<>!&|?]", cond):
+                A, B = _norm(cparts[0]), _norm(cparts[1])
+                for k, f in enumerate(factors):
+                    sub, seps = _split_top(_strip_outer_parens(f), "+-")
+                    if len(sub) == 2 and seps == ["-"] and _norm(sub[0]) == A and _norm(sub[1]) == B:
+                        rest = factors[:k] + factors[k + 1:]
+                        R = " * ".join(rest)
+                        if len(rest) == 1:
+                            R = re.sub(r"^odx_rpow15\s*\(", "odx_rpow15_fast<ODX_EXACT>(", rest[0].strip())
+                        rep = "odx_zmul<ODX_EXACT>(odx_c, %s, %s, %s)" % (cparts[0].strip(), cparts[1].strip(), R)
+                        expr = expr[:b] + rep + expr[en:]
+                        pos = b + len(rep)
+                        done = True
+                        break
+        if not done:
+            pos = b + len("odx_sel(")
+
+
 class Emitter:
     def __init__(self, m: PopModel, fast_pow: bool = True, fast_div: bool = True):
         self.m = m
@@ -253,7 +363,7 @@ class Emitter:
             return {"MA": "(odx_aux[%d])", "OA": "(odx_oaux[%d])", "SA": "(odx_c.has_sister ? odx_c.sis_aux[%d] : 0.0)"}[kind] % i
         raise PopError("unknown macro %s" % kind)
 
-    def tr(self, expr: str, where: str, exact: bool = False) -> str:
+    def tr(self, expr: str, where: str, exact: bool = False, zmul: bool = False) -> str:
         """translate one model expression to C++.  exact = True (initial conditions): no arithmetic peepholes, so that replayed
         initial conditions stay bit-identical to the reference's"""
         e = expr.strip().rstrip(";")
@@ -287,6 +397,8 @@ class Emitter:
         if self.fast_div and not exact:
             e = _rpow_peephole(_div_peephole(e))
             e = _ternary_to_select_nested(e)
+            if zmul:
+                e = _zmul_peephole(e)
         return _mangle_expr(e)
 
     def cse(self, e, cache, out, record=None, hinted=None):
@@ -490,8 +602,23 @@ class Emitter:
         w("      const double *odx_aux, const double *odx_oy, const double *odx_oe, const double *odx_oaux, double *odx_p) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_oy; (void)odx_oe; (void)odx_oaux; (void)odx_c; (void)odx_p;")
         tc = {}
+        scales = {}
         for c in pair_cpls:
-            w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.cse(self.tr(c.rhs, "%C " + c.name), tc, w)))
+            term = self.tr(c.rhs, "%C " + c.name, zmul=self.fast_div)
+            if self.fast_div:
+                scales[c.name], term = _hoist_invariant_factors(term)
+                term = _strip_outer_parens(term)
+            w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.cse(term, tc, w)))
+        w("  }\n")
+        w("  /* factors of the %C terms that do not depend on the other particle: psi_k(i) = scale_k(i) * sum_j term_k(i,j) */")
+        w("  static constexpr bool CPL_SCALED = %s;" % ("true" if any(scales.values()) else "false"))
+        w("  /* the fast %C terms signal an unrepresentable term by a non-finite sum (odx_zmul) */")
+        w("  static constexpr bool CPL_POISON = %s;" % ("true" if any("odx_zmul<" in ln for ln in L) else "false"))
+        w("  template <bool ODX_EXACT, class C> ODX_HD static void cpl_scale(C &odx_c, double t, const double *odx_y, const double *odx_e,")
+        w("      const double *odx_aux, double *odx_s) {")
+        w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_s;")
+        for c in pair_cpls:
+            w("    odx_s[%d] = %s;" % (self.psi_idx[c.name], scales.get(c.name) or "1.0"))
         w("  }\n")
         # ---- initial conditions
         w("  /* ode_init_conditions: EXPR in file order, then INIT in file order (draw order matters for replay) */")

@@ -53,7 +53,11 @@ def test_emit_translates_macros():
     assert "NVAR = 1, NEXPR = 1, NAUX = 2, NPSI = 0, NMFD = 3" in cu
     nb = cudagen.emit_cuda(popfile.parse_file(fixture_path("nbody")))
     # pow(x,1.5) -> x*sqrt(x) in the emitted helper function; inlined + 1/pow(x,1.5) -> rsqrt(x)^3 in the %C terms
-    assert "odx_pow15(" in nb and "odx_rpow15(" in nb and "odx_sel(" in nb
+    assert "odx_pow15(" in nb and "odx_sel(" in nb
+    # %C terms: guard + product -> odx_zmul, 1/pow(x,1.5) -> rsqrt-seeded x^(-3/2), particle-independent factors hoisted out of the sum
+    assert "odx_zmul<ODX_EXACT>(odx_c, " in nb and "odx_rpow15_fast<ODX_EXACT>(" in nb
+    assert "CPL_SCALED = true" in nb and "CPL_POISON = true" in nb and "odx_s[0] = (-G) * ((odx_c.mu[0]));" in nb
+    assert "CPL_SCALED = false" in cu and "CPL_POISON = false" in cu
     assert "pow(" not in nb.replace("odx_pow", "").replace("odx_rpow", "")
     sde = cudagen.emit_cuda(popfile.parse_file(fixture_path("vdp_sde")))
     assert "odx_c.dwdt()" in sde and "odx_c.atbirth" in sde and "HAS_BIRTH = true" in sde
