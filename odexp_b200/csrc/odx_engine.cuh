@@ -378,11 +378,18 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
 constexpr int TMA_MAXBUF = TMA_MAXBUF_N;
 constexpr int TMA_NCOL_MAX = 3 * NVAR + NEXPR + NPSI;                       /* y0, e, psi, ys, acc */
 constexpr size_t TMA_SMEM = 192 * 1024;
-/* the ring is used when at least two tiles of the widest stage fit */
-constexpr bool TMA_ON = PERSIST_TMA && ((size_t)TMA_NCOL_MAX * 2 * (PERSIST_THREADS_TMA - 32) * sizeof(double) * 2 <= TMA_SMEM);
 constexpr int PT_TMA = PERSIST_THREADS_TMA, PT_LD = PERSIST_THREADS;       /* CTA size of the two kernel variants */
 constexpr int TMA_CONS = PT_TMA - 32;                                      /* consumer threads (the last warp produces) */
-constexpr size_t TMA_COL_BYTES = (size_t)2 * TMA_CONS * sizeof(double);    /* one column of one tile */
+/* pairs of particles per consumer thread and ring tile: two when two tiles of the widest stage still fit (the per-tile work of a
+ * consumer -- barrier wait, slot release, index arithmetic, ~45 issue slots -- is then shared by four particles instead of two) */
+#ifndef TMA_PPT_MAX
+#define TMA_PPT_MAX 2
+#endif
+constexpr int TMA_PPT = (TMA_PPT_MAX >= 2 && (size_t)TMA_NCOL_MAX * 4 * TMA_CONS * sizeof(double) * 2 <= TMA_SMEM) ? 2 : 1;
+constexpr int TMA_TILE = 2 * TMA_PPT * TMA_CONS;                           /* particles per ring tile */
+constexpr size_t TMA_COL_BYTES = (size_t)TMA_TILE * sizeof(double);        /* one column of one tile */
+/* the ring is used when at least two tiles of the widest stage fit */
+constexpr bool TMA_ON = PERSIST_TMA && ((size_t)TMA_NCOL_MAX * TMA_COL_BYTES * 2 <= TMA_SMEM);
 /* barrier over the NT computing threads of the CTA: all of it (NT = PT_LD), or all but the TMA producer warp, which never joins */
 template <int NT>
 __device__ __forceinline__ void cta_sync() {
@@ -400,6 +407,7 @@ struct TmaRing {
   unsigned char *buf;            /* TMA_SMEM bytes, 128-byte aligned */
   uint32_t base;                 /* the same as a 32-bit shared-window address */
   uint64_t *full, *empty;        /* [TMA_MAXBUF] each */
+  uint32_t full_a, empty_a;      /* their 32-bit shared-window addresses (no generic-to-shared conversion per tile) */
   uint32_t full_par;             /* bit b: parity of the next phase of full[b] this thread will wait for */
 };
 __device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
@@ -409,23 +417,27 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { mbar_arrive_a(smem_u32(bar)); }
+__device__ __forceinline__ uint32_t mbar_try_wait_a(uint32_t bar_a, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+               : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
   return ok;
 }
 /* one thread waits */
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  const uint32_t a = smem_u32(bar);
+  while (!mbar_try_wait_a(a, parity)) {}
 }
 /* a whole (converged) warp waits: the vote keeps the loop warp-uniform, so the compiler may go on using the uniform datapath
- * (constant-bank coefficients in uniform registers) in the code that follows */
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
-  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
+ * (constant-bank coefficients in uniform registers) in the code that follows.  Address and parity are formed before the loop:
+ * a waiting warp issues three instructions per try, and every issue slot it takes is one the computing warps of its scheduler
+ * do not get. */
+__device__ __forceinline__ void mbar_wait_warp_a(uint32_t bar_a, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait_a(bar_a, parity))) {}
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -455,7 +467,7 @@ __device__ __forceinline__ uint32_t tma_produce(const double *Y, const double *E
     const int kk = reverse ? (niter - 1 - k) : k;
     const int64_t start = (int64_t)kk * per_iter + cta_off;
     int64_t cnt = n - start;
-    if (cnt > 2 * (int64_t)TMA_CONS) cnt = 2 * (int64_t)TMA_CONS;
+    if (cnt > (int64_t)TMA_TILE) cnt = (int64_t)TMA_TILE;
     if (cnt < 0) cnt = 0;
     cnt = (cnt + 1) & ~(int64_t)1;                      /* whole pairs: the partner of a trailing single particle lies inside the
                                                            (32-particle padded) column and is ignored by the consumer */
@@ -516,57 +528,69 @@ __device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, con
   }
 }
 
-/* one pass of a chain stage over this GPU's particles (grid-stride, two particles per thread).
+/* One pass over this GPU's particles, two particles per thread and load (128-bit accesses).  body(i, two, full, y0, e, psi, ys,
+ * acc) does the arithmetic and the stores of one pair; full (a compile-time tag) says that the pair lies inside the population.
+ * The grid sweeps the columns as a moving window of gridDim.x tiles; alternate stages sweep in opposite directions so that the
+ * tail of one stage (still resident in the 126 MB L2) is the head of the next.
  * TMA: warp-specialised.  The last warp of the CTA is the producer (one lane issues the bulk copies and runs ahead as far as
- * the ring allows); the other warps consume.  Its registers do not add to the consumers' live state. */
-template <bool FIRST, bool LAST, bool TMA>
-__device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED],
-                                            TmaRing &ring) {
-  /* the grid sweeps the columns as a moving window of gridDim.x tiles; alternate stages sweep in opposite directions so that
-   * the tail of one stage (still resident in the 126 MB L2) is the head of the next */
+ * the ring allows); the other warps consume TMA_PPT pairs per thread from every tile and release the slot as soon as the last
+ * pair has been copied out.  The producer's registers do not add to the consumers' live state. */
+struct FullTile { static constexpr bool value = true; };
+struct RaggedTile { static constexpr bool value = false; };
+template <bool TMA, class F>
+__device__ __forceinline__ void tile_sweep(const Pop &p, int reverse, bool has_ys, bool has_acc, TmaRing &ring, F &&body) {
+  constexpr int PPT = TMA ? TMA_PPT : 1;
   const int ncons = TMA ? TMA_CONS : (int)blockDim.x;
-  const int64_t per_iter = 2 * (int64_t)gridDim.x * ncons;
+  const int tile = 2 * PPT * ncons;                                   /* particles per CTA and iteration */
+  const int64_t per_iter = (int64_t)gridDim.x * tile;
   const int niter = (int)((p.n + per_iter - 1) / per_iter);
-  const bool use_acc = !FIRST && a.recon == 0.0;
+  /* iterations kk <= kfull find this CTA's whole tile inside the population (CTA-uniform) */
+  const int64_t need = (int64_t)tile * (blockIdx.x + 1);
+  const int kfull = (TMA && p.n >= need) ? (int)((p.n - need) / per_iter) : -1;
   int ncol, nbuf; uint32_t tile_bytes;
-  tma_geometry(FIRST, use_acc, ncol, tile_bytes, nbuf);
-  const int64_t toff = 2 * ((int64_t)blockIdx.x * ncons + threadIdx.x);
+  tma_geometry(!has_ys, has_acc, ncol, tile_bytes, nbuf);
+  const int64_t toff = (int64_t)tile * blockIdx.x + 2 * threadIdx.x;
   int bcur = 0;
   for (int k = 0; k < niter; k++) {
-    const int kk = a.reverse ? (niter - 1 - k) : k;
-    const int64_t i = (int64_t)kk * per_iter + toff;
-    const bool two = (i + 1 < p.n);
-    double y0[2][A1(NVAR)], yc[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)];
+    const int kk = reverse ? (niter - 1 - k) : k;
+    const int64_t i0 = (int64_t)kk * per_iter + toff;
+    uint32_t slot = 0;
     if (TMA) {
-      mbar_wait_warp(ring.full + bcur, (ring.full_par >> bcur) & 1u);
+      mbar_wait_warp_a(ring.full_a + 8u * bcur, (ring.full_par >> bcur) & 1u);
       ring.full_par ^= 1u << bcur;
-      const uint32_t slot = ring.base + (uint32_t)bcur * tile_bytes + threadIdx.x * (uint32_t)sizeof(double2);
-      unstage_cols<NVAR>(slot, y0[0], y0[1]);
-      unstage_cols<NEXPR>(slot + (uint32_t)(NVAR * TMA_COL_BYTES), e[0], e[1]);
-      if (NPSI > 0) unstage_cols<NPSI>(slot + (uint32_t)((NVAR + NEXPR) * TMA_COL_BYTES), psi[0], psi[1]);
-      if (!FIRST) {
-        unstage_cols<NVAR>(slot + (uint32_t)((NVAR + NEXPR + NPSI) * TMA_COL_BYTES), yc[0], yc[1]);
-        if (use_acc) unstage_cols<NVAR>(slot + (uint32_t)((2 * NVAR + NEXPR + NPSI) * TMA_COL_BYTES), acc[0], acc[1]);
-      }
-      /* the slot is refilled through the async proxy: order this thread's generic-proxy reads of it before the release below
-       * (without this fence a refill was observed to overtake the reads once in a few 10^5 tiles) */
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(ring.empty + bcur);
-      if (++bcur == nbuf) bcur = 0;
-    } else {
-      if (i >= p.n) continue;
-      load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
-      load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
-      if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
-      if (!FIRST) {
-        load_cols2<NVAR>(p.YS, p.stride, i, two, yc[0], yc[1]);
-        if (use_acc) load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
-      }
+      slot = ring.base + (uint32_t)bcur * tile_bytes + threadIdx.x * (uint32_t)sizeof(double2);
     }
-    const bool full_tile = TMA && ((int64_t)kk * per_iter + 2 * (int64_t)(blockIdx.x + 1) * ncons <= p.n);   /* CTA-uniform */
-    if (full_tile) chain_pair<FIRST, LAST, true>(p, a, mfd, i, true, y0, yc, e, psi, acc, red);
-    else if (i < p.n) chain_pair<FIRST, LAST, false>(p, a, mfd, i, two, y0, yc, e, psi, acc, red);
+#pragma unroll
+    for (int q = 0; q < PPT; q++) {
+      const int64_t i = i0 + 2 * q * ncons;
+      const bool two = (i + 1 < p.n);
+      double y0[2][A1(NVAR)], ys[2][A1(NVAR)], e[2][A1(NEXPR)], psi[2][A1(NPSI)], acc[2][A1(NVAR)];
+      if (TMA) {
+        const uint32_t sq = slot + (uint32_t)(q * TMA_CONS * sizeof(double2));
+        unstage_cols<NVAR>(sq, y0[0], y0[1]);
+        unstage_cols<NEXPR>(sq + (uint32_t)(NVAR * TMA_COL_BYTES), e[0], e[1]);
+        if (NPSI > 0) unstage_cols<NPSI>(sq + (uint32_t)((NVAR + NEXPR) * TMA_COL_BYTES), psi[0], psi[1]);
+        if (has_ys) unstage_cols<NVAR>(sq + (uint32_t)((NVAR + NEXPR + NPSI) * TMA_COL_BYTES), ys[0], ys[1]);
+        if (has_acc) unstage_cols<NVAR>(sq + (uint32_t)((2 * NVAR + NEXPR + NPSI) * TMA_COL_BYTES), acc[0], acc[1]);
+        if (q == PPT - 1) {
+          /* the slot is refilled through the async proxy: order this thread's generic-proxy reads of it before the release
+           * (without this fence a refill was observed to overtake the reads once in a few 10^5 tiles) */
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if ((threadIdx.x & 31) == 0) mbar_arrive_a(ring.empty_a + 8u * bcur);
+          if (++bcur == nbuf) bcur = 0;
+        }
+        if (kk <= kfull) { body(i, true, FullTile(), y0, e, psi, ys, acc); continue; }
+      } else {
+        if (i >= p.n) continue;
+        load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);
+        load_cols2<NEXPR>(p.E, p.stride, i, two, e[0], e[1]);
+        if (NPSI > 0) load_cols2<NPSI>(p.PSI, p.stride, i, two, psi[0], psi[1]);
+        if (has_ys) load_cols2<NVAR>(p.YS, p.stride, i, two, ys[0], ys[1]);
+        if (has_acc) load_cols2<NVAR>(p.ACC, p.stride, i, two, acc[0], acc[1]);
+      }
+      if (i < p.n) body(i, two, RaggedTile(), y0, e, psi, ys, acc);
+    }
   }
   /* the next stage fetches what this one stored through the async proxy (TMA), which reads L2 directly: the stores must have
    * reached gpu scope (a CTA-scope release could leave them in flight between the SM and L2), then cross the proxy boundary */
@@ -574,6 +598,134 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
     __threadfence();
     asm volatile("fence.proxy.async.global;" ::: "memory");
   }
+}
+
+/* one pass of a chain stage (stored scheme) */
+template <bool FIRST, bool LAST, bool TMA>
+__device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED],
+                                            TmaRing &ring) {
+  const bool use_acc = !FIRST && a.recon == 0.0;
+  tile_sweep<TMA>(p, a.reverse, !FIRST, use_acc, ring,
+                  [&](int64_t i, bool two, auto full, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)], double (&psi)[2][A1(NPSI)],
+                      double (&ys)[2][A1(NVAR)], double (&acc)[2][A1(NVAR)]) {
+                    chain_pair<FIRST, LAST, decltype(full)::value>(p, a, mfd, i, two, y0, ys, e, psi, acc, red);
+                  });
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Lean classic RK4 for HBM-resident mean-field populations (persistent TMA kernel only).
+ *
+ * The stored scheme above moves 152 B per particle-step for a one-variable model (stage states and the slope accumulator go
+ * to HBM and come back); the compulsory traffic with one mean-field barrier per stage is 72 B.  Here stages are recomputed or
+ * recovered instead of stored wherever that costs fewer FP64 instructions than the bytes cost time:
+ *   stage 1: read y0, e          k1 = f(y0; M0), y2 = y0 + h/2 k1                        -> sums of y2      (nothing stored)
+ *   stage 2: read y0, e          k1 again (M0 kept in shared memory), y2, k2 = f(y2; M1), y3 = y0 + h/2 k2  -> store y3 (YS)
+ *   stage 3: read y0, e, y3      k3 = f(y3; M2), y4 = y0 + h k3                                             -> store y4 (ACC)
+ *   stage 4: read y0, e, y3, y4  k1 again, k2 = (y3 - y0) / (h/2), k3 = (y4 - y0) / h (recovered: exact to <= 1 ulp of
+ *                                y0 / (a h), like `recon` above), k4 = f(y4; M3), y += h/6 (k1 + 2 k2 + 2 k3 + k4)  -> store y
+ * = 16 + 24 + 32 + 40 = 112 B per particle-step for nvar = nexpr = 1, six RHS evaluations instead of four.  The recomputed
+ * evaluations reuse the sincos triple of y0 through angle addition (rhs_inc), so a step costs ~245 FP64 instructions
+ * instead of ~200.  Requires: no %C columns (psi of earlier stages would have to be kept), no random numbers or STOPIF in the
+ * RHS.  While the population sits in L2 the stored scheme is faster (FP64-bound there) and stays in use.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr bool LEAN_OK = (NPSI == 0) && !M::RHS_RNG && !M::HAS_STOPIF && !M::HAS_PAIR && !M::HAS_LOWRANK;
+template <int LS, bool EXACT>
+__device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
+                                         int32_t id, const double (&y0)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+                                         const double (&y3)[A1(NVAR)], const double (&y4)[A1(NVAR)], double (&yout)[A1(NVAR)],
+                                         double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
+  double psi[A1(NPSI)], f[A1(NVAR)], f2[A1(NVAR)];
+#pragma unroll
+  for (int k = 0; k < A1(NPSI); k++) psi[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) tm[k] = 0.0;
+  const double t = a.t_eval, h = a.h, half = a.h / 2.0;
+  DevCtx c = make_ctx(p, h, a.eval_index, DOM_RHS, id);
+  OdxHint h0, h1;
+  OdxHint *hl = &h0;                    /* triple the %M terms of the new state are incremented from */
+  double t_next;
+  if (LS == 0) {
+    M::template rhs<EXACT>(c, t, y0, e, psi, mfd, f, aux, death, repli, USE_HINTS ? &h0 : nullptr);
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) yout[v] = y0[v] + half * f[v];
+    t_next = t + half;
+  } else if (LS == 1) {
+    double y2[A1(NVAR)];
+    M::template rhs<EXACT>(c, t, y0, e, psi, mfd0, f, aux, death, repli, USE_HINTS ? &h0 : nullptr);
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) y2[v] = y0[v] + half * f[v];
+    M::template rhs_inc<EXACT>(c, t + half, y2, e, psi, mfd, f2, aux, death, repli, h0, USE_HINTS ? &h1 : nullptr);
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) yout[v] = y0[v] + half * f2[v];
+    hl = &h1; t_next = t + half;
+  } else if (LS == 2) {
+    M::template rhs<EXACT>(c, t + half, y3, e, psi, mfd, f, aux, death, repli, USE_HINTS ? &h0 : nullptr);
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) yout[v] = y0[v] + h * f[v];
+    t_next = t + h;
+  } else {
+    M::template rhs<EXACT>(c, t, y0, e, psi, mfd0, f, aux, death, repli, USE_HINTS ? &h0 : nullptr);
+    M::template rhs_inc<EXACT>(c, t + h, y4, e, psi, mfd, f2, aux, death, repli, h0, USE_HINTS ? &h1 : nullptr);
+    const double r2 = 1.0 / half, r3 = 1.0 / h;
+#pragma unroll
+    for (int v = 0; v < NVAR; v++) {
+      double acc = f[v];                                  /* k1 + 2 k2 + 2 k3, then y += h/6 (acc + k4): the order of the stored scheme */
+      acc = acc + 2.0 * ((y3[v] - y0[v]) * r2);
+      acc = acc + 2.0 * ((y4[v] - y0[v]) * r3);
+      yout[v] = y0[v] + (h / 6.0) * (acc + f2[v]);
+    }
+    tm[RED_RATES] = death + repli;
+    hl = &h1; t_next = t + h;
+  }
+  int slow = c.slow;
+  if (NMFD > 0 || M::HAS_BIRTH) {
+    DevCtx c2 = make_ctx(p, h, a.eval_index + 1, DOM_RHS, id);
+    particle_terms_x<EXACT>(c2, t_next, yout, e, psi, tm, USE_HINTS ? hl : nullptr);
+    slow |= c2.slow;
+  }
+  return slow;
+}
+
+template <int LS, bool FULL>
+__device__ __forceinline__ void lean_pair(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
+                                          int64_t i, bool two_rt, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)],
+                                          double (&y3)[2][A1(NVAR)], double (&y4)[2][A1(NVAR)], double (&red)[NRED]) {
+  const bool two = FULL ? true : two_rt;
+  double yn[2][A1(NVAR)], aux[2][A1(NAUX)], tm[2][NRED];
+  double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
+  int32_t id0 = 0, id1 = 0;
+  if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
+  const int s0 = lean_lane<LS, false>(p, a, mfd0, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+  const int s1 = lean_lane<LS, false>(p, a, mfd0, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  if (s0 | s1) {          /* rare: a sincos argument outside the fast range, or a stage increment too large for angle addition */
+    lean_lane<LS, true>(p, a, mfd0, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    lean_lane<LS, true>(p, a, mfd0, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  }
+#pragma unroll
+  for (int k2 = 0; k2 < NRED; k2++) red[k2] += tm[0][k2] + (two ? tm[1][k2] : 0.0);
+  if (LS == 1) store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
+  if (LS == 2) store_cols2<NVAR>(p.ACC, p.stride, i, two, yn[0], yn[1]);
+  if (LS == 3) {
+    store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
+    if (a.want_out) {
+      store_cols2<NAUX>(p.AUX, p.stride, i, two, aux[0], aux[1]);
+      if (M::HAS_DEATH) { p.DEATH[i] = death[0]; if (two) p.DEATH[i + 1] = death[1]; }
+      if (M::HAS_REPLI) { p.REPLI[i] = repli[0]; if (two) p.REPLI[i + 1] = repli[1]; }
+    }
+  }
+}
+
+/* ring columns of lean stage LS: Y, E, [YS = y3], [ACC = y4] */
+__device__ __forceinline__ bool lean_has_ys(int ls) { return ls >= 2; }
+__device__ __forceinline__ bool lean_has_acc(int ls) { return ls == 3; }
+template <int LS, bool TMA>
+__device__ __forceinline__ void lean_sweep(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
+                                           double (&red)[NRED], TmaRing &ring) {
+  tile_sweep<TMA>(p, a.reverse, LS >= 2, LS == 3, ring,
+                  [&](int64_t i, bool two, auto full, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)], double (&psi)[2][A1(NPSI)],
+                      double (&y3)[2][A1(NVAR)], double (&y4)[2][A1(NVAR)]) {
+                    lean_pair<LS, decltype(full)::value>(p, a, mfd0, mfd, i, two, y0, e, y3, y4, red);
+                  });
 }
 
 template <bool FIRST, bool LAST>
@@ -602,6 +754,7 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
 constexpr int MAX_RANKS = 8;
 struct PersistArgs {
   int nst; long long nsteps; double t0, h; int want_out_last; uint32_t eval_index0; int recon; int iterate;
+  int lean;                        /* classic RK4 by the lean scheme (lean_sweep) */
   const double *sums_y;            /* global raw sums of the %M terms of Y at entry */
   double *partial;                 /* [2][grid][NRED] */
   unsigned int *bar;               /* [2][PERSIST_MAX_CTAS] epoch tags of the published block partials, then [2] global-sum flags */
@@ -736,13 +889,16 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, (PF_ON || 1024 / PT_LD
   TmaRing ring_;
   ring_.buf = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(s_dyn) + 127) & ~(uintptr_t)127);
   ring_.base = smem_u32(ring_.buf); ring_.full = s_full; ring_.empty = s_empty; ring_.full_par = 0;
+  ring_.full_a = smem_u32(s_full); ring_.empty_a = smem_u32(s_empty);
   if (PF_ON && threadIdx.x == 0) {
     for (int b = 0; b < TMA_MAXBUF; b++) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, TMA_CONS / 32); }
     mbar_init(&s_go, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  double mfd[A1(NMFD)];
+  double mfd[A1(NMFD)], mfd0[A1(NMFD)];
+#pragma unroll
+  for (int k = 0; k < A1(NMFD); k++) mfd0[k] = 0.0;
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
   __syncthreads();
   /* role by warp index, broadcast from lane 0 so that the compiler knows the branch is warp-uniform */
@@ -751,20 +907,20 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, (PF_ON || 1024 / PT_LD
     /* ---- producer warp: walks the same (step, stage) sequence as the consumers and keeps the ring full.  A stage may only be
      * fetched once this CTA's consumers have stored the previous one (same CTA, same particle ranges in every stage): s_go. */
     if (threadIdx.x == NTC) {
-      const int64_t per_iter = 2 * (int64_t)gridDim.x * TMA_CONS;
+      const int64_t per_iter = (int64_t)gridDim.x * TMA_TILE;
       const int niter = (int)((p.n + per_iter - 1) / per_iter);
       uint32_t state = 0, go_par = 0, ep = g.epoch0;
       for (long long step = 0; step < g.nsteps; step++) {
         for (int s = 0; s < g.nst; s++) {
-          const bool first = (s == 0);
-          const bool use_acc = !first && !(s == 1 && g.recon);
+          const bool first = g.lean ? !lean_has_ys(s) : (s == 0);
+          const bool use_acc = g.lean ? lean_has_acc(s) : (!first && !(s == 1 && g.recon));
           int ncol, nbuf; uint32_t tile_bytes;
           tma_geometry(first, use_acc, ncol, tile_bytes, nbuf);
           if (step != 0 || s != 0) { mbar_wait(&s_go, go_par); go_par ^= 1u; }
           asm volatile("fence.proxy.async;" ::: "memory");
 
           state = tma_produce(p.Y, p.E, p.PSI, first ? nullptr : p.YS, use_acc ? p.ACC : nullptr, p.stride, p.n, per_iter,
-                              2 * (int64_t)blockIdx.x * TMA_CONS, niter, (int)(ep & 1u), nbuf, tile_bytes, ring_.buf, s_full, s_empty, state);
+                              (int64_t)blockIdx.x * TMA_TILE, niter, (int)(ep & 1u), nbuf, tile_bytes, ring_.buf, s_full, s_empty, state);
           ep++;
         }
       }
@@ -788,7 +944,16 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, (PF_ON || 1024 / PT_LD
       double red[NRED];
 #pragma unroll
       for (int k = 0; k < NRED; k++) red[k] = 0.0;
-      if (g.nst == 1) {                                   /* Euler */
+      if (LEAN_OK && PF_ON && g.lean) {                          /* lean classic RK4: a.t_eval is the start of the step in every stage */
+        a.t_eval = t; a.t_next = t; a.a = 0.0; a.w = 0.0;
+        if (s == 0) {
+#pragma unroll
+          for (int k = 0; k < A1(NMFD); k++) mfd0[k] = mfd[k];
+          lean_sweep<0, PF_ON>(p, a, mfd0, mfd, red, ring_);
+        } else if (s == 1) lean_sweep<1, PF_ON>(p, a, mfd0, mfd, red, ring_);
+        else if (s == 2) lean_sweep<2, PF_ON>(p, a, mfd0, mfd, red, ring_);
+        else lean_sweep<3, PF_ON>(p, a, mfd0, mfd, red, ring_);
+      } else if (g.nst == 1) {                            /* Euler */
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
         chain_sweep<true, true, PF_ON>(p, a, mfd, red, ring_);
       } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */

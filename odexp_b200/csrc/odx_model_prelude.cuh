@@ -43,7 +43,11 @@ ODX_HD void odx_sincos(C &ctx, double x, double *sp, double *cp) {
   const double *T = odx_sc_host;
 #endif
   if (EXACT) { odx_sincos_library(x, sp, cp); return; }
+#if defined(__CUDA_ARCH__)
+  ctx.slow |= !((__double2hiint(x) & 0x7fffffff) < 0x40f9c8f0);      /* !(|x| < 105615.0) on the integer pipe: the bound's low word is 0 */
+#else
   ctx.slow |= !(fabs(x) < 105615.0);
+#endif
   const double q = rint(x * T[0]);
   const int n = (int)q;
   double r = fma(-q, T[1], x);
@@ -86,7 +90,11 @@ ODX_HD void odx_sincos_inc(C &ctx, double x, double x0, double s0, double c0, do
   const double *T = odx_sc_host;
 #endif
   const double d = x - x0;
+#if defined(__CUDA_ARCH__)
+  ctx.slow |= !((__double2hiint(d) & 0x7fffffff) < 0x3fc00000);      /* !(|d| < 0.125), integer pipe */
+#else
   ctx.slow |= !(fabs(d) < 0.125);
+#endif
   const double z = d * d;
   double ps = fma(z, T[16], T[17]);
   ps = fma(z, ps, T[18]);

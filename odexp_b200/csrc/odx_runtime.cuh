@@ -84,6 +84,7 @@ struct odx_handle {
   unsigned long long *ll_words = nullptr;     /* LL exchange words of the persistent kernel (zero-initialised) */
   int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
   int coop_blocks_tma = 0, tma_mode = -1;     /* tma_mode: -1 choose by size, 0 never, 1 always (option "tma") */
+  int lean_mode = -1;                         /* lean RK4 scheme: -1 with the TMA ring (HBM-resident populations), 0 never, 1 whenever eligible (option "lean") */
   double l2_bytes = 0.0;
   uint32_t epoch = 0;
   void *mail = nullptr;                       /* [2][MAX_RANKS][NRED] doubles | [2][MAX_RANKS] flags | abort int (IPC-exported) */
@@ -418,7 +419,8 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   /* TMA-ring variant for populations that stream from HBM, plain loads while the working set is L2-resident */
   const bool ring = TMA_ON && h->coop_blocks_tma > 0 &&
                     (h->tma_mode == 1 || (h->tma_mode < 0 && (double)h->n * TMA_NCOL_MAX * sizeof(double) > 1.5 * h->l2_bytes));
-  const int pt = ring ? PT_TMA : PT_LD, per_cta = ring ? 2 * TMA_CONS : 2 * PT_LD;
+  g.lean = (LEAN_OK && ring && nst == 4 && !iterate && h->lean_mode != 0) ? 1 : 0;      /* compiled into the ring variant only */
+  const int pt = ring ? PT_TMA : PT_LD, per_cta = ring ? TMA_TILE : 2 * PT_LD;
   int64_t grid = (h->n + per_cta - 1) / per_cta;
   if (grid > (ring ? h->coop_blocks_tma : h->coop_blocks)) grid = ring ? h->coop_blocks_tma : h->coop_blocks;
   if (grid > PERSIST_MAX_CTAS) grid = PERSIST_MAX_CTAS;
@@ -760,6 +762,7 @@ int odx_sync(odx_handle *h) {
 int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
+  if (strcmp(name, "lean") == 0) { h->lean_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }
   if (strcmp(name, "lrabstol") == 0) { h->lr_abstol = value; return ODX_SUCCESS; }

@@ -401,7 +401,7 @@ class Emitter:
                 e = _zmul_peephole(e)
         return _mangle_expr(e)
 
-    def cse(self, e, cache, out, record=None, hinted=None):
+    def cse(self, e, cache, out, record=None, hinted=None, hin="odx_h"):
         """hoist sin(A) / cos(A) into one odx_sincos(A) per distinct argument (innermost calls first).
         record: {canonical argument: hint slot} -- after the sincos of such an argument, store (A, sin A, cos A) in *odx_h
         (the RHS side of the stage-to-stage increment); hinted: the same map on the %M side, where sincos(A') is then formed
@@ -425,13 +425,13 @@ class Emitter:
                 canon = self.canon_arg(arg)
                 if hinted is not None and canon in hinted:
                     j = hinted[canon]
-                    out("    double odx_sn%d, odx_cs%d; odx_sincos_inc<ODX_EXACT>(odx_c, %s, odx_h.a[%d], odx_h.s[%d], odx_h.c[%d], &odx_sn%d, &odx_cs%d);"
-                        % (k, k, arg, j, j, j, k, k))
+                    out("    double odx_sn%d, odx_cs%d; odx_sincos_inc<ODX_EXACT>(odx_c, %s, %s.a[%d], %s.s[%d], %s.c[%d], &odx_sn%d, &odx_cs%d);"
+                        % (k, k, arg, hin, j, hin, j, hin, j, k, k))
                 else:
                     out("    double odx_sn%d, odx_cs%d; odx_sincos<ODX_EXACT>(odx_c, %s, &odx_sn%d, &odx_cs%d);" % (k, k, arg, k, k))
-                    if record is not None and canon in record:
-                        j = record[canon]
-                        out("    if (odx_h) { odx_h->a[%d] = %s; odx_h->s[%d] = odx_sn%d; odx_h->c[%d] = odx_cs%d; }" % (j, arg, j, k, j, k))
+                if record is not None and canon in record:
+                    j = record[canon]
+                    out("    if (odx_h) { odx_h->a[%d] = %s; odx_h->s[%d] = odx_sn%d; odx_h->c[%d] = odx_cs%d; }" % (j, arg, j, k, j, k))
             k = cache[key]
             e = e[:b] + ("odx_sn%d" % k if fn == "sin" else "odx_cs%d" % k) + e[en:]
 
@@ -533,46 +533,49 @@ class Emitter:
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %
           tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr, needs_id)))
         w("")
-        # ---- ode_rhs
-        w("  /* per-particle right-hand side: AUX, D/DT, %DEATH, %REPLI (reference: generated ode_rhs) */")
-        w("  /* ODX_EXACT = false: range-limited fast sincos, the context records when an argument was out of range and the engine")
-        w("   * redoes the particle with ODX_EXACT = true (library sincos); keeps the hot code free of branches */")
-        w("  template <bool ODX_EXACT, class C> ODX_HD static void rhs(C &odx_c, double t, const double *odx_y, const double *odx_e,")
-        w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli,")
-        w("      OdxHint *odx_h = nullptr) {")
-        w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e; (void)odx_h;")
-        for i, p in enumerate(m.pars):
-            if not re.search(r"\b(init|impl)\b", p.attr, flags=re.I):
-                ctype = "double"
-                mt = re.search(r"\b(int|long|double)\b", p.attr)
-                if mt:
-                    ctype = mt.group(1)
-                w("    const %s %s = (%s)odx_c.mu[%d];" % (ctype, mangle(p.name), ctype, i))
-        for e in m.exprs:
-            b = self.expr_base[e.name]
-            if e.length:
-                w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
-                  (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
-            else:
-                w("    const double %s = odx_e[%d];" % (mangle(e.name), b))
-        for e in m.eqs:
-            w("    const double %s = odx_y[%d];" % (mangle(e.name), self.var_idx[e.name]))
-        for c in m.cpls:
-            w("    const double %s = odx_psi[%d];" % (mangle(c.name), self.psi_idx[c.name]))
-        for e in m.mfds:
-            w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
-        tc = {}
-        for e in m.auxs:
-            w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots)))
-        for e in m.eqs:
-            w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots)))
-        for e in m.auxs:
-            w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
-        if m.death:
-            w("    odx_death = %s;" % self.cse(self.tr(m.death, "%DEATH"), tc, w))
-        if m.repli:
-            w("    odx_repli = %s;" % self.cse(self.tr(m.repli, "%REPLI"), tc, w))
-        w("  }\n")
+        # ---- ode_rhs (and the variant whose shared sincos arguments come from the previous stage's triple)
+        for inc in (False, True):
+            if inc:
+                w("  /* the RHS at a state one stage after the one described by odx_hi (the lean RK4 scheme recomputes stages) */")
+            w("  /* per-particle right-hand side: AUX, D/DT, %DEATH, %REPLI (reference: generated ode_rhs) */")
+            w("  /* ODX_EXACT = false: range-limited fast sincos, the context records when an argument was out of range and the engine")
+            w("   * redoes the particle with ODX_EXACT = true (library sincos); keeps the hot code free of branches */")
+            w("  template <bool ODX_EXACT, class C> ODX_HD static void %s(C &odx_c, double t, const double *odx_y, const double *odx_e," % ("rhs_inc" if inc else "rhs"))
+            w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli,")
+            w("      %sOdxHint *odx_h = nullptr) {" % ("const OdxHint &odx_hi, " if inc else ""))
+            w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e; (void)odx_h;%s" % (" (void)odx_hi;" if inc else ""))
+            for i, p in enumerate(m.pars):
+                if not re.search(r"\b(init|impl)\b", p.attr, flags=re.I):
+                    ctype = "double"
+                    mt = re.search(r"\b(int|long|double)\b", p.attr)
+                    if mt:
+                        ctype = mt.group(1)
+                    w("    const %s %s = (%s)odx_c.mu[%d];" % (ctype, mangle(p.name), ctype, i))
+            for e in m.exprs:
+                b = self.expr_base[e.name]
+                if e.length:
+                    w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
+                      (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
+                else:
+                    w("    const double %s = odx_e[%d];" % (mangle(e.name), b))
+            for e in m.eqs:
+                w("    const double %s = odx_y[%d];" % (mangle(e.name), self.var_idx[e.name]))
+            for c in m.cpls:
+                w("    const double %s = odx_psi[%d];" % (mangle(c.name), self.psi_idx[c.name]))
+            for e in m.mfds:
+                w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
+            tc = {}
+            for e in m.auxs:
+                w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
+            for e in m.eqs:
+                w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
+            for e in m.auxs:
+                w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
+            if m.death:
+                w("    odx_death = %s;" % self.cse(self.tr(m.death, "%DEATH"), tc, w))
+            if m.repli:
+                w("    odx_repli = %s;" % self.cse(self.tr(m.repli, "%REPLI"), tc, w))
+            w("  }\n")
         # ---- %M terms
         w("  /* per-particle %M expressions (summed over the population, then divided by POP_SIZE) */")
         w("  template <bool ODX_EXACT, class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")

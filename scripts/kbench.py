@@ -20,7 +20,7 @@ def run(n=1 << 24, steps=100):
     from odexp_b200 import capi, build as b
     for tag in VARIANTS:
         lib = capi.ModelLib(b.lib_path("kuramoto_" + tag))
-        for persistent in (1, 0):
+        for persistent in ((1, 0) if os.environ.get("KBENCH_BOTH") else (1,)):
             pop = capi.Population(lib, capacity=n)
             pop.set_option("persistent", persistent)
             pop.init(n, replay=False)
