@@ -423,8 +423,10 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_a) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) { mbar_arrive_a(smem_u32(bar)); }
 __device__ __forceinline__ uint32_t mbar_try_wait_a(uint32_t bar_a, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+  /* the suspend-time hint lets the hardware park the warp until the phase completes instead of returning after the default
+   * (short) limit: fewer re-issues of the try, fewer issue slots taken from the computing warps */
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar_a), "r"(parity), "r"(0x989680u) : "memory");
   return ok;
 }
 /* one thread waits */

@@ -170,3 +170,63 @@ def test_sincos_out_of_range_takes_library_path(model_lib):
         k1 = f(y); k2 = f(y + h / 2.0 * k1); k3 = f(y + h / 2.0 * k2); k4 = f(y + h * k3)
         y = y + h / 6.0 * (k1 + 2.0 * (k2 + k3) + k4)
     np.testing.assert_allclose(got, y, rtol=1e-12, atol=1e-9)
+
+
+# persistent step kernel variants: plain 128-bit loads + stored stages (L2-resident populations), TMA ring + stored stages, TMA ring
+# + lean RK4 (recomputed / recovered stages; what the BASELINE-size run uses).  Forced here at sizes the oracle can follow.
+VARIANTS = {"plain-stored": (0, 0), "ring-stored": (1, 0), "ring-lean": (1, 1)}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 1471, 1473, 2945, 6001, 70001])
+def test_step_kernel_variants_vs_oracle(model_lib, variant, n):
+    """every variant of the RK4 step kernel against the CPU restatement (ragged sizes around the ring tile of 2944 particles)"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto")
+    pop = capi.Population(lib, capacity=max(4096, n))
+    tma, lean = VARIANTS[variant]
+    pop.set_option("tma", tma); pop.set_option("lean", lean)
+    out = capi.odesolver(pop, (0, 1.0), meth="dde", h0=0.05, res=3, popsize=n, replay_ic=True)
+    ref = port.run("kuramoto", {"meth": "dde", "h0": 0.05, "res": 3, "ps": n}, (0, 1.0))
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(out["traj"]["id"], ref["traj"]["id"])
+    pop.close()
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_step_kernel_variants_vs_golden(model_lib, variant):
+    """... and against the unchanged reference binary's output (160 RK4 steps of 1000 oscillators)"""
+    import ast
+    from conftest import load_golden
+    from odexp_b200 import capi
+    g = load_golden("kuramoto_dde_n1000")
+    meta = ast.literal_eval(str(g["meta"][0])); o = meta["opts"]
+    pop = capi.Population(model_lib("kuramoto"), capacity=4096)
+    tma, lean = VARIANTS[variant]
+    pop.set_option("tma", tma); pop.set_option("lean", lean)
+    out = capi.odesolver(pop, meta["timespan"], replay_ic=True, meth=o["meth"], res=o["res"], popsize=o["ps"], h0=o.get("h0", 0.1),
+                         hmin=o.get("hmin", 1e-5))
+    tr = out["traj"]
+    last = tr[tr["step"] == tr["step"].max()]
+    np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["stats"]["mfd"], g["stats_mfd"], rtol=0, atol=1e-12)
+    pop.close()
+
+
+def test_lean_scheme_large_steps_take_exact_path(model_lib):
+    """a step so large that the stage increments leave the range of the angle-addition sincos (|d| >= 1/8): the lean scheme must
+    fall back to the library sincos per pair and still agree with the stored scheme"""
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    res = {}
+    for variant, (tma, lean) in VARIANTS.items():
+        pop = capi.Population(lib, capacity=8192)
+        pop.set_option("tma", tma); pop.set_option("lean", lean)
+        pop.init(5000, replay=True)
+        pop.run_fixed("dde", 0.0, 1.5, 4)          # h |k| ~ 1: far outside 1/8
+        res[variant] = pop.download()["y"][:, 0].copy()
+        pop.close()
+    np.testing.assert_allclose(res["ring-stored"], res["plain-stored"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(res["ring-lean"], res["plain-stored"], rtol=1e-12, atol=1e-12)
