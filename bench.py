@@ -23,6 +23,7 @@ METRIC = "particle-steps/sec (RK4, FP64)"
 N_TOTAL = 1 << 24
 H_STEP = 0.05
 ALG_BYTES_PER_PARTICLE_STEP = 72.0
+NCU_DRAM_BYTES_PER_PARTICLE_STEP = 96.4    # measured, see roofline.traffic below
 
 
 def peaks():
@@ -237,13 +238,14 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of k_chain_persist from the ncu --set full capture
-                             # profiles/r1_k_chain_persist_kuramoto_n16M.txt: 44.54 GB for 20 steps at N=2^24 = 132.7 B per particle-step
-                             # (152 B by construction, minus what the alternating sweep direction finds in L2)
-                             "traffic": (132.7 * n_local * args.steps) if (world == 1 and n_total == N_TOTAL) else None,
+                             # profiles/r1_k_chain_persist_lean_kuramoto_n16M.txt: 32.34 GB for 20 steps at N=2^24 = 96.4 B per
+                             # particle-step (lean RK4: 112 B by construction, minus what the alternating sweep direction finds in L2)
+                             "traffic": (NCU_DRAM_BYTES_PER_PARTICLE_STEP * n_local * args.steps) if (world == 1 and n_total == N_TOTAL) else None,
                              "traffic_unit": "bytes per launch (one cooperative launch = all timed steps)",
                              "peak_source": how, "algorithmic_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_local * args.steps,
-                             "kernel": "k_chain_persist (one cooperative launch runs all timed RK4 steps: 4 stages per step, in-kernel mean-field exchange)"}}
+                             "kernel": "k_chain_persist (one cooperative launch runs all timed RK4 steps: 4 stages per step, in-kernel mean-field exchange; "
+                                       + ("TMA ring + lean RK4 stages" if n_local * 32 > 1.5 * 126e6 else "plain loads + stored stages, L2-resident shard") + ")"}}
         if world == 1 and not args.no_cpu:
             v, info = cpu_reference_sample(1 << 20, 16)
             line["cpu_baseline"] = dict(info, value=v, unit="particle-steps/s")

@@ -13,12 +13,17 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for model, n, meth, nsteps, tol in [("kuramoto", 100003, "dde", 20, 1e-12), ("nbody", 3001, "dde", 2, 1e-12), ("nbody", 2048, "rkf45", 3, 1e-9),
-                                    ("vdp_sde", 50001, "fe", 10, 1e-12), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10)]:
+CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 0}),
+         ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 1}),          # ring / lean step kernels with the NVLink exchange
+         ("nbody", 3001, "dde", 2, 1e-12, {}), ("nbody", 2048, "rkf45", 3, 1e-9, {}),
+         ("vdp_sde", 50001, "fe", 10, 1e-12, {}), ("vdp_sde", 50001, "fe", 10, 1e-12, {"tma": 1}), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10, {})]
+for model, n, meth, nsteps, tol, opts in CASES:
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
     pop = capi.Population(lib, capacity=hi - lo + 64, device=local)
     odist.connect(pop)
+    for k, v in opts.items():
+        pop.set_option(k, v)
     pop.set_seed(77)
     pop.init(hi - lo, replay=False, seed=77)
     t, h = 0.0, 0.01
@@ -51,8 +56,8 @@ for model, n, meth, nsteps, tol in [("kuramoto", 100003, "dde", 20, 1e-12), ("nb
         dm = np.abs(mfd - solo.meanfields()).max() if lib.nmfd else 0.0
         good = (dy <= tol) and (dp <= max(tol, 1e-12)) and (dm <= 1e-13) and np.array_equal(mine["id"], ref["id"]) and abs(t - ts) < 1e-15
         ok &= bool(good)
-        print("%-8s %-5s N=%d world=%d  t=%.6g (solo %.6g)  max rel dy=%.2e  dpsi=%.2e  dmfd=%.2e  ids_equal=%s  -> %s" % (
-            model, meth, n, world, t, ts, dy, dp, dm, np.array_equal(mine["id"], ref["id"]), "OK" if good else "MISMATCH"), flush=True)
+        print("%-8s %-5s %-22s N=%d world=%d  t=%.6g (solo %.6g)  max rel dy=%.2e  dpsi=%.2e  dmfd=%.2e  ids_equal=%s  -> %s" % (
+            model, meth, opts or "", n, world, t, ts, dy, dp, dm, np.array_equal(mine["id"], ref["id"]), "OK" if good else "MISMATCH"), flush=True)
         solo.close()
     dist.barrier()
     pop.close()
