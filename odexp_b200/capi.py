@@ -283,12 +283,21 @@ class Population:
         self._ck(self.L.odx_ssa_apply(self.h, t, u, C.byref(row)), "odx_ssa_apply")
         return (row.n, row.stop_flag, tuple(row.event))
 
-    def tauleap_apply(self, t, dt, leap_index, max_rows=None):
+    def tauleap_apply(self, t, dt, leap_index, max_rows=None, as_array=False):
+        """one tau-leaping sweep; returns the stats.dat event rows (list of (n, stop_flag, (parent, +-1, child)), or with
+        as_array=True a numpy structured array: no per-row Python work, for large populations)"""
         n = self.size()[0]
         max_rows = max_rows or (3 * n + 4096)
-        rows = (EventRow * max_rows)()
+        if as_array:
+            buf = np.zeros(max_rows, dtype=np.dtype([("n", "<i4"), ("stop_flag", "<i4"), ("event", "<i4", (3,))]))
+            assert buf.itemsize == C.sizeof(EventRow)
+            rows = buf.ctypes.data_as(C.POINTER(EventRow))
+        else:
+            rows = (EventRow * max_rows)()
         nr = C.c_int64()
         self._ck(self.L.odx_tauleap_apply(self.h, t, dt, int(leap_index), rows, max_rows, C.byref(nr)), "odx_tauleap_apply")
+        if as_array:
+            return buf[:nr.value]
         return [(rows[i].n, rows[i].stop_flag, tuple(rows[i].event)) for i in range(nr.value)]
 
 

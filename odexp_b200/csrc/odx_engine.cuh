@@ -71,6 +71,14 @@ struct DevCtx {
   int has_sister;
   int stop;                 /* STOPIF */
   int slow;                 /* a fast-path sincos saw an out-of-range argument: redo this particle with the library path */
+  /* KY(name, degree) (src/odexp.h:334-357): variable `name` of the degree-th neighbour in list order, the list closed to a ring;
+   * the neighbour's value is the state the current RHS evaluation is made at (p->y after pass 1 of pop_rhs) */
+  const double *ky_base; int64_t ky_i, ky_n, ky_stride;
+  ODX_HD double ky(int v, long d) const {
+    int64_t j = (ky_i + d) % ky_n;
+    if (j < 0) j += ky_n;
+    return ky_base[(int64_t)v * ky_stride + j];
+  }
   ODX_HD double rand01() { return rng.rand01(); }
   ODX_HD double randN(double m, double s) { return rng.randN(m, s); }
   ODX_HD double exprand(double r) { return rng.exprand(r); }
@@ -82,6 +90,7 @@ struct DevCtx {
 struct HostCtx {
   const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli, ist0;
   const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop; int slow;
+  ODX_HD double ky(int, long) const { return 0.0; }      /* not reachable: KY is rejected inside initial conditions */
   ODX_HD double rand01() { return hr->rand01(); }
   ODX_HD double randN(double m, double s) { return hr->randN(m, s); }
   ODX_HD double exprand(double r) { return hr->exprand(r); }
@@ -94,6 +103,9 @@ constexpr int MUV_MAX = 48;                                   /* parameters carr
 constexpr int MUV_N = (NPAR >= 1 && NPAR <= MUV_MAX) ? NPAR : 1;
 struct Pop {
   double *Y, *YS, *ACC, *E, *AUX, *PSI, *DEATH, *REPLI, *KS;
+  double *Y_OUT;            /* where the last stage stores the new state: Y (the other buffer for Euler / iteration with KY()) */
+  double *YS_OUT;           /* where a stage stores the stage state it forms: YS, except for models with KY(), whose stages
+                               alternate between two buffers because neighbours still read the previous stage state */
   int32_t *ID;
   int64_t stride;           /* column stride = capacity */
   int64_t n;                /* particles on this GPU */
@@ -193,7 +205,11 @@ __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stre
   c.mu = (NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu; c.pop_size = p.n_global; c.h = h;
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
   c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
+  c.ky_base = nullptr; c.ky_i = 0; c.ky_n = 1; c.ky_stride = 0;
   return c;
+}
+__device__ __forceinline__ void ctx_neighbours(DevCtx &c, const Pop &p, const double *ycur, int64_t i) {
+  if (M::USES_KY) { c.ky_base = ycur; c.ky_i = i; c.ky_n = p.n; c.ky_stride = p.stride; }
 }
 
 /* STOPIF (src/odexp.h:400-406): the reference sets the global EVENT_TYPE from inside ode_rhs; here the full (second-pass)
@@ -297,12 +313,13 @@ struct ChainArgs {
  * Each thread carries two adjacent particles per iteration: every column is moved with 128-bit accesses and the two
  * independent dependency chains hide the FP64 latency of the per-particle model code. */
 template <bool FIRST, bool LAST, bool EXACT>
-__device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id,
+__device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id, int64_t gi,
                                           const double (&y0)[A1(NVAR)], const double (&yc)[A1(NVAR)], const double (&e)[A1(NEXPR)],
                                           const double (&psi)[A1(NPSI)], const double (&acc_in)[A1(NVAR)], double (&acc)[A1(NVAR)],
                                           double (&yn)[A1(NVAR)], double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
   double f[A1(NVAR)];
   DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+  ctx_neighbours(c, p, FIRST ? p.Y : p.YS, gi);
   OdxHint hint;
   M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli, USE_HINTS ? &hint : nullptr);
   note_stop(p, c);
@@ -509,16 +526,16 @@ __device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, con
   int32_t id0 = 0, id1 = 0;
   if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
   double acco[2][A1(NVAR)], tm[2][NRED];
-  const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-  const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+  const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   if (s0 | s1) {          /* rare: an argument outside the fast sincos range -> library path for this pair */
-    chain_lane<FIRST, LAST, true>(p, a, mfd, id0, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-    chain_lane<FIRST, LAST, true>(p, a, mfd, id1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+    chain_lane<FIRST, LAST, true>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    chain_lane<FIRST, LAST, true>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   }
 #pragma unroll
   for (int k2 = 0; k2 < NRED; k2++) red[k2] += tm[0][k2] + (two ? tm[1][k2] : 0.0);
   if (LAST) {
-    store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
+    store_cols2<NVAR>(p.Y_OUT, p.stride, i, two, yn[0], yn[1]);
     if (a.want_out) {
       store_cols2<NAUX>(p.AUX, p.stride, i, two, aux[0], aux[1]);
       if (M::HAS_DEATH) { p.DEATH[i] = death[0]; if (two) p.DEATH[i + 1] = death[1]; }
@@ -526,7 +543,7 @@ __device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, con
     }
   } else {
     if (!(FIRST && a.skip_acc_store)) store_cols2<NVAR>(p.ACC, p.stride, i, two, acco[0], acco[1]);
-    store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
+    store_cols2<NVAR>(p.YS_OUT, p.stride, i, two, yn[0], yn[1]);
   }
 }
 
@@ -630,7 +647,7 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
  * instead of ~200.  Requires: no %C columns (psi of earlier stages would have to be kept), no random numbers or STOPIF in the
  * RHS.  While the population sits in L2 the stored scheme is faster (FP64-bound there) and stays in use.
  * ---------------------------------------------------------------------------------------------- */
-constexpr bool LEAN_OK = (NPSI == 0) && !M::RHS_RNG && !M::HAS_STOPIF && !M::HAS_PAIR && !M::HAS_LOWRANK;
+constexpr bool LEAN_OK = (NPSI == 0) && !M::RHS_RNG && !M::HAS_STOPIF && !M::HAS_PAIR && !M::HAS_LOWRANK && !M::USES_KY;
 template <int LS, bool EXACT>
 __device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
                                          int32_t id, const double (&y0)[A1(NVAR)], const double (&e)[A1(NEXPR)],
@@ -1089,6 +1106,7 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
     load_cols<NEXPR>(p.E, p.stride, i, e);
     if (NPSI > 0) load_cols<NPSI>(p.PSI, p.stride, i, psi);
     DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
+    ctx_neighbours(c, p, ysrc, i);
     rhs_checked(p, c, a.t, y, e, psi, mfd, f, aux, death, repli);
     store_cols<NAUX>(p.AUX, p.stride, i, aux);
     if (M::HAS_DEATH) p.DEATH[i] = death;

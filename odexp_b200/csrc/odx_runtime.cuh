@@ -58,7 +58,7 @@ struct odx_handle {
   int64_t cap = 0, n = 0;
   int32_t max_id = 0;
   double *Y = nullptr, *YS = nullptr, *ACC = nullptr, *E = nullptr, *AUX = nullptr, *PSI = nullptr, *DEATH = nullptr,
-         *REPLI = nullptr, *KS = nullptr, *K1 = nullptr, *DOUT = nullptr, *YONE = nullptr, *YH = nullptr, *K1B = nullptr;
+         *REPLI = nullptr, *KS = nullptr, *YALT = nullptr, *K1 = nullptr, *DOUT = nullptr, *YONE = nullptr, *YH = nullptr, *K1B = nullptr;
   int32_t *ID = nullptr;
   double *d_mu = nullptr;
   double h_mu[A1(NPAR)];
@@ -115,7 +115,7 @@ namespace odx {
 
 static inline Pop pop_view(const odx_handle *h) {
   Pop p;
-  p.Y = h->Y; p.YS = h->YS; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
+  p.Y = h->Y; p.YS = h->YS; p.YS_OUT = h->YS; p.Y_OUT = h->Y; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
   p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
   p.stop = reinterpret_cast<int *>(h->counter + 8);
   for (int k = 0; k < MUV_N; k++) p.muv[k] = (k < NPAR) ? h->h_mu[k] : 0.0;
@@ -438,13 +438,22 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   return ODX_SUCCESS;
 }
 static inline bool can_persist(const odx_handle *h) {
-  return h->use_persistent && h->coop_ok && !M::HAS_PAIR && !M::HAS_LOWRANK && (h->nranks == 1 || h->peers_attached);
+  return h->use_persistent && h->coop_ok && !M::HAS_PAIR && !M::HAS_LOWRANK && !M::USES_KY && (h->nranks == 1 || h->peers_attached);
+}
+static int alloc_cols(odx_handle *h, double **ptr, int ncol);
+/* models with KY(): neighbours read the stage state while the stage forms the next one, so nothing is updated in place */
+static int ky_guard(odx_handle *h) {
+  if (!M::USES_KY) return ODX_SUCCESS;
+  if (h->nranks > 1) { h->err = "KY() ring neighbours are not supported on a sharded population yet (needs a halo exchange)"; return ODX_EUNSUP; }
+  if (!h->YALT) ODX_TRY(alloc_cols(h, &h->YALT, NVAR));
+  return ODX_SUCCESS;
 }
 
 /* one step of a chain method.  nst = 1: Euler (fe_apply); nst = 4: classic RK4 (dde_apply) */
 static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out, int iterate = 0) {
   if (h->n <= 0) return ODX_SUCCESS;
   if (can_persist(h)) return chain_run_persist(h, nst, t, hh, 1, want_out, iterate);
+  ODX_TRY(ky_guard(h));
   ODX_TRY(ensure_moments_Y(h, t));
   const int g = grid_chain(h, h->n);
   Pop p = pop_view(h);
@@ -454,8 +463,10 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     ODX_TRY(compute_psi(h, h->Y, t));
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + hh; a.a = hh; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1);
+    if (M::USES_KY) p.Y_OUT = h->YS;              /* the new state goes to the other buffer, then the buffers change roles */
     k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
     ODX_TRY(launch_check(h));
+    if (M::USES_KY) { double *tmp = h->Y; h->Y = h->YS; h->YS = tmp; }
     h->report_slot = h->y_slot; h->rhs_evals += 1;
   } else {
     /* k[i] = y[i] + (*h)/2.0*k1[i]; ...; y[i] += (*h)/6.0*(k1 + 2.0*(k2+k3) + k4)   (methods_odexp.c:1846-1863) */
@@ -469,13 +480,16 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     ODX_TRY(compute_psi(h, h->YS, t + half));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 0); a.t_eval = t + half; a.t_next = t + half; a.a = half; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1); a.recon = h->use_recon ? 1.0 / half : 0.0;
+    if (M::USES_KY) p.YS_OUT = h->YALT;           /* y2 in YS is still read by the neighbours: y3 goes to the other buffer */
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 1));
     a.recon = 0.0;
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 1));
-    ODX_TRY(compute_psi(h, h->YS, t + half));
+    ODX_TRY(compute_psi(h, M::USES_KY ? h->YALT : h->YS, t + half));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 1); a.t_eval = t + half; a.t_next = t + hh; a.a = hh; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1);
+    if (M::USES_KY) { p.YS = h->YALT; p.YS_OUT = h->YS; }
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 2));
+    if (M::USES_KY) { p.YS = h->YS; p.YS_OUT = h->YS; }
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 2));
     ODX_TRY(compute_psi(h, h->YS, t + hh));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 2); a.t_eval = t + hh; a.t_next = t + hh; a.a = hh / 6.0; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
@@ -737,7 +751,7 @@ void odx_destroy(odx_handle *h) {
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   if (h->ll_words) cudaFree(h->ll_words);
-  double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->K1, h->DOUT, h->YONE, h->YH, h->K1B, h->d_mu, h->partial,
+  double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->YALT, h->K1, h->DOUT, h->YONE, h->YH, h->K1B, h->d_mu, h->partial,
                     h->sums, h->stage_dev, h->gather, h->pair_part};
   for (double *b : bufs) if (b) cudaFree(b);
   if (h->ID) cudaFree(h->ID);
@@ -1122,6 +1136,7 @@ int odx_iteration_apply(odx_handle *h, double *t, int want_outputs) {
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (h->n > 0) {
     if (M::HAS_PAIR || M::HAS_LOWRANK) { h->err = "meth iteration with %C coupling is not supported"; return ODX_EUNSUP; }
+    if (M::USES_KY) { h->err = "meth iteration with KY() is not supported (pop_rhs(t, y, y) aliases the list the neighbours are read from)"; return ODX_EUNSUP; }
     const int g = grid_chain(h, h->n);
     Pop p = pop_view(h);
     ChainArgs a; memset(&a, 0, sizeof a);
@@ -1169,6 +1184,7 @@ int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uin
  * Behaviour follows GSL's documented driver: reuse dydt_out as the next dydt_in, clip the step to reach t1,
  * on rmax > 1.1 shrink by max(0.2, 0.9 rmax^(-1/ord)) and retry, on rmax < 0.5 grow by min(5, max(1, 0.9 rmax^(-1/(ord+1)))). */
 int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
+  if (M::USES_KY) { h->err = "KY() ring neighbours are supported with the fixed-step methods fe and dde only"; return ODX_EUNSUP; }
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4) {
     h->err = "odx_evolve_apply: method must be rkf45, rkck or rk4"; return ODX_EUNSUP;

@@ -371,8 +371,12 @@ class Emitter:
             e = _inline_funs(e, self.m.funs)
         e = re.sub(r"\b(MU|MF|MC|MY|OY|SY|ME|OE|SE|MA|OA|SA)\(\s*(%s)\s*\)" % IDENT,
                    lambda mm: self._macro(mm.group(1), mm.group(2), where), e)
-        if re.search(r"\bKY\s*\(", e):
-            raise PopError("KY() ring neighbours are not supported on the device yet (%s)" % where)
+        for b, en, args in list(_find_call(e, "KY"))[::-1]:       # KY(name, degree): the degree-th neighbour in list order, ring
+            if len(args) != 2 or args[0] not in self.var_idx:
+                raise PopError("KY(name, degree) in %s: '%s' is not a dynamical variable" % (where, args[0] if args else ""))
+            if exact or where.startswith("%M") or where.startswith("%C") or where.startswith("%BIRTH"):
+                raise PopError("KY() ring neighbours are only supported inside AUX / D/DT / %%DEATH / %%REPLI (%s)" % where)
+            e = e[:b] + "odx_c.ky(%d, (%s))" % (self.var_idx[args[0]], args[1]) + e[en:]
         if re.search(r"\b(delay|interp)\s*\(", e):
             raise PopError("delay()/interp() history stacks are host-only (%s)" % where)
         e = re.sub(r"\bDWDT\b", "odx_c.dwdt()", e)
@@ -494,6 +498,11 @@ class Emitter:
         if self.uses(term_exprs, r"\b(OY|OE)\("):
             raise PopError("OY()/OE() are only meaningful inside %C")
         terms_use_aux = self.uses(term_exprs, r"\bMA\(")
+        uses_ky = self.uses(rhs_exprs, r"\bKY\s*\(")
+        if self.uses(term_exprs + cpl_exprs + [x.rhs for x in m.exprs] + [x.rhs for x in m.inits], r"\bKY\s*\("):
+            raise PopError("KY() ring neighbours are only supported inside AUX / D/DT / %DEATH / %REPLI")
+        if uses_ky and terms_use_aux:
+            raise PopError("KY() together with MA() inside %M is not supported (the reference's first pass sees a half-updated list)")
         cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
         rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
         has_stopif = self.uses(rhs_exprs, r"\bSTOPIF\s*\(")
@@ -529,6 +538,7 @@ class Emitter:
         w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
         w("  static constexpr bool HAS_STOPIF = %s;" % ("true" if has_stopif else "false"))
+        w("  static constexpr bool USES_KY = %s;      /* KY(name, degree): the RHS reads the stage state of list neighbours */" % ("true" if uses_ky else "false"))
         w("  static constexpr int NHINT = ODX_NHINT;")
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %
           tuple("true" if x else "false" for x in (pair_cpls, lr_cpls, terms_use_aux, cpl_uses_expr, needs_id)))

@@ -140,7 +140,30 @@ static void rd_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = c->ist0 ? e[0] : 2.0 * e[0];          /* IST0(x0, 2.0*x0) */
 }
 
+/* ---------------------------------------------------------------- ring_diffusion.pop (KY list neighbours) */
+static const double ring_pars[] = {0.8, 0.05, 0.3};
+static void ring_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                     double *aux, double *death, double *repli) {
+  const double D = c->mu[0], eps = c->mu[1], a = c->mu[2], w = e[0], x = y_[0], v = y_[1], XBAR = mfd[0];
+  const double lap = orc_ky(c, 0, 1) + orc_ky(c, 0, -1) - 2 * x;
+  (void)t; (void)psi; (void)death; (void)repli;
+  f[0] = w * v + D * lap + eps * (orc_ky(c, 0, 2) - orc_ky(c, 0, -2));
+  f[1] = -w * x - a * v + 0.1 * (XBAR - x);
+  aux[0] = lap;
+}
+static double ring_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void ring_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = orc_randN(c, 1.0, 0.1);
+  y[0] = orc_rand01(c);
+  y[1] = 0.0;
+}
+
 static const orc_model MODELS[] = {
+  {"ring_diffusion", 2, 1, 1, 0, 1, 3, ring_pars, ring_rhs, ring_mfd, NULL, NULL, ring_ic, 0, 0, 0, 0, 0, NULL},
   {"reset_decay", 1, 1, 1, 0, 1, 2, rd_pars, rd_rhs, rd_mfd, NULL, NULL, rd_ic, 0, 0, 0, 0, 0, NULL},
   {"logistic_map", 1, 1, 1, 0, 1, 2, lm_pars, lm_rhs, lm_mfd, NULL, NULL, lm_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto", 1, 1, 2, 0, 3, 1, kur_pars, kur_rhs, kur_mfd, NULL, NULL, kur_ic, 0, 0, 0, 0, 0, NULL},

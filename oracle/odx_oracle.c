@@ -151,6 +151,16 @@ static void rhs_ctx(orc_sim *s, orc_ctx *c, const orc_par *p) {
   c->sim = s; c->mu = s->mu; c->pop_size = (double)s->size; c->h = s->h ? *s->h : 0.0; c->id = p->id; c->oid = p->id;
   c->kid = (uint32_t)p->id; c->kstream = s->eval_index; c->kdom = ORC_DOM_RHS; c->kslot = 0;
 }
+/* KY(name, degree) (src/odexp.h:334-357): walk |degree| links forwards (nextel, NULL -> list start) or backwards (prevel,
+ * NULL -> list end) from the particle and read that neighbour's y as stored in the list: in pass 1 of pop_rhs the neighbours
+ * before the particle already hold the state of this evaluation and those after it the state of the previous evaluation; in
+ * pass 2 (the values that reach f) all hold the current state. */
+double orc_ky(orc_ctx *c, int var, int degree) {
+  orc_sim *s = c->sim;
+  int j = (c->pos + degree) % s->n;
+  if (j < 0) j += s->n;
+  return s->p[j]->y[var];
+}
 int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
   orc_sim *s = params; const orc_model *m = s->model;
   int i, j, k; orc_ctx c;
@@ -160,7 +170,7 @@ int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
   /* pass 1: aux / rates with zeroed mean fields and the psi of the previous call; copy the state into the particles */
   for (i = 0; i < s->n; i++) {
     orc_par *p = s->p[i];
-    rhs_ctx(s, &c, p);
+    rhs_ctx(s, &c, p); c.pos = i;
     m->rhs(&c, t, y_ + (size_t)i * m->nvar, p->expr, p->psi, s->mfd, f_ + (size_t)i * m->nvar, p->aux, &p->death, &p->repli);
     memcpy(p->y, y_ + (size_t)i * m->nvar, sizeof(double) * m->nvar);
     if (m->birth_term) s->pop_birth_rate += m->birth_term(&c, p->y, p->expr, p->aux);
@@ -184,7 +194,7 @@ int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
       }
       for (k = 0; k < m->npsi; k++) p->psi[k] /= s->size;
     }
-    rhs_ctx(s, &c, p);
+    rhs_ctx(s, &c, p); c.pos = i;
     m->rhs(&c, t, y_ + (size_t)i * m->nvar, p->expr, p->psi, s->mfd, f_ + (size_t)i * m->nvar, p->aux, &p->death, &p->repli);
   }
   s->eval_index += 2;

@@ -29,6 +29,7 @@ typedef struct orc_ctx {
   const double *mu; double pop_size, h;
   int id, oid, atbirth, atrepli, ist0;
   const orc_par *sister;
+  int pos;                                 /* position of the particle in the list (KY) */
   uint32_t kid, kstream, kdom, kslot;      /* keyed-Philox address of the next draw (rng_mode 1) */
 } orc_ctx;
 
@@ -81,6 +82,7 @@ double orc_exprand(orc_ctx *c, double r);
 long   orc_poisson(orc_ctx *c, double lambda);
 double orc_dwdt(orc_ctx *c);
 int    orc_stopif(orc_ctx *c, int cond);      /* STOPIF(cond), src/odexp.h:400-406 */
+double orc_ky(orc_ctx *c, int var, int degree); /* KY(name, degree), src/odexp.h:334-357 */
 
 const orc_model *orc_find_model(const char *name);
 int orc_pop_rhs(double t, const double *y, double *f, void *sim);

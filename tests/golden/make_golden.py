@@ -14,6 +14,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 KUR = dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1)
 NBD = dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0)
 VDP = dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0)
+RING = dict(nvar=2, naux=1, npsi=0, nmfd=1, nexpr=1)
 
 CASES = {
     # name: (fixture, opts, timespan, dims)
@@ -28,12 +29,18 @@ CASES = {
     "kuramoto_rk4_n50": ("kuramoto", {"meth": "rk4", "res": 6, "ps": 50}, (0, 5.0), KUR),      # GSL step-doubling rk4
     "nbody_dde_n64": ("nbody", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 64}, (0, 0.4), NBD),
     # short horizon: at T=0.4 a close encounter makes the reference itself change by 7e-6 under a 1e-7 relative change of the tolerance
+    # KY() list neighbours: ring with nearest / next-nearest coupling; n = 3 wraps around more than once for degree 2
+    "ring_dde_n50": ("ring_diffusion", {"meth": "dde", "h0": 0.05, "res": 11, "ps": 50}, (0, 2.0), RING),
+    "ring_fe_n3": ("ring_diffusion", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 3}, (0, 0.2), RING),
     "nbody_rkf45_n96": ("nbody", {"meth": "rkf45", "h0": 0.02, "res": 3, "ps": 96, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 0.2), NBD),
 }
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, (fx, opts, ts, dims) in CASES.items():
+        if only and name not in only:
+            continue
         r = refrun.run(fx, opts, timespan=ts, dims=dims)
         if name == "kuramoto_shipped_rkck":
             opts, ts = {"meth": "rkck", "res": 801, "ps": 1000}, (0, 160)     # what the shipped file sets itself

@@ -93,3 +93,35 @@ def test_config1_kuramoto_as_shipped(model_lib):
     tr = out["traj"]
     last = tr[tr["step"] == tr["step"].max()]
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["ring_dde_n50", "ring_fe_n3"])
+def test_ring_neighbours_ky(model_lib, name):
+    """KY(name, degree): list neighbours on a ring (src/odexp.h:334-357).  The stages alternate between two buffers on the device
+    because neighbours read the stage state while the next one is formed; golden = the unchanged reference binary."""
+    g, out, meta = run_case(model_lib, name)
+    first, last = check(g, out)
+    np.testing.assert_array_equal(first["cols"][:, :2], g["first_cols"][:, :2])
+    np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("n,meth", [(1, "dde"), (2, "dde"), (5, "fe"), (1025, "dde"), (4099, "fe")])
+def test_ring_neighbours_vs_oracle(model_lib, n, meth):
+    """ragged ring sizes (a ring of 1 or 2 particles wraps onto itself) against the CPU restatement"""
+    from odexp_b200 import capi
+    from oracle import port
+    pop = capi.Population(model_lib("ring_diffusion"), capacity=max(1024, n + 8))
+    out = capi.odesolver(pop, (0, 0.6), meth=meth, h0=0.02, res=4, popsize=n, replay_ic=True)
+    ref = port.run("ring_diffusion", {"meth": meth, "h0": 0.02, "res": 4, "ps": n}, (0, 0.6))
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+    pop.close()
+
+
+def test_ring_neighbours_unsupported_paths_fail_loudly(model_lib):
+    from odexp_b200 import capi
+    pop = capi.Population(model_lib("ring_diffusion"), capacity=1024)
+    pop.init(10, replay=True)
+    with pytest.raises(capi.OdxError, match="KY"):
+        pop.evolve_reset(); pop.evolve_apply("rkck", 0.0, 1.0, 0.1)
+    pop.close()

@@ -9,7 +9,7 @@ import pytest
 from conftest import load_golden
 
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
-                "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96"]
+                "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -46,6 +46,10 @@ REF_CASES = [
     ("reset_decay", {"meth": "dde", "h0": 0.05, "res": 25, "ps": 20}, (0, 1.5, 3.25, 6)),
     ("reset_decay", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 7}, (0, 0.5, 4.0, 4.1, 7)),
     ("kuramoto", {"meth": "rkf45", "h0": 0.1, "res": 6, "ps": 30}, (0, 0.7, 2.0)),
+    # KY() list neighbours on a ring (src/odexp.h:334-357), fixed-step and adaptive
+    ("ring_diffusion", {"meth": "dde", "h0": 0.05, "res": 11, "ps": 50}, (0, 2.0)),
+    ("ring_diffusion", {"meth": "fe", "h0": 0.01, "res": 5, "ps": 7}, (0, 0.5)),
+    ("ring_diffusion", {"meth": "rkck", "res": 4, "ps": 33}, (0, 1.0)),
 ]
 
 
