@@ -1288,6 +1288,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
       load_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     } else {
       DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+      ctx_neighbours(c, p, a.ycur, i);
       rhs_checked(p, c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli);
       store_cols<NVAR>(slope_ptr(p, a, a.s - 1), p.stride, i, f);
     }
@@ -1310,7 +1311,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
         if (rr > rloc) rloc = rr;          /* GSL_MAX_DBL: a NaN ratio is dropped */
       }
     }
-    store_cols<NVAR>(p.YS, p.stride, i, yn);
+    store_cols<NVAR>(p.YS_OUT, p.stride, i, yn);
     if (NMFD > 0 || M::HAS_BIRTH) {
       DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
       particle_terms(c2, a.t_next, yn, e, psi, red);

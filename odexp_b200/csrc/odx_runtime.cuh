@@ -569,10 +569,13 @@ static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh
     a.eval_index = h->eval_index; h->eval_index += 2;
     if (!a.skip_rhs) h->rhs_evals++;
     const int out_slot = SLOT_STAGE + (s - 1);
+    /* KY(): neighbours read the stage state this kernel evaluates the RHS at, so the state it forms goes to the other buffer
+     * (odd stages write YALT, even ones YS: the sixth leaves y_new in YS) */
+    if (M::USES_KY) { p.YS_OUT = (s & 1) ? h->YALT : h->YS; if (s > 1) a.ycur = (s & 1) ? h->YS : h->YALT; }
     k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, out_slot));
     ODX_TRY(launch_check(h));
     if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, out_slot));
-    ODX_TRY(compute_psi(h, h->YS, a.t_next));
+    ODX_TRY(compute_psi(h, p.YS_OUT, a.t_next));
   }
   h->k1_valid = true;   /* K1 now holds f(t, Y) whatever happens to this attempt */
   /* dydt_out = f(t + h, y_new): also refreshes aux / rates / reported mean fields like every reference RHS call */
@@ -601,10 +604,11 @@ static int rk4_tab_step(odx_handle *h, const double *y0src, double *k1buf, bool 
     a.eval_index = h->eval_index; h->eval_index += 2;
     if (!a.skip_rhs) h->rhs_evals++;
     const int slot = (s == 4) ? out_slot : SLOT_STAGE + (s - 1);
+    if (M::USES_KY) { p.YS_OUT = (s & 1) ? h->YALT : h->YS; if (s > 1) a.ycur = (s & 1) ? h->YS : h->YALT; }
     k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, slot));
     ODX_TRY(launch_check(h));
     if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, slot));
-    ODX_TRY(compute_psi(h, h->YS, a.t_next));
+    ODX_TRY(compute_psi(h, p.YS_OUT, a.t_next));
   }
   return ODX_SUCCESS;
 }
@@ -1184,7 +1188,7 @@ int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uin
  * Behaviour follows GSL's documented driver: reuse dydt_out as the next dydt_in, clip the step to reach t1,
  * on rmax > 1.1 shrink by max(0.2, 0.9 rmax^(-1/ord)) and retry, on rmax < 0.5 grow by min(5, max(1, 0.9 rmax^(-1/(ord+1)))). */
 int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
-  if (M::USES_KY) { h->err = "KY() ring neighbours are supported with the fixed-step methods fe and dde only"; return ODX_EUNSUP; }
+  ODX_TRY(ky_guard(h));
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4) {
     h->err = "odx_evolve_apply: method must be rkf45, rkck or rk4"; return ODX_EUNSUP;

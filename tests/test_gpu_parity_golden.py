@@ -118,10 +118,15 @@ def test_ring_neighbours_vs_oracle(model_lib, n, meth):
     pop.close()
 
 
-def test_ring_neighbours_unsupported_paths_fail_loudly(model_lib):
+@pytest.mark.parametrize("meth,n", [("rkck", 33), ("rkf45", 200), ("rk4", 17)])
+def test_ring_neighbours_adaptive_vs_oracle(model_lib, meth, n):
+    """KY() under the embedded pairs and the step-doubling rk4 (same accept / reject sequence as the restatement, which is
+    bit-identical to the reference binary for this fixture)"""
     from odexp_b200 import capi
+    from oracle import port
     pop = capi.Population(model_lib("ring_diffusion"), capacity=1024)
-    pop.init(10, replay=True)
-    with pytest.raises(capi.OdxError, match="KY"):
-        pop.evolve_reset(); pop.evolve_apply("rkck", 0.0, 1.0, 0.1)
+    out = capi.odesolver(pop, (0, 1.5), meth=meth, res=4, popsize=n, replay_ic=True)
+    ref = port.run("ring_diffusion", {"meth": meth, "res": 4, "ps": n}, (0, 1.5))
+    assert len(out["stats"]) == len(ref["stats"])
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-9, atol=1e-12)
     pop.close()
