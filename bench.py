@@ -24,6 +24,7 @@ N_TOTAL = 1 << 24
 H_STEP = 0.05
 ALG_BYTES_PER_PARTICLE_STEP = 72.0
 NCU_DRAM_BYTES_PER_PARTICLE_STEP = 96.4    # measured, see roofline.traffic below
+L2_BYTES = 132644864                       # cudaDeviceProp::l2CacheSize of the B200 (the library's variant thresholds use it)
 
 
 def peaks():
@@ -191,7 +192,17 @@ def main():
     ms = pop.event_elapsed_ms(0, 1)
     barrier()
     launches = pop.launch_count() - l0
+    # the timed region lasts tens of milliseconds: too short for more than a few nvidia-smi samples.  Keep the sampler running
+    # over an UNTIMED continuation of the same workload (same kernel, same population) so that the clocks of every GPU under
+    # this load are on record: in a strong-scaling run one power-capped GPU sets the pace of all.
+    t_samples = len(sampler.rows) if rank == 0 else 0
+    extra = max(0, min(4000, int(400.0 / max(ms / args.steps, 1e-3))))          # ~0.4 s
+    t = pop.run_fixed("dde", t, H_STEP, extra)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["samples_in_timed_region"] = t_samples
+        clocks["note"] = "sampling continued over %d untimed steps of the same workload after the timed region" % extra
     if world > 1:
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -245,7 +256,8 @@ def main():
                              "peak_source": how, "algorithmic_bytes_per_particle_step": ALG_BYTES_PER_PARTICLE_STEP,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_local * args.steps,
                              "kernel": "k_chain_persist (one cooperative launch runs all timed RK4 steps: 4 stages per step, in-kernel mean-field exchange; "
-                                       + ("TMA ring + lean RK4 stages" if n_local * 32 > 1.5 * 126e6 else "plain loads + stored stages, L2-resident shard") + ")"}}
+                                       + ("TMA ring + lean RK4 stages" if n_local * 32 > 1.5 * L2_BYTES else "TMA ring + stored stages" if n_local * 32 > 0.9 * L2_BYTES
+                                          else "plain loads + stored stages, L2-resident shard") + ")"}}
         if world == 1 and not args.no_cpu:
             v, info = cpu_reference_sample(1 << 20, 16)
             line["cpu_baseline"] = dict(info, value=v, unit="particle-steps/s")
