@@ -231,6 +231,21 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
     e2e_value = n_total * ne2e / e2e_s
+    # the same path used the way odesolver uses it: ONE upload of the host state, args.steps RK4 steps, ONE download of the final
+    # state (information only; the contract's e2e above re-uploads the inputs for every step)
+    barrier()
+    w0 = time.perf_counter()
+    pop.upload_ptr(n_local, y_pin.data_ptr(), e_pin.data_ptr())
+    pop.run_fixed("dde", 0.0, H_STEP, args.steps)
+    fin = pop.download()
+    barrier()
+    sess_s = time.perf_counter() - w0
+    if world > 1:
+        ts_ = torch.tensor([sess_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        sess_s = float(ts_.item())
+    sess_bytes = (int(n_local * 16), int(sum(v.nbytes for v in fin.values())))
+    del fin
 
     if rank == 0:
         peak, how = peaks()
@@ -246,6 +261,8 @@ def main():
                            "parallelism": "particle sharding x%d, %%M sums per stage through %s" % (world, "NCCL allreduce" if args.no_peers else "in-kernel NVLink peer mailboxes"), "mean_fields_after": [float(x) for x in mfd]},
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(8 * lib.nmfd),
                         "steps": ne2e, "what": "odx_pop_upload(host theta, omega) + odx_run_fixed(dde, 1 step) + odx_meanfields per step"},
+                "e2e_session": {"value": n_total * args.steps / sess_s, "unit": "particle-steps/s", "steps": args.steps, "h2d_bytes_total": sess_bytes[0],
+                                "d2h_bytes_total": sess_bytes[1], "what": "one odx_pop_upload + odx_run_fixed(dde, %d steps) + one odx_pop_download (host wall clock)" % args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of k_chain_persist from the ncu --set full capture
