@@ -69,15 +69,26 @@ __global__ void __launch_bounds__(BLOCK) k_lr_stats(const double *__restrict__ x
     s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last) {                       /* the last block folds the block partials with all its threads, in a fixed order */
     __threadfence();
     double a = INFINITY, b = -INFINITY, c = 0.0;
-    for (unsigned int k = 0; k < gridDim.x; k++) {
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += BLOCK) {
       const double p0 = __ldcg(&partial[3 * k]), p1 = __ldcg(&partial[3 * k + 1]), p2 = __ldcg(&partial[3 * k + 2]);
       a = p0 < a ? p0 : a; b = p1 > b ? p1 : b; c += p2;
     }
-    stats[0] = a; stats[1] = b; stats[2] = c; stats[3] = -a;     /* [3] = -min so that one MAX allreduce covers min and max */
-    *counter = 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
+      a = a2 < a ? a2 : a; b = b2 > b ? b2 : b; c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();
+    if (lane == 0) { s_min[warp] = a; s_max[warp] = b; s_sum[warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < BLOCK / 32; w++) { a = s_min[w] < a ? s_min[w] : a; b = s_max[w] > b ? s_max[w] : b; c += s_sum[w]; }
+      stats[0] = a; stats[1] = b; stats[2] = c; stats[3] = -a;     /* [3] = -min so that one MAX allreduce covers min and max */
+      *counter = 0u;
+    }
   }
 }
 
@@ -271,11 +282,41 @@ __global__ void __launch_bounds__(BLOCK, 5) k_lr_moments(const double *__restric
  * stored pair-swizzled (pair index XOR particle index) so the transposing stores of the staging phase spread over the banks. */
 constexpr bool LR_WSPLIT = (LR_R == 64);
 constexpr int LR_WS_THREADS = 128, LR_WS_WARPS = 4, LR_WS_TILE = 32;
+__device__ __forceinline__ void lr_cp_async8(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+/* stage tile `base` into buffer b: V through cp.async (8-byte copies, transposed + pair-swizzled by the destination address),
+ * powers of xi by the first warp */
 template <int P1T>
-__global__ void __launch_bounds__(LR_WS_THREADS, 3) k_lr_moments_ws(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
+__device__ __forceinline__ void lr_stage_tile(double (*s_v)[64], double (*s_pw)[P1T], const double *__restrict__ x, const double *__restrict__ V,
+                                              int64_t vstride, int64_t n, int64_t base, int p1, double meanx, double range) {
+  const int cnt = (int)((n - base) < LR_WS_TILE ? (n - base) : LR_WS_TILE);
+#pragma unroll 2
+  for (int q = threadIdx.x; q < LR_WS_TILE * 64; q += LR_WS_THREADS) {
+    const int jj = q % LR_WS_TILE, m = q / LR_WS_TILE;                  /* coalesced along particles */
+    double *dst = &s_v[jj][(((m >> 1) ^ jj) << 1) | (m & 1)];
+    if (jj < cnt) lr_cp_async8(dst, V + (int64_t)m * vstride + base + jj);
+    else *dst = 0.0;
+  }
+  if (threadIdx.x < LR_WS_TILE) {
+    const int jj = threadIdx.x;
+    const double xi = (jj < cnt) ? (x[base + jj] - meanx) / range : 0.0;
+    double pw = 1.0;
+#pragma unroll
+    for (int k = 0; k < P1T; k++) { s_pw[jj][k] = (jj < cnt && k < p1) ? pw : 0.0; pw *= xi; }
+  }
+}
+constexpr int LR_WS_STAGES = 3;
+constexpr size_t lr_ws_smem_bytes(int p1t) { return sizeof(double) * LR_WS_STAGES * LR_WS_TILE * (64 + p1t); }
+template <int P1T>
+__global__ void __launch_bounds__(LR_WS_THREADS, P1T <= 16 ? 3 : 2) k_lr_moments_ws(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
                                                                     int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
-  __shared__ __align__(16) double s_v[LR_WS_TILE][64];
-  __shared__ __align__(16) double s_pw[LR_WS_TILE][P1T];
+  /* ring of LR_WS_STAGES buffers: the next tiles stream in (cp.async) while the FMAs of the current one run.  With one buffer
+   * the kernel spent most of its time waiting for the tile loads, with two the loads of tile t+1 (issued one tile of arithmetic,
+   * ~0.3 us, earlier) were still not back when tile t was done (ncu: barrier stalls at the wait). */
+  extern __shared__ __align__(16) unsigned char lr_ws_smem[];     /* dynamic: 54-66 KB, above the static limit */
+  double (*s_v)[LR_WS_TILE][64] = reinterpret_cast<double (*)[LR_WS_TILE][64]>(lr_ws_smem);
+  double (*s_pw)[LR_WS_TILE][P1T] = reinterpret_cast<double (*)[LR_WS_TILE][P1T]>(lr_ws_smem + sizeof(double) * LR_WS_STAGES * LR_WS_TILE * 64);
   const int p1 = plan->p + 1;
   if ((p1 + 7) / 8 * 8 != P1T) return;
   const double meanx = plan->meanx, range = plan->range;
@@ -283,38 +324,39 @@ __global__ void __launch_bounds__(LR_WS_THREADS, 3) k_lr_moments_ws(const double
   double acc[2][P1T];
 #pragma unroll
   for (int k = 0; k < P1T; k++) { acc[0][k] = 0.0; acc[1][k] = 0.0; }
-  for (int64_t base = (int64_t)blockIdx.x * LR_WS_TILE; base < n; base += (int64_t)gridDim.x * LR_WS_TILE) {
-    const int cnt = (int)((n - base) < LR_WS_TILE ? (n - base) : LR_WS_TILE);
-    __syncthreads();
-#pragma unroll 4
-    for (int q = threadIdx.x; q < LR_WS_TILE * 64; q += LR_WS_THREADS) {
-      const int jj = q % LR_WS_TILE, m = q / LR_WS_TILE;                  /* coalesced along particles */
-      const double v = (jj < cnt) ? V[(int64_t)m * vstride + base + jj] : 0.0;
-      s_v[jj][(((m >> 1) ^ jj) << 1) | (m & 1)] = v;
-    }
-    if (threadIdx.x < LR_WS_TILE) {
-      const int jj = threadIdx.x;
-      const double xi = (jj < cnt) ? (x[base + jj] - meanx) / range : 0.0;
-      double pw = 1.0;
+  const int64_t stride = (int64_t)gridDim.x * LR_WS_TILE;
+  const int64_t first = (int64_t)blockIdx.x * LR_WS_TILE;
 #pragma unroll
-      for (int k = 0; k < P1T; k++) { s_pw[jj][k] = (jj < cnt && k < p1) ? pw : 0.0; pw *= xi; }
-    }
+  for (int st = 0; st < LR_WS_STAGES - 1; st++) {             /* prologue: tiles 0 .. STAGES-2 in flight */
+    if (first + st * stride < n) lr_stage_tile<P1T>(s_v[st], s_pw[st], x, V, vstride, n, first + st * stride, p1, meanx, range);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int buf = 0, nbuf = LR_WS_STAGES - 1;
+  for (int64_t base = first; base < n; base += stride) {
+    const int64_t ahead = base + (LR_WS_STAGES - 1) * stride;
+    if (ahead < n) lr_stage_tile<P1T>(s_v[nbuf], s_pw[nbuf], x, V, vstride, n, ahead, p1, meanx, range);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(LR_WS_STAGES - 1) : "memory");
     __syncthreads();
 #pragma unroll 2
     for (int tq = 0; tq < LR_WS_TILE / LR_WS_WARPS; tq++) {
       const int jj = warp * (LR_WS_TILE / LR_WS_WARPS) + tq;
-      const double2 va = *reinterpret_cast<const double2 *>(&s_v[jj][(lane ^ jj) << 1]);
+      const double2 va = *reinterpret_cast<const double2 *>(&s_v[buf][jj][(lane ^ jj) << 1]);
 #pragma unroll
       for (int k = 0; k < P1T; k += 2) {
-        const double2 pk = *reinterpret_cast<const double2 *>(&s_pw[jj][k]);
+        const double2 pk = *reinterpret_cast<const double2 *>(&s_pw[buf][jj][k]);
         acc[0][k] = fma(va.x, pk.x, acc[0][k]); acc[1][k] = fma(va.y, pk.x, acc[1][k]);
         acc[0][k + 1] = fma(va.x, pk.y, acc[0][k + 1]); acc[1][k + 1] = fma(va.y, pk.y, acc[1][k + 1]);
       }
     }
+    __syncthreads();                      /* every warp is done with this buffer before a later iteration refills it */
+    if (++buf == LR_WS_STAGES) buf = 0;
+    if (++nbuf == LR_WS_STAGES) nbuf = 0;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   /* the four warps add their accumulators in warp order through shared memory (the staged tile is dead by now), then the CTA
    * writes ONE partial, layout q = k * 64 + m; orders >= P1T stay zero (the buffer is cleared by the host) */
-  double *s_red = &s_v[0][0];                       /* LR_WS_TILE * 64 = 2048 doubles >= P1T * 64 */
+  double *s_red = &s_v[0][0][0];                    /* LR_WS_TILE * 64 = 2048 doubles >= P1T * 64 */
   for (int w = 0; w < LR_WS_WARPS; w++) {
     __syncthreads();
     if (warp == w) {
@@ -359,11 +401,18 @@ __global__ void __launch_bounds__(128) k_lr_apply(const double *__restrict__ x, 
     const double nxi = -(x[i] - meanx) / range;
 #pragma unroll
     for (int k = 0; k < P1T; k++) ua[k] = 0.0;
-    constexpr int UB = (LR_R % 8 == 0) ? 8 : 1;              /* U values fetched ahead of their FMAs */
+    constexpr int UB = (LR_R % 8 == 0) ? 8 : 1;              /* U values fetched one batch ahead of their FMAs */
+    double un[UB];
+#pragma unroll
+    for (int q = 0; q < UB; q++) un[q] = U[(int64_t)q * ustride + i];
     for (int m = 0; m < LR_R; m += UB) {
       double u[UB];
 #pragma unroll
-      for (int q = 0; q < UB; q++) u[q] = U[(int64_t)(m + q) * ustride + i];
+      for (int q = 0; q < UB; q++) u[q] = un[q];
+      if (m + UB < LR_R) {
+#pragma unroll
+        for (int q = 0; q < UB; q++) un[q] = U[(int64_t)(m + UB + q) * ustride + i];
+      }
 #pragma unroll
       for (int q = 0; q < UB; q++) {
 #pragma unroll

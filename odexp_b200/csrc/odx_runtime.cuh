@@ -91,7 +91,7 @@ struct odx_handle {
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_attached = false;
   /* low-rank coupling scratch + options (opt lrmax / lrabstol / lrreltol) */
-  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr;
+  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr; bool lr_attr_done = false;
   int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
@@ -217,10 +217,17 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     npart = nblk;
     const double *Vc = h->E + (size_t)M::LR0_V * h->cap; const LrPlan *plm = (const LrPlan *)h->lr_plan;
     ODX_CUDA(h, cudaMemsetAsync(h->lr_apart, 0, sizeof(double) * (size_t)LR_R * LR_P1 * npart, h->stream));
-    k_lr_moments_ws<8><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<16><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<24><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<32><<<nblk, LR_WS_THREADS, 0, h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    if (!h->lr_attr_done) {                       /* the three-stage ring needs more than the 48 KB static limit */
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(8)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(16)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(24)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(32)));
+      h->lr_attr_done = true;
+    }
+    k_lr_moments_ws<8><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(8), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<16><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(16), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<24><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(24), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_ws<32><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(32), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
   } else {
     k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
     ODX_TRY(launch_check(h));
@@ -239,7 +246,9 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
   }
 #endif
-  int ga = (int)((n + 127) / 128); if (ga > 64 * h->sm_count) ga = 64 * h->sm_count; if (ga < 1) ga = 1;
+  /* a CTA first stages A (r x (p+1) doubles) and the coefficient table in shared memory: with one chunk of 128 particles per CTA
+   * that prologue cost as much as the chunk (ncu: long-scoreboard stalls, FP64 pipe 32 %); six resident CTAs per SM loop instead */
+  int ga = (int)((n + 127) / 128); if (ga > 6 * h->sm_count) ga = 6 * h->sm_count; if (ga < 1) ga = 1;
   const double *Uc = h->E + (size_t)M::LR0_U * h->cap; double *psi = h->PSI + (size_t)M::LR0_PSI * h->cap;
   const LrPlan *pl = (const LrPlan *)h->lr_plan;
   k_lr_apply<8><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
