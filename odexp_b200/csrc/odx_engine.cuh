@@ -570,14 +570,23 @@ __device__ __forceinline__ void tile_sweep(const Pop &p, int reverse, bool has_y
   tma_geometry(!has_ys, has_acc, ncol, tile_bytes, nbuf);
   const int64_t toff = (int64_t)tile * blockIdx.x + 2 * threadIdx.x;
   int bcur = 0;
+  /* shared-window addresses formed once per sweep and made opaque: left to itself the compiler re-derives them from the special
+   * registers (S2R CgaCtaId / SWINHI / TID.X + alignment arithmetic, ~10 instructions) in front of every pair of every tile */
+  uint32_t slot0 = 0, full_a = 0, empty_a = 0;
+  if (TMA) {
+    slot0 = ring.base + threadIdx.x * (uint32_t)sizeof(double2); full_a = ring.full_a; empty_a = ring.empty_a;
+    asm volatile("" : "+r"(slot0), "+r"(full_a), "+r"(empty_a));
+  }
   for (int k = 0; k < niter; k++) {
     const int kk = reverse ? (niter - 1 - k) : k;
     const int64_t i0 = (int64_t)kk * per_iter + toff;
+    int full_tile = (kk <= kfull);                      /* kept as a register: re-deriving it costs six instructions per pair */
+    if (TMA) asm volatile("" : "+r"(full_tile));
     uint32_t slot = 0;
     if (TMA) {
-      mbar_wait_warp_a(ring.full_a + 8u * bcur, (ring.full_par >> bcur) & 1u);
+      mbar_wait_warp_a(full_a + 8u * bcur, (ring.full_par >> bcur) & 1u);
       ring.full_par ^= 1u << bcur;
-      slot = ring.base + (uint32_t)bcur * tile_bytes + threadIdx.x * (uint32_t)sizeof(double2);
+      slot = slot0 + (uint32_t)bcur * tile_bytes;
     }
 #pragma unroll
     for (int q = 0; q < PPT; q++) {
@@ -596,10 +605,10 @@ __device__ __forceinline__ void tile_sweep(const Pop &p, int reverse, bool has_y
            * (without this fence a refill was observed to overtake the reads once in a few 10^5 tiles) */
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if ((threadIdx.x & 31) == 0) mbar_arrive_a(ring.empty_a + 8u * bcur);
+          if ((threadIdx.x & 31) == 0) mbar_arrive_a(empty_a + 8u * bcur);
           if (++bcur == nbuf) bcur = 0;
         }
-        if (kk <= kfull) { body(i, true, FullTile(), y0, e, psi, ys, acc); continue; }
+        if (full_tile) { body(i, true, FullTile(), y0, e, psi, ys, acc); continue; }
       } else {
         if (i >= p.n) continue;
         load_cols2<NVAR>(p.Y, p.stride, i, two, y0[0], y0[1]);

@@ -48,8 +48,16 @@ ODX_HD void odx_sincos(C &ctx, double x, double *sp, double *cp) {
 #else
   ctx.slow |= !(fabs(x) < 105615.0);
 #endif
+  /* round-to-nearest by the 1.5 * 2^52 shift: the quadrant is the low word of the shifted sum (no FRND / F2I, whose FP64 forms
+   * run at conversion-unit rate), valid far beyond the range bound above */
+#if defined(__CUDA_ARCH__)
+  const double qs = fma(x, T[0], 6755399441055744.0);
+  const int n = __double2loint(qs);
+  const double q = qs - 6755399441055744.0;
+#else
   const double q = rint(x * T[0]);
   const int n = (int)q;
+#endif
   double r = fma(-q, T[1], x);
   r = fma(-q, T[2], r);
   r = fma(-q, T[3], r);
