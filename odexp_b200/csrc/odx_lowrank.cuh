@@ -373,6 +373,254 @@ __global__ void __launch_bounds__(LR_WS_THREADS, P1T <= 16 ? 3 : 2) k_lr_moments
   for (int q = threadIdx.x; q < P1T * 64; q += LR_WS_THREADS) dst[q] = s_red[q];
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * rank-64 path (BASELINE config 3): TMA-staged tiles, FP64 tensor-core contractions.
+ *
+ * Both contractions are dense skinny GEMMs that stream a 64-column array once.  The warps that do the arithmetic never issue a
+ * global load: a producer warp fetches the column runs of the next tiles with cp.async.bulk into a ring of shared-memory
+ * buffers (mbarrier complete_tx = "tile landed", one arrival per consumer warp = "slot free").  The first version did the
+ * arithmetic as DFMAs fed by 16-byte broadcast reads; ncu showed it bound by the shared-memory pipe (a broadcast LDS.128 costs
+ * ~3 cycles and feeds two DFMAs: 25-34 % FP64 pipe, short-scoreboard stalls).  DMMA (mma.sync m8n8k4, f64) has the same peak rate
+ * as DFMA on B200 but needs one 8-byte operand read per 8 FMAs of a lane, so the operand traffic drops fourfold; this is the one
+ * place of the hot path that is a dense contraction, hence the one place that uses tensor cores.
+ *
+ * Fragment layout of mma.m8n8k4 (g = lane >> 2, t = lane & 3): A[g][t], B[t][g], C[g][2t], C[g][2t+1].  Row strides are = 4
+ * (mod 16) doubles, which makes every fragment read conflict-free.
+ *
+ * k_lr_moments_tma: A[m][k] = sum_j V[m][j] xi_j^k  (M = 64 columns, N = P1T orders, K = particles).  The ring holds chunks of 16
+ * column runs of V for a batch of 256 particles (2 KB per run: 512-byte runs kept the TMA unit, not HBM, busy); four chunks make
+ * a batch.  Each of the 8 consumer warps takes 32 particles of the batch (eight K-steps) and keeps all 64 x P1T accumulators.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+constexpr int LRT_PT = 256, LRT_SU = LRT_PT + 4, LRT_CH = 16, LRT_CW = LRT_PT / 32, LRT_THREADS = LRT_PT + 32, LRT_STAGES = 4;
+constexpr size_t lrt_smem_bytes(int p1t) {
+  return sizeof(double) * ((size_t)LRT_STAGES * LRT_CH * LRT_SU + (size_t)LRT_PT * (p1t + 4)) + 2 * LRT_STAGES * sizeof(uint64_t);
+}
+template <int P1T>
+__global__ void __launch_bounds__(LRT_THREADS, 1) k_lr_moments_tma(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
+                                                                 int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char lrt_smem[];
+  const int p1 = plan->p + 1;
+  if ((p1 + 7) / 8 * 8 != P1T) return;
+  constexpr int SP = P1T + 4, NB = P1T / 8, NCH = 64 / LRT_CH;
+  double *s_v = reinterpret_cast<double *>(lrt_smem);                          /* ring: [stage][16 runs][256 + 4] */
+  double (*s_pw)[SP] = reinterpret_cast<double (*)[SP]>(s_v + (size_t)LRT_STAGES * LRT_CH * LRT_SU);      /* [particle of the batch][k] */
+  uint64_t *s_full = reinterpret_cast<uint64_t *>(&s_pw[LRT_PT][0]), *s_empty = s_full + LRT_STAGES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < LRT_STAGES; b++) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, LRT_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nbatch = (n + LRT_PT - 1) / LRT_PT;
+  double acc[8][NB][2];
+#pragma unroll
+  for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+  if (warp == LRT_CW) {                                         /* producer: lanes 0..15 issue the 16 runs (2 KB each) of a chunk */
+    int it = 0;
+    for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+      const int64_t base = bt * LRT_PT;
+      int64_t cnt = n - base; if (cnt > LRT_PT) cnt = LRT_PT;
+      const uint32_t bytes = (uint32_t)(((cnt + 1) & ~(int64_t)1) * sizeof(double));     /* whole 16-byte units; columns are padded */
+      for (int c = 0; c < NCH; c++, it++) {
+        const int b = it % LRT_STAGES;
+        if (it >= LRT_STAGES) mbar_wait(s_empty + b, (uint32_t)((it / LRT_STAGES - 1) & 1));
+        if (lane == 0) mbar_expect_tx(s_full + b, bytes * (uint32_t)LRT_CH);
+        __syncwarp();
+        if (lane < LRT_CH)
+          bulk_g2s(s_v + ((size_t)b * LRT_CH + lane) * LRT_SU, V + (int64_t)(c * LRT_CH + lane) * vstride + base, bytes, s_full + b);
+      }
+    }
+  } else {
+    const double meanx = plan->meanx, range = plan->range;
+    int it = 0;
+    const int64_t first = (int64_t)blockIdx.x * LRT_PT + threadIdx.x;
+    double xnext = (first < n) ? x[first] : 0.0;
+    for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+      const int64_t i = bt * LRT_PT + threadIdx.x;              /* powers of this lane's particle: the reference's product order */
+      {
+        const double xi = (xnext - meanx) / range;
+        const bool valid = i < n;
+        double pw = 1.0;
+#pragma unroll
+        for (int k = 0; k < P1T; k++) { s_pw[threadIdx.x][k] = (valid && k < p1) ? pw : 0.0; pw *= xi; }
+        const int64_t inext = i + (int64_t)gridDim.x * LRT_PT;  /* x of the next batch: its latency hides behind this one */
+        xnext = (inext < n) ? x[inext] : 0.0;
+      }
+      __syncwarp();
+      const int64_t wleft = n - (bt * LRT_PT + warp * 32);      /* particles of this warp inside the population */
+#pragma unroll
+      for (int c = 0; c < NCH; c++, it++) {
+        const int b = it % LRT_STAGES;
+        mbar_wait_warp_a(smem_u32(s_full + b), (uint32_t)((it / LRT_STAGES) & 1));
+        const double *vb = s_v + (size_t)b * LRT_CH * LRT_SU + g * LRT_SU + warp * 32 + t;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          const bool valid = (4 * ks + t) < wleft;              /* beyond the population the slot holds stale bytes */
+          double bf[NB];
+#pragma unroll
+          for (int nb = 0; nb < NB; nb++) bf[nb] = s_pw[warp * 32 + 4 * ks + t][8 * nb + g];
+#pragma unroll
+          for (int ml = 0; ml < LRT_CH / 8; ml++) {
+            double a = vb[ml * 8 * LRT_SU + 4 * ks];
+            a = valid ? a : 0.0;
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) dmma884(acc[c * (LRT_CH / 8) + ml][nb][0], acc[c * (LRT_CH / 8) + ml][nb][1], a, bf[nb]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + b);
+      }
+    }
+  }
+  /* the consumer warps add their accumulators in warp order through shared memory (the ring is dead by now), then the CTA
+   * writes ONE partial, layout q = k * 64 + m; orders >= P1T stay zero (the buffer is cleared by the host) */
+  __syncthreads();
+  double *s_red = s_v;                                          /* P1T * 64 doubles <= one ring slot */
+  for (int w = 0; w < LRT_CW; w++) {
+    if (warp == w) {
+#pragma unroll
+      for (int mb = 0; mb < 8; mb++)
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            double *slot = &s_red[(8 * nb + 2 * t + e) * 64 + 8 * mb + g];
+            if (w == 0) *slot = acc[mb][nb][e]; else *slot += acc[mb][nb][e];
+          }
+    }
+    __syncthreads();
+  }
+  double *dst = partial + (size_t)blockIdx.x * LR_R * LR_P1;
+  for (int q = threadIdx.x; q < P1T * 64; q += LRT_THREADS) dst[q] = s_red[q];
+}
+
+/* k_lr_apply_tma: UA[i][k] = sum_m U[m][i] A[m][k] (M = particles, N = P1T orders, K = 64 columns), then
+ * psi_i = sum_k UA[i][k] phi_k(-xi_i).  The ring holds chunks of 16 column runs of U for a batch of 256 particles; four chunks
+ * make a batch, a warp owns 32 particles of it.  The accumulator fragments leave particle i = 8 ib + g and orders 2t, 2t+1 (per
+ * block of 8) in lane (g, t); phi_k(-xi_i) is produced in the same layout by one more small contraction (see the tail). */
+constexpr int LRA_PT = 256, LRA_SU = LRA_PT + 4, LRA_CH = 16, LRA_CW = LRA_PT / 32, LRA_THREADS = LRA_PT + 32, LRA_STAGES = 4;
+constexpr size_t lra_smem_bytes(int p1t) {
+  return sizeof(double) * ((size_t)LRA_STAGES * LRA_CH * LRA_SU + (size_t)(64 + p1t) * (p1t + 4)) + 2 * LRA_STAGES * sizeof(uint64_t);
+}
+template <int P1T>
+__global__ void __launch_bounds__(LRA_THREADS, 1) k_lr_apply_tma(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride,
+                                                               int64_t n, const LrPlan *__restrict__ plan, const double *__restrict__ A,
+                                                               double *__restrict__ psi) {
+  extern __shared__ __align__(16) unsigned char lra_smem[];
+  const int p1 = plan->p + 1;
+  if ((p1 + 7) / 8 * 8 != P1T) return;
+  constexpr int SA = P1T + 4, NB = P1T / 8, NCH = 64 / LRA_CH;
+  double *s_u = reinterpret_cast<double *>(lra_smem);
+  double (*s_A)[SA] = reinterpret_cast<double (*)[SA]>(s_u + (size_t)LRA_STAGES * LRA_CH * LRA_SU);       /* [m][k] */
+  double (*s_BCt)[SA] = reinterpret_cast<double (*)[SA]>(&s_A[64][0]);       /* [d][k] = BC[k+d][k] */
+  uint64_t *s_full = reinterpret_cast<uint64_t *>(&s_BCt[P1T][0]), *s_empty = s_full + LRA_STAGES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < LRA_STAGES; b++) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, LRA_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nbatch = (n + LRA_PT - 1) / LRA_PT;
+  if (warp == LRA_CW) {                                         /* producer: lanes 0..15 issue the 16 runs of a chunk */
+    int it = 0;
+    for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+      const int64_t base = bt * LRA_PT;
+      int64_t cnt = n - base; if (cnt > LRA_PT) cnt = LRA_PT;
+      const uint32_t bytes = (uint32_t)(((cnt + 1) & ~(int64_t)1) * sizeof(double));
+      for (int c = 0; c < NCH; c++, it++) {
+        const int b = it % LRA_STAGES;
+        if (it >= LRA_STAGES) mbar_wait(s_empty + b, (uint32_t)((it / LRA_STAGES - 1) & 1));
+        if (lane == 0) mbar_expect_tx(s_full + b, bytes * (uint32_t)LRA_CH);
+        __syncwarp();
+        if (lane < LRA_CH)
+          bulk_g2s(s_u + ((size_t)b * LRA_CH + lane) * LRA_SU, U + (int64_t)(c * LRA_CH + lane) * ustride + base, bytes, s_full + b);
+      }
+    }
+    return;
+  }
+  /* consumers (a named barrier keeps the producer warp out of their synchronisation) */
+  for (int q = threadIdx.x; q < P1T * 64; q += LRA_PT) s_A[q % 64][q / 64] = A[q];
+  for (int q = threadIdx.x; q < P1T * P1T; q += LRA_PT) {
+    const int d = q / P1T, k = q % P1T;
+    s_BCt[d][k] = (k + d < p1) ? plan->BC[k + d][k] : 0.0;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(LRA_PT) : "memory");
+  const double meanx = plan->meanx, range = plan->range;
+  int it = 0;
+  double xnext[4];
+#pragma unroll
+  for (int ib = 0; ib < 4; ib++) {
+    const int64_t i = (int64_t)blockIdx.x * LRA_PT + warp * 32 + ib * 8 + g;
+    xnext[ib] = (i < n) ? x[i] : 0.0;
+  }
+  for (int64_t bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
+    const int64_t i0 = bt * LRA_PT + warp * 32 + g;
+    double nxi[4];
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++) {
+      nxi[ib] = -(xnext[ib] - meanx) / range;
+      const int64_t inext = i0 + (int64_t)gridDim.x * LRA_PT + ib * 8;         /* x of the next batch: its latency hides behind this one */
+      xnext[ib] = (inext < n) ? x[inext] : 0.0;
+    }
+    double ua[4][NB][2];
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++)
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) { ua[ib][nb][0] = 0.0; ua[ib][nb][1] = 0.0; }
+    for (int c = 0; c < NCH; c++, it++) {
+      const int b = it % LRA_STAGES;
+      mbar_wait_warp_a(smem_u32(s_full + b), (uint32_t)((it / LRA_STAGES) & 1));
+      const double *ub = s_u + (size_t)b * LRA_CH * LRA_SU + warp * 32 + g;
+#pragma unroll
+      for (int ks = 0; ks < LRA_CH / 4; ks++) {
+        double bf[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) bf[nb] = s_A[c * LRA_CH + 4 * ks + t][8 * nb + g];
+#pragma unroll
+        for (int ib = 0; ib < 4; ib++) {
+          const double a = ub[(4 * ks + t) * LRA_SU + ib * 8];
+#pragma unroll
+          for (int nb = 0; nb < NB; nb++) dmma884(ua[ib][nb][0], ua[ib][nb][1], a, bf[nb]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + b);
+    }
+    /* phi_k(nxi_i) = sum_d nxi_i^d BC[k+d][k] is one more small contraction (M = particles, K = d, N = orders) whose result has
+     * the fragment layout of UA: psi_i = sum_k UA[i][k] phi_k is a dot product inside the lane and a sum over the quad.  (As
+     * Horner loops per lane this tail was two thirds of the kernel's instructions.)  Blocks with 4 db + 8 nb >= P1T are zero. */
+#pragma unroll
+    for (int ib = 0; ib < 4; ib++) {
+      const double z = nxi[ib], z2 = z * z, z3 = z2 * z, z4 = z2 * z2;
+      double a = (t == 0) ? 1.0 : (t == 1) ? z : (t == 2) ? z2 : z3;             /* nxi^(4 db + t) */
+      double phi[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) { phi[nb][0] = 0.0; phi[nb][1] = 0.0; }
+#pragma unroll
+      for (int db = 0; db < P1T / 4; db++) {
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+          if (4 * db + 8 * nb < P1T) dmma884(phi[nb][0], phi[nb][1], a, s_BCt[4 * db + t][8 * nb + g]);
+        a *= z4;
+      }
+      double y = 0.0;
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) { y = fma(phi[nb][0], ua[ib][nb][0], y); y = fma(phi[nb][1], ua[ib][nb][1], y); }
+      y += __shfl_xor_sync(0xffffffffu, y, 1);
+      y += __shfl_xor_sync(0xffffffffu, y, 2);
+      const int64_t i = i0 + ib * 8;
+      if (t == 0 && i < n) psi[i] = y;
+    }
+  }
+}
+
 /* fixed-order sum of groups of partials: out[g][q] = sum_{b in group g} in[b][q]; called twice (groups of 32, then all) */
 __global__ void __launch_bounds__(BLOCK) k_lr_moments_sum(const double *__restrict__ in, int nin, int group, double *__restrict__ out) {
   const int q = blockIdx.x * BLOCK + threadIdx.x, g = blockIdx.y;

@@ -211,23 +211,27 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   ODX_TRY(launch_check(h));
   int npart = nblk;
   if (LR_WSPLIT) {
-    nblk = (int)((n + LR_WS_TILE - 1) / LR_WS_TILE);
-    if (nblk > 6 * h->sm_count) nblk = 6 * h->sm_count;
+    const int64_t ntiles = (n + LRT_PT - 1) / LRT_PT;
+    nblk = ntiles < h->sm_count ? (int)ntiles : h->sm_count;     /* persistent: one CTA per SM, batches strided over the grid */
     if (nblk < 1) nblk = 1;
     npart = nblk;
     const double *Vc = h->E + (size_t)M::LR0_V * h->cap; const LrPlan *plm = (const LrPlan *)h->lr_plan;
     ODX_CUDA(h, cudaMemsetAsync(h->lr_apart, 0, sizeof(double) * (size_t)LR_R * LR_P1 * npart, h->stream));
-    if (!h->lr_attr_done) {                       /* the three-stage ring needs more than the 48 KB static limit */
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(8)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(16)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(24)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_ws<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lr_ws_smem_bytes(32)));
+    if (!h->lr_attr_done) {                       /* the rings need more than the 48 KB static limit */
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(8)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(16)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(24)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(32)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(8)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(16)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(24)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(32)));
       h->lr_attr_done = true;
     }
-    k_lr_moments_ws<8><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(8), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<16><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(16), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<24><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(24), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_ws<32><<<nblk, LR_WS_THREADS, lr_ws_smem_bytes(32), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_tma<8><<<nblk, LRT_THREADS, lrt_smem_bytes(8), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_tma<16><<<nblk, LRT_THREADS, lrt_smem_bytes(16), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_tma<24><<<nblk, LRT_THREADS, lrt_smem_bytes(24), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_tma<32><<<nblk, LRT_THREADS, lrt_smem_bytes(32), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
   } else {
     k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
     ODX_TRY(launch_check(h));
@@ -251,6 +255,15 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   int ga = (int)((n + 127) / 128); if (ga > 6 * h->sm_count) ga = 6 * h->sm_count; if (ga < 1) ga = 1;
   const double *Uc = h->E + (size_t)M::LR0_U * h->cap; double *psi = h->PSI + (size_t)M::LR0_PSI * h->cap;
   const LrPlan *pl = (const LrPlan *)h->lr_plan;
+  if (LR_WSPLIT) {
+    const int64_t nbatch = (n + LRA_PT - 1) / LRA_PT;
+    const int gt = nbatch < h->sm_count ? (nbatch < 1 ? 1 : (int)nbatch) : h->sm_count;
+    k_lr_apply_tma<8><<<gt, LRA_THREADS, lra_smem_bytes(8), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+    k_lr_apply_tma<16><<<gt, LRA_THREADS, lra_smem_bytes(16), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+    k_lr_apply_tma<24><<<gt, LRA_THREADS, lra_smem_bytes(24), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
+    k_lr_apply_tma<32><<<gt, LRA_THREADS, lra_smem_bytes(32), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi);
+    return launch_check(h);
+  }
   k_lr_apply<8><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
   k_lr_apply<16><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
   k_lr_apply<24><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));

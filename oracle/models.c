@@ -99,6 +99,26 @@ static void klr_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = 2 * LPI * orc_rand01(c);
 }
 
+/* ---------------------------------------------------------------- kuramoto_lowrank64.pop (LET R 64, LET N 1048576) */
+#define LR64_R 64
+static void klr64_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                      double *aux, double *death, double *repli) {
+  const double K = c->mu[0], omega = e[0], theta = y_[0], CPL = psi[0];
+  const double y = sin(theta);
+  const double cpl = CPL;
+  (void)t; (void)mfd; (void)death; (void)repli;
+  f[0] = omega + K / 1048576 * CPL;
+  aux[0] = y; aux[1] = cpl;
+}
+static void klr64_ic(orc_ctx *c, double t, double *y, double *e) {
+  int i;
+  (void)t;
+  e[0] = orc_randN(c, 2 * LPI / 10.0, 0.1);
+  for (i = 0; i < LR64_R; i++) e[1 + i] = orc_rand01(c);
+  for (i = 0; i < LR64_R; i++) e[1 + LR64_R + i] = orc_rand01(c);
+  y[0] = 2 * LPI * orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- logistic_map.pop */
 static const double lm_pars[] = {3.7, 0.1};
 static void lm_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -170,6 +190,7 @@ static const orc_model MODELS[] = {
   {"nbody", 6, 0, 0, 3, 0, 1, nb_pars, nb_rhs, NULL, NULL, nb_cpl, nb_ic, 0, 0, 0, 0, 0, NULL},
   {"vdp_sde", 2, 0, 0, 0, 0, 4, vdp_pars, vdp_rhs, NULL, vdp_birth, NULL, vdp_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank", 1, 1 + 2 * LR_R, 2, 1, 2, 1, klr_pars, klr_rhs, klr_mfd, NULL, NULL, klr_ic, LR_R, 0, 0, 1, 1 + LR_R, sin},
+  {"kuramoto_lowrank64", 1, 1 + 2 * LR64_R, 2, 1, 2, 1, klr_pars, klr64_rhs, klr_mfd, NULL, NULL, klr64_ic, LR64_R, 0, 0, 1, 1 + LR64_R, sin},
 };
 const orc_model *orc_find_model(const char *name) {
   unsigned i;

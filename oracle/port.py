@@ -14,6 +14,7 @@ METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5}
 DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0),
         "vdp_sde": dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0),
         "kuramoto_lowrank": dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=17),
+        "kuramoto_lowrank64": dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=129),
         "logistic_map": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1),
         "reset_decay": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1),
         "ring_diffusion": dict(nvar=2, naux=1, npsi=0, nmfd=1, nexpr=1)}

@@ -48,3 +48,27 @@ def test_lowrank_matches_direct_sum(model_lib):
     pop.close()
     # lrabstol / lrreltol = 1e-6 of the reference bound the truncation error of the expansion
     assert np.abs(psi - direct).max() <= 1e-4 * np.abs(direct).max()
+
+
+@pytest.mark.parametrize("ps", [203, 3001, 8192])
+def test_lowrank_rank64_matches_restatement(model_lib, ps):
+    """the rank-64 kernels of BASELINE config 3 (TMA-staged moment / apply contractions) at ragged sizes: fewer particles than
+    one tile, an odd count, whole tiles; the restatement is pinned to the reference binary for this fixture (test_oracle_port)"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto_lowrank64")
+    opts = {"meth": "dde", "h0": 0.1, "res": 3, "ps": ps}
+    pop = capi.Population(lib, capacity=max(1024, ps))
+    out = capi.odesolver(pop, (0, 0.4), meth="dde", res=3, popsize=ps, h0=0.1, replay_ic=True)
+    pop.close()
+    ref = port.run("kuramoto_lowrank64", opts, (0, 0.4))
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb)
+    np.testing.assert_array_equal(ta["id"], tb["id"])
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, 6:], tb[tb["step"] == 0]["cols"][:, 6:])     # omega, U, V
+    psi_a, psi_b = ta["cols"][:, 3], tb["cols"][:, 3]
+    scale = np.abs(psi_b).max()
+    print("max |dpsi|/scale", np.abs(psi_a - psi_b).max() / scale)
+    assert np.abs(psi_a - psi_b).max() <= 1e-8 * scale
+    np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)

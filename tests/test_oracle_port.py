@@ -40,6 +40,7 @@ REF_CASES = [
     # low-rank %C coupling (src/lrexp.c): restated lrexpars / lrexprank / lrexpwp
     ("kuramoto_lowrank", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 256}, (0, 0.4)),
     ("kuramoto_lowrank", {"meth": "rkck", "res": 3, "ps": 300}, (0, 1.0)),
+    ("kuramoto_lowrank64", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 203}, (0, 0.4)),        # rank 64 (BASELINE config 3)
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
