@@ -6,12 +6,13 @@
  * generated gather / scatter src/odexp:1565-1594.  Same algorithm (Chebyshev fit of f on [-range, range] converted to the
  * monomial basis), laid out for the GPU:
  *   k_lr_stats    min / max / sum of x over the population                      (HBM stream, 8 B per particle)
- *   k_lr_plan     one CTA: mean, range, adaptive order p, cc[], B[l], B[l]*C(l,k) (tiny)
- *   k_lr_moments  A[m][k] = sum_j V_jm xi_j^k: block partials of an r x (p+1) reduction over particles, fixed-order sum
- *   k_lr_apply    psi_i = sum_k (sum_m U_im A[m][k]) (sum_{l>=k} B[l] C(l,k) (-xi_i)^(l-k))
+ *   k_lr_rank_plan  mean, range, adaptive order p (fit + sample sums on the whole grid), cc[], B[l], B[l]*C(l,k)
+ *   k_lr_moments    A[m][k] = sum_j V_jm xi_j^k: block partials of an r x (p+1) reduction over particles, fixed-order sum
+ *   k_lr_apply      psi_i = sum_k (sum_m U_im A[m][k]) (sum_{l>=k} B[l] C(l,k) (-xi_i)^(l-k))
  * The two contractions are skinny FP64 GEMMs (K = N, then K = r) that stream U and V once (16 N r bytes); with r = 64,
  * p + 1 <= 32 their arithmetic intensity is (p+1)/4 flop per byte, i.e. HBM-bound below p + 1 ~ 23 and FP64-bound above.
- * They run as FP64 FMA on the CUDA cores: B200's FP64 tensor rate equals its CUDA-core rate, so DMMA would buy nothing.
+ * Rank 64 (BASELINE config 3) runs them on the FP64 tensor cores from TMA-staged tiles (k_lr_moments_tma, k_lr_apply_tma below):
+ * same peak as DFMA, a quarter of the operand traffic; other ranks use the CUDA-core kernels k_lr_moments / k_lr_apply.
  */
 #pragma once
 
@@ -29,21 +30,40 @@ struct LrPlan {
   double cc[LR_P1], B[LR_P1], BC[LR_P1][LR_P1];
 };
 
-/* gsl_cheb_init restated: c_j = (2/(n+1)) sum_k f(cos(pi (k+1/2)/(n+1)) * range) cos(pi j (k+1/2)/(n+1)) on [-range, range] */
-__device__ void lr_cheb_init(int order, double range, double *fk, double *c) {
+/* gsl_cheb_init restated: c_j = (2/(n+1)) sum_k f(cos(pi (k+1/2)/(n+1)) * range) cos(pi j (k+1/2)/(n+1)) on [-range, range].
+ * The (order+1)^2 cosines are spread over the CTA (prod[j][k]); the sum over k then runs in the reference's order. */
+__device__ void lr_cheb_init(int order, double range, double *fk, double *c, double (*prod)[LR_P1]) {
   for (int k = threadIdx.x; k <= order; k += blockDim.x) {
     const double y = cos(M_PI * (k + 0.5) / (order + 1));
     fk[k] = M::lr0_fun(y * range + 0.0);
   }
   __syncthreads();
+  const int o1 = order + 1;
+  for (int q = threadIdx.x; q < o1 * o1; q += blockDim.x) {
+    const int j = q / o1, k = q % o1;
+    prod[j][k] = fk[k] * cos(M_PI * j * (k + 0.5) / (order + 1));
+  }
+  __syncthreads();
   const double fac = 2.0 / (order + 1.0);
   for (int j = threadIdx.x; j <= order; j += blockDim.x) {
     double sum = 0.0;
-    for (int k = 0; k <= order; k++) sum += fk[k] * cos(M_PI * j * (k + 0.5) / (order + 1));
+    for (int k = 0; k <= order; k++) sum += prod[j][k];
     c[j] = fac * sum;
   }
   __syncthreads();
 }
+
+/* Chebyshev polynomials in the monomial basis, T_{n+1} = 2 x T_n - T_{n-1}: exact in 64-bit integers up to n = 50; built at
+ * compile time (as a serial loop of one thread it was most of k_lr_plan's 29 us) */
+struct LrTC { long long v[LR_P1][LR_P1]; };
+constexpr LrTC lr_make_tc() {
+  LrTC tc{};
+  tc.v[0][0] = 1; tc.v[1][1] = 1;
+  for (int n = 1; n + 1 < LR_P1; n++)
+    for (int l = 0; l <= n + 1; l++) tc.v[n + 1][l] = (l > 0 ? 2 * tc.v[n][l - 1] : 0) - tc.v[n - 1][l];
+  return tc;
+}
+__device__ const LrTC lr_tc = lr_make_tc();
 
 __global__ void __launch_bounds__(BLOCK) k_lr_stats(const double *__restrict__ x, int64_t n, double *partial, unsigned int *counter,
                                                      double *stats) {
@@ -92,18 +112,26 @@ __global__ void __launch_bounds__(BLOCK) k_lr_stats(const double *__restrict__ x
   }
 }
 
-/* lrexprank, part 1 (one CTA): Chebyshev fit of f at the maximal order on [-range, range], parity of f, candidate orders */
 constexpr int LR_NCAND = 12;
 struct LrRank {
   double c[LR_P1];            /* fit at order pmax */
   int p0, pstep, ncand;       /* candidates p0 + pstep * (1..ncand), capped at pmax */
-  double spe[LR_NCAND];       /* sum_i |series_p(x_i)| over the errn sample points, per candidate (filled by k_lr_rank_spe) */
+  double spe[LR_NCAND];       /* sum_i |series_p(x_i)| over the errn sample points, per candidate */
 };
-__global__ void __launch_bounds__(BLOCK) k_lr_rank_fit(const double *__restrict__ stats, int pmax, LrRank *rk) {
-  __shared__ double s_f[LR_P1], s_c[LR_P1];
+/* lrexprank + the coefficient work of lrexpwp in one launch (as three kernels -- fit on one CTA, sample sums on the grid, plan on one
+ * CTA -- they cost ~29 us as a dependent chain): every CTA
+ * repeats the fit at the maximal order (same bits everywhere), adds its share of the sample sums, and the last CTA to finish
+ * selects the order and writes the plan.  rk->spe and the counter are left zeroed for the next call. */
+__global__ void __launch_bounds__(BLOCK) k_lr_rank_plan(const double *__restrict__ stats, double n_global, int pmax, double abstol, double reltol,
+                                                         LrRank *rk, unsigned int *counter, LrPlan *plan) {
+  __shared__ double s_f[LR_P1], s_c[LR_P1], s_c2[LR_P1], s_prod[LR_P1][LR_P1], s_B[LR_P1];
+  __shared__ double s_red[BLOCK / 32][LR_NCAND];
+  __shared__ int s_p0, s_pstep, s_ncand, s_p;
+  __shared__ bool s_last;
+  const double meanx = stats[2] / n_global;
   double range = stats[1] - (-stats[3]);
   if (range == 0.0) range = 1.0;
-  lr_cheb_init(pmax, range, s_f, s_c);
+  lr_cheb_init(pmax, range, s_f, s_c, s_prod);
   if (threadIdx.x == 0) {
     double sc = 0.0; int oddity = 2;
     for (int i = 0; i < pmax + 1; i += 2) sc += fabs(s_c[i]);
@@ -112,27 +140,14 @@ __global__ void __launch_bounds__(BLOCK) k_lr_rank_fit(const double *__restrict_
     if (sc < (double)pmax / 2 * 1e-8) oddity = 0;
     int pstep = 4, p0;
     if (oddity == 0) p0 = 0; else if (oddity == 1) p0 = -1; else { p0 = -1; pstep = 3; }
-    rk->p0 = p0; rk->pstep = pstep;
     int nc = 0;
     for (int p = p0 + pstep; nc < LR_NCAND; p += pstep) { nc++; if (p >= pmax) break; }
-    rk->ncand = nc;
-    for (int i = 0; i < LR_NCAND; i++) rk->spe[i] = 0.0;
-    for (int i = 0; i <= pmax; i++) rk->c[i] = s_c[i];
+    s_p0 = p0; s_pstep = pstep; s_ncand = nc;
   }
-}
-/* part 2 (whole grid): spe_p = sum over the errn sample points of |series truncated at order p|, for every candidate p at once.
- * The reference walks the candidates one after the other and stops at the first that passes; evaluating all of them costs
- * errn * sum(p) FMAs spread over the GPU instead of a serial loop on one CTA. */
-__global__ void __launch_bounds__(BLOCK) k_lr_rank_spe(const double *__restrict__ stats, double n_global, int pmax, LrRank *rk) {
-  __shared__ double s_c[LR_P1];
-  __shared__ double s_red[BLOCK / 32][LR_NCAND];
-  if (threadIdx.x <= pmax) s_c[threadIdx.x] = rk->c[threadIdx.x];
   __syncthreads();
-  double range = stats[1] - (-stats[3]);
-  if (range == 0.0) range = 1.0;
   const long long ng = (long long)n_global;
   const long long errn = (ng / 10 > 10) ? ng / 10 : 10;
-  const int ncand = rk->ncand, p0 = rk->p0, pstep = rk->pstep;
+  const int ncand = s_ncand, p0 = s_p0, pstep = s_pstep;
   double spe[LR_NCAND];
 #pragma unroll
   for (int q = 0; q < LR_NCAND; q++) spe[q] = 0.0;
@@ -162,52 +177,43 @@ __global__ void __launch_bounds__(BLOCK) k_lr_rank_spe(const double *__restrict_
     for (int w = 0; w < BLOCK / 32; w++) v += s_red[w][threadIdx.x];
     atomicAdd(&rk->spe[threadIdx.x], v);
   }
-}
-/* part 3 (one CTA): first candidate that passes err/errn <= abstol + reltol * spe (or the last one), then lrexpwp's
- * coefficient work: refit at order p, cc[0] /= 2, B[l] = sum_{k>=l} cc[k] TC[k][l], BC[l][k] = B[l] C(l,k) */
-__global__ void __launch_bounds__(BLOCK) k_lr_plan(const double *__restrict__ stats, double n_global, int pmax, double abstol, double reltol,
-                                                    const LrRank *__restrict__ rk, LrPlan *plan) {
-  __shared__ double s_f[LR_P1], s_c[LR_P1];
-  __shared__ long long s_tc[LR_P1][LR_P1];
-  __shared__ int s_p;
-  const double meanx = stats[2] / n_global;
-  double range = stats[1] - (-stats[3]);
-  if (range == 0.0) range = 1.0;
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(counter, 1u) == gridDim.x - 1); }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x == 0) {
-    /* Chebyshev polynomials in the monomial basis: T_{n+1} = 2 x T_n - T_{n-1} (exact in 64-bit integers up to n = 50) */
-    for (int a = 0; a < LR_P1; a++) for (int b = 0; b < LR_P1; b++) s_tc[a][b] = 0;
-    s_tc[0][0] = 1; s_tc[1][1] = 1;
-    for (int n = 1; n + 1 < LR_P1; n++)
-      for (int l = 0; l <= n + 1; l++) s_tc[n + 1][l] = (l > 0 ? 2 * s_tc[n][l - 1] : 0) - s_tc[n - 1][l];
-    const long long ng = (long long)n_global;
-    const long long errn = (ng / 10 > 10) ? ng / 10 : 10;
-    int p = rk->p0;
-    for (int q = 0; q < rk->ncand; q++) {
-      p = rk->p0 + rk->pstep * (q + 1);
+    int p = p0;
+    for (int q = 0; q < ncand; q++) {
+      p = p0 + pstep * (q + 1);
       const int eo = p < pmax ? p : pmax;
       double absc = 0.0;
-      for (int i = 0; i <= eo; i++) absc += fabs(rk->c[i]);
-      const double abserr = fabs(rk->c[eo]) + absc * 2.2204460492503131e-16;
+      for (int i = 0; i <= eo; i++) absc += fabs(s_c[i]);
+      const double abserr = fabs(s_c[eo]) + absc * 2.2204460492503131e-16;
       const double err = abserr * (double)errn;               /* abserr does not depend on the sample point */
-      if (!((err / errn > (abstol + reltol * rk->spe[q])) & (p < pmax))) break;
+      if (!((err / errn > (abstol + reltol * __ldcg(&rk->spe[q]))) & (p < pmax))) break;
     }
     s_p = p;
+    for (int q = 0; q < LR_NCAND; q++) rk->spe[q] = 0.0;
+    *counter = 0u;
   }
   __syncthreads();
   const int p = s_p;
-  lr_cheb_init(p, range, s_f, s_c);
+  lr_cheb_init(p, range, s_f, s_c2, s_prod);
   if (threadIdx.x == 0) {
-    s_c[0] /= 2;
+    s_c2[0] /= 2;
     plan->meanx = meanx; plan->range = range; plan->p = p;
-    for (int l = 0; l <= p; l++) {
-      double b = 0;
-      for (int k = l; k <= p; k++) b += s_c[k] * (double)s_tc[k][l];
-      plan->B[l] = b; plan->cc[l] = s_c[l];
-    }
-    for (int l = 0; l <= p; l++) {
-      double ch = 1.0;                                    /* C(l,0); C(l,k+1) = C(l,k) (l-k)/(k+1) exact in double here */
-      for (int k = 0; k <= l; k++) { plan->BC[l][k] = plan->B[l] * ch; ch = ch * (double)(l - k) / (double)(k + 1); }
-    }
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l <= p; l += blockDim.x) {          /* one order per thread, the sum over k in the reference's order */
+    double b = 0;
+    for (int k = l; k <= p; k++) b += s_c2[k] * (double)lr_tc.v[k][l];
+    s_B[l] = b; plan->B[l] = b; plan->cc[l] = s_c2[l];
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l <= p; l += blockDim.x) {
+    double ch = 1.0;                                      /* C(l,0); C(l,k+1) = C(l,k) (l-k)/(k+1) exact in double here */
+    for (int k = 0; k <= l; k++) { plan->BC[l][k] = s_B[l] * ch; ch = ch * (double)(l - k) / (double)(k + 1); }
   }
 }
 
@@ -276,102 +282,7 @@ __global__ void __launch_bounds__(BLOCK, 5) k_lr_moments(const double *__restric
     }
   }
 }
-/* rank-64 path: warp-split moment GEMM.  4 warps per CTA share a staged tile of 32 particles; every warp takes 8 of them and
- * every lane owns the column pair m = 2*lane, 2*lane+1 for ALL orders k: one 16-byte shared-memory read of V per particle feeds
- * 2 x P1T DFMAs (the powers are broadcast reads), so the kernel is bound by the FP64 pipe, not by shared memory.  The tile is
- * stored pair-swizzled (pair index XOR particle index) so the transposing stores of the staging phase spread over the banks. */
-constexpr bool LR_WSPLIT = (LR_R == 64);
-constexpr int LR_WS_THREADS = 128, LR_WS_WARPS = 4, LR_WS_TILE = 32;
-__device__ __forceinline__ void lr_cp_async8(void *dst_smem, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-/* stage tile `base` into buffer b: V through cp.async (8-byte copies, transposed + pair-swizzled by the destination address),
- * powers of xi by the first warp */
-template <int P1T>
-__device__ __forceinline__ void lr_stage_tile(double (*s_v)[64], double (*s_pw)[P1T], const double *__restrict__ x, const double *__restrict__ V,
-                                              int64_t vstride, int64_t n, int64_t base, int p1, double meanx, double range) {
-  const int cnt = (int)((n - base) < LR_WS_TILE ? (n - base) : LR_WS_TILE);
-#pragma unroll 2
-  for (int q = threadIdx.x; q < LR_WS_TILE * 64; q += LR_WS_THREADS) {
-    const int jj = q % LR_WS_TILE, m = q / LR_WS_TILE;                  /* coalesced along particles */
-    double *dst = &s_v[jj][(((m >> 1) ^ jj) << 1) | (m & 1)];
-    if (jj < cnt) lr_cp_async8(dst, V + (int64_t)m * vstride + base + jj);
-    else *dst = 0.0;
-  }
-  if (threadIdx.x < LR_WS_TILE) {
-    const int jj = threadIdx.x;
-    const double xi = (jj < cnt) ? (x[base + jj] - meanx) / range : 0.0;
-    double pw = 1.0;
-#pragma unroll
-    for (int k = 0; k < P1T; k++) { s_pw[jj][k] = (jj < cnt && k < p1) ? pw : 0.0; pw *= xi; }
-  }
-}
-constexpr int LR_WS_STAGES = 3;
-constexpr size_t lr_ws_smem_bytes(int p1t) { return sizeof(double) * LR_WS_STAGES * LR_WS_TILE * (64 + p1t); }
-template <int P1T>
-__global__ void __launch_bounds__(LR_WS_THREADS, P1T <= 16 ? 3 : 2) k_lr_moments_ws(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
-                                                                    int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
-  /* ring of LR_WS_STAGES buffers: the next tiles stream in (cp.async) while the FMAs of the current one run.  With one buffer
-   * the kernel spent most of its time waiting for the tile loads, with two the loads of tile t+1 (issued one tile of arithmetic,
-   * ~0.3 us, earlier) were still not back when tile t was done (ncu: barrier stalls at the wait). */
-  extern __shared__ __align__(16) unsigned char lr_ws_smem[];     /* dynamic: 54-66 KB, above the static limit */
-  double (*s_v)[LR_WS_TILE][64] = reinterpret_cast<double (*)[LR_WS_TILE][64]>(lr_ws_smem);
-  double (*s_pw)[LR_WS_TILE][P1T] = reinterpret_cast<double (*)[LR_WS_TILE][P1T]>(lr_ws_smem + sizeof(double) * LR_WS_STAGES * LR_WS_TILE * 64);
-  const int p1 = plan->p + 1;
-  if ((p1 + 7) / 8 * 8 != P1T) return;
-  const double meanx = plan->meanx, range = plan->range;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double acc[2][P1T];
-#pragma unroll
-  for (int k = 0; k < P1T; k++) { acc[0][k] = 0.0; acc[1][k] = 0.0; }
-  const int64_t stride = (int64_t)gridDim.x * LR_WS_TILE;
-  const int64_t first = (int64_t)blockIdx.x * LR_WS_TILE;
-#pragma unroll
-  for (int st = 0; st < LR_WS_STAGES - 1; st++) {             /* prologue: tiles 0 .. STAGES-2 in flight */
-    if (first + st * stride < n) lr_stage_tile<P1T>(s_v[st], s_pw[st], x, V, vstride, n, first + st * stride, p1, meanx, range);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  int buf = 0, nbuf = LR_WS_STAGES - 1;
-  for (int64_t base = first; base < n; base += stride) {
-    const int64_t ahead = base + (LR_WS_STAGES - 1) * stride;
-    if (ahead < n) lr_stage_tile<P1T>(s_v[nbuf], s_pw[nbuf], x, V, vstride, n, ahead, p1, meanx, range);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group %0;" ::"n"(LR_WS_STAGES - 1) : "memory");
-    __syncthreads();
-#pragma unroll 2
-    for (int tq = 0; tq < LR_WS_TILE / LR_WS_WARPS; tq++) {
-      const int jj = warp * (LR_WS_TILE / LR_WS_WARPS) + tq;
-      const double2 va = *reinterpret_cast<const double2 *>(&s_v[buf][jj][(lane ^ jj) << 1]);
-#pragma unroll
-      for (int k = 0; k < P1T; k += 2) {
-        const double2 pk = *reinterpret_cast<const double2 *>(&s_pw[buf][jj][k]);
-        acc[0][k] = fma(va.x, pk.x, acc[0][k]); acc[1][k] = fma(va.y, pk.x, acc[1][k]);
-        acc[0][k + 1] = fma(va.x, pk.y, acc[0][k + 1]); acc[1][k + 1] = fma(va.y, pk.y, acc[1][k + 1]);
-      }
-    }
-    __syncthreads();                      /* every warp is done with this buffer before a later iteration refills it */
-    if (++buf == LR_WS_STAGES) buf = 0;
-    if (++nbuf == LR_WS_STAGES) nbuf = 0;
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  /* the four warps add their accumulators in warp order through shared memory (the staged tile is dead by now), then the CTA
-   * writes ONE partial, layout q = k * 64 + m; orders >= P1T stay zero (the buffer is cleared by the host) */
-  double *s_red = &s_v[0][0][0];                    /* LR_WS_TILE * 64 = 2048 doubles >= P1T * 64 */
-  for (int w = 0; w < LR_WS_WARPS; w++) {
-    __syncthreads();
-    if (warp == w) {
-#pragma unroll
-      for (int k = 0; k < P1T; k++) {
-        double2 *slot = reinterpret_cast<double2 *>(&s_red[k * 64 + 2 * lane]);
-        if (w == 0) *slot = make_double2(acc[0][k], acc[1][k]);
-        else { const double2 o = *slot; *slot = make_double2(o.x + acc[0][k], o.y + acc[1][k]); }
-      }
-    }
-  }
-  __syncthreads();
-  double *dst = partial + (size_t)blockIdx.x * LR_R * LR_P1;
-  for (int q = threadIdx.x; q < P1T * 64; q += LR_WS_THREADS) dst[q] = s_red[q];
-}
+constexpr bool LR_WSPLIT = (LR_R == 64);          /* rank 64: TMA-staged tensor-core path below */
 
 /* ------------------------------------------------------------------------------------------------
  * rank-64 path (BASELINE config 3): TMA-staged tiles, FP64 tensor-core contractions.
@@ -399,11 +310,10 @@ constexpr size_t lrt_smem_bytes(int p1t) {
   return sizeof(double) * ((size_t)LRT_STAGES * LRT_CH * LRT_SU + (size_t)LRT_PT * (p1t + 4)) + 2 * LRT_STAGES * sizeof(uint64_t);
 }
 template <int P1T>
-__global__ void __launch_bounds__(LRT_THREADS, 1) k_lr_moments_tma(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
-                                                                 int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
+__device__ __forceinline__ void lr_moments_tma_body(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride, int64_t n,
+                                                    const LrPlan *__restrict__ plan, double *__restrict__ partial) {
   extern __shared__ __align__(16) unsigned char lrt_smem[];
   const int p1 = plan->p + 1;
-  if ((p1 + 7) / 8 * 8 != P1T) return;
   constexpr int SP = P1T + 4, NB = P1T / 8, NCH = 64 / LRT_CH;
   double *s_v = reinterpret_cast<double *>(lrt_smem);                          /* ring: [stage][16 runs][256 + 4] */
   double (*s_pw)[SP] = reinterpret_cast<double (*)[SP]>(s_v + (size_t)LRT_STAGES * LRT_CH * LRT_SU);      /* [particle of the batch][k] */
@@ -499,6 +409,17 @@ __global__ void __launch_bounds__(LRT_THREADS, 1) k_lr_moments_tma(const double 
   double *dst = partial + (size_t)blockIdx.x * LR_R * LR_P1;
   for (int q = threadIdx.x; q < P1T * 64; q += LRT_THREADS) dst[q] = s_red[q];
 }
+/* one launch for every order: the order is chosen on the device (k_lr_plan), the kernel branches to the body specialised on
+ * p + 1 rounded up to a multiple of 8.  One persistent CTA per SM either way, so the larger bodies cost the smaller ones nothing. */
+__global__ void __launch_bounds__(LRT_THREADS, 1) k_lr_moments_tma(const double *__restrict__ x, const double *__restrict__ V, int64_t vstride,
+                                                                 int64_t n, const LrPlan *__restrict__ plan, double *__restrict__ partial) {
+  switch ((plan->p + 8) / 8) {
+    case 1: lr_moments_tma_body<8>(x, V, vstride, n, plan, partial); break;
+    case 2: lr_moments_tma_body<16>(x, V, vstride, n, plan, partial); break;
+    case 3: lr_moments_tma_body<24>(x, V, vstride, n, plan, partial); break;
+    default: lr_moments_tma_body<32>(x, V, vstride, n, plan, partial); break;
+  }
+}
 
 /* k_lr_apply_tma: UA[i][k] = sum_m U[m][i] A[m][k] (M = particles, N = P1T orders, K = 64 columns), then
  * psi_i = sum_k UA[i][k] phi_k(-xi_i).  The ring holds chunks of 16 column runs of U for a batch of 256 particles; four chunks
@@ -509,12 +430,10 @@ constexpr size_t lra_smem_bytes(int p1t) {
   return sizeof(double) * ((size_t)LRA_STAGES * LRA_CH * LRA_SU + (size_t)(64 + p1t) * (p1t + 4)) + 2 * LRA_STAGES * sizeof(uint64_t);
 }
 template <int P1T>
-__global__ void __launch_bounds__(LRA_THREADS, 1) k_lr_apply_tma(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride,
-                                                               int64_t n, const LrPlan *__restrict__ plan, const double *__restrict__ A,
-                                                               double *__restrict__ psi) {
+__device__ __forceinline__ void lr_apply_tma_body(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride, int64_t n,
+                                                  const LrPlan *__restrict__ plan, const double *__restrict__ A, double *__restrict__ psi) {
   extern __shared__ __align__(16) unsigned char lra_smem[];
   const int p1 = plan->p + 1;
-  if ((p1 + 7) / 8 * 8 != P1T) return;
   constexpr int SA = P1T + 4, NB = P1T / 8, NCH = 64 / LRA_CH;
   double *s_u = reinterpret_cast<double *>(lra_smem);
   double (*s_A)[SA] = reinterpret_cast<double (*)[SA]>(s_u + (size_t)LRA_STAGES * LRA_CH * LRA_SU);       /* [m][k] */
@@ -618,6 +537,16 @@ __global__ void __launch_bounds__(LRA_THREADS, 1) k_lr_apply_tma(const double *_
       const int64_t i = i0 + ib * 8;
       if (t == 0 && i < n) psi[i] = y;
     }
+  }
+}
+__global__ void __launch_bounds__(LRA_THREADS, 1) k_lr_apply_tma(const double *__restrict__ x, const double *__restrict__ U, int64_t ustride,
+                                                               int64_t n, const LrPlan *__restrict__ plan, const double *__restrict__ A,
+                                                               double *__restrict__ psi) {
+  switch ((plan->p + 8) / 8) {
+    case 1: lr_apply_tma_body<8>(x, U, ustride, n, plan, A, psi); break;
+    case 2: lr_apply_tma_body<16>(x, U, ustride, n, plan, A, psi); break;
+    case 3: lr_apply_tma_body<24>(x, U, ustride, n, plan, A, psi); break;
+    default: lr_apply_tma_body<32>(x, U, ustride, n, plan, A, psi); break;
   }
 }
 

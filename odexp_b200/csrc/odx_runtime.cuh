@@ -182,6 +182,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   if (!h->lr_plan) {
     ODX_CUDA(h, cudaMalloc(&h->lr_plan, sizeof(LrPlan)));
     ODX_CUDA(h, cudaMalloc(&h->lr_rank, sizeof(LrRank)));
+    ODX_CUDA(h, cudaMemsetAsync(h->lr_rank, 0, sizeof(LrRank), h->stream));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_stats, sizeof(double) * 8));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_spart, sizeof(double) * 3 * (h->grid_cap + 1)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (24 * h->sm_count + 24 * h->sm_count / 32 + 2)));
@@ -203,11 +204,8 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   }
 #endif
   LrRank *rk = (LrRank *)h->lr_rank;
-  k_lr_rank_fit<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->lr_pmax, rk);
-  ODX_TRY(launch_check(h));
-  k_lr_rank_spe<<<2 * h->sm_count, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, rk);
-  ODX_TRY(launch_check(h));
-  k_lr_plan<<<1, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, rk, (LrPlan *)h->lr_plan);
+  k_lr_rank_plan<<<2 * h->sm_count, BLOCK, 0, h->stream>>>(h->lr_stats, h->n_global, h->lr_pmax, h->lr_abstol, h->lr_reltol, rk, h->counter + 2,
+                                                          (LrPlan *)h->lr_plan);
   ODX_TRY(launch_check(h));
   int npart = nblk;
   if (LR_WSPLIT) {
@@ -218,20 +216,11 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     const double *Vc = h->E + (size_t)M::LR0_V * h->cap; const LrPlan *plm = (const LrPlan *)h->lr_plan;
     ODX_CUDA(h, cudaMemsetAsync(h->lr_apart, 0, sizeof(double) * (size_t)LR_R * LR_P1 * npart, h->stream));
     if (!h->lr_attr_done) {                       /* the rings need more than the 48 KB static limit */
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(8)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(16)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(24)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(32)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(8)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(16)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(24)));
-      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(32)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(LR_P1)));
+      ODX_CUDA(h, cudaFuncSetAttribute(k_lr_apply_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lra_smem_bytes(LR_P1)));
       h->lr_attr_done = true;
     }
-    k_lr_moments_tma<8><<<nblk, LRT_THREADS, lrt_smem_bytes(8), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_tma<16><<<nblk, LRT_THREADS, lrt_smem_bytes(16), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_tma<24><<<nblk, LRT_THREADS, lrt_smem_bytes(24), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
-    k_lr_moments_tma<32><<<nblk, LRT_THREADS, lrt_smem_bytes(32), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
+    k_lr_moments_tma<<<nblk, LRT_THREADS, lrt_smem_bytes(LR_P1), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
   } else {
     k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
     ODX_TRY(launch_check(h));
@@ -239,7 +228,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   {
     const int qb = (LR_R * LR_P1 + BLOCK - 1) / BLOCK, ng = (npart + 31) / 32;
     double *stage2 = h->lr_apart + (size_t)LR_R * LR_P1 * (24 * h->sm_count);      /* tail of the partial buffer */
-    k_lr_moments_sum<<<dim3(qb, ng), BLOCK, 0, h->stream>>>(h->lr_apart, npart, 32, stage2);
+    k_lr_moments_sum<<<dim3(qb, ng), BLOCK, 0, h->stream>>>(h->lr_apart, npart, 32, stage2);      /* one pass over all partials was slower */
     ODX_TRY(launch_check(h));
     k_lr_moments_sum<<<dim3(qb, 1), BLOCK, 0, h->stream>>>(stage2, ng, ng, h->lr_A);
     ODX_TRY(launch_check(h));
@@ -258,10 +247,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
   if (LR_WSPLIT) {
     const int64_t nbatch = (n + LRA_PT - 1) / LRA_PT;
     const int gt = nbatch < h->sm_count ? (nbatch < 1 ? 1 : (int)nbatch) : h->sm_count;
-    k_lr_apply_tma<8><<<gt, LRA_THREADS, lra_smem_bytes(8), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
-    k_lr_apply_tma<16><<<gt, LRA_THREADS, lra_smem_bytes(16), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
-    k_lr_apply_tma<24><<<gt, LRA_THREADS, lra_smem_bytes(24), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
-    k_lr_apply_tma<32><<<gt, LRA_THREADS, lra_smem_bytes(32), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi);
+    k_lr_apply_tma<<<gt, LRA_THREADS, lra_smem_bytes(LR_P1), h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi);
     return launch_check(h);
   }
   k_lr_apply<8><<<ga, 128, 0, h->stream>>>(x, Uc, h->cap, n, pl, h->lr_A, psi); ODX_TRY(launch_check(h));
