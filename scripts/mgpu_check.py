@@ -16,7 +16,8 @@ ok = True
 CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 0}),
          ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 1}),          # ring / lean step kernels with the NVLink exchange
          ("nbody", 3001, "dde", 2, 1e-12, {}), ("nbody", 2048, "rkf45", 3, 1e-9, {}),
-         ("vdp_sde", 50001, "fe", 10, 1e-12, {}), ("vdp_sde", 50001, "fe", 10, 1e-12, {"tma": 1}), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10, {})]
+         ("vdp_sde", 50001, "fe", 10, 1e-12, {}), ("vdp_sde", 50001, "fe", 10, 1e-12, {"tma": 1}), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10, {}),
+         ("kuramoto_lowrank64", 4099, "dde", 2, 1e-10, {})]
 for model, n, meth, nsteps, tol, opts in CASES:
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
