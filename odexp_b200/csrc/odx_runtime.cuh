@@ -514,7 +514,7 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
 }
 
 /* embedded pairs: coefficient tables as published for GSL's rkf45 / rkck steppers */
-struct Tableau { double ah[5]; double b[5][5]; double c[6]; double ec[6]; unsigned order; };
+struct Tableau { double ah[5]; double b[5][5]; double c[6]; double ec[6]; unsigned order; int nst; };
 static const Tableau TAB_RKF45 = {
     {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0},
     {{1.0 / 4.0},
@@ -523,7 +523,7 @@ static const Tableau TAB_RKF45 = {
      {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0},
      {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0}},
     {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0, 277020.0 / 7618050.0},
-    {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0}, 5};
+    {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0}, 5, 6};
 static const Tableau TAB_RKCK = {
     {1.0 / 5.0, 3.0 / 10.0, 3.0 / 5.0, 1.0, 7.0 / 8.0},
     {{1.0 / 5.0},
@@ -533,7 +533,14 @@ static const Tableau TAB_RKCK = {
      {1631.0 / 55296.0, 175.0 / 512.0, 575.0 / 13824.0, 44275.0 / 110592.0, 253.0 / 4096.0}},
     {37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0},
     {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0, 125.0 / 594.0 - 13525.0 / 55296.0,
-     -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5};
+     -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5, 6};
+/* GSL rk2: k2 at the midpoint, k3 at y + h (-k1 + 2 k2), y += h (k1 + 4 k2 + k3) / 6, yerr = h (k2 - (k1 + 4 k2 + k3) / 6) */
+static const Tableau TAB_RK2 = {
+    {1.0 / 2.0, 1.0},
+    {{1.0 / 2.0},
+     {-1.0, 2.0}},
+    {1.0 / 6.0, 4.0 / 6.0, 1.0 / 6.0},
+    {-1.0 / 6.0, 1.0 / 3.0, -1.0 / 6.0}, 2, 3};
 
 static int read_rmax(odx_handle *h, double *rmax_out) {
   ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -555,31 +562,31 @@ static int read_rmax(odx_handle *h, double *rmax_out) {
 
 /* one attempted embedded step of size hh from (t, Y): leaves y_new in YS, dydt_out in DOUT, returns rmax */
 static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh, double *rmax_out) {
-  const int g = grid_for(h, h->n);
+  const int g = grid_for(h, h->n), nst = T.nst;
   Pop p = pop_view(h);
   ODX_CUDA(h, cudaMemsetAsync(h->rmax, 0, sizeof(unsigned long long), h->stream));
   if (!h->k1_valid) {
     ODX_TRY(ensure_moments_Y(h, t));
     ODX_TRY(compute_psi(h, h->Y, t));
   }
-  for (int s = 1; s <= 6; s++) {
+  for (int s = 1; s <= nst; s++) {
     TabArgs a;
     memset(&a, 0, sizeof a);
     a.s = s; a.h = hh; a.K1 = h->K1; a.eps_abs = h->eps_abs; a.eps_rel = h->eps_rel; a.rmax_bits = h->rmax;
-    a.final_ = (s == 6);
+    a.final_ = (s == nst);
     a.skip_rhs = (s == 1 && h->k1_valid) ? 1 : 0;
     a.ycur = (s == 1) ? h->Y : h->YS; a.y0src = h->Y;
     a.sums_in = sums_ptr(h, s == 1 ? h->y_slot : SLOT_STAGE + (s - 2));
     a.t_eval = (s == 1) ? t : t + T.ah[s - 2] * hh;
-    a.t_next = (s == 6) ? t + hh : t + T.ah[s - 1] * hh;
-    if (s < 6) { for (int j = 0; j < s; j++) a.b[j] = T.b[s - 1][j]; }
-    else { for (int j = 0; j < 6; j++) { a.b[j] = T.c[j]; a.ec[j] = T.ec[j]; } }
+    a.t_next = (s == nst) ? t + hh : t + T.ah[s - 1] * hh;
+    if (s < nst) { for (int j = 0; j < s; j++) a.b[j] = T.b[s - 1][j]; }
+    else { for (int j = 0; j < nst; j++) { a.b[j] = T.c[j]; a.ec[j] = T.ec[j]; } }
     a.eval_index = h->eval_index; h->eval_index += 2;
     if (!a.skip_rhs) h->rhs_evals++;
-    const int out_slot = SLOT_STAGE + (s - 1);
+    const int out_slot = (s == nst) ? SLOT_STAGE + 5 : SLOT_STAGE + (s - 1);      /* the sums of y_new always land in slot 5 */
     /* KY(): neighbours read the stage state this kernel evaluates the RHS at, so the state it forms goes to the other buffer
-     * (odd stages write YALT, even ones YS: the sixth leaves y_new in YS) */
-    if (M::USES_KY) { p.YS_OUT = (s & 1) ? h->YALT : h->YS; if (s > 1) a.ycur = (s & 1) ? h->YS : h->YALT; }
+     * (the stages alternate so that the last one leaves y_new in YS) */
+    if (M::USES_KY) { const bool alt = ((nst - s) & 1) != 0; p.YS_OUT = alt ? h->YALT : h->YS; if (s > 1) a.ycur = alt ? h->YS : h->YALT; }
     k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, out_slot));
     ODX_TRY(launch_check(h));
     if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, out_slot));
@@ -1198,11 +1205,11 @@ int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uin
 int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
   ODX_TRY(ky_guard(h));
   ODX_CUDA(h, cudaSetDevice(h->device));
-  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4) {
-    h->err = "odx_evolve_apply: method must be rkf45, rkck or rk4"; return ODX_EUNSUP;
+  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4 && method != ODX_METH_RK2) {
+    h->err = "odx_evolve_apply: method must be rkf45, rkck, rk4 or rk2"; return ODX_EUNSUP;
   }
   if (h->n <= 0) { *t = t1; return ODX_SUCCESS; }
-  const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : TAB_RKCK;
+  const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : (method == ODX_METH_RK2) ? TAB_RK2 : TAB_RKCK;
   const unsigned order = (method == ODX_METH_RK4) ? 4u : T.order;
   if (!h->KS) {
     ODX_TRY(alloc_cols(h, &h->KS, 5 * A1(NVAR))); ODX_TRY(alloc_cols(h, &h->K1, NVAR)); ODX_TRY(alloc_cols(h, &h->DOUT, NVAR));

@@ -4,14 +4,14 @@
  * not installed here, and the reference ships no golden outputs.  The algorithms below restate GSL's
  * published behaviour (gsl-2.x doc, "Ordinary Differential Equations" and "Chebyshev Approximations"):
  *
- *   gsl_odeiv2_step_{rk4,rkf45,rkck}  call sites  src/methods_odexp.c:154-183,445-447,698-701
+ *   gsl_odeiv2_step_{rk2,rk4,rkf45,rkck}  call sites  src/methods_odexp.c:154-183,445-447,698-701
  *   gsl_odeiv2_control_y_new          call site   src/methods_odexp.c:446
  *   gsl_odeiv2_evolve_apply           call site   src/methods_odexp.c:619
  *   gsl_cheb_{alloc,init,coeffs,eval_n_err,free}, gsl_sf_choose, gsl_pow_int
  *                                     call sites  src/lrexp.c:116-165,191-245,296-353,407-468
  *
  * What pins them here: order-of-convergence, the embedded-pair identities and closed forms
- * (tests/test_oracle_minigsl.py).  rk2, rk8pd and bsimp are not restated (abort if selected).
+ * (tests/test_oracle_minigsl.py).  rk8pd and bsimp are not restated (abort if selected).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -92,9 +92,17 @@ static const tableau TAB_RKCK = {
   {37.0/378.0 - 2825.0/27648.0, 0.0, 250.0/621.0 - 18575.0/48384.0, 125.0/594.0 - 13525.0/55296.0,
    -277.0/14336.0, 512.0/1771.0 - 0.25}};
 
-/* test hook: copy a tableau out (kind: 2 = rkf45, 3 = rkck); ah[5], b[25] row-major, c[6], ec[6] */
+/* GSL rk2 as a tableau (for the order-condition test only; rk2_apply below uses GSL's own arithmetic form) */
+static const tableau TAB_RK2 = {
+  {1.0/2.0, 1.0},
+  {{1.0/2.0},
+   {-1.0, 2.0}},
+  {1.0/6.0, 4.0/6.0, 1.0/6.0},
+  {-1.0/6.0, 1.0/3.0, -1.0/6.0}};
+
+/* test hook: copy a tableau out (kind: 0 = rk2, 2 = rkf45, 3 = rkck); ah[5], b[25] row-major, c[6], ec[6] */
 int minigsl_tableau(int kind, double *ah, double *b, double *c, double *ec) {
-  const tableau *T = kind == 2 ? &TAB_RKF45 : (kind == 3 ? &TAB_RKCK : NULL);
+  const tableau *T = kind == 2 ? &TAB_RKF45 : (kind == 3 ? &TAB_RKCK : (kind == 0 ? &TAB_RK2 : NULL));
   int i, j;
   if (!T) return -1;
   for (i = 0; i < 5; i++) { ah[i] = T->ah[i]; for (j = 0; j < 5; j++) b[5 * i + j] = T->b[i][j]; }
@@ -165,12 +173,37 @@ static int rk4_apply(gsl_odeiv2_step *s, double t, double h, double y[], double 
   return GSL_SUCCESS;
 }
 
+/* GSL "rk2": embedded Runge-Kutta (2, 3).  k2 at the midpoint, k3 at y + h (-k1 + 2 k2); the third-order combination
+ * (k1 + 4 k2 + k3) / 6 is propagated, yerr = h (k2 - (k1 + 4 k2 + k3) / 6), order() = 2 */
+static int rk2_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
+                     const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
+  const size_t n = s->dim; size_t i;
+  double *k1 = s->k[0], *k2 = s->k[1], *k3 = s->k[2], *ytmp = s->ytmp, *y0 = s->y0;
+  memcpy(y0, y, n * sizeof(double));
+  if (dydt_in) memcpy(k1, dydt_in, n * sizeof(double)); else FEVAL(sys, t, y, k1);
+  for (i = 0; i < n; i++) ytmp[i] = y[i] + 0.5 * h * k1[i];
+  FEVAL(sys, t + 0.5 * h, ytmp, k2);
+  for (i = 0; i < n; i++) ytmp[i] = y[i] + h * (-k1[i] + 2.0 * k2[i]);
+  FEVAL(sys, t + h, ytmp, k3);
+  for (i = 0; i < n; i++) {
+    const double ksum3 = (k1[i] + 4.0 * k2[i] + k3[i]) / 6.0;
+    y[i] += h * ksum3;
+    yerr[i] = h * (k2[i] - ksum3);
+  }
+  if (dydt_out) {
+    int s_ = sys->function(t + h, y, dydt_out, sys->params);
+    if (s_ != GSL_SUCCESS) { memcpy(y, y0, n * sizeof(double)); return s_; }
+  }
+  return GSL_SUCCESS;
+}
+
 static int step_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
                       const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
   switch (s->type->kind) {
     case MG_RKF45: return embedded_apply(s, &TAB_RKF45, t, h, y, yerr, dydt_in, dydt_out, sys);
     case MG_RKCK:  return embedded_apply(s, &TAB_RKCK, t, h, y, yerr, dydt_in, dydt_out, sys);
     case MG_RK4:   return rk4_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
+    case MG_RK2:   return rk2_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
     default:
       fprintf(stderr, "minigsl: stepper '%s' is not restated (no GSL source offline)\n", s->type->name);
       abort();

@@ -118,6 +118,23 @@ def test_ring_neighbours_vs_oracle(model_lib, n, meth):
     pop.close()
 
 
+@pytest.mark.parametrize("model,n,ts", [("kuramoto", 257, (0, 3.0)), ("nbody", 40, (0, 0.2))])
+def test_gsl_rk2_vs_oracle(model_lib, model, n, ts):
+    """GSL's embedded rk2 (2, 3) through the general tableau kernel: same accept / reject sequence and states as the restatement"""
+    from odexp_b200 import capi
+    from oracle import port
+    tol = 1e-8 if model == "nbody" else 1e-6
+    pop = capi.Population(model_lib(model), capacity=1024)
+    out = capi.odesolver(pop, ts, meth="rk2", res=4, popsize=n, abstol=tol, reltol=tol, hmin=0.0 if model == "nbody" else 1e-5,
+                         h0=0.02 if model == "nbody" else 0.1, replay_ic=True)
+    ref = port.run(model, {"meth": "rk2", "res": 4, "ps": n, "abstol": tol, "reltol": tol, "hmin": 0.0 if model == "nbody" else 1e-5,
+                           "h0": 0.02 if model == "nbody" else 0.1}, ts)
+    assert len(out["stats"]) == len(ref["stats"])
+    assert out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-8 if model == "nbody" else 1e-9, atol=1e-12)
+    pop.close()
+
+
 @pytest.mark.parametrize("meth,n", [("rkck", 33), ("rkf45", 200), ("rk4", 17)])
 def test_ring_neighbours_adaptive_vs_oracle(model_lib, meth, n):
     """KY() under the embedded pairs and the step-doubling rk4 (same accept / reject sequence as the restatement, which is

@@ -42,6 +42,27 @@ def test_embedded_pair_order_conditions(kind, name):
     assert abs(ec.sum()) < 1e-15                                                 # error weights sum to zero
 
 
+def test_rk2_order_conditions_and_convergence():
+    """GSL rk2 = embedded (2, 3): the propagated weights (1, 4, 1)/6 satisfy the conditions of order 3 on its three stages, the
+    comparison solution c + ec = (0, 1, 0) (the midpoint rule; GSL's yerr = y_midpoint - y_new here) those of order 2, the error weights sum to zero; the whole evolve
+    loop converges under tightening tolerances"""
+    from oracle import port
+    A, nodes, c, ec = tableau(0)
+    A, nodes, c, ec = A[:3, :3], nodes[:3], c[:3], ec[:3]
+    np.testing.assert_allclose(A.sum(axis=1), nodes, atol=1e-15)
+    assert np.abs(order_conditions(A, nodes, c, 3)).max() < 1e-15
+    assert np.abs(order_conditions(A, nodes, c + ec, 2)).max() < 1e-15
+    np.testing.assert_allclose(c + ec, [0.0, 1.0, 0.0], atol=1e-16)
+    assert abs(ec.sum()) < 1e-16
+    ref = port.run("kuramoto", {"meth": "dde", "h0": 0.0005, "res": 2, "ps": 20}, (0, 2.0))["traj"]
+    yref = ref[ref["step"] == 1]["cols"][:, 0]
+    errs = []
+    for tol in (1e-5, 1e-7, 1e-9):
+        tr = port.run("kuramoto", {"meth": "rk2", "res": 2, "ps": 20, "abstol": tol, "reltol": tol, "h0": 0.5}, (0, 2.0))["traj"]
+        errs.append(np.abs(tr[tr["step"] == 1]["cols"][:, 0] - yref).max())
+    assert errs[2] < errs[1] < errs[0] and errs[0] < 1e-3 and errs[2] < 1e-7
+
+
 def test_evolve_convergence_and_control():
     """K = 0 turns the Kuramoto fixture into theta' = omega (integrated exactly by any consistent RK method); with coupling, tightening
     the tolerance by 100 must reduce the error against a tiny-step RK4 run by ~100 (5th-order pair under standard control)."""
