@@ -12,7 +12,7 @@ import numpy as np
 from . import build as _build
 from . import popfile
 
-METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5, "rk2": 6}
+METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5, "rk2": 6, "rk8pd": 7}
 
 
 class OdxError(RuntimeError):

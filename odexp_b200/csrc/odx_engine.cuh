@@ -1267,11 +1267,12 @@ __global__ void __launch_bounds__(BLOCK) k_pair_finish(Pop p, const double *__re
  *   r_i = |yerr_i| / (eps_abs + eps_rel |y_new,i|), grid max -> rmax (gsl_odeiv2_control standard, a_y=1, a_dydt=0). */
 struct TabArgs {
   const double *sums_in; double t_eval, t_next, h; int s; /* index of the slope computed here, 1-based */
-  double b[6];          /* weights of k_1..k_s for the state formed here */
-  double ec[6];         /* error weights (final only) */
+  double b[13];         /* weights of k_1..k_s for the state formed here */
+  double ec[13];        /* error weights (final only); err_diff: the weights of the comparison solution instead */
+  int err_diff;         /* yerr = h (sum ec_j k_j - sum b_j k_j), GSL's arithmetic form for rk8pd (ksum7 - ksum8) */
   double eps_abs, eps_rel; int final_; uint32_t eval_index; unsigned long long *rmax_bits;
   const double *ycur;   /* state the RHS is evaluated at (Y for s == 1, else YS) */
-  double *K1;           /* slope k_1 (= dydt_in of gsl_odeiv2_evolve_apply); k_2..k_6 live in Pop::KS */
+  double *K1;           /* slope k_1 (= dydt_in of gsl_odeiv2_evolve_apply); k_2..k_13 live in Pop::KS */
   const double *y0src;  /* state at the start of the (sub)step (Y, or the half-step state of the step-doubling rk4) */
   int skip_rhs;         /* s == 1 only: k_1 is already in K1 (reused dydt_out of the previous step, or a retry) */
 };
@@ -1314,7 +1315,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
       yn[v] = y0[v] + a.h * sacc;
       if (a.final_) {
         if (a.ec[a.s - 1] != 0.0) eacc += a.ec[a.s - 1] * f[v];
-        const double yerr = a.h * eacc;
+        const double yerr = a.err_diff ? a.h * (eacc - sacc) : a.h * eacc;
         const double D0 = a.eps_rel * fabs(yn[v]) + a.eps_abs;
         const double rr = fabs(yerr) / fabs(D0);
         if (rr > rloc) rloc = rr;          /* GSL_MAX_DBL: a NaN ratio is dropped */

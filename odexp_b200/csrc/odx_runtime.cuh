@@ -69,7 +69,7 @@ struct odx_handle {
   double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
   double *pair_part = nullptr; size_t pair_part_len = 0;                             /* [segment][npsi][cap] raw partial sums of k_pair */
   int64_t all_n[MAX_RANKS] = {0, 0, 0, 0, 0, 0, 0, 0};                               /* particles per rank */
-  int sm_count = 148, grid_cap = 148 * 8;
+  int sm_count = 148, grid_cap = 148 * 8; int ks_slots = 0;
   uint32_t k0 = 3141592u, k1 = 0u;
   uint32_t eval_index = 0;
   int y_slot = SLOT_Y0; bool ymoments_valid = false;
@@ -514,7 +514,7 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
 }
 
 /* embedded pairs: coefficient tables as published for GSL's rkf45 / rkck steppers */
-struct Tableau { double ah[5]; double b[5][5]; double c[6]; double ec[6]; unsigned order; int nst; };
+struct Tableau { double ah[12]; double b[12][12]; double c[13]; double ec[13]; unsigned order; int nst; int err_diff; };
 static const Tableau TAB_RKF45 = {
     {1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0},
     {{1.0 / 4.0},
@@ -523,7 +523,7 @@ static const Tableau TAB_RKF45 = {
      {8341.0 / 4104.0, -32832.0 / 4104.0, 29440.0 / 4104.0, -845.0 / 4104.0},
      {-6080.0 / 20520.0, 41040.0 / 20520.0, -28352.0 / 20520.0, 9295.0 / 20520.0, -5643.0 / 20520.0}},
     {902880.0 / 7618050.0, 0.0, 3953664.0 / 7618050.0, 3855735.0 / 7618050.0, -1371249.0 / 7618050.0, 277020.0 / 7618050.0},
-    {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0}, 5, 6};
+    {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0}, 5, 6, 0};
 static const Tableau TAB_RKCK = {
     {1.0 / 5.0, 3.0 / 10.0, 3.0 / 5.0, 1.0, 7.0 / 8.0},
     {{1.0 / 5.0},
@@ -533,14 +533,42 @@ static const Tableau TAB_RKCK = {
      {1631.0 / 55296.0, 175.0 / 512.0, 575.0 / 13824.0, 44275.0 / 110592.0, 253.0 / 4096.0}},
     {37.0 / 378.0, 0.0, 250.0 / 621.0, 125.0 / 594.0, 0.0, 512.0 / 1771.0},
     {37.0 / 378.0 - 2825.0 / 27648.0, 0.0, 250.0 / 621.0 - 18575.0 / 48384.0, 125.0 / 594.0 - 13525.0 / 55296.0,
-     -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5, 6};
+     -277.0 / 14336.0, 512.0 / 1771.0 - 0.25}, 5, 6, 0};
 /* GSL rk2: k2 at the midpoint, k3 at y + h (-k1 + 2 k2), y += h (k1 + 4 k2 + k3) / 6, yerr = h (k2 - (k1 + 4 k2 + k3) / 6) */
 static const Tableau TAB_RK2 = {
     {1.0 / 2.0, 1.0},
     {{1.0 / 2.0},
      {-1.0, 2.0}},
     {1.0 / 6.0, 4.0 / 6.0, 1.0 / 6.0},
-    {-1.0 / 6.0, 1.0 / 3.0, -1.0 / 6.0}, 2, 3};
+    {-1.0 / 6.0, 1.0 / 3.0, -1.0 / 6.0}, 2, 3, 0};
+/* GSL rk8pd = Prince-Dormand RK8(7)13M: c = the 8th-order weights (propagated), ec = the 7th-order weights, yerr = h (ksum7 - ksum8) */
+static const Tableau TAB_RK8PD = {
+    {1.0 / 18.0, 1.0 / 12.0, 1.0 / 8.0, 5.0 / 16.0, 3.0 / 8.0, 59.0 / 400.0, 93.0 / 200.0, 5490023248.0 / 9719169821.0, 13.0 / 20.0,
+   1201146811.0 / 1299019798.0, 1.0, 1.0},
+    {{1.0 / 18.0},
+   {1.0 / 48.0, 1.0 / 16.0},
+   {1.0 / 32.0, 0.0, 3.0 / 32.0},
+   {5.0 / 16.0, 0.0, -75.0 / 64.0, 75.0 / 64.0},
+   {3.0 / 80.0, 0.0, 0.0, 3.0 / 16.0, 3.0 / 20.0},
+   {29443841.0 / 614563906.0, 0.0, 0.0, 77736538.0 / 692538347.0, -28693883.0 / 1125000000.0, 23124283.0 / 1800000000.0},
+   {16016141.0 / 946692911.0, 0.0, 0.0, 61564180.0 / 158732637.0, 22789713.0 / 633445777.0, 545815736.0 / 2771057229.0,
+    -180193667.0 / 1043307555.0},
+   {39632708.0 / 573591083.0, 0.0, 0.0, -433636366.0 / 683701615.0, -421739975.0 / 2616292301.0, 100302831.0 / 723423059.0,
+    790204164.0 / 839813087.0, 800635310.0 / 3783071287.0},
+   {246121993.0 / 1340847787.0, 0.0, 0.0, -37695042795.0 / 15268766246.0, -309121744.0 / 1061227803.0, -12992083.0 / 490766935.0,
+    6005943493.0 / 2108947869.0, 393006217.0 / 1396673457.0, 123872331.0 / 1001029789.0},
+   {-1028468189.0 / 846180014.0, 0.0, 0.0, 8478235783.0 / 508512852.0, 1311729495.0 / 1432422823.0, -10304129995.0 / 1701304382.0,
+    -48777925059.0 / 3047939560.0, 15336726248.0 / 1032824649.0, -45442868181.0 / 3398467696.0, 3065993473.0 / 597172653.0},
+   {185892177.0 / 718116043.0, 0.0, 0.0, -3185094517.0 / 667107341.0, -477755414.0 / 1098053517.0, -703635378.0 / 230739211.0,
+    5731566787.0 / 1027545527.0, 5232866602.0 / 850066563.0, -4093664535.0 / 808688257.0, 3962137247.0 / 1805957418.0,
+    65686358.0 / 487910083.0},
+   {403863854.0 / 491063109.0, 0.0, 0.0, -5068492393.0 / 434740067.0, -411421997.0 / 543043805.0, 652783627.0 / 914296604.0,
+    11173962825.0 / 925320556.0, -13158990841.0 / 6184727034.0, 3936647629.0 / 1978049680.0, -160528059.0 / 685178525.0,
+    248638103.0 / 1413531060.0, 0.0}},
+    {14005451.0 / 335480064.0, 0.0, 0.0, 0.0, 0.0, -59238493.0 / 1068277825.0, 181606767.0 / 758867731.0, 561292985.0 / 797845732.0,
+   -1041891430.0 / 1371343529.0, 760417239.0 / 1151165299.0, 118820643.0 / 751138087.0, -528747749.0 / 2220607170.0, 1.0 / 4.0},
+    {13451932.0 / 455176623.0, 0.0, 0.0, 0.0, 0.0, -808719846.0 / 976000145.0, 1757004468.0 / 5645159321.0, 656045339.0 / 265891186.0,
+   -3867574721.0 / 1518517206.0, 465885868.0 / 322736535.0, 53011238.0 / 667516719.0, 2.0 / 45.0, 0.0}, 8, 13, 1};
 
 static int read_rmax(odx_handle *h, double *rmax_out) {
   ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->rmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -573,17 +601,17 @@ static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh
     TabArgs a;
     memset(&a, 0, sizeof a);
     a.s = s; a.h = hh; a.K1 = h->K1; a.eps_abs = h->eps_abs; a.eps_rel = h->eps_rel; a.rmax_bits = h->rmax;
-    a.final_ = (s == nst);
+    a.final_ = (s == nst); a.err_diff = T.err_diff;
     a.skip_rhs = (s == 1 && h->k1_valid) ? 1 : 0;
     a.ycur = (s == 1) ? h->Y : h->YS; a.y0src = h->Y;
-    a.sums_in = sums_ptr(h, s == 1 ? h->y_slot : SLOT_STAGE + (s - 2));
+    a.sums_in = sums_ptr(h, s == 1 ? h->y_slot : SLOT_STAGE + (s - 2) % 5);       /* only the previous stage's sums are read */
     a.t_eval = (s == 1) ? t : t + T.ah[s - 2] * hh;
     a.t_next = (s == nst) ? t + hh : t + T.ah[s - 1] * hh;
     if (s < nst) { for (int j = 0; j < s; j++) a.b[j] = T.b[s - 1][j]; }
     else { for (int j = 0; j < nst; j++) { a.b[j] = T.c[j]; a.ec[j] = T.ec[j]; } }
     a.eval_index = h->eval_index; h->eval_index += 2;
     if (!a.skip_rhs) h->rhs_evals++;
-    const int out_slot = (s == nst) ? SLOT_STAGE + 5 : SLOT_STAGE + (s - 1);      /* the sums of y_new always land in slot 5 */
+    const int out_slot = (s == nst) ? SLOT_STAGE + 5 : SLOT_STAGE + (s - 1) % 5;  /* the sums of y_new always land in slot 5 */
     /* KY(): neighbours read the stage state this kernel evaluates the RHS at, so the state it forms goes to the other buffer
      * (the stages alternate so that the last one leaves y_new in YS) */
     if (M::USES_KY) { const bool alt = ((nst - s) & 1) != 0; p.YS_OUT = alt ? h->YALT : h->YS; if (s > 1) a.ycur = alt ? h->YS : h->YALT; }
@@ -1205,15 +1233,16 @@ int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uin
 int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hstep) {
   ODX_TRY(ky_guard(h));
   ODX_CUDA(h, cudaSetDevice(h->device));
-  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4 && method != ODX_METH_RK2) {
-    h->err = "odx_evolve_apply: method must be rkf45, rkck, rk4 or rk2"; return ODX_EUNSUP;
+  if (method != ODX_METH_RKF45 && method != ODX_METH_RKCK && method != ODX_METH_RK4 && method != ODX_METH_RK2 && method != ODX_METH_RK8PD) {
+    h->err = "odx_evolve_apply: method must be rkf45, rkck, rk8pd, rk4 or rk2"; return ODX_EUNSUP;
   }
   if (h->n <= 0) { *t = t1; return ODX_SUCCESS; }
-  const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : (method == ODX_METH_RK2) ? TAB_RK2 : TAB_RKCK;
+  const Tableau &T = (method == ODX_METH_RKF45) ? TAB_RKF45 : (method == ODX_METH_RK2) ? TAB_RK2 : (method == ODX_METH_RK8PD) ? TAB_RK8PD : TAB_RKCK;
   const unsigned order = (method == ODX_METH_RK4) ? 4u : T.order;
-  if (!h->KS) {
-    ODX_TRY(alloc_cols(h, &h->KS, 5 * A1(NVAR))); ODX_TRY(alloc_cols(h, &h->K1, NVAR)); ODX_TRY(alloc_cols(h, &h->DOUT, NVAR));
-  }
+  const int ks_need = (method == ODX_METH_RK8PD) ? 12 : 5;        /* slope buffers k_2 .. k_nst */
+  if (h->KS && h->ks_slots < ks_need) { ODX_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(h->KS); h->KS = nullptr; h->k1_valid = false; }
+  if (!h->KS) { ODX_TRY(alloc_cols(h, &h->KS, ks_need * A1(NVAR))); h->ks_slots = ks_need; }
+  if (!h->K1) { ODX_TRY(alloc_cols(h, &h->K1, NVAR)); ODX_TRY(alloc_cols(h, &h->DOUT, NVAR)); }
   if (method == ODX_METH_RK4 && !h->YONE) {
     ODX_TRY(alloc_cols(h, &h->YONE, NVAR)); ODX_TRY(alloc_cols(h, &h->YH, NVAR)); ODX_TRY(alloc_cols(h, &h->K1B, NVAR));
   }

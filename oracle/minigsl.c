@@ -4,14 +4,14 @@
  * not installed here, and the reference ships no golden outputs.  The algorithms below restate GSL's
  * published behaviour (gsl-2.x doc, "Ordinary Differential Equations" and "Chebyshev Approximations"):
  *
- *   gsl_odeiv2_step_{rk2,rk4,rkf45,rkck}  call sites  src/methods_odexp.c:154-183,445-447,698-701
+ *   gsl_odeiv2_step_{rk2,rk4,rkf45,rkck,rk8pd}  call sites  src/methods_odexp.c:154-183,445-447,698-701
  *   gsl_odeiv2_control_y_new          call site   src/methods_odexp.c:446
  *   gsl_odeiv2_evolve_apply           call site   src/methods_odexp.c:619
  *   gsl_cheb_{alloc,init,coeffs,eval_n_err,free}, gsl_sf_choose, gsl_pow_int
  *                                     call sites  src/lrexp.c:116-165,191-245,296-353,407-468
  *
  * What pins them here: order-of-convergence, the embedded-pair identities and closed forms
- * (tests/test_oracle_minigsl.py).  rk8pd and bsimp are not restated (abort if selected).
+ * (tests/test_oracle_minigsl.py).  bsimp is not restated (abort if selected).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,7 +37,8 @@ const gsl_odeiv2_step_type *gsl_odeiv2_step_rkck = &t_rkck;
 const gsl_odeiv2_step_type *gsl_odeiv2_step_rk8pd = &t_rk8pd;
 const gsl_odeiv2_step_type *gsl_odeiv2_step_bsimp = &t_bsimp;
 
-struct gsl_odeiv2_step_struct { const gsl_odeiv2_step_type *type; size_t dim; double *k[6], *y0, *ytmp, *yone; };
+#define MG_MAXK 13
+struct gsl_odeiv2_step_struct { const gsl_odeiv2_step_type *type; size_t dim; double *k[MG_MAXK], *y0, *ytmp, *yone; };
 struct gsl_odeiv2_control_struct { double eps_abs, eps_rel, a_y, a_dydt; };
 struct gsl_odeiv2_evolve_struct { size_t dim; double *y0, *yerr, *dydt_in, *dydt_out; double last_step; unsigned long count, failed_steps; };
 
@@ -45,13 +46,13 @@ gsl_odeiv2_step *gsl_odeiv2_step_alloc(const gsl_odeiv2_step_type *T, size_t dim
   gsl_odeiv2_step *s = calloc(1, sizeof *s);
   size_t n = dim ? dim : 1;
   s->type = T; s->dim = dim;
-  for (int i = 0; i < 6; i++) s->k[i] = calloc(n, sizeof(double));
+  for (int i = 0; i < MG_MAXK; i++) s->k[i] = calloc(n, sizeof(double));
   s->y0 = calloc(n, sizeof(double)); s->ytmp = calloc(n, sizeof(double)); s->yone = calloc(n, sizeof(double));
   return s;
 }
 void gsl_odeiv2_step_free(gsl_odeiv2_step *s) {
   if (!s) return;
-  for (int i = 0; i < 6; i++) free(s->k[i]);
+  for (int i = 0; i < MG_MAXK; i++) free(s->k[i]);
   free(s->y0); free(s->ytmp); free(s->yone); free(s);
 }
 gsl_odeiv2_control *gsl_odeiv2_control_y_new(double eps_abs, double eps_rel) {
@@ -197,6 +198,77 @@ static int rk2_apply(gsl_odeiv2_step *s, double t, double h, double y[], double 
   return GSL_SUCCESS;
 }
 
+/* GSL "rk8pd": Prince-Dormand 8(7) with 13 stages (RK8(7)13M).  The 8th-order weights Abar are propagated,
+ * yerr = h (ksum7 - ksum8) with the 7th-order weights A, order() = 8.  Sums run over the non-zero coefficients in stage order. */
+static const double RK8_AH[12] = {
+   1.0 / 18.0, 1.0 / 12.0, 1.0 / 8.0, 5.0 / 16.0, 3.0 / 8.0, 59.0 / 400.0, 93.0 / 200.0, 5490023248.0 / 9719169821.0, 13.0 / 20.0,
+   1201146811.0 / 1299019798.0, 1.0, 1.0};
+static const double RK8_B[12][12] = {
+   {1.0 / 18.0},
+   {1.0 / 48.0, 1.0 / 16.0},
+   {1.0 / 32.0, 0.0, 3.0 / 32.0},
+   {5.0 / 16.0, 0.0, -75.0 / 64.0, 75.0 / 64.0},
+   {3.0 / 80.0, 0.0, 0.0, 3.0 / 16.0, 3.0 / 20.0},
+   {29443841.0 / 614563906.0, 0.0, 0.0, 77736538.0 / 692538347.0, -28693883.0 / 1125000000.0, 23124283.0 / 1800000000.0},
+   {16016141.0 / 946692911.0, 0.0, 0.0, 61564180.0 / 158732637.0, 22789713.0 / 633445777.0, 545815736.0 / 2771057229.0,
+    -180193667.0 / 1043307555.0},
+   {39632708.0 / 573591083.0, 0.0, 0.0, -433636366.0 / 683701615.0, -421739975.0 / 2616292301.0, 100302831.0 / 723423059.0,
+    790204164.0 / 839813087.0, 800635310.0 / 3783071287.0},
+   {246121993.0 / 1340847787.0, 0.0, 0.0, -37695042795.0 / 15268766246.0, -309121744.0 / 1061227803.0, -12992083.0 / 490766935.0,
+    6005943493.0 / 2108947869.0, 393006217.0 / 1396673457.0, 123872331.0 / 1001029789.0},
+   {-1028468189.0 / 846180014.0, 0.0, 0.0, 8478235783.0 / 508512852.0, 1311729495.0 / 1432422823.0, -10304129995.0 / 1701304382.0,
+    -48777925059.0 / 3047939560.0, 15336726248.0 / 1032824649.0, -45442868181.0 / 3398467696.0, 3065993473.0 / 597172653.0},
+   {185892177.0 / 718116043.0, 0.0, 0.0, -3185094517.0 / 667107341.0, -477755414.0 / 1098053517.0, -703635378.0 / 230739211.0,
+    5731566787.0 / 1027545527.0, 5232866602.0 / 850066563.0, -4093664535.0 / 808688257.0, 3962137247.0 / 1805957418.0,
+    65686358.0 / 487910083.0},
+   {403863854.0 / 491063109.0, 0.0, 0.0, -5068492393.0 / 434740067.0, -411421997.0 / 543043805.0, 652783627.0 / 914296604.0,
+    11173962825.0 / 925320556.0, -13158990841.0 / 6184727034.0, 3936647629.0 / 1978049680.0, -160528059.0 / 685178525.0,
+    248638103.0 / 1413531060.0, 0.0}};
+static const double RK8_ABAR[13] = {
+   14005451.0 / 335480064.0, 0.0, 0.0, 0.0, 0.0, -59238493.0 / 1068277825.0, 181606767.0 / 758867731.0, 561292985.0 / 797845732.0,
+   -1041891430.0 / 1371343529.0, 760417239.0 / 1151165299.0, 118820643.0 / 751138087.0, -528747749.0 / 2220607170.0, 1.0 / 4.0};
+static const double RK8_A[13] = {
+   13451932.0 / 455176623.0, 0.0, 0.0, 0.0, 0.0, -808719846.0 / 976000145.0, 1757004468.0 / 5645159321.0, 656045339.0 / 265891186.0,
+   -3867574721.0 / 1518517206.0, 465885868.0 / 322736535.0, 53011238.0 / 667516719.0, 2.0 / 45.0, 0.0};
+/* test hook: the tableau as dense arrays, b[144] row-major */
+int minigsl_rk8pd_tableau(double *ah, double *b, double *abar, double *a7) {
+  int i, j;
+  for (i = 0; i < 12; i++) { ah[i] = RK8_AH[i]; for (j = 0; j < 12; j++) b[12 * i + j] = RK8_B[i][j]; }
+  for (i = 0; i < 13; i++) { abar[i] = RK8_ABAR[i]; a7[i] = RK8_A[i]; }
+  return 0;
+}
+static int rk8pd_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
+                       const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
+  const size_t n = s->dim; size_t i; int st, j;
+  double **k = s->k, *y0 = s->y0, *ytmp = s->ytmp;
+  memcpy(y0, y, n * sizeof(double));
+  if (dydt_in) memcpy(k[0], dydt_in, n * sizeof(double)); else FEVAL(sys, t, y, k[0]);
+  for (st = 1; st < 13; st++) {
+    for (i = 0; i < n; i++) {
+      double acc = 0.0;
+      for (j = 0; j < st; j++) if (RK8_B[st-1][j] != 0.0) acc += RK8_B[st-1][j] * k[j][i];
+      ytmp[i] = y[i] + h * acc;
+    }
+    FEVAL(sys, t + RK8_AH[st-1] * h, ytmp, k[st]);
+  }
+  for (i = 0; i < n; i++) {
+    double ksum8 = 0.0;
+    for (j = 0; j < 13; j++) if (RK8_ABAR[j] != 0.0) ksum8 += RK8_ABAR[j] * k[j][i];
+    y[i] += h * ksum8;
+  }
+  if (dydt_out) {
+    int s_ = sys->function(t + h, y, dydt_out, sys->params);
+    if (s_ != GSL_SUCCESS) { memcpy(y, y0, n * sizeof(double)); return s_; }
+  }
+  for (i = 0; i < n; i++) {
+    double ksum8 = 0.0, ksum7 = 0.0;
+    for (j = 0; j < 13; j++) if (RK8_ABAR[j] != 0.0) ksum8 += RK8_ABAR[j] * k[j][i];
+    for (j = 0; j < 13; j++) if (RK8_A[j] != 0.0) ksum7 += RK8_A[j] * k[j][i];
+    yerr[i] = h * (ksum7 - ksum8);
+  }
+  return GSL_SUCCESS;
+}
+
 static int step_apply(gsl_odeiv2_step *s, double t, double h, double y[], double yerr[],
                       const double dydt_in[], double dydt_out[], const gsl_odeiv2_system *sys) {
   switch (s->type->kind) {
@@ -204,6 +276,7 @@ static int step_apply(gsl_odeiv2_step *s, double t, double h, double y[], double
     case MG_RKCK:  return embedded_apply(s, &TAB_RKCK, t, h, y, yerr, dydt_in, dydt_out, sys);
     case MG_RK4:   return rk4_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
     case MG_RK2:   return rk2_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
+    case MG_RK8PD: return rk8pd_apply(s, t, h, y, yerr, dydt_in, dydt_out, sys);
     default:
       fprintf(stderr, "minigsl: stepper '%s' is not restated (no GSL source offline)\n", s->type->name);
       abort();

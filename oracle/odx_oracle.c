@@ -406,6 +406,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   else if (o->method == ORC_METH_RKCK) odeT = gsl_odeiv2_step_rkck;
   else if (o->method == ORC_METH_RK4) odeT = gsl_odeiv2_step_rk4;
   else if (o->method == ORC_METH_RK2) odeT = gsl_odeiv2_step_rk2;
+  else if (o->method == ORC_METH_RK8PD) odeT = gsl_odeiv2_step_rk8pd;
   t = o->tspan[0]; t1 = o->tspan[o->tspan_len - 1];
   /* stopping times = interior TIMESPAN values, sorted (src/methods_odexp.c:222-236); past the last one the reference reads
    * beyond its array, restated as "no further stop" */

@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-enum { ORC_METH_FE = 0, ORC_METH_DDE = 1, ORC_METH_RKF45 = 2, ORC_METH_RKCK = 3, ORC_METH_RK4 = 4, ORC_METH_ITERATION = 5, ORC_METH_RK2 = 6 };
+enum { ORC_METH_FE = 0, ORC_METH_DDE = 1, ORC_METH_RKF45 = 2, ORC_METH_RKCK = 3, ORC_METH_RK4 = 4, ORC_METH_ITERATION = 5, ORC_METH_RK2 = 6, ORC_METH_RK8PD = 7 };
 enum { ORC_EVENT_NONE = 0x00, ORC_EVENT_T0 = 0x01, ORC_EVENT_TFINAL = 0x02, ORC_STOP_TSPAN = 0x04, ORC_STOP_COND = 0x08, ORC_STOP_BIRTH = 0x10, ORC_STOP_DEATH = 0x20,
        ORC_STOP_REPLI = 0x40, ORC_POP_MASK = 0x70, ORC_EVENT_GSL = 0x100 };
 /* Philox domain tags, identical to odexp_b200/csrc/odx_rng.h (rng_mode 1 only) */

@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
-METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5, "rk2": 6}
+METHODS = {"fe": 0, "dde": 1, "rkf45": 2, "rkck": 3, "rk4": 4, "iteration": 5, "rk2": 6, "rk8pd": 7}
 DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0),
         "vdp_sde": dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0),
         "kuramoto_lowrank": dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=17),

@@ -118,16 +118,18 @@ def test_ring_neighbours_vs_oracle(model_lib, n, meth):
     pop.close()
 
 
-@pytest.mark.parametrize("model,n,ts", [("kuramoto", 257, (0, 3.0)), ("nbody", 40, (0, 0.2))])
-def test_gsl_rk2_vs_oracle(model_lib, model, n, ts):
-    """GSL's embedded rk2 (2, 3) through the general tableau kernel: same accept / reject sequence and states as the restatement"""
+@pytest.mark.parametrize("meth", ["rk2", "rk8pd"])
+@pytest.mark.parametrize("model,n,ts", [("kuramoto", 257, (0, 3.0)), ("nbody", 40, (0, 0.2)), ("ring_diffusion", 33, (0, 1.5))])
+def test_gsl_rk2_rk8pd_vs_oracle(model_lib, model, n, ts, meth):
+    """GSL's embedded rk2 (2, 3) and Prince-Dormand rk8pd (13 stages) through the general tableau kernel: same accept / reject
+    sequence and states as the restatement (ring_diffusion: KY() neighbours, alternating stage buffers with an odd stage count)"""
     from odexp_b200 import capi
     from oracle import port
     tol = 1e-8 if model == "nbody" else 1e-6
     pop = capi.Population(model_lib(model), capacity=1024)
-    out = capi.odesolver(pop, ts, meth="rk2", res=4, popsize=n, abstol=tol, reltol=tol, hmin=0.0 if model == "nbody" else 1e-5,
+    out = capi.odesolver(pop, ts, meth=meth, res=4, popsize=n, abstol=tol, reltol=tol, hmin=0.0 if model == "nbody" else 1e-5,
                          h0=0.02 if model == "nbody" else 0.1, replay_ic=True)
-    ref = port.run(model, {"meth": "rk2", "res": 4, "ps": n, "abstol": tol, "reltol": tol, "hmin": 0.0 if model == "nbody" else 1e-5,
+    ref = port.run(model, {"meth": meth, "res": 4, "ps": n, "abstol": tol, "reltol": tol, "hmin": 0.0 if model == "nbody" else 1e-5,
                            "h0": 0.02 if model == "nbody" else 0.1}, ts)
     assert len(out["stats"]) == len(ref["stats"])
     assert out["report"]["steps"] == ref["report"]["steps"]

@@ -63,6 +63,34 @@ def test_rk2_order_conditions_and_convergence():
     assert errs[2] < errs[1] < errs[0] and errs[0] < 1e-3 and errs[2] < 1e-7
 
 
+def test_rk8pd_order_conditions_and_convergence():
+    """Prince-Dormand RK8(7)13M as GSL's rk8pd: row sums equal the nodes, the rooted-tree conditions up to order 5 hold for both
+    weight sets, the quadrature conditions sum_j w_j c_j^(q-1) = 1/q up to q = 8 for the propagated weights and q = 7 (not 8) for the
+    comparison weights; the evolve loop converges at high order (a wrong digit in any coefficient breaks these at ~1e-9)"""
+    from oracle import port
+    L = port.lib()
+    P = C.POINTER(C.c_double)
+    ah, b, w8, w7 = np.zeros(12), np.zeros(144), np.zeros(13), np.zeros(13)
+    assert L.minigsl_rk8pd_tableau(ah.ctypes.data_as(P), b.ctypes.data_as(P), w8.ctypes.data_as(P), w7.ctypes.data_as(P)) == 0
+    A = np.zeros((13, 13)); A[1:, :12] = b.reshape(12, 12)
+    nodes = np.concatenate([[0.0], ah])
+    np.testing.assert_allclose(A.sum(axis=1), nodes, atol=4e-15)
+    assert np.abs(order_conditions(A, nodes, w8, 5)).max() < 2e-15
+    assert np.abs(order_conditions(A, nodes, w7, 5)).max() < 2e-15
+    for q in range(1, 9):
+        assert abs(w8 @ nodes**(q - 1) - 1 / q) < 1e-15
+        if q < 8: assert abs(w7 @ nodes**(q - 1) - 1 / q) < 1e-15
+    assert abs(w7 @ nodes**7 - 1 / 8) > 1e-5
+    ref = port.run("kuramoto", {"meth": "dde", "h0": 0.00025, "res": 2, "ps": 20}, (0, 2.0))["traj"]
+    yref = ref[ref["step"] == 1]["cols"][:, 0]
+    errs, steps = [], []
+    for tol in (1e-6, 1e-9, 1e-12):
+        out = port.run("kuramoto", {"meth": "rk8pd", "res": 2, "ps": 20, "abstol": tol, "reltol": tol, "h0": 0.5}, (0, 2.0))
+        tr = out["traj"]
+        errs.append(np.abs(tr[tr["step"] == 1]["cols"][:, 0] - yref).max()); steps.append(out["report"]["steps"])
+    assert errs[0] < 1e-6 and errs[1] < 1e-9 and errs[2] < 5e-12 and steps[2] < 40       # few steps even at 1e-12: high order
+
+
 def test_evolve_convergence_and_control():
     """K = 0 turns the Kuramoto fixture into theta' = omega (integrated exactly by any consistent RK method); with coupling, tightening
     the tolerance by 100 must reduce the error against a tiny-step RK4 run by ~100 (5th-order pair under standard control)."""

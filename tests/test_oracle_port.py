@@ -33,6 +33,7 @@ REF_CASES = [
     ("kuramoto", {"meth": "dde", "h0": 0.07, "res": 4, "ps": 333}, (0, 1.0)),
     ("kuramoto", {"meth": "rk4", "res": 4, "ps": 40}, (0, 3.0)),
     ("kuramoto", {"meth": "rk2", "res": 4, "ps": 25}, (0, 3.0)),
+    ("kuramoto", {"meth": "rk8pd", "res": 4, "ps": 25, "abstol": 1e-10, "reltol": 1e-10}, (0, 3.0)),
     ("nbody", {"meth": "rkck", "h0": 0.02, "res": 3, "ps": 48, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 0.2)),
     # birth / death: SSA (ssahmin 0) and tau-leaping (ssahmin 1), libc stream consumed draw for draw
     ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 21, "ps": 50, "ssahmin": 0.0}, (0, 4)),
