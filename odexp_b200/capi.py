@@ -51,7 +51,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
-               "odx_pop_download_strided"]
+               "odx_pop_download_strided", "odx_tauleap_apply_view"]
 
 
 def _dp(a):
@@ -100,6 +100,7 @@ class ModelLib:
         L.odx_run_fixed.argtypes = [H, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_int64]
         L.odx_ssa_apply.argtypes = [H, C.c_double, C.c_double, C.POINTER(EventRow)]
         L.odx_tauleap_apply.argtypes = [H, C.c_double, C.c_double, C.c_uint64, C.POINTER(EventRow), C.c_int64, C.POINTER(C.c_int64)]
+        L.odx_tauleap_apply_view.argtypes = [H, C.c_double, C.c_double, C.c_uint64, C.POINTER(C.POINTER(EventRow)), C.POINTER(C.c_int64)]
         L.odx_draw_uniform.argtypes = [H, C.c_int]; L.odx_draw_uniform.restype = C.c_double
         L.odx_draw_poisson.argtypes = [H, C.c_double, C.c_int]; L.odx_draw_poisson.restype = C.c_long
         L.odx_odesolver.argtypes = [H, C.POINTER(SolverOpts), C.POINTER(SolverReport)]
@@ -286,6 +287,18 @@ class Population:
     def tauleap_apply(self, t, dt, leap_index, max_rows=None, as_array=False):
         """one tau-leaping sweep; returns the stats.dat event rows (list of (n, stop_flag, (parent, +-1, child)), or with
         as_array=True a numpy structured array: no per-row Python work, for large populations)"""
+        nr = C.c_int64()
+        if as_array and max_rows is None:
+            # rows stay in the library's pinned buffer; the array is a copy of exactly the rows of this sweep
+            view = C.POINTER(EventRow)()
+            self._ck(self.L.odx_tauleap_apply_view(self.h, t, dt, int(leap_index), C.byref(view), C.byref(nr)), "odx_tauleap_apply_view")
+            dt_row = np.dtype([("n", "<i4"), ("stop_flag", "<i4"), ("event", "<i4", (3,))])
+            assert dt_row.itemsize == C.sizeof(EventRow)
+            if nr.value == 0:
+                return np.zeros(0, dtype=dt_row)
+            out = np.empty(nr.value, dtype=dt_row)
+            C.memmove(out.ctypes.data, view, nr.value * dt_row.itemsize)
+            return out
         n = self.size()[0]
         max_rows = max_rows or (3 * n + 4096)
         if as_array:
@@ -294,7 +307,6 @@ class Population:
             rows = buf.ctypes.data_as(C.POINTER(EventRow))
         else:
             rows = (EventRow * max_rows)()
-        nr = C.c_int64()
         self._ck(self.L.odx_tauleap_apply(self.h, t, dt, int(leap_index), rows, max_rows, C.byref(nr)), "odx_tauleap_apply")
         if as_array:
             return buf[:nr.value]

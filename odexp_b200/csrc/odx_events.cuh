@@ -250,6 +250,7 @@ __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
 struct EventBufs {
   int32_t *outcome = nullptr, *flag = nullptr, *scan = nullptr, *tile = nullptr, *grand = nullptr, *child = nullptr, *f3 = nullptr, *s3 = nullptr;
   odx_event_row *rows = nullptr; int64_t rows_cap = 0;
+  odx_event_row *rows_pin = nullptr; int64_t rows_pin_cap = 0;      /* pinned host copy of the event rows of the last sweep */
   AltBufs alt = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ready = false;
 };
@@ -267,8 +268,10 @@ static int exclusive_scan(odx_handle *h, const int32_t *in, int32_t *out, int64_
     k_scan_add<NCH><<<ntiles, BLOCK, 0, h->stream>>>(out, tile, n);
     ODX_TRY(launch_check(h));
   }
-  ODX_CUDA(h, cudaMemcpyAsync(grand_host, grand, sizeof(int32_t) * NCH, cudaMemcpyDeviceToHost, h->stream));
+  int32_t *pin = reinterpret_cast<int32_t *>(h->h_pin + NSLOT * NRED + 12);       /* pinned: a pageable target makes the copy a staged, blocking one */
+  ODX_CUDA(h, cudaMemcpyAsync(pin, grand, sizeof(int32_t) * NCH, cudaMemcpyDeviceToHost, h->stream));
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < NCH; c++) grand_host[c] = pin[c];
   return ODX_SUCCESS;
 }
 
@@ -285,6 +288,7 @@ static void odx_events_free(odx_handle *h) {
   void *ptrs[] = {b.outcome, b.flag, b.scan, b.tile, b.grand, b.child, b.f3, b.s3, b.rows, b.alt.Y, b.alt.E, b.alt.AUX, b.alt.PSI,
                   b.alt.DEATH, b.alt.REPLI, b.alt.ID};
   for (void *q : ptrs) if (q) cudaFree(q);
+  if (b.rows_pin) cudaFreeHost(b.rows_pin);
   delete h->ev_state;
   h->ev_state = nullptr;
 }
@@ -310,16 +314,27 @@ static int ensure_event_bufs(odx_handle *h, EventBufs &b) {
   return ODX_SUCCESS;
 }
 
-/* compaction + bookkeeping shared by tau-leap and SSA.  nsweep = particles covered by `outcome`, nbirth appended after. */
+/* compaction + bookkeeping shared by tau-leap and SSA.  nsweep = particles covered by `outcome`, nbirth appended after.
+ * The event rows land in a pinned host buffer owned by the library (a pageable target turns the 20-byte-per-event copy into a staged
+ * one at a few GB/s); `rows` (caller's memory, may be NULL) receives a copy, `view_out` (may be NULL) the pinned pointer itself. */
 static int finish_events(odx_handle *h, EventBufs &b, int64_t nsweep, int64_t nbirth, int32_t n0, odx_event_row *rows, int64_t max_rows,
-                         int64_t *nrows_out, int32_t *g3) {
+                         int64_t *nrows_out, int32_t *g3, const odx_event_row **view_out = nullptr) {
   Pop p = pop_view(h);
   const int g = grid_for(h, nsweep > 0 ? nsweep : 1);
   if (nsweep > 0) { k_sweep_flags<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.f3, nsweep); ODX_TRY(launch_check(h)); }
   ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3));
   const int32_t kept = g3[0], nrows = g3[1];
   int64_t written = 0;
-  if (rows && max_rows > 0 && nrows > 0) {
+  const bool want = (rows && max_rows > 0) || view_out;
+  if (view_out) max_rows = (int64_t)nrows + nbirth;
+  if (want && (int64_t)nrows + nbirth > b.rows_pin_cap) {
+    if (b.rows_pin) cudaFreeHost(b.rows_pin);
+    b.rows_pin = nullptr; b.rows_pin_cap = 0;
+    const int64_t cap2 = 2 * ((int64_t)nrows + nbirth) + 1024;
+    ODX_CUDA(h, cudaMallocHost((void **)&b.rows_pin, sizeof(odx_event_row) * (size_t)cap2));
+    b.rows_pin_cap = cap2;
+  }
+  if (want && nrows > 0) {
     if (b.rows_cap < nrows) {
       if (b.rows) cudaFree(b.rows);
       b.rows = nullptr; b.rows_cap = 0;
@@ -329,19 +344,20 @@ static int finish_events(odx_handle *h, EventBufs &b, int64_t nsweep, int64_t nb
     k_event_rows<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.s3, h->ID, b.child, nsweep, n0, b.rows, b.rows_cap);
     ODX_TRY(launch_check(h));
     written = nrows < max_rows ? nrows : max_rows;
-    ODX_CUDA(h, cudaMemcpyAsync(rows, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, h->stream));
-    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    ODX_CUDA(h, cudaMemcpyAsync(b.rows_pin, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, h->stream));
+    /* no synchronisation here: the copy overlaps the compaction below, the stream is synchronised before the rows are read */
   }
+  const int64_t sweep_rows = written;
   /* births: rows {n+1.., STOP_BIRTH, {-1, +1, id}} follow the sweep rows */
   const int32_t n_after_sweep = n0 - g3[2];
   const int32_t first_birth_id = h->max_id - (int32_t)nbirth;
   for (int64_t k = 0; k < nbirth; k++) {
-    if (rows && written < max_rows) {
+    if (want && written < max_rows) {
       odx_event_row e = {n_after_sweep + (int32_t)k + 1, ODX_STOP_BIRTH, {-1, 1, first_birth_id + (int32_t)k}};
-      rows[written++] = e;
+      b.rows_pin[written++] = e;
     }
   }
-  if (nrows_out) *nrows_out = written;
+  (void)sweep_rows;
   const int64_t ntotal = nsweep + nbirth;
   if (ntotal > 0) {
     k_compact<<<grid_for(h, ntotal), BLOCK, 0, h->stream>>>(p, b.alt, b.outcome, b.s3, nsweep, ntotal, kept);
@@ -351,7 +367,14 @@ static int finish_events(odx_handle *h, EventBufs &b, int64_t nsweep, int64_t nb
   std::swap(h->DEATH, b.alt.DEATH); std::swap(h->REPLI, b.alt.REPLI); std::swap(h->ID, b.alt.ID);
   h->n = kept + nbirth;
   invalidate_state(h);
-  return refresh_global_n(h);
+  ODX_TRY(refresh_global_n(h));
+  if (want) {
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));                 /* the rows have landed in the pinned buffer */
+    if (rows && written > 0) memcpy(rows, b.rows_pin, sizeof(odx_event_row) * (size_t)written);
+    if (view_out) *view_out = b.rows_pin;
+  }
+  if (nrows_out) *nrows_out = written;
+  return ODX_SUCCESS;
 }
 
 }  // namespace odx
@@ -440,12 +463,13 @@ static int replica_scatter(odx_handle *h) {
 
 extern "C" {
 
-int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows) {
+static int tauleap_core(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows,
+                        const odx_event_row **view_out) {
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (h->nranks > 1) {
 #ifdef ODX_HAVE_NCCL_H
     ODX_TRY(replica_gather(h));
-    int st = odx_tauleap_apply(h->replica, t, dt, leap_index, rows, max_rows, nrows);
+    int st = tauleap_core(h->replica, t, dt, leap_index, rows, max_rows, nrows, view_out);
     if (st != ODX_SUCCESS) { h->err = std::string("replicated sweep: ") + h->replica->err; return st; }
     return replica_scatter(h);
 #else
@@ -488,9 +512,18 @@ int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, o
     h->max_id += (int32_t)nnew;
   }
   int32_t g3[4];
-  ODX_TRY(finish_events(h, b, nsweep, nnew, n0, rows, max_rows, nrows, g3));
+  ODX_TRY(finish_events(h, b, nsweep, nnew, n0, rows, max_rows, nrows, g3, view_out));
   es->event_index++;
   return ODX_SUCCESS;
+}
+int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows) {
+  return tauleap_core(h, t, dt, leap_index, rows, max_rows, nrows, nullptr);
+}
+/* the same sweep, all event rows left in pinned host memory owned by the library (valid until the next birth / death call) */
+int odx_tauleap_apply_view(odx_handle *h, double t, double dt, uint64_t leap_index, const odx_event_row **rows, int64_t *nrows) {
+  if (!rows || !nrows) { h->err = "odx_tauleap_apply_view: rows and nrows must not be NULL"; return ODX_EINVAL; }
+  *rows = nullptr; *nrows = 0;
+  return tauleap_core(h, t, dt, leap_index, nullptr, 0, nrows, rows);
 }
 
 int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {

@@ -100,8 +100,8 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   enum { SSA, TAU_LEAPING } bd_meth = SSA;
   out_state os;
   char path[4096];
-  odx_event_row *rows = NULL;
-  int64_t rows_cap = 0, nrows = 0;
+  const odx_event_row *rows = NULL;       /* pinned memory owned by the library */
+  int64_t nrows = 0;
   uint64_t leap_index = 0;
   double *tstops = NULL, nextstop = INFINITY;
   int nstops = 0, idx_stop = 0;
@@ -225,13 +225,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
           write_stats_row(&os, t, row.n, row.stop_flag, row.event);
         }
       } else {
-        if (rows_cap < 3 * n + 1024) {
-          rows_cap = 3 * n + 1024 + (int64_t)(4.0 * birth_rate * dt_next);
-          free(rows);
-          rows = malloc(sizeof(odx_event_row) * rows_cap);
-          if (!rows) { status = ODX_ENOMEM; break; }
-        }
-        if ((status = odx_tauleap_apply(h, t, dt_next, leap_index++, rows, rows_cap, &nrows)) != 0) break;
+        if ((status = odx_tauleap_apply_view(h, t, dt_next, leap_index++, &rows, &nrows)) != 0) break;
         for (i = 0; i < nrows; i++) write_stats_row(&os, t, rows[i].n, rows[i].stop_flag, rows[i].event);
       }
       odx_pop_size(h, NULL, &n, NULL);
@@ -259,7 +253,7 @@ done:
   if (os.fstats) fclose(os.fstats);
   if (os.ftraj) fclose(os.ftraj);
   free(tstops);
-  free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids); free(rows);
+  free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids);
   if (rep) {
     rep->total_ms = now_ms() - t_start; rep->solver_ms = tot_solver; rep->steps = steps; rep->particle_steps = particle_steps;
     rep->status = status; rep->final_n = n;

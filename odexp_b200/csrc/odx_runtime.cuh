@@ -1289,6 +1289,7 @@ int odx_evolve_apply(odx_handle *h, int method, double *t, double t1, double *hs
 
 int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row);
 int odx_tauleap_apply(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows);
+int odx_tauleap_apply_view(odx_handle *h, double t, double dt, uint64_t leap_index, const odx_event_row **rows, int64_t *nrows);
 
 }  // extern "C"
 

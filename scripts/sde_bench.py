@@ -19,12 +19,12 @@ print("vdp_sde fe  N=%d  %.4f ms/step  %.3e particle-steps/s  %.0f GB/s at 48 B/
     n, best, n / (best * 1e-3), 48.0 * n / (best * 1e-3) / 1e9, 48.0 * n / (best * 1e-3) / 6550.4e9), flush=True)
 # tau-leap sweeps (each: rates -> flags -> scans -> spawn generations -> compaction -> event rows)
 pop.rhs(t); pop.sync()
-for k in range(3):
+for k in range(6):
     n0 = pop.size()[0]
     pop.sync()
     w0 = time.perf_counter()
     pop.event_record(0)
-    rows = pop.tauleap_apply(t, 1.0, k, max_rows=1 << 21, as_array=True)
+    rows = pop.tauleap_apply(t, 1.0, k, as_array=True, max_rows=(1 << 21) if os.environ.get('SDE_COPY_ROWS') else None)
     pop.event_record(1)
     pop.sync()
     w = time.perf_counter() - w0
