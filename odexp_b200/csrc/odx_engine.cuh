@@ -394,7 +394,10 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
 #endif
 constexpr int TMA_MAXBUF = TMA_MAXBUF_N;
 constexpr int TMA_NCOL_MAX = 3 * NVAR + NEXPR + NPSI;                       /* y0, e, psi, ys, acc */
-constexpr size_t TMA_SMEM = 192 * 1024;
+#ifndef TMA_SMEM_KB
+#define TMA_SMEM_KB 192      /* ring size per CTA: 192 KB with one CTA per SM */
+#endif
+constexpr size_t TMA_SMEM = (size_t)TMA_SMEM_KB * 1024;
 constexpr int PT_TMA = PERSIST_THREADS_TMA, PT_LD = PERSIST_THREADS;       /* CTA size of the two kernel variants */
 constexpr int TMA_CONS = PT_TMA - 32;                                      /* consumer threads (the last warp produces) */
 /* pairs of particles per consumer thread and ring tile: two when two tiles of the widest stage still fit (the per-tile work of a
@@ -900,15 +903,21 @@ __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s
   }
   cta_sync<NT>();
 }
-constexpr int PERSIST_MAX_CTAS = 256;
+#ifndef PERSIST_MAX_CTAS_N
+#define PERSIST_MAX_CTAS_N 256
+#endif
+constexpr int PERSIST_MAX_CTAS = PERSIST_MAX_CTAS_N;
 #ifndef PEER_POLL_ALL
 #define PEER_POLL_ALL 1
 #endif
 constexpr size_t PF_BYTES = TMA_SMEM + 128;
 /* PF_ON: the TMA-ring variant (768 threads, HBM-resident populations); otherwise plain 128-bit loads (1024 threads), which is
  * faster while the working set sits in L2 (measured crossover: 5-6 M Kuramoto particles per GPU) */
+#ifndef PERSIST_TMA_CTAS_PER_SM
+#define PERSIST_TMA_CTAS_PER_SM 1
+#endif
 template <bool PF_ON>
-__global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, (PF_ON || 1024 / PT_LD < 1) ? 1 : 1024 / PT_LD) k_chain_persist(Pop p, PersistArgs g) {
+__global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CTAS_PER_SM : ((1024 / PT_LD < 1) ? 1 : 1024 / PT_LD)) k_chain_persist(Pop p, PersistArgs g) {
   __shared__ double s_tot[NRED], s_bp[NRED];
   __shared__ uint32_t s_words[PERSIST_MAX_CTAS * LLW];
   extern __shared__ __align__(16) unsigned char s_dyn[];
