@@ -195,9 +195,10 @@ __device__ __forceinline__ void grid_reduce(double (&red)[NR], const Red &r) {
 }
 
 /* mean fields from raw sums: SIM->meanfield[k] /= POP_SIZE (src/odexp:897) */
-__device__ __forceinline__ void load_mfd(const double *__restrict__ sums, double n_global, double (&mfd)[A1(NMFD)]) {
+__device__ __forceinline__ void load_mfd(const Pop &p, const double *__restrict__ sums, double n_global, double (&mfd)[A1(NMFD)]) {
 #pragma unroll
   for (int k = 0; k < NMFD; k++) mfd[k] = (sums != nullptr) ? sums[k] / n_global : 0.0;
+  if (M::HAS_VECT_MFD && sums != nullptr) M::mfd_vect((NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu, n_global, mfd);      /* %M ... {vect} */
 }
 
 __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(BLOCK, CHAIN_MIN_BLOCKS) k_chain(Pop p, ChainA
 #pragma unroll
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
-  load_mfd(a.sums_in, p.n_global, mfd);
+  load_mfd(p, a.sums_in, p.n_global, mfd);
   TmaRing none{};
   chain_sweep<FIRST, LAST, false>(p, a, mfd, red, none);
   if (NMFD > 0 || M::HAS_BIRTH || (LAST && (M::HAS_DEATH || M::HAS_REPLI))) grid_reduce<NRED>(red, r);
@@ -971,6 +972,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
     for (int s = 0; s < g.nst; s++) {
 #pragma unroll
       for (int k = 0; k < NMFD; k++) mfd[k] = s_tot[k] / p.n_global;
+      if (M::HAS_VECT_MFD) M::mfd_vect((NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu, p.n_global, mfd);
       const bool last_stage = (s == g.nst - 1);
       if (last_stage && step == g.nsteps - 1 && blockIdx.x == 0 && threadIdx.x < NRED) g.sums_report[threadIdx.x] = s_tot[threadIdx.x];
       cta_sync<NTC>();
@@ -1116,7 +1118,7 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
 #pragma unroll
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
-  load_mfd(a.sums_in, p.n_global, mfd);
+  load_mfd(p, a.sums_in, p.n_global, mfd);
   for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
     double y[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)];
     double death = 0.0, repli = 0.0;
@@ -1293,7 +1295,7 @@ __global__ void __launch_bounds__(BLOCK) k_tab(Pop p, TabArgs a, Red r) {
 #pragma unroll
   for (int k = 0; k < NRED; k++) red[k] = 0.0;
   double mfd[A1(NMFD)];
-  load_mfd(a.sums_in, p.n_global, mfd);
+  load_mfd(p, a.sums_in, p.n_global, mfd);
   double rloc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
     double y0[A1(NVAR)], yc[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)];

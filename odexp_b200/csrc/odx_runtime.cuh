@@ -1139,6 +1139,7 @@ int odx_meanfields(odx_handle *h, double *mfd) {
   ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->sums, sizeof(double) * NSLOT * NRED, cudaMemcpyDeviceToHost, h->stream));
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int k = 0; k < NMFD; k++) mfd[k] = h->h_pin[(size_t)h->report_slot * NRED + k] / h->n_global;
+  if (M::HAS_VECT_MFD) M::mfd_vect(h->h_mu, h->n_global, mfd);
   return ODX_SUCCESS;
 }
 

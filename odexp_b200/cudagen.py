@@ -323,6 +323,11 @@ def _zmul_peephole(expr: str) -> str:
             pos = b + len("odx_sel(")
 
 
+def is_vect(e):
+    """%M name rhs {vect} / {noloop}"""
+    return bool(re.search(r"\b(vect|noloop)\b", getattr(e, "attr", "") or ""))
+
+
 class Emitter:
     def __init__(self, m: PopModel, fast_pow: bool = True, fast_div: bool = True):
         self.m = m
@@ -593,6 +598,9 @@ class Emitter:
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m;")
         tc = {}
         for e in m.mfds:
+            if is_vect(e):
+                w("    odx_m[%d] = 0.0;      /* {vect}: no per-particle term, see mfd_vect */" % self.mfd_idx[e.name])
+                continue
             w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w)))
         w("  }\n")
         w("  /* the same terms for the state one stage after the one the RHS was evaluated at: sin / cos of an argument the RHS has")
@@ -602,7 +610,24 @@ class Emitter:
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m; (void)odx_h;")
         tc = {}
         for e in m.mfds:
+            if is_vect(e):
+                w("    odx_m[%d] = 0.0;" % self.mfd_idx[e.name])
+                continue
             w("    odx_m[%d] = %s;" % (self.mfd_idx[e.name], self.cse(self.tr(e.rhs, "%M " + e.name), tc, w, hinted=hint_slots)))
+        w("  }\n")
+        # ---- %M ... {vect}
+        vects = [e for e in m.mfds if is_vect(e)]
+        w("  /* %M ... {vect}: evaluated once per RHS evaluation from POP_SIZE, the parameters and the mean fields before it, in file order")
+        w("   * (reference: `SIM->meanfield[k] = rhs;` instead of the list walk, src/odexp:886-889) */")
+        w("  static constexpr bool HAS_VECT_MFD = %s;" % ("true" if vects else "false"))
+        w("  ODX_HD static void mfd_vect(const double *odx_mu, double odx_pop_size, double *odx_mfd) {")
+        w("    (void)odx_mu; (void)odx_pop_size; (void)odx_mfd;")
+        if vects:
+            w("    struct { const double *mu; double pop_size; } odx_c = {odx_mu, odx_pop_size}; (void)odx_c;")
+        for e in vects:
+            if re.search(r"\b(MY|ME|MA|OY|OE|OA|SY|SE|SA|MC|KY|DWDT|rand01|randN)\b", e.rhs):
+                raise PopError("%%M %s {vect}: the expression is evaluated once, it cannot read a particle (%s)" % (e.name, e.rhs))
+            w("    odx_mfd[%d] = %s;" % (self.mfd_idx[e.name], self.tr(e.rhs, "%M " + e.name + " {vect}", exact=True)))
         w("  }\n")
         w("  template <bool ODX_EXACT, class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux) {")

@@ -229,9 +229,7 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body))
     elif kwl == "%m" or kwl.startswith("%m"):
         e = _name_and_rhs(rest, lineno, raw)
-        if re.search(r"\b(vect|noloop)\b", e.attr):
-            raise PopError("line %d: %%M {vect} is not supported" % lineno)
-        m.mfds.append(e)
+        m.mfds.append(e)          # {vect} / {noloop}: evaluated once instead of averaged over the particles (Entry.attr)
     elif kwl.startswith("%c"):
         rest2, attr = _split_attr(rest)
         f = rest2.split(None, 1)

@@ -182,7 +182,30 @@ static void ring_ic(orc_ctx *c, double t, double *y, double *e) {
   y[1] = 0.0;
 }
 
+/* ---------------------------------------------------------------- vect_meanfield.pop */
+static const double vm_pars[] = {0.5, 0.1};
+static void vm_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double a = c->mu[0], x = y_[0], TOTAL = mfd[1], SCALED = mfd[2];
+  const double w = x * TOTAL;
+  (void)t; (void)e; (void)psi; (void)repli;
+  f[0] = -a * x + 0.01 * SCALED;
+  aux[0] = w;
+  *death = c->mu[1];                                  /* %DEATH MU(d) */
+}
+static double vm_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];                                        /* %M XBAR MY(x) */
+}
+static const int vm_vect[] = {0, 1, 1};
+static double vm_vect_eval(int k, const double *mu, double pop_size, const double *mfd) {
+  return k == 1 ? pop_size : mu[0] * mfd[0] * pop_size;     /* TOTAL = POP_SIZE; SCALED = MU(a)*MF(XBAR)*POP_SIZE */
+}
+static double vm_birth(orc_ctx *c, const double *y, const double *e, const double *aux) { (void)c; (void)y; (void)e; (void)aux; return 2.0; }
+static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
+
 static const orc_model MODELS[] = {
+  {"vect_meanfield", 1, 0, 1, 0, 3, 2, vm_pars, vm_rhs, vm_mfd, vm_birth, NULL, vm_ic, 0, 0, 0, 0, 0, NULL, vm_vect, vm_vect_eval},
   {"ring_diffusion", 2, 1, 1, 0, 1, 3, ring_pars, ring_rhs, ring_mfd, NULL, NULL, ring_ic, 0, 0, 0, 0, 0, NULL},
   {"reset_decay", 1, 1, 1, 0, 1, 2, rd_pars, rd_rhs, rd_mfd, NULL, NULL, rd_ic, 0, 0, 0, 0, 0, NULL},
   {"logistic_map", 1, 1, 1, 0, 1, 2, lm_pars, lm_rhs, lm_mfd, NULL, NULL, lm_ic, 0, 0, 0, 0, 0, NULL},

@@ -178,6 +178,7 @@ int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
   if (m->lr_rank > 0) orc_lowrank_apply(s);      /* low-rank coupling between pass 1 and the mean fields (src/odexp:841) */
   /* one walk per mean field, summed in list order, then divided by POP_SIZE */
   for (k = 0; k < m->nmfd; k++) {
+    if (m->mfd_vect && m->mfd_vect[k]) { s->mfd[k] = m->mfd_vect_eval(k, s->mu, (double)s->size, s->mfd); continue; }      /* {vect} */
     for (i = 0; i < s->n; i++) { orc_par *p = s->p[i]; rhs_ctx(s, &c, p); s->mfd[k] += m->mfd_term(&c, k, p->y, p->expr, p->aux, s->mfd); }
     s->mfd[k] /= s->size;
   }

@@ -46,6 +46,10 @@ typedef struct {
   /* low-rank %C ... lrwexp {var, fun, U, V, rank}: lr_rank == 0 means none */
   int lr_rank, lr_psi, lr_var, lr_iu, lr_iv;
   double (*lr_fun)(double);
+  /* %M ... {vect}: mean field k with mfd_vect[k] != 0 is assigned once (no list walk, src/odexp:886-889) from POP_SIZE, the
+   * parameters and the mean fields before it */
+  const int *mfd_vect;
+  double (*mfd_vect_eval)(int k, const double *mu, double pop_size, const double *mfd);
 } orc_model;
 
 typedef struct {

@@ -65,6 +65,25 @@ def test_ssa_single_events(model_lib, ps, seed):
     compare(out, ref)
 
 
+@pytest.mark.parametrize("meth,opts,ts", [
+    ("fe", {"h0": 0.01, "res": 21, "ps": 10, "ssahmin": 0.0}, (0, 2)),                  # SSA single events
+    ("fe", {"h0": 0.01, "res": 11, "ps": 40, "ssahmin": 1.0}, (0, 2)),                  # tau-leaping
+    ("dde", {"h0": 0.05, "res": 9, "ps": 500, "ssahmin": 1.0, "seed": 4}, (0, 2)),
+    ("rkck", {"h0": 0.1, "res": 5, "ps": 12, "ssahmin": 1.0}, (0, 1)),
+    ("rk8pd", {"h0": 0.1, "res": 5, "ps": 300, "ssahmin": 1.0, "seed": 8}, (0, 1)),
+])
+def test_vect_meanfields_with_birth_death(model_lib, meth, opts, ts):
+    """%M ... {vect} (src/odexp:886-889): POP_SIZE as a mean field and a vect field reading a looped one, while the
+    population size changes under SSA / tau-leaping; the mean-field columns of every trajectory row are compared too"""
+    opts = dict(opts, meth=meth)
+    out, ref = run_both(model_lib, "vect_meanfield", opts, ts)
+    assert len(np.unique(out["stats"]["n"])) > 1, "population size must change during the run"
+    compare(out, ref)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=1e-11, atol=1e-13)
+    solver_rows = out["stats"]["event"][:, 1] == 0          # event rows are written before the mean fields are re-evaluated
+    np.testing.assert_array_equal(out["stats"]["mfd"][solver_rows, 1], out["stats"]["n"][solver_rows].astype(float))      # TOTAL == POP_SIZE
+
+
 def test_population_can_die_out(model_lib):
     """edge: every particle dies (huge death rate, no births): the loop stops with an empty population"""
     from odexp_b200 import capi

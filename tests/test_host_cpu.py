@@ -63,6 +63,20 @@ def test_emit_translates_macros():
     assert "odx_c.dwdt()" in sde and "odx_c.atbirth" in sde and "HAS_BIRTH = true" in sde
 
 
+def test_emit_vect_meanfields():
+    """%M name rhs {vect}: assigned once per RHS evaluation (src/odexp:886-889), never summed over the particles"""
+    from odexp_b200 import popfile, cudagen
+    m = popfile.parse_file(fixture_path("vect_meanfield"))
+    assert [cudagen.is_vect(e) for e in m.mfds] == [False, True, True]
+    cu = cudagen.emit_cuda(m)
+    assert "HAS_VECT_MFD = true" in cu and "odx_mfd[1] = " in cu and "odx_mfd[2] = " in cu
+    assert "odx_m[1] = 0.0;" in cu and "odx_m[2] = 0.0;" in cu          # no per-particle term
+    assert "HAS_VECT_MFD = false" in cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto")))
+    bad = popfile.parse("%M T MY(x) {vect}\ndx/dt = -x\ninit x 1\n")
+    with pytest.raises(popfile.PopError):
+        cudagen.emit_cuda(bad)
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")

@@ -49,6 +49,10 @@ REF_CASES = [
     ("reset_decay", {"meth": "dde", "h0": 0.05, "res": 25, "ps": 20}, (0, 1.5, 3.25, 6)),
     ("reset_decay", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 7}, (0, 0.5, 4.0, 4.1, 7)),
     ("kuramoto", {"meth": "rkf45", "h0": 0.1, "res": 6, "ps": 30}, (0, 0.7, 2.0)),
+    # %M ... {vect} mean fields (POP_SIZE as a mean field) in a birth / death population: SSA and tau-leaping
+    ("vect_meanfield", {"meth": "fe", "h0": 0.01, "res": 21, "ps": 10, "ssahmin": 0.0}, (0, 2)),
+    ("vect_meanfield", {"meth": "fe", "h0": 0.01, "res": 11, "ps": 40, "ssahmin": 1.0}, (0, 2)),
+    ("vect_meanfield", {"meth": "rkck", "h0": 0.1, "res": 5, "ps": 12, "ssahmin": 1.0}, (0, 1)),
     # KY() list neighbours on a ring (src/odexp.h:334-357), fixed-step and adaptive
     ("ring_diffusion", {"meth": "dde", "h0": 0.05, "res": 11, "ps": 50}, (0, 2.0)),
     ("ring_diffusion", {"meth": "fe", "h0": 0.01, "res": 5, "ps": 7}, (0, 0.5)),
