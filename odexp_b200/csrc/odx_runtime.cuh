@@ -91,7 +91,7 @@ struct odx_handle {
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_attached = false;
   /* low-rank coupling scratch + options (opt lrmax / lrabstol / lrreltol) */
-  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr; bool lr_attr_done = false;
+  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr, *lr_x = nullptr; bool lr_attr_done = false;
   int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
@@ -169,8 +169,25 @@ static int launch_check(odx_handle *h) {
 }
 
 #ifdef ODX_MODEL_HAS_LOWRANK
+/* the expansion variable of `%C ... lrwexp {var = <auxiliary variable>}`: the generated gather reads myself_->aux after pass 1 of
+ * pop_rhs (mvar(), src/odexp:1578, src/datastruct.c:840-850), i.e. ode_rhs of the stage state with zeroed mean fields and the psi
+ * of the previous evaluation */
+__global__ void __launch_bounds__(BLOCK) k_lr_x_aux(Pop p, const double *__restrict__ ysrc, double t, double *__restrict__ x) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y[A1(NVAR)], e[A1(NEXPR)], psi[A1(NPSI)], f[A1(NVAR)], aux[A1(NAUX)], mz[A1(NMFD)], d = 0.0, r = 0.0;
+    load_cols<NVAR>(ysrc, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    load_cols<NPSI>(p.PSI, p.stride, i, psi);
+#pragma unroll
+    for (int k = 0; k < A1(NMFD); k++) mz[k] = 0.0;
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
+    M::template rhs<true>(c, t, y, e, psi, mz, f, aux, d, r);
+    x[i] = aux[M::LR0_VAR_KIND == 1 ? M::LR0_VAR : 0];
+  }
+}
+
 /* lrwpkern on the device (see odx_lowrank.cuh); writes PSI[LR0_PSI] */
-static int compute_lowrank(odx_handle *h, const double *ysrc) {
+static int compute_lowrank(odx_handle *h, const double *ysrc, double t) {
   const int64_t n = h->n;
   if (n <= 0 && h->nranks <= 1) return ODX_SUCCESS;
 #ifdef ODX_HAVE_NCCL_H
@@ -189,6 +206,12 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
   }
   const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
+  if (M::LR0_VAR_KIND == 2) x = h->E + (size_t)M::LR0_VAR * h->cap;
+  if (M::LR0_VAR_KIND == 1) {
+    if (!h->lr_x) ODX_CUDA(h, cudaMalloc((void **)&h->lr_x, sizeof(double) * h->cap));
+    if (n > 0) { k_lr_x_aux<<<grid_for(h, n), BLOCK, 0, h->stream>>>(pop_view(h), ysrc, t, h->lr_x); ODX_TRY(launch_check(h)); }
+    x = h->lr_x;
+  }
   k_lr_stats<<<grid_for(h, n), BLOCK, 0, h->stream>>>(x, n, h->lr_spart, h->counter + 1, h->lr_stats);
   ODX_TRY(launch_check(h));
 #ifdef ODX_HAVE_NCCL_H
@@ -261,7 +284,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc) {
 /* psi for the state in ysrc (all-pairs %C).  Multi-GPU: allgather of the coupled columns first. */
 static int compute_psi(odx_handle *h, const double *ysrc, double t) {
 #ifdef ODX_MODEL_HAS_LOWRANK
-  ODX_TRY(compute_lowrank(h, ysrc));
+  ODX_TRY(compute_lowrank(h, ysrc, t));
 #endif
   if (!M::HAS_PAIR) return ODX_SUCCESS;
   if (h->n <= 0) return ODX_SUCCESS;
@@ -794,7 +817,7 @@ void odx_destroy(odx_handle *h) {
   if (h->gcol) cudaFree(h->gcol);
   if (h->lr_plan) cudaFree(h->lr_plan);
   if (h->lr_rank) cudaFree(h->lr_rank);
-  { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A}; for (double *q : lb) if (q) cudaFree(q); }
+  { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A, h->lr_x}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   if (h->ll_words) cudaFree(h->ll_words);

@@ -685,8 +685,18 @@ class Emitter:
         for k, c in enumerate(lr_cpls):
             d = c.lowrank
             var = d.get("var")
-            if var not in self.var_idx:
-                raise PopError("low-rank coupling %s: var=%s is not a dynamical variable" % (c.name, var))
+            # the generated gather uses mvar(): dynamical variables, then auxiliary variables, then expressions (src/datastruct.c:824-855)
+            if var in self.var_idx:
+                var_kind, var_i = 0, self.var_idx[var]
+            elif var in self.aux_idx:
+                var_kind, var_i = 1, self.aux_idx[var]
+                if rhs_rng:
+                    raise PopError("low-rank coupling %s: var=%s is an auxiliary variable of a model with random numbers in its RHS "
+                                   "(its pass-1 value would consume draws)" % (c.name, var))
+            elif var in self.expr_base and not next(e for e in m.exprs if e.name == var).length:
+                var_kind, var_i = 2, self.expr_base[var]
+            else:
+                raise PopError("low-rank coupling %s: var=%s is not a dynamical variable, an auxiliary variable or a scalar expression" % (c.name, var))
             fun = d.get("fun", "sin")
             rank = int(d.get("rank", "1")) if d["kind"] == "lrwexp" else 0
             ub = self.expr_base.get(d.get("U", ""), -1) if d["kind"] == "lrwexp" else -1
@@ -694,7 +704,8 @@ class Emitter:
             if d["kind"] == "lrwexp" and (ub < 0 or vb < 0):
                 raise PopError("low-rank coupling %s: U/V must name EXPR arrays" % c.name)
             w("  static constexpr int LR%d_PSI = %d, LR%d_VAR = %d, LR%d_RANK = %d, LR%d_U = %d, LR%d_V = %d;" %
-              (k, self.psi_idx[c.name], k, self.var_idx[var], k, rank, k, ub, k, vb))
+              (k, self.psi_idx[c.name], k, var_i, k, rank, k, ub, k, vb))
+            w("  static constexpr int LR%d_VAR_KIND = %d;      /* LR%d_VAR indexes 0: Y, 1: AUX (pass-1 value), 2: EXPR */" % (k, var_kind, k))
             w("  ODX_HD static double lr%d_fun(double x) { return %s(x); }" % (k, mangle(fun)))
         w("")
         # ---- static info

@@ -182,6 +182,32 @@ static void ring_ic(orc_ctx *c, double t, double *y, double *e) {
   y[1] = 0.0;
 }
 
+/* ---------------------------------------------------------------- kuramoto_lowrank_aux.pop (LET R 3, LET N 100) */
+#define LRA_R 3
+#define LRA_PI 3.141592
+static const double klra_pars[] = {0.1};
+static void klra_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                     double *aux, double *death, double *repli) {
+  const double K = c->mu[0], omega = e[0], th = y_[0], CPL = psi[0];
+  const double y = sin(th);
+  const double theta = th - ( (int) (th/2/LRA_PI) * 2 * LRA_PI );      /* aux theta: the expansion variable of the coupling */
+  (void)t; (void)mfd; (void)death; (void)repli;
+  f[0] = omega + K/100*CPL;
+  aux[0] = y; aux[1] = theta;
+}
+static double klra_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)y; (void)mfd;
+  return k == 0 ? e[0] : aux[0];                       /* %M Omega ME(omega); %M MEANY MA(y) */
+}
+static void klra_ic(orc_ctx *c, double t, double *y, double *e) {
+  int i;
+  (void)t;
+  e[0] = orc_randN(c, 2*LRA_PI/10.0, 0.1);
+  for (i = 0; i < LRA_R; i++) e[1 + i] = orc_rand01(c);
+  for (i = 0; i < LRA_R; i++) e[1 + LRA_R + i] = orc_rand01(c);
+  y[0] = 2*LRA_PI*orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- vect_meanfield.pop */
 static const double vm_pars[] = {0.5, 0.1};
 static void vm_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -205,6 +231,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},
   {"vect_meanfield", 1, 0, 1, 0, 3, 2, vm_pars, vm_rhs, vm_mfd, vm_birth, NULL, vm_ic, 0, 0, 0, 0, 0, NULL, vm_vect, vm_vect_eval},
   {"ring_diffusion", 2, 1, 1, 0, 1, 3, ring_pars, ring_rhs, ring_mfd, NULL, NULL, ring_ic, 0, 0, 0, 0, 0, NULL},
   {"reset_decay", 1, 1, 1, 0, 1, 2, rd_pars, rd_rhs, rd_mfd, NULL, NULL, rd_ic, 0, 0, 0, 0, 0, NULL},

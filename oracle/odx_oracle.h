@@ -50,6 +50,9 @@ typedef struct {
    * parameters and the mean fields before it */
   const int *mfd_vect;
   double (*mfd_vect_eval)(int k, const double *mu, double pop_size, const double *mfd);
+  /* what lr_var indexes: 0 a dynamical variable, 1 an auxiliary variable (its pass-1 value), 2 a parametric expression --
+   * the generated gather calls mvar(name, ...) which searches the three in this order (src/datastruct.c:824-855) */
+  int lr_var_kind;
 } orc_model;
 
 typedef struct {

@@ -72,3 +72,31 @@ def test_lowrank_rank64_matches_restatement(model_lib, ps):
     assert np.abs(psi_a - psi_b).max() <= 1e-8 * scale
     np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("meth,ps,ts,res", [("dde", 100, (0, 2.0), 5), ("rkf45", 57, (0, 25.0), 4), ("fe", 1500, (0, 12.0), 3)])
+def test_lowrank_in_an_auxiliary_variable(model_lib, meth, ps, ts, res):
+    """`%C CPL lrwexp {var = theta}` with theta an AUXILIARY variable (the wrapped phase), as in the reference's shipped
+    examples/kuramoto_lowrank.pop: the gather reads the aux values pass 1 of pop_rhs left (mvar, src/datastruct.c:824-855); plus
+    MA() inside %M.  The long runs take the phases past 2 pi, where the wrapped variable jumps."""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto_lowrank_aux")
+    opts = {"meth": meth, "h0": 0.1, "res": res, "ps": ps}
+    pop = capi.Population(lib, capacity=max(1024, ps))
+    out = capi.odesolver(pop, ts, meth=meth, res=res, popsize=ps, h0=0.1, replay_ic=True)
+    pop.close()
+    ref = port.run("kuramoto_lowrank_aux", opts, ts)
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb)
+    np.testing.assert_array_equal(ta["id"], tb["id"])
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, 6:], tb[tb["step"] == 0]["cols"][:, 6:])     # omega, U, V
+    if ts[1] > 10:
+        assert (tb["cols"][:, 0] > 2 * 3.141592).any() and (tb["cols"][:, 2] < tb["cols"][:, 0] - 6).any(), "phases must wrap"
+    psi_a, psi_b = ta["cols"][:, 3], tb["cols"][:, 3]
+    scale = np.abs(psi_b).max()
+    print("max |dpsi|/scale", np.abs(psi_a - psi_b).max() / scale)
+    assert np.abs(psi_a - psi_b).max() <= 1e-8 * scale
+    np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)            # theta
+    np.testing.assert_allclose(ta["cols"][:, 1:3], tb["cols"][:, 1:3], rtol=0, atol=1e-9)             # aux y, aux theta (wrapped)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)

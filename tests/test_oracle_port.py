@@ -43,6 +43,9 @@ REF_CASES = [
     ("kuramoto_lowrank", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 256}, (0, 0.4)),
     ("kuramoto_lowrank", {"meth": "rkck", "res": 3, "ps": 300}, (0, 1.0)),
     ("kuramoto_lowrank64", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 203}, (0, 0.4)),        # rank 64 (BASELINE config 3)
+    # low-rank coupling expanded in an AUXILIARY variable (the wrapped phase, as in the shipped examples/kuramoto_lowrank.pop) + MA() in %M
+    ("kuramoto_lowrank_aux", {"meth": "dde", "h0": 0.1, "res": 5, "ps": 100}, (0, 2.0)),
+    ("kuramoto_lowrank_aux", {"meth": "rkf45", "h0": 0.1, "res": 4, "ps": 57}, (0, 25.0)),       # phases pass 2 pi: the aux wraps
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
