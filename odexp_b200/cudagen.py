@@ -519,13 +519,17 @@ class Emitter:
         w('#include <math.h>\n#include <stdint.h>\n#include "odx.h"\n#include "odx_rng.h"\n#include "odx_model_prelude.cuh"\n')
         for name, val in m.macros:
             w("#define %s %s" % (mangle(name), _mangle_expr(val)))
+        # constant scalars / arrays (`decl const double a[] = {..}`, file scope in the reference's model.c): constexpr locals of every
+        # generated function, so that host and device code index the same values without a __constant__ / host copy pair
+        w("#define ODX_CONSTS %s" % " ".join("constexpr %s %s%s = %s; (void)%s;" % (t, mangle(n), d, _mangle_expr(init), mangle(n))
+                                             for t, n, d, init in m.consts))
         w("")
         for f in m.funs:
             args = ", ".join("double %s" % mangle(a) for a in f.args)
             body = _pow_peephole(f.body) if self.fast_pow else f.body
             body = _div_peephole(body) if self.fast_div else body
             body = _mangle_expr(_ternary_to_select(body))
-            w("ODX_HD double %s(%s) { return %s; }" % (mangle(f.name), args, body))
+            w("ODX_HD double %s(%s) { ODX_CONSTS return %s; }" % (mangle(f.name), args, body))
         w("")
         # sincos arguments shared by the RHS and the %M terms: candidates for the stage-to-stage increment
         hint_slots = {}
@@ -559,8 +563,9 @@ class Emitter:
             w("      const double *odx_psi, const double *odx_mfd, double *odx_f, double *odx_aux, double &odx_death, double &odx_repli,")
             w("      %sOdxHint *odx_h = nullptr) {" % ("const OdxHint &odx_hi, " if inc else ""))
             w("    (void)t; (void)odx_psi; (void)odx_mfd; (void)odx_e; (void)odx_h;%s" % (" (void)odx_hi;" if inc else ""))
+            w("    ODX_CONSTS")
             for i, p in enumerate(m.pars):
-                if not re.search(r"\b(init|impl)\b", p.attr, flags=re.I):
+                if not re.search(r"\b(init|impl)", p.attr, flags=re.I):
                     ctype = "double"
                     mt = re.search(r"\b(int|long|double)\b", p.attr)
                     if mt:
@@ -596,6 +601,7 @@ class Emitter:
         w("  template <bool ODX_EXACT, class C> ODX_HD static void mfd_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, double *odx_m) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m;")
+        w("    ODX_CONSTS")
         tc = {}
         for e in m.mfds:
             if is_vect(e):
@@ -608,6 +614,7 @@ class Emitter:
         w("  template <bool ODX_EXACT, class C> ODX_HD static void mfd_terms_inc(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, double *odx_m, const OdxHint &odx_h) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_m; (void)odx_h;")
+        w("    ODX_CONSTS")
         tc = {}
         for e in m.mfds:
             if is_vect(e):
@@ -622,6 +629,7 @@ class Emitter:
         w("  static constexpr bool HAS_VECT_MFD = %s;" % ("true" if vects else "false"))
         w("  ODX_HD static void mfd_vect(const double *odx_mu, double odx_pop_size, double *odx_mfd) {")
         w("    (void)odx_mu; (void)odx_pop_size; (void)odx_mfd;")
+        w("    ODX_CONSTS")
         if vects:
             w("    struct { const double *mu; double pop_size; } odx_c = {odx_mu, odx_pop_size}; (void)odx_c;")
         for e in vects:
@@ -632,6 +640,7 @@ class Emitter:
         w("  template <bool ODX_EXACT, class C> ODX_HD static double birth_term(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c;")
+        w("    ODX_CONSTS")
         w("    return %s;" % (self.tr(m.birth, "%BIRTH") if m.birth else "0.0"))
         w("  }\n")
         # ---- %C terms
@@ -639,6 +648,7 @@ class Emitter:
         w("  template <bool ODX_EXACT, class C> ODX_HD static void cpl_terms(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, const double *odx_oy, const double *odx_oe, const double *odx_oaux, double *odx_p) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_oy; (void)odx_oe; (void)odx_oaux; (void)odx_c; (void)odx_p;")
+        w("    ODX_CONSTS")
         tc = {}
         scales = {}
         for c in pair_cpls:
@@ -655,6 +665,7 @@ class Emitter:
         w("  template <bool ODX_EXACT, class C> ODX_HD static void cpl_scale(C &odx_c, double t, const double *odx_y, const double *odx_e,")
         w("      const double *odx_aux, double *odx_s) {")
         w("    (void)t; (void)odx_y; (void)odx_e; (void)odx_aux; (void)odx_c; (void)odx_s;")
+        w("    ODX_CONSTS")
         for c in pair_cpls:
             w("    odx_s[%d] = %s;" % (self.psi_idx[c.name], scales.get(c.name) or "1.0"))
         w("  }\n")
@@ -662,8 +673,9 @@ class Emitter:
         w("  /* ode_init_conditions: EXPR in file order, then INIT in file order (draw order matters for replay) */")
         w("  template <class C> ODX_HD static void ic(C &odx_c, double t, double *odx_y, double *odx_e) {")
         w("    (void)t; (void)odx_e;")
+        w("    ODX_CONSTS")
         for i, p in enumerate(m.pars):
-            if re.search(r"\b(init|ever)\b", p.attr, flags=re.I):
+            if re.search(r"\b(init|ever)", p.attr, flags=re.I):
                 w("    const double %s = odx_c.mu[%d];" % (mangle(p.name), i))
         for e in m.exprs:
             b = self.expr_base[e.name]
@@ -699,8 +711,10 @@ class Emitter:
                 raise PopError("low-rank coupling %s: var=%s is not a dynamical variable, an auxiliary variable or a scalar expression" % (c.name, var))
             fun = d.get("fun", "sin")
             rank = int(d.get("rank", "1")) if d["kind"] == "lrwexp" else 0
-            ub = self.expr_base.get(d.get("U", ""), -1) if d["kind"] == "lrwexp" else -1
-            vb = self.expr_base.get(d.get("V", ""), -1) if d["kind"] == "lrwexp" else -1
+            # `U = U[0]` (the shipped examples/kuramoto_lowrank.pop) names the first element of the array: same column base
+            base = lambda key: self.expr_base.get(re.sub(r"\[\s*0\s*\]$", "", d.get(key, "").strip()), -1)
+            ub = base("U") if d["kind"] == "lrwexp" else -1
+            vb = base("V") if d["kind"] == "lrwexp" else -1
             if d["kind"] == "lrwexp" and (ub < 0 or vb < 0):
                 raise PopError("low-rank coupling %s: U/V must name EXPR arrays" % c.name)
             w("  static constexpr int LR%d_PSI = %d, LR%d_VAR = %d, LR%d_RANK = %d, LR%d_U = %d, LR%d_V = %d;" %

@@ -62,6 +62,7 @@ class PopModel:
     repli: Optional[str] = None
     options: Dict[str, str] = field(default_factory=dict)
     timespan: List[float] = field(default_factory=list)
+    consts: List[Tuple[str, str, str, str]] = field(default_factory=list)      # (C type, name, "[..]" or "", initialiser)
 
     # flattened dimensions (arrays count element-wise, as in the reference's nbr_expr etc.)
     @staticmethod
@@ -249,6 +250,17 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.death = _split_attr(rest)[0]
     elif kwl.startswith("%repli"):
         m.repli = _split_attr(rest)[0]
+    elif kwl.startswith("dec") or kwl.startswith("const"):
+        # `decl const double a[] = {..}` is printed verbatim at file scope by the reference (add_declarations, src/odexp:660-674);
+        # `const a[] {..}` is the older spelling the shipped examples/Nbody.pop still uses (declare_constant_array, src/odexp:643-658).
+        # Only constant scalars / arrays are taken: they become constexpr locals of every generated function.
+        mm = re.match(r"^(?:static\s+)?const\s+(double|int|long)\s+(%s)\s*((?:\[[^\]]*\])*)\s*=\s*(.+?);?\s*$" % IDENT, rest, flags=re.S) \
+            if kwl.startswith("dec") else re.match(r"^()(%s)\s*((?:\[[^\]]*\])*)\s*=?\s*(.+?);?\s*$" % IDENT, rest, flags=re.S)
+        if not mm:
+            raise PopError("line %d: only `decl const double|int|long name[..] = value` declarations are supported" % lineno)
+        if bool(mm.group(3)) != mm.group(4).strip().startswith("{"):
+            raise PopError("line %d: a constant array needs a braced initialiser list, a constant scalar a single value" % lineno)
+        m.consts.append((mm.group(1) or "double", mm.group(2), mm.group(3).replace(" ", ""), mm.group(4).strip()))
     elif kwl.startswith("cmd") or kwl.startswith("end"):
         return
     elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):

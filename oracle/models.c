@@ -54,6 +54,28 @@ static void nb_ic(orc_ctx *c, double t, double *y, double *e) {
   y[3] = 0.0; y[4] = 0.0; y[5] = 0.0;
 }
 
+/* ---------------------------------------------------------------- nbody_const.pop (constant arrays indexed by ID, as in examples/Nbody.pop) */
+static const double nbc_pars[] = {1, 1e+09};
+static const double nbc_x_ic[] = { 0.0, 1.0, 0.5 };
+static const double nbc_y_ic[] = { 0.0, 0.0, 0.8660254037844386 };
+static const double nbc_z_ic[] = { 0.0, 0.0, 0.0 };
+static const double nbc_vx0[] = { 0.1, 0.0, -.1 };
+static const double nbc_vy0[] = { 0.0, 0.1, 0.0 };
+static const double nbc_vz0[] = { 0.0, 0.0, 0.0 };
+static void nbc_cpl(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi) {
+  const double mass = c->mu[1];
+  (void)e; (void)oe;
+  psi[0] += -NB_G * mass * grav(y[0], oy[0], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+  psi[1] += -NB_G * mass * grav(y[1], oy[1], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+  psi[2] += -NB_G * mass * grav(y[2], oy[2], y[0], y[1], y[2], oy[0], oy[1], oy[2]);
+}
+static void nbc_ic(orc_ctx *c, double t, double *y, double *e) {
+  const double v0 = c->mu[0]; const int ID = c->id;
+  (void)t; (void)e;
+  y[0] = nbc_x_ic[ID]; y[1] = nbc_y_ic[ID]; y[2] = nbc_z_ic[ID];
+  y[3] = v0*nbc_vx0[ID]; y[4] = v0*nbc_vy0[ID]; y[5] = v0*nbc_vz0[ID];
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -231,6 +253,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},
   {"vect_meanfield", 1, 0, 1, 0, 3, 2, vm_pars, vm_rhs, vm_mfd, vm_birth, NULL, vm_ic, 0, 0, 0, 0, 0, NULL, vm_vect, vm_vect_eval},
   {"ring_diffusion", 2, 1, 1, 0, 1, 3, ring_pars, ring_rhs, ring_mfd, NULL, NULL, ring_ic, 0, 0, 0, 0, 0, NULL},

@@ -149,3 +149,23 @@ def test_ring_neighbours_adaptive_vs_oracle(model_lib, meth, n):
     assert len(out["stats"]) == len(ref["stats"])
     np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-9, atol=1e-12)
     pop.close()
+
+
+@pytest.mark.parametrize("replay", [True, False])
+@pytest.mark.parametrize("meth,ts,res", [("rkf45", (0, 20.0), 11), ("rk8pd", (0, 20.0), 5), ("dde", (0, 2.0), 5)])
+def test_const_arrays_indexed_by_id(model_lib, meth, ts, res, replay):
+    """`decl const double a[] = {..}` arrays indexed by ID in the initial conditions and an {initial} parameter: the three bodies of
+    the reference's shipped examples/Nbody.pop (src/odexp:660-674; restatement bit-identical to the reference binary).  ICs are
+    set by the host replay path and by the device kernel; the orbit is followed over t = 20 (close encounters included)"""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": 0.05 if meth == "dde" else 0.1, "res": res, "ps": 3, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0.0}
+    pop = capi.Population(model_lib("nbody_const"), capacity=1024)
+    out = capi.odesolver(pop, ts, meth=meth, res=res, popsize=3, abstol=1e-8, reltol=1e-8, hmin=0.0, h0=opts["h0"], replay_ic=replay)
+    pop.close()
+    ref = port.run("nbody_const", opts, ts)
+    ta, tb = out["traj"], ref["traj"]
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :6], tb[tb["step"] == 0]["cols"][:, :6])       # x_ic[ID] .. v0*vz0[ID]
+    assert len(out["stats"]) == len(ref["stats"])
+    assert out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-8, atol=1e-10)

@@ -77,6 +77,20 @@ def test_emit_vect_meanfields():
         cudagen.emit_cuda(bad)
 
 
+def test_const_arrays():
+    """`decl const double a[] = {..}` (src/odexp:660-674) and the shipped example's older `const a[] {..}` spelling"""
+    from odexp_b200 import popfile, cudagen
+    m = popfile.parse_file(fixture_path("nbody_const"))
+    assert [c[1] for c in m.consts] == ["x_ic", "y_ic", "z_ic", "vx0", "vy0", "vz0"] and m.consts[0][0] == "double"
+    cu = cudagen.emit_cuda(m)
+    assert "constexpr double x_ic[] = { 0.0, 1.0, 0.5 };" in cu and "odx_y[3] = v0*vx0[(odx_c.id)];" in cu
+    assert "const double v0 = odx_c.mu[0];" in cu                   # {initial}: attribute prefixes count (src/odexp:1269)
+    old = popfile.parse("const a[] { 1, 2 }\ndecl const int k = 3\ndx/dt = a[ID] + k\ninit x 0\n")
+    assert old.consts == [("double", "a", "[]", "{ 1, 2 }"), ("int", "k", "", "3")]
+    with pytest.raises(popfile.PopError):
+        popfile.parse("decl double buffer[10]\ndx/dt = 1\ninit x 0\n")        # only constants
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")

@@ -46,6 +46,11 @@ REF_CASES = [
     # low-rank coupling expanded in an AUXILIARY variable (the wrapped phase, as in the shipped examples/kuramoto_lowrank.pop) + MA() in %M
     ("kuramoto_lowrank_aux", {"meth": "dde", "h0": 0.1, "res": 5, "ps": 100}, (0, 2.0)),
     ("kuramoto_lowrank_aux", {"meth": "rkf45", "h0": 0.1, "res": 4, "ps": 57}, (0, 25.0)),       # phases pass 2 pi: the aux wraps
+    # constant arrays (`decl const double a[] = {..}`) indexed by ID in the initial conditions, {initial} parameter: the three
+    # bodies of the shipped examples/Nbody.pop, explicit methods
+    ("nbody_const", {"meth": "rkf45", "h0": 0.1, "res": 11, "ps": 3, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 20)),
+    ("nbody_const", {"meth": "rk8pd", "h0": 0.1, "res": 5, "ps": 3, "abstol": 1e-10, "reltol": 1e-10, "hmin": 0}, (0, 20)),
+    ("nbody_const", {"meth": "dde", "h0": 0.05, "res": 5, "ps": 3, "hmin": 0, "abstol": 1e-8, "reltol": 1e-8}, (0, 2)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
