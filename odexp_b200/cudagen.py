@@ -333,11 +333,12 @@ class Emitter:
         self.m = m
         self.fast_pow = fast_pow
         self.fast_div = fast_div
-        self.var_idx = {n: i for i, n in enumerate(e.name for e in m.eqs)}
+        self.var_idx = {e.name: m.index_of(m.eqs, e.name) for e in m.eqs}       # flattened base index (arrays count element-wise)
+        self.arrays = {e.name for e in list(m.eqs) + list(m.auxs) if e.length}
         self.par_idx = {e.name: i for i, e in enumerate(m.pars)}
         self.mfd_idx = {e.name: i for i, e in enumerate(m.mfds)}
         self.psi_idx = {c.name: i for i, c in enumerate(m.cpls)}
-        self.aux_idx = {e.name: i for i, e in enumerate(m.auxs)}
+        self.aux_idx = {e.name: m.index_of(m.auxs, e.name) for e in m.auxs}
         self.expr_base = {}
         k = 0
         for e in m.exprs:
@@ -357,6 +358,8 @@ class Emitter:
             return "(odx_mfd[%d])" % need(self.mfd_idx, "mean field")
         if kind == "MC":
             return "(odx_psi[%d])" % need(self.psi_idx, "coupling")
+        if kind in ("MY", "OY", "SY", "MA", "OA", "SA") and name in self.arrays:
+            raise PopError("%s(%s) in %s: macros on array variables are not supported" % (kind, name, where))
         if kind in ("MY", "OY", "SY"):
             i = need(self.var_idx, "dynamical variable")
             return {"MY": "(odx_y[%d])", "OY": "(odx_oy[%d])", "SY": "(odx_c.has_sister ? odx_c.sis_y[%d] : 0.0)"}[kind] % i
@@ -534,7 +537,7 @@ class Emitter:
         # sincos arguments shared by the RHS and the %M terms: candidates for the stage-to-stage increment
         hint_slots = {}
         if not terms_use_aux and not rhs_rng:
-            shared = self.sincos_args([e.rhs for e in m.auxs] + [e.rhs for e in m.eqs], "rhs") & \
+            shared = self.sincos_args([e.rhs for e in m.auxs if not e.length] + [e.rhs for e in m.eqs if not e.length], "rhs") & \
                      self.sincos_args([e.rhs for e in m.mfds], "%M")
             hint_slots = {a: i for i, a in enumerate(sorted(shared))}
         self.hint_slots = hint_slots
@@ -579,18 +582,37 @@ class Emitter:
                 else:
                     w("    const double %s = odx_e[%d];" % (mangle(e.name), b))
             for e in m.eqs:
-                w("    const double %s = odx_y[%d];" % (mangle(e.name), self.var_idx[e.name]))
+                if e.length:
+                    w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_y[%d + odx_i];" %
+                      (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, self.var_idx[e.name]))
+                else:
+                    w("    const double %s = odx_y[%d];" % (mangle(e.name), self.var_idx[e.name]))
             for c in m.cpls:
                 w("    const double %s = odx_psi[%d];" % (mangle(c.name), self.psi_idx[c.name]))
             for e in m.mfds:
                 w("    const double %s = odx_mfd[%d];" % (mangle(e.name), self.mfd_idx[e.name]))
             tc = {}
+            # arrays: one loop per entry with the reference's `size_t` iterator (src/odexp:1381-1436, 1439-1506); no common-subexpression
+            # hoisting across the loop
             for e in m.auxs:
-                w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
+                if e.length:
+                    it = mangle(e.iterator)
+                    w("    double %s[%d]; for (size_t %s = %d; %s < %d; ++%s) %s[%s] = %s;" % (mangle(e.name), e.start + e.length, it, e.start, it,
+                      e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "aux " + e.name)))
+                else:
+                    w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
             for e in m.eqs:
-                w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
+                if e.length:
+                    it = mangle(e.iterator)
+                    w("    for (size_t %s = %d; %s < %d; ++%s) odx_f[%d + %s - %d] = %s;" % (it, e.start, it, e.start + e.length, it,
+                      self.var_idx[e.name], it, e.start, self.tr(e.rhs, "d%s/dt" % e.name)))
+                else:
+                    w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
             for e in m.auxs:
-                w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
+                if e.length:
+                    w("    for (int odx_i = 0; odx_i < %d; odx_i++) odx_aux[%d + odx_i] = %s[%d + odx_i];" % (e.length, self.aux_idx[e.name], mangle(e.name), e.start))
+                else:
+                    w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
             if m.death:
                 w("    odx_death = %s;" % self.cse(self.tr(m.death, "%DEATH"), tc, w))
             if m.repli:
@@ -682,13 +704,18 @@ class Emitter:
             if e.length:
                 it = mangle(e.iterator)
                 w("    double %s[%d];" % (mangle(e.name), e.start + e.length))
-                w("    for (int %s = %d; %s < %d; %s++) { %s[%s] = %s; odx_e[%d + %s - %d] = %s[%s]; }" %
+                w("    for (size_t %s = %d; %s < %d; %s++) { %s[%s] = %s; odx_e[%d + %s - %d] = %s[%s]; }" %
                   (it, e.start, it, e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "expr " + e.name, exact=True), b, it, e.start,
                    mangle(e.name), it))
             else:
                 w("    const double %s = %s; odx_e[%d] = %s;" % (mangle(e.name), self.tr(e.rhs, "expr " + e.name, exact=True), b, mangle(e.name)))
         for e in m.inits:
-            w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name, exact=True)))
+            if e.length:
+                it = mangle(e.iterator)
+                w("    for (size_t %s = %d; %s < %d; ++%s) odx_y[%d + %s - %d] = %s;" % (it, e.start, it, e.start + e.length, it, self.var_idx[e.name],
+                  it, e.start, self.tr(e.rhs, "init " + e.name, exact=True)))
+            else:
+                w("    odx_y[%d] = %s;" % (self.var_idx[e.name], self.tr(e.rhs, "init " + e.name, exact=True)))
         w("  }\n")
         w("  ODX_HD static constexpr bool psi_is_pairwise(int k) { return %s; }\n" %
           (" || ".join("k == %d" % self.psi_idx[c.name] for c in pair_cpls) or "false"))

@@ -197,14 +197,11 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.exprs.append(_name_and_rhs(rest, lineno, raw))
     elif kwl.startswith("aux"):
         e = _name_and_rhs(rest, lineno, raw)
-        if e.length:
-            raise PopError("line %d: array auxiliary variables are not supported yet" % lineno)
-        m.auxs.append(e)
+        if e.length and re.search(r"\b(vect|noloop)\b", e.attr):
+            raise PopError("line %d: {vect} array auxiliary variables (filled by a function) are not supported" % lineno)
+        m.auxs.append(e)          # scalar, or one-dimensional array `aux a[i=0:5] X[i]*X[i]` (define_array_functions, src/odexp:1381-1436)
     elif kwl.startswith("init"):
-        e = _name_and_rhs(rest, lineno, raw)
-        if e.length:
-            raise PopError("line %d: array dynamical variables are not supported yet" % lineno)
-        m.inits.append(e)
+        m.inits.append(_name_and_rhs(rest, lineno, raw))
     elif kwl.startswith("mac"):
         f = rest.split(None, 1)
         if len(f) != 2:
@@ -263,6 +260,15 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.consts.append((mm.group(1) or "double", mm.group(2), mm.group(3).replace(" ", ""), mm.group(4).strip()))
     elif kwl.startswith("cmd") or kwl.startswith("end"):
         return
+    elif re.match(r"^d%s\s*\[" % IDENT, kw + " " + rest, flags=re.I) and re.match(r"^d(%s)\s*\[([^\]]*)\]\s*/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S):
+        # array of dynamical variables `dX[i=0:5]/dt = rhs`: one equation per index, the iterator is visible in the rhs (src/odexp:1439-1506)
+        mm = re.match(r"^d(%s)\s*\[([^\]]*)\]\s*/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S)
+        rhs, attr = _split_attr(mm.group(3))
+        ma = _RE_ARRAY.match("%s[%s]" % (mm.group(1), mm.group(2).replace(" ", "")))
+        if not ma or int(ma.group(4)) <= int(ma.group(3)):
+            raise PopError("line %d: unsupported index expression in '%s'" % (lineno, raw.strip()))
+        a, b = int(ma.group(3)), int(ma.group(4))
+        m.eqs.append(Entry(mm.group(1), rhs.strip(), attr, length=b - a, iterator=ma.group(2), start=a))
     elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):
         var = re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I).group(1)
         rhs, attr = _split_attr(rest)
@@ -287,6 +293,9 @@ def _validate(m):
     ini = [e.name for e in m.inits]
     if dyn != ini:
         raise PopError("initial conditions must be declared for, and in the order of, the dynamical variables: %s vs %s" % (dyn, ini))
+    for e, i in zip(m.eqs, m.inits):
+        if (e.length, e.start) != (i.length, i.start):
+            raise PopError("initial condition of %s does not cover the same index range as its equation" % e.name)
     for k, v in OPT_DEFAULTS.items():
         m.options.setdefault(k, v)
     if not m.timespan:

@@ -76,6 +76,38 @@ static void nbc_ic(orc_ctx *c, double t, double *y, double *e) {
   y[3] = v0*nbc_vx0[ID]; y[4] = v0*nbc_vy0[ID]; y[5] = v0*nbc_vz0[ID];
 }
 
+/* ---------------------------------------------------------------- chain_array.pop (LET NC 4): array D/DT, AUX and EXPR entries */
+static const double ca_pars[] = {1.5, 0.3};
+static double ca_sum(const double *array, long len) { double s = 0.0; long i; for (i = 0; i < len; i++) s += array[i]; return s; }      /* src/utils_odexp.c:11-21 */
+static double ca_dotprod(const double *x, const double *y, long len) { double s = 0.0; long i; for (i = 0; i < len; i++) s += x[i] * y[i]; return s; }
+static void ca_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double k = c->mu[0], a = c->mu[1];
+  const double *w = e, z = y_[0], *X = y_ + 1, u = y_[5], SBAR = mfd[0], ZBAR = mfd[1];
+  double sq[4], nrm, dp; size_t i;
+  (void)t; (void)psi; (void)death; (void)repli;
+  for (i = 0; i < 4; ++i) sq[i] = X[i]*X[i];
+  nrm = sqrt(ca_sum(sq,4));
+  dp = ca_dotprod(X,w,4);
+  f[0] = -z + 0.1*dp;
+  for (i = 0; i < 4; ++i) f[1 + i] = (i == 0) ? (-k*X[0] + a*SBAR) : k*(X[i-1] - X[i]);
+  f[5] = X[4-1] - a*u*ZBAR;
+  for (i = 0; i < 4; ++i) aux[i] = sq[i];
+  aux[4] = nrm; aux[5] = dp;
+}
+static double ca_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)e; (void)mfd;
+  return k == 0 ? aux[4] : y[0];                        /* %M SBAR MA(nrm); %M ZBAR MY(z) */
+}
+static void ca_ic(orc_ctx *c, double t, double *y, double *e) {
+  size_t i;
+  (void)t;
+  for (i = 0; i < 4; ++i) e[i] = 0.5 + orc_rand01(c);
+  y[0] = 1.0;
+  for (i = 0; i < 4; ++i) y[1 + i] = orc_rand01(c)/(i+1);
+  y[5] = 0.0;
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -253,6 +285,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},
   {"vect_meanfield", 1, 0, 1, 0, 3, 2, vm_pars, vm_rhs, vm_mfd, vm_birth, NULL, vm_ic, 0, 0, 0, 0, 0, NULL, vm_vect, vm_vect_eval},

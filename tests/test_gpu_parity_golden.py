@@ -169,3 +169,26 @@ def test_const_arrays_indexed_by_id(model_lib, meth, ts, res, replay):
     assert len(out["stats"]) == len(ref["stats"])
     assert out["report"]["steps"] == ref["report"]["steps"]
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("replay", [True, False])
+@pytest.mark.parametrize("meth,n,res", [("dde", 20, 4), ("rkck", 33, 4), ("fe", 5, 3), ("dde", 4099, 3), ("rk8pd", 257, 3)])
+def test_array_variables(model_lib, meth, n, res, replay):
+    """`dX[i=0:NC]/dt`, `aux sq[i=0:NC]`, `expr w[i=0:NC]`, `init X[i=0:NC]` (one loop per entry, size_t iterator visible in the
+    rhs: src/odexp:1331-1506) mixed with scalar entries, helper functions on the arrays (sum, dotprod), MA() in %M.  ICs from
+    the replayed libc stream (bit-identical to the restatement) and from the device's keyed Philox draws."""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": 0.05, "res": res, "ps": n, "hmin": 1e-5}
+    pop = capi.Population(model_lib("chain_array"), capacity=max(1024, n))
+    out = capi.odesolver(pop, (0, 3), meth=meth, res=res, popsize=n, h0=0.05, hmin=1e-5, replay_ic=replay)
+    pop.close()
+    ref = port.run("chain_array", opts, (0, 3), rng_mode=0 if replay else 1)
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and len(out["stats"]) == len(ref["stats"])
+    if replay:
+        np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :6], tb[tb["step"] == 0]["cols"][:, :6])      # z, X[0..3], u
+        np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, -4:], tb[tb["step"] == 0]["cols"][:, -4:])    # w[0..3]
+    assert out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

@@ -51,6 +51,10 @@ REF_CASES = [
     ("nbody_const", {"meth": "rkf45", "h0": 0.1, "res": 11, "ps": 3, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 20)),
     ("nbody_const", {"meth": "rk8pd", "h0": 0.1, "res": 5, "ps": 3, "abstol": 1e-10, "reltol": 1e-10, "hmin": 0}, (0, 20)),
     ("nbody_const", {"meth": "dde", "h0": 0.05, "res": 5, "ps": 3, "hmin": 0, "abstol": 1e-8, "reltol": 1e-8}, (0, 2)),
+    # array dynamical / auxiliary / expression entries (`dX[i=0:NC]/dt`, `aux sq[i=0:NC]`), MA() of a scalar aux fed by an array
+    ("chain_array", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 20, "hmin": 1e-5}, (0, 3)),
+    ("chain_array", {"meth": "rkck", "h0": 0.05, "res": 4, "ps": 33, "hmin": 1e-5}, (0, 3)),
+    ("chain_array", {"meth": "fe", "h0": 0.05, "res": 3, "ps": 5, "hmin": 1e-5}, (0, 1)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
