@@ -174,6 +174,8 @@ def _inline_funs(expr: str, funs) -> str:
     for _ in range(8):                      # bounded nesting depth
         changed = False
         for f in funs:
+            if f.block or any(not re.match(r"^%s$" % IDENT, a) for a in f.args):
+                continue                    # statements / pointer or typed arguments: called, not inlined
             for b, e, args in _find_call(expr, f.name):
                 if len(args) != len(f.args):
                     continue
@@ -528,7 +530,13 @@ class Emitter:
                                              for t, n, d, init in m.consts))
         w("")
         for f in m.funs:
-            args = ", ".join("double %s" % mangle(a) for a in f.args)
+            # arguments are doubles unless they carry a type; `*x` passes an array (src/odexp:694-707)
+            args = ", ".join(_mangle_expr(a) if re.search(r"\b(void|int|long|char|float|const)\b", a) else
+                             "double " + _mangle_expr(a) for a in f.args)
+            if f.block:
+                rt = re.search(r"return\s*\((int|long|char|float)\)", f.body)
+                w("ODX_HD %s %s(%s) { ODX_CONSTS %s }" % (rt.group(1) if rt else "double", mangle(f.name), args, _mangle_expr(f.body)))
+                continue
             body = _pow_peephole(f.body) if self.fast_pow else f.body
             body = _div_peephole(body) if self.fast_div else body
             body = _mangle_expr(_ternary_to_select(body))

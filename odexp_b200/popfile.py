@@ -34,7 +34,8 @@ class Entry:
 class Fun:
     name: str
     args: List[str]
-    body: str                # expression (one-liner) — `return` is added by the emitters
+    body: str                # expression (one-liner) — `return` is added by the emitters; statements when block is set
+    block: bool = False      # `FUN name(args)` ... `end`: C statements, printed as the function body (src/odexp:676-737)
 
 
 @dataclass
@@ -155,6 +156,24 @@ def parse(text: str, name: str = "model") -> PopModel:
         cont = ""
     if cont:
         lines.append(cont)
+    # multi-line functions: `FUN name(args)` without `=`, statements, `end` -> one line `fun name(args) = {block} statements`
+    joined, block = [], None
+    for s in lines:
+        t = _strip_comment(s).strip()
+        if block is not None:
+            if re.match(r"^end\b", t, flags=re.I):
+                joined.append(block[0] + " = \x01" + " ".join(block[1:]))
+                block = None
+            elif t:
+                block.append(t)
+            continue
+        if re.match(r"^fun\w*\s+%s\s*\([^)]*\)\s*$" % IDENT, t, flags=re.I):
+            block = [t]
+            continue
+        joined.append(s)
+    if block is not None:
+        raise PopError("FUN %s: multi-line function without `end`" % block[0])
+    lines = joined
     lets = []
     for s in lines:
         f = _strip_comment(s).split()
@@ -220,8 +239,11 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
     elif kwl.startswith("fun"):
         mm = re.match(r"^(%s)\s*\(([^)]*)\)\s*=\s*(.*?);?\s*$" % IDENT, rest, flags=re.S)
         if not mm:
-            raise PopError("line %d: only one-line functions `fun f(a,b) = expr` are supported" % lineno)
+            raise PopError("line %d: cannot parse the function definition '%s'" % (lineno, raw.strip()))
         body = mm.group(3).strip()
+        if body.startswith("\x01"):
+            m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body[1:].strip() + ";", block=True))
+            return
         if re.search(r"\b(for|while|if|return)\b", body) or ";" in body:
             raise PopError("line %d: function bodies with statements are not supported" % lineno)
         m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body))

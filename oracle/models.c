@@ -108,6 +108,42 @@ static void ca_ic(orc_ctx *c, double t, double *y, double *e) {
   y[5] = 0.0;
 }
 
+/* ---------------------------------------------------------------- fun_block.pop (LET NW 3): FUN ... end blocks, pointer arguments */
+static const double fb_pars[] = {2.0, 0.5};
+static double fb_mean(double *x) { return ca_sum(x,3)/3; }
+static double fb_wmean(double *x, double *w) {
+  double s = 0.0, sw = 0.0;
+  int j;
+  for (j = 0;j < 3;j++) { s += w[j]*x[j]; sw += w[j]; }
+  return s/sw;
+}
+static double fb_clip(double x, double lo, double hi) {
+  if (x < lo) { return lo; }
+  if (x > hi) { return hi; }
+  return x;
+}
+static void fb_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double a = c->mu[0], b = c->mu[1], MBAR = mfd[0];
+  double w[3], X[3], m, wm; size_t i;
+  (void)psi; (void)death; (void)repli;
+  for (i = 0; i < 3; ++i) { w[i] = e[i]; X[i] = y_[i]; }
+  m = fb_mean(X);
+  wm = fb_wmean(X, w);
+  for (i = 0; i < 3; ++i) f[i] = -a*(X[i] - fb_clip(MBAR, -b, b)) + sin(t + i);
+  aux[0] = m; aux[1] = wm;
+}
+static double fb_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)y; (void)e; (void)mfd;
+  return aux[1];                                         /* %M MBAR MA(wm) */
+}
+static void fb_ic(orc_ctx *c, double t, double *y, double *e) {
+  size_t i;
+  (void)t;
+  for (i = 0; i < 3; ++i) e[i] = 0.5 + orc_rand01(c);
+  for (i = 0; i < 3; ++i) y[i] = 2*orc_rand01(c) - 1;
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -285,6 +321,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"fun_block", 3, 3, 2, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},

@@ -192,3 +192,25 @@ def test_array_variables(model_lib, meth, n, res, replay):
     assert out["report"]["steps"] == ref["report"]["steps"]
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("meth,n", [("dde", 10), ("rkf45", 21), ("fe", 1500), ("rk8pd", 300)])
+def test_function_blocks(model_lib, meth, n):
+    """`FUN name(args)` ... `end` blocks with statements, pointer arguments (`*x` passes an array) and a one-line function on an
+    array (src/odexp:676-737, README FUN), called from AUX and from an array D/DT whose rhs also reads t and the iterator"""
+    from odexp_b200 import capi
+    from oracle import port
+    # rk8pd at the default tolerance 1e-6 is not a parity case: its step-size control amplifies a 1e-10 relative change of the
+    # tolerance into a 4e-8 change of the restatement's own solution (measured); at 1e-12 the step sequence no longer matters
+    tol = 1e-12 if meth == "rk8pd" else 1e-6
+    opts = {"meth": meth, "h0": 0.05, "res": 4, "ps": n, "hmin": 1e-5, "abstol": tol, "reltol": tol}
+    pop = capi.Population(model_lib("fun_block"), capacity=max(1024, n))
+    out = capi.odesolver(pop, (0, 3), meth=meth, res=4, popsize=n, h0=0.05, hmin=1e-5, abstol=tol, reltol=tol, replay_ic=True)
+    pop.close()
+    ref = port.run("fun_block", opts, (0, 3))
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and (meth == "rk8pd" or out["report"]["steps"] == ref["report"]["steps"])
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :3], tb[tb["step"] == 0]["cols"][:, :3])
+    # rk8pd: the restatement itself moves by 6e-12 under a 1e-8 relative change of the tolerance (states are O(1))
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=2e-11 if meth == "rk8pd" else 1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=2e-11 if meth == "rk8pd" else 1e-12)

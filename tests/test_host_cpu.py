@@ -91,6 +91,21 @@ def test_const_arrays():
         popfile.parse("decl double buffer[10]\ndx/dt = 1\ninit x 0\n")        # only constants
 
 
+def test_function_blocks_and_arrays():
+    from odexp_b200 import popfile, cudagen
+    m = popfile.parse_file(fixture_path("fun_block"))
+    assert [(f.name, f.block) for f in m.funs] == [("mean", False), ("wmean", True), ("clip", True)]
+    cu = cudagen.emit_cuda(m)
+    assert "ODX_HD double wmean(double *x, double *w) {" in cu and "for (j = 0; j < 3; j++)" in cu
+    assert "for (size_t i = 0; i < 3; ++i) odx_f[0 + i - 0] = " in cu and "clip(MBAR, -b, b)" in cu          # called, not inlined
+    c = popfile.parse_file(fixture_path("chain_array"))
+    assert (c.nvar, c.naux, c.nexpr) == (6, 6, 4) and c.flat_names(c.eqs) == ["z", "X[0]", "X[1]", "X[2]", "X[3]", "u"]
+    with pytest.raises(popfile.PopError):
+        popfile.parse("fun f(x)\n return x;\ndx/dt = f(x)\ninit x 0\n")                     # no `end`
+    with pytest.raises(popfile.PopError):
+        popfile.parse("dX[i=0:3]/dt = -X[i]\ninit X[i=0:2] 1\n")                             # ranges differ
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")
