@@ -47,7 +47,11 @@ def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False
             text, n = re.subn(r"^\s*times\w*\s+.*$", ts, text, flags=re.I | re.M)
             if n == 0:
                 text += "\n" + ts + "\n"
-        for k, v in (opts or {}).items():
+        # every solver option is written out (the restatement's defaults = src/options.c's for the ones not given), so that a
+        # fixture's own `opt` lines cannot make the two sides of a comparison run with different values
+        full = dict(meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592)
+        full.update(opts or {})
+        for k, v in full.items():
             text += "\nOPT %s %s\n" % (k, v)
         text += "\nOPT pr 0\n"
         open(ppath, "w").write(text)
