@@ -91,7 +91,7 @@ struct odx_handle {
   void *peer_mail[MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_attached = false;
   /* low-rank coupling scratch + options (opt lrmax / lrabstol / lrreltol) */
-  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr, *lr_x = nullptr; bool lr_attr_done = false;
+  void *lr_plan = nullptr, *lr_rank = nullptr; double *lr_stats = nullptr, *lr_spart = nullptr, *lr_apart = nullptr, *lr_A = nullptr, *lr_x = nullptr, *lr_ones = nullptr; bool lr_attr_done = false;
   int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
@@ -205,6 +205,14 @@ static int compute_lowrank(odx_handle *h, const double *ysrc, double t) {
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_apart, sizeof(double) * (size_t)LR_R * LR_P1 * (24 * h->sm_count + 24 * h->sm_count / 32 + 2)));
     ODX_CUDA(h, cudaMalloc((void **)&h->lr_A, sizeof(double) * LR_R * LR_P1));
   }
+  /* weights: the U / V columns of E, or one column of ones for the unweighted `lrexp` (same arithmetic as lrexp(): 1.0 * x) */
+  if (M::LR0_UNWEIGHTED && !h->lr_ones) {
+    std::vector<double> ones((size_t)h->cap, 1.0);
+    ODX_CUDA(h, cudaMalloc((void **)&h->lr_ones, sizeof(double) * h->cap));
+    ODX_CUDA(h, cudaMemcpy(h->lr_ones, ones.data(), sizeof(double) * h->cap, cudaMemcpyHostToDevice));
+  }
+  const double *lrU = M::LR0_UNWEIGHTED ? h->lr_ones : h->E + (size_t)(M::LR0_U < 0 ? 0 : M::LR0_U) * h->cap;
+  const double *lrV = M::LR0_UNWEIGHTED ? h->lr_ones : h->E + (size_t)(M::LR0_V < 0 ? 0 : M::LR0_V) * h->cap;
   const double *x = ysrc + (size_t)M::LR0_VAR * h->cap;
   if (M::LR0_VAR_KIND == 2) x = h->E + (size_t)M::LR0_VAR * h->cap;
   if (M::LR0_VAR_KIND == 1) {
@@ -236,7 +244,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc, double t) {
     nblk = ntiles < h->sm_count ? (int)ntiles : h->sm_count;     /* persistent: one CTA per SM, batches strided over the grid */
     if (nblk < 1) nblk = 1;
     npart = nblk;
-    const double *Vc = h->E + (size_t)M::LR0_V * h->cap; const LrPlan *plm = (const LrPlan *)h->lr_plan;
+    const double *Vc = lrV; const LrPlan *plm = (const LrPlan *)h->lr_plan;
     ODX_CUDA(h, cudaMemsetAsync(h->lr_apart, 0, sizeof(double) * (size_t)LR_R * LR_P1 * npart, h->stream));
     if (!h->lr_attr_done) {                       /* the rings need more than the 48 KB static limit */
       ODX_CUDA(h, cudaFuncSetAttribute(k_lr_moments_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lrt_smem_bytes(LR_P1)));
@@ -245,7 +253,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc, double t) {
     }
     k_lr_moments_tma<<<nblk, LRT_THREADS, lrt_smem_bytes(LR_P1), h->stream>>>(x, Vc, h->cap, n, plm, h->lr_apart); ODX_TRY(launch_check(h));
   } else {
-    k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, h->E + (size_t)M::LR0_V * h->cap, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
+    k_lr_moments<<<nblk, BLOCK, 0, h->stream>>>(x, lrV, h->cap, n, (const LrPlan *)h->lr_plan, h->lr_apart);
     ODX_TRY(launch_check(h));
   }
   {
@@ -265,7 +273,7 @@ static int compute_lowrank(odx_handle *h, const double *ysrc, double t) {
   /* a CTA first stages A (r x (p+1) doubles) and the coefficient table in shared memory: with one chunk of 128 particles per CTA
    * that prologue cost as much as the chunk (ncu: long-scoreboard stalls, FP64 pipe 32 %); six resident CTAs per SM loop instead */
   int ga = (int)((n + 127) / 128); if (ga > 6 * h->sm_count) ga = 6 * h->sm_count; if (ga < 1) ga = 1;
-  const double *Uc = h->E + (size_t)M::LR0_U * h->cap; double *psi = h->PSI + (size_t)M::LR0_PSI * h->cap;
+  const double *Uc = lrU; double *psi = h->PSI + (size_t)M::LR0_PSI * h->cap;
   const LrPlan *pl = (const LrPlan *)h->lr_plan;
   if (LR_WSPLIT) {
     const int64_t nbatch = (n + LRA_PT - 1) / LRA_PT;
@@ -817,7 +825,7 @@ void odx_destroy(odx_handle *h) {
   if (h->gcol) cudaFree(h->gcol);
   if (h->lr_plan) cudaFree(h->lr_plan);
   if (h->lr_rank) cudaFree(h->lr_rank);
-  { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A, h->lr_x}; for (double *q : lb) if (q) cudaFree(q); }
+  { double *lb[] = {h->lr_stats, h->lr_spart, h->lr_apart, h->lr_A, h->lr_x, h->lr_ones}; for (double *q : lb) if (q) cudaFree(q); }
   for (int r = 0; r < MAX_RANKS; r++) if (h->peer_mail[r] && h->peer_mail[r] != h->mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
   if (h->mail) cudaFree(h->mail);
   if (h->ll_words) cudaFree(h->ll_words);

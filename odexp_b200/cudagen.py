@@ -745,7 +745,7 @@ class Emitter:
             else:
                 raise PopError("low-rank coupling %s: var=%s is not a dynamical variable, an auxiliary variable or a scalar expression" % (c.name, var))
             fun = d.get("fun", "sin")
-            rank = int(d.get("rank", "1")) if d["kind"] == "lrwexp" else 0
+            rank = int(d.get("rank", "1")) if d["kind"] == "lrwexp" else 1          # lrexp = rank 1 with unit weights (lrkern, src/lrexp.c:484-496)
             # `U = U[0]` (the shipped examples/kuramoto_lowrank.pop) names the first element of the array: same column base
             base = lambda key: self.expr_base.get(re.sub(r"\[\s*0\s*\]$", "", d.get(key, "").strip()), -1)
             ub = base("U") if d["kind"] == "lrwexp" else -1
@@ -754,6 +754,7 @@ class Emitter:
                 raise PopError("low-rank coupling %s: U/V must name EXPR arrays" % c.name)
             w("  static constexpr int LR%d_PSI = %d, LR%d_VAR = %d, LR%d_RANK = %d, LR%d_U = %d, LR%d_V = %d;" %
               (k, self.psi_idx[c.name], k, var_i, k, rank, k, ub, k, vb))
+            w("  static constexpr bool LR%d_UNWEIGHTED = %s;      /* %%C ... lrexp: U = V = 1, no EXPR columns are read */" % (k, "true" if d["kind"] != "lrwexp" else "false"))
             w("  static constexpr int LR%d_VAR_KIND = %d;      /* LR%d_VAR indexes 0: Y, 1: AUX (pass-1 value), 2: EXPR */" % (k, var_kind, k))
             w("  ODX_HD static double lr%d_fun(double x) { return %s(x); }" % (k, mangle(fun)))
         w("")
@@ -777,8 +778,6 @@ class Emitter:
         if lr_cpls:
             if len(lr_cpls) > 1:
                 raise PopError("only one low-rank coupling per model is supported")
-            if lr_cpls[0].lowrank["kind"] != "lrwexp":
-                raise PopError("%C ... lrexp (unweighted) is not supported yet; use lrwexp with U = V = 1")
             w("#define ODX_MODEL_HAS_LOWRANK 1")
         w('#include "odx_engine.cuh"')
         return "\n".join(L) + "\n"

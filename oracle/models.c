@@ -144,6 +144,25 @@ static void fb_ic(orc_ctx *c, double t, double *y, double *e) {
   for (i = 0; i < 3; ++i) y[i] = 2*orc_rand01(c) - 1;
 }
 
+/* ---------------------------------------------------------------- kuramoto_lrexp.pop (LET N 200): unweighted %C ... lrexp */
+static const double kle_pars[] = {0.8};
+static void kle_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                    double *aux, double *death, double *repli) {
+  const double K = c->mu[0], omega = e[0], CPL = psi[0];
+  (void)t; (void)y_; (void)mfd; (void)death; (void)repli;
+  f[0] = omega + K/200*CPL;
+  aux[0] = CPL;
+}
+static void kle_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = orc_randN(c, 2 * 3.141592653589793 / 10.0, 0.1);
+  y[0] = 2 * 3.141592653589793 * orc_rand01(c);
+}
+static double kle_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)e; (void)aux; (void)mfd;
+  return k == 0 ? sin(y[0]) : cos(y[0]);
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -321,6 +340,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 3, 2, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},

@@ -53,6 +53,7 @@ typedef struct {
   /* what lr_var indexes: 0 a dynamical variable, 1 an auxiliary variable (its pass-1 value), 2 a parametric expression --
    * the generated gather calls mvar(name, ...) which searches the three in this order (src/datastruct.c:824-855) */
   int lr_var_kind;
+  int lr_unweighted;      /* `%C ... lrexp {var, fun}`: lrkern instead of lrwpkern (lr_rank is set to 1, lr_iu / lr_iv are unused) */
 } orc_model;
 
 typedef struct {

@@ -100,3 +100,34 @@ def test_lowrank_in_an_auxiliary_variable(model_lib, meth, ps, ts, res):
     np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)            # theta
     np.testing.assert_allclose(ta["cols"][:, 1:3], tb["cols"][:, 1:3], rtol=0, atol=1e-9)             # aux y, aux theta (wrapped)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("meth,ps,ts", [("dde", 200, (0, 1.0)), ("rkck", 77, (0, 2.0)), ("fe", 5000, (0, 0.3))])
+def test_unweighted_lrexp(model_lib, meth, ps, ts):
+    """`%C CPL lrexp {var, fun}` = lrkern (src/lrexp.c:484-496): the rank-1 kernels with a column of ones, against the
+    restatement of lrexp() (bit-identical to the reference binary) and against the direct O(N^2) sum"""
+    from odexp_b200 import capi
+    from oracle import port
+    lib = model_lib("kuramoto_lrexp")
+    opts = {"meth": meth, "h0": 0.1, "res": 3, "ps": ps}
+    pop = capi.Population(lib, capacity=max(1024, ps))
+    out = capi.odesolver(pop, ts, meth=meth, res=3, popsize=ps, h0=0.1, replay_ic=True)
+    pop.close()
+    ref = port.run("kuramoto_lrexp", opts, ts)
+    ta, tb = out["traj"], ref["traj"]                       # cols: theta, aux cpl, CPL, A1, A2, omega
+    assert len(ta) == len(tb)
+    psi_a, psi_b = ta["cols"][:, 2], tb["cols"][:, 2]
+    scale = np.abs(psi_b).max()
+    print("max |dpsi|/scale", np.abs(psi_a - psi_b).max() / scale)
+    assert np.abs(psi_a - psi_b).max() <= 1e-8 * scale
+    np.testing.assert_allclose(ta["cols"][:, 0], tb["cols"][:, 0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-11)
+    # the expansion itself against the direct sum, on the state the RHS was evaluated at
+    pop = capi.Population(lib, capacity=max(1024, ps))
+    pop.init(ps, replay=True)
+    pop.rhs(0.0)
+    d = pop.download()
+    pop.close()
+    th = d["y"][:, 0]
+    direct = np.sin(th[None, :] - th[:, None]).sum(axis=1)
+    assert np.abs(d["psi"][:, 0] - direct).max() <= 1e-4 * max(1.0, np.abs(direct).max())      # lrabstol / lrreltol = 1e-6

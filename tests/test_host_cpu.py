@@ -106,6 +106,16 @@ def test_function_blocks_and_arrays():
         popfile.parse("dX[i=0:3]/dt = -X[i]\ninit X[i=0:2] 1\n")                             # ranges differ
 
 
+def test_emit_lowrank_variants():
+    from odexp_b200 import popfile, cudagen
+    cu = cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto_lrexp")))
+    assert "LR0_RANK = 1" in cu and "LR0_UNWEIGHTED = true" in cu and "LR0_VAR_KIND = 0" in cu
+    cu = cudagen.emit_cuda(popfile.parse_file(fixture_path("kuramoto_lowrank_aux")))
+    assert "LR0_RANK = 3" in cu and "LR0_UNWEIGHTED = false" in cu and "LR0_VAR = 1" in cu and "LR0_VAR_KIND = 1" in cu
+    with pytest.raises(popfile.PopError):
+        cudagen.emit_cuda(popfile.parse("expr U[i=0:2] 1\nexpr V[i=0:2] 1\n%C P lrwexp {var = nope, fun = sin, U = U, V = V, rank = 2}\ndx/dt = P\ninit x 0\n"))
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")

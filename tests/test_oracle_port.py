@@ -58,6 +58,9 @@ REF_CASES = [
     # multi-line FUN ... end blocks, pointer arguments, time-dependent rhs
     ("fun_block", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 10, "hmin": 1e-5}, (0, 3)),
     ("fun_block", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 21, "hmin": 1e-5}, (0, 3)),
+    # unweighted low-rank expansion %C ... lrexp {var, fun} (lrkern)
+    ("kuramoto_lrexp", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 200}, (0, 1.0)),
+    ("kuramoto_lrexp", {"meth": "rkck", "h0": 0.1, "res": 3, "ps": 77}, (0, 2.0)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
