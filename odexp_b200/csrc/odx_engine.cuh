@@ -1165,8 +1165,9 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
                                           const int32_t *__restrict__ jid, int64_t jstride, int64_t jbeg, int64_t jend, double t,
                                           const double (&ya)[A1(NVAR)], const double (&ea)[A1(NEXPR)], const double (&yb)[A1(NVAR)],
                                           const double (&eb)[A1(NEXPR)], int32_t ida, int32_t idb, double (&acca)[A1(NPSI)],
-                                          double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id) {
-  double aux[A1(NAUX)];
+                                          double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id,
+                                          const double (&auxa)[A1(NAUX)], const double (&auxb)[A1(NAUX)]) {
+  double aux[A1(NAUX)];      /* stands for the other particle's auxiliaries: OA() is rejected by the emitter */
 #pragma unroll
   for (int k = 0; k < A1(NPSI); k++) { acca[k] = 0.0; accb[k] = 0.0; }
   DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida);
@@ -1198,8 +1199,8 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
         for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
       }
       if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
-      M::template cpl_terms<false>(ca, t, ya, ea, aux, oy, oe, aux, acca);
-      M::template cpl_terms<false>(cb, t, yb, eb, aux, oy, oe, aux, accb);
+      M::template cpl_terms<false>(ca, t, ya, ea, auxa, oy, oe, aux, acca);
+      M::template cpl_terms<false>(cb, t, yb, eb, auxb, oy, oe, aux, accb);
     }
     int redo = ca.slow | cb.slow;
     if (M::CPL_POISON) {
@@ -1220,8 +1221,8 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
           for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
         }
         if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
-        M::template cpl_terms<true>(ca, t, ya, ea, aux, oy, oe, aux, acca);
-        M::template cpl_terms<true>(cb, t, yb, eb, aux, oy, oe, aux, accb);
+        M::template cpl_terms<true>(ca, t, ya, ea, auxa, oy, oe, aux, acca);
+        M::template cpl_terms<true>(cb, t, yb, eb, auxb, oy, oe, aux, accb);
       }
     }
   }
@@ -1243,12 +1244,23 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__re
   load_cols<NVAR>(ysrc, p.stride, ja, ya); load_cols<NEXPR>(p.E, p.stride, ja, ea);
   load_cols<NVAR>(ysrc, p.stride, jb, yb); load_cols<NEXPR>(p.E, p.stride, jb, eb);
   const int32_t ida = M::NEEDS_ID ? p.ID[ja] : 0, idb = M::NEEDS_ID ? p.ID[jb] : 0;
-  pair_rows(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id);
-  if (M::CPL_SCALED) {      /* factors that do not depend on the other particle, hoisted out of the sum by the emitter */
-    double aux[A1(NAUX)], sa[A1(NPSI)], sb[A1(NPSI)];
+  double auxa[A1(NAUX)], auxb[A1(NAUX)];
+  if (M::CPL_USES_AUX) {    /* MA() inside %C: what pass 1 of pop_rhs left in myself_->aux = ode_rhs with zeroed mean fields and the psi
+                             * of the previous evaluation (still in the PSI columns: k_pair_finish runs after this kernel) */
+    double psia[A1(NPSI)], psib[A1(NPSI)], mz[A1(NMFD)], f[A1(NVAR)], d = 0.0, r = 0.0;
+    load_cols<NPSI>(p.PSI, p.stride, ja, psia); load_cols<NPSI>(p.PSI, p.stride, jb, psib);
+#pragma unroll
+    for (int k = 0; k < A1(NMFD); k++) mz[k] = 0.0;
     DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida), cb = make_ctx(p, 0.0, 0, DOM_RHS, idb);
-    M::template cpl_scale<true>(ca, t, ya, ea, aux, sa);
-    M::template cpl_scale<true>(cb, t, yb, eb, aux, sb);
+    M::template rhs<true>(ca, t, ya, ea, psia, mz, f, auxa, d, r);
+    M::template rhs<true>(cb, t, yb, eb, psib, mz, f, auxb, d, r);
+  }
+  pair_rows(p, jy, je, jid, jstride, jbeg, jend, t, ya, ea, yb, eb, ida, idb, acca, accb, s_col, s_id, auxa, auxb);
+  if (M::CPL_SCALED) {      /* factors that do not depend on the other particle, hoisted out of the sum by the emitter */
+    double sa[A1(NPSI)], sb[A1(NPSI)];
+    DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida), cb = make_ctx(p, 0.0, 0, DOM_RHS, idb);
+    M::template cpl_scale<true>(ca, t, ya, ea, auxa, sa);
+    M::template cpl_scale<true>(cb, t, yb, eb, auxb, sb);
 #pragma unroll
     for (int k = 0; k < NPSI; k++) { acca[k] *= sa[k]; accb[k] *= sb[k]; }
   }

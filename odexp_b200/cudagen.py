@@ -503,8 +503,7 @@ class Emitter:
         rhs_exprs = [e.rhs for e in m.auxs] + [e.rhs for e in m.eqs] + [m.death, m.repli]
         if self.uses(cpl_exprs + term_exprs, r"\b(OA|SA)\("):
             raise PopError("OA()/SA() inside %M / %C is not supported (needs the pass-1 auxiliary values of other particles)")
-        if self.uses(cpl_exprs, r"\bMA\("):
-            raise PopError("MA() inside %C is not supported yet")
+        cpl_uses_aux = self.uses(cpl_exprs, r"\bMA\(")       # the particle's own pass-1 auxiliary values (src/odexp:820-833, 905-954)
         if self.uses(term_exprs, r"\b(OY|OE)\("):
             raise PopError("OY()/OE() are only meaningful inside %C")
         terms_use_aux = self.uses(term_exprs, r"\bMA\(")
@@ -515,6 +514,8 @@ class Emitter:
             raise PopError("KY() together with MA() inside %M is not supported (the reference's first pass sees a half-updated list)")
         cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
         rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
+        if cpl_uses_aux and rhs_rng:
+            raise PopError("MA() inside %C in a model with random numbers in its RHS is not supported (the pass-1 evaluation would consume draws)")
         has_stopif = self.uses(rhs_exprs, r"\bSTOPIF\s*\(")
         # the particle id column is only read by the stage kernels when something can observe it
         needs_id = rhs_rng or self.uses(rhs_exprs + term_exprs + cpl_exprs, r"\b(ID|OID|MID|rand01|randN|exprand|poisson|DWDT)\b")
@@ -558,6 +559,7 @@ class Emitter:
         w("  static constexpr bool HAS_BIRTH = %s, HAS_DEATH = %s, HAS_REPLI = %s, RHS_RNG = %s;" %
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
         w("  static constexpr bool HAS_STOPIF = %s;" % ("true" if has_stopif else "false"))
+        w("  static constexpr bool CPL_USES_AUX = %s;      /* MA() inside %%C: ode_rhs with zeroed mean fields and the previous psi first */" % ("true" if cpl_uses_aux else "false"))
         w("  static constexpr bool USES_KY = %s;      /* KY(name, degree): the RHS reads the stage state of list neighbours */" % ("true" if uses_ky else "false"))
         w("  static constexpr int NHINT = ODX_NHINT;")
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %

@@ -214,3 +214,23 @@ def test_function_blocks(model_lib, meth, n):
     # rk8pd: the restatement itself moves by 6e-12 under a 1e-8 relative change of the tolerance (states are O(1))
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=2e-11 if meth == "rk8pd" else 1e-12)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=2e-11 if meth == "rk8pd" else 1e-12)
+
+
+@pytest.mark.parametrize("meth,n,ts", [("dde", 30, (0, 2)), ("rkf45", 41, (0, 2)), ("fe", 7, (0, 0.5)), ("dde", 1300, (0, 0.5))])
+def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
+    """`%C FRC MA(s)*OE(q)*sin(OY(x) - MY(x))`: the particle's own auxiliary value inside an all-pairs coupling is the one pass 1
+    of pop_rhs left (zeroed mean fields -- the aux of the fixture reads a mean field -- and the previous psi); the factor is
+    hoisted out of the N^2 sum by the emitter.  Restatement bit-identical to the reference binary (tests/test_oracle_port.py)."""
+    from odexp_b200 import capi
+    from oracle import port
+    h0 = 0.01 if meth == "fe" else 0.05
+    opts = {"meth": meth, "h0": h0, "res": 3, "ps": n}
+    pop = capi.Population(model_lib("pair_aux"), capacity=max(1024, n))
+    out = capi.odesolver(pop, ts, meth=meth, res=3, popsize=n, h0=h0, replay_ic=True)
+    pop.close()
+    ref = port.run("pair_aux", opts, ts)
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :2], tb[tb["step"] == 0]["cols"][:, :2])
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

@@ -61,6 +61,10 @@ REF_CASES = [
     # unweighted low-rank expansion %C ... lrexp {var, fun} (lrkern)
     ("kuramoto_lrexp", {"meth": "dde", "h0": 0.1, "res": 3, "ps": 200}, (0, 1.0)),
     ("kuramoto_lrexp", {"meth": "rkck", "h0": 0.1, "res": 3, "ps": 77}, (0, 2.0)),
+    # MA() (pass-1 value: zeroed mean fields) and OE() inside an all-pairs %C
+    ("pair_aux", {"meth": "dde", "h0": 0.05, "res": 3, "ps": 30}, (0, 2)),
+    ("pair_aux", {"meth": "rkf45", "h0": 0.05, "res": 3, "ps": 41}, (0, 2)),
+    ("pair_aux", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 7}, (0, 0.5)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
