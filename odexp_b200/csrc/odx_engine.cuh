@@ -1156,7 +1156,12 @@ __global__ void __launch_bounds__(BLOCK) k_rhs_out(Pop p, const double *__restri
 #define PAIR_WAVES 16      /* CTAs per resident slot: the tail of the last wave costs <= 1 / PAIR_WAVES of the launch */
 #endif
 constexpr int PAIR_THREADS = PAIR_THREADS_N, PAIR_ITILE = 2 * PAIR_THREADS_N, PAIR_TJ = PAIR_TJ_N, PAIR_UNROLL = PAIR_UNROLL_N;
-constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);
+constexpr int PAIR_NCOL = NVAR + (M::CPL_USES_EXPR ? NEXPR : 0);       /* columns of the other particles read from memory (and allgathered) */
+/* OA() inside %C: the other particle's auxiliary values are evaluated once per staged j-particle and kept next to its columns in
+ * the shared-memory tile (1 / PAIR_ITILE of the pair work); the emitter admits only auxiliaries that read neither mean fields
+ * nor couplings, for which the reference's pass-1 and pass-2 values coincide */
+constexpr int PAIR_SCOL = PAIR_NCOL + (M::CPL_USES_OAUX ? NAUX : 0);
+static_assert(sizeof(double) * (PAIR_SCOL > 0 ? PAIR_SCOL : 1) * PAIR_TJ <= 40 * 1024, "j-tile of the %C kernel exceeds static shared memory");
 /* Fast path + tile-local redo: the straight-line fast forms of the model code only signal when they cannot represent a term
  * (range-limited sincos: the context's slow flag; odx_zmul: a non-finite sum); the thread then discards what this j-tile added
  * to its sums and repeats the tile with the exact forms.  The self term of a 1/r^n kernel does this once per i-particle (1 tile
@@ -1167,7 +1172,7 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
                                           const double (&eb)[A1(NEXPR)], int32_t ida, int32_t idb, double (&acca)[A1(NPSI)],
                                           double (&accb)[A1(NPSI)], double (*s_col)[PAIR_TJ], int32_t *s_id,
                                           const double (&auxa)[A1(NAUX)], const double (&auxb)[A1(NAUX)]) {
-  double aux[A1(NAUX)];      /* stands for the other particle's auxiliaries: OA() is rejected by the emitter */
+  double aux[A1(NAUX)];      /* the other particle's auxiliaries (OA()), filled from the tile when the model reads them */
 #pragma unroll
   for (int k = 0; k < A1(NPSI); k++) { acca[k] = 0.0; accb[k] = 0.0; }
   DevCtx ca = make_ctx(p, 0.0, 0, DOM_RHS, ida);
@@ -1183,6 +1188,21 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
         for (int v = 0; v < NEXPR; v++) s_col[NVAR + v][jj] = je[(int64_t)v * jstride + j0 + jj];
       }
       if (M::NEEDS_ID) s_id[jj] = jid[j0 + jj];
+      if (M::CPL_USES_OAUX) {
+        double oyv[A1(NVAR)], oev[A1(NEXPR)], zp[A1(NPSI)], zm[A1(NMFD)], fo[A1(NVAR)], oax[A1(NAUX)], d = 0.0, r = 0.0;
+#pragma unroll
+        for (int v = 0; v < NVAR; v++) oyv[v] = s_col[v][jj];
+#pragma unroll
+        for (int v = 0; v < NEXPR; v++) oev[v] = s_col[NVAR + v][jj];          /* CPL_USES_EXPR is set together with CPL_USES_OAUX */
+#pragma unroll
+        for (int k = 0; k < A1(NPSI); k++) zp[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < A1(NMFD); k++) zm[k] = 0.0;
+        DevCtx co = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? jid[j0 + jj] : 0);
+        M::template rhs<true>(co, t, oyv, oev, zp, zm, fo, oax, d, r);
+#pragma unroll
+        for (int v = 0; v < NAUX; v++) s_col[PAIR_NCOL + v][jj] = oax[v];
+      }
     }
     __syncthreads();
     double sava[A1(NPSI)], savb[A1(NPSI)];
@@ -1199,6 +1219,10 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
         for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
       }
       if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
+      if (M::CPL_USES_OAUX) {
+#pragma unroll
+        for (int v = 0; v < NAUX; v++) aux[v] = s_col[PAIR_NCOL + v][jj];
+      }
       M::template cpl_terms<false>(ca, t, ya, ea, auxa, oy, oe, aux, acca);
       M::template cpl_terms<false>(cb, t, yb, eb, auxb, oy, oe, aux, accb);
     }
@@ -1221,6 +1245,10 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
           for (int v = 0; v < NEXPR; v++) oe[v] = s_col[NVAR + v][jj];
         }
         if (M::NEEDS_ID) { ca.oid = s_id[jj]; cb.oid = s_id[jj]; }
+        if (M::CPL_USES_OAUX) {
+#pragma unroll
+          for (int v = 0; v < NAUX; v++) aux[v] = s_col[PAIR_NCOL + v][jj];
+        }
         M::template cpl_terms<true>(ca, t, ya, ea, auxa, oy, oe, aux, acca);
         M::template cpl_terms<true>(cb, t, yb, eb, auxb, oy, oe, aux, accb);
       }
@@ -1230,7 +1258,7 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
                                                        const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
                                                        int64_t nj, double t, double *__restrict__ part, int seg_base) {
-  __shared__ double s_col[A1(PAIR_NCOL)][PAIR_TJ];
+  __shared__ double s_col[A1(PAIR_SCOL)][PAIR_TJ];
   __shared__ int32_t s_id[PAIR_TJ];
   /* this CTA's j-range: segment blockIdx.y of gridDim.y, boundaries aligned to the j-tile */
   const int64_t tiles = (nj + PAIR_TJ - 1) / PAIR_TJ;

@@ -501,8 +501,24 @@ class Emitter:
         term_exprs = [e.rhs for e in m.mfds] + ([m.birth] if m.birth else [])
         cpl_exprs = [c.rhs for c in pair_cpls]
         rhs_exprs = [e.rhs for e in m.auxs] + [e.rhs for e in m.eqs] + [m.death, m.repli]
-        if self.uses(cpl_exprs + term_exprs, r"\b(OA|SA)\("):
-            raise PopError("OA()/SA() inside %M / %C is not supported (needs the pass-1 auxiliary values of other particles)")
+        if self.uses(term_exprs, r"\b(OA|SA)\(") or self.uses(cpl_exprs, r"\bSA\("):
+            raise PopError("OA()/SA() inside %M and SA() inside %C are not supported")
+        # OA(a) inside %C: in the reference other_->aux holds pass-2 values for the particles before myself_ in the list and pass-1
+        # values (zeroed mean fields, previous psi) for those after it (src/odexp:905-954).  The two coincide -- and the sum can be
+        # formed in parallel -- exactly when `a`, through the auxiliaries it reads, depends on no mean field and no coupling.
+        cpl_uses_oaux = self.uses(cpl_exprs, r"\bOA\(")
+        if cpl_uses_oaux:
+            tainted = {x.name for x in m.mfds} | {x.name for x in m.cpls}
+            dirty = set()
+            for a in m.auxs:                                   # file order: an auxiliary can only read the ones before it
+                ids = set(re.findall(IDENT, a.rhs))
+                if ids & (tainted | dirty) or re.search(r"\b(MF|MC|KY|rand01|randN|exprand|poisson|DWDT)\b", a.rhs):
+                    dirty.add(a.name)
+            for ex in cpl_exprs:
+                for nm in re.findall(r"\bOA\(\s*(%s)\s*\)" % IDENT, ex or ""):
+                    if nm in dirty:
+                        raise PopError("OA(%s) inside %%C: '%s' depends on a mean field, a coupling or a random number, so its value for "
+                                       "the other particle depends on the list order in the reference; not supported" % (nm, nm))
         cpl_uses_aux = self.uses(cpl_exprs, r"\bMA\(")       # the particle's own pass-1 auxiliary values (src/odexp:820-833, 905-954)
         if self.uses(term_exprs, r"\b(OY|OE)\("):
             raise PopError("OY()/OE() are only meaningful inside %C")
@@ -512,7 +528,7 @@ class Emitter:
             raise PopError("KY() ring neighbours are only supported inside AUX / D/DT / %DEATH / %REPLI")
         if uses_ky and terms_use_aux:
             raise PopError("KY() together with MA() inside %M is not supported (the reference's first pass sees a half-updated list)")
-        cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(")
+        cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(") or (cpl_uses_oaux and m.nexpr > 0)      # the other particle's aux may read its expressions
         rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
         if cpl_uses_aux and rhs_rng:
             raise PopError("MA() inside %C in a model with random numbers in its RHS is not supported (the pass-1 evaluation would consume draws)")
@@ -560,6 +576,7 @@ class Emitter:
           tuple("true" if x else "false" for x in (m.birth, m.death, m.repli, rhs_rng)))
         w("  static constexpr bool HAS_STOPIF = %s;" % ("true" if has_stopif else "false"))
         w("  static constexpr bool CPL_USES_AUX = %s;      /* MA() inside %%C: ode_rhs with zeroed mean fields and the previous psi first */" % ("true" if cpl_uses_aux else "false"))
+        w("  static constexpr bool CPL_USES_OAUX = %s;     /* OA() inside %%C: the other particle's auxiliaries, evaluated per staged j-particle */" % ("true" if cpl_uses_oaux else "false"))
         w("  static constexpr bool USES_KY = %s;      /* KY(name, degree): the RHS reads the stage state of list neighbours */" % ("true" if uses_ky else "false"))
         w("  static constexpr int NHINT = ODX_NHINT;")
         w("  static constexpr bool HAS_PAIR = %s, HAS_LOWRANK = %s, TERMS_USE_AUX = %s, CPL_USES_EXPR = %s, NEEDS_ID = %s;" %

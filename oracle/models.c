@@ -167,17 +167,19 @@ static double kle_mfd(orc_ctx *c, int k, const double *y, const double *e, const
 static const double pa_pars[] = {0.5, 0.1};
 static void pa_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
                    double *aux, double *death, double *repli) {
-  const double g = c->mu[0], cc = c->mu[1], q = e[0], x = y_[0], v = y_[1], FRC = psi[0], XM = mfd[0];
+  const double g = c->mu[0], cc = c->mu[1], q = e[0], x = y_[0], v = y_[1], FRC = psi[0], DRG = psi[1], XM = mfd[0];
   const double s = q*(1 + x*x) + cc*XM;
+  const double w = q/(1 + v*v);
   const double fo = FRC;
   (void)t; (void)death; (void)repli;
   f[0] = v;
-  f[1] = -x + g*FRC - cc*XM;
-  aux[0] = s; aux[1] = fo;
+  f[1] = -x + g*FRC - cc*XM + 0.2*DRG;
+  aux[0] = s; aux[1] = w; aux[2] = fo;
 }
 static void pa_cpl(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi) {
   (void)e;
   psi[0] += c->my_aux[0]*oe[0]*sin(oy[0] - y[0]);        /* MA(s)*OE(q)*sin(OY(x) - MY(x)) */
+  psi[1] += c->other_aux[1]*(oy[1] - y[1]);              /* OA(w)*(OY(v) - MY(v)) */
 }
 static double pa_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
   (void)c; (void)k; (void)e; (void)aux; (void)mfd;
@@ -367,7 +369,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
-  {"pair_aux", 2, 1, 2, 1, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
+  {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 3, 2, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},

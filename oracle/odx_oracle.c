@@ -190,7 +190,7 @@ int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
       for (k = 0; k < m->npsi; k++) p->psi[k] = 0.0;
       for (j = 0; j < s->n; j++) {
         orc_par *o = s->p[j];
-        rhs_ctx(s, &c, p); c.oid = o->id; c.my_aux = p->aux;
+        rhs_ctx(s, &c, p); c.oid = o->id; c.my_aux = p->aux; c.other_aux = o->aux;
         m->cpl_terms(&c, p->y, p->expr, o->y, o->expr, p->psi);
       }
       for (k = 0; k < m->npsi; k++) p->psi[k] /= s->size;

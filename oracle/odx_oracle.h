@@ -30,6 +30,7 @@ typedef struct orc_ctx {
   int id, oid, atbirth, atrepli, ist0;
   const orc_par *sister;
   int pos;                                 /* position of the particle in the list (KY) */
+  const double *other_aux;                 /* other_->aux (OA() inside %C) */
   const double *my_aux;                    /* myself_->aux while the %C terms are summed (MA() inside %C: pass-1 values) */
   uint32_t kid, kstream, kdom, kslot;      /* keyed-Philox address of the next draw (rng_mode 1) */
 } orc_ctx;

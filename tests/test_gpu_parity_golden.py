@@ -220,7 +220,9 @@ def test_function_blocks(model_lib, meth, n):
 def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
     """`%C FRC MA(s)*OE(q)*sin(OY(x) - MY(x))`: the particle's own auxiliary value inside an all-pairs coupling is the one pass 1
     of pop_rhs left (zeroed mean fields -- the aux of the fixture reads a mean field -- and the previous psi); the factor is
-    hoisted out of the N^2 sum by the emitter.  Restatement bit-identical to the reference binary (tests/test_oracle_port.py)."""
+    hoisted out of the N^2 sum by the emitter.  `%C DRG OA(w)*(OY(v) - MY(v))`: the OTHER particle's auxiliary value, evaluated
+    per staged j-particle (w reads no mean field / coupling, so pass-1 and pass-2 values coincide).  Restatement bit-identical
+    to the reference binary (tests/test_oracle_port.py); n = 1300 spans several j-tiles and i-tiles."""
     from odexp_b200 import capi
     from oracle import port
     h0 = 0.01 if meth == "fe" else 0.05

@@ -118,9 +118,17 @@ def test_emit_lowrank_variants():
 
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
-    m = popfile.parse("aux a 1\n%C P OA(a)\ndx/dt = P\ninit x 0\n")
-    with pytest.raises(popfile.PopError):
-        cudagen.emit_cuda(m)
+    # OA() of an auxiliary that reads a mean field (directly or through another auxiliary) or a coupling: its value for the other
+    # particle depends on the list order in the reference
+    for txt in ("%M XM MY(x)\naux a x*XM\n%C P OA(a)\ndx/dt = P\ninit x 0\n",
+                "%M XM MY(x)\naux a x*XM\naux b 2*a\n%C P OA(b)\ndx/dt = P\ninit x 0\n",
+                "aux a P\n%C P OA(a)\ndx/dt = P\ninit x 0\n",
+                "aux a x\n%M XM OA(a)\ndx/dt = XM\ninit x 0\n",
+                "aux a x\n%C P SA(a)\ndx/dt = P\ninit x 0\n"):
+        with pytest.raises(popfile.PopError):
+            cudagen.emit_cuda(popfile.parse(txt))
+    ok = cudagen.emit_cuda(popfile.parse("expr q 1\naux a q*x\n%C P OA(a)*MA(a)\ndx/dt = P\ninit x 0\n"))
+    assert "CPL_USES_OAUX = true" in ok and "CPL_USES_AUX = true" in ok and "CPL_USES_EXPR = true" in ok
 
 
 def test_unicode_identifiers_are_mangled():
