@@ -17,7 +17,11 @@ CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde",
          ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 1}),          # ring / lean step kernels with the NVLink exchange
          ("nbody", 3001, "dde", 2, 1e-12, {}), ("nbody", 2048, "rkf45", 3, 1e-9, {}),
          ("vdp_sde", 50001, "fe", 10, 1e-12, {}), ("vdp_sde", 50001, "fe", 10, 1e-12, {"tma": 1}), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10, {}),
-         ("kuramoto_lowrank64", 4099, "dde", 2, 1e-10, {})]
+         ("kuramoto_lowrank64", 4099, "dde", 2, 1e-10, {}),
+         # model-language coverage added late in round 1: MA()/OA() in %C, low-rank in an auxiliary variable, unweighted lrexp,
+         # array variables + MA() in %M, {vect} mean fields
+         ("pair_aux", 3001, "dde", 3, 1e-12, {}), ("kuramoto_lowrank_aux", 4097, "dde", 3, 1e-10, {}), ("kuramoto_lrexp", 4097, "dde", 3, 1e-10, {}),
+         ("chain_array", 50001, "dde", 5, 1e-12, {}), ("vect_meanfield", 50001, "fe", 5, 1e-12, {})]
 for model, n, meth, nsteps, tol, opts in CASES:
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
@@ -54,7 +58,7 @@ for model, n, meth, nsteps, tol, opts in CASES:
         ref = solo.download(lo, hi - lo)
         dy = np.abs(mine["y"] - ref["y"]).max() / (np.abs(ref["y"]).max() + 1e-300)
         dp = (np.abs(mine["psi"] - ref["psi"]).max() / (np.abs(ref["psi"]).max() + 1e-300)) if lib.npsi else 0.0
-        dm = np.abs(mfd - solo.meanfields()).max() if lib.nmfd else 0.0
+        dm = (np.abs(mfd - solo.meanfields()) / np.maximum(1.0, np.abs(mfd))).max() if lib.nmfd else 0.0      # {vect} fields scale with POP_SIZE
         good = (dy <= tol) and (dp <= max(tol, 1e-12)) and (dm <= 1e-13) and np.array_equal(mine["id"], ref["id"]) and abs(t - ts) < 1e-15
         ok &= bool(good)
         print("%-8s %-5s %-22s N=%d world=%d  t=%.6g (solo %.6g)  max rel dy=%.2e  dpsi=%.2e  dmfd=%.2e  ids_equal=%s  -> %s" % (
