@@ -36,7 +36,8 @@ class SolverOpts(C.Structure):
     _fields_ = [("method", C.c_int), ("res", C.c_int), ("hmin", C.c_double), ("h0", C.c_double), ("abstol", C.c_double),
                 ("reltol", C.c_double), ("ssahmin", C.c_double), ("aleap", C.c_double), ("popsize", C.c_int), ("seed", C.c_uint32),
                 ("replay_ic", C.c_int), ("traj_stride", C.c_int), ("outdir", C.c_char_p), ("tspan", C.POINTER(C.c_double)),
-                ("tspan_len", C.c_int), ("mu", C.POINTER(C.c_double))]
+                ("tspan_len", C.c_int), ("mu", C.POINTER(C.c_double)),
+                ("quick", C.c_int), ("plot_x", C.c_int), ("plot_y", C.c_int), ("plot_z", C.c_int), ("particle", C.c_int)]
 
 
 class SolverReport(C.Structure):
@@ -51,7 +52,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
-               "odx_pop_download_strided", "odx_tauleap_apply_view"]
+               "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id"]
 
 
 def _dp(a):
@@ -85,6 +86,7 @@ class ModelLib:
         L.odx_pop_download.argtypes = [H, C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 2
         L.odx_pop_download_strided.argtypes = [H, C.c_int64, C.c_int64, C.c_int64] + [C.POINTER(C.c_double)] * 4 + [C.POINTER(C.c_int32)]
         L.odx_pop_size.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        L.odx_pop_find_id.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
         L.odx_pop_init.argtypes = [H, C.c_int64, C.c_double, C.c_uint32, C.c_int]
         L.odx_pop_reinit.argtypes = [H, C.c_double, C.c_int]
         L.odx_stop_flag.argtypes = [H, C.POINTER(C.c_int)]
@@ -206,6 +208,12 @@ class Population:
         self.L.odx_pop_size(self.h, C.byref(a), C.byref(b), C.byref(m))
         return a.value, b.value, m.value
 
+    def find_id(self, pid):
+        """getpar(id): local position of the particle with this id, -1 if it is not on this GPU"""
+        pos = C.c_int64()
+        self._ck(self.L.odx_pop_find_id(self.h, int(pid), C.byref(pos)), "odx_pop_find_id")
+        return pos.value
+
     def download(self, first=0, count=None):
         n = self.size()[0]
         count = n - first if count is None else count
@@ -323,12 +331,17 @@ def read_outputs(outdir, dims, read_traj=True):
         nc = dims["nvar"] + dims["naux"] + dims["npsi"] + nmfd + dims["nexpr"]
         tdt = np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (nc,))])
         out["traj"] = np.fromfile(tp, dtype=tdt)
+    qp = os.path.join(outdir, "current.plot")
+    if os.path.exists(qp):
+        out["quick"] = np.fromfile(qp, dtype="<f8").reshape(-1, 3)      # fwrite_quick rows (x, y, z)
     return out
 
 
 def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, popsize=1, ssahmin=0.0,
-              aleap=0.01, seed=3141592, replay_ic=True, traj_stride=1, outdir=None, mu=None, read_traj=True):
-    """Python mirror of `odesolver` (src/methods_odexp.h:13-17) driving the C host loop; returns outputs + report."""
+              aleap=0.01, seed=3141592, replay_ic=True, traj_stride=1, outdir=None, mu=None, read_traj=True, quick=True,
+              plot=(-1, 0, 1), particle=0):
+    """Python mirror of `odesolver` (src/methods_odexp.h:13-17) driving the C host loop; returns outputs + report.
+    quick / plot / particle: current.plot with `opt x|y|z` as indices (-1 = T; reference defaults T, [0], [1]) and `opt particle`."""
     own = outdir is None
     if own:
         outdir = tempfile.mkdtemp(prefix="odx_out_")
@@ -336,7 +349,8 @@ def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, a
     ts = np.ascontiguousarray(tspan, dtype=np.float64)
     muarr = np.ascontiguousarray(mu, dtype=np.float64) if mu is not None else None
     o = SolverOpts(METHODS[meth], int(res), hmin, h0, abstol, reltol, ssahmin, aleap, int(popsize), int(seed), 1 if replay_ic else 0,
-                   int(traj_stride), outdir.encode(), _dp(ts), len(ts), _dp(muarr))
+                   int(traj_stride), outdir.encode(), _dp(ts), len(ts), _dp(muarr), 1 if quick else 0, int(plot[0]), int(plot[1]),
+                   int(plot[2]), int(particle))
     rep = SolverReport()
     st = pop.L.odx_odesolver(pop.h, C.byref(o), C.byref(rep))
     if st != 0:

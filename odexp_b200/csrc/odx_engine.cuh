@@ -1431,6 +1431,11 @@ __global__ void k_soa_to_aos_strided(const double *__restrict__ soa, double *__r
 __global__ void k_gather_ids(const int32_t *__restrict__ id, int32_t *__restrict__ out, int64_t m, int64_t first, int64_t step) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) out[i] = id[first + i * step];
 }
+/* position of the particle with a given id in this GPU's part of the list (getpar(), src/datastruct.c): ids are unique */
+__global__ void k_find_id(const int32_t *__restrict__ id, int64_t n, int32_t want, long long *__restrict__ pos) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (id[i] == want) *pos = (long long)i;
+}
 __global__ void k_iota_ids(int32_t *id, int64_t n, int32_t first) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) id[i] = first + (int32_t)i;
 }

@@ -9,7 +9,8 @@
  *   - stopping times inside TIMESPAN (STOP_TSPAN) and STOPIF (STOP_COND) end the current output interval and re-initialise
  *     the living particles (src/methods_odexp.c:222-236, 453-459, 704-720);
  *   - traj.dat can be thinned (traj_stride) or switched off: at N = 2^24 one frame is 1.2 GB;
- *   - current.plot (the 3-column quick buffer of the gnuplot UI) is not written.
+ *   - current.plot (the 3-column quick buffer of the gnuplot UI, fwrite_quick) is written when odx_solver_opts.quick is set:
+ *     one particle and the mean fields per row, never the population;
  */
 #include <math.h>
 #include <stdio.h>
@@ -25,7 +26,8 @@ static double now_ms(void) {
 }
 
 typedef struct {
-  FILE *fstats, *ftraj;
+  FILE *fstats, *ftraj, *fquick;
+  int ngx, ngy, ngz, cp;          /* opt x / y / z as indices, opt particle */
   unsigned int nbrsteps;
   int nmfd, nvar, naux, npsi, nexpr;
   double *mfd;
@@ -57,10 +59,49 @@ static int ensure_buffers(out_state *os, int64_t n) {
   return (os->y && os->e && os->aux && os->psi && os->ids) ? 0 : ODX_ENOMEM;
 }
 
+/* fwrite_quick (src/methods_odexp.c:1353-1436): one (x, y, z) row of current.plot.  An axis index is -1 for T, then counts the
+ * dynamical variables, auxiliary variables and couplings of the current particle (getpar(opt particle): looked up by id), then
+ * the mean fields.  As coded in the reference a dynamical variable is read from the state array at y[cp * tx + ng] with
+ * tx = nvar + naux + npsi (not cp * nvar): reproduced, NaN where the reference would read past the end of y.  Multi-GPU: a
+ * rank that does not own the particle writes NaN in its columns. */
+static int write_quick_row(odx_handle *h, out_state *os, double t) {
+  const int tx = os->nvar + os->naux + os->npsi, ng[3] = {os->ngx, os->ngy, os->ngz};
+  double row[3];
+  int64_t n = 0, pos = -1;
+  int k, st, need_par = 0;
+  if (!os->fquick) return 0;
+  odx_pop_size(h, &n, NULL, NULL);
+  for (k = 0; k < 3; k++) if (ng[k] >= 0 && ng[k] < tx) need_par = 1;
+  if (need_par) {                                 /* pars = getpar(cp): NULL when the particle is dead (or on another GPU) */
+    if ((st = odx_pop_find_id(h, os->cp, &pos)) != 0) return st;
+    if ((st = ensure_buffers(os, 1)) != 0) return st;
+    if (pos >= 0 && (st = odx_pop_download(h, pos, 1, NULL, NULL, os->aux, os->psi, NULL, NULL, NULL)) != 0) return st;
+  }
+  for (k = 0; k < 3; k++) {
+    const int g = ng[k];
+    if (g == -1) row[k] = t;
+    else if (g < os->nvar && pos >= 0) {          /* y + cp * tx + ng: an element of the particle-major state array */
+      const int64_t el = (int64_t)os->cp * tx + g, ip = el / os->nvar;
+      row[k] = NAN;
+      if (ip < n) {
+        if ((st = odx_pop_download(h, ip, 1, os->y, NULL, NULL, NULL, NULL, NULL, NULL)) != 0) return st;
+        row[k] = os->y[el % os->nvar];
+      }
+    }
+    else if (g < os->nvar + os->naux && pos >= 0) row[k] = os->aux[g - os->nvar];
+    else if (g < tx && pos >= 0) row[k] = os->psi[g - os->nvar - os->naux];
+    else if (g >= tx) row[k] = (g - tx < os->nmfd) ? os->mfd[g - tx] : NAN;
+    else row[k] = NAN;
+  }
+  fwrite(row, sizeof(double), 3, os->fquick);
+  return 0;
+}
+
 /* fwrite_all_particles (src/datastruct.c:655-674): per particle: step, id, t, y, aux, psi, meanfield, expr */
 static int write_traj_frame(odx_handle *h, out_state *os, double t, int stride) {
   int64_t n = 0, m, i;
   int st;
+  if ((st = write_quick_row(h, os, t)) != 0) return st;          /* fwrite_quick precedes fwrite_all_particles at every call site */
   if (!os->ftraj || stride <= 0) { os->nbrsteps++; return 0; }
   odx_pop_size(h, &n, NULL, NULL);
   m = (n + stride - 1) / stride;                  /* particles 0, stride, 2*stride, ... */
@@ -134,6 +175,11 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   if (o->traj_stride > 0) {
     snprintf(path, sizeof path, "%s/traj.dat", o->outdir ? o->outdir : ".odexp");
     if ((os.ftraj = fopen(path, "w")) == NULL) { status = ODX_EFAILED; goto done; }
+  }
+  if (o->quick) {                                 /* QUICK_BUFFER, src/macros.h:30 */
+    snprintf(path, sizeof path, "%s/current.plot", o->outdir ? o->outdir : ".odexp");
+    if ((os.fquick = fopen(path, "w")) == NULL) { status = ODX_EFAILED; goto done; }
+    os.ngx = o->plot_x; os.ngy = o->plot_y; os.ngz = o->plot_z; os.cp = o->particle;
   }
 
   if (o->mu && (status = odx_set_params(h, o->mu, mi->npar)) != 0) goto done;
@@ -252,6 +298,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
 done:
   if (os.fstats) fclose(os.fstats);
   if (os.ftraj) fclose(os.ftraj);
+  if (os.fquick) fclose(os.fquick);
   free(tstops);
   free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids);
   if (rep) {

@@ -1041,6 +1041,25 @@ int odx_pop_size(odx_handle *h, int64_t *n_local, int64_t *n_global, int32_t *ma
   return ODX_SUCCESS;
 }
 
+/* getpar(id) (src/datastruct.c): local position of the particle with this id, -1 when it is not on this GPU (dead, or owned by
+ * another rank) */
+int odx_pop_find_id(odx_handle *h, int32_t id, int64_t *pos) {
+  if (!pos) return ODX_EINVAL;
+  *pos = -1;
+  if (h->n <= 0) return ODX_SUCCESS;
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  long long *d = (long long *)h->rmax;                       /* 8-byte device scratch word, idle between steps */
+  long long init = -1;
+  ODX_CUDA(h, cudaMemcpyAsync(d, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  k_find_id<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(h->ID, h->n, id, d);
+  ODX_TRY(launch_check(h));
+  ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, d, sizeof init, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  long long got; memcpy(&got, h->h_pin, sizeof got);
+  *pos = (int64_t)got;
+  return ODX_SUCCESS;
+}
+
 int odx_pop_init(odx_handle *h, int64_t n, double t, uint32_t seed, int replay) {
   if (n < 0 || n > h->cap) { h->err = "odx_pop_init: n exceeds capacity"; return ODX_EINVAL; }
   ODX_CUDA(h, cudaSetDevice(h->device));

@@ -260,6 +260,24 @@ static void write_stats(orc_sim *s, double t) {
   fwrite(&s->stop_flag, sizeof(int), 1, s->fstats);
   fwrite(s->event, sizeof(int), 3, s->fstats);
 }
+/* fwrite_quick (src/methods_odexp.c:1353-1436): one (x, y, z) row of current.plot; dynamical variables are read at
+ * y[cp * tx + ng] with tx = nvar + naux + npsi as coded there (NaN where that lies past the end of y) */
+static void write_quick(orc_sim *s, double t, const double *y) {
+  const orc_model *m = s->model; const int tx = m->nvar + m->naux + m->npsi, ng[3] = {s->ngx, s->ngy, s->ngz};
+  const orc_par *pars = NULL; double row[3]; int i, k;
+  if (!s->fquick) return;
+  for (i = 0; i < s->n; i++) if (!s->p[i]->dead && s->p[i]->id == s->cp) pars = s->p[i];          /* getpar(cp) */
+  for (k = 0; k < 3; k++) {
+    const int g = ng[k];
+    if (g == -1) row[k] = t;
+    else if (g < m->nvar && pars != NULL) row[k] = ((long)s->cp * tx + g < (long)s->n * m->nvar) ? y[s->cp * tx + g] : NAN;
+    else if (g < m->nvar + m->naux && pars != NULL) row[k] = pars->aux[g - m->nvar];
+    else if (g < tx && pars != NULL) row[k] = pars->psi[g - m->nvar - m->naux];
+    else if (g >= tx) row[k] = (g - tx < m->nmfd) ? s->mfd[g - tx] : NAN;
+    else row[k] = NAN;
+  }
+  fwrite(row, sizeof(double), 3, s->fquick);
+}
 static void write_traj(orc_sim *s, double t) {
   const orc_model *m = s->model; int i;
   if (s->ftraj) {
@@ -422,6 +440,9 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   dt = (t1 - t) / (double)(o->res - 1);
   snprintf(path, sizeof path, "%s/stats.dat", o->outdir);
   if (!(s->fstats = fopen(path, "w"))) return GSL_EFAILED;
+  snprintf(path, sizeof path, "%s/current.plot", o->outdir);
+  if (!(s->fquick = fopen(path, "w"))) return GSL_EFAILED;
+  s->ngx = o->plot_x; s->ngy = o->plot_y; s->ngz = o->plot_z; s->cp = o->particle;
   if (o->write_traj) { snprintf(path, sizeof path, "%s/traj.dat", o->outdir); if (!(s->ftraj = fopen(path, "w"))) return GSL_EFAILED; }
 
   for (i = 0; i < o->popsize; i++) par_birth(s);
@@ -434,6 +455,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
   for (i = 0; i < o->popsize; i++) { s->event[2] = i; write_stats(s, t); }
   memset(s->event, 0, sizeof s->event);
   s->stop_flag = ORC_EVENT_NONE;
+  write_quick(s, t, y);
   write_traj(s, t);
   if (odeT) { gs = gsl_odeiv2_step_alloc(odeT, dim); gc = gsl_odeiv2_control_y_new(o->abstol, o->reltol); ge = gsl_odeiv2_evolve_alloc(dim); }
 
@@ -470,6 +492,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
     write_stats(s, t);
     if (status != GSL_SUCCESS && status != GSL_EBADFUNC) break;
     tot_solver += (clock() - c0) * 1000.0 / CLOCKS_PER_SEC;
+    write_quick(s, t, y);
     write_traj(s, t);
     if (s->stop_flag & ORC_POP_MASK) {
       if (!tau) orc_ssa_apply(s, t); else orc_tauleap_apply(s, t, dt_next);
@@ -477,6 +500,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
       y = realloc(y, sizeof(double) * (dim > 0 ? dim : 1)); f = realloc(f, sizeof(double) * (dim > 0 ? dim : 1));
       fill_y(s, y);
       orc_pop_rhs(t, y, f, s);
+      write_quick(s, t, y);
       write_traj(s, t);
       memset(s->event, 0, sizeof s->event);
       if (odeT) { gsl_odeiv2_evolve_free(ge); gsl_odeiv2_step_free(gs); gs = gsl_odeiv2_step_alloc(odeT, dim); ge = gsl_odeiv2_evolve_alloc(dim); }
@@ -487,6 +511,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
       s->reinit_index++;
       fill_y(s, y);
       orc_pop_rhs(t, y, f, s);
+      write_quick(s, t, y);
       write_traj(s, t);
     }
     if (s->stop_flag & ORC_STOP_TSPAN) nextstop = (idx_stop < nstops) ? tstops[idx_stop++] : INFINITY;
@@ -498,7 +523,7 @@ int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep) {
     rep->steps = s->steps; rep->particle_steps = s->particle_steps; rep->final_n = s->size; rep->status = status;
     rep->rand_draws = s->hr.ndraws; rep->rhs_evals = s->rhs_evals;
   }
-  fclose(s->fstats); if (s->ftraj) fclose(s->ftraj);
+  fclose(s->fstats); if (s->ftraj) fclose(s->ftraj); if (s->fquick) fclose(s->fquick);
   if (odeT) { gsl_odeiv2_evolve_free(ge); gsl_odeiv2_control_free(gc); gsl_odeiv2_step_free(gs); }
   for (i = 0; i < s->n; i++) par_free(s->p[i]);
   free(s->p); free(y); free(f); free(s->mu); free(s->mfd);

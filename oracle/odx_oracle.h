@@ -67,6 +67,7 @@ typedef struct {
   const char *outdir;
   const double *tspan; int tspan_len;
   const double *mu;
+  int plot_x, plot_y, plot_z, particle;      /* opt x / y / z as indices (-1 = T), opt particle: current.plot is always written */
 } orc_opts;
 
 typedef struct { double total_ms, solver_ms, function_ms; int64_t steps; double particle_steps; int64_t final_n; int status;
@@ -79,7 +80,7 @@ typedef struct orc_sim {
   double *mu, *mfd, pop_birth_rate, *h;
   int stop_flag, event[3];
   unsigned int nbrsteps;
-  FILE *fstats, *ftraj;
+  FILE *fstats, *ftraj, *fquick; int ngx, ngy, ngz, cp;
   int rng_mode; orc_hostrand hr; uint32_t k0, k1, eval_index, host_draws, event_index;
   uint64_t rhs_evals; int64_t steps; double particle_steps, function_ms;
   int lr_last_p; uint32_t reinit_index;

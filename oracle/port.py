@@ -31,7 +31,8 @@ class Opts(C.Structure):
     _fields_ = [("method", C.c_int), ("res", C.c_int), ("hmin", C.c_double), ("h0", C.c_double), ("abstol", C.c_double),
                 ("reltol", C.c_double), ("ssahmin", C.c_double), ("aleap", C.c_double), ("popsize", C.c_int), ("seed", C.c_uint32),
                 ("rng_mode", C.c_int), ("write_traj", C.c_int), ("outdir", C.c_char_p), ("tspan", C.POINTER(C.c_double)),
-                ("tspan_len", C.c_int), ("mu", C.POINTER(C.c_double))]
+                ("tspan_len", C.c_int), ("mu", C.POINTER(C.c_double)),
+                ("plot_x", C.c_int), ("plot_y", C.c_int), ("plot_z", C.c_int), ("particle", C.c_int)]
 
 
 class Report(C.Structure):
@@ -60,7 +61,8 @@ def lib():
     return _lib
 
 
-def run(model, opts=None, timespan=(0.0, 1.0), rng_mode=0, read_traj=True, mu=None, outdir=None):
+def run(model, opts=None, timespan=(0.0, 1.0), rng_mode=0, read_traj=True, mu=None, outdir=None, plot=(-1, 0, 1), particle=0):
+    """plot = (x, y, z) axis indices of current.plot: -1 = T, then dynamical variables, auxiliaries, couplings, mean fields"""
     o = dict(meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, ps=1, seed=3141592)
     o.update(opts or {})
     own = outdir is None
@@ -71,7 +73,8 @@ def run(model, opts=None, timespan=(0.0, 1.0), rng_mode=0, read_traj=True, mu=No
     op = Opts(METHODS[o["meth"]], int(o["res"]), float(o["hmin"]), float(o["h0"]), float(o["abstol"]), float(o["reltol"]),
               float(o["ssahmin"]), float(o["aleap"]), int(o["ps"]), int(o["seed"]), int(rng_mode), 1 if read_traj else 0,
               outdir.encode(), ts.ctypes.data_as(C.POINTER(C.c_double)), len(ts),
-              muarr.ctypes.data_as(C.POINTER(C.c_double)) if muarr is not None else None)
+              muarr.ctypes.data_as(C.POINTER(C.c_double)) if muarr is not None else None,
+              int(plot[0]), int(plot[1]), int(plot[2]), int(particle))
     rep = Report()
     st = lib().orc_odesolver(model.encode(), C.byref(op), C.byref(rep))
     if st != 0:
@@ -83,6 +86,7 @@ def run(model, opts=None, timespan=(0.0, 1.0), rng_mode=0, read_traj=True, mu=No
         nc = d["nvar"] + d["naux"] + d["npsi"] + d["nmfd"] + d["nexpr"]
         tdt = np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (nc,))])
         out["traj"] = np.fromfile(os.path.join(outdir, "traj.dat"), dtype=tdt)
+    out["quick"] = np.fromfile(os.path.join(outdir, "current.plot"), dtype="<f8").reshape(-1, 3)
     out["report"] = {k: getattr(rep, k) for k, _ in Report._fields_}
     if own:
         shutil.rmtree(outdir, ignore_errors=True)

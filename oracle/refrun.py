@@ -76,6 +76,9 @@ def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False
         if read_traj and all(k in dims for k in ("nvar", "naux", "npsi", "nexpr")):
             nc = dims["nvar"] + dims["naux"] + dims["npsi"] + nmfd + dims["nexpr"]
             res["traj"] = np.fromfile(os.path.join(work, ".odexp", "traj.dat"), dtype=traj_dtype(nc))
+        qp = os.path.join(work, ".odexp", "current.plot")
+        if os.path.exists(qp):
+            res["quick"] = np.fromfile(qp, dtype="<f8").reshape(-1, 3)
         if rand_log and os.path.exists(env["ODX_RAND_LOG"]):
             res["rand"] = np.fromfile(env["ODX_RAND_LOG"], dtype="<i4")
         if keep:

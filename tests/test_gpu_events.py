@@ -180,3 +180,36 @@ def test_stopping_time_keeps_evolve_state(model_lib):
     np.testing.assert_array_equal(out["stats"]["stop_flag"], ref["stats"]["stop_flag"])
     np.testing.assert_allclose(out["stats"]["t"], ref["stats"]["t"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("model,opts,ts,axes,particle", [
+    ("kuramoto", {"meth": "dde", "h0": 0.05, "res": 6, "ps": 20}, (0, 1.0), (-1, 0, 1), 0),                 # reference defaults T, [0], [1]
+    ("kuramoto", {"meth": "dde", "h0": 0.05, "res": 6, "ps": 20}, (0, 1.0), (2, 4, 5), 0),                  # an auxiliary, two mean fields
+    ("kuramoto", {"meth": "rkck", "h0": 0.1, "res": 6, "ps": 20}, (0, 1.0), (0, 1, 3), 3),                  # y[cp * tx + ng]: another particle's variable
+    ("kuramoto", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 5}, (0, 1.0), (0, -1, 2), 4),                  # past the end of y: NaN
+    ("nbody", {"meth": "dde", "h0": 0.05, "res": 3, "ps": 12}, (0, 0.1), (7, 2, 8), 5),                     # couplings of particle 5
+    ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 41, "ps": 30, "ssahmin": 1.0}, (0, 8), (1, 0, -1), 21),   # the plotted particle dies
+    ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 21, "ps": 10, "ssahmin": 0.0}, (0, 4), (-1, 1, 0), 11),   # ... or is born later
+    ("reset_decay", {"meth": "dde", "h0": 0.05, "res": 25, "ps": 20}, (0, 1.5, 3.25, 6), (-1, 0, 2), 1),    # rows after stopping times
+])
+def test_quick_buffer(model_lib, model, opts, ts, axes, particle):
+    """current.plot, the three-column buffer the reference's gnuplot UI plots (fwrite_quick, src/methods_odexp.c:1353-1436):
+    one row at t0, after every output interval, after every birth / death sweep and after every stop; columns by `opt x|y|z`
+    for the particle `opt particle` (looked up by id on the device).  The restatement is pinned to the reference binary
+    (tests/test_oracle_port.py::test_quick_buffer_matches_reference_binary)."""
+    from odexp_b200 import capi
+    from oracle import port
+    keyed = model == "vdp_sde"
+    pop = capi.Population(model_lib(model), capacity=4096)
+    out = capi.odesolver(pop, ts, meth=opts["meth"], res=opts["res"], popsize=opts["ps"], h0=opts["h0"], ssahmin=opts.get("ssahmin", 0.0),
+                         replay_ic=not keyed, plot=axes, particle=particle)
+    if model == "kuramoto":
+        assert pop.find_id(particle) == particle and pop.find_id(10 ** 6) == -1
+    pop.close()
+    ref = port.run(model, opts, ts, rng_mode=1 if keyed else 0, plot=axes, particle=particle)
+    qa, qb = out["quick"], ref["quick"]
+    assert qa.shape == qb.shape == (len(out["traj"]["step"]) and out["traj"]["step"].max() + 1, 3)
+    np.testing.assert_array_equal(np.isnan(qa), np.isnan(qb))
+    np.testing.assert_allclose(qa, qb, rtol=1e-10, atol=1e-12, equal_nan=True)
+    if model == "vdp_sde":
+        assert np.isnan(qb).any() and not np.isnan(qb).all()

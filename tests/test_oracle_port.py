@@ -97,6 +97,9 @@ def test_port_matches_reference_binary(model, opts, ts):
     np.testing.assert_array_equal(ta["step"], tb["step"])
     np.testing.assert_allclose(sa["t"], sb["t"], rtol=0, atol=1e-14)
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-13, atol=1e-15)
+    # current.plot with the default axes (T, first variable, second column of [variables | auxiliaries | couplings | mean fields])
+    assert a["quick"].shape == b["quick"].shape
+    np.testing.assert_allclose(a["quick"], b["quick"], rtol=1e-13, atol=1e-15, equal_nan=True)
     if model == "reset_decay":
         assert (sa["stop_flag"] & 8).any() and (sa["stop_flag"] & 4).any(), "case must contain STOP_COND and STOP_TSPAN"
     if model == "vdp_sde":
@@ -128,3 +131,23 @@ def test_minigsl_rkf45_vs_rkck_agree_to_tolerance():
     lc = c["traj"][c["traj"]["step"] == 2]["cols"][:, 0]
     np.testing.assert_allclose(la, lb, rtol=1e-9)
     np.testing.assert_allclose(la, lc, rtol=1e-9)
+
+
+@pytest.mark.parametrize("model,opts,ts,axes,names,particle", [
+    # an auxiliary variable, two mean fields; particle 3: the reference reads y[cp * tx + ng], i.e. another particle's variable
+    ("kuramoto", {"meth": "dde", "h0": 0.05, "res": 6, "ps": 20}, (0, 1.0), (2, 4, 5), ("coupling", "A2", "OMEGA"), 0),
+    ("kuramoto", {"meth": "rkck", "h0": 0.1, "res": 6, "ps": 20}, (0, 1.0), (0, 1, 3), ("theta", "y", "A1"), 3),
+    # birth / death: the plotted particle dies (NaN columns from then on) or is born later
+    ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 41, "ps": 30, "ssahmin": 1.0}, (0, 8), (1, 0, -1), ("x", "y", "T"), 7),
+    ("vdp_sde", {"meth": "fe", "h0": 0.01, "res": 21, "ps": 10, "ssahmin": 0.0}, (0, 4), (-1, 1, 0), ("T", "x", "y"), 2),
+])
+def test_quick_buffer_matches_reference_binary(model, opts, ts, axes, names, particle):
+    """current.plot (fwrite_quick, src/methods_odexp.c:1353-1436) for chosen axes / particle, to 1e-13.  Not compared: rows where
+    the reference's y[cp * tx + ng] lies past the end of y (it reads the heap there; the restatement and the CUDA path write NaN)"""
+    from oracle import port, refrun
+    if not refrun.have(model):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    a = port.run(model, opts, ts, plot=axes, particle=particle)
+    b = refrun.run(model, dict(opts, x=names[0], y=names[1], z=names[2], particle=particle), timespan=ts, dims=port.DIMS[model])
+    assert a["quick"].shape == b["quick"].shape and len(a["quick"]) > 3
+    np.testing.assert_allclose(a["quick"], b["quick"], rtol=1e-13, atol=1e-15, equal_nan=True)
