@@ -622,7 +622,9 @@ class Emitter:
             # arrays: one loop per entry with the reference's `size_t` iterator (src/odexp:1381-1436, 1439-1506); no common-subexpression
             # hoisting across the loop
             for e in m.auxs:
-                if e.length:
+                if e.length and is_vect(e):        # filled by a function: the rhs is evaluated once, as a statement (src/odexp:1394-1397)
+                    w("    double %s[%d]; %s;" % (mangle(e.name), e.start + e.length, self.tr(e.rhs, "aux " + e.name)))
+                elif e.length:
                     it = mangle(e.iterator)
                     w("    double %s[%d]; for (size_t %s = %d; %s < %d; ++%s) %s[%s] = %s;" % (mangle(e.name), e.start + e.length, it, e.start, it,
                       e.start + e.length, it, mangle(e.name), it, self.tr(e.rhs, "aux " + e.name)))
@@ -728,7 +730,10 @@ class Emitter:
                 w("    const double %s = odx_c.mu[%d];" % (mangle(p.name), i))
         for e in m.exprs:
             b = self.expr_base[e.name]
-            if e.length:
+            if e.length and is_vect(e):
+                w("    double %s[%d]; %s;" % (mangle(e.name), e.start + e.length, self.tr(e.rhs, "expr " + e.name, exact=True)))
+                w("    for (int odx_i = 0; odx_i < %d; odx_i++) odx_e[%d + odx_i] = %s[%d + odx_i];" % (e.length, b, mangle(e.name), e.start))
+            elif e.length:
                 it = mangle(e.iterator)
                 w("    double %s[%d];" % (mangle(e.name), e.start + e.length))
                 w("    for (size_t %s = %d; %s < %d; %s++) { %s[%s] = %s; odx_e[%d + %s - %d] = %s[%s]; }" %

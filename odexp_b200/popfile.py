@@ -216,9 +216,7 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.exprs.append(_name_and_rhs(rest, lineno, raw))
     elif kwl.startswith("aux"):
         e = _name_and_rhs(rest, lineno, raw)
-        if e.length and re.search(r"\b(vect|noloop)\b", e.attr):
-            raise PopError("line %d: {vect} array auxiliary variables (filled by a function) are not supported" % lineno)
-        m.auxs.append(e)          # scalar, or one-dimensional array `aux a[i=0:5] X[i]*X[i]` (define_array_functions, src/odexp:1381-1436)
+        m.auxs.append(e)          # {vect}: the rhs is a statement that fills the array (`aux arr[i=0:5] myfunc(arr) {vect}`)          # scalar, or one-dimensional array `aux a[i=0:5] X[i]*X[i]` (define_array_functions, src/odexp:1381-1436)
     elif kwl.startswith("init"):
         m.inits.append(_name_and_rhs(rest, lineno, raw))
     elif kwl.startswith("mac"):

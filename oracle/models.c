@@ -122,16 +122,23 @@ static double fb_clip(double x, double lo, double hi) {
   if (x > hi) { return hi; }
   return x;
 }
+static double fb_fill(double *a, double x0, double n) {
+  int j;
+  for (j = 0;j < n;j++) { a[j] = x0*(j + 1); }
+  return 0.0;
+}
 static void fb_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
                    double *aux, double *death, double *repli) {
   const double a = c->mu[0], b = c->mu[1], MBAR = mfd[0];
-  double w[3], X[3], m, wm; size_t i;
+  double w[3], c_[3], X[3], pw[3], m, wm; size_t i;
   (void)psi; (void)death; (void)repli;
-  for (i = 0; i < 3; ++i) { w[i] = e[i]; X[i] = y_[i]; }
+  for (i = 0; i < 3; ++i) { w[i] = e[i]; c_[i] = e[3 + i]; X[i] = y_[i]; }
   m = fb_mean(X);
   wm = fb_wmean(X, w);
-  for (i = 0; i < 3; ++i) f[i] = -a*(X[i] - fb_clip(MBAR, -b, b)) + sin(t + i);
+  fb_fill(pw, m, 3);                                     /* aux pw[i=0:NW] fill(pw, m, NW) {vect} */
+  for (i = 0; i < 3; ++i) f[i] = -a*(X[i] - fb_clip(MBAR, -b, b)) + sin(t + i) + 0.1*pw[i] - c_[i];
   aux[0] = m; aux[1] = wm;
+  for (i = 0; i < 3; ++i) aux[2 + i] = pw[i];
 }
 static double fb_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
   (void)c; (void)k; (void)y; (void)e; (void)mfd;
@@ -141,6 +148,7 @@ static void fb_ic(orc_ctx *c, double t, double *y, double *e) {
   size_t i;
   (void)t;
   for (i = 0; i < 3; ++i) e[i] = 0.5 + orc_rand01(c);
+  fb_fill(e + 3, 0.25, 3);                               /* expr c[i=0:NW] fill(c, 0.25, NW) {vect} */
   for (i = 0; i < 3; ++i) y[i] = 2*orc_rand01(c) - 1;
 }
 
@@ -371,7 +379,7 @@ static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e
 static const orc_model MODELS[] = {
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
-  {"fun_block", 3, 3, 2, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
+  {"fun_block", 3, 6, 5, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},

@@ -20,7 +20,7 @@ DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict
         "ring_diffusion": dict(nvar=2, naux=1, npsi=0, nmfd=1, nexpr=1),
         "vect_meanfield": dict(nvar=1, naux=1, npsi=0, nmfd=3, nexpr=0),
         "chain_array": dict(nvar=6, naux=6, npsi=0, nmfd=2, nexpr=4),
-        "fun_block": dict(nvar=3, naux=2, npsi=0, nmfd=1, nexpr=3),
+        "fun_block": dict(nvar=3, naux=5, npsi=0, nmfd=1, nexpr=6),
         "kuramoto_lrexp": dict(nvar=1, naux=1, npsi=1, nmfd=2, nexpr=1),
         "pair_aux": dict(nvar=2, naux=3, npsi=2, nmfd=1, nexpr=1),
         "nbody_const": dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0),

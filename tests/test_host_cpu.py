@@ -94,10 +94,11 @@ def test_const_arrays():
 def test_function_blocks_and_arrays():
     from odexp_b200 import popfile, cudagen
     m = popfile.parse_file(fixture_path("fun_block"))
-    assert [(f.name, f.block) for f in m.funs] == [("mean", False), ("wmean", True), ("clip", True)]
+    assert [(f.name, f.block) for f in m.funs] == [("mean", False), ("wmean", True), ("clip", True), ("fill", True)]
     cu = cudagen.emit_cuda(m)
     assert "ODX_HD double wmean(double *x, double *w) {" in cu and "for (j = 0; j < 3; j++)" in cu
     assert "for (size_t i = 0; i < 3; ++i) odx_f[0 + i - 0] = " in cu and "clip(MBAR, -b, b)" in cu          # called, not inlined
+    assert "double pw[3]; fill(pw, m, 3);" in cu and "double c[3]; fill(c, 0.25, 3);" in cu                 # {vect}: filled by a function
     c = popfile.parse_file(fixture_path("chain_array"))
     assert (c.nvar, c.naux, c.nexpr) == (6, 6, 4) and c.flat_names(c.eqs) == ["z", "X[0]", "X[1]", "X[2]", "X[3]", "u"]
     with pytest.raises(popfile.PopError):
