@@ -117,6 +117,23 @@ def test_emit_lowrank_variants():
         cudagen.emit_cuda(popfile.parse("expr U[i=0:2] 1\nexpr V[i=0:2] 1\n%C P lrwexp {var = nope, fun = sin, U = U, V = V, rank = 2}\ndx/dt = P\ninit x 0\n"))
 
 
+@pytest.mark.parametrize("name", ["kuramoto", "kuramoto_lowrank", "Nbody", "vanDerPol"])
+def test_shipped_examples_emit_as_shipped(name):
+    """every example the reference ships parses and emits unchanged (build container only: /root/reference does not travel)"""
+    import os
+    from odexp_b200 import popfile, cudagen
+    path = os.path.join(os.environ.get("ODX_REFERENCE", "/root/reference"), "examples", name + ".pop")
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not present")
+    m = popfile.parse_file(path)
+    cu = cudagen.emit_cuda(m)
+    assert "struct OdxModel" in cu and "NVAR = %d" % m.nvar in cu
+    if name == "Nbody":
+        assert len(m.consts) == 6 and "x_ic[(odx_c.id)]" in cu and m.macros == [("G", "6.674e-11")]      # comment on the macro line dropped
+    if name == "kuramoto_lowrank":
+        assert "LR0_VAR_KIND = 1" in cu and "LR0_RANK = 1" in cu                                          # var = theta is an AUX; U = U[0]
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     # OA() of an auxiliary that reads a mean field (directly or through another auxiliary) or a coupling: its value for the other
