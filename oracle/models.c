@@ -200,6 +200,36 @@ static void pa_ic(orc_ctx *c, double t, double *y, double *e) {
   y[1] = 0.0;
 }
 
+/* ---------------------------------------------------------------- lineage.pop: SE / SA / SY, exprand / poisson in expressions */
+static const double ln_pars[] = {0.8, 0.05, 0.6};
+static void ln_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double r = c->mu[0], b = c->mu[2], life = e[0], gen = e[2], x = y_[0];
+  const double size = x*(1 + 0.1*gen);
+  (void)t; (void)psi; (void)mfd;
+  f[0] = r*x*(1 - x) - 0.01*life*x;
+  aux[0] = size;
+  *death = c->mu[1];                                   /* %DEATH MU(d) */
+  *repli = b*(x > 0.5);
+}
+static double ln_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)aux; (void)mfd;
+  return k == 0 ? y[0] : e[2];                         /* %M XM MY(x); %M GM ME(gen) */
+}
+static double ln_birth(orc_ctx *c, const double *y, const double *e, const double *aux) { (void)c; (void)y; (void)e; (void)aux; return 0.3; }
+static void ln_ic(orc_ctx *c, double t, double *y, double *e) {
+  const orc_par *sis = c->sister;
+  double life, kids, gen, tag;
+  (void)t;
+  life = orc_exprand(c, 2.0);
+  kids = orc_poisson(c, 3.0);
+  gen = c->atbirth ? (0.0) : ((sis == NULL ? 0.0 : sis->expr[2]) + 1);                 /* BR(0.0, SE(gen) + 1) */
+  tag = (sis != NULL)*10 + kids;                                                       /* ISDAUGHTER*10 + kids */
+  e[0] = life; e[1] = kids; e[2] = gen; e[3] = tag;
+  y[0] = c->atbirth ? (0.1 + 0.05*kids)
+                    : (0.5*(sis == NULL ? 0.0 : sis->aux[0])/(1 + 0.1*gen) + 0.25*(sis == NULL ? 0.0 : sis->y[0]));
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -377,6 +407,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"lineage", 1, 4, 1, 0, 2, 3, ln_pars, ln_rhs, ln_mfd, ln_birth, NULL, ln_ic, 0, 0, 0, 0, 0, NULL},
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 6, 5, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},

@@ -213,3 +213,18 @@ def test_quick_buffer(model_lib, model, opts, ts, axes, particle):
     np.testing.assert_allclose(qa, qb, rtol=1e-10, atol=1e-12, equal_nan=True)
     if model == "vdp_sde":
         assert np.isnan(qb).any() and not np.isnan(qb).all()
+
+
+@pytest.mark.parametrize("meth,ssahmin,ps,seed", [("fe", 1.0, 20, 3141592), ("fe", 1.0, 2000, 17), ("fe", 0.0, 20, 5), ("rkck", 1.0, 50, 9)])
+def test_lineage_sister_macros(model_lib, meth, ssahmin, ps, seed):
+    """SE / SA / SY and ISDAUGHTER in the expressions and initial conditions of replicating particles (the mother is re-initialised
+    first with no sister, the daughter then reads the mother's NEW expressions and state and her OLD auxiliaries:
+    src/methods_odexp.c:1697-1717, src/odexp.h:296-326), exprand / poisson draws inside expressions; same keyed draws on both sides"""
+    opts = {"meth": meth, "h0": 0.01 if meth == "fe" else 0.1, "res": 31 if meth == "fe" else 13, "ps": ps, "ssahmin": ssahmin, "seed": seed}
+    out, ref = run_both(model_lib, "lineage", opts, (0, 6))
+    ev = ref["stats"]["event"]
+    assert ((ev[:, 1] == 1) & (ev[:, 0] >= 0)).sum() > 0, "case must contain replications"
+    gen = ref["traj"]["cols"][:, -2]
+    assert gen.max() >= 2, "case must contain second-generation daughters"
+    compare(out, ref)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=1e-11, atol=1e-13)

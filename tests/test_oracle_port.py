@@ -65,6 +65,10 @@ REF_CASES = [
     ("pair_aux", {"meth": "dde", "h0": 0.05, "res": 3, "ps": 30}, (0, 2)),
     ("pair_aux", {"meth": "rkf45", "h0": 0.05, "res": 3, "ps": 41}, (0, 2)),
     ("pair_aux", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 7}, (0, 0.5)),
+    # inheritance at replication (SE / SA / SY, ISDAUGHTER), exprand / poisson inside expressions; tau-leaping and SSA
+    ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 1.0}, (0, 6)),
+    ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 0.0}, (0, 6)),
+    ("lineage", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 50, "ssahmin": 1.0}, (0, 6)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
