@@ -51,7 +51,7 @@ def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False
         # fixture's own `opt` lines cannot make the two sides of a comparison run with different values
         full = dict(meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592)
         full.update(opts or {})
-        for k, v in full.items():
+        for k, v in (full.items() if opts else ()):          # opts = {} / None: the fixture exactly as written
             text += "\nOPT %s %s\n" % (k, v)
         text += "\nOPT pr 0\n"
         open(ppath, "w").write(text)

@@ -16,6 +16,7 @@ NBD = dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0)
 VDP = dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0)
 RING = dict(nvar=2, naux=1, npsi=0, nmfd=1, nexpr=1)
 
+FULL = dict(meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592)
 CASES = {
     # name: (fixture, opts, timespan, dims)
     "kuramoto_dde_n64": ("kuramoto", {"meth": "dde", "h0": 0.1, "res": 5, "ps": 64}, (0, 0.8), KUR),
@@ -32,6 +33,17 @@ CASES = {
     # KY() list neighbours: ring with nearest / next-nearest coupling; n = 3 wraps around more than once for degree 2
     "ring_dde_n50": ("ring_diffusion", {"meth": "dde", "h0": 0.05, "res": 11, "ps": 50}, (0, 2.0), RING),
     "ring_fe_n3": ("ring_diffusion", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 3}, (0, 0.2), RING),
+    # model-language coverage: every option spelled out
+    "chain_array_dde_n20": ("chain_array", dict(FULL, meth="dde", h0=0.05, res=4, ps=20), (0, 3), dict(nvar=6, naux=6, npsi=0, nmfd=2, nexpr=4)),
+    "fun_block_rkf45_n21": ("fun_block", dict(FULL, meth="rkf45", h0=0.05, res=4, ps=21), (0, 3), dict(nvar=3, naux=5, npsi=0, nmfd=1, nexpr=6)),
+    "pair_aux_dde_n30": ("pair_aux", dict(FULL, meth="dde", h0=0.05, res=3, ps=30), (0, 2), dict(nvar=2, naux=3, npsi=2, nmfd=1, nexpr=1)),
+    "nbody_const_rkf45": ("nbody_const", dict(FULL, meth="rkf45", h0=0.1, res=11, ps=3, abstol=1e-8, reltol=1e-8, hmin=0), (0, 20),
+                          dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0)),
+    "lowrank_aux_dde_n100": ("kuramoto_lowrank_aux", dict(FULL, meth="dde", h0=0.1, res=5, ps=100), (0, 2.0), dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=7)),
+    "lrexp_dde_n200": ("kuramoto_lrexp", dict(FULL, meth="dde", h0=0.1, res=3, ps=200), (0, 1.0), dict(nvar=1, naux=1, npsi=1, nmfd=2, nexpr=1)),
+    "vect_meanfield_tauleap": ("vect_meanfield", dict(FULL, meth="fe", h0=0.01, res=11, ps=40, ssahmin=1.0), (0, 2), dict(nvar=1, naux=1, npsi=0, nmfd=3, nexpr=0)),
+    "lineage_tauleap_n20": ("lineage", dict(FULL, meth="fe", h0=0.01, res=31, ps=20, ssahmin=1.0), (0, 6), dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=4)),
+    "lineage_ssa_n20": ("lineage", dict(FULL, meth="fe", h0=0.01, res=31, ps=20, ssahmin=0.0), (0, 6), dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=4)),
     "nbody_rkf45_n96": ("nbody", {"meth": "rkf45", "h0": 0.02, "res": 3, "ps": 96, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 0.2), NBD),
 }
 
@@ -50,7 +62,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"),
                             stats_t=st["t"], stats_mfd=st["mfd"], stats_n=st["n"], stats_flag=st["stop_flag"], stats_event=st["event"],
                             first_id=first["id"], first_cols=first["cols"], last_id=last["id"], last_cols=last["cols"], last_t=last["t"],
-                            nframes=np.array([tr["step"].max() + 1]),
+                            nframes=np.array([tr["step"].max() + 1]), quick=r.get("quick", np.zeros((0, 3))),
                             meta=np.array([repr(dict(fixture=fx, opts=opts, timespan=ts, dims=dims))]))
         print(name, "stats rows", len(st), "frames", tr["step"].max() + 1)
 

@@ -9,7 +9,9 @@ import pytest
 from conftest import load_golden
 
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
-                "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3"]
+                "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3",
+                "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "nbody_const_rkf45", "lowrank_aux_dde_n100",
+                "lrexp_dde_n200", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -27,6 +29,8 @@ def test_port_matches_golden(name):
     last = tr[tr["step"] == tr["step"].max()]
     np.testing.assert_array_equal(last["id"], g["last_id"])
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-13, atol=1e-15)
+    if "quick" in g.files and len(g["quick"]):                  # current.plot rows (default axes)
+        np.testing.assert_allclose(out["quick"], g["quick"], rtol=1e-13, atol=1e-15, equal_nan=True)
 
 
 REF_CASES = [
