@@ -236,3 +236,19 @@ def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
     np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :2], tb[tb["step"] == 0]["cols"][:, :2])
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,rtol,atol", [("chain_array_dde_n20", 1e-10, 1e-13), ("fun_block_rkf45_n21", 1e-10, 1e-12),
+                                            ("pair_aux_dde_n30", 1e-10, 1e-12), ("nbody_const_rkf45", 1e-8, 1e-10),
+                                            ("lowrank_aux_dde_n100", 1e-10, 1e-9), ("lrexp_dde_n200", 1e-10, 1e-9)])
+def test_model_language_fixtures_against_reference_outputs(model_lib, name, rtol, atol):
+    """the model-language fixtures of DESIGN 1.1 against what the UNCHANGED reference binary wrote for them (tests/golden): stats
+    rows, ids, bit-identical initial state, final frame, current.plot.  atol 1e-9 for the low-rank cases covers the psi column
+    (values ~ 1e2, expansion round-off, see test_gpu_lowrank.py); states are checked to rtol"""
+    g, out, meta = run_case(model_lib, name)
+    first, last = check(g, out, atol_mfd=1e-11)
+    d = meta["dims"]
+    np.testing.assert_array_equal(first["cols"][:, :d["nvar"]], g["first_cols"][:, :d["nvar"]])
+    np.testing.assert_allclose(last["cols"][:, :d["nvar"]], g["last_cols"][:, :d["nvar"]], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(out["quick"], g["quick"], rtol=rtol, atol=atol, equal_nan=True)
