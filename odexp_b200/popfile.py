@@ -267,7 +267,7 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.death = _split_attr(rest)[0]
     elif kwl.startswith("%repli"):
         m.repli = _split_attr(rest)[0]
-    elif kwl.startswith("dec") or kwl.startswith("const"):
+    elif (kwl.startswith("dec") and "/" not in kw) or kwl.startswith("const"):      # `decay/dt = ...` is an equation, not a declaration
         # `decl const double a[] = {..}` is printed verbatim at file scope by the reference (add_declarations, src/odexp:660-674);
         # `const a[] {..}` is the older spelling the shipped examples/Nbody.pop still uses (declare_constant_array, src/odexp:643-658).
         # Only constant scalars / arrays are taken: they become constexpr locals of every generated function.

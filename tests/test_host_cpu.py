@@ -89,6 +89,8 @@ def test_const_arrays():
     assert old.consts == [("double", "a", "[]", "{ 1, 2 }"), ("int", "k", "", "3")]
     with pytest.raises(popfile.PopError):
         popfile.parse("decl double buffer[10]\ndx/dt = 1\ninit x 0\n")        # only constants
+    eq = popfile.parse("decoli/dt = -ecoli\ninit ecoli 1\n")                    # a variable whose d/dt keyword starts with `dec`
+    assert [e.name for e in eq.eqs] == ["ecoli"] and not eq.consts
 
 
 def test_function_blocks_and_arrays():
