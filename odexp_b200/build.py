@@ -37,7 +37,7 @@ def build_model(pop_path=None, text=None, name=None, force=False, verbose=False,
             text = f.read()
     if name is None:
         name = os.path.splitext(os.path.basename(pop_path))[0]
-    model = popfile.parse(text, name=name)
+    model = popfile.parse(text, name=name, base_dir=os.path.dirname(os.path.abspath(pop_path)) if pop_path else ".")
     cu = cudagen.emit_cuda(model)
     os.makedirs(BUILD, exist_ok=True)
     so, cu_path, stamp = lib_path(name), os.path.join(BUILD, "model_%s.cu" % name), os.path.join(BUILD, "model_%s.stamp" % name)

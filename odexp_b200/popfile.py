@@ -64,6 +64,7 @@ class PopModel:
     options: Dict[str, str] = field(default_factory=dict)
     timespan: List[float] = field(default_factory=list)
     consts: List[Tuple[str, str, str, str]] = field(default_factory=list)      # (C type, name, "[..]" or "", initialiser)
+    base_dir: str = "."       # FILE tables are read relative to the model file
 
     # flattened dimensions (arrays count element-wise, as in the reference's nbr_expr etc.)
     @staticmethod
@@ -143,8 +144,9 @@ def _name_and_rhs(rest, lineno, raw):
     return Entry(lhs, rhs, attr)
 
 
-def parse(text: str, name: str = "model") -> PopModel:
+def parse(text: str, name: str = "model", base_dir: str = ".") -> PopModel:
     m = PopModel(name=name)
+    m.base_dir = base_dir
     # pass 1: join continuation lines, collect LET constants
     lines, cont = [], ""
     for raw in text.splitlines():
@@ -278,6 +280,30 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         if bool(mm.group(3)) != mm.group(4).strip().startswith("{"):
             raise PopError("line %d: a constant array needs a braced initialiser list, a constant scalar a single value" % lineno)
         m.consts.append((mm.group(1) or "double", mm.group(2), mm.group(3).replace(" ", ""), mm.group(4).strip()))
+    elif kwl.startswith("fi"):
+        # FILE name filename {nrow, ncol, sep, skip}: a constant table read at generation time (declare_array_from_file,
+        # src/odexp:581-641) -> `static const double name[rows][cols]`, here one more constexpr constant
+        import os
+        body, attr = _split_attr(rest)
+        f = body.split(None, 1)
+        if len(f) != 2:
+            raise PopError("line %d: FILE needs a name and a file name" % lineno)
+        fname = f[1].strip().strip('"')
+        def opt(key, default):
+            mo = re.search(r"\b%s\b\s*=\s*(\"(.*?)\"|\d+)" % key, attr, flags=re.I)
+            return default if not mo else (mo.group(2) if mo.group(2) is not None else int(mo.group(1)))
+        sep, skip = opt("sep", " "), opt("skip", 0)
+        path = fname if os.path.isabs(fname) else os.path.join(m.base_dir, fname)
+        try:
+            lines_ = open(path).read().splitlines()[skip:]
+        except OSError as ex:
+            raise PopError("line %d: FILE %s: %s" % (lineno, fname, ex))
+        rows = [ln.split(sep) for ln in lines_ if ln.split(sep) != ['']]
+        nrow, ncol = min(opt("nrow", len(rows)), len(rows)), min(opt("ncol", 10 ** 9), max(len(r) for r in rows) if rows else 0)
+        if nrow < 1 or ncol < 1:
+            raise PopError("line %d: FILE %s holds no data" % (lineno, fname))
+        init = "{" + ", ".join("{" + ",".join(x.strip() for x in r[:ncol]) + "}" for r in rows[:nrow]) + "}"
+        m.consts.append(("double", f[0], "[%d][%d]" % (nrow, ncol), init))
     elif kwl.startswith("cmd") or kwl.startswith("end"):
         return
     elif re.match(r"^d%s\s*\[" % IDENT, kw + " " + rest, flags=re.I) and re.match(r"^d(%s)\s*\[([^\]]*)\]\s*/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S):
@@ -325,4 +351,4 @@ def _validate(m):
 def parse_file(path: str) -> PopModel:
     import os
     with open(path, encoding="utf8") as f:
-        return parse(f.read(), name=os.path.splitext(os.path.basename(path))[0])
+        return parse(f.read(), name=os.path.splitext(os.path.basename(path))[0], base_dir=os.path.dirname(os.path.abspath(path)))

@@ -79,6 +79,9 @@ def build(force=False, verbose=False):
         os.makedirs(d)
         local = os.path.join(d, os.path.basename(pop))
         shutil.copy(pop, local)
+        for extra in os.listdir(os.path.dirname(pop)):           # data files a fixture reads at generation time (FILE keyword)
+            if extra.startswith(name + ".") and not extra.endswith(".pop"):
+                shutil.copy(os.path.join(os.path.dirname(pop), extra), os.path.join(d, extra))
         # reference generator: -d generate only, -q quiet (appends `OPT loudness quiet`)
         run(["perl", os.path.join(REF, "src", "odexp"), "-d", "-q", os.path.basename(pop)], cwd=d)
         # link order: model + whole archive objects first so rand()/srand() from rand_hook.o win over libc

@@ -230,6 +230,31 @@ static void ln_ic(orc_ctx *c, double t, double *y, double *e) {
                     : (0.5*(sis == NULL ? 0.0 : sis->aux[0])/(1 + 0.1*gen) + 0.25*(sis == NULL ? 0.0 : sis->y[0]));
 }
 
+/* ---------------------------------------------------------------- table_drive.pop: FILE table indexed by ID */
+static const double td_pars[] = {0.7};
+static const double td_tab[4][3] = {
+    {0.0,1.0,0.1},
+    {0.5,0.8,0.2},
+    {1.0,0.6,0.3},
+    {1.5,0.4,0.4}};                                      /* table_drive.csv { nrow = 4, ncol = 3, sep = ",", skip = 1 } */
+static void td_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double k = c->mu[0], x = y_[0], XM = mfd[0]; const int ID = c->id;
+  const double amp = td_tab[ID % 4][1];
+  (void)e; (void)psi; (void)death; (void)repli;
+  f[0] = -k*(x - td_tab[ID % 4][2]) + amp*sin(t + td_tab[ID % 4][0]) - 0.1*XM;
+  aux[0] = amp;
+}
+static double td_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void td_ic(orc_ctx *c, double t, double *y, double *e) {
+  const int ID = c->id;
+  (void)t; (void)e;
+  y[0] = td_tab[ID % 4][2] + 0.1*orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -407,6 +432,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"table_drive", 1, 0, 1, 0, 1, 1, td_pars, td_rhs, td_mfd, NULL, NULL, td_ic, 0, 0, 0, 0, 0, NULL},
   {"lineage", 1, 4, 1, 0, 2, 3, ln_pars, ln_rhs, ln_mfd, ln_birth, NULL, ln_ic, 0, 0, 0, 0, 0, NULL},
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},

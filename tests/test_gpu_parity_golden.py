@@ -252,3 +252,22 @@ def test_model_language_fixtures_against_reference_outputs(model_lib, name, rtol
     np.testing.assert_allclose(last["cols"][:, :d["nvar"]], g["last_cols"][:, :d["nvar"]], rtol=rtol, atol=1e-12)
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=rtol, atol=atol)
     np.testing.assert_allclose(out["quick"], g["quick"], rtol=rtol, atol=atol, equal_nan=True)
+
+
+@pytest.mark.parametrize("meth,n", [("dde", 10), ("rkf45", 23), ("fe", 3000)])
+def test_file_table(model_lib, meth, n):
+    """`FILE tab table_drive.csv {nrow, ncol, sep, skip}` (declare_array_from_file, src/odexp:581-641): the table becomes a constexpr
+    constant of the generated functions, indexed by the particle ID in AUX, D/DT and the initial conditions"""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": 0.05, "res": 4, "ps": n}
+    pop = capi.Population(model_lib("table_drive"), capacity=max(1024, n))
+    out = capi.odesolver(pop, (0, 3), meth=meth, res=4, popsize=n, h0=0.05, replay_ic=True)
+    pop.close()
+    ref = port.run("table_drive", opts, (0, 3))
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, 0], tb[tb["step"] == 0]["cols"][:, 0])
+    np.testing.assert_array_equal(ta["cols"][:, 1], tb["cols"][:, 1])                  # aux amp = tab[ID % 4][1]
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

@@ -89,6 +89,11 @@ def test_const_arrays():
     assert old.consts == [("double", "a", "[]", "{ 1, 2 }"), ("int", "k", "", "3")]
     with pytest.raises(popfile.PopError):
         popfile.parse("decl double buffer[10]\ndx/dt = 1\ninit x 0\n")        # only constants
+    tab = popfile.parse_file(fixture_path("table_drive"))           # FILE table: 4 rows x 3 columns after one skipped line
+    assert tab.consts == [("double", "tab", "[4][3]", "{{0.0,1.0,0.1}, {0.5,0.8,0.2}, {1.0,0.6,0.3}, {1.5,0.4,0.4}}")]
+    assert "constexpr double tab[4][3] = " in cudagen.emit_cuda(tab)
+    with pytest.raises(popfile.PopError):
+        popfile.parse("file tab no_such_file.csv\ndx/dt = 1\ninit x 0\n")
     eq = popfile.parse("decoli/dt = -ecoli\ninit ecoli 1\n")                    # a variable whose d/dt keyword starts with `dec`
     assert [e.name for e in eq.eqs] == ["ecoli"] and not eq.consts
 

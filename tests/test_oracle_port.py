@@ -73,6 +73,9 @@ REF_CASES = [
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 1.0}, (0, 6)),
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 0.0}, (0, 6)),
     ("lineage", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 50, "ssahmin": 1.0}, (0, 6)),
+    # FILE table (read from a text file at generation time) indexed by ID
+    ("table_drive", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 10}, (0, 3)),
+    ("table_drive", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 23}, (0, 3)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
