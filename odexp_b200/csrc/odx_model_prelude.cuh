@@ -180,4 +180,9 @@ ODX_HD double prod(const double *array, long len) { double s = 1.0; for (long i 
 ODX_HD double dotprod(const double *x, const double *y, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += x[i] * y[i]; return s; }
 ODX_HD double minus(double x, double y) { return x - y; }
 ODX_HD double plus(double x, double y) { return x + y; }
+/* one link of a linear chain delay (src/utils_odexp.c:162-167); LAG lines expand into an array of these */
+ODX_HD double linchaindelay(const double root, const double *chain, const int link, const double delay, const int len) {
+  const double beta = (double)len / delay;
+  return beta * ((link == 0 ? root : chain[link - 1]) - chain[link]);
+}
 ODX_HD double identity(double x) { return x; }

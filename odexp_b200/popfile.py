@@ -158,6 +158,22 @@ def parse(text: str, name: str = "model", base_dir: str = ".") -> PopModel:
         cont = ""
     if cont:
         lines.append(cont)
+    # LAG name {root, len, mean, init}: rewritten in place into a chain of hidden dynamical variables, the auxiliary variable at
+    # the end of the chain and their initial conditions, exactly like the reference's preprocessor (src/odexp:383-391)
+    expanded = []
+    for s in lines:
+        ml = re.match(r"^\s*lag\w*\s+(%s)\s*\{(.*?)\}" % IDENT, _strip_comment(s), flags=re.I)
+        if not ml:
+            expanded.append(s)
+            continue
+        v, attr = ml.group(1), ml.group(2)
+        get = lambda key: (re.search(r"\b%s\s*=\s*(.*?)([,\s]|$)" % key, attr) or [None, None])[1]
+        root, ic, ln, mean = get("root"), get("init"), get("len"), get("mean")
+        if None in (root, ic, ln, mean):
+            raise PopError("LAG %s needs root, len, mean and init attributes" % v)
+        expanded += ["d%s_chain[i=0:%s]/dt = linchaindelay(%s,%s_chain,i,%s,%s) {hidden}" % (v, ln, root, v, mean, ln),
+                     "macro %s_end %s-1" % (v, ln), "AUX %s %s_chain[%s_end]" % (v, v, v), "INIT %s_chain[i=0:%s] %s {hidden}" % (v, ln, ic)]
+    lines = expanded
     # multi-line functions: `FUN name(args)` without `=`, statements, `end` -> one line `fun name(args) = {block} statements`
     joined, block = [], None
     for s in lines:

@@ -255,6 +255,33 @@ static void td_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = td_tab[ID % 4][2] + 0.1*orc_rand01(c);
 }
 
+/* ---------------------------------------------------------------- lag_chain.pop (LET L 5): LAG -> linear chain of hidden variables */
+static const double lg_pars[] = {2.0, 1.0};
+static double lg_linchaindelay(const double root, const double *chain, const int link, const double delay, const int len) {
+  double beta = (double)len/delay;                       /* src/utils_odexp.c:162-167 */
+  return beta*((link==0 ? root : chain[link-1]) - chain[link]);
+}
+static void lg_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double tau = c->mu[0], k = c->mu[1], *xd_chain = y_, x = y_[5], XM = mfd[0];
+  const double xd = xd_chain[5-1];
+  size_t i;
+  (void)t; (void)e; (void)psi; (void)death; (void)repli;
+  for (i = 0; i < 5; ++i) f[i] = lg_linchaindelay(x,xd_chain,i,tau,5);
+  f[5] = k*(1 - xd) - 0.2*x*XM;
+  aux[0] = xd;
+}
+static double lg_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[5];
+}
+static void lg_ic(orc_ctx *c, double t, double *y, double *e) {
+  size_t i;
+  (void)t; (void)e;
+  for (i = 0; i < 5; ++i) y[i] = 0.5;
+  y[5] = orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- vdp_sde.pop */
 static const double vdp_pars[] = {1.0, 0.1, 0.01, 0.02};
 static void vdp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -432,6 +459,7 @@ static double vm_birth(orc_ctx *c, const double *y, const double *e, const doubl
 static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e; y[0] = orc_rand01(c); }
 
 static const orc_model MODELS[] = {
+  {"lag_chain", 6, 0, 1, 0, 1, 2, lg_pars, lg_rhs, lg_mfd, NULL, NULL, lg_ic, 0, 0, 0, 0, 0, NULL},
   {"table_drive", 1, 0, 1, 0, 1, 1, td_pars, td_rhs, td_mfd, NULL, NULL, td_ic, 0, 0, 0, 0, 0, NULL},
   {"lineage", 1, 4, 1, 0, 2, 3, ln_pars, ln_rhs, ln_mfd, ln_birth, NULL, ln_ic, 0, 0, 0, 0, 0, NULL},
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},

@@ -271,3 +271,22 @@ def test_file_table(model_lib, meth, n):
     np.testing.assert_array_equal(ta["cols"][:, 1], tb["cols"][:, 1])                  # aux amp = tab[ID % 4][1]
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("meth,n", [("dde", 12), ("rkck", 31), ("fe", 2500)])
+def test_lag_linear_chain(model_lib, meth, n):
+    """`LAG xd {root = x, len = L, mean = tau, init = 0.5}` (src/odexp:383-391): rewritten into an array of hidden dynamical
+    variables driven by linchaindelay() (src/utils_odexp.c:162-167), the auxiliary variable at the end of the chain and their
+    initial conditions; restatement bit-identical to the reference binary"""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": 0.05, "res": 5, "ps": n}
+    pop = capi.Population(model_lib("lag_chain"), capacity=max(1024, n))
+    out = capi.odesolver(pop, (0, 4), meth=meth, res=5, popsize=n, h0=0.05, replay_ic=True)
+    pop.close()
+    ref = port.run("lag_chain", opts, (0, 4))
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :6], tb[tb["step"] == 0]["cols"][:, :6])
+    np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

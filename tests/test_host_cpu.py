@@ -94,6 +94,9 @@ def test_const_arrays():
     assert "constexpr double tab[4][3] = " in cudagen.emit_cuda(tab)
     with pytest.raises(popfile.PopError):
         popfile.parse("file tab no_such_file.csv\ndx/dt = 1\ninit x 0\n")
+    lag = popfile.parse_file(fixture_path("lag_chain"))              # LAG -> chain of hidden variables + aux + inits, in place
+    assert lag.flat_names(lag.eqs) == ["xd_chain[%d]" % i for i in range(5)] + ["x"] and [a.name for a in lag.auxs] == ["xd"]
+    assert ("xd_end", "5-1") in lag.macros and "linchaindelay(x,xd_chain,i,tau,5)" in cudagen.emit_cuda(lag)
     eq = popfile.parse("decoli/dt = -ecoli\ninit ecoli 1\n")                    # a variable whose d/dt keyword starts with `dec`
     assert [e.name for e in eq.eqs] == ["ecoli"] and not eq.consts
 

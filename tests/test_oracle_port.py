@@ -76,6 +76,9 @@ REF_CASES = [
     # FILE table (read from a text file at generation time) indexed by ID
     ("table_drive", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 10}, (0, 3)),
     ("table_drive", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 23}, (0, 3)),
+    # LAG: distributed delay as a linear chain of hidden dynamical variables (linchaindelay)
+    ("lag_chain", {"meth": "dde", "h0": 0.05, "res": 5, "ps": 12}, (0, 4)),
+    ("lag_chain", {"meth": "rkck", "h0": 0.05, "res": 5, "ps": 31}, (0, 4)),
     # discrete maps: meth iteration (y <- f(y) with the reference's aliasing of input and output)
     ("logistic_map", {"meth": "iteration", "ps": 50}, (0, 20)),
     # stopping times inside TIMESPAN, STOPIF and IST0: interval cut short, population re-initialised (methods_odexp.c:704-720)
