@@ -186,3 +186,18 @@ ODX_HD double linchaindelay(const double root, const double *chain, const int li
   return beta * ((link == 0 ? root : chain[link - 1]) - chain[link]);
 }
 ODX_HD double identity(double x) { return x; }
+/* sum over all but one dimension of a 3-index array, as coded (src/utils_odexp.c:38-60: offsets i + d2*j + d3*k) */
+ODX_HD double sum3(const double *array, long d1, long d2, long d3, long dim) {
+  double s = 0.0; long n[3] = {d1, d2, d3};
+  n[dim - 1] = 1;
+  for (long i = 0; i < n[0]; i++) for (long j = 0; j < n[1]; j++) for (long k = 0; k < n[2]; k++) s += array[i + d2 * j + d3 * k];
+  return s;
+}
+ODX_HD double conv(const double *u, const double *v, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += u[len - 1 - i] * v[i]; return s; }
+/* sumxy / kern take model functions as arguments (src/utils_odexp.c:122-152): templates, so that the calls inline on the device */
+template <class F, class G> ODX_HD double sumxy(long len, F f, G g, const double *x, const double yi) {
+  double s = 0.0; for (long j = 0; j < len; j++) s += f(g(x[j], yi)); return s;
+}
+template <class F> ODX_HD double kern(const double *Wi, F f, double xi, const double *x, double *p, long len) {
+  double s = 0.0; for (long j = 0; j < len; j++) s += Wi[j] * f(xi, x[j], p); return s;
+}
