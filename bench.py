@@ -196,17 +196,23 @@ def main():
     # over an UNTIMED continuation of the same workload (same kernel, same population) so that the clocks of every GPU under
     # this load are on record: in a strong-scaling run one power-capped GPU sets the pace of all.
     t_samples = len(sampler.rows) if rank == 0 else 0
+    if world > 1:                                 # device time of the timed region: MAX over ranks
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    # every rank MUST run the same number of steps (the step kernel exchanges the mean-field sums with its peers every stage: a
+    # rank with one step more would wait for ever), so the count is derived from the reduced time and then taken from rank 0
     extra = max(0, min(4000, int(400.0 / max(ms / args.steps, 1e-3))))          # ~0.4 s
+    if world > 1:
+        tex = torch.tensor([extra], device="cuda", dtype=torch.int64)
+        dist.broadcast(tex, src=0)
+        extra = int(tex.item())
     t = pop.run_fixed("dde", t, H_STEP, extra)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["samples_in_timed_region"] = t_samples
         clocks["note"] = "sampling continued over %d untimed steps of the same workload after the timed region" % extra
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
     mfd = pop.meanfields()
     value = n_total * args.steps / (ms * 1e-3)
 
