@@ -291,6 +291,20 @@ __global__ void __launch_bounds__(BLOCK) k_moments(Pop p, const double *__restri
   grid_reduce<NRED>(red, r);
 }
 
+/* Bounded wait of the in-kernel exchanges: a peer (CTA or GPU) that never arrives must not hang the box.  Returns true when the
+ * wait is to be abandoned: after SPIN_LIMIT polls (tens of seconds; a legitimate wait lasts micro- to milliseconds), or as soon
+ * as any earlier wait on this GPU has given up -- so that after the first time-out the remaining stages drain in ~1024 polls each
+ * and the host reports the error (odx_sync) instead of waiting SPIN_LIMIT polls per stage. */
+constexpr unsigned long long SPIN_LIMIT = 1ull << 25;
+__device__ __forceinline__ bool spin_give_up(unsigned long long &spins, int *abort_flag) {
+  if ((++spins & 1023ull) != 0) return false;
+  if (spins > SPIN_LIMIT || (abort_flag != nullptr && *(volatile int *)abort_flag != 0)) {
+    if (abort_flag != nullptr) *abort_flag = 1;
+    return true;
+  }
+  return false;
+}
+
 struct ChainArgs {
   const double *sums_in;    /* raw %M sums of the state the RHS is evaluated at */
   double t_eval;            /* time of that state */
@@ -1021,7 +1035,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
       if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
       for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
         unsigned long long w; unsigned long long spins = 0;
-        while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (++spins > (1ull << 28)) { if (g.abort_flag) *g.abort_flag = 1; break; } }
+        while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
         s_words[idx] = (uint32_t)w;
       }
       cta_sync<NTC>();
@@ -1051,7 +1065,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
           if (r != g.rank) {
             unsigned long long w; unsigned long long spins = 0;
             while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + k)) >> 32) != tag) {
-              if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; }
+              if (spin_give_up(spins, g.abort_flag)) break;
             }
             s_words[threadIdx.x] = (uint32_t)w;
           }
@@ -1078,7 +1092,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
             if (r != g.rank) {
               unsigned long long w; unsigned long long spins = 0;
               while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + k)) >> 32) != tag) {
-                if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; }
+                if (spin_give_up(spins, g.abort_flag)) break;
               }
               s_words[threadIdx.x] = (uint32_t)w;
             }
@@ -1096,7 +1110,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         } else {
           if (threadIdx.x < LLW) {
             unsigned long long w; unsigned long long spins = 0;
-            while ((uint32_t)((w = ll_load_gpu(gt + threadIdx.x)) >> 32) != tag) { if (++spins > (1ull << 28)) { *g.abort_flag = 1; break; } }
+            while ((uint32_t)((w = ll_load_gpu(gt + threadIdx.x)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
             s_words[threadIdx.x] = (uint32_t)w;
           }
           cta_sync<NTC>();
