@@ -204,9 +204,8 @@ def main():
     # rank with one step more would wait for ever), so the count is derived from the reduced time and then taken from rank 0
     extra = max(0, min(4000, int(400.0 / max(ms / args.steps, 1e-3))))          # ~0.4 s
     if world > 1:
-        tex = torch.tensor([extra], device="cuda", dtype=torch.int64)
-        dist.broadcast(tex, src=0)
-        extra = int(tex.item())
+        from odexp_b200 import dist as odist
+        extra = int(odist.agreed(extra, src=0))
     t = pop.run_fixed("dde", t, H_STEP, extra)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -29,6 +29,17 @@ def all_gather_bytes(payload):
     return out
 
 
+def agreed(value, src=0):
+    """the value rank `src` holds, on every rank.  Loop counts handed to the stepping calls (odx_run_fixed, ...) MUST go through
+    this when they derive from anything rank-local (timings, sample counts): the step kernels exchange the mean-field sums with
+    their peers at every stage, and a rank that runs one step more than the others waits for words that never arrive."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    box = [value if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def connect(pop, use_nccl=True, use_peers=True):
     """wire a Population into the process group: NCCL communicator + NVLink peer mailboxes"""
     rank, world = dist.get_rank(), dist.get_world_size()

@@ -22,7 +22,9 @@ def _worker(rank, world, port, q):
         def peer_detach(self): self.peers = None
     fp = FakePop()
     odist.connect(fp)
-    q.put((rank, uid, handles, lo, hi, fp.comm, fp.peers))
+    # a loop count derived from rank-local timings (bench.py's untimed continuation): every rank must end up with rank 0's
+    steps = odist.agreed(2094 - rank, src=0)
+    q.put((rank, uid, handles, lo, hi, fp.comm, fp.peers, steps))
     dist.destroy_process_group()
 
 
@@ -37,6 +39,8 @@ def test_two_rank_plumbing():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert [r[7] for r in res] == [2094, 2094]
+    res = [r[:7] for r in res]
     for rank, uid, handles, lo, hi, comm, peers in res:
         assert uid == bytes(range(128))
         assert handles == [bytes([0]) * 64, bytes([1]) * 64]
