@@ -331,6 +331,9 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
             raise PopError("line %d: unsupported index expression in '%s'" % (lineno, raw.strip()))
         a, b = int(ma.group(3)), int(ma.group(4))
         m.eqs.append(Entry(mm.group(1), rhs.strip(), attr, length=b - a, iterator=ma.group(2), start=a))
+        mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)               # {init = value}: `INIT name[i=a:b] value` (src/odexp:377-382)
+        if mi:
+            m.inits.append(Entry(mm.group(1), mi.group(1).strip(), "", length=b - a, iterator=ma.group(2), start=a))
     elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):
         var = re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I).group(1)
         rhs, attr = _split_attr(rest)

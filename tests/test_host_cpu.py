@@ -97,6 +97,9 @@ def test_const_arrays():
     lag = popfile.parse_file(fixture_path("lag_chain"))              # LAG -> chain of hidden variables + aux + inits, in place
     assert lag.flat_names(lag.eqs) == ["xd_chain[%d]" % i for i in range(5)] + ["x"] and [a.name for a in lag.auxs] == ["xd"]
     assert ("xd_end", "5-1") in lag.macros and "linchaindelay(x,xd_chain,i,tau,5)" in cudagen.emit_cuda(lag)
+    arr = popfile.parse("let NN 3\ndX[i=0:NN]/dt = -X[i] {init = 0.5*(i+1)}\n")      # {init = ...} on an array equation
+    assert arr.nvar == 3 and arr.inits[0].rhs == "0.5*(i+1)" and arr.inits[0].length == 3
+    assert "odx_y[0 + i - 0] = 0.5*(i+1);" in cudagen.emit_cuda(arr)
     eq = popfile.parse("decoli/dt = -ecoli\ninit ecoli 1\n")                    # a variable whose d/dt keyword starts with `dec`
     assert [e.name for e in eq.eqs] == ["ecoli"] and not eq.consts
 
