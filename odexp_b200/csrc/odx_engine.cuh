@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK) k_moments(Pop p, const double *__restri
  * wait is to be abandoned: after SPIN_LIMIT polls (tens of seconds; a legitimate wait lasts micro- to milliseconds), or as soon
  * as any earlier wait on this GPU has given up -- so that after the first time-out the remaining stages drain in ~1024 polls each
  * and the host reports the error (odx_sync) instead of waiting SPIN_LIMIT polls per stage. */
-constexpr unsigned long long SPIN_LIMIT = 1ull << 25;
+constexpr unsigned long long SPIN_LIMIT = 1ull << 26;      /* ~ 20 - 45 s of polling; a rank may legitimately be late by seconds (host-side output of a large frame) */
 __device__ __forceinline__ bool spin_give_up(unsigned long long &spins, int *abort_flag) {
   if ((++spins & 1023ull) != 0) return false;
   if (spins > SPIN_LIMIT || (abort_flag != nullptr && *(volatile int *)abort_flag != 0)) {
