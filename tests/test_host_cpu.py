@@ -147,6 +147,24 @@ def test_shipped_examples_emit_as_shipped(name):
         assert "LR0_VAR_KIND = 1" in cu and "LR0_RANK = 1" in cu                                          # var = theta is an AUX; U = U[0]
 
 
+def test_every_fixture_emits_and_is_registered():
+    """every .pop under oracle/fixtures parses, emits, has a restatement in oracle/models.c (port.DIMS agrees with the parser's
+    dimensions) and is built by __graft_entry__.build()"""
+    import glob, os
+    from odexp_b200 import popfile, cudagen
+    from oracle import port
+    import __graft_entry__ as ge
+    from conftest import FIXTURES
+    names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(FIXTURES, "*.pop")))
+    assert len(names) >= 18
+    for n in names:
+        m = popfile.parse_file(fixture_path(n))
+        assert "struct OdxModel" in cudagen.emit_cuda(m)
+        assert n in port.DIMS, "no oracle dimensions for fixture %s" % n
+        assert port.DIMS[n] == dict(nvar=m.nvar, naux=m.naux, npsi=m.npsi, nmfd=m.nmfd, nexpr=m.nexpr), n
+        assert n in ge.MODELS, "fixture %s is not built by __graft_entry__.build()" % n
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     # OA() of an auxiliary that reads a mean field (directly or through another auxiliary) or a coupling: its value for the other
