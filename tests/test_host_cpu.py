@@ -165,6 +165,22 @@ def test_every_fixture_emits_and_is_registered():
         assert n in ge.MODELS, "fixture %s is not built by __graft_entry__.build()" % n
 
 
+def test_ctypes_mirror_matches_the_c_structs(tmp_path):
+    """the ctypes mirror of the C-ABI structs (odexp_b200/capi.py) has the layout gcc gives include/odx.h"""
+    import ctypes as C, subprocess
+    from conftest import ROOT
+    from odexp_b200 import capi
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "odx.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(odx_solver_opts), offsetof(odx_solver_opts, outdir), offsetof(odx_solver_opts, mu), offsetof(odx_solver_opts, quick), '
+                   'offsetof(odx_solver_opts, particle), sizeof(odx_solver_report), offsetof(odx_solver_report, final_n)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout.split()]
+    O, R = capi.SolverOpts, capi.SolverReport
+    assert got == [C.sizeof(O), O.outdir.offset, O.mu.offset, O.quick.offset, O.particle.offset, C.sizeof(R), R.final_n.offset]
+
+
 def test_emit_rejects_unsupported():
     from odexp_b200 import popfile, cudagen
     # OA() of an auxiliary that reads a mean field (directly or through another auxiliary) or a coupling: its value for the other
