@@ -160,7 +160,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop"))
+    lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto.pop"))
     n_total = args.n
     from odexp_b200.dist import shard_range
     lo, hi = shard_range(n_total, rank, world)
@@ -258,7 +258,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "Kuramoto mean-field (oracle/fixtures/kuramoto.pop), N=%d oscillators, classic RK4 (meth dde) h=%g, FP64" % (n_total, H_STEP),
+                "config": {"workload": "Kuramoto mean-field (models/kuramoto.pop), N=%d oscillators, classic RK4 (meth dde) h=%g, FP64" % (n_total, H_STEP),
                            "n_particles": n_total, "per_gpu_particles": n_local, "l2": ("state larger than L2 (%.0f MB per GPU vs 126 MB): every stage streams it from HBM" % (n_local * 32 / 1e6)) if n_local * 32 > 126e6
                                  else ("state fits in L2 (%.0f MB per GPU): consecutive steps of one simulation reuse the resident population by construction, "
                                        "no flush between steps (a flush would not be part of the workload)" % (n_local * 32 / 1e6)),

@@ -46,9 +46,9 @@ def build_model(pop_path=None, text=None, name=None, force=False, verbose=False,
         return so
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        if os.path.exists(so):
-            return so           # prebuilt library shipped with the tree (GPU box without a changed source)
-        raise RuntimeError("nvcc not found and no prebuilt %s" % so)
+        # a prebuilt library is only trusted when its stamp matches the current .pop, csrc and flags (checked above): a stale one
+        # would have other dimensions / another ABI than the parse the caller holds
+        raise RuntimeError("nvcc not found and the prebuilt %s is missing or stale (stamp != digest of the current sources)" % so)
     with open(cu_path, "w") as f:
         f.write(cu)
     host_o = os.path.join(BUILD, "odx_host_%s.o" % name)

@@ -62,11 +62,27 @@ struct PhiloxStream {
     return mu + sigma * (sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2));
   }
   ODX_HD double exprand(double r) { const double u = rand01(); return log(1.0 / (1.0 - u)) / r; }
-  /* Knuth's product method, as the reference composes it (src/rand_gen.c:37-46) */
+  /* lambda < 30: Knuth's product method, as the reference composes it (src/rand_gen.c:37-46).  Above that the reference's form
+   * is O(lambda) serial work and, from lambda ~ 745 on, silently wrong (exp(-lambda) underflows to 0 and the loop only ends when
+   * the product itself underflows: the count saturates near 745).  The keyed stream has no bit-parity constraint with libc rand(),
+   * so large means use Hoermann's transformed rejection (PTRS, 1993): exact in distribution, ~1.1 iterations of two uniforms. */
   ODX_HD long poisson(double lambda) {
-    long k = 0; const double L = exp(-lambda); double p = 1.0;
-    do { ++k; p *= rand01(); } while (p > L);
-    return k - 1;
+    if (!(lambda >= 30.0)) {
+      long k = 0; const double L = exp(-lambda); double p = 1.0;
+      do { ++k; p *= rand01(); } while (p > L);
+      return k - 1;
+    }
+    const double slam = sqrt(lambda), loglam = log(lambda);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+      const double U = rand01() - 0.5, V = rand01();
+      const double us = 0.5 - fabs(U);
+      const double kf = floor((2.0 * a / us + b) * U + lambda + 0.43);
+      if (us >= 0.07 && V <= vr) return (long)kf;
+      if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+      if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lambda + kf * loglam - lgamma(kf + 1.0)) return (long)kf;
+    }
   }
 };
 

@@ -1140,8 +1140,12 @@ int odx_stop_flag(odx_handle *h, int *raised) {
   int *flag = reinterpret_cast<int *>(h->counter + 8);
   int *pin = reinterpret_cast<int *>(h->h_pin + NSLOT * NRED + 8);
   if (h->nranks > 1) {
+#ifdef ODX_HAVE_NCCL_H
     ncclResult_t r = g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMax, h->comm, h->stream);
     if (r != ncclSuccess) { h->err = std::string("ncclAllReduce(MAX): ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
+#else
+    h->err = "built without nccl.h"; return ODX_ENCCL;
+#endif
   }
   ODX_CUDA(h, cudaMemcpyAsync(pin, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ODX_CUDA(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));

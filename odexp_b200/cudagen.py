@@ -391,7 +391,7 @@ class Emitter:
             raise PopError("delay()/interp() history stacks are host-only (%s)" % where)
         e = re.sub(r"\bDWDT\b", "odx_c.dwdt()", e)
         e = re.sub(r"\b(rand01|randN|exprand|poisson)\s*\(", lambda mm: "odx_c.%s(" % mm.group(1), e)
-        e = re.sub(r"\bPOP_SIZE\b", "odx_c.pop_size", e)
+        e = re.sub(r"\bPOP_SIZE\b", "((int)odx_c.pop_size)", e)      # SIM->pop->size is an int in the reference (src/odexp.h): 1/POP_SIZE is 0
         e = re.sub(r"\bATBIRTH\b", "(odx_c.atbirth)", e)
         e = re.sub(r"\bATREPLI\b", "(odx_c.atrepli)", e)
         e = re.sub(r"\bISDAUGHTER\b", "(odx_c.has_sister)", e)

@@ -6,8 +6,9 @@ case-insensitively by prefix (PAR, EXPR, AUX, D<var>/DT, INIT, LET, MACRO, TIMES
 %BIRTH, %DEATH, %REPLI), `#` starts a comment, `{...}` carries attributes, LET constants are substituted
 textually, `;` separates several PAR / OPT entries on one line, a bare `name value` line is a parameter.
 
-Only what the population path needs is accepted; constructs outside it (CONST/DECL arrays, FILE, LAG,
-multi-line FUN bodies with control flow, multi-dimensional iterators) raise PopError with the line.
+Accepted beyond the basic keywords: `decl const` / `const` arrays, FILE tables, LAG chains, one-dimensional array
+entries `name[i=a:b]`, multi-line `FUN ... end` blocks.  Constructs outside the population path (iterators with more
+than one index, `decl` of anything but constants, the TIMESPAN array mini-language) raise PopError with the line.
 """
 import re
 from dataclasses import dataclass, field

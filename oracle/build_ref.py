@@ -39,7 +39,7 @@ def available():
 
 def fixtures():
     fx = {}
-    d = os.path.join(HERE, "fixtures")
+    d = os.path.join(os.path.dirname(HERE), "models")
     for f in sorted(os.listdir(d)):
         if f.endswith(".pop"):
             fx[f[:-4]] = os.path.join(d, f)

@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE — the fixture models of oracle/fixtures/ (.pop files) written out by hand as plain C, the way the
+/* TEST INFRASTRUCTURE — the fixture models of models/ (.pop files) written out by hand as plain C, the way the
  * reference's generator lays out ode_rhs / %M / %C / ode_init_conditions (src/odexp:981-1069, 874-954; a concrete
  * instance is quoted in SURVEY.md Appendix B).  Hand-written on purpose: the oracle must not share the product's
  * code generator. */

@@ -97,6 +97,19 @@ double orc_randN(orc_ctx *c, double mu, double sigma) {
 double orc_exprand(orc_ctx *c, double r) { double mu = orc_rand01(c); return log(1 / (1 - mu)) / r; }
 long orc_poisson(orc_ctx *c, double lambda) {
   long k = 0; double L = exp(-lambda), p = 1;
+  if (c->sim->rng_mode != 0 && lambda >= 30.0) {      /* keyed convention of odx_rng.h: Hoermann's PTRS for large means */
+    const double slam = sqrt(lambda), loglam = log(lambda);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+      const double U = orc_rand01(c) - 0.5, V = orc_rand01(c);
+      const double us = 0.5 - fabs(U);
+      const double kf = floor((2.0 * a / us + b) * U + lambda + 0.43);
+      if (us >= 0.07 && V <= vr) return (long)kf;
+      if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+      if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lambda + kf * loglam - lgamma(kf + 1.0)) return (long)kf;
+    }
+  }
   do {
     ++k;
     p *= (c->sim->rng_mode == 0) ? hr_next(&c->sim->hr) / (double)2147483647 : orc_rand01(c);

@@ -7,7 +7,7 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = json.loads(os.environ.get("KBENCH_VARIANTS", '{"mb2": ["-DCHAIN_MIN_BLOCKS=2"], "mb3": ["-DCHAIN_MIN_BLOCKS=3"], "mb4": ["-DCHAIN_MIN_BLOCKS=4"]}'))
-POP = os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop")
+POP = os.path.join(ROOT, "models", "kuramoto.pop")
 
 
 def build():

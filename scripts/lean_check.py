@@ -6,7 +6,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto.pop"))
 
 
 def state(n, steps, tma, lean):

@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto.pop"))
 for n in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1048576,2097152,4194304,8388608,16777216,33554432").split(",")]:
     for tma, lean in ((0, 0), (1, 0), (1, 1)):
         pop = capi.Population(lib, capacity=n)

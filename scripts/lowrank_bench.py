@@ -4,7 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto_lowrank64.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto_lowrank64.pop"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 pop = capi.Population(lib, capacity=n)
 pop.init(n, replay=False)

@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, "/root/repo")
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop("/root/repo/oracle/fixtures/kuramoto_lowrank64.pop")
+lib = capi.ModelLib.from_pop("/root/repo/models/kuramoto_lowrank64.pop")
 n = 1 << 20
 for pad in (0, 32, 224, 1056, 4128, 33*32*31):
     pop = capi.Population(lib, capacity=n + pad)

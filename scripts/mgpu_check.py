@@ -23,7 +23,7 @@ CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde",
          ("pair_aux", 3001, "dde", 3, 1e-12, {}), ("kuramoto_lowrank_aux", 4097, "dde", 3, 1e-10, {}), ("kuramoto_lrexp", 4097, "dde", 3, 1e-10, {}),
          ("chain_array", 50001, "dde", 5, 1e-12, {}), ("vect_meanfield", 50001, "fe", 5, 1e-12, {})]
 for model, n, meth, nsteps, tol, opts in CASES:
-    lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", model + ".pop"))
+    lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
     pop = capi.Population(lib, capacity=hi - lo + 64, device=local)
     odist.connect(pop)
@@ -67,7 +67,7 @@ for model, n, meth, nsteps, tol, opts in CASES:
     dist.barrier()
     pop.close()
 # ---- whole simulation with birth / death through the C host driver: every rank's stats.dat must equal the solo run's
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "vdp_sde.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
 for ssahmin, ps, res, T in [(1.0, 2000, 21, 2.0), (0.0, 60, 6, 1.0)]:
     pop = capi.Population(lib, capacity=4 * ps + 1024, device=local)
     odist.connect(pop)

@@ -4,7 +4,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "nbody.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "nbody.pop"))
 for n in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "32768,131072").split(",")]:
     pop = capi.Population(lib, capacity=n)
     pop.init(n, replay=False)

@@ -14,7 +14,7 @@ VARIANTS = {
     "nbody_w4": ["-DPAIR_WAVES=4"],
     "nbody_w2": ["-DPAIR_WAVES=2"],
 }
-text = open(os.path.join(ROOT, "oracle", "fixtures", "nbody.pop"), encoding="utf8").read()
+text = open(os.path.join(ROOT, "models", "nbody.pop"), encoding="utf8").read()
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(8) as ex:

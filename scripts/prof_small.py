@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from odexp_b200 import capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 21
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "kuramoto.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto.pop"))
 pop = capi.Population(lib, capacity=n)
 pop.init(n, replay=False)
 t = pop.run_fixed("dde", 0.0, 0.05, 5)

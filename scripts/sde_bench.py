@@ -6,7 +6,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "oracle", "fixtures", "vdp_sde.pop"))
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 pop = capi.Population(lib, capacity=2 * n)
 pop.init(n, replay=False, seed=8)

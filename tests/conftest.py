@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FIXTURES = os.path.join(ROOT, "oracle", "fixtures")
+FIXTURES = os.path.join(ROOT, "models")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

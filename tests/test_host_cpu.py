@@ -148,7 +148,7 @@ def test_shipped_examples_emit_as_shipped(name):
 
 
 def test_every_fixture_emits_and_is_registered():
-    """every .pop under oracle/fixtures parses, emits, has a restatement in oracle/models.c (port.DIMS agrees with the parser's
+    """every .pop under models/ parses, emits, has a restatement in oracle/models.c (port.DIMS agrees with the parser's
     dimensions) and is built by __graft_entry__.build()"""
     import glob, os
     from odexp_b200 import popfile, cudagen
