@@ -52,7 +52,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
-               "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id"]
+               "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id", "odx_lowrank_order"]
 
 
 def _dp(a):
@@ -93,6 +93,7 @@ class ModelLib:
         L.odx_rhs.argtypes = [H, C.c_double]
         L.odx_meanfields.argtypes = [H, C.POINTER(C.c_double)]
         L.odx_rates.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.odx_lowrank_order.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         for f in (L.odx_fe_apply, L.odx_dde_apply):
             f.argtypes = [H, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int]
         L.odx_iteration_apply.argtypes = [H, C.POINTER(C.c_double), C.c_int]
@@ -233,6 +234,12 @@ class Population:
         m = np.zeros(max(1, self.lib.nmfd))
         self._ck(self.L.odx_meanfields(self.h, _dp(m)), "odx_meanfields")
         return m[:self.lib.nmfd]
+
+    def lowrank_order(self):
+        """(p, centre, half-range) chosen by the adaptive low-rank expansion in the last RHS evaluation"""
+        p, m, r = C.c_int(), C.c_double(), C.c_double()
+        self._ck(self.L.odx_lowrank_order(self.h, C.byref(p), C.byref(m), C.byref(r)), "odx_lowrank_order")
+        return p.value, m.value, r.value
 
     def rates(self):
         a, b = C.c_double(), C.c_double()

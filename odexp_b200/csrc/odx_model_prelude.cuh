@@ -32,6 +32,25 @@ static void odx_sincos_library(double x, double *sp, double *cp) { sincos(x, sp,
 __constant__ double odx_sc_dev[24] = ODX_SC_TABLE;
 #endif
 static const double odx_sc_host[24] = ODX_SC_TABLE;
+/* Table-assisted form for the persistent step kernels (contexts tagged by odx_ctx_sctab).  The argument is reduced to the nearest
+ * multiple of 2 pi / 1024 with the same shifted-sum rounding and a two-term Cody-Waite product (the third term is < 6e-27 here),
+ * sin / cos of that node come from a 16 KB shared-memory table the kernel fills once per launch (sincospi: the nodes are exact
+ * binary fractions of pi), and the residual |r| <= pi / 1024 needs only r - r^3/6 + r^5/120 and 1 - r^2/2 + r^4/24 (truncation
+ * < 1e-18): 14 FP64 operations and one 16-byte shared load instead of 26 FP64 + a dozen integer ones, and 6 instead of 16
+ * polynomial coefficients to keep in registers.  Error <= ~2 ulp of 1 (table 0.5 ulp + combination), far inside the 1e-10 parity
+ * bound; the quadrant logic is the table index. */
+template <class C> struct odx_ctx_sctab { static constexpr bool value = false; };
+#define ODX_SCT_N 1024
+#if defined(__CUDACC__)
+__shared__ double2 odx_sct_smem[ODX_SCT_N];          /* allocated only in kernels that reference it */
+__device__ __forceinline__ void odx_sct_fill() {     /* whole CTA; the caller synchronises afterwards */
+  for (int k = threadIdx.x; k < ODX_SCT_N; k += blockDim.x) {
+    double sv, cv;
+    sincospi((double)k * (2.0 / ODX_SCT_N), &sv, &cv);
+    odx_sct_smem[k] = make_double2(sv, cv);
+  }
+}
+#endif
 /* EXACT = false: straight-line fast path for every argument; out-of-range arguments only raise c.slow, and the caller redoes
  * the particle with EXACT = true.  (A branch to the library inside the fast path splits the basic block and keeps the compiler
  * from interleaving the two particles a thread carries: measured 135 -> ~100 issued instructions per particle-stage.) */
@@ -45,6 +64,20 @@ ODX_HD void odx_sincos(C &ctx, double x, double *sp, double *cp) {
   if (EXACT) { odx_sincos_library(x, sp, cp); return; }
 #if defined(__CUDA_ARCH__)
   ctx.slow |= !((__double2hiint(x) & 0x7fffffff) < 0x40f9c8f0);      /* !(|x| < 105615.0) on the integer pipe: the bound's low word is 0 */
+  if (odx_ctx_sctab<C>::value) {
+    const double qs = fma(x, 162.97466172610082 /* 1024 / (2 pi) */, 6755399441055744.0);
+    const int n = __double2loint(qs);
+    const double q = qs - 6755399441055744.0;
+    double r = fma(-q, 0x1.921fb54442d18p-8, x);          /* 2 pi / 1024, head (exact difference) and tail */
+    r = fma(-q, 0x1.1a62633145c07p-62, r);
+    const double z = r * r;
+    const double sr = fma(r * z, fma(z, 8.33333333333333333333e-03, -1.66666666666666666667e-01), r);      /* sin r */
+    const double cm = z * fma(z, 4.16666666666666666667e-02, -0.5);                                         /* cos r - 1 */
+    const double2 nd = odx_sct_smem[n & (ODX_SCT_N - 1)];
+    *sp = fma(nd.x, cm, fma(nd.y, sr, nd.x));
+    *cp = fma(nd.y, cm, fma(-nd.x, sr, nd.y));
+    return;
+  }
 #else
   ctx.slow |= !(fabs(x) < 105615.0);
 #endif

@@ -1188,6 +1188,24 @@ int odx_rhs(odx_handle *h, double t) {
   return do_rhs(h, t, 0.0);
 }
 
+/* what the adaptive low-rank expansion chose in the last RHS evaluation (lrexprank, src/lrexp.c:82-173): order p, centre, range */
+int odx_lowrank_order(odx_handle *h, int *p, double *meanx, double *range) {
+#ifdef ODX_MODEL_HAS_LOWRANK
+  ODX_CUDA(h, cudaSetDevice(h->device));
+  if (!h->lr_plan) { h->err = "odx_lowrank_order: no RHS evaluation yet"; return ODX_EINVAL; }
+  struct { double meanx, range; int p; } head;
+  static_assert(offsetof(LrPlan, p) == 16, "LrPlan head layout");
+  ODX_CUDA(h, cudaMemcpyAsync(&head, h->lr_plan, sizeof head, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (p) *p = head.p;
+  if (meanx) *meanx = head.meanx;
+  if (range) *range = head.range;
+  return ODX_SUCCESS;
+#else
+  (void)p; (void)meanx; (void)range; h->err = "odx_lowrank_order: the model has no low-rank %C coupling"; return ODX_EUNSUP;
+#endif
+}
+
 int odx_meanfields(odx_handle *h, double *mfd) {
   ODX_CUDA(h, cudaSetDevice(h->device));
   ODX_CUDA(h, cudaMemcpyAsync(h->h_pin, h->sums, sizeof(double) * NSLOT * NRED, cudaMemcpyDeviceToHost, h->stream));

@@ -68,6 +68,10 @@ static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
 }
+/* known-answer hook for tests/: the block function alone (Random123 philox4x32-10 vectors) */
+void orc_philox_block(uint32_t c[4], uint32_t k0, uint32_t k1) { philox(c, k0, k1); }
+/* draws through the keyed convention with an explicit key / counter prefix (tests/: distribution checks of orc_poisson) */
+long orc_poisson_keyed(uint32_t k0, uint32_t k1, uint32_t id, uint32_t stream, double lambda);
 static double u01(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
@@ -115,6 +119,12 @@ long orc_poisson(orc_ctx *c, double lambda) {
     p *= (c->sim->rng_mode == 0) ? hr_next(&c->sim->hr) / (double)2147483647 : orc_rand01(c);
   } while (p > L);
   return --k;
+}
+long orc_poisson_keyed(uint32_t k0, uint32_t k1, uint32_t id, uint32_t stream, double lambda) {
+  orc_sim s; orc_ctx c;
+  memset(&s, 0, sizeof s); memset(&c, 0, sizeof c);
+  s.rng_mode = 1; s.k0 = k0; s.k1 = k1; c.sim = &s; c.kid = id; c.kstream = stream; c.kdom = ORC_DOM_HOST; c.kslot = 0;
+  return orc_poisson(&c, lambda);
 }
 double orc_dwdt(orc_ctx *c) { return orc_randN(c, 0, 1) / sqrt(c->h); }
 int orc_stopif(orc_ctx *c, int cond) { if (cond) c->sim->stop_flag = ORC_STOP_COND; return cond; }

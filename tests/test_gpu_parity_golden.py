@@ -80,6 +80,49 @@ def test_nbody_rkf45(model_lib):
     np.testing.assert_allclose(last["cols"], g["last_cols"], rtol=1e-8, atol=1e-12)
 
 
+@pytest.mark.parametrize("meth,n,ts,h0", [("dde", 257, (0, 0.04), 0.02), ("dde", 1025, (0, 0.04), 0.02), ("dde", 4099, (0, 0.02), 0.02),
+                                          ("rkf45", 257, (0, 0.05), 0.005), ("rkf45", 1025, (0, 0.05), 0.005), ("rkf45", 4099, (0, 0.002), 0.002)])
+def test_nbody_multi_tile_vs_oracle(model_lib, meth, n, ts, h0):
+    """the O(N^2) %C kernel beyond one tile: several i-tiles (256 particles) and j-segments (PAIR_TJ = 128), the self term's
+    poison-and-redo in a tile other than the first, k_pair_finish adding the segments in list order -- against the CPU
+    restatement (bit-identical to the reference binary for this fixture).  Stated tolerance for the chaotic N-body: 1e-8
+    relative over this short horizon, identical accept / reject sequence for rkf45."""
+    from odexp_b200 import capi
+    from oracle import port
+    o = {"meth": meth, "h0": h0, "res": 2, "ps": n, "hmin": 0.0, "abstol": 1e-8, "reltol": 1e-8}
+    pop = capi.Population(model_lib("nbody"), capacity=n + 64)
+    out = capi.odesolver(pop, ts, meth=meth, h0=h0, res=2, popsize=n, hmin=0.0, abstol=1e-8, reltol=1e-8, replay_ic=True)
+    pop.close()
+    ref = port.run("nbody", o, ts)
+    assert out["report"]["steps"] == ref["report"]["steps"]
+    a, b = out["traj"], ref["traj"]
+    np.testing.assert_array_equal(a["id"], b["id"])
+    np.testing.assert_array_equal(a["cols"][a["step"] == 0][:, :6], b["cols"][b["step"] == 0][:, :6])      # replayed ICs: bit-identical
+    np.testing.assert_allclose(a["cols"][:, :6], b["cols"][:, :6], rtol=1e-8, atol=1e-12)
+    # the couplings themselves (columns 6..8 of a frame = psi): relative to the largest coupling of the frame
+    scale = np.abs(b["cols"][:, 6:9]).max()
+    assert np.abs(a["cols"][:, 6:9] - b["cols"][:, 6:9]).max() <= 1e-10 * scale
+
+
+@pytest.mark.parametrize("n", [16387, 40001])
+def test_nbody_psi_many_tiles_per_cta_vs_numpy(model_lib, n):
+    """N large enough that every CTA of k_pair walks several j-tiles (more than 64 tiles of 128): the redo of the self term
+    then happens in the middle of a CTA's j-loop, and the partial sums of 64 segments are added by k_pair_finish.  Checked for
+    200 sampled particles against the numpy restatement of the generated %C walk (oracle/nbody_np.py)."""
+    from odexp_b200 import capi
+    from oracle import nbody_np
+    pop = capi.Population(model_lib("nbody"), capacity=n)
+    pop.init(n, replay=False, seed=5)
+    pop.rhs(0.0)
+    d = pop.download()
+    pop.close()
+    rng = np.random.default_rng(1)
+    idx = np.unique(np.concatenate([[0, 1, 127, 128, 255, 256, n - 1, n - 2], rng.integers(0, n, 192)]))
+    want = nbody_np.psi_subset(d["y"][:, :3], idx)
+    scale = np.abs(want).max()
+    assert np.abs(d["psi"][idx] - want).max() <= 1e-11 * scale
+
+
 def test_config1_kuramoto_as_shipped(model_lib):
     """BASELINE config 1: the reference's examples/kuramoto.pop as shipped (N=1000, rkck, 801 output points over [0,160]);
     golden = the unchanged reference binary built from the shipped file.  160 time units of adaptive stepping: the GPU and

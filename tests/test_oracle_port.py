@@ -165,3 +165,96 @@ def test_quick_buffer_matches_reference_binary(model, opts, ts, axes, names, par
     b = refrun.run(model, dict(opts, x=names[0], y=names[1], z=names[2], particle=particle), timespan=ts, dims=port.DIMS[model])
     assert a["quick"].shape == b["quick"].shape and len(a["quick"]) > 3
     np.testing.assert_allclose(a["quick"], b["quick"], rtol=1e-13, atol=1e-15, equal_nan=True)
+
+
+# ---- random numbers: known answers ---------------------------------------------------------------------------------------
+# Random123 (Salmon et al., SC'11) kat_vectors for philox4x32-10: (counter, key) -> output
+PHILOX_KAT = [((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+              ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+              ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+
+
+def test_philox_known_answers_oracle():
+    """the checker's Philox4x32-10 (oracle/odx_oracle.c) against the Random123 known-answer vectors"""
+    import ctypes as C
+    from oracle import port
+    L = port.lib()
+    for ctr, key, want in PHILOX_KAT:
+        c = (C.c_uint32 * 4)(*ctr)
+        L.orc_philox_block(c, C.c_uint32(key[0]), C.c_uint32(key[1]))
+        assert tuple(c) == want
+
+
+def _rng_harness(tmp_path):
+    """odexp_b200/csrc/odx_rng.h compiled for the host (its functions are __host__ __device__): one small C++ program"""
+    import subprocess
+    from conftest import ROOT
+    import os
+    src = tmp_path / "rng_kat.cpp"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "odx_rng.h"
+int main(int argc, char **argv) {
+  if (argc > 1 && strcmp(argv[1], "kat") == 0) {
+    uint32_t c[4], k[2];
+    while (scanf("%x %x %x %x %x %x", &c[0], &c[1], &c[2], &c[3], &k[0], &k[1]) == 6) {
+      odx::philox4x32_10(c, k[0], k[1]);
+      printf("%08x %08x %08x %08x\n", c[0], c[1], c[2], c[3]);
+    }
+  } else if (argc > 4 && strcmp(argv[1], "poisson") == 0) {       /* poisson <lambda> <n> <first id>: one draw per particle id */
+    const double lam = atof(argv[2]); const long n = atol(argv[3]); const uint32_t id0 = (uint32_t)atol(argv[4]);
+    for (long i = 0; i < n; i++) {
+      odx::PhiloxStream ps; ps.k0 = 3141592u; ps.k1 = 0; ps.id = id0 + (uint32_t)i; ps.stream = 7; ps.dom = 0x484f5354u; ps.slot = 0;
+      printf("%ld\n", ps.poisson(lam));
+    }
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "rng_kat"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), str(src), "-o", str(exe), "-lm"], check=True)
+    return str(exe)
+
+
+def test_philox_known_answers_product_header(tmp_path):
+    """the product's Philox4x32-10 (odexp_b200/csrc/odx_rng.h, the same source the device compiles) against the Random123 vectors"""
+    import subprocess
+    exe = _rng_harness(tmp_path)
+    inp = "".join("%x %x %x %x %x %x\n" % (ctr + key) for ctr, key, _ in PHILOX_KAT)
+    out = subprocess.run([exe, "kat"], input=inp, capture_output=True, text=True, check=True).stdout.split("\n")
+    for (ctr, key, want), got in zip(PHILOX_KAT, out):
+        assert tuple(int(x, 16) for x in got.split()) == want
+
+
+@pytest.mark.parametrize("lam", [0.5, 12.0, 29.9, 30.0, 1e4, 1.7e5])
+def test_keyed_poisson_moments_and_oracle_agreement(tmp_path, lam):
+    """the keyed Poisson sampler: Knuth's product method below 30 (the reference's form, src/rand_gen.c:37-46), transformed
+    rejection above (the reference's form saturates near 745 once exp(-lambda) underflows).  Mean and variance are lambda, and
+    the checker's copy draws the same numbers."""
+    import ctypes as C, subprocess
+    from oracle import port
+    n = 4000
+    exe = _rng_harness(tmp_path)
+    got = np.array([int(x) for x in subprocess.run([exe, "poisson", repr(lam), str(n), "100"], capture_output=True, text=True, check=True).stdout.split()])
+    assert len(got) == n
+    se = np.sqrt(lam / n)
+    assert abs(got.mean() - lam) < 5 * se
+    assert abs(got.var() / lam - 1.0) < 0.15
+    L = port.lib()
+    L.orc_poisson_keyed.restype = C.c_long
+    L.orc_poisson_keyed.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+    ref = np.array([L.orc_poisson_keyed(3141592, 0, 100 + i, 7, lam) for i in range(200)])
+    np.testing.assert_array_equal(got[:200], ref)
+
+
+def test_nbody_numpy_restatement_matches_port():
+    """oracle/nbody_np.py (used for populations the C restatement cannot walk in seconds) against oracle/odx_oracle.c"""
+    from oracle import port, nbody_np
+    n = 300
+    r = port.run("nbody", {"meth": "dde", "h0": 0.02, "res": 2, "ps": n, "hmin": 0.0}, (0, 0.02))
+    fr = r["traj"][r["traj"]["step"] == 0]["cols"]              # first frame: positions + the couplings of the initial evaluation
+    want = nbody_np.psi_subset(fr[:, :3], np.arange(n))
+    scale = np.abs(fr[:, 6:9]).max()
+    assert np.abs(want - fr[:, 6:9]).max() <= 1e-13 * scale
