@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 def _digest(text):
     h = hashlib.sha1(text.encode("utf8"))
-    for f in sorted(os.listdir(CSRC)) + ["../../include/odx.h"]:
+    for f in sorted(os.listdir(CSRC)) + ["../../include/odx.h", "../../include/odx_compat.h"]:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):
             h.update(open(p, "rb").read())
@@ -51,10 +51,12 @@ def build_model(pop_path=None, text=None, name=None, force=False, verbose=False,
         raise RuntimeError("nvcc not found and the prebuilt %s is missing or stale (stamp != digest of the current sources)" % so)
     with open(cu_path, "w") as f:
         f.write(cu)
-    host_o = os.path.join(BUILD, "odx_host_%s.o" % name)
-    subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I" + INCLUDE, "-c", os.path.join(CSRC, "odx_host.c"), "-o", host_o],
-                   check=True)
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I" + CSRC, "-I" + INCLUDE, cu_path, host_o, "-o", so, "-ldl"]
+    host_objs = []
+    for src in ("odx_host.c", "odx_compat.c"):      # host side in C: the GPU branch of odesolver, the reference-signature stepper entry points
+        obj = os.path.join(BUILD, "%s_%s.o" % (src[:-2], name))
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I" + INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        host_objs.append(obj)
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I" + CSRC, "-I" + INCLUDE, cu_path] + host_objs + ["-o", so, "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout)

@@ -37,7 +37,8 @@ class SolverOpts(C.Structure):
                 ("reltol", C.c_double), ("ssahmin", C.c_double), ("aleap", C.c_double), ("popsize", C.c_int), ("seed", C.c_uint32),
                 ("replay_ic", C.c_int), ("traj_stride", C.c_int), ("outdir", C.c_char_p), ("tspan", C.POINTER(C.c_double)),
                 ("tspan_len", C.c_int), ("mu", C.POINTER(C.c_double)),
-                ("quick", C.c_int), ("plot_x", C.c_int), ("plot_y", C.c_int), ("plot_z", C.c_int), ("particle", C.c_int)]
+                ("quick", C.c_int), ("plot_x", C.c_int), ("plot_y", C.c_int), ("plot_z", C.c_int), ("particle", C.c_int),
+                ("init_mode", C.c_int)]
 
 
 class SolverReport(C.Structure):
@@ -52,7 +53,8 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_evolve_apply", "odx_evolve_stats", "odx_run_fixed", "odx_ssa_apply", "odx_tauleap_apply", "odx_draw_uniform",
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
-               "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id", "odx_lowrank_order"]
+               "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id", "odx_lowrank_order",
+               "odx_request_abort", "odx_abort_requested", "odx_clear_abort"]
 
 
 def _dp(a):
@@ -110,6 +112,9 @@ class ModelLib:
         L.odx_event_record.argtypes = [H, C.c_int]
         L.odx_event_elapsed_ms.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.odx_launch_count.argtypes = [H]; L.odx_launch_count.restype = C.c_uint64
+        L.odx_request_abort.argtypes = [H]; L.odx_request_abort.restype = None
+        L.odx_clear_abort.argtypes = [H]; L.odx_clear_abort.restype = None
+        L.odx_abort_requested.argtypes = [H]
         mi = L.odx_model().contents
         self.info = mi
         self.name = mi.name.decode()
@@ -346,7 +351,7 @@ def read_outputs(outdir, dims, read_traj=True):
 
 def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, abstol=1e-6, reltol=1e-6, popsize=1, ssahmin=0.0,
               aleap=0.01, seed=3141592, replay_ic=True, traj_stride=1, outdir=None, mu=None, read_traj=True, quick=True,
-              plot=(-1, 0, 1), particle=0):
+              plot=(-1, 0, 1), particle=0, init_mode=0):
     """Python mirror of `odesolver` (src/methods_odexp.h:13-17) driving the C host loop; returns outputs + report.
     quick / plot / particle: current.plot with `opt x|y|z` as indices (-1 = T; reference defaults T, [0], [1]) and `opt particle`."""
     own = outdir is None
@@ -357,7 +362,7 @@ def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, a
     muarr = np.ascontiguousarray(mu, dtype=np.float64) if mu is not None else None
     o = SolverOpts(METHODS[meth], int(res), hmin, h0, abstol, reltol, ssahmin, aleap, int(popsize), int(seed), 1 if replay_ic else 0,
                    int(traj_stride), outdir.encode(), _dp(ts), len(ts), _dp(muarr), 1 if quick else 0, int(plot[0]), int(plot[1]),
-                   int(plot[2]), int(particle))
+                   int(plot[2]), int(particle), int(init_mode))
     rep = SolverReport()
     st = pop.L.odx_odesolver(pop.h, C.byref(o), C.byref(rep))
     if st != 0:

@@ -46,6 +46,10 @@ constexpr int NRED = NMFD + 2;                          /* [%M sums..., %BIRTH s
 constexpr int RED_BIRTH = NMFD, RED_RATES = NMFD + 1;
 constexpr int BLOCK = 256;
 constexpr int MAXSTAGE = 7;
+#ifndef ODX_NO_SCTAB
+#define ODX_NO_SCTAB 0
+#endif
+constexpr bool SCTAB_MODEL = (M::NHINT > 0) && !ODX_NO_SCTAB;      /* table-assisted sincos in the persistent step kernels (odx_model_prelude.cuh) */
 #ifndef STAGE_LOAD_CS
 #define STAGE_LOAD_CS 0
 #endif
@@ -85,6 +89,15 @@ struct DevCtx {
   ODX_HD long poisson(double l) { return rng.poisson(l); }
   ODX_HD double dwdt() { return rng.randN(0.0, 1.0) / sqrt(h); }
 };
+
+/* the same context inside the persistent step kernels, which hold the sincos node table in shared memory (odx_model_prelude.cuh):
+ * the tag selects the table-assisted odx_sincos at compile time */
+struct DevCtxT : DevCtx {};
+}  // namespace odx
+template <> struct odx_ctx_sctab<odx::DevCtxT> { static constexpr bool value = true; };
+namespace odx {
+template <bool TAB> struct CtxSel { typedef DevCtx type; };
+template <> struct CtxSel<true> { typedef DevCtxT type; };
 
 /* host context for replayed initial conditions: draws through the serial libc stream */
 struct HostCtx {
@@ -209,6 +222,12 @@ __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stre
   c.ky_base = nullptr; c.ky_i = 0; c.ky_n = 1; c.ky_stride = 0;
   return c;
 }
+template <bool TAB>
+__device__ __forceinline__ typename CtxSel<TAB>::type make_ctx_t(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
+  typename CtxSel<TAB>::type c;
+  static_cast<DevCtx &>(c) = make_ctx(p, h, stream, dom, id);
+  return c;
+}
 __device__ __forceinline__ void ctx_neighbours(DevCtx &c, const Pop &p, const double *ycur, int64_t i) {
   if (M::USES_KY) { c.ky_base = ycur; c.ky_i = i; c.ky_n = p.n; c.ky_stride = p.stride; }
 }
@@ -224,15 +243,16 @@ __device__ __forceinline__ void note_stop(const Pop &p, const DevCtx &c) {
  * auxiliary variable (MA), that value comes from ode_rhs evaluated with zeroed mean fields and the
  * previous psi (src/odexp:820-833). */
 constexpr bool USE_HINTS = (M::NHINT > 0) && !M::TERMS_USE_AUX;     /* stage-to-stage sincos increments (odx_sincos_inc) */
-template <bool EXACT>
-__device__ __forceinline__ void particle_terms_x(DevCtx &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+constexpr bool USE_SCTAB = SCTAB_MODEL;                          /* models whose RHS and %M terms take sin / cos: table-assisted sincos in the persistent kernels */
+template <bool EXACT, class CT>
+__device__ __forceinline__ void particle_terms_x(CT &c, double t, const double (&y)[A1(NVAR)], const double (&e)[A1(NEXPR)],
                                                  const double (&psi)[A1(NPSI)], double (&tm)[NRED], const OdxHint *hint = nullptr) {
   double aux[A1(NAUX)];
   if (M::TERMS_USE_AUX) {
     double f[A1(NVAR)], mz[A1(NMFD)], d = 0.0, r = 0.0;
 #pragma unroll
     for (int k = 0; k < A1(NMFD); k++) mz[k] = 0.0;
-    DevCtx c1 = c;
+    CT c1 = c;
     M::template rhs<EXACT>(c1, t, y, e, psi, mz, f, aux, d, r);
     c.slow |= c1.slow;
   }
@@ -327,13 +347,13 @@ struct ChainArgs {
  * new state, which are exactly what the first stage of the next step needs.
  * Each thread carries two adjacent particles per iteration: every column is moved with 128-bit accesses and the two
  * independent dependency chains hide the FP64 latency of the per-particle model code. */
-template <bool FIRST, bool LAST, bool EXACT>
+template <bool FIRST, bool LAST, bool EXACT, bool TAB>
 __device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int32_t id, int64_t gi,
                                           const double (&y0)[A1(NVAR)], const double (&yc)[A1(NVAR)], const double (&e)[A1(NEXPR)],
                                           const double (&psi)[A1(NPSI)], const double (&acc_in)[A1(NVAR)], double (&acc)[A1(NVAR)],
                                           double (&yn)[A1(NVAR)], double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
   double f[A1(NVAR)];
-  DevCtx c = make_ctx(p, a.h, a.eval_index, DOM_RHS, id);
+  typename CtxSel<TAB>::type c = make_ctx_t<TAB>(p, a.h, a.eval_index, DOM_RHS, id);
   ctx_neighbours(c, p, FIRST ? p.Y : p.YS, gi);
   OdxHint hint;
   M::template rhs<EXACT>(c, a.t_eval, yc, e, psi, mfd, f, aux, death, repli, USE_HINTS ? &hint : nullptr);
@@ -353,7 +373,7 @@ __device__ __forceinline__ int chain_lane(const Pop &p, const ChainArgs &a, cons
     }
   }
   if (NMFD > 0 || M::HAS_BIRTH) {
-    DevCtx c2 = make_ctx(p, a.h, a.eval_index + 1, DOM_RHS, id);
+    typename CtxSel<TAB>::type c2 = make_ctx_t<TAB>(p, a.h, a.eval_index + 1, DOM_RHS, id);
     particle_terms_x<EXACT>(c2, a.t_next, yn, e, psi, tm, USE_HINTS ? &hint : nullptr);
     slow |= c2.slow;
   }
@@ -402,7 +422,9 @@ __device__ __forceinline__ void store_cols2(double *__restrict__ base, int64_t s
 #define PERSIST_THREADS_TMA 768    /* 23 consumer warps + 1 producer warp, 80 registers: measured best of 512 / 640 / 768 / 896 / 1024 */
 #endif
 #ifndef PERSIST_THREADS
-#define PERSIST_THREADS 1024       /* without the ring: 32 warps x 64 registers hide the load latency best */
+/* without the ring: 32 warps x 64 registers hide the load latency best; with the sincos table the stage body needs ~80 registers
+ * (at 64 it spills inside the sweep: 0.068 instead of 0.055 ms per step at 2^21 particles), so 24 warps x 85 */
+#define PERSIST_THREADS (SCTAB_MODEL ? 768 : 1024)
 #endif
 #ifndef TMA_MAXBUF_N
 #define TMA_MAXBUF_N 8   /* <= 16 (state word of tma_produce) */
@@ -527,7 +549,7 @@ __device__ __forceinline__ uint32_t tma_produce(const double *Y, const double *E
 
 /* the arithmetic and the stores of one thread's pair of particles.  FULL: the pair lies inside the population (known per
  * tile, so the tail predicates vanish from the hot path) */
-template <bool FIRST, bool LAST, bool FULL>
+template <bool FIRST, bool LAST, bool FULL, bool TAB>
 __device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], int64_t i, bool two_rt,
                                            double (&y0)[2][A1(NVAR)], double (&yc)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)],
                                            double (&psi)[2][A1(NPSI)], double (&acc)[2][A1(NVAR)], double (&red)[NRED]) {
@@ -544,11 +566,11 @@ __device__ __forceinline__ void chain_pair(const Pop &p, const ChainArgs &a, con
   int32_t id0 = 0, id1 = 0;
   if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
   double acco[2][A1(NVAR)], tm[2][NRED];
-  const int s0 = chain_lane<FIRST, LAST, false>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-  const int s1 = chain_lane<FIRST, LAST, false>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  const int s0 = chain_lane<FIRST, LAST, false, TAB>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+  const int s1 = chain_lane<FIRST, LAST, false, TAB>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   if (s0 | s1) {          /* rare: an argument outside the fast sincos range -> library path for this pair */
-    chain_lane<FIRST, LAST, true>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-    chain_lane<FIRST, LAST, true>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+    chain_lane<FIRST, LAST, true, TAB>(p, a, mfd, id0, i, y0[0], yc[0], e[0], psi[0], acc[0], acco[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    chain_lane<FIRST, LAST, true, TAB>(p, a, mfd, id1, i + 1, y0[1], yc[1], e[1], psi[1], acc[1], acco[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   }
 #pragma unroll
   for (int k2 = 0; k2 < NRED; k2++) red[k2] += tm[0][k2] + (two ? tm[1][k2] : 0.0);
@@ -647,14 +669,14 @@ __device__ __forceinline__ void tile_sweep(const Pop &p, int reverse, bool has_y
 }
 
 /* one pass of a chain stage (stored scheme) */
-template <bool FIRST, bool LAST, bool TMA>
+template <bool FIRST, bool LAST, bool TMA, bool TAB = false>
 __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, const double (&mfd)[A1(NMFD)], double (&red)[NRED],
                                             TmaRing &ring) {
   const bool use_acc = !FIRST && a.recon == 0.0;
   tile_sweep<TMA>(p, a.reverse, !FIRST, use_acc, ring,
                   [&](int64_t i, bool two, auto full, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)], double (&psi)[2][A1(NPSI)],
                       double (&ys)[2][A1(NVAR)], double (&acc)[2][A1(NVAR)]) {
-                    chain_pair<FIRST, LAST, decltype(full)::value>(p, a, mfd, i, two, y0, ys, e, psi, acc, red);
+                    chain_pair<FIRST, LAST, decltype(full)::value, TAB>(p, a, mfd, i, two, y0, ys, e, psi, acc, red);
                   });
 }
 
@@ -686,7 +708,7 @@ __device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const
 #pragma unroll
   for (int k = 0; k < NRED; k++) tm[k] = 0.0;
   const double t = a.t_eval, h = a.h, half = a.h / 2.0;
-  DevCtx c = make_ctx(p, h, a.eval_index, DOM_RHS, id);
+  typename CtxSel<USE_SCTAB>::type c = make_ctx_t<USE_SCTAB>(p, h, a.eval_index, DOM_RHS, id);
   OdxHint h0, h1;
   OdxHint *hl = &h0;                    /* triple the %M terms of the new state are incremented from */
   double t_next;
@@ -725,7 +747,7 @@ __device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const
   }
   int slow = c.slow;
   if (NMFD > 0 || M::HAS_BIRTH) {
-    DevCtx c2 = make_ctx(p, h, a.eval_index + 1, DOM_RHS, id);
+    typename CtxSel<USE_SCTAB>::type c2 = make_ctx_t<USE_SCTAB>(p, h, a.eval_index + 1, DOM_RHS, id);
     particle_terms_x<EXACT>(c2, t_next, yout, e, psi, tm, USE_HINTS ? hl : nullptr);
     slow |= c2.slow;
   }
@@ -952,6 +974,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
 #pragma unroll
   for (int k = 0; k < A1(NMFD); k++) mfd0[k] = 0.0;
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
+  if (USE_SCTAB) odx_sct_fill();
   __syncthreads();
   /* role by warp index, broadcast from lane 0 so that the compiler knows the branch is warp-uniform */
   const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -1008,19 +1031,19 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         else lean_sweep<3, PF_ON>(p, a, mfd0, mfd, red, ring_);
       } else if (g.nst == 1) {                            /* Euler */
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
-        chain_sweep<true, true, PF_ON>(p, a, mfd, red, ring_);
+        chain_sweep<true, true, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       } else if (s == 0) {                                /* RK4 (methods_odexp.c:1846-1863) */
         a.t_eval = t; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 1.0; a.skip_acc_store = g.recon ? 1 : 0;
-        chain_sweep<true, false, PF_ON>(p, a, mfd, red, ring_);
+        chain_sweep<true, false, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       } else if (s == 1) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h / 2.0; a.a = g.h / 2.0; a.w = 2.0; a.recon = g.recon ? 1.0 / (g.h / 2.0) : 0.0;
-        chain_sweep<false, false, PF_ON>(p, a, mfd, red, ring_);
+        chain_sweep<false, false, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       } else if (s == 2) {
         a.t_eval = t + g.h / 2.0; a.t_next = t + g.h; a.a = g.h; a.w = 2.0;
-        chain_sweep<false, false, PF_ON>(p, a, mfd, red, ring_);
+        chain_sweep<false, false, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       } else {
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
-        chain_sweep<false, true, PF_ON>(p, a, mfd, red, ring_);
+        chain_sweep<false, true, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       }
       /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
        * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence

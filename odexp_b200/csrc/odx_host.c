@@ -193,15 +193,19 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
     odx_comm_rank(h, &rank, &nranks);
     base = o->popsize / nranks; extra = o->popsize % nranks;
     local = base + (rank < extra ? 1 : 0);
-    if ((status = odx_pop_init(h, local, t, o->seed, o->replay_ic)) != 0) goto done;
+    if (o->init_mode == 0) {
+      if ((status = odx_pop_init(h, local, t, o->seed, o->replay_ic)) != 0) goto done;
+    }
+    /* init_mode 1 / 2: the caller has uploaded the population (opt init 1: the state the previous run left in SIM->pop) */
   }
   /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364) */
   if ((status = odx_rhs(h, t)) != 0) goto done;
   if ((status = odx_meanfields(h, os.mfd)) != 0) goto done;
   if (mi->has_stopif) odx_stop_flag(h, NULL);      /* EVENT_TYPE = EVENT_NONE after the initial evaluation (:380) */
   odx_pop_size(h, NULL, &n, NULL);
-  for (i = 0; i < o->popsize; i++) {              /* one stats row per initial particle (methods_odexp.c:372-376) */
-    event[0] = -1; event[1] = 1; event[2] = (int)i;
+  for (i = 0; i < (o->init_mode == 0 ? (int64_t)o->popsize : n); i++) {      /* one stats row per initial particle (methods_odexp.c:372-376) */
+    /* SIM->event is {-1, 1, .} after par_birth; with `opt init 1` it still holds the zeros the previous run left (:339-354, 675) */
+    event[0] = o->init_mode == 1 ? 0 : -1; event[1] = o->init_mode == 1 ? 0 : 1; event[2] = (int)i;
     write_stats_row(&os, t, (int)n, stop_flag, event);
   }
   memset(event, 0, sizeof event);
@@ -209,7 +213,8 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) goto done;
   if ((status = odx_evolve_reset(h)) != 0) goto done;
 
-  while (t < t1 && n > 0) {
+  odx_clear_abort(h);
+  while (t < t1 && n > 0 && !odx_abort_requested(h)) {        /* while (t < t1 && !abort_odesolver_flag && POP_SIZE > 0), :451 */
     double u;
     dt_dyn = fmin(dt, t1 - t);
     if ((t <= nextstop) && (dt_dyn >= (nextstop - t))) { dt_dyn = nextstop - t; stop_flag = ODX_STOP_TSPAN; }
@@ -254,6 +259,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
         steps++; particle_steps += (double)n_step;
         if (hstep < o->hmin) hstep = o->hmin;
       }
+      if (odx_abort_requested(h)) stop_flag = ODX_EVENT_ABORT;   /* the SIGINT handler's EVENT_TYPE = EVENT_ABORT (:23-30) */
       if (t >= t1) stop_flag = ODX_EVENT_TFINAL;
       if (odx_meanfields(h, os.mfd) != 0 && status == 0) status = ODX_ECUDA;
       write_stats_row(&os, t, (int)n, stop_flag, event);

@@ -27,11 +27,13 @@ static void odx_sincos_library(double x, double *sp, double *cp) { sincos(x, sp,
   -1.38888888888741095749e-03, 4.16666666666666019037e-02, \
   /* [16..] Taylor coefficients of odx_sincos_inc: sin d / d - 1 and cos d - 1 in z = d^2 */ \
   2.75573192239858906526e-06, -1.98412698412698412698e-04, 8.33333333333333333333e-03, -1.66666666666666666667e-01, \
-  -2.75573192239858906526e-07, 2.48015873015873015873e-05, -1.38888888888888888889e-03, 4.16666666666666666667e-02 }
+  -2.75573192239858906526e-07, 2.48015873015873015873e-05, -1.38888888888888888889e-03, 4.16666666666666666667e-02, \
+  /* [24..] table-assisted odx_sincos: 1024 / (2 pi), head and tail of 2 pi / 1024 */ \
+  162.97466172610082, 0x1.921fb54442d18p-8, 0x1.1a62633145c07p-62 }
 #if defined(__CUDACC__)
-__constant__ double odx_sc_dev[24] = ODX_SC_TABLE;
+__constant__ double odx_sc_dev[27] = ODX_SC_TABLE;
 #endif
-static const double odx_sc_host[24] = ODX_SC_TABLE;
+static const double odx_sc_host[27] = ODX_SC_TABLE;
 /* Table-assisted form for the persistent step kernels (contexts tagged by odx_ctx_sctab).  The argument is reduced to the nearest
  * multiple of 2 pi / 1024 with the same shifted-sum rounding and a two-term Cody-Waite product (the third term is < 6e-27 here),
  * sin / cos of that node come from a 16 KB shared-memory table the kernel fills once per launch (sincospi: the nodes are exact
@@ -65,14 +67,14 @@ ODX_HD void odx_sincos(C &ctx, double x, double *sp, double *cp) {
 #if defined(__CUDA_ARCH__)
   ctx.slow |= !((__double2hiint(x) & 0x7fffffff) < 0x40f9c8f0);      /* !(|x| < 105615.0) on the integer pipe: the bound's low word is 0 */
   if (odx_ctx_sctab<C>::value) {
-    const double qs = fma(x, 162.97466172610082 /* 1024 / (2 pi) */, 6755399441055744.0);
+    const double qs = fma(x, T[24], 6755399441055744.0);
     const int n = __double2loint(qs);
     const double q = qs - 6755399441055744.0;
-    double r = fma(-q, 0x1.921fb54442d18p-8, x);          /* 2 pi / 1024, head (exact difference) and tail */
-    r = fma(-q, 0x1.1a62633145c07p-62, r);
+    double r = fma(-q, T[25], x);                         /* 2 pi / 1024, head (exact difference) and tail */
+    r = fma(-q, T[26], r);
     const double z = r * r;
-    const double sr = fma(r * z, fma(z, 8.33333333333333333333e-03, -1.66666666666666666667e-01), r);      /* sin r */
-    const double cm = z * fma(z, 4.16666666666666666667e-02, -0.5);                                         /* cos r - 1 */
+    const double sr = fma(r * z, fma(z, T[18], T[19]), r);      /* sin r = r - r^3/6 + r^5/120 */
+    const double cm = z * fma(z, T[23], -0.5);                  /* cos r - 1 = -r^2/2 + r^4/24 */
     const double2 nd = odx_sct_smem[n & (ODX_SCT_N - 1)];
     *sp = fma(nd.x, cm, fma(nd.y, sr, nd.x));
     *cp = fma(nd.y, cm, fma(-nd.x, sr, nd.y));

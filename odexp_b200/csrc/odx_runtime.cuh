@@ -95,6 +95,8 @@ struct odx_handle {
   int lr_pmax = 31; double lr_abstol = 1e-6, lr_reltol = 1e-6;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
+  volatile int abort_req = 0;                 /* odx_request_abort (SIGINT) */
+  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   HostRand hr; bool hr_seeded = false; uint32_t host_draws = 0;   /* serial stream of the host loop (replay mode) */
   std::string err;
 };
@@ -838,6 +840,7 @@ void odx_destroy(odx_handle *h) {
   if (h->rmax) cudaFree(h->rmax);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1281,16 +1284,38 @@ int odx_run_fixed(odx_handle *h, int method, double *t, double hstep, int64_t ns
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (method != ODX_METH_FE && method != ODX_METH_DDE) { h->err = "odx_run_fixed: fixed-step methods are fe and dde"; return ODX_EINVAL; }
   if (can_persist(h) && h->n > 0 && nsteps > 0) {
-    ODX_TRY(chain_run_persist(h, method == ODX_METH_FE ? 1 : 4, *t, hstep, nsteps, 1));
-    *t += hstep * (double)nsteps;
+    /* one cooperative launch cannot be interrupted: cut the run into launches of ~2e10 particle-stages (~0.1 s) and keep at
+     * most two in flight, so that odx_request_abort takes effect within a few tenths of a second */
+    const int nst = method == ODX_METH_FE ? 1 : 4;
+    int64_t chunk = (int64_t)(2.0e10 / ((double)h->n * nst));
+    if (chunk < 1) chunk = 1;
+    const double t0 = *t;
+    int64_t done = 0;
+    for (int k = 0; done < nsteps; k++) {
+      if (h->abort_req) break;
+      const int64_t m = (nsteps - done < chunk) ? nsteps - done : chunk;
+      if (k >= 2) ODX_CUDA(h, cudaEventSynchronize(h->chunk_ev[k & 1]));
+      ODX_TRY(chain_run_persist(h, nst, t0 + hstep * (double)done, hstep, m, done + m == nsteps ? 1 : 0));
+      if (nsteps > chunk) {
+        if (!h->chunk_ev[k & 1]) ODX_CUDA(h, cudaEventCreateWithFlags(&h->chunk_ev[k & 1], cudaEventDisableTiming));
+        ODX_CUDA(h, cudaEventRecord(h->chunk_ev[k & 1], h->stream));
+      }
+      done += m;
+    }
+    *t = t0 + hstep * (double)done;
     return ODX_SUCCESS;
   }
   for (int64_t s = 0; s < nsteps; s++) {
+    if (h->abort_req) break;
     ODX_TRY(chain_step(h, method == ODX_METH_FE ? 1 : 4, *t, hstep, s == nsteps - 1));
     *t += hstep;
   }
   return ODX_SUCCESS;
 }
+
+void odx_request_abort(odx_handle *h) { if (h) h->abort_req = 1; }
+int odx_abort_requested(const odx_handle *h) { return h ? h->abort_req : 0; }
+void odx_clear_abort(odx_handle *h) { if (h) h->abort_req = 0; }
 
 int odx_evolve_reset(odx_handle *h) { h->ev_count = 0; h->k1_valid = false; return ODX_SUCCESS; }
 int odx_evolve_stats(odx_handle *h, uint64_t *count, uint64_t *failed_steps, uint64_t *rhs_evals) {

@@ -90,7 +90,33 @@ def build(force=False, verbose=False):
         os.remove(local)
         if verbose:
             print("built", exe)
+        # the drop-in test artefact: the same model.c linked against the reference with the B200 branch added to a COPY of
+        # methods_odexp.c (integration/apply_gpu_branch.py) + integration/odexp_gpu_branch.c -> model_gpu.out.  It runs the GPU
+        # branch when ODEXP_CUDA_MODEL names the model library, and the unchanged CPU path otherwise.
+        if name in DROPIN_FIXTURES:
+            gobjs = dropin_objects(force)
+            run(["gcc"] + CFLAGS + ["-I" + os.path.join(d, ".odexp"), os.path.join(d, ".odexp", "model.c")]
+                + [o for o in objs if not o.endswith(os.sep + "methods_odexp.o")] + gobjs + ["-lm", "-ldl", "-o", os.path.join(d, "model_gpu.out")])
     return True
+
+
+DROPIN_FIXTURES = ("kuramoto", "lineage", "nbody", "vdp_sde")
+ROOT = os.path.dirname(HERE)
+
+
+def dropin_objects(force=False):
+    """methods_odexp.c with the GPU branch inserted (a copy under oracle/_ref/obj) + the branch itself (product source)"""
+    gen = os.path.join(OUT, "obj", "methods_odexp_gpu.c")
+    script = os.path.join(ROOT, "integration", "apply_gpu_branch.py")
+    branch = os.path.join(ROOT, "integration", "odexp_gpu_branch.c")
+    src = os.path.join(REF, "src", "methods_odexp.c")
+    o1, o2 = os.path.join(OUT, "obj", "methods_odexp_gpu.o"), os.path.join(OUT, "obj", "odexp_gpu_branch.o")
+    newest = max(os.path.getmtime(f) for f in (script, branch, src, os.path.join(ROOT, "include", "odx.h")))
+    if force or not (os.path.exists(o1) and os.path.exists(o2)) or min(os.path.getmtime(o1), os.path.getmtime(o2)) < newest:
+        run([sys.executable, script, src, gen, "--diff", os.path.join(OUT, "odesolver_gpu.patch")])
+        run(["gcc"] + CFLAGS + ["-c", gen, "-o", o1])
+        run(["gcc"] + CFLAGS + ["-I" + os.path.join(ROOT, "include"), "-c", branch, "-o", o2])
+    return [o1, o2]
 
 
 if __name__ == "__main__":

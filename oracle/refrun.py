@@ -29,7 +29,11 @@ def traj_dtype(ncol_doubles):
     return np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (ncol_doubles,))])
 
 
-def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False, timeout=3600, read_traj=True):
+def have_dropin(fixture):
+    return os.path.isfile(os.path.join(REFDIR, fixture, "model_gpu.out"))
+
+
+def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False, timeout=3600, read_traj=True, exe="model.out", extra_env=None):
     """Run fixture with option overrides.  dims = dict(nvar,naux,npsi,nmfd,nexpr) to decode traj.dat.
     Returns dict(stats=..., traj=..., solver_ms=..., total_ms=..., function_ms=..., stdout=..., rand=...)."""
     src = os.path.join(REFDIR, fixture)
@@ -58,8 +62,9 @@ def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False
         env = dict(os.environ)
         if rand_log:
             env["ODX_RAND_LOG"] = os.path.join(work, "rand.log")
+        env.update(extra_env or {})
         # unbuffered stdout: the timing line would otherwise be lost in the reference's exit-time SIGSEGV
-        cmd = ([shutil.which("stdbuf"), "-o0"] if shutil.which("stdbuf") else []) + [os.path.join(src, "model.out")]
+        cmd = ([shutil.which("stdbuf"), "-o0"] if shutil.which("stdbuf") else []) + [os.path.join(src, exe)]
         r = subprocess.run(cmd, cwd=work, env=env, stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, timeout=timeout)
         # quiet mode ends in the reference's teardown pclose(NULL) SIGSEGV (src/main.c:1739) AFTER outputs are closed.
@@ -81,6 +86,9 @@ def run(fixture, opts=None, timespan=None, dims=None, keep=False, rand_log=False
             res["quick"] = np.fromfile(qp, dtype="<f8").reshape(-1, 3)
         if rand_log and os.path.exists(env["ODX_RAND_LOG"]):
             res["rand"] = np.fromfile(env["ODX_RAND_LOG"], dtype="<i4")
+        dp = (extra_env or {}).get("ODEXP_CUDA_DUMP_POP")
+        if dp and os.path.exists(os.path.join(work, dp) if not os.path.isabs(dp) else dp):
+            res["pop_dump"] = open(os.path.join(work, dp) if not os.path.isabs(dp) else dp, "rb").read()
         if keep:
             res["workdir"] = work
         return res

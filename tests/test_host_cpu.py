@@ -214,6 +214,24 @@ def test_library_exports_full_abi(model_lib):
     assert lib.dims() == dict(nvar=1, nexpr=1, naux=2, npsi=0, nmfd=3)
 
 
+def test_library_exports_reference_entry_points(model_lib):
+    """every model library also exports the reference's own stepper entry points by name (src/methods_odexp.h:47-63), as declared
+    in include/odx_compat.h; ncumsum needs no device and is checked against its definition (src/methods_odexp.c:1764-1777)"""
+    lib = model_lib("kuramoto")
+    hdr = open(os.path.join(ROOT, "include", "odx_compat.h")).read()
+    decl = hdr.split("} odx_gsl_system;")[1].split("\n", 2)[2]        # the prototypes after the two typedefs
+    decl = re.sub(r"/\*.*?\*/", "", decl, flags=re.S)
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", decl)) - {"defined", "visibility"}
+    assert declared == {"odx_compat_bind", "odx_compat_last_rows", "fe_apply", "iteration_apply", "dde_apply", "SSA_timestep",
+                        "SSA_apply_birthdeath", "tau_leaping_apply_birthdeath", "ncumsum"}
+    for s_ in declared:
+        assert hasattr(lib.lib, s_), s_
+    x = (ctypes.c_double * 5)(0.5, 1.5, 0.0, 2.0, 1.0)
+    tot = ctypes.c_double()
+    assert lib.lib.ncumsum(x, 5, ctypes.byref(tot)) == 0
+    assert tot.value == 5.0 and list(x) == [0.1, 0.4, 0.4, 0.8, 1.0]
+
+
 def test_no_gpu_fails_loudly(model_lib):
     import torch
     if torch.cuda.is_available():
