@@ -442,10 +442,17 @@ def main():
     w0 = time.perf_counter()
     pop.upload_ptr(n_local, y_pin.data_ptr(), e_pin.data_ptr())
     pop.run_fixed("dde", 0.0, H_STEP, args.steps)
+    pop.sync()
+    w1 = time.perf_counter()
     fin = pop.download()
+    w2 = time.perf_counter()
     barrier()
     sess_s = _max_over_ranks(time.perf_counter() - w0, world)
     sess_bytes = (int(n_local * 16), int(sum(v.nbytes for v in fin.values())))
+    dl_gbs = sess_bytes[1] / (w2 - w1) / 1e9
+    w3 = time.perf_counter()
+    fin = pop.download(out=fin)                 # the same download into buffers whose pages exist already
+    dl_gbs_warm = sess_bytes[1] / (time.perf_counter() - w3) / 1e9
     del fin, y_pin, e_pin
 
     peak, how = peaks()
@@ -468,7 +475,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(n_local * 16), "d2h_bytes_per_step": int(8 * lib.nmfd),
                         "steps": ne2e, "what": "odx_pop_upload(host theta, omega) + odx_run_fixed(dde, 1 step) + odx_meanfields per step"},
                 "e2e_session": {"value": n_total * args.steps / sess_s, "unit": "particle-steps/s", "steps": args.steps, "h2d_bytes_total": sess_bytes[0],
-                                "d2h_bytes_total": sess_bytes[1], "what": "one odx_pop_upload + odx_run_fixed(dde, %d steps) + one odx_pop_download (host wall clock)" % args.steps},
+                                "d2h_bytes_total": sess_bytes[1], "download_gb_per_s_rank0": dl_gbs, "download_gb_per_s_rank0_touched_buffers": dl_gbs_warm, "what": "one odx_pop_upload + odx_run_fixed(dde, %d steps) + one odx_pop_download (host wall clock)" % args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "frac_sustained": ALG_BYTES_PER_PARTICLE_STEP * n_local * extra / (ms_sus * 1e-3) / 1e9 / peak,

@@ -54,7 +54,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
                "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id", "odx_lowrank_order",
-               "odx_request_abort", "odx_abort_requested", "odx_clear_abort"]
+               "odx_request_abort", "odx_abort_requested", "odx_clear_abort", "odx_frame_begin", "odx_frame_end"]
 
 
 def _dp(a):
@@ -220,12 +220,15 @@ class Population:
         self._ck(self.L.odx_pop_find_id(self.h, int(pid), C.byref(pos)), "odx_pop_find_id")
         return pos.value
 
-    def download(self, first=0, count=None):
+    def download(self, first=0, count=None, out=None):
+        """host copies of the population columns (particle-major); out = the dict of a previous call of the same size, to reuse
+        its (already touched) buffers"""
         n = self.size()[0]
         count = n - first if count is None else count
         lb = self.lib
-        out = dict(y=np.empty((count, lb.nvar)), expr=np.empty((count, lb.nexpr)), aux=np.empty((count, lb.naux)),
-                   psi=np.empty((count, lb.npsi)), id=np.empty(count, dtype=np.int32), death=np.empty(count), repli=np.empty(count))
+        if out is None or len(out["id"]) != count:
+            out = dict(y=np.empty((count, lb.nvar)), expr=np.empty((count, lb.nexpr)), aux=np.empty((count, lb.naux)),
+                       psi=np.empty((count, lb.npsi)), id=np.empty(count, dtype=np.int32), death=np.empty(count), repli=np.empty(count))
         self._ck(self.L.odx_pop_download(self.h, first, count, _dp(out["y"]), _dp(out["expr"]), _dp(out["aux"]), _dp(out["psi"]),
                                          out["id"].ctypes.data_as(C.POINTER(C.c_int32)), _dp(out["death"]), _dp(out["repli"])),
                  "odx_pop_download")

@@ -12,9 +12,10 @@
  *               prefix-scan compaction that preserves list order, ids by exclusive scan on max_id, and the event rows
  *               reconstructed in sweep order from two more scans.  Draws are keyed Philox: (particle id, slot 0..2,
  *               stream = event index, domain LEAP), so the outcome does not depend on the traversal.
- *  SSA          one event per call.  The normalised cumulative sum over [death_0..N-1, repli_0..N-1, birth] and the linear
- *               search `while (u > r[k]) k++` are done on the host from the downloaded rate columns, in the reference's
- *               summation order, so the chosen event is identical to the reference for the same u; the list edit
+ *  SSA          one event per call.  The normalised cumulative sum over [death_0..N-1, repli_0..N-1, birth] and the search
+ *               `while (u > r[k]) k++` run on the device for keyed runs (k_ssa_tile_sums / k_ssa_pick: 16 bytes cross PCIe per
+ *               event); runs on the replayed serial stream do them on the host from the downloaded rate columns in the reference's
+ *               order of additions, so the chosen event is identical to the reference for the same u.  The list edit
  *               (delete / clone / append, initial conditions) runs on the device.
  */
 #pragma once
@@ -246,8 +247,74 @@ __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+/* ---- SSA event pick on the device (SSA_apply_birthdeath + ncumsum, src/methods_odexp.c:1556-1660, 1764-1777) ---------------
+ * The reference normalises the running sum of [death_0..N-1, repli_0..N-1, birth] by its total and takes the first index with
+ * u <= r[idx] (`while (u > r[idx]) idx++`).  Here: per-tile sums of the logical array (fixed-order tree inside a tile), one block
+ * that scans the tile sums, finds the tile and then the element with the same comparison u > cum / total.  The running sum is
+ * formed hierarchically, so it can differ from the serial one in the last bits: a different event only if u falls within
+ * round-off of a boundary.  Parity runs (replayed serial stream) therefore keep the host path, which reproduces the serial
+ * arithmetic exactly; keyed runs use this one: two 8-byte words cross PCIe instead of 2N doubles. */
+constexpr int SSA_TILE = 4096;
+__device__ __forceinline__ double ssa_elem(const double *__restrict__ death, const double *__restrict__ repli, int64_t N, double birth, int64_t i) {
+  return i < N ? death[i] : (i < 2 * N ? repli[i - N] : (i == 2 * N ? birth : 0.0));
+}
+__global__ void __launch_bounds__(BLOCK) k_ssa_tile_sums(const double *__restrict__ death, const double *__restrict__ repli, int64_t N, double birth,
+                                                          double *__restrict__ tile_sum) {
+  __shared__ double s_w[BLOCK / 32];
+  const int64_t base = (int64_t)blockIdx.x * SSA_TILE + (int64_t)threadIdx.x * (SSA_TILE / BLOCK);
+  double v = 0.0;
+#pragma unroll
+  for (int k = 0; k < SSA_TILE / BLOCK; k++) v += ssa_elem(death, repli, N, birth, base + k);
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < BLOCK / 32; w++) t += s_w[w]; tile_sum[blockIdx.x] = t; }
+}
+/* out[0] = chosen index (as a double-sized integer word), out[1] = total rate */
+__global__ void __launch_bounds__(BLOCK) k_ssa_pick(const double *__restrict__ death, const double *__restrict__ repli, int64_t N, double birth,
+                                                     const double *__restrict__ tile_sum, int ntiles, double u, long long *__restrict__ out_idx,
+                                                     double *__restrict__ out_total) {
+  __shared__ double s_total, s_prefix, s_thr[BLOCK];
+  __shared__ int s_tile;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int t = 0; t < ntiles; t++) tot += tile_sum[t];
+    int t = 0; double pre = 0.0;
+    if (tot > 0.0) {
+      while (t < ntiles - 1 && u > (pre + tile_sum[t]) / tot) { pre += tile_sum[t]; t++; }
+    }
+    s_total = tot; s_prefix = pre; s_tile = t;
+  }
+  __syncthreads();
+  const double tot = s_total;
+  if (!(tot > 0.0)) { if (threadIdx.x == 0) { *out_idx = -1; *out_total = tot; } return; }
+  constexpr int PER = SSA_TILE / BLOCK;
+  const int64_t base = (int64_t)s_tile * SSA_TILE + (int64_t)threadIdx.x * PER;
+  double x[PER], loc = 0.0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) { x[k] = ssa_elem(death, repli, N, birth, base + k); loc += x[k]; }
+  s_thr[threadIdx.x] = loc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    /* first thread whose running end reaches u, then the element inside it; the last logical element (2N) ends the search */
+    double cum = s_prefix; int th = 0;
+    const int64_t last = 2 * N;
+    while (th < BLOCK - 1 && u > (cum + s_thr[th]) / tot && (int64_t)s_tile * SSA_TILE + (int64_t)(th + 1) * PER <= last) { cum += s_thr[th]; th++; }
+    s_prefix = cum; s_tile = th;
+  }
+  __syncthreads();
+  if (threadIdx.x == s_tile) {
+    double cum = s_prefix; int k = 0;
+    while (k < PER - 1 && base + k < 2 * N && u > (cum + x[k]) / tot) { cum += x[k]; k++; }
+    long long idx = base + k;
+    if (idx > 2 * N) idx = 2 * N;
+    *out_idx = idx; *out_total = tot;
+  }
+}
+
 /* ---- host side -------------------------------------------------------------------------------------------------- */
 struct EventBufs {
+  double *ssa_tiles = nullptr; int64_t ssa_tiles_cap = 0; long long *ssa_out = nullptr;
   int32_t *outcome = nullptr, *flag = nullptr, *scan = nullptr, *tile = nullptr, *grand = nullptr, *child = nullptr, *f3 = nullptr, *s3 = nullptr;
   odx_event_row *rows = nullptr; int64_t rows_cap = 0;
   odx_event_row *rows_pin = nullptr; int64_t rows_pin_cap = 0;      /* pinned host copy of the event rows of the last sweep */
@@ -286,7 +353,7 @@ static void odx_events_free(odx_handle *h) {
   if (!h->ev_state) return;
   odx::EventBufs &b = h->ev_state->b;
   void *ptrs[] = {b.outcome, b.flag, b.scan, b.tile, b.grand, b.child, b.f3, b.s3, b.rows, b.alt.Y, b.alt.E, b.alt.AUX, b.alt.PSI,
-                  b.alt.DEATH, b.alt.REPLI, b.alt.ID};
+                  b.alt.DEATH, b.alt.REPLI, b.alt.ID, b.ssa_tiles, b.ssa_out};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (b.rows_pin) cudaFreeHost(b.rows_pin);
   delete h->ev_state;
@@ -545,20 +612,43 @@ int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {
   if (row) { row->n = (int32_t)N; row->stop_flag = 0; row->event[0] = row->event[1] = row->event[2] = 0; }
   double birth_rate = 0.0;
   ODX_TRY(odx_rates(h, nullptr, &birth_rate));
-  /* normalised cumulative sum and linear search exactly as SSA_apply_birthdeath / ncumsum (host, reference order) */
-  std::vector<double> r((size_t)(2 * N + 1));
-  if (N > 0) {
-    ODX_CUDA(h, cudaMemcpyAsync(r.data(), h->DEATH, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
-    ODX_CUDA(h, cudaMemcpyAsync(r.data() + N, h->REPLI, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
-    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
-  }
-  r[2 * N] = birth_rate;
-  for (int64_t i = 1; i < 2 * N + 1; i++) r[i] += r[i - 1];
-  const double sumr = r[2 * N];
-  for (int64_t i = 0; i < 2 * N + 1; i++) r[i] /= r[2 * N];
-  if (!(sumr > 0.0)) return ODX_SUCCESS;
   int64_t idx = 0;
-  while (u > r[idx]) idx++;
+  const bool on_device = (h->ssa_mode == 1) || (h->ssa_mode < 0 && !h->hr_seeded);
+  if (on_device) {
+    /* keyed runs: scan + search on the device (see k_ssa_pick), 16 bytes back */
+    const int ntiles = (int)((2 * N + 1 + SSA_TILE - 1) / SSA_TILE);
+    if (b.ssa_tiles_cap < ntiles) {
+      if (b.ssa_tiles) cudaFree(b.ssa_tiles);
+      b.ssa_tiles = nullptr; b.ssa_tiles_cap = 0;
+      ODX_CUDA(h, cudaMalloc((void **)&b.ssa_tiles, sizeof(double) * (size_t)(2 * ntiles + 16)));
+      b.ssa_tiles_cap = 2 * ntiles + 16;
+    }
+    if (!b.ssa_out) ODX_CUDA(h, cudaMalloc((void **)&b.ssa_out, 16));
+    k_ssa_tile_sums<<<ntiles, BLOCK, 0, h->stream>>>(h->DEATH, h->REPLI, N, birth_rate, b.ssa_tiles);
+    ODX_TRY(launch_check(h));
+    k_ssa_pick<<<1, BLOCK, 0, h->stream>>>(h->DEATH, h->REPLI, N, birth_rate, b.ssa_tiles, ntiles, u, b.ssa_out, (double *)(b.ssa_out + 1));
+    ODX_TRY(launch_check(h));
+    long long *pin = reinterpret_cast<long long *>(h->h_pin + NSLOT * NRED);
+    ODX_CUDA(h, cudaMemcpyAsync(pin, b.ssa_out, 16, cudaMemcpyDeviceToHost, h->stream));
+    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (pin[0] < 0) return ODX_SUCCESS;            /* total rate 0: nothing happens */
+    idx = (int64_t)pin[0];
+  } else {
+    /* replayed serial stream (parity runs): normalised cumulative sum and linear search exactly as SSA_apply_birthdeath / ncumsum
+     * (host, reference order of additions) */
+    std::vector<double> r((size_t)(2 * N + 1));
+    if (N > 0) {
+      ODX_CUDA(h, cudaMemcpyAsync(r.data(), h->DEATH, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+      ODX_CUDA(h, cudaMemcpyAsync(r.data() + N, h->REPLI, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+      ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    r[2 * N] = birth_rate;
+    for (int64_t i = 1; i < 2 * N + 1; i++) r[i] += r[i - 1];
+    const double sumr = r[2 * N];
+    for (int64_t i = 0; i < 2 * N + 1; i++) r[i] /= r[2 * N];
+    if (!(sumr > 0.0)) return ODX_SUCCESS;
+    while (u > r[idx]) idx++;
+  }
   const uint32_t stream = es->event_index;
   int64_t nbirth = 0;
   if (N > 0) { k_fill_i32<<<grid_for(h, N), BLOCK, 0, h->stream>>>(b.outcome, N, OUT_NONE); ODX_TRY(launch_check(h)); }

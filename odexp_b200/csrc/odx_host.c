@@ -35,6 +35,8 @@ typedef struct {
   double *y, *e, *aux, *psi;
   int32_t *ids;
   int64_t bufcap;
+  /* frames in flight (odx_frame_begin / odx_frame_end), oldest first */
+  int pend[2], npend;
 } out_state;
 
 /* fwrite_SIM (src/datastruct.c:643-653): t, meanfield[nmfd], N, stop_flag, event[3] */
@@ -97,8 +99,37 @@ static int write_quick_row(odx_handle *h, out_state *os, double t) {
   return 0;
 }
 
-/* fwrite_all_particles (src/datastruct.c:655-674): per particle: step, id, t, y, aux, psi, meanfield, expr */
+/* the oldest frame in flight: its records (assembled on the device in the file's byte layout) and its current.plot row go to the files */
+static int flush_frame(odx_handle *h, out_state *os) {
+  const void *rec = NULL; int64_t nrec = 0, recb = 0; double q[3]; int st;
+  if (os->npend == 0) return 0;
+  if ((st = odx_frame_end(h, os->pend[0], &rec, &nrec, &recb, q)) != 0) return st;
+  os->pend[0] = os->pend[1]; os->npend--;
+  if (os->fquick) fwrite(q, sizeof(double), 3, os->fquick);
+  if (os->ftraj && nrec > 0) fwrite(rec, (size_t)recb, (size_t)nrec, os->ftraj);
+  return 0;
+}
+static int flush_frames(odx_handle *h, out_state *os) {
+  int st;
+  while (os->npend > 0) if ((st = flush_frame(h, os)) != 0) return st;
+  return 0;
+}
+/* fwrite_quick + fwrite_all_particles (src/methods_odexp.c:1353-1436, src/datastruct.c:655-674) without stalling the integration:
+ * the frame is snapshotted and copied by the device asynchronously, written when the next one is started or at the next flush */
+static int write_traj_frame_sync(odx_handle *h, out_state *os, double t, int stride);
 static int write_traj_frame(odx_handle *h, out_state *os, double t, int stride) {
+  int st, ticket = 0;
+  if (os->nmfd > 24) return write_traj_frame_sync(h, os, t, stride);
+  if (os->npend == 2 && (st = flush_frame(h, os)) != 0) return st;
+  if ((st = odx_frame_begin(h, os->nbrsteps, t, (os->ftraj && stride > 0) ? stride : 0, os->mfd, os->fquick != NULL, os->ngx, os->ngy, os->ngz,
+                            os->cp, &ticket)) != 0) return st;
+  os->pend[os->npend++] = ticket;
+  os->nbrsteps++;
+  return 0;
+}
+
+/* the synchronous form (models with more mean fields than the record kernel takes by value) */
+static int write_traj_frame_sync(odx_handle *h, out_state *os, double t, int stride) {
   int64_t n = 0, m, i;
   int st;
   if ((st = write_quick_row(h, os, t)) != 0) return st;          /* fwrite_quick precedes fwrite_all_particles at every call site */
@@ -259,6 +290,8 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
         steps++; particle_steps += (double)n_step;
         if (hstep < o->hmin) hstep = o->hmin;
       }
+      /* the interval's steps are queued: write the frames that have landed while the GPU works */
+      if (status == ODX_SUCCESS && (status = flush_frames(h, &os)) != 0) stop_flag = ODX_EVENT_GSL;
       if (odx_abort_requested(h)) stop_flag = ODX_EVENT_ABORT;   /* the SIGINT handler's EVENT_TYPE = EVENT_ABORT (:23-30) */
       if (t >= t1) stop_flag = ODX_EVENT_TFINAL;
       if (odx_meanfields(h, os.mfd) != 0 && status == 0) status = ODX_ECUDA;
@@ -302,6 +335,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   if (status == ODX_SUCCESS) status = odx_sync(h);
 
 done:
+  { int st2 = flush_frames(h, &os); if (status == ODX_SUCCESS) status = st2; }
   if (os.fstats) fclose(os.fstats);
   if (os.ftraj) fclose(os.ftraj);
   if (os.fquick) fclose(os.fquick);

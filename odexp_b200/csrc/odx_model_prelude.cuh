@@ -209,7 +209,7 @@ template <class C> ODX_HD int odx_stopif(C &c, int cond) { if (cond) c.stop = 1;
 
 /* device twins of the pure helpers a model expression may call (src/utils_odexp.c:11-107) */
 ODX_HD double sum(const double *array, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += array[i]; return s; }
-ODX_HD double sumsub(const double *array, long *ind, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += array[ind[i]]; return s; }
+ODX_HD double sumsub(const double *array, const long *ind, long len)      /* const: a `decl const long idx[]` array is the usual argument */ { double s = 0.0; for (long i = 0; i < len; i++) s += array[ind[i]]; return s; }
 ODX_HD double sumstep(const double *array, long len, long step) { double s = 0.0; for (long i = 0; i < len; i += step) s += array[i]; return s; }
 ODX_HD double prod(const double *array, long len) { double s = 1.0; for (long i = 0; i < len; i++) s *= array[i]; return s; }
 ODX_HD double dotprod(const double *x, const double *y, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += x[i] * y[i]; return s; }

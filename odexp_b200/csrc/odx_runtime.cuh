@@ -48,9 +48,11 @@ using namespace odx;
 
 struct odx_event_state;
 static void odx_events_free(odx_handle *h);
+static void odx_output_free(odx_handle *h);
 
 struct odx_handle {
   odx_event_state *ev_state = nullptr;       /* birth / death scratch (odx_events.cuh), allocated on first use */
+  void *out = nullptr;                       /* output path state (odx_output.cuh), allocated on first use */
   odx_handle *replica = nullptr;             /* multi-GPU birth/death: whole ordered population, rebuilt per sweep */
   void *gcol = nullptr; int64_t gcol_cap = 0;
   int device = 0;
@@ -84,6 +86,7 @@ struct odx_handle {
   unsigned long long *ll_words = nullptr;     /* LL exchange words of the persistent kernel (zero-initialised) */
   int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
   int coop_blocks_tma = 0, tma_mode = -1;     /* tma_mode: -1 choose by size, 0 never, 1 always (option "tma") */
+  int ssa_mode = -1;                          /* SSA event pick: -1 device for keyed runs / host for replayed ones, 0 host, 1 device (option "ssa_device") */
   int lean_mode = -1;                         /* lean RK4 scheme: -1 with the TMA ring (HBM-resident populations), 0 never, 1 whenever eligible (option "lean") */
   double l2_bytes = 0.0;
   uint32_t epoch = 0;
@@ -737,20 +740,15 @@ static int upload_cols(odx_handle *h, const double *aos, double *soa, int ncol, 
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
   return ODX_SUCCESS;
 }
+static int d2h_pipelined(odx_handle *h, void *dst, const void *src_dev, size_t bytes);      /* odx_output.cuh */
 static int download_cols(odx_handle *h, const double *soa, double *aos, int ncol, int64_t n, int64_t first) {
   if (ncol == 0 || n == 0 || aos == nullptr) return ODX_SUCCESS;
-  if (ncol == 1) {
-    ODX_CUDA(h, cudaMemcpyAsync(aos, soa + first, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
-    ODX_CUDA(h, cudaStreamSynchronize(h->stream));
-    return ODX_SUCCESS;
-  }
+  if (ncol == 1) return d2h_pipelined(h, aos, soa + first, sizeof(double) * n);      /* already in host layout */
   const size_t bytes = sizeof(double) * (size_t)ncol * n;
   ODX_TRY(ensure_stage(h, bytes));
   k_soa_to_aos<<<h->sm_count * 4, 256, 0, h->stream>>>(soa, h->stage_dev, ncol, n, h->cap, first);
   ODX_TRY(launch_check(h));
-  ODX_CUDA(h, cudaMemcpyAsync(aos, h->stage_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
-  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
-  return ODX_SUCCESS;
+  return d2h_pipelined(h, aos, h->stage_dev, bytes);
 }
 
 }  // namespace odx
@@ -823,6 +821,7 @@ void odx_destroy(odx_handle *h) {
   if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
   odx_events_free(h);
+  odx_output_free(h);
   if (h->replica) { odx_destroy(h->replica); h->replica = nullptr; cudaSetDevice(h->device); }
   if (h->gcol) cudaFree(h->gcol);
   if (h->lr_plan) cudaFree(h->lr_plan);
@@ -860,6 +859,7 @@ int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "lean") == 0) { h->lean_mode = (int)value; return ODX_SUCCESS; }
+  if (strcmp(name, "ssa_device") == 0) { h->ssa_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }
   if (strcmp(name, "lrabstol") == 0) { h->lr_abstol = value; return ODX_SUCCESS; }
@@ -998,9 +998,9 @@ int odx_pop_download(odx_handle *h, int64_t first, int64_t count, double *y, dou
   ODX_TRY(download_cols(h, h->E, expr, NEXPR, count, first));
   ODX_TRY(download_cols(h, h->AUX, aux, NAUX, count, first));
   ODX_TRY(download_cols(h, h->PSI, psi, NPSI, count, first));
-  if (ids && count) ODX_CUDA(h, cudaMemcpyAsync(ids, h->ID + first, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream));
-  if (death_rate && count) ODX_CUDA(h, cudaMemcpyAsync(death_rate, h->DEATH + first, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
-  if (repli_rate && count) ODX_CUDA(h, cudaMemcpyAsync(repli_rate, h->REPLI + first, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  if (ids && count) ODX_TRY(d2h_pipelined(h, ids, h->ID + first, sizeof(int32_t) * count));
+  if (death_rate && count) ODX_TRY(d2h_pipelined(h, death_rate, h->DEATH + first, sizeof(double) * count));
+  if (repli_rate && count) ODX_TRY(d2h_pipelined(h, repli_rate, h->REPLI + first, sizeof(double) * count));
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
   return ODX_SUCCESS;
 }
@@ -1392,3 +1392,4 @@ int odx_tauleap_apply_view(odx_handle *h, double t, double dt, uint64_t leap_ind
 }  // extern "C"
 
 #include "odx_events.cuh"
+#include "odx_output.cuh"

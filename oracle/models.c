@@ -152,6 +152,63 @@ static void fb_ic(orc_ctx *c, double t, double *y, double *e) {
   for (i = 0; i < 3; ++i) y[i] = 2*orc_rand01(c) - 1;
 }
 
+/* ---------------------------------------------------------------- helper_calls.pop (LET NW 4): the helper functions of src/utils_odexp.c
+ * restated next to their call sites: sumsub :23-33, sumstep :35-45, sum3 :47-69, prod :71-84, conv :99-111, minus / plus / identity
+ * :113-126, sumxy :132-143, kern :149-160 */
+static const double hc_pars[] = {1.5, 0.3};
+static const long hc_pick[] = {0, 2, 3};
+static double hc_sumsub(const double *array, const long *ind, long len) { double s = 0.0; long i; for (i = 0; i < len; i++) s += array[ind[i]]; return s; }
+static double hc_sumstep(const double *array, long len, long step) { double s = 0.0; long i; for (i = 0; i < len; i += step) s += array[i]; return s; }
+static double hc_sum3(const double *array, long d1, long d2, long d3, long dim) {
+  double s = 0.0; long i, j, k; long n[3];
+  n[0] = d1; n[1] = d2; n[2] = d3; n[dim - 1] = 1;
+  for (i = 0; i < n[0]; i++) for (j = 0; j < n[1]; j++) for (k = 0; k < n[2]; k++) s += array[i + d2 * j + d3 * k];
+  return s;
+}
+static double hc_prod(const double *array, long len) { double p = 1.0; long i; for (i = 0; i < len; i++) p *= array[i]; return p; }
+static double hc_conv(const double *u, const double *v, long len) { double s = 0.0; long i; for (i = 0; i < len; i++) s += u[len - 1 - i] * v[i]; return s; }
+static double hc_minus(double x, double y) { return x - y; }
+static double hc_plus(double x, double y) { return x + y; }
+static double hc_identity(double x) { return x; }
+static double hc_sumxy(long len, double (*f)(double), double (*g)(double, double), const double *x, const double yi) {
+  double s = 0.0; long j; for (j = 0; j < len; j++) s += f(g(x[j], yi)); return s;
+}
+static double hc_kern(const double *Wi, double (*f)(double, double, double *), double xi, const double *x, double *p, long len) {
+  double s = 0.0; long j; for (j = 0; j < len; j++) s += Wi[j] * f(xi, x[j], p); return s;
+}
+static double hc_kf(double xi, double xj, double *p) { return p[0]*exp(-p[1]*(xi-xj)*(xi-xj)); }
+static void hc_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double a = c->mu[0], b = c->mu[1], MB = mfd[0];
+  double w[4], q[2], X[4], sxy[4], kn[4], s_sub, s_step, s_3, p_all, cv; size_t i;
+  (void)t; (void)psi; (void)death; (void)repli;
+  for (i = 0; i < 4; ++i) w[i] = e[i];
+  for (i = 0; i < 2; ++i) q[i] = e[4 + i];
+  for (i = 0; i < 4; ++i) X[i] = y_[i];
+  s_sub = hc_sumsub(X, hc_pick, 3);
+  s_step = hc_sumstep(X, 4, 2);
+  s_3 = hc_sum3(X, 2, 2, 1, 1);
+  p_all = hc_prod(w, 4);
+  cv = hc_conv(X, w, 4);
+  for (i = 0; i < 4; ++i) sxy[i] = hc_sumxy(4, hc_identity, hc_minus, X, X[i]);
+  for (i = 0; i < 4; ++i) kn[i] = hc_kern(w, hc_kf, X[i], X, q, 4);
+  for (i = 0; i < 4; ++i) f[i] = -a*X[i] + b*hc_plus(sxy[i], kn[i])/4 + 0.01*(s_sub + s_step + s_3)*p_all + 0.1*MB;
+  aux[0] = s_sub; aux[1] = s_step; aux[2] = s_3; aux[3] = p_all; aux[4] = cv;
+  for (i = 0; i < 4; ++i) aux[5 + i] = sxy[i];
+  for (i = 0; i < 4; ++i) aux[9 + i] = kn[i];
+}
+static double hc_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)y; (void)e; (void)mfd;
+  return aux[4];                                         /* %M MB MA(cv) */
+}
+static void hc_ic(orc_ctx *c, double t, double *y, double *e) {
+  size_t i;
+  (void)t;
+  for (i = 0; i < 4; ++i) e[i] = 0.5 + orc_rand01(c);
+  for (i = 0; i < 2; ++i) e[4 + i] = 0.2*(i+1);
+  for (i = 0; i < 4; ++i) y[i] = 2*orc_rand01(c) - 1;
+}
+
 /* ---------------------------------------------------------------- kuramoto_lrexp.pop (LET N 200): unweighted %C ... lrexp */
 static const double kle_pars[] = {0.8};
 static void kle_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -465,6 +522,7 @@ static const orc_model MODELS[] = {
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 6, 5, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
+  {"helper_calls", 4, 6, 13, 0, 1, 2, hc_pars, hc_rhs, hc_mfd, NULL, NULL, hc_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},

@@ -228,3 +228,35 @@ def test_lineage_sister_macros(model_lib, meth, ssahmin, ps, seed):
     assert gen.max() >= 2, "case must contain second-generation daughters"
     compare(out, ref)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [1, 7, 2047, 2048, 2049, 100003])
+def test_ssa_pick_device_equals_host(model_lib, n):
+    """the SSA event pick on the device (tile sums + one search block, 16 bytes back) chooses the same event as the host form
+    that restates ncumsum + `while (u > r[k]) k++` in the reference's order (src/methods_odexp.c:1596, 1764-1777), over uniforms
+    that hit the death range, the replication range, the birth entry and both ends"""
+    from odexp_b200 import capi
+    lib = model_lib("vdp_sde")
+    pops = []
+    for dev in (0, 1):
+        p = capi.Population(lib, capacity=n + 256)
+        p.set_option("ssa_device", dev)
+        p.init(n, replay=False, seed=21)
+        t = p.run_fixed("fe", 0.0, 0.01, 30)            # spread x around 0 so that the replication rates b*(x > 0) differ
+        p.rhs(t)
+        pops.append(p)
+    us = [0.0, 1e-300, 1e-9, 0.013, 0.25, 0.49999, 0.5, 0.731, 0.9, 0.99, 0.999999, 1.0 - 1e-16, 1.0]
+    rng = np.random.default_rng(3)
+    us += list(rng.random(12))
+    for u in us:
+        ra = pops[0].ssa_apply(t, u)
+        rb = pops[1].ssa_apply(t, u)
+        assert ra == rb, (u, ra, rb)
+        assert pops[0].size() == pops[1].size()
+        for p in pops:
+            p.rhs(t)
+    da, db = pops[0].download(), pops[1].download()
+    np.testing.assert_array_equal(da["id"], db["id"])
+    np.testing.assert_array_equal(da["y"], db["y"])
+    for p in pops:
+        p.close()

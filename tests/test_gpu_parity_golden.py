@@ -282,6 +282,7 @@ def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
 
 
 @pytest.mark.parametrize("name,rtol,atol", [("chain_array_dde_n20", 1e-10, 1e-13), ("fun_block_rkf45_n21", 1e-10, 1e-12),
+                                            ("helper_calls_dde_n12", 1e-10, 1e-13), ("helper_calls_rkck_n9", 1e-9, 1e-12),
                                             ("pair_aux_dde_n30", 1e-10, 1e-12), ("nbody_const_rkf45", 1e-8, 1e-10),
                                             ("lowrank_aux_dde_n100", 1e-10, 1e-9), ("lrexp_dde_n200", 1e-10, 1e-9)])
 def test_model_language_fixtures_against_reference_outputs(model_lib, name, rtol, atol):

@@ -230,3 +230,49 @@ def test_lean_scheme_large_steps_take_exact_path(model_lib):
         pop.close()
     np.testing.assert_allclose(res["ring-stored"], res["plain-stored"], rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(res["ring-lean"], res["plain-stored"], rtol=1e-12, atol=1e-12)
+
+
+def test_large_download_through_the_pinned_ring(model_lib):
+    """odx_pop_download of a population large enough for the pipelined path (pinned chunk ring + host copy threads): every column
+    equals what the strided gather (a different code path) returns for the same particles, and a full frame assembled on the
+    device (odx_frame_begin / odx_frame_end) carries the same values in traj.dat's record layout"""
+    import ctypes as C
+    from odexp_b200 import capi
+    lib = model_lib("kuramoto")
+    n = (1 << 22) + 12345
+    pop = capi.Population(lib, capacity=n)
+    pop.init(n, replay=False, seed=9)
+    t = pop.run_fixed("dde", 0.0, 0.05, 3)
+    pop.rhs(t)
+    full = pop.download()
+    m, step = 5000, 839
+    y = np.empty((m, 1)); e = np.empty((m, 1)); aux = np.empty((m, 2)); psi = np.empty((m, 0)); ids = np.empty(m, dtype=np.int32)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.lib.odx_pop_download_strided(pop.h, 0, step, m, dp(y), dp(e), dp(aux), dp(psi), ids.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    sel = np.arange(m) * step
+    np.testing.assert_array_equal(full["y"][sel], y)
+    np.testing.assert_array_equal(full["expr"][sel], e)
+    np.testing.assert_array_equal(full["aux"][sel], aux)
+    np.testing.assert_array_equal(full["id"][sel], ids)
+    np.testing.assert_array_equal(full["id"], np.arange(n, dtype=np.int32))
+    # one frame in the file's layout: {u32 step, i32 id, f64 t, y, aux[2], mfd[3], expr}
+    L = lib.lib
+    L.odx_frame_begin.argtypes = [C.c_void_p, C.c_uint, C.c_double, C.c_int64, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.odx_frame_end.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    mfd = pop.meanfields()
+    tick = C.c_int()
+    assert L.odx_frame_begin(pop.h, 7, t, 64, dp(np.ascontiguousarray(mfd)), 1, -1, 0, 5, 0, C.byref(tick)) == 0
+    rec, nrec, recb, q = C.c_void_p(), C.c_int64(), C.c_int64(), (C.c_double * 3)()
+    assert L.odx_frame_end(pop.h, tick.value, C.byref(rec), C.byref(nrec), C.byref(recb), q) == 0
+    dt = np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (7,))])
+    assert recb.value == dt.itemsize and nrec.value == (n + 63) // 64
+    fr = np.frombuffer(C.string_at(rec, nrec.value * recb.value), dtype=dt)
+    s64 = np.arange(nrec.value) * 64
+    assert np.all(fr["step"] == 7) and np.all(fr["t"] == t)
+    np.testing.assert_array_equal(fr["id"], full["id"][s64])
+    np.testing.assert_array_equal(fr["cols"][:, 0], full["y"][s64, 0])
+    np.testing.assert_array_equal(fr["cols"][:, 1:3], full["aux"][s64])
+    np.testing.assert_array_equal(fr["cols"][:, 3:6], np.tile(mfd, (nrec.value, 1)))
+    np.testing.assert_array_equal(fr["cols"][:, 6], full["expr"][s64, 0])
+    assert q[0] == t and q[1] == full["y"][0, 0] and q[2] == mfd[2]       # current.plot row: T, theta of particle 0, third mean field
+    pop.close()

@@ -11,7 +11,7 @@ from conftest import load_golden
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
                 "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3",
                 "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "nbody_const_rkf45", "lowrank_aux_dde_n100",
-                "lrexp_dde_n200", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
+                "lrexp_dde_n200", "helper_calls_dde_n12", "helper_calls_rkck_n9", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -55,6 +55,9 @@ REF_CASES = [
     ("nbody_const", {"meth": "rkf45", "h0": 0.1, "res": 11, "ps": 3, "abstol": 1e-8, "reltol": 1e-8, "hmin": 0}, (0, 20)),
     ("nbody_const", {"meth": "rk8pd", "h0": 0.1, "res": 5, "ps": 3, "abstol": 1e-10, "reltol": 1e-10, "hmin": 0}, (0, 20)),
     ("nbody_const", {"meth": "dde", "h0": 0.05, "res": 5, "ps": 3, "hmin": 0, "abstol": 1e-8, "reltol": 1e-8}, (0, 2)),
+    # the helper functions of src/utils_odexp.c (sumsub, sumstep, sum3, prod, conv, minus, plus, identity, sumxy, kern)
+    ("helper_calls", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 17, "hmin": 1e-5}, (0, 1.5)),
+    ("helper_calls", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 5, "hmin": 1e-5}, (0, 1.5)),
     # array dynamical / auxiliary / expression entries (`dX[i=0:NC]/dt`, `aux sq[i=0:NC]`), MA() of a scalar aux fed by an array
     ("chain_array", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 20, "hmin": 1e-5}, (0, 3)),
     ("chain_array", {"meth": "rkck", "h0": 0.05, "res": 4, "ps": 33, "hmin": 1e-5}, (0, 3)),
