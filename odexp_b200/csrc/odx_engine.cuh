@@ -900,6 +900,25 @@ __device__ __forceinline__ unsigned long long ll_load_sys(const unsigned long lo
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+#ifndef PERSIST_MAX_CTAS_N
+#define PERSIST_MAX_CTAS_N 256
+#endif
+constexpr int PERSIST_MAX_CTAS = PERSIST_MAX_CTAS_N;
+constexpr size_t PF_BYTES = TMA_SMEM + 128;
+/* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
+ * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence
+ * or separate flag round trip is needed (the LL idea of NCCL's small-message protocol).  Every CTA publishes its
+ * block partials as such words, every CTA polls the words of all CTAs and adds the partials itself in a fixed order
+ * (identical bits everywhere, no atomics).  Buffers alternate with the epoch parity: a CTA is one epoch ahead at most.
+ * Three CTA barriers per stage: [A] warp partials in shared memory (warp 0 alone then forms and publishes the block partial),
+ * [B] all words of all CTAs in shared memory, [C] the totals in s_tot.  Warp k adds value k over the CTAs (lane-strided, then a
+ * shuffle tree: one fixed order) and, across GPUs, exchanges it with the peers itself: CTA 0's warp k stores the rank
+ * total as LL words straight into every peer's mailbox over NVLink, warp k of EVERY CTA polls the peers' words in this GPU's
+ * mailbox and adds the rank totals in rank order -- no further barrier, only the NVLink latency.
+ * Used by the plain (L2-resident, latency-sensitive) variant: 4.4 instead of 5.2 us per stage with one tile per CTA, 50.8 instead of
+ * 55.5 us per step at 2^21 particles.  The ring variant keeps the older eight-barrier form below: inlined there, the shuffle trees
+ * and poll loops of this one raised the register pressure of its 80-register stage sweeps (432 bytes of spills, 0.326 -> 0.347 ms
+ * per step at 2^24), and out of line the call itself cost more (0.40 ms). */
 /* block sum of red[] into shared s_bp[NRED] */
 template <int NT>
 __device__ __forceinline__ void block_partial_smem(const double (&red)[NRED], double *s_bp) {
@@ -940,14 +959,72 @@ __device__ __forceinline__ void block_total(const double (&acc)[NRED], double *s
   }
   cta_sync<NT>();
 }
-#ifndef PERSIST_MAX_CTAS_N
-#define PERSIST_MAX_CTAS_N 256
-#endif
-constexpr int PERSIST_MAX_CTAS = PERSIST_MAX_CTAS_N;
-#ifndef PEER_POLL_ALL
-#define PEER_POLL_ALL 1
-#endif
-constexpr size_t PF_BYTES = TMA_SMEM + 128;
+struct ExchangeArgs {          /* the few fields of PersistArgs the exchange needs, by value (a reference to the kernel parameter block
+                                  would be copied to the stack) */
+  unsigned long long *ll_part, *mail_ll; unsigned long long *const *peer_ll;      /* peer_ll: this CTA's shared-memory copy of the peer mailboxes */
+  int *abort_flag; int rank, nranks;
+};
+template <int NTC, bool PF_ON>
+__device__ __forceinline__ void stage_exchange(const double (&red)[NRED], const ExchangeArgs &g, uint32_t epoch, double *s_tot,
+                                            double (*s_wp)[NRED], uint32_t *s_words, uint64_t *s_go) {
+  const size_t par = (size_t)(epoch & 1u);
+  const uint32_t tag = epoch + 1u;
+  unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
+  constexpr int NW = NTC / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    const double v = warp_sum(red[k]);
+    if (lane == 0) s_wp[warp][k] = v;
+  }
+  cta_sync<NTC>();                                         /* [A] */
+  if (PF_ON && threadIdx.x == 0) mbar_arrive(s_go);     /* every consumer has stored (and fenced) this stage */
+  if (warp == 0) {
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < NRED; k++) {
+      double v = (lane < NW) ? s_wp[lane][k] : 0.0;
+      v = warp_sum(v);
+      v = __shfl_sync(0xffffffffu, v, 0);
+      if ((lane >> 1) == k) mine = v;
+    }
+    if (lane < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + lane, ll_pack(mine, lane & 1, tag));
+  }
+  for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
+    unsigned long long w; unsigned long long spins = 0;
+    while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
+    s_words[idx] = (uint32_t)w;
+  }
+  cta_sync<NTC>();                                         /* [B] */
+  for (int k = warp; k < NRED; k += NW) {
+    double a = 0.0;
+    for (unsigned int b2 = lane; b2 < gridDim.x; b2 += 32) a += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
+    a = warp_sum(a);
+    if (g.nranks > 1) {
+      a = __shfl_sync(0xffffffffu, a, 0);
+      const int r = lane >> 1, half = lane & 1;
+      uint32_t w32 = 0;
+      if (lane < 2 * g.nranks && r != g.rank) {
+        if (blockIdx.x == 0) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + 2 * k + half, ll_pack(a, half, tag));
+        unsigned long long w; unsigned long long spins = 0;
+        while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + 2 * k + half)) >> 32) != tag) {
+          if (spin_give_up(spins, g.abort_flag)) break;
+        }
+        w32 = (uint32_t)w;
+      }
+      double tot = 0.0;
+      for (int q = 0; q < g.nranks; q++) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, w32, 2 * q), hi = __shfl_sync(0xffffffffu, w32, 2 * q + 1);
+        tot += (q == g.rank) ? a : ll_unpack(lo, hi);
+      }
+      a = tot;
+    }
+    if (lane == 0) s_tot[k] = a;
+  }
+  cta_sync<NTC>();                                         /* [C] */
+}
+
+
 /* PF_ON: the TMA-ring variant (768 threads, HBM-resident populations); otherwise plain 128-bit loads (1024 threads), which is
  * faster while the working set sits in L2 (measured crossover: 5-6 M Kuramoto particles per GPU) */
 #ifndef PERSIST_TMA_CTAS_PER_SM
@@ -955,7 +1032,7 @@ constexpr size_t PF_BYTES = TMA_SMEM + 128;
 #endif
 template <bool PF_ON>
 __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CTAS_PER_SM : ((1024 / PT_LD < 1) ? 1 : 1024 / PT_LD)) k_chain_persist(Pop p, PersistArgs g) {
-  __shared__ double s_tot[NRED], s_bp[NRED];
+  __shared__ double s_tot[NRED], s_bp[NRED], s_wp[(PF_ON ? TMA_CONS : PT_LD) / 32][NRED];
   __shared__ uint32_t s_words[PERSIST_MAX_CTAS * LLW];
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ __align__(8) uint64_t s_full[TMA_MAXBUF], s_empty[TMA_MAXBUF], s_go;
@@ -974,6 +1051,13 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
 #pragma unroll
   for (int k = 0; k < A1(NMFD); k++) mfd0[k] = 0.0;
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
+  __shared__ unsigned long long *s_peer[MAX_RANKS];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < MAX_RANKS; r++) s_peer[r] = g.peer_ll[r];
+  }
+  ExchangeArgs xa;
+  xa.ll_part = g.ll_part; xa.mail_ll = g.mail_ll; xa.peer_ll = s_peer; xa.abort_flag = g.abort_flag; xa.rank = g.rank; xa.nranks = g.nranks;
   if (USE_SCTAB) odx_sct_fill();
   __syncthreads();
   /* role by warp index, broadcast from lane 0 so that the compiler knows the branch is warp-uniform */
@@ -1012,7 +1096,7 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
       if (M::HAS_VECT_MFD) M::mfd_vect((NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu, p.n_global, mfd);
       const bool last_stage = (s == g.nst - 1);
       if (last_stage && step == g.nsteps - 1 && blockIdx.x == 0 && threadIdx.x < NRED) g.sums_report[threadIdx.x] = s_tot[threadIdx.x];
-      cta_sync<NTC>();
+      /* no barrier here: s_tot is rewritten only behind barriers [A] and [B] of this stage's exchange */
       ChainArgs a;
       a.sums_in = nullptr; a.h = g.h; a.eval_index = eval; eval += 2; a.reverse = (int)(epoch & 1u);
       a.recon = 0.0; a.skip_acc_store = 0; a.iterate = g.iterate;
@@ -1045,67 +1129,42 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
         chain_sweep<false, true, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       }
-      /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
-       * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence
-       * or separate flag round trip is needed (the LL idea of NCCL's small-message protocol).  Every CTA publishes its
-       * block partials as such words, every CTA polls the words of all CTAs and adds the partials itself in a fixed order
-       * (identical bits everywhere, no atomics).  Buffers alternate with the epoch parity: a CTA is one epoch ahead at most. */
-      const size_t par = (size_t)(epoch & 1u);
-      const uint32_t tag = epoch + 1u;
-      unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
-      block_partial_smem<NTC>(red, s_bp);
-      if (PF_ON && threadIdx.x == 0) mbar_arrive(&s_go);     /* every consumer has stored (and fenced) this stage */
-      if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
-      for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
-        unsigned long long w; unsigned long long spins = 0;
-        while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
-        s_words[idx] = (uint32_t)w;
-      }
-      cta_sync<NTC>();
-      {
-        double acc[NRED];
-#pragma unroll
-        for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-        for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += NTC) {
-#pragma unroll
-          for (int k = 0; k < NRED; k++) acc[k] += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
+      if (!PF_ON) {
+        stage_exchange<NTC, PF_ON>(red, xa, epoch, s_tot, s_wp, s_words, &s_go);
+      } else {
+        /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
+         * {32 data bits, 32-bit epoch tag}: an 8-byte store is atomic, so data and "ready" flag arrive together and no fence
+         * or separate flag round trip is needed (the LL idea of NCCL's small-message protocol).  Every CTA publishes its
+         * block partials as such words, every CTA polls the words of all CTAs and adds the partials itself in a fixed order
+         * (identical bits everywhere, no atomics).  Buffers alternate with the epoch parity: a CTA is one epoch ahead at most. */
+        const size_t par = (size_t)(epoch & 1u);
+        const uint32_t tag = epoch + 1u;
+        unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
+        block_partial_smem<NTC>(red, s_bp);
+        if (PF_ON && threadIdx.x == 0) mbar_arrive(&s_go);     /* every consumer has stored (and fenced) this stage */
+        if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
+        for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
+          unsigned long long w; unsigned long long spins = 0;
+          while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
+          s_words[idx] = (uint32_t)w;
         }
-        block_total<NTC>(acc, s_tot);
-      }
-      if (g.nranks > 1) {
-        /* cross-GPU: CTA 0 stores this rank's sums as LL words straight into every peer's mailbox over NVLink (8-byte
-         * st.relaxed.sys on IPC-mapped pointers), polls the words of the other ranks in its own GPU's mailbox, adds the rank
-         * sums in rank order and republishes the global sums to the other CTAs of this GPU, again as LL words */
-#if PEER_POLL_ALL
-        /* every CTA polls the peers' words itself (no local republish hop) */
-        if (blockIdx.x == 0 && threadIdx.x < LLW) {
-          const unsigned long long w = ll_pack(s_tot[threadIdx.x >> 1], threadIdx.x & 1, tag);
-          for (int r = 0; r < g.nranks; r++)
-            if (r != g.rank) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + threadIdx.x, w);
-        }
-        if (threadIdx.x < (unsigned)(g.nranks * LLW)) {
-          const int r = threadIdx.x / LLW, k = threadIdx.x % LLW;
-          if (r != g.rank) {
-            unsigned long long w; unsigned long long spins = 0;
-            while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + k)) >> 32) != tag) {
-              if (spin_give_up(spins, g.abort_flag)) break;
-            }
-            s_words[threadIdx.x] = (uint32_t)w;
+        cta_sync<NTC>();
+        {
+          double acc[NRED];
+  #pragma unroll
+          for (int k = 0; k < NRED; k++) acc[k] = 0.0;
+          for (unsigned int b2 = threadIdx.x; b2 < gridDim.x; b2 += NTC) {
+  #pragma unroll
+            for (int k = 0; k < NRED; k++) acc[k] += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
           }
+          block_total<NTC>(acc, s_tot);
         }
-        cta_sync<NTC>();
-        if (threadIdx.x < NRED) {
-          double v = 0.0;
-          for (int r = 0; r < g.nranks; r++)
-            v += (r == g.rank) ? s_tot[threadIdx.x] : ll_unpack(s_words[r * LLW + 2 * threadIdx.x], s_words[r * LLW + 2 * threadIdx.x + 1]);
-          s_bp[threadIdx.x] = v;
-        }
-        cta_sync<NTC>();
-        if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
-#else
-        unsigned long long *gt = g.ll_gtot + par * LLW;
-        if (blockIdx.x == 0) {
-          if (threadIdx.x < LLW) {
+        if (g.nranks > 1) {
+          /* cross-GPU: CTA 0 stores this rank's sums as LL words straight into every peer's mailbox over NVLink (8-byte
+           * st.relaxed.sys on IPC-mapped pointers), polls the words of the other ranks in its own GPU's mailbox, adds the rank
+           * sums in rank order and republishes the global sums to the other CTAs of this GPU, again as LL words */
+          /* every CTA polls the peers' words itself (no local republish hop) */
+          if (blockIdx.x == 0 && threadIdx.x < LLW) {
             const unsigned long long w = ll_pack(s_tot[threadIdx.x >> 1], threadIdx.x & 1, tag);
             for (int r = 0; r < g.nranks; r++)
               if (r != g.rank) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + threadIdx.x, w);
@@ -1129,18 +1188,8 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
           }
           cta_sync<NTC>();
           if (threadIdx.x < NRED) s_tot[threadIdx.x] = s_bp[threadIdx.x];
-          if (threadIdx.x < LLW) ll_store_gpu(gt + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
-        } else {
-          if (threadIdx.x < LLW) {
-            unsigned long long w; unsigned long long spins = 0;
-            while ((uint32_t)((w = ll_load_gpu(gt + threadIdx.x)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
-            s_words[threadIdx.x] = (uint32_t)w;
-          }
           cta_sync<NTC>();
-          if (threadIdx.x < NRED) s_tot[threadIdx.x] = ll_unpack(s_words[2 * threadIdx.x], s_words[2 * threadIdx.x + 1]);
         }
-#endif
-        cta_sync<NTC>();
       }
       epoch++;
     }
