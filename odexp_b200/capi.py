@@ -25,7 +25,7 @@ class ModelInfo(C.Structure):
                 ("rhs_uses_rng", C.c_int), ("has_pairwise", C.c_int), ("has_lowrank", C.c_int),
                 ("var_names", C.POINTER(C.c_char_p)), ("expr_names", C.POINTER(C.c_char_p)), ("aux_names", C.POINTER(C.c_char_p)),
                 ("psi_names", C.POINTER(C.c_char_p)), ("mfd_names", C.POINTER(C.c_char_p)), ("par_names", C.POINTER(C.c_char_p)),
-                ("par_defaults", C.POINTER(C.c_double)), ("has_stopif", C.c_int)]
+                ("par_defaults", C.POINTER(C.c_double)), ("has_stopif", C.c_int), ("ndelay", C.c_int)]
 
 
 class EventRow(C.Structure):
@@ -54,7 +54,7 @@ ABI_SYMBOLS = ["odx_model", "odx_create", "odx_destroy", "odx_last_error", "odx_
                "odx_draw_poisson", "odx_odesolver", "odx_event_record", "odx_event_elapsed_ms", "odx_launch_count",
                "odx_set_option", "odx_peer_export", "odx_peer_attach", "odx_comm_rank", "odx_iteration_apply",
                "odx_pop_download_strided", "odx_tauleap_apply_view", "odx_pop_find_id", "odx_lowrank_order",
-               "odx_request_abort", "odx_abort_requested", "odx_clear_abort", "odx_frame_begin", "odx_frame_end"]
+               "odx_request_abort", "odx_abort_requested", "odx_clear_abort", "odx_frame_begin", "odx_frame_end", "odx_set_event_type"]
 
 
 def _dp(a):
@@ -77,6 +77,7 @@ class ModelLib:
         L.odx_sync.argtypes = [H]
         L.odx_set_params.argtypes = [H, C.POINTER(C.c_double), C.c_int]
         L.odx_set_seed.argtypes = [H, C.c_uint64]
+        L.odx_set_event_type.argtypes = [H, C.c_int, C.c_double]
         L.odx_set_tolerances.argtypes = [H, C.c_double, C.c_double]
         L.odx_set_option.argtypes = [H, C.c_char_p, C.c_double]
         L.odx_peer_export.argtypes = [H, C.c_void_p]

@@ -63,7 +63,34 @@ constexpr bool SCTAB_MODEL = (M::NHINT > 0) && !ODX_NO_SCTAB;      /* table-assi
 /* ------------------------------------------------------------------------------------------------
  * evaluation context handed to the generated model code
  * ---------------------------------------------------------------------------------------------- */
+/* history stacks of one delay() call site (src/odexp.h:151-162: DELAY_SSTACK samples of (t, x) and the write position), one per
+ * particle that the site indexes.  Sample s of stack q lives at [s * K + q]: the particles of a warp advance in lock step, so their
+ * pushes and most probes of their searches touch consecutive addresses. */
+constexpr int DELAY_SSTACK = 1000;
+struct DelayView { double *T, *X; int *pos; long K; };
+
 struct DevCtx {
+  const DelayView *dl;      /* [NDELAY] */
+  /* interp() on the circular stack (src/utils_odexp.c:173-203), index arithmetic as coded: start = pos + 1, the samples are read at
+   * (start + i) % DELAY_SSTACK.  idx outside the declared array: the reference reads foreign memory; here NaN. */
+  ODX_HD double delay_lookup(int k, double xi, long idx) const {
+#if defined(__CUDA_ARCH__)
+    const DelayView v = dl[k];
+    if (idx < 0 || idx >= v.K) return __longlong_as_double(0x7ff8000000000000LL);
+    const int nx = DELAY_SSTACK, start = v.pos[idx] + 1;
+    int i1 = 0, i9 = nx - 1;
+    while (i9 > i1 + 1) {
+      const int i5 = (i1 + i9 + 1) / 2;
+      if (v.T[(long)((start + i5) % nx) * v.K + idx] > xi) i9 = i5; else i1 = i5;
+    }
+    const double x1 = v.T[(long)((i1 + start) % nx) * v.K + idx], y1 = v.X[(long)((i1 + start) % nx) * v.K + idx];
+    if (i1 == i9) return y1;
+    const double x9 = v.T[(long)((i9 + start) % nx) * v.K + idx], y9 = v.X[(long)((i9 + start) % nx) * v.K + idx];
+    return y1 + (y9 - y1) * (xi - x1) / (x9 - x1);
+#else
+    (void)k; (void)xi; (void)idx; return 0.0;
+#endif
+  }
   const double *mu;
   double pop_size;          /* POP_SIZE */
   double h;                 /* *SIM->h (DWDT = randN(0,1)/sqrt(h), src/odexp.h:384) */
@@ -104,6 +131,7 @@ struct HostCtx {
   const double *mu; double pop_size; double h; HostRand *hr; int32_t id, oid; int atbirth, atrepli, ist0;
   const double *sis_y, *sis_e, *sis_aux; int has_sister; int stop; int slow;
   ODX_HD double ky(int, long) const { return 0.0; }      /* not reachable: KY is rejected inside initial conditions */
+  ODX_HD double delay_lookup(int, double, long) const { return 0.0; }      /* not reachable: delay() is rejected there too */
   ODX_HD double rand01() { return hr->rand01(); }
   ODX_HD double randN(double m, double s) { return hr->randN(m, s); }
   ODX_HD double exprand(double r) { return hr->exprand(r); }
@@ -127,6 +155,7 @@ struct Pop {
   double muv[MUV_N];        /* the parameters by value: kernel-argument (constant bank) operands instead of a load per use */
   uint32_t k0, k1;          /* Philox key */
   int *stop;                /* sticky STOPIF flag of the whole population (models with STOPIF only) */
+  DelayView dl[A1(M::NDELAY)];      /* history stacks of the delay() call sites */
 };
 
 struct Red {                /* grid reduction scratch */
@@ -220,6 +249,7 @@ __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stre
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
   c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   c.ky_base = nullptr; c.ky_i = 0; c.ky_n = 1; c.ky_stride = 0;
+  c.dl = p.dl;
   return c;
 }
 template <bool TAB>
@@ -1488,6 +1518,53 @@ __global__ void __launch_bounds__(BLOCK) k_err_doubling(Pop p, const double *__r
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_down_sync(0xffffffffu, rloc, o); if (other > rloc) rloc = other; }
   if ((threadIdx.x & 31) == 0) atomicMax(rmax_bits, (unsigned long long)__double_as_longlong(rloc));
+}
+
+/* delay(): the side effects of the call sites, carried out between evaluations (src/utils_odexp.c:205-240).
+ * k_delay_fill: `if (EVENT_TYPE && EVENT_T0)` -- a logical AND, true while ANY event flag is set (t0, a pending stopping time or
+ *   birth / death event): the whole history is rewritten from the history function, sample s at t - (DELAY_SSTACK - s) h, pos = DELAY_SSTACK.
+ * k_delay_push: the first evaluation of a dde step (DELAY_FIRST_EVAL, src/methods_odexp.c:1842-1844) appends (t, x) -- once per ode_rhs
+ *   call, and pop_rhs calls ode_rhs twice per particle: two identical samples. */
+__global__ void __launch_bounds__(BLOCK) k_delay_fill(Pop p, const double *__restrict__ ysrc, double t, double hstep) {
+  const int64_t total = p.n * DELAY_SSTACK;
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < total; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = q % p.n; const int sl = (int)(q / p.n);
+    double y[A1(NVAR)], e[A1(NEXPR)];
+    load_cols<NVAR>(ysrc, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    DevCtx c = make_ctx(p, hstep, 0, DOM_RHS, p.ID[i]);
+#pragma unroll
+    for (int k = 0; k < M::NDELAY; k++) {
+      double tt, xx; long idx;
+      M::delay_sample(c, k, t, y, e, tt, xx, idx);
+      if (idx < 0 || idx >= p.dl[k].K) continue;
+      const double ti = tt - (double)(DELAY_SSTACK - sl) * hstep;
+      p.dl[k].T[(long)sl * p.dl[k].K + idx] = ti;
+      p.dl[k].X[(long)sl * p.dl[k].K + idx] = M::delay_ic(k, ti);
+      if (sl == 0) p.dl[k].pos[idx] = DELAY_SSTACK;
+    }
+  }
+}
+__global__ void __launch_bounds__(BLOCK) k_delay_push(Pop p, const double *__restrict__ ysrc, double t) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    double y[A1(NVAR)], e[A1(NEXPR)];
+    load_cols<NVAR>(ysrc, p.stride, i, y);
+    load_cols<NEXPR>(p.E, p.stride, i, e);
+    DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, p.ID[i]);
+#pragma unroll
+    for (int k = 0; k < M::NDELAY; k++) {
+      double tt, xx; long idx;
+      M::delay_sample(c, k, t, y, e, tt, xx, idx);
+      if (idx < 0 || idx >= p.dl[k].K) continue;
+      int pos = p.dl[k].pos[idx];
+      for (int twice = 0; twice < 2; twice++) {
+        pos = (pos + 1) % DELAY_SSTACK;
+        p.dl[k].T[(long)pos * p.dl[k].K + idx] = tt;
+        p.dl[k].X[(long)pos * p.dl[k].K + idx] = xx;
+      }
+      p.dl[k].pos[idx] = pos;
+    }
+  }
 }
 
 /* AoS <-> SoA transposes for upload / download (host arrays are particle-major like the reference's y[]) */

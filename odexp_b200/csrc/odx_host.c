@@ -229,8 +229,10 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
     }
     /* init_mode 1 / 2: the caller has uploaded the population (opt init 1: the state the previous run left in SIM->pop) */
   }
-  /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364) */
+  /* first RHS evaluation fills aux / psi / mean fields / rates (methods_odexp.c:364); EVENT_TYPE is EVENT_T0 while it runs */
+  odx_set_event_type(h, stop_flag, hstep);
   if ((status = odx_rhs(h, t)) != 0) goto done;
+  odx_set_event_type(h, ODX_EVENT_NONE, hstep);
   if ((status = odx_meanfields(h, os.mfd)) != 0) goto done;
   if (mi->has_stopif) odx_stop_flag(h, NULL);      /* EVENT_TYPE = EVENT_NONE after the initial evaluation (:380) */
   odx_pop_size(h, NULL, &n, NULL);
@@ -269,6 +271,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
       const double c0 = now_ms();
       while (t < tnext) {
         const int64_t n_step = n;
+        if (mi->ndelay) odx_set_event_type(h, stop_flag, hstep);      /* what delay() sees: a pending stopping time / event flag */
         if (o->method == ODX_METH_ITERATION) {
           status = odx_iteration_apply(h, &t, 1);
         } else if (o->method == ODX_METH_FE || o->method == ODX_METH_DDE) {
@@ -315,6 +318,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
       }
       odx_pop_size(h, NULL, &n, NULL);
       if (n > 0) {
+        if (mi->ndelay) odx_set_event_type(h, stop_flag, hstep);
         if ((status = odx_rhs(h, t)) != 0) break;                 /* methods_odexp.c:687 */
         if ((status = odx_meanfields(h, os.mfd)) != 0) break;
       }
@@ -324,6 +328,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
     }
     if (stop_flag & (ODX_STOP_COND | ODX_STOP_TSPAN)) {            /* reset the dynamical variables (:704-714) */
       if ((status = odx_pop_reinit(h, t, o->replay_ic)) != 0) break;
+      if (mi->ndelay) odx_set_event_type(h, stop_flag, hstep);
       if ((status = odx_rhs(h, t)) != 0) break;
       if ((status = odx_meanfields(h, os.mfd)) != 0) break;
       if ((status = write_traj_frame(h, &os, t, o->traj_stride)) != 0) break;
@@ -331,6 +336,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
     if (stop_flag & ODX_STOP_TSPAN) nextstop = (idx_stop < nstops) ? tstops[idx_stop++] : INFINITY;
     if (mi->has_stopif) odx_stop_flag(h, NULL);                     /* EVENT_TYPE = EVENT_NONE */
     stop_flag = ODX_EVENT_NONE;
+    if (mi->ndelay) odx_set_event_type(h, stop_flag, hstep);
   }
   if (status == ODX_SUCCESS) status = odx_sync(h);
 

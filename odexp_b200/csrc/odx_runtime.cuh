@@ -99,6 +99,9 @@ struct odx_handle {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t launches = 0;
   volatile int abort_req = 0;                 /* odx_request_abort (SIGINT) */
+  /* delay(): history stacks per call site, EVENT_TYPE and *SIM->h as the model code sees them (odx_set_event_type) */
+  double *dl_T[A1(M::NDELAY)] = {}, *dl_X[A1(M::NDELAY)] = {}; int *dl_pos[A1(M::NDELAY)] = {};
+  int event_type = 0; double event_h = 0.0;
   cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   HostRand hr; bool hr_seeded = false; uint32_t host_draws = 0;   /* serial stream of the host loop (replay mode) */
   std::string err;
@@ -124,7 +127,26 @@ static inline Pop pop_view(const odx_handle *h) {
   p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
   p.stop = reinterpret_cast<int *>(h->counter + 8);
   for (int k = 0; k < MUV_N; k++) p.muv[k] = (k < NPAR) ? h->h_mu[k] : 0.0;
+  for (int k = 0; k < A1(M::NDELAY); k++) { p.dl[k].T = h->dl_T[k]; p.dl[k].X = h->dl_X[k]; p.dl[k].pos = h->dl_pos[k]; p.dl[k].K = M::delay_count(k); }
   return p;
+}
+/* delay(): what the call sites do besides looking up, before the RHS evaluation at (t, ysrc): refill while an event flag is set,
+ * push at the first evaluation of a dde step (see k_delay_fill / k_delay_push) */
+static int launch_check(odx_handle *h);
+static int delay_before_eval(odx_handle *h, const double *ysrc, double t, double hstep, bool first_eval) {
+  if (M::NDELAY == 0 || h->n <= 0) return ODX_SUCCESS;
+  if (h->nranks > 1) { h->err = "delay() history stacks are not supported on a sharded population"; return ODX_EUNSUP; }
+  if (h->event_type != 0) {
+    int64_t g = (h->n * DELAY_SSTACK + BLOCK - 1) / BLOCK; if (g > 8 * h->grid_cap) g = 8 * h->grid_cap;
+    k_delay_fill<<<(unsigned)g, BLOCK, 0, h->stream>>>(pop_view(h), ysrc, t, hstep);
+    return launch_check(h);
+  }
+  if (first_eval) {
+    int64_t g = (h->n + BLOCK - 1) / BLOCK; if (g > h->grid_cap) g = h->grid_cap;
+    k_delay_push<<<(unsigned)g, BLOCK, 0, h->stream>>>(pop_view(h), ysrc, t);
+    return launch_check(h);
+  }
+  return ODX_SUCCESS;
 }
 static inline Red red_view(const odx_handle *h, int slot) {
   Red r; r.partial = h->partial; r.counter = h->counter; r.sums = h->sums + (size_t)slot * NRED; return r;
@@ -379,6 +401,7 @@ static inline const double *sums_ptr(const odx_handle *h, int slot) { return NEE
 
 /* generated pop_rhs once, with outputs (reference call sites methods_odexp.c:364, 687, 709) */
 static int eval_rhs_out(odx_handle *h, const double *ysrc, int sums_slot, double t, double hcur, double *fout) {
+  ODX_TRY(delay_before_eval(h, ysrc, t, hcur != 0.0 ? hcur : h->event_h, false));
   RhsArgs a; a.sums_in = sums_ptr(h, sums_slot); a.t = t; a.h = hcur; a.eval_index = h->eval_index; a.fout = fout;
   h->eval_index += 2; h->rhs_evals++;
   k_rhs_out<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(pop_view(h), ysrc, a, red_view(h, SLOT_RATES));
@@ -482,7 +505,8 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   return ODX_SUCCESS;
 }
 static inline bool can_persist(const odx_handle *h) {
-  return h->use_persistent && h->coop_ok && !M::HAS_PAIR && !M::HAS_LOWRANK && !M::USES_KY && (h->nranks == 1 || h->peers_attached);
+  /* delay(): the history is edited between evaluations, by kernels of their own */
+  return h->use_persistent && h->coop_ok && !M::HAS_PAIR && !M::HAS_LOWRANK && !M::USES_KY && M::NDELAY == 0 && (h->nranks == 1 || h->peers_attached);
 }
 static int alloc_cols(odx_handle *h, double **ptr, int ncol);
 /* models with KY(): neighbours read the stage state while the stage forms the next one, so nothing is updated in place */
@@ -508,6 +532,7 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + hh; a.a = hh; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1);
     if (M::USES_KY) p.Y_OUT = h->YS;              /* the new state goes to the other buffer, then the buffers change roles */
+    ODX_TRY(delay_before_eval(h, h->Y, t, hh, false));       /* fe_apply never sets DELAY_FIRST_EVAL: look-ups only */
     k_chain<true, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
     ODX_TRY(launch_check(h));
     if (M::USES_KY) { double *tmp = h->Y; h->Y = h->YS; h->YS = tmp; }
@@ -518,6 +543,7 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     ODX_TRY(compute_psi(h, h->Y, t));
     a.sums_in = sums_ptr(h, h->y_slot); a.t_eval = t; a.t_next = t + half; a.a = half; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1); a.skip_acc_store = h->use_recon;
+    ODX_TRY(delay_before_eval(h, h->Y, t, hh, true));        /* DELAY_FIRST_EVAL = 1 around k1 (src/methods_odexp.c:1842-1844) */
     k_chain<true, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 0));
     a.skip_acc_store = 0;
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 0));
@@ -525,6 +551,7 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     a.sums_in = sums_ptr(h, SLOT_STAGE + 0); a.t_eval = t + half; a.t_next = t + half; a.a = half; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1); a.recon = h->use_recon ? 1.0 / half : 0.0;
     if (M::USES_KY) p.YS_OUT = h->YALT;           /* y2 in YS is still read by the neighbours: y3 goes to the other buffer */
+    ODX_TRY(delay_before_eval(h, h->YS, t + half, hh, false));
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 1));
     a.recon = 0.0;
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 1));
@@ -532,12 +559,14 @@ static int chain_step(odx_handle *h, int nst, double t, double hh, int want_out,
     a.sums_in = sums_ptr(h, SLOT_STAGE + 1); a.t_eval = t + half; a.t_next = t + hh; a.a = hh; a.w = 2.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1);
     if (M::USES_KY) { p.YS = h->YALT; p.YS_OUT = h->YS; }
+    ODX_TRY(delay_before_eval(h, p.YS, t + half, hh, false));
     k_chain<false, false><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, SLOT_STAGE + 2));
     if (M::USES_KY) { p.YS = h->YS; p.YS_OUT = h->YS; }
     ODX_TRY(launch_check(h)); if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, SLOT_STAGE + 2));
     ODX_TRY(compute_psi(h, h->YS, t + hh));
     a.sums_in = sums_ptr(h, SLOT_STAGE + 2); a.t_eval = t + hh; a.t_next = t + hh; a.a = hh / 6.0; a.w = 1.0; a.eval_index = h->eval_index; h->eval_index += 2;
     a.reverse = (h->sweep_dir ^= 1);
+    ODX_TRY(delay_before_eval(h, h->YS, t + hh, hh, false));
     k_chain<false, true><<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, new_slot));
     ODX_TRY(launch_check(h));
     h->report_slot = SLOT_STAGE + 2; h->rhs_evals += 4;
@@ -651,6 +680,7 @@ static int embedded_attempt(odx_handle *h, const Tableau &T, double t, double hh
     /* KY(): neighbours read the stage state this kernel evaluates the RHS at, so the state it forms goes to the other buffer
      * (the stages alternate so that the last one leaves y_new in YS) */
     if (M::USES_KY) { const bool alt = ((nst - s) & 1) != 0; p.YS_OUT = alt ? h->YALT : h->YS; if (s > 1) a.ycur = alt ? h->YS : h->YALT; }
+    if (!a.skip_rhs) ODX_TRY(delay_before_eval(h, a.ycur, a.t_eval, hh, false));      /* the GSL steppers never push: look-ups (or refills) only */
     k_tab<<<g, BLOCK, 0, h->stream>>>(p, a, red_view(h, out_slot));
     ODX_TRY(launch_check(h));
     if (NEEDS_MOMENTS) ODX_TRY(post_reduce(h, out_slot));
@@ -796,6 +826,15 @@ int odx_create(odx_handle **out, int device, int64_t capacity) {
   ODX_TRY(alloc_cols(h, &h->E, NEXPR)); ODX_TRY(alloc_cols(h, &h->AUX, NAUX)); ODX_TRY(alloc_cols(h, &h->PSI, NPSI));
   ODX_TRY(alloc_cols(h, &h->DEATH, 1)); ODX_TRY(alloc_cols(h, &h->REPLI, 1));
   ODX_CUDA(h, cudaMalloc((void **)&h->ID, sizeof(int32_t) * h->cap));
+  for (int k = 0; k < M::NDELAY; k++) {       /* delay(): DELAY_SSTACK samples of (t, x) + the write position per declared stack */
+    const size_t K = (size_t)M::delay_count(k);
+    ODX_CUDA(h, cudaMalloc((void **)&h->dl_T[k], sizeof(double) * K * DELAY_SSTACK));
+    ODX_CUDA(h, cudaMalloc((void **)&h->dl_X[k], sizeof(double) * K * DELAY_SSTACK));
+    ODX_CUDA(h, cudaMalloc((void **)&h->dl_pos[k], sizeof(int) * K));
+    ODX_CUDA(h, cudaMemsetAsync(h->dl_T[k], 0, sizeof(double) * K * DELAY_SSTACK, h->stream));      /* a global `stack` is zero-initialised */
+    ODX_CUDA(h, cudaMemsetAsync(h->dl_X[k], 0, sizeof(double) * K * DELAY_SSTACK, h->stream));
+    ODX_CUDA(h, cudaMemsetAsync(h->dl_pos[k], 0, sizeof(int) * K, h->stream));
+  }
   ODX_CUDA(h, cudaMalloc((void **)&h->d_mu, sizeof(double) * A1(NPAR)));
   const odx_model_info *mi = odx_model();
   for (int k = 0; k < NPAR; k++) h->h_mu[k] = mi->par_defaults[k];
@@ -834,6 +873,7 @@ void odx_destroy(odx_handle *h) {
                     h->sums, h->stage_dev, h->gather, h->pair_part};
   for (double *b : bufs) if (b) cudaFree(b);
   if (h->ID) cudaFree(h->ID);
+  for (int k = 0; k < A1(M::NDELAY); k++) { if (h->dl_T[k]) cudaFree(h->dl_T[k]); if (h->dl_X[k]) cudaFree(h->dl_X[k]); if (h->dl_pos[k]) cudaFree(h->dl_pos[k]); }
   if (h->gather_id) cudaFree(h->gather_id);
   if (h->counter) cudaFree(h->counter);
   if (h->rmax) cudaFree(h->rmax);
@@ -905,6 +945,9 @@ int odx_set_params(odx_handle *h, const double *mu, int npar) {
   invalidate_state(h);
   return ODX_SUCCESS;
 }
+/* EVENT_TYPE (SIM->stop_flag, src/odexp.h:387-399) and *SIM->h as the model code sees them during the evaluations that follow: only
+ * delay() reads them (`if (EVENT_TYPE && EVENT_T0)` refills the history, src/utils_odexp.c:212-226) */
+int odx_set_event_type(odx_handle *h, int event_type, double hstep) { h->event_type = event_type; h->event_h = hstep; return ODX_SUCCESS; }
 int odx_set_seed(odx_handle *h, uint64_t seed) { h->k0 = (uint32_t)seed; h->k1 = (uint32_t)(seed >> 32); h->eval_index = 0; return ODX_SUCCESS; }
 int odx_set_tolerances(odx_handle *h, double eps_abs, double eps_rel) { h->eps_abs = eps_abs; h->eps_rel = eps_rel; return ODX_SUCCESS; }
 

@@ -341,11 +341,42 @@ class Emitter:
         self.mfd_idx = {e.name: i for i, e in enumerate(m.mfds)}
         self.psi_idx = {c.name: i for i, c in enumerate(m.cpls)}
         self.aux_idx = {e.name: m.index_of(m.auxs, e.name) for e in m.auxs}
+        self.delay_sites = []
         self.expr_base = {}
         k = 0
         for e in m.exprs:
             self.expr_base[e.name] = k
             k += max(1, e.length)
+
+    # ---- delay() call sites ----------------------------------------------------------------------
+    def _delay_site(self, args, where):
+        """register delay(t, x, tau, ic, &stack[idx]); returns (site, t expression, tau expression, stack index expression)"""
+        if len(args) != 5:
+            raise PopError("delay(t, x, tau, ic, &stack) takes five arguments (%s)" % where)
+        mm = re.match(r"^&\s*(%s)\s*(?:\[(.+)\])?$" % IDENT, args[4].strip())
+        stacks = dict(self.m.stacks)
+        if not mm or mm.group(1) not in stacks:
+            raise PopError("delay(): the last argument must be the address of a `decl stack` (%s)" % where)
+        name, idx = mm.group(1), (mm.group(2) or "0").strip()
+        if bool(mm.group(2)) != bool(stacks[name]):
+            raise PopError("delay(): `%s` is %s (%s)" % (name, "an array of stacks: index it" if stacks[name] else "a single stack", where))
+        if args[3] not in {f.name for f in self.m.funs}:
+            raise PopError("delay(): the history function '%s' must be a FUN of one argument (%s)" % (args[3], where))
+        forbidden = {x.name for x in self.m.auxs} | {x.name for x in self.m.mfds} | {x.name for x in self.m.cpls}
+        for a in (args[0], args[1], idx):
+            bad = set(re.findall(IDENT, a)) & forbidden
+            if bad or re.search(r"\b(MA|MF|MC|OY|OE|OA|KY|rand01|randN|DWDT)\b", a):
+                raise PopError("delay(): the time, the delayed value and the stack index may read t, dynamical variables, parametric expressions "
+                               "and parameters only (%s reads %s): in the reference the two ode_rhs passes of one evaluation would push different "
+                               "values" % (where, ", ".join(sorted(bad)) or "a macro"))
+        key = (args[0], args[1], args[3], name, idx)
+        for k, site in enumerate(self.delay_sites):
+            if site["key"] == key:
+                return k, args[0], args[2], idx
+            if site["stack"] == name:
+                raise PopError("delay(): the stack '%s' is used by two different call sites (%s)" % (name, where))
+        self.delay_sites.append(dict(key=key, t=args[0], x=args[1], ic=args[3], stack=name, idx=idx, count=max(1, stacks[name])))
+        return len(self.delay_sites) - 1, args[0], args[2], idx
 
     # ---- macro translation ---------------------------------------------------------------------
     def _macro(self, kind, name, where):
@@ -387,8 +418,15 @@ class Emitter:
             if exact or where.startswith("%M") or where.startswith("%C") or where.startswith("%BIRTH"):
                 raise PopError("KY() ring neighbours are only supported inside AUX / D/DT / %%DEATH / %%REPLI (%s)" % where)
             e = e[:b] + "odx_c.ky(%d, (%s))" % (self.var_idx[args[0]], args[1]) + e[en:]
-        if re.search(r"\b(delay|interp)\s*\(", e):
-            raise PopError("delay()/interp() history stacks are host-only (%s)" % where)
+        for b, en, args in list(_find_call(e, "delay"))[::-1]:
+            # delay(t, x, tau, ic, &stack[idx]) (src/utils_odexp.c:205-240): the lookup stays in the expression, the side effects (the
+            # fill of the history at t0 / while an event is pending, the push at the first evaluation of a dde step) are carried out by
+            # the engine between evaluations from the call site's description (delay_sample / delay_ic below)
+            if not (where.startswith("aux ") or where.startswith("d") or where == "rhs") or exact:
+                raise PopError("delay() is only supported inside AUX / D/DT expressions (%s)" % where)
+            e = e[:b] + "odx_c.delay_lookup(%d, (%s) - (%s), (long)(%s))" % self._delay_site(args, where) + e[en:]
+        if re.search(r"\binterp\s*\(", e):
+            raise PopError("interp() on user arrays is not supported on the device (%s)" % where)
         e = re.sub(r"\bDWDT\b", "odx_c.dwdt()", e)
         e = re.sub(r"\b(rand01|randN|exprand|poisson)\s*\(", lambda mm: "odx_c.%s(" % mm.group(1), e)
         e = re.sub(r"\bPOP_SIZE\b", "((int)odx_c.pop_size)", e)      # SIM->pop->size is an int in the reference (src/odexp.h): 1/POP_SIZE is 0
@@ -721,6 +759,53 @@ class Emitter:
             w("    odx_s[%d] = %s;" % (self.psi_idx[c.name], scales.get(c.name) or "1.0"))
         w("  }\n")
         # ---- initial conditions
+        # ---- delay() call sites: what the engine needs to carry out their side effects between evaluations
+        nd = len(self.delay_sites)
+        if nd and terms_use_aux:
+            raise PopError("delay() in a model whose %M terms read an auxiliary variable through MA() is not supported (the reference's first pass "
+                           "would look the history up before / after the push of the step)")
+        if nd and (m.birth or m.death or m.repli):
+            raise PopError("delay() together with %BIRTH / %DEATH / %REPLI is not supported (the history stacks are indexed by particle)")
+        w("  /* delay(t, x, tau, ic, &stack[idx]) call sites (src/utils_odexp.c:205-240): (time, value) pushed at the first evaluation of a dde")
+        w("   * step, the stack the particle uses, and the history function that fills the stack at t0 */")
+        w("  static constexpr int NDELAY = %d;" % nd)
+        w("  ODX_HD static constexpr long delay_count(int k) { return %s; }" %
+          (" : ".join(["k == %d ? %dL" % (k, st["count"]) for k, st in enumerate(self.delay_sites)] + ["1L"]) if nd else "1L"))
+        w("  template <class C> ODX_HD static void delay_sample(C &odx_c, int odx_k, double t, const double *odx_y, const double *odx_e,")
+        w("      double &odx_tt, double &odx_xx, long &odx_idx) {")
+        w("    (void)odx_c; (void)odx_k; (void)t; (void)odx_y; (void)odx_e; odx_tt = t; odx_xx = 0.0; odx_idx = 0;")
+        w("    ODX_CONSTS")
+        if nd:
+            for i, p in enumerate(m.pars):
+                if not re.search(r"\b(init|impl)", p.attr, flags=re.I):
+                    ctype = "double"
+                    mt = re.search(r"\b(int|long|double)\b", p.attr)
+                    if mt:
+                        ctype = mt.group(1)
+                    w("    const %s %s = (%s)odx_c.mu[%d]; (void)%s;" % (ctype, mangle(p.name), ctype, i, mangle(p.name)))
+            for e in m.exprs:
+                b = self.expr_base[e.name]
+                if e.length:
+                    w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
+                      (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
+                else:
+                    w("    const double %s = odx_e[%d]; (void)%s;" % (mangle(e.name), b, mangle(e.name)))
+            for e in m.eqs:
+                if e.length:
+                    w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_y[%d + odx_i];" %
+                      (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, self.var_idx[e.name]))
+                else:
+                    w("    const double %s = odx_y[%d]; (void)%s;" % (mangle(e.name), self.var_idx[e.name], mangle(e.name)))
+            for k, st in enumerate(self.delay_sites):
+                w("    if (odx_k == %d) { odx_tt = %s; odx_xx = %s; odx_idx = (long)(%s); }" %
+                  (k, self.tr(st["t"], "delay", exact=True), self.tr(st["x"], "delay", exact=True), self.tr(st["idx"], "delay", exact=True)))
+        w("  }")
+        w("  ODX_HD static double delay_ic(int odx_k, double odx_s) {")
+        w("    (void)odx_k; (void)odx_s;")
+        for k, st in enumerate(self.delay_sites):
+            w("    if (odx_k == %d) return %s(odx_s);" % (k, mangle(st["ic"])))
+        w("    return 0.0;")
+        w("  }\n")
         w("  /* ode_init_conditions: EXPR in file order, then INIT in file order (draw order matters for replay) */")
         w("  template <class C> ODX_HD static void ic(C &odx_c, double t, double *odx_y, double *odx_e) {")
         w("    (void)t; (void)odx_e;")
@@ -795,7 +880,7 @@ class Emitter:
         vals = ", ".join(repr(float(p.rhs)) for p in m.pars) or "0.0"
         w("    static const double pd[] = {%s};" % vals)
         w('    static const odx_model_info mi = {"%s", NVAR, NEXPR, NAUX, NPSI, NMFD, NPAR, HAS_BIRTH, HAS_DEATH, HAS_REPLI, RHS_RNG,' % m.name)
-        w("                                      HAS_PAIR, HAS_LOWRANK, vn, en, an, pn, mn, qn, pd, HAS_STOPIF};")
+        w("                                      HAS_PAIR, HAS_LOWRANK, vn, en, an, pn, mn, qn, pd, HAS_STOPIF, NDELAY};")
         w("    return mi;")
         w("  }")
         w("};\n")

@@ -65,6 +65,7 @@ class PopModel:
     options: Dict[str, str] = field(default_factory=dict)
     timespan: List[float] = field(default_factory=list)
     consts: List[Tuple[str, str, str, str]] = field(default_factory=list)      # (C type, name, "[..]" or "", initialiser)
+    stacks: List[Tuple[str, int]] = field(default_factory=list)                # `decl stack name[K]`: history stacks of delay() (name, K; K = 0: a scalar)
     base_dir: str = "."       # FILE tables are read relative to the model file
 
     # flattened dimensions (arrays count element-wise, as in the reference's nbr_expr etc.)
@@ -290,10 +291,20 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         # `decl const double a[] = {..}` is printed verbatim at file scope by the reference (add_declarations, src/odexp:660-674);
         # `const a[] {..}` is the older spelling the shipped examples/Nbody.pop still uses (declare_constant_array, src/odexp:643-658).
         # Only constant scalars / arrays are taken: they become constexpr locals of every generated function.
+        ms = re.match(r"^stack\s+(%s)\s*(?:\[\s*([^\]]+?)\s*\])?\s*;?\s*$" % IDENT, rest) if kwl.startswith("dec") else None
+        if ms:
+            # `decl stack hist[NP]`: printed verbatim at file scope by the reference; the history of one delay() call site per particle
+            # (src/odexp.h:151-162, src/utils_odexp.c:205-240)
+            try:
+                cnt = int(eval(ms.group(2), {"__builtins__": {}}, {})) if ms.group(2) else 0
+            except Exception:
+                raise PopError("line %d: the size of a `decl stack` array must be an integer constant" % lineno)
+            m.stacks.append((ms.group(1), cnt))
+            return
         mm = re.match(r"^(?:static\s+)?const\s+(double|int|long)\s+(%s)\s*((?:\[[^\]]*\])*)\s*=\s*(.+?);?\s*$" % IDENT, rest, flags=re.S) \
             if kwl.startswith("dec") else re.match(r"^()(%s)\s*((?:\[[^\]]*\])*)\s*=?\s*(.+?);?\s*$" % IDENT, rest, flags=re.S)
         if not mm:
-            raise PopError("line %d: only `decl const double|int|long name[..] = value` declarations are supported" % lineno)
+            raise PopError("line %d: only `decl const double|int|long name[..] = value` and `decl stack name[K]` declarations are supported" % lineno)
         if bool(mm.group(3)) != mm.group(4).strip().startswith("{"):
             raise PopError("line %d: a constant array needs a braced initialiser list, a constant scalar a single value" % lineno)
         m.consts.append((mm.group(1) or "double", mm.group(2), mm.group(3).replace(" ", ""), mm.group(4).strip()))

@@ -209,6 +209,28 @@ static void hc_ic(orc_ctx *c, double t, double *y, double *e) {
   for (i = 0; i < 4; ++i) y[i] = 2*orc_rand01(c) - 1;
 }
 
+/* ---------------------------------------------------------------- delay_pop.pop (LET NP 16): delay() with one history stack per particle */
+static const double dp_pars[] = {1.0, 2.0, 0.4};
+static orc_stack dp_hist[16];
+static double dp_x0(double s) { return 0.5 + 0.1*sin(s); }
+static void dp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double tau = c->mu[0], beta = c->mu[1], k = c->mu[2], gam = e[0], x = y_[0], XM = mfd[0];
+  const double xd = orc_delay(c, t, x, tau, dp_x0, &dp_hist[c->id]);
+  (void)psi; (void)death; (void)repli;
+  f[0] = beta*xd/(1 + xd*xd*xd*xd) - gam*x + k*(XM - x);
+  aux[0] = xd;
+}
+static double dp_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void dp_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = 0.8 + 0.4*orc_rand01(c);
+  y[0] = 0.5 + 0.2*orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- kuramoto_lrexp.pop (LET N 200): unweighted %C ... lrexp */
 static const double kle_pars[] = {0.8};
 static void kle_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -523,6 +545,7 @@ static const orc_model MODELS[] = {
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 6, 5, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"helper_calls", 4, 6, 13, 0, 1, 2, hc_pars, hc_rhs, hc_mfd, NULL, NULL, hc_ic, 0, 0, 0, 0, 0, NULL},
+  {"delay_pop", 1, 1, 1, 0, 1, 3, dp_pars, dp_rhs, dp_mfd, NULL, NULL, dp_ic, 0, 0, 0, 0, 0, NULL},
   {"chain_array", 6, 4, 6, 0, 2, 2, ca_pars, ca_rhs, ca_mfd, NULL, NULL, ca_ic, 0, 0, 0, 0, 0, NULL},
   {"nbody_const", 6, 0, 0, 3, 0, 2, nbc_pars, nb_rhs, NULL, NULL, nbc_cpl, nbc_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lowrank_aux", 1, 1 + 2 * LRA_R, 2, 1, 2, 1, klra_pars, klra_rhs, klra_mfd, NULL, NULL, klra_ic, LRA_R, 0, 1, 1, 1 + LRA_R, sin, NULL, NULL, 1},

@@ -184,6 +184,38 @@ double orc_ky(orc_ctx *c, int var, int degree) {
   if (j < 0) j += s->n;
   return s->p[j]->y[var];
 }
+/* interp and delay, src/utils_odexp.c:173-240, index arithmetic as coded: after the fill at t0 (`EVENT_TYPE && EVENT_T0`, a logical
+ * AND: true whenever any event flag is set) pos is DELAY_SSTACK, so the search starts one element late and the oldest sample
+ * sits at the logical end; a first evaluation of dde_apply pushes (t, x) -- once per ode_rhs call, i.e. twice per pop_rhs */
+double orc_interp(double *x, double *y, double xi, int nx, int start) {
+  int i1 = 0, i9 = nx - 1, i5;
+  while (i9 > i1 + 1) {
+    i5 = (i1 + i9 + 1) / 2;
+    if (x[(start + i5) % nx] > xi) i9 = i5; else i1 = i5;
+  }
+  if (i1 == i9) return y[(i1 + start) % nx];
+  return y[(i1 + start) % nx] + (y[(i9 + start) % nx] - y[(i1 + start) % nx])
+         * (xi - x[(i1 + start) % nx]) / (x[(i9 + start) % nx] - x[(i1 + start) % nx]);
+}
+double orc_delay(orc_ctx *c, const double t, const double x, const double tau, double (*ic)(double), orc_stack *xhist) {
+  double ti; const double h = *(c->sim->h);
+  if (c->sim->stop_flag && ORC_EVENT_T0) {
+    xhist->pos = 0;
+    while (xhist->pos < ORC_DELAY_SSTACK) {
+      ti = t - (ORC_DELAY_SSTACK - xhist->pos) * h;
+      xhist->t[xhist->pos] = ti;
+      xhist->array[xhist->pos] = ic(ti);
+      xhist->pos++;
+    }
+  } else if (c->sim->first_eval_flag) {
+    xhist->pos++;
+    xhist->pos %= ORC_DELAY_SSTACK;
+    xhist->t[xhist->pos] = t;
+    xhist->array[xhist->pos] = x;
+  }
+  return orc_interp(xhist->t, xhist->array, t - tau, ORC_DELAY_SSTACK, xhist->pos + 1);
+}
+
 int orc_pop_rhs(double t, const double *y_, double *f_, void *params) {
   orc_sim *s = params; const orc_model *m = s->model;
   int i, j, k; orc_ctx c;
@@ -242,7 +274,9 @@ static int orc_dde_apply(orc_sim *s, double *t, double tnext, double *h, double 
   double *k = malloc(sizeof(double) * dim * 5), *k1 = k + dim, *k2 = k1 + dim, *k3 = k2 + dim, *k4 = k3 + dim, dt = tnext - *t;
   int i;
   if (*h > (dt - s->o.hmin)) *h = dt;
+  s->first_eval_flag = 1;                 /* DELAY_FIRST_EVAL, src/methods_odexp.c:1842-1844 */
   orc_pop_rhs(*t, y, k1, s);
+  s->first_eval_flag = 0;
   for (i = 0; i < dim; i++) k[i] = y[i] + (*h) / 2.0 * k1[i];
   orc_pop_rhs(*t + *h / 2.0, k, k2, s);
   for (i = 0; i < dim; i++) k[i] = y[i] + (*h) / 2.0 * k2[i];

@@ -84,6 +84,7 @@ typedef struct orc_sim {
   int rng_mode; orc_hostrand hr; uint32_t k0, k1, eval_index, host_draws, event_index;
   uint64_t rhs_evals; int64_t steps; double particle_steps, function_ms;
   int lr_last_p; uint32_t reinit_index;
+  int first_eval_flag;                   /* DELAY_FIRST_EVAL = SIM->first_eval_flag: set by dde_apply around its first RHS evaluation */
 } orc_sim;
 void orc_lowrank_apply(orc_sim *s);
 
@@ -94,6 +95,11 @@ long   orc_poisson(orc_ctx *c, double lambda);
 double orc_dwdt(orc_ctx *c);
 int    orc_stopif(orc_ctx *c, int cond);      /* STOPIF(cond), src/odexp.h:400-406 */
 double orc_ky(orc_ctx *c, int var, int degree); /* KY(name, degree), src/odexp.h:334-357 */
+/* delay(): one history stack of DELAY_SSTACK samples (src/odexp.h:151-162), src/utils_odexp.c:173-240 */
+#define ORC_DELAY_SSTACK 1000
+typedef struct { double t[ORC_DELAY_SSTACK]; double array[ORC_DELAY_SSTACK]; int pos; } orc_stack;
+double orc_interp(double *x, double *y, double xi, int nx, int start);
+double orc_delay(orc_ctx *c, const double t, const double x, const double tau, double (*ic)(double), orc_stack *xhist);
 
 const orc_model *orc_find_model(const char *name);
 int orc_pop_rhs(double t, const double *y, double *f, void *sim);

@@ -22,6 +22,7 @@ DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict
         "chain_array": dict(nvar=6, naux=6, npsi=0, nmfd=2, nexpr=4),
         "fun_block": dict(nvar=3, naux=5, npsi=0, nmfd=1, nexpr=6),
         "helper_calls": dict(nvar=4, naux=13, npsi=0, nmfd=1, nexpr=6),
+        "delay_pop": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1),
         "kuramoto_lrexp": dict(nvar=1, naux=1, npsi=1, nmfd=2, nexpr=1),
         "pair_aux": dict(nvar=2, naux=3, npsi=2, nmfd=1, nexpr=1),
         "lineage": dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=4),

@@ -11,7 +11,7 @@ try:
     print("   ms/step %.4f sustained %.4f per-rank %s variant %s" % (d["ms_per_step"], d["ms_per_step_sustained"], ["%.4f" % x for x in d["per_rank_ms_per_step"]], d["run"]["step_kernel_variant"]))
     c = d.get("configs") or {}
     for k, v in c.items():
-        if isinstance(v, dict): print("   ", k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ("ms_per_rhs_eval", "rk4_ms_per_step", "em_ms_per_step", "tauleap_ms_best")}, v.get("rkf45", {}).get("ms_per_accepted_step"), round(v.get("roofline", {}).get("frac", 0), 3))
+        if isinstance(v, dict): print("   ", k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ("ms_per_rhs_eval", "rk4_ms_per_step", "em_ms_per_step", "tauleap_ms_steady")}, v.get("rkf45", {}).get("ms_per_accepted_step"), round(v.get("roofline", {}).get("frac", 0), 3))
         else: print("   ", k, v)
 except Exception as e:
     print("   no line:", e)

@@ -283,6 +283,7 @@ def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
 
 @pytest.mark.parametrize("name,rtol,atol", [("chain_array_dde_n20", 1e-10, 1e-13), ("fun_block_rkf45_n21", 1e-10, 1e-12),
                                             ("helper_calls_dde_n12", 1e-10, 1e-13), ("helper_calls_rkck_n9", 1e-9, 1e-12),
+                                            ("delay_pop_dde_n8", 1e-10, 1e-13), ("delay_pop_dde_stop_n5", 1e-10, 1e-13),
                                             ("pair_aux_dde_n30", 1e-10, 1e-12), ("nbody_const_rkf45", 1e-8, 1e-10),
                                             ("lowrank_aux_dde_n100", 1e-10, 1e-9), ("lrexp_dde_n200", 1e-10, 1e-9)])
 def test_model_language_fixtures_against_reference_outputs(model_lib, name, rtol, atol):
@@ -333,4 +334,24 @@ def test_lag_linear_chain(model_lib, meth, n):
     assert len(ta) == len(tb) and out["report"]["steps"] == ref["report"]["steps"]
     np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :6], tb[tb["step"] == 0]["cols"][:, :6])
     np.testing.assert_allclose(ta["cols"], tb["cols"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("meth,n,ts,h0", [("dde", 16, (0, 3.1), 0.03), ("dde", 1, (0, 2.0), 0.05), ("dde", 5, (0, 1.0, 2.5), 0.05), ("fe", 7, (0, 1.0), 0.02),
+                                          ("rkck", 7, (0, 1.0), 0.05)])
+def test_delay_history_stacks_vs_oracle(model_lib, meth, n, ts, h0):
+    """delay(t, x, tau, ic, &hist[ID]) (src/utils_odexp.c:205-240): one circular history of 1000 samples per particle on the device,
+    filled from the history function at t0 and while an event flag is pending (an interior TIMESPAN value), pushed twice per first
+    evaluation of a dde step, interpolated with the reference's index arithmetic; the other steppers only look up (as in the
+    reference, where only dde_apply sets DELAY_FIRST_EVAL).  Against the restatement, which is bit-identical to the reference binary."""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": h0, "res": 7, "ps": n}
+    pop = capi.Population(model_lib("delay_pop"), capacity=64)
+    out = capi.odesolver(pop, ts, meth=meth, h0=h0, res=7, popsize=n, replay_ic=True)
+    pop.close()
+    ref = port.run("delay_pop", opts, ts)
+    assert len(out["stats"]) == len(ref["stats"]) and out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_array_equal(out["stats"]["stop_flag"], ref["stats"]["stop_flag"])
+    np.testing.assert_allclose(out["traj"]["cols"], ref["traj"]["cols"], rtol=1e-10 if meth != "rkck" else 1e-9, atol=1e-13)
     np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

@@ -11,7 +11,7 @@ from conftest import load_golden
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
                 "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3",
                 "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "nbody_const_rkf45", "lowrank_aux_dde_n100",
-                "lrexp_dde_n200", "helper_calls_dde_n12", "helper_calls_rkck_n9", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
+                "lrexp_dde_n200", "helper_calls_dde_n12", "helper_calls_rkck_n9", "delay_pop_dde_n8", "delay_pop_dde_stop_n5", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -58,6 +58,11 @@ REF_CASES = [
     # the helper functions of src/utils_odexp.c (sumsub, sumstep, sum3, prod, conv, minus, plus, identity, sumxy, kern)
     ("helper_calls", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 17, "hmin": 1e-5}, (0, 1.5)),
     ("helper_calls", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 5, "hmin": 1e-5}, (0, 1.5)),
+    # delay(): one history stack per particle (src/utils_odexp.c:173-240), with and without a stopping time (which refills the history)
+    ("delay_pop", {"meth": "dde", "h0": 0.03, "res": 7, "ps": 16}, (0, 3.1)),
+    ("delay_pop", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 5}, (0, 1.0, 2.5)),
+    ("delay_pop", {"meth": "fe", "h0": 0.02, "res": 4, "ps": 7}, (0, 1.0)),
+    ("delay_pop", {"meth": "rkck", "h0": 0.05, "res": 4, "ps": 7}, (0, 1.0)),
     # array dynamical / auxiliary / expression entries (`dX[i=0:NC]/dt`, `aux sq[i=0:NC]`), MA() of a scalar aux fed by an array
     ("chain_array", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 20, "hmin": 1e-5}, (0, 3)),
     ("chain_array", {"meth": "rkck", "h0": 0.05, "res": 4, "ps": 33, "hmin": 1e-5}, (0, 3)),
