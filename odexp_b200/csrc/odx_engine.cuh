@@ -1159,7 +1159,10 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         a.t_eval = t + g.h; a.t_next = t + g.h; a.a = g.h / 6.0; a.w = 1.0;
         chain_sweep<false, true, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
       }
-      if (!PF_ON) {
+#ifndef ODX_RING_NEW_XCHG
+#define ODX_RING_NEW_XCHG 0
+#endif
+      if (!PF_ON || ODX_RING_NEW_XCHG) {
         stage_exchange<NTC, PF_ON>(red, xa, epoch, s_tot, s_wp, s_words, &s_go);
       } else {
         /* ---- mean-field barrier without a barrier, low-latency words.  Every exchanged double travels as two 8-byte words
