@@ -1001,9 +1001,11 @@ __device__ __forceinline__ void stage_exchange(const double (&red)[NRED], const 
   const uint32_t tag = epoch + 1u;
   unsigned long long *ll_part = g.ll_part + par * (size_t)PERSIST_MAX_CTAS * LLW;
   constexpr int NW = NTC / 32;
+  /* the birth and rate slots are structurally zero in a model without %BIRTH / %DEATH / %REPLI: not reduced, not exchanged */
+  constexpr int NX = (M::HAS_BIRTH || M::HAS_DEATH || M::HAS_REPLI) ? NRED : A1(NMFD), LLX = 2 * NX;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < NRED; k++) {
+  for (int k = 0; k < NX; k++) {
     const double v = warp_sum(red[k]);
     if (lane == 0) s_wp[warp][k] = v;
   }
@@ -1012,23 +1014,23 @@ __device__ __forceinline__ void stage_exchange(const double (&red)[NRED], const 
   if (warp == 0) {
     double mine = 0.0;
 #pragma unroll
-    for (int k = 0; k < NRED; k++) {
+    for (int k = 0; k < NX; k++) {
       double v = (lane < NW) ? s_wp[lane][k] : 0.0;
       v = warp_sum(v);
       v = __shfl_sync(0xffffffffu, v, 0);
       if ((lane >> 1) == k) mine = v;
     }
-    if (lane < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + lane, ll_pack(mine, lane & 1, tag));
+    if (lane < LLX) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLX + lane, ll_pack(mine, lane & 1, tag));
   }
-  for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
+  for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLX; idx += NTC) {
     unsigned long long w; unsigned long long spins = 0;
     while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
     s_words[idx] = (uint32_t)w;
   }
   cta_sync<NTC>();                                         /* [B] */
-  for (int k = warp; k < NRED; k += NW) {
+  for (int k = warp; k < NX; k += NW) {
     double a = 0.0;
-    for (unsigned int b2 = lane; b2 < gridDim.x; b2 += 32) a += ll_unpack(s_words[b2 * LLW + 2 * k], s_words[b2 * LLW + 2 * k + 1]);
+    for (unsigned int b2 = lane; b2 < gridDim.x; b2 += 32) a += ll_unpack(s_words[b2 * LLX + 2 * k], s_words[b2 * LLX + 2 * k + 1]);
     a = warp_sum(a);
     if (g.nranks > 1) {
       a = __shfl_sync(0xffffffffu, a, 0);

@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(BLOCK) k_ssa_pick(const double *__restrict__ d
 /* ---- host side -------------------------------------------------------------------------------------------------- */
 struct EventBufs {
   double *ssa_tiles = nullptr; int64_t ssa_tiles_cap = 0; long long *ssa_out = nullptr;
+  int32_t *xch = nullptr; void *xch_pin = nullptr;                  /* count exchanges of the sharded sweep */
   int32_t *outcome = nullptr, *flag = nullptr, *scan = nullptr, *tile = nullptr, *grand = nullptr, *child = nullptr, *f3 = nullptr, *s3 = nullptr;
   odx_event_row *rows = nullptr; int64_t rows_cap = 0;
   odx_event_row *rows_pin = nullptr; int64_t rows_pin_cap = 0;      /* pinned host copy of the event rows of the last sweep */
@@ -353,9 +354,10 @@ static void odx_events_free(odx_handle *h) {
   if (!h->ev_state) return;
   odx::EventBufs &b = h->ev_state->b;
   void *ptrs[] = {b.outcome, b.flag, b.scan, b.tile, b.grand, b.child, b.f3, b.s3, b.rows, b.alt.Y, b.alt.E, b.alt.AUX, b.alt.PSI,
-                  b.alt.DEATH, b.alt.REPLI, b.alt.ID, b.ssa_tiles, b.ssa_out};
+                  b.alt.DEATH, b.alt.REPLI, b.alt.ID, b.ssa_tiles, b.ssa_out, b.xch};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (b.rows_pin) cudaFreeHost(b.rows_pin);
+  if (b.xch_pin) cudaFreeHost(b.xch_pin);
   delete h->ev_state;
   h->ev_state = nullptr;
 }
@@ -525,6 +527,250 @@ static int replica_scatter(odx_handle *h) {
   invalidate_state(h);
   return refresh_global_n(h);
 }
+
+/* ---- sharded tau-leaping sweep ---------------------------------------------------------------------------------------------
+ * The sweep has the semantics of ONE ordered list: generation 0 = the particles in list order, generation g + 1 = the daughters of
+ * generation g in their mothers' order, appended at the end and visited later in the same sweep; ids and the population size in
+ * every event row follow that order.  With the list sharded by contiguous ranges, the global order of generation g is
+ * (rank 0's part, rank 1's part, ...), so every position-dependent quantity is a local prefix plus the totals of the
+ * (generation, rank) segments in front: each rank flags and spawns its own particles (keyed draws: by particle id, the same on any
+ * GPU), and the ranks exchange only counts -- one allgather of one int per generation (daughter ids), one allgather of 3 ints per
+ * generation at the end (survivors, rows, deaths: the event rows' positions and population sizes).  The rows of all ranks are
+ * combined by an allreduce over the (disjoint) row positions.  The new list -- survivors of generation 0, 1, ... in global order,
+ * then the de-novo births -- is cut into balanced contiguous shards again and moved with grouped ncclSend / ncclRecv of the
+ * contiguous pieces of every column: the rebalancing of SURVEY 8(e).  Result identical to the single-GPU sweep (tests/mgpu). */
+constexpr int SHARD_MAXGEN = 24;
+struct SegInfo { int ngen; int64_t first[SHARD_MAXGEN + 1]; int32_t rows_off[SHARD_MAXGEN], deaths_off[SHARD_MAXGEN]; };
+__global__ void k_seg_totals(const int32_t *__restrict__ s3, const int32_t *__restrict__ grand, SegInfo sg, int64_t nsweep, int32_t *__restrict__ out) {
+  /* out[g][c] = total of channel c over segment g = prefix(first[g+1]) - prefix(first[g]) (exclusive prefixes; the end is the grand total) */
+  const int q = threadIdx.x;
+  if (q >= sg.ngen * 3) return;
+  const int g = q / 3, c = q % 3;
+  const int32_t a = sg.first[g] < nsweep ? s3[sg.first[g] * 3 + c] : grand[c];
+  const int32_t b = sg.first[g + 1] < nsweep ? s3[sg.first[g + 1] * 3 + c] : grand[c];
+  out[q] = b - a;
+}
+__global__ void __launch_bounds__(BLOCK) k_event_rows_sharded(const int32_t *__restrict__ outcome, const int32_t *__restrict__ s3,
+                                                               const int32_t *__restrict__ ids, const int32_t *__restrict__ child_id, int64_t n,
+                                                               int32_t n0, SegInfo sg, odx_event_row *__restrict__ rows, int64_t max_rows) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * BLOCK) {
+    const int o = outcome[i];
+    if (o == OUT_NONE) continue;
+    int g = 0;
+    while (g + 1 < sg.ngen && i >= sg.first[g + 1]) g++;
+    const int64_t f = sg.first[g];
+    const int64_t r = (int64_t)sg.rows_off[g] + (s3[i * 3 + 1] - s3[f * 3 + 1]);
+    const int32_t nbefore = n0 - (sg.deaths_off[g] + (s3[i * 3 + 2] - s3[f * 3 + 2]));
+    if (o == OUT_DIE) {
+      if (r < max_rows) { odx_event_row e = {nbefore - 1, ODX_STOP_DEATH, {ids[i], -1, -1}}; rows[r] = e; }
+    } else {
+      if (r < max_rows) { odx_event_row e = {nbefore + 1, ODX_STOP_REPLI, {ids[i], 1, child_id[i]}}; rows[r] = e; }
+      if (o == OUT_REPL_DIE && r + 1 < max_rows) { odx_event_row e = {nbefore, ODX_STOP_DEATH, {ids[i], -1, -1}}; rows[r + 1] = e; }
+    }
+  }
+}
+
+#define ODX_NCCL(h, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { (h)->err = std::string("NCCL: ") + g_nccl.GetErrorString(r_); return ODX_ENCCL; } } while (0)
+
+/* all ranks: ints[count] -> all[nranks][count] on the host */
+static int allgather_ints(odx_handle *h, EventBufs &b, const int32_t *dev_src, int count, std::vector<int32_t> &all) {
+  ODX_NCCL(h, g_nccl.AllGather(dev_src, b.xch, (size_t)count, ncclInt32, h->comm, h->stream));
+  all.resize((size_t)count * h->nranks);
+  int32_t *pin = reinterpret_cast<int32_t *>(b.xch_pin);
+  ODX_CUDA(h, cudaMemcpyAsync(pin, b.xch, sizeof(int32_t) * (size_t)count * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k < all.size(); k++) all[k] = pin[k];
+  return ODX_SUCCESS;
+}
+
+/* move the pieces [gstart, gstart + cnt) of the new global list this rank holds at `src` (local offset lstart) to their new owners,
+ * and receive this rank's new shard [lo, hi) into `dst`; one column of `elem`-byte entries */
+struct Piece { int64_t gstart, cnt, lstart; };
+static int exchange_column(odx_handle *h, const char *src, char *dst, size_t elem, const std::vector<std::vector<Piece>> &pieces,
+                           const std::vector<int64_t> &lo, const std::vector<int64_t> &hi) {
+  const int me = h->rank;
+  ODX_NCCL(h, g_nccl.GroupStart());
+  for (int q = 0; q < h->nranks; q++) {
+    /* what I send to q: my pieces cut to [lo[q], hi[q]) */
+    for (const Piece &pc : pieces[me]) {
+      const int64_t a = std::max(pc.gstart, lo[q]), e = std::min(pc.gstart + pc.cnt, hi[q]);
+      if (e <= a) continue;
+      const char *sp = src + (size_t)(pc.lstart + (a - pc.gstart)) * elem;
+      if (q == me) {
+        ODX_CUDA(h, cudaMemcpyAsync(dst + (size_t)(a - lo[me]) * elem, sp, (size_t)(e - a) * elem, cudaMemcpyDeviceToDevice, h->stream));
+      } else {
+        ODX_NCCL(h, g_nccl.Send(sp, (size_t)(e - a) * elem, ncclChar, q, h->comm, h->stream));
+      }
+    }
+    if (q == me) continue;
+    /* what I receive from q: q's pieces cut to my range, in the same order q sends them */
+    for (const Piece &pc : pieces[q]) {
+      const int64_t a = std::max(pc.gstart, lo[me]), e = std::min(pc.gstart + pc.cnt, hi[me]);
+      if (e <= a) continue;
+      ODX_NCCL(h, g_nccl.Recv(dst + (size_t)(a - lo[me]) * elem, (size_t)(e - a) * elem, ncclChar, q, h->comm, h->stream));
+    }
+  }
+  ODX_NCCL(h, g_nccl.GroupEnd());
+  return ODX_SUCCESS;
+}
+
+static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows_out,
+                           const odx_event_row **view_out) {
+  if (!h->comm) { h->err = "multi-GPU birth/death needs odx_comm_init"; return ODX_ENCCL; }
+  odx_event_state *es = event_state(h);
+  EventBufs &b = es->b;
+  ODX_TRY(ensure_event_bufs(h, b));
+  const int nrk_ = h->nranks, me = h->rank;
+  if (!b.xch) {
+    ODX_CUDA(h, cudaMalloc((void **)&b.xch, sizeof(int32_t) * (size_t)(3 * SHARD_MAXGEN + 8) * (MAX_RANKS + 1)));
+    ODX_CUDA(h, cudaMallocHost((void **)&b.xch_pin, sizeof(int32_t) * (size_t)(3 * SHARD_MAXGEN + 8) * (MAX_RANKS + 1)));
+  }
+  int32_t *xsend = b.xch + (size_t)(3 * SHARD_MAXGEN + 8) * MAX_RANKS;
+  const uint32_t stream = (leap_index == UINT64_MAX) ? es->event_index : (uint32_t)leap_index;
+  const int32_t N0 = (int32_t)h->n_global;
+  double birth_rate = 0.0;
+  ODX_TRY(odx_rates(h, nullptr, &birth_rate));
+  /* ---- generations */
+  SegInfo sg; memset(&sg, 0, sizeof sg);
+  std::vector<std::vector<int32_t>> cgen;          /* cgen[g][r]: daughters born to rank r's generation-g particles */
+  int64_t first = 0, end = h->n;
+  int32_t max_id = h->max_id;
+  std::vector<int32_t> all;
+  int32_t g1[4];
+  for (int g = 0;; g++) {
+    if (g >= SHARD_MAXGEN) { h->err = "sharded tau-leaping: more generations of daughters in one sweep than supported"; return ODX_EUNSUP; }
+    sg.first[g] = first;
+    const int64_t count = end - first;
+    Pop p = pop_view(h);
+    int32_t nd = 0;
+    if (count > 0) {
+      k_leap_flags<<<grid_for(h, count), BLOCK, 0, h->stream>>>(p, first, count, dt, stream, b.outcome, b.flag);
+      ODX_TRY(launch_check(h));
+      ODX_TRY(exclusive_scan<1>(h, b.flag, b.scan, count, b.tile, b.grand, g1));
+      nd = g1[0];
+    }
+    ODX_CUDA(h, cudaMemcpyAsync(xsend, &nd, sizeof nd, cudaMemcpyHostToDevice, h->stream));
+    ODX_TRY(allgather_ints(h, b, xsend, 1, all));
+    cgen.push_back(all);
+    int64_t ctot_ = 0, before = 0;
+    for (int r = 0; r < nrk_; r++) { ctot_ += all[r]; if (r < me) before += all[r]; }
+    sg.ngen = g + 1;
+    if (ctot_ == 0) { sg.first[g + 1] = end; break; }
+    if (nd > 0) {
+      if (end + nd > h->cap) { h->err = "odx_tauleap_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+      k_spawn<<<grid_for(h, count), BLOCK, 0, h->stream>>>(p, first, count, b.outcome, b.scan, end, max_id + (int32_t)before, t, stream, b.child);
+      ODX_TRY(launch_check(h));
+    }
+    max_id += (int32_t)ctot_;
+    first = end; end += nd;
+  }
+  const int ngen_ = sg.ngen;
+  const int64_t nsweep = end;
+  /* de-novo births: the host loop's draw, the same number on every rank */
+  long nnew = M::HAS_BIRTH ? odx_draw_poisson(h, birth_rate * dt, h->hr_seeded ? 1 : 0) : 0;
+  if (nnew < 0) nnew = 0;
+  /* ---- per-segment totals (survivors, rows, deaths) of every rank */
+  int32_t g3[4] = {0, 0, 0, 0};
+  if (nsweep > 0) { k_sweep_flags<<<grid_for(h, nsweep), BLOCK, 0, h->stream>>>(b.outcome, b.f3, nsweep); ODX_TRY(launch_check(h)); }
+  ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3));
+  k_seg_totals<<<1, 3 * SHARD_MAXGEN, 0, h->stream>>>(b.s3, b.grand, sg, nsweep, xsend);
+  ODX_TRY(launch_check(h));
+  ODX_TRY(allgather_ints(h, b, xsend, 3 * ngen_, all));
+  auto tot = [&](int r, int g, int c) { return (int64_t)all[(size_t)r * 3 * ngen_ + 3 * g + c]; };
+  /* offsets of my segments in the global sweep order (generation-major, then rank), and the pieces of the new list */
+  int64_t keep_run = 0, rows_run = 0, deaths_run = 0, my_keep_local = 0;
+  std::vector<std::vector<Piece>> pieces(nrk_);
+  std::vector<int64_t> keep_local_run(nrk_, 0);
+  for (int g = 0; g < ngen_; g++) {
+    for (int r = 0; r < nrk_; r++) {
+      if (r == me) { sg.rows_off[g] = (int32_t)rows_run; sg.deaths_off[g] = (int32_t)deaths_run; }
+      const int64_t k = tot(r, g, 0);
+      if (k > 0) pieces[r].push_back(Piece{keep_run, k, keep_local_run[r]});
+      keep_local_run[r] += k;
+      keep_run += k; rows_run += tot(r, g, 1); deaths_run += tot(r, g, 2);
+    }
+  }
+  my_keep_local = keep_local_run[me];
+  const int64_t nrows_sweep = rows_run, Nnew = keep_run + nnew;
+  /* ---- event rows: every rank writes its rows at their global positions, an allreduce over the disjoint positions completes them */
+  int64_t written = 0;
+  const bool want = (rows && max_rows > 0) || view_out;
+  if (view_out) max_rows = nrows_sweep + nnew;
+  if (want && nrows_sweep + nnew > b.rows_pin_cap) {
+    if (b.rows_pin) cudaFreeHost(b.rows_pin);
+    b.rows_pin = nullptr; b.rows_pin_cap = 0;
+    const int64_t cap2 = 2 * (nrows_sweep + nnew) + 1024;
+    ODX_CUDA(h, cudaMallocHost((void **)&b.rows_pin, sizeof(odx_event_row) * (size_t)cap2));
+    b.rows_pin_cap = cap2;
+  }
+  if (want && nrows_sweep > 0) {
+    if (b.rows_cap < nrows_sweep) {
+      if (b.rows) cudaFree(b.rows);
+      b.rows = nullptr; b.rows_cap = 0;
+      ODX_CUDA(h, cudaMalloc((void **)&b.rows, sizeof(odx_event_row) * (size_t)(nrows_sweep + 1024)));
+      b.rows_cap = nrows_sweep + 1024;
+    }
+    ODX_CUDA(h, cudaMemsetAsync(b.rows, 0, sizeof(odx_event_row) * (size_t)nrows_sweep, h->stream));
+    if (nsweep > 0) {
+      k_event_rows_sharded<<<grid_for(h, nsweep), BLOCK, 0, h->stream>>>(b.outcome, b.s3, h->ID, b.child, nsweep, N0, sg, b.rows, nrows_sweep);
+      ODX_TRY(launch_check(h));
+    }
+    static_assert(sizeof(odx_event_row) == 5 * sizeof(int32_t), "event row layout");
+    ODX_NCCL(h, g_nccl.AllReduce(b.rows, b.rows, (size_t)nrows_sweep * 5, ncclInt32, ncclSum, h->comm, h->stream));
+    written = nrows_sweep < max_rows ? nrows_sweep : max_rows;
+    ODX_CUDA(h, cudaMemcpyAsync(b.rows_pin, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, h->stream));
+  }
+  const int32_t n_after_sweep = N0 - (int32_t)deaths_run;
+  /* ---- local stable compaction (alt buffers), then the redistribution into balanced contiguous shards */
+  Pop p = pop_view(h);
+  if (nsweep > 0) {
+    k_compact<<<grid_for(h, nsweep), BLOCK, 0, h->stream>>>(p, b.alt, b.outcome, b.s3, nsweep, nsweep, (int32_t)my_keep_local);
+    ODX_TRY(launch_check(h));
+  }
+  std::vector<int64_t> lo(nrk_), hi(nrk_);
+  { const int64_t base = Nnew / nrk_, extra = Nnew % nrk_;
+    for (int r = 0; r < nrk_; r++) { lo[r] = r * base + std::min<int64_t>(r, extra); hi[r] = lo[r] + base + (r < extra ? 1 : 0); } }
+  const int64_t mine = hi[me] - lo[me];
+  if (mine > h->cap) { h->err = "birth/death: this rank's shard exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+  /* survivors occupy global positions [0, keep_run); de-novo births [keep_run, Nnew) are created in place by their new owners */
+  std::vector<int64_t> hi_s(nrk_), lo_s(nrk_);
+  for (int r = 0; r < nrk_; r++) { lo_s[r] = std::min(lo[r], keep_run); hi_s[r] = std::min(hi[r], keep_run); }
+  for (int c = 0; c < NVAR; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.Y + (size_t)c * h->cap), (char *)(h->Y + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
+  for (int c = 0; c < NEXPR; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.E + (size_t)c * h->cap), (char *)(h->E + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
+  for (int c = 0; c < NAUX; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.AUX + (size_t)c * h->cap), (char *)(h->AUX + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
+  for (int c = 0; c < NPSI; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.PSI + (size_t)c * h->cap), (char *)(h->PSI + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
+  ODX_TRY(exchange_column(h, (const char *)b.alt.DEATH, (char *)h->DEATH, 8, pieces, lo_s, hi_s));
+  ODX_TRY(exchange_column(h, (const char *)b.alt.REPLI, (char *)h->REPLI, 8, pieces, lo_s, hi_s));
+  ODX_TRY(exchange_column(h, (const char *)b.alt.ID, (char *)h->ID, 4, pieces, lo_s, hi_s));
+  /* de-novo births that fall into my new shard */
+  {
+    const int64_t a = std::max(lo[me], keep_run), e = std::min(hi[me], Nnew);
+    if (e > a) {
+      h->n = mine;
+      k_births<<<grid_for(h, e - a), BLOCK, 0, h->stream>>>(pop_view(h), a - lo[me], e - a, max_id + (int32_t)(a - keep_run), t, stream);
+      ODX_TRY(launch_check(h));
+    }
+  }
+  for (long k = 0; k < nnew; k++) {
+    if (want && written < max_rows) {
+      odx_event_row ev = {n_after_sweep + (int32_t)k + 1, ODX_STOP_BIRTH, {-1, 1, max_id + (int32_t)k}};
+      b.rows_pin[written++] = ev;       /* behind the sweep rows (the copy in flight fills only the entries below them) */
+    }
+  }
+  max_id += (int32_t)nnew;
+  h->n = mine; h->max_id = max_id;
+  h->n_global = (double)Nnew; h->n_before = lo[me];
+  for (int r = 0; r < nrk_ && r < MAX_RANKS; r++) h->all_n[r] = hi[r] - lo[r];
+  invalidate_state(h);
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (want) {
+    if (rows && written > 0) memcpy(rows, b.rows_pin, sizeof(odx_event_row) * (size_t)written);
+    if (view_out) *view_out = b.rows_pin;
+  }
+  if (nrows_out) *nrows_out = written;
+  es->event_index++;
+  return ODX_SUCCESS;
+}
 #endif
 }  // namespace odx
 
@@ -535,9 +781,12 @@ static int tauleap_core(odx_handle *h, double t, double dt, uint64_t leap_index,
   ODX_CUDA(h, cudaSetDevice(h->device));
   if (h->nranks > 1) {
 #ifdef ODX_HAVE_NCCL_H
+    if (h->shard_events) return tauleap_sharded(h, t, dt, leap_index, rows, max_rows, nrows, view_out);
     ODX_TRY(replica_gather(h));
+    event_state(h->replica)->event_index = event_state(h)->event_index;       /* one event counter, whichever path an event takes */
     int st = tauleap_core(h->replica, t, dt, leap_index, rows, max_rows, nrows, view_out);
     if (st != ODX_SUCCESS) { h->err = std::string("replicated sweep: ") + h->replica->err; return st; }
+    event_state(h)->event_index = event_state(h->replica)->event_index;
     return replica_scatter(h);
 #else
     h->err = "built without nccl.h"; return ODX_ENCCL;
@@ -598,8 +847,10 @@ int odx_ssa_apply(odx_handle *h, double t, double u, odx_event_row *row) {
   if (h->nranks > 1) {
 #ifdef ODX_HAVE_NCCL_H
     ODX_TRY(replica_gather(h));
+    event_state(h->replica)->event_index = event_state(h)->event_index;
     int st = odx_ssa_apply(h->replica, t, u, row);
     if (st != ODX_SUCCESS) { h->err = std::string("replicated SSA event: ") + h->replica->err; return st; }
+    event_state(h)->event_index = event_state(h->replica)->event_index;
     return replica_scatter(h);
 #else
     h->err = "built without nccl.h"; return ODX_ENCCL;

@@ -24,6 +24,10 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (lib) return true;
@@ -35,8 +39,10 @@ struct NcclApi {
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
     AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    Send = (decltype(Send))dlsym(lib, "ncclSend"); Recv = (decltype(Recv))dlsym(lib, "ncclRecv");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart"); GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString;
+    return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString && Send && Recv && GroupStart && GroupEnd;
   }
 };
 static NcclApi g_nccl;
@@ -86,6 +92,7 @@ struct odx_handle {
   unsigned long long *ll_words = nullptr;     /* LL exchange words of the persistent kernel (zero-initialised) */
   int use_persistent = 1, coop_ok = 0, coop_blocks = 0, sweep_dir = 0, use_recon = 1;
   int coop_blocks_tma = 0, tma_mode = -1;     /* tma_mode: -1 choose by size, 0 never, 1 always (option "tma") */
+  int shard_events = 1;                       /* multi-GPU tau-leaping: 1 sharded sweep + redistribution, 0 replicate the population (option "shard_events") */
   int ssa_mode = -1;                          /* SSA event pick: -1 device for keyed runs / host for replayed ones, 0 host, 1 device (option "ssa_device") */
   int lean_mode = -1;                         /* lean RK4 scheme: -1 with the TMA ring (HBM-resident populations), 0 never, 1 whenever eligible (option "lean") */
   double l2_bytes = 0.0;
@@ -899,6 +906,7 @@ int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "lean") == 0) { h->lean_mode = (int)value; return ODX_SUCCESS; }
+  if (strcmp(name, "shard_events") == 0) { h->shard_events = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "ssa_device") == 0) { h->ssa_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "lrmax") == 0) { h->lr_pmax = (int)value < 1 ? 1 : ((int)value > 31 ? 31 : (int)value); return ODX_SUCCESS; }

@@ -66,6 +66,43 @@ for model, n, meth, nsteps, tol, opts in CASES:
         solo.close()
     dist.barrier()
     pop.close()
+# ---- tau-leaping sweeps on a sharded population: sharded sweep + redistribution (and the replicated form) against the solo run
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
+for n, shard in ((200001, 1), (200001, 0), (5, 1), (70001, 1)):
+    lo, hi = odist.shard_range(n, rank, world)
+    pop = capi.Population(lib, capacity=2 * (hi - lo) + 4096, device=local)
+    odist.connect(pop)
+    pop.set_option("shard_events", shard)
+    pop.init(hi - lo, replay=False, seed=5)
+    t = pop.run_fixed("fe", 0.0, 0.01, 20)
+    solo = None
+    if rank == 0:
+        solo = capi.Population(lib, capacity=2 * n + 4096, device=local)
+        solo.init(n, replay=False, seed=5)
+        solo.run_fixed("fe", 0.0, 0.01, 20)
+    good = True
+    for k in range(4):
+        pop.rhs(t)
+        rows = pop.tauleap_apply(t, 2.0 if n > 100 else 8.0, k, as_array=True)
+        mine = pop.download()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine["id"], mine["y"]))
+        if rank == 0:
+            solo.rhs(t)
+            srows = solo.tauleap_apply(t, 2.0 if n > 100 else 8.0, k, as_array=True)
+            ref = solo.download()
+            ids_all = np.concatenate([g[0] for g in gathered]); y_all = np.concatenate([g[1] for g in gathered])
+            sizes = [len(g[0]) for g in gathered]
+            ok_k = (rows.tobytes() == srows.tobytes() and np.array_equal(ids_all, ref["id"]) and np.array_equal(y_all, ref["y"])
+                    and max(sizes) - min(sizes) <= 1 and pop.size()[1] == solo.size()[0] and pop.size()[2] == solo.size()[2])
+            good &= bool(ok_k)
+            print("tau-leap sweep %d N=%d world=%d %s: %d rows (solo %d), N -> %d (solo %d), shards %s -> %s" % (
+                k, n, world, "sharded" if shard else "replicated", len(rows), len(srows), pop.size()[1], solo.size()[0], sizes, "OK" if ok_k else "MISMATCH"), flush=True)
+    ok &= good
+    if rank == 0:
+        solo.close()
+    dist.barrier()
+    pop.close()
 # ---- whole simulation with birth / death through the C host driver: every rank's stats.dat must equal the solo run's
 lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
 for ssahmin, ps, res, T in [(1.0, 2000, 21, 2.0), (0.0, 60, 6, 1.0)]:
