@@ -240,6 +240,16 @@ def config_nbody(capi, odist, rank, world, local, no_peers, peak_hbm):
         pop.rhs(0.0)
     pop.event_record(1)
     ms_eval = _max_over_ranks(pop.event_elapsed_ms(0, 1) / reps, world)
+    ms_ordered = None
+    if world == 1:                                        # the ordered kernel (k_pair: the reference's summation order) beside the symmetric one
+        pop.set_option("pair_sym", 0)
+        pop.rhs(0.0); pop.sync()
+        pop.event_record(0)
+        pop.rhs(0.0)
+        pop.event_record(1)
+        ms_ordered = pop.event_elapsed_ms(0, 1)
+        pop.set_option("pair_sym", -1)
+        pop.rhs(0.0); pop.sync()
     pop.set_tolerances(1e-8, 1e-8)
     pop.evolve_reset()
     t, h = 0.0, 1e-3
@@ -256,13 +266,18 @@ def config_nbody(capi, odist, rank, world, local, no_peers, peak_hbm):
     pop.close()
     pairs = float(n) * n
     flops = 20.0 * pairs / (ms_eval * 1e-3) / world         # per GPU
+    sym = world == 1
+    inst = 9.0 if sym else 15.0                              # executed FP64 instructions per ordered pair
     return {"workload": "models/nbody.pop (from examples/Nbody.pop), N=%d bodies, O(N^2) %%C gravity" % n, "n_particles": n,
-            "ms_per_rhs_eval": ms_eval, "pairs_per_s": pairs / (ms_eval * 1e-3),
+            "ms_per_rhs_eval": ms_eval, "ms_per_rhs_eval_ordered_kernel": ms_ordered, "pairs_per_s": pairs / (ms_eval * 1e-3),
             "rkf45": {"ms_per_accepted_step": ms_step, "particle_steps_per_s": n / (ms_step * 1e-3), "accepted": nacc,
                       "rejected_attempts": int(c1[1] - c0[1]), "rhs_evals": int(c1[2] - c0[2]), "abstol": 1e-8, "reltol": 1e-8},
             "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": FP64_PEAK_FLOPS / 1e12, "unit": "TFLOP/s", "frac": flops / FP64_PEAK_FLOPS,
                          "algorithmic_flops_per_pair": 20, "peak_source": "measured DFMA issue rate x 2 (profiles/r1_fp64_peak.txt); nominal 37.2",
-                         "kernel": "k_pair"}}
+                         "kernel": "k_pair_sym (every unordered pair once, added to both particles; 20 flop are credited per ORDERED pair, "
+                                   "the convention of SURVEY 8(d))" if sym else "k_pair (ordered: one launch per source rank over the allgathered columns)",
+                         "fp64_pipe_frac": inst * pairs / (ms_eval * 1e-3) / world / (FP64_PEAK_FLOPS / 2.0),
+                         "executed_fp64_inst_per_ordered_pair": inst}}
 
 
 def config_lowrank(capi, odist, rank, world, local, no_peers, peak_hbm):

@@ -1378,9 +1378,11 @@ __device__ __forceinline__ void pair_rows(const Pop &p, const double *__restrict
 }
 __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__restrict__ ysrc, const double *__restrict__ jy,
                                                        const double *__restrict__ je, const int32_t *__restrict__ jid, int64_t jstride,
-                                                       int64_t nj, double t, double *__restrict__ part, int seg_base) {
+                                                       int64_t nj, double t, double *__restrict__ part, int seg_base,
+                                                       const int *__restrict__ only_if) {
   __shared__ double s_col[A1(PAIR_SCOL)][PAIR_TJ];
   __shared__ int32_t s_id[PAIR_TJ];
+  if (only_if != nullptr && *only_if == 0) return;      /* ordered exact pass after k_pair_sym: runs only when that kernel met a non-finite term */
   /* this CTA's j-range: segment blockIdx.y of gridDim.y, boundaries aligned to the j-tile */
   const int64_t tiles = (nj + PAIR_TJ - 1) / PAIR_TJ;
   const int64_t tps = (tiles + gridDim.y - 1) / gridDim.y;
@@ -1421,7 +1423,9 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair(Pop p, const double *__re
   }
 }
 /* psi = (sum over segments, ascending j) / POP_SIZE; only the pairwise couplings are touched (a low-rank psi keeps its column) */
-__global__ void __launch_bounds__(BLOCK) k_pair_finish(Pop p, const double *__restrict__ part, int nseg, double *__restrict__ psi) {
+__global__ void __launch_bounds__(BLOCK) k_pair_finish(Pop p, const double *__restrict__ part, int nseg, double *__restrict__ psi,
+                                                       const int *__restrict__ only_if) {
+  if (only_if != nullptr && *only_if == 0) return;
   for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
 #pragma unroll
     for (int k = 0; k < NPSI; k++) {
@@ -1432,6 +1436,182 @@ __global__ void __launch_bounds__(BLOCK) k_pair_finish(Pop p, const double *__re
     }
   }
 }
+
+#ifdef ODX_MODEL_CPL_SYM
+/* ------------------------------------------------------------------------------------------------
+ * Symmetric all-pairs %C (Newton's third law) for couplings the emitter has proven antisymmetric bit for bit
+ * (OdxModel::CPL_SYM: term_k(i,j) = (y_i - y_j) R with R even in every difference, so term_k(j,i) = -term_k(i,j) exactly):
+ * every unordered pair is evaluated once and added to both particles -- for the N-body coupling 18 FP64 instructions per
+ * unordered pair (3 differences, 3 for r^2, 6 for r^-3, 3 + 3 FMAs) = 9 per ordered pair instead of the 15 of k_pair.
+ *
+ * Work item = one pair of tiles (A <= B) of PSYM_TILE particles, one CTA.  Warp w owns i-superblock w of tile A (32 x PSYM_PI
+ * particles, PSYM_PI per lane, in registers with their sums for the whole work item) and walks over the j-superblocks of tile B
+ * (32 x PSYM_PJ particles) in a staggered order, so that at any time every j-superblock is held by one warp only.  Inside a
+ * (i-superblock, j-superblock) block the lanes rotate over the j-groups: at rotation step r lane l reads the positions of
+ * j-group (l + r) mod 32 from the warp's shared-memory copy (consecutive lanes, consecutive addresses: conflict-free) and holds
+ * that group's running sums in registers; after the step the sums move to the next lane by one shuffle each, and after 32 steps
+ * they are back in their home lane.  Register blocking PSYM_PI x PSYM_PJ is what makes the j-side cheap: 6 PSYM_PJ shuffles and
+ * PSYM_NYC PSYM_PJ shared loads per PSYM_PI PSYM_PJ pairs.  The j-side sums of a block are then added into the tile's
+ * shared-memory accumulators (exclusive owner, fixed order), the i-side sums stay in registers.  A tile pair writes two blocks
+ * of raw partial sums, part[A][B] (i-side) and part[B][A] (j-side); the diagonal pair A = B evaluates all ordered pairs through
+ * the i-side only, skipping i = j.  k_pair_sym_finish adds the partial blocks of a tile in ascending order of the other tile:
+ * the result is deterministic (fixed schedule, no atomics) but the order of summation differs from k_pair's ascending-j order,
+ * i.e. from the reference's by rounding (tests: <= 1e-12 relative on psi).  Blocks that contain the end of the population or the
+ * diagonal take a masked form.  A non-finite term (coincident particles: the fast term is 0 x inf) poisons the sums; the finish
+ * kernel raises a flag, and the ordered kernels (which redo such tiles with the exact forms) then run over the whole
+ * population -- they are launched after every symmetric evaluation and return at once while the flag is down. */
+/* measured at N = 2^17 (profiles/r2p_pair_sym_variants.txt), PI x PJ / CTAs per SM: 8x2/1 10.27 ms, 8x4/1 10.50, 8x1/2 10.59,
+ * 4x2/2 10.65, 4x4/2 10.72, 4x4/1 10.97; ordered kernel 15.76 */
+#ifndef PSYM_PI
+#define PSYM_PI 8
+#endif
+#ifndef PSYM_PJ
+#define PSYM_PJ 2
+#endif
+#ifndef PSYM_MINB
+#define PSYM_MINB 1
+#endif
+constexpr int PSYM_TILE = 1024, PSYM_SI = 32 * PSYM_PI, PSYM_SJ = 32 * PSYM_PJ, PSYM_W = PSYM_TILE / PSYM_SI, PSYM_NJ = PSYM_TILE / PSYM_SJ;
+constexpr int PSYM_THREADS = 32 * PSYM_W;
+static_assert(PSYM_TILE % PSYM_SI == 0 && PSYM_TILE % PSYM_SJ == 0 && PSYM_NJ % PSYM_W == 0, "k_pair_sym: j-superblocks must not be larger than i-superblocks");
+constexpr int psym_count_cols() { int c = 0; for (int v = 0; v < NVAR; v++) c += (M::CPL_SYM_YMASK >> v) & 1u; return c; }
+constexpr int PSYM_NYC = psym_count_cols();                       /* dynamical variables the terms read */
+constexpr int psym_col(int c) { int k = 0; for (int v = 0; v < NVAR; v++) if ((M::CPL_SYM_YMASK >> v) & 1u) { if (k == c) return v; k++; } return 0; }
+constexpr size_t PSYM_SMEM = sizeof(double) * ((size_t)PSYM_W * PSYM_NYC * PSYM_SJ + (size_t)A1(NPSI) * PSYM_TILE);
+
+template <bool MASKED>
+__device__ __forceinline__ void psym_block(DevCtx &c, double t, const double (&yi)[PSYM_PI][A1(NVAR)], double (&ai)[PSYM_PI][A1(NPSI)],
+                                           const double (&yj)[PSYM_PJ][A1(NVAR)], double (&aj)[PSYM_PJ][A1(NPSI)], int64_t gi0, int64_t gj0,
+                                           int64_t n) {
+#pragma unroll
+  for (int u = 0; u < PSYM_PI; u++) {
+#pragma unroll
+    for (int v = 0; v < PSYM_PJ; v++) {
+      if (MASKED) {
+        const int64_t gi = gi0 + 32 * u, gj = gj0 + 32 * v;
+        if (gi < n && gj < n && gi != gj) M::template cpl_terms_sym<false>(c, t, yi[u], yj[v], ai[u], aj[v]);
+      } else {
+        M::template cpl_terms_sym<false>(c, t, yi[u], yj[v], ai[u], aj[v]);
+      }
+    }
+  }
+}
+template <bool MASKED>
+__device__ __forceinline__ void psym_rotate(DevCtx &c, double t, const double (&yi)[PSYM_PI][A1(NVAR)], double (&ai)[PSYM_PI][A1(NPSI)],
+                                            double (&aj)[PSYM_PJ][A1(NPSI)], const double *__restrict__ s_pos, int lane, int64_t gi0,
+                                            int64_t jbase, int64_t n) {
+#pragma unroll 1
+  for (int r = 0; r < 32; r++) {
+    const int src = (lane + r) & 31;
+    double yj[PSYM_PJ][A1(NVAR)];
+#pragma unroll
+    for (int v = 0; v < PSYM_PJ; v++) {
+#pragma unroll
+      for (int cc = 0; cc < PSYM_NYC; cc++) yj[v][psym_col(cc)] = s_pos[cc * PSYM_SJ + src + 32 * v];
+    }
+    psym_block<MASKED>(c, t, yi, ai, yj, aj, gi0, jbase + src, n);
+    const int from = (lane + 1) & 31;
+#pragma unroll
+    for (int v = 0; v < PSYM_PJ; v++) {
+#pragma unroll
+      for (int k = 0; k < NPSI; k++) aj[v][k] = __shfl_sync(0xffffffffu, aj[v][k], from);
+    }
+  }
+}
+__global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, const double *__restrict__ ysrc, double t,
+                                                                       double *__restrict__ part, int ntile) {
+  const int A = blockIdx.y, B = blockIdx.x;
+  if (B < A) return;
+  extern __shared__ __align__(16) double s_psym[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *s_pos = s_psym + (size_t)w * PSYM_NYC * PSYM_SJ;                    /* this warp's copy of the current j-superblock */
+  double *s_acc = s_psym + (size_t)PSYM_W * PSYM_NYC * PSYM_SJ;               /* [NPSI][PSYM_TILE] j-side sums of tile B */
+  const int64_t n = p.n;
+  const int64_t ibase = (int64_t)A * PSYM_TILE + (int64_t)w * PSYM_SI;
+  double yi[PSYM_PI][A1(NVAR)], ai[PSYM_PI][A1(NPSI)];
+#pragma unroll
+  for (int u = 0; u < PSYM_PI; u++) {
+    int64_t gi = ibase + lane + 32 * u; if (gi > n - 1) gi = n - 1;
+#pragma unroll
+    for (int cc = 0; cc < PSYM_NYC; cc++) yi[u][psym_col(cc)] = ysrc[(int64_t)psym_col(cc) * p.stride + gi];
+#pragma unroll
+    for (int k = 0; k < A1(NPSI); k++) ai[u][k] = 0.0;
+  }
+  for (int idx = threadIdx.x; idx < A1(NPSI) * PSYM_TILE; idx += PSYM_THREADS) s_acc[idx] = 0.0;
+  __syncthreads();
+  DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, 0);
+  const bool diag = (A == B);
+#pragma unroll 1
+  for (int s = 0; s < PSYM_NJ; s++) {
+    const int jb = (w * (PSYM_NJ / PSYM_W) + s) % PSYM_NJ;
+    const int64_t jbase = (int64_t)B * PSYM_TILE + (int64_t)jb * PSYM_SJ;
+#pragma unroll
+    for (int v = 0; v < PSYM_PJ; v++) {
+      int64_t gj = jbase + lane + 32 * v; if (gj > n - 1) gj = n - 1;
+#pragma unroll
+      for (int cc = 0; cc < PSYM_NYC; cc++) s_pos[cc * PSYM_SJ + lane + 32 * v] = ysrc[(int64_t)psym_col(cc) * p.stride + gj];
+    }
+    __syncwarp();
+    double aj[PSYM_PJ][A1(NPSI)];
+#pragma unroll
+    for (int v = 0; v < PSYM_PJ; v++) {
+#pragma unroll
+      for (int k = 0; k < A1(NPSI); k++) aj[v][k] = 0.0;
+    }
+    const bool masked = (jbase + PSYM_SJ > n) || (ibase + PSYM_SI > n) || (diag && jbase < ibase + PSYM_SI && ibase < jbase + PSYM_SJ);
+    if (jbase < n && ibase < n) {
+      if (masked) psym_rotate<true>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, n);
+      else psym_rotate<false>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, n);
+    }
+    if (!diag) {
+#pragma unroll
+      for (int v = 0; v < PSYM_PJ; v++) {
+#pragma unroll
+        for (int k = 0; k < NPSI; k++) s_acc[k * PSYM_TILE + jb * PSYM_SJ + lane + 32 * v] += aj[v][k];
+      }
+    }
+    __syncthreads();
+  }
+  double *pa = part + ((size_t)A * ntile + B) * A1(NPSI) * PSYM_TILE;
+#pragma unroll
+  for (int u = 0; u < PSYM_PI; u++) {
+#pragma unroll
+    for (int k = 0; k < NPSI; k++) pa[(size_t)k * PSYM_TILE + w * PSYM_SI + lane + 32 * u] = ai[u][k];
+  }
+  if (!diag) {
+    double *pb = part + ((size_t)B * ntile + A) * A1(NPSI) * PSYM_TILE;
+    for (int idx = threadIdx.x; idx < NPSI * PSYM_TILE; idx += PSYM_THREADS) pb[idx] = s_acc[idx];
+  }
+}
+/* psi_k(i) = scale_k(i) * (sum over the partial blocks of i's tile, ascending other tile) / POP_SIZE; a non-finite result
+ * raises *poison (the ordered kernels then redo the evaluation with the exact forms) */
+__global__ void __launch_bounds__(BLOCK) k_pair_sym_finish(Pop p, const double *__restrict__ ysrc, double t, const double *__restrict__ part,
+                                                           int ntile, double *__restrict__ psi, int *__restrict__ poison) {
+  for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
+    const int64_t T = i / PSYM_TILE, il = i % PSYM_TILE;
+    double sc[A1(NPSI)];
+#pragma unroll
+    for (int k = 0; k < A1(NPSI); k++) sc[k] = 1.0;
+    if (M::CPL_SCALED) {
+      double y[A1(NVAR)], e[A1(NEXPR)], aux[A1(NAUX)];
+      load_cols<NVAR>(ysrc, p.stride, i, y); load_cols<NEXPR>(p.E, p.stride, i, e);
+      DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, M::NEEDS_ID ? p.ID[i] : 0);
+      M::template cpl_scale<true>(c, t, y, e, aux, sc);
+    }
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NPSI; k++) {
+      double a = 0.0;
+      const double *src = part + ((size_t)T * ntile * A1(NPSI) + k) * PSYM_TILE + il;
+      for (int o = 0; o < ntile; o++) a += src[(size_t)o * A1(NPSI) * PSYM_TILE];
+      a = a * sc[k] / p.n_global;
+      bad |= ((__double2hiint(a) & 0x7ff00000) == 0x7ff00000);
+      psi[(int64_t)k * p.stride + i] = a;
+    }
+    if (bad) *poison = 1;
+  }
+}
+#endif
 
 /* embedded Runge-Kutta pairs (GSL rkf45 / rkck semantics), general tableau with stored slopes.
  * Kernel for stage s (2..6): k_{s-1} = rhs(y_{s-1}); y_s = y0 + h sum_{j<s} b_{s,j} k_j; %M terms of y_s.

@@ -75,6 +75,7 @@ struct odx_handle {
   uint32_t reinit_index = 0;               /* resets at stopping times so far (Philox stream of the re-drawn ICs) */
   double *stage_dev = nullptr; size_t stage_bytes = 0;   /* AoS staging for upload / download */
   double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
+  double *pair_sym_part = nullptr; size_t pair_sym_len = 0; int *pair_poison = nullptr; int pair_sym = -1;     /* k_pair_sym: [tile][other tile][npsi][PSYM_TILE], flag, option */
   double *pair_part = nullptr; size_t pair_part_len = 0;                             /* [segment][npsi][cap] raw partial sums of k_pair */
   int64_t all_n[MAX_RANKS] = {0, 0, 0, 0, 0, 0, 0, 0};                               /* particles per rank */
   int sm_count = 148, grid_cap = 148 * 8; int ks_slots = 0;
@@ -351,8 +352,39 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
     ODX_CUDA(h, cudaMalloc((void **)&h->pair_part, sizeof(double) * need));
     h->pair_part_len = need;
   }
+  const int *only_if = nullptr;
+#ifdef ODX_MODEL_CPL_SYM
+  /* antisymmetric couplings on one GPU: every unordered pair once (k_pair_sym), then the ordered kernels below as a pass that
+   * returns at once unless the symmetric one met a non-finite term.  pair_sym: -1 automatic (populations of at least 16 tiles
+   * whose partial blocks fit in 8 GiB), 0 never, 1 always. */
+  {
+    const int64_t ntile = (h->n + PSYM_TILE - 1) / PSYM_TILE;
+    const size_t sym_need = (size_t)ntile * ntile * A1(NPSI) * PSYM_TILE;
+    const bool use_sym = h->nranks <= 1 && h->pair_sym != 0 && (h->pair_sym > 0 || (ntile >= 16 && sym_need * sizeof(double) <= ((size_t)8 << 30)));
+    if (use_sym) {
+      if (h->pair_sym_len < sym_need) {
+        if (h->pair_sym_part) cudaFree(h->pair_sym_part);
+        h->pair_sym_part = nullptr; h->pair_sym_len = 0;
+        ODX_CUDA(h, cudaMalloc((void **)&h->pair_sym_part, sizeof(double) * sym_need));
+        h->pair_sym_len = sym_need;
+      }
+      if (!h->pair_poison) ODX_CUDA(h, cudaMalloc((void **)&h->pair_poison, sizeof(int)));
+      static bool attr_set = false;
+      if (!attr_set) {
+        ODX_CUDA(h, cudaFuncSetAttribute(k_pair_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSYM_SMEM));
+        attr_set = true;
+      }
+      ODX_CUDA(h, cudaMemsetAsync(h->pair_poison, 0, sizeof(int), h->stream));
+      k_pair_sym<<<dim3((unsigned)ntile, (unsigned)ntile), PSYM_THREADS, PSYM_SMEM, h->stream>>>(p, ysrc, t, h->pair_sym_part, (int)ntile);
+      ODX_TRY(launch_check(h));
+      k_pair_sym_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, t, h->pair_sym_part, (int)ntile, h->PSI, h->pair_poison);
+      ODX_TRY(launch_check(h));
+      only_if = h->pair_poison;
+    }
+  }
+#endif
   if (h->nranks <= 1) {
-    k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, ysrc, h->E, h->ID, h->cap, h->n, t, h->pair_part, 0);
+    k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, ysrc, h->E, h->ID, h->cap, h->n, t, h->pair_part, 0, only_if);
     ODX_TRY(launch_check(h));
   } else {
 #ifdef ODX_HAVE_NCCL_H
@@ -385,14 +417,14 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
     for (int src = 0; src < h->nranks; src++) {
       const double *gy = h->gather + (size_t)src * ncol * nmax;
       k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, gy, gy + (size_t)NVAR * nmax, h->gather_id + (size_t)src * nmax, nmax,
-                                                               h->all_n[src], t, h->pair_part, src * js);
+                                                               h->all_n[src], t, h->pair_part, src * js, nullptr);
       ODX_TRY(launch_check(h));
     }
 #else
     h->err = "built without nccl.h"; return ODX_ENCCL;
 #endif
   }
-  k_pair_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, h->pair_part, nsrc * js, h->PSI);
+  k_pair_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, h->pair_part, nsrc * js, h->PSI, only_if);
   return launch_check(h);
 }
 
@@ -877,7 +909,8 @@ void odx_destroy(odx_handle *h) {
   if (h->mail) cudaFree(h->mail);
   if (h->ll_words) cudaFree(h->ll_words);
   double *bufs[] = {h->Y, h->YS, h->ACC, h->E, h->AUX, h->PSI, h->DEATH, h->REPLI, h->KS, h->YALT, h->K1, h->DOUT, h->YONE, h->YH, h->K1B, h->d_mu, h->partial,
-                    h->sums, h->stage_dev, h->gather, h->pair_part};
+                    h->sums, h->stage_dev, h->gather, h->pair_part, h->pair_sym_part};
+  if (h->pair_poison) cudaFree(h->pair_poison);
   for (double *b : bufs) if (b) cudaFree(b);
   if (h->ID) cudaFree(h->ID);
   for (int k = 0; k < A1(M::NDELAY); k++) { if (h->dl_T[k]) cudaFree(h->dl_T[k]); if (h->dl_X[k]) cudaFree(h->dl_X[k]); if (h->dl_pos[k]) cudaFree(h->dl_pos[k]); }
@@ -906,6 +939,7 @@ int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "persistent") == 0) { h->use_persistent = value != 0.0; return ODX_SUCCESS; }
   if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "lean") == 0) { h->lean_mode = (int)value; return ODX_SUCCESS; }
+  if (strcmp(name, "pair_sym") == 0) { h->pair_sym = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "shard_events") == 0) { h->shard_events = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "ssa_device") == 0) { h->ssa_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }

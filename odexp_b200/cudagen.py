@@ -325,6 +325,40 @@ def _zmul_peephole(expr: str) -> str:
             pos = b + len("odx_sel(")
 
 
+def _antisymmetric_pair_term(term: str):
+    """A %C term that changes sign, bit for bit, when the two particles are exchanged: the whole term is
+    odx_zmul<..>(odx_c, odx_y[k], odx_oy[k], R) and R reads the particles only through products of two differences of the same
+    dynamical variable ((y_u - oy_u) * (y_u - oy_u): (-d) * (-d) == d * d exactly), parameters, constants and t.  Returns
+    (k, R, set of variable indices read) or None.  Such couplings take the symmetric all-pairs kernel (k_pair_sym): every
+    unordered pair is evaluated once and added to both particles."""
+    calls = list(_find_call(term, "odx_zmul<ODX_EXACT>"))
+    if len(calls) != 1:
+        return None
+    b, en, args = calls[0]
+    if term[:b].strip() != "" or term[en + 1:].strip() != "" or len(args) != 4:
+        return None
+    A, B, R = _norm(args[1]), _norm(args[2]), args[3]
+    ma, mb = re.fullmatch(r"odx_y\[(\d+)\]", A), re.fullmatch(r"odx_oy\[(\d+)\]", B)
+    if not ma or not mb or ma.group(1) != mb.group(1):
+        return None
+    r = re.sub(r"\s+", "", R)
+    while True:
+        r2 = re.sub(r"\((odx_o?y\[\d+\])\)", r"\1", r)
+        r2 = re.sub(r"\(odx_y\[(\d+)\]-odx_oy\[\1\]\)", r"@D\1@", r2)
+        r2 = re.sub(r"\(odx_oy\[(\d+)\]-odx_y\[\1\]\)", r"@D\1@", r2)
+        r2 = re.sub(r"\((@D\d+@)\)", r"\1", r2)
+        if r2 == r:
+            break
+        r = r2
+    used = {int(ma.group(1))} | {int(x) for x in re.findall(r"@D(\d+)@", r)}
+    r = re.sub(r"@D(\d+)@\*@D\1@", "@SQ@", r)
+    if "@D" in r or re.search(r"odx_o?y\b|odx_o?e\b|odx_o?aux\b|odx_psi|odx_mfd|odx_stopif", r):
+        return None
+    if re.search(r"odx_c\.(?!mu\[|muv\[)", r):
+        return None
+    return int(ma.group(1)), R, used
+
+
 def is_vect(e):
     """%M name rhs {vect} / {noloop}"""
     return bool(re.search(r"\b(vect|noloop)\b", getattr(e, "attr", "") or ""))
@@ -740,13 +774,34 @@ class Emitter:
         w("    ODX_CONSTS")
         tc = {}
         scales = {}
+        sym_terms = []
         for c in pair_cpls:
             term = self.tr(c.rhs, "%C " + c.name, zmul=self.fast_div)
             if self.fast_div:
                 scales[c.name], term = _hoist_invariant_factors(term)
                 term = _strip_outer_parens(term)
+            sym_terms.append((self.psi_idx[c.name], _antisymmetric_pair_term(term)))
             w("    odx_p[%d] += %s;" % (self.psi_idx[c.name], self.cse(term, tc, w)))
         w("  }\n")
+        # ---- antisymmetric couplings (Newton's third law): one evaluation per unordered pair
+        self.cpl_sym = bool(pair_cpls) and not lr_cpls and self.fast_div and all(st is not None for _, st in sym_terms) \
+            and not (cpl_uses_aux or cpl_uses_oaux)
+        w("  /* every %C term changes sign (bit for bit) when the two particles are exchanged: k_pair_sym evaluates each unordered pair once */")
+        w("  static constexpr bool CPL_SYM = %s;" % ("true" if self.cpl_sym else "false"))
+        if self.cpl_sym:
+            ymask = 0
+            for _, (k, R, used) in sym_terms:
+                for u in used:
+                    ymask |= 1 << u
+            w("  static constexpr unsigned CPL_SYM_YMASK = 0x%xu;      /* dynamical variables the terms read */" % ymask)
+            w("  template <bool ODX_EXACT, class C> ODX_HD static void cpl_terms_sym(C &odx_c, double t, const double *odx_y, const double *odx_oy,")
+            w("      double *odx_p, double *odx_q) {")
+            w("    (void)t; (void)odx_c;")
+            w("    ODX_CONSTS")
+            for pi, (k, R, used) in sym_terms:
+                w("    { const double odx_d = odx_y[%d] - odx_oy[%d], odx_r = %s;" % (k, k, R.strip()))
+                w("      odx_p[%d] = fma(odx_d, odx_r, odx_p[%d]); odx_q[%d] = fma(-odx_d, odx_r, odx_q[%d]); }" % (pi, pi, pi, pi))
+            w("  }\n")
         w("  /* factors of the %C terms that do not depend on the other particle: psi_k(i) = scale_k(i) * sum_j term_k(i,j) */")
         w("  static constexpr bool CPL_SCALED = %s;" % ("true" if any(scales.values()) else "false"))
         w("  /* the fast %C terms signal an unrepresentable term by a non-finite sum (odx_zmul) */")
@@ -888,6 +943,8 @@ class Emitter:
             if len(lr_cpls) > 1:
                 raise PopError("only one low-rank coupling per model is supported")
             w("#define ODX_MODEL_HAS_LOWRANK 1")
+        if getattr(self, "cpl_sym", False):
+            w("#define ODX_MODEL_CPL_SYM 1")
         w('#include "odx_engine.cuh"')
         return "\n".join(L) + "\n"
 

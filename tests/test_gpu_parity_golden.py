@@ -82,15 +82,18 @@ def test_nbody_rkf45(model_lib):
 
 @pytest.mark.parametrize("meth,n,ts,h0", [("dde", 257, (0, 0.04), 0.02), ("dde", 1025, (0, 0.04), 0.02), ("dde", 4099, (0, 0.02), 0.02),
                                           ("rkf45", 257, (0, 0.05), 0.005), ("rkf45", 1025, (0, 0.05), 0.005), ("rkf45", 4099, (0, 0.002), 0.002)])
-def test_nbody_multi_tile_vs_oracle(model_lib, meth, n, ts, h0):
+@pytest.mark.parametrize("sym", [0, 1])
+def test_nbody_multi_tile_vs_oracle(model_lib, meth, n, ts, h0, sym):
     """the O(N^2) %C kernel beyond one tile: several i-tiles (256 particles) and j-segments (PAIR_TJ = 128), the self term's
     poison-and-redo in a tile other than the first, k_pair_finish adding the segments in list order -- against the CPU
     restatement (bit-identical to the reference binary for this fixture).  Stated tolerance for the chaotic N-body: 1e-8
-    relative over this short horizon, identical accept / reject sequence for rkf45."""
+    relative over this short horizon, identical accept / reject sequence for rkf45.  sym = 1 forces the symmetric kernel
+    (k_pair_sym: every unordered pair once, the default from 16 tiles of 1024 particles on) through the same comparison."""
     from odexp_b200 import capi
     from oracle import port
     o = {"meth": meth, "h0": h0, "res": 2, "ps": n, "hmin": 0.0, "abstol": 1e-8, "reltol": 1e-8}
     pop = capi.Population(model_lib("nbody"), capacity=n + 64)
+    pop.set_option("pair_sym", sym)
     out = capi.odesolver(pop, ts, meth=meth, h0=h0, res=2, popsize=n, hmin=0.0, abstol=1e-8, reltol=1e-8, replay_ic=True)
     pop.close()
     ref = port.run("nbody", o, ts)
