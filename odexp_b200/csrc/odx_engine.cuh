@@ -922,6 +922,10 @@ __device__ __forceinline__ unsigned long long ll_load_gpu(const unsigned long lo
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+/* both words of a double in one 16-byte request (each word still carries its own tag: no 16-byte atomicity is assumed) */
+__device__ __forceinline__ void ll_load2_gpu(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void ll_store_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1022,10 +1026,27 @@ __device__ __forceinline__ void stage_exchange(const double (&red)[NRED], const 
     }
     if (lane < LLX) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLX + lane, ll_pack(mine, lane & 1, tag));
   }
-  for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLX; idx += NTC) {
-    unsigned long long w; unsigned long long spins = 0;
-    while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
-    s_words[idx] = (uint32_t)w;
+#ifndef ODX_LL_POLL16
+#define ODX_LL_POLL16 1
+#endif
+  if (ODX_LL_POLL16) {
+    /* one 16-byte request per double: when the CTAs arrive together, the grid x grid x LLX polls of the same few cache lines are what
+     * the barrier costs (every L2 slice serialises the requests to its line) */
+    for (unsigned int idx = threadIdx.x; idx < gridDim.x * NX; idx += NTC) {
+      unsigned long long w0, w1; unsigned long long spins = 0;
+      for (;;) {
+        ll_load2_gpu(ll_part + 2 * idx, w0, w1);
+        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+        if (spin_give_up(spins, g.abort_flag)) break;
+      }
+      s_words[2 * idx] = (uint32_t)w0; s_words[2 * idx + 1] = (uint32_t)w1;
+    }
+  } else {
+    for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLX; idx += NTC) {
+      unsigned long long w; unsigned long long spins = 0;
+      while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
+      s_words[idx] = (uint32_t)w;
+    }
   }
   cta_sync<NTC>();                                         /* [B] */
   for (int k = warp; k < NX; k += NW) {
@@ -1120,6 +1141,8 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
   }
   uint32_t epoch = g.epoch0;
   uint32_t eval = g.eval_index0;
+  /* sharded population: k_peer_agree (same stream, just before this launch) has compared this rank's request with its peers' */
+  if (g.nranks > 1 && g.abort_flag != nullptr && *(volatile int *)g.abort_flag != 0) return;
   for (long long step = 0; step < g.nsteps; step++) {
     const double t = g.t0 + (double)step * g.h;
     for (int s = 0; s < g.nst; s++) {
@@ -1178,10 +1201,22 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         block_partial_smem<NTC>(red, s_bp);
         if (PF_ON && threadIdx.x == 0) mbar_arrive(&s_go);     /* every consumer has stored (and fenced) this stage */
         if (threadIdx.x < LLW) ll_store_gpu(ll_part + (size_t)blockIdx.x * LLW + threadIdx.x, ll_pack(s_bp[threadIdx.x >> 1], threadIdx.x & 1, tag));
-        for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
-          unsigned long long w; unsigned long long spins = 0;
-          while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
-          s_words[idx] = (uint32_t)w;
+        if (ODX_LL_POLL16) {
+          for (unsigned int idx = threadIdx.x; idx < gridDim.x * NRED; idx += NTC) {
+            unsigned long long w0, w1; unsigned long long spins = 0;
+            for (;;) {
+              ll_load2_gpu(ll_part + 2 * idx, w0, w1);
+              if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+              if (spin_give_up(spins, g.abort_flag)) break;
+            }
+            s_words[2 * idx] = (uint32_t)w0; s_words[2 * idx + 1] = (uint32_t)w1;
+          }
+        } else {
+          for (unsigned int idx = threadIdx.x; idx < gridDim.x * LLW; idx += NTC) {
+            unsigned long long w; unsigned long long spins = 0;
+            while ((uint32_t)((w = ll_load_gpu(ll_part + idx)) >> 32) != tag) { if (spin_give_up(spins, g.abort_flag)) break; }
+            s_words[idx] = (uint32_t)w;
+          }
         }
         cta_sync<NTC>();
         {

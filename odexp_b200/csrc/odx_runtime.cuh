@@ -499,6 +499,32 @@ __global__ void k_peer_allreduce(double *sums, int rank, int nranks, uint32_t ep
   }
 }
 
+/* Before a persistent launch on a sharded population every rank tells its peers (stage count, step count, epoch) through the same
+ * mailbox and compares: a rank that asks for another number of steps would leave the others spinning at a mean-field barrier
+ * until the poll limit (tens of seconds).  On a mismatch the abort code 2 is raised, the step kernel that follows returns at
+ * once, and odx_sync reports it.  Device-side only: no host synchronisation is added to the launch path. */
+__global__ void k_peer_agree(int rank, int nranks, uint32_t epoch, double want0, double want1, double *mailbox, uint32_t *mailflag, PersistArgs g) {
+  const uint32_t tag = epoch + 1u; const size_t par = (size_t)(epoch & 1u);
+  if (threadIdx.x < 2) {
+    for (int r = 0; r < nranks; r++) g.peer_box[r][(par * MAX_RANKS + rank) * NRED + threadIdx.x] = threadIdx.x ? want1 : want0;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < nranks) { volatile uint32_t *f = g.peer_flag[threadIdx.x] + par * MAX_RANKS + rank; *f = tag; }
+  __threadfence_system();
+  if (threadIdx.x < nranks) {
+    volatile uint32_t *f = mailflag + par * MAX_RANKS + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*f != tag) { __nanosleep(64); if (++spins > (1ull << 26)) { *g.abort_flag = 1; break; } }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < nranks && *g.abort_flag == 0) {
+    const double a = __ldcv(&mailbox[(par * MAX_RANKS + threadIdx.x) * NRED + 0]), b = __ldcv(&mailbox[(par * MAX_RANKS + threadIdx.x) * NRED + 1]);
+    if (a != want0 || b != want1) *g.abort_flag = 2;
+  }
+}
+
 static void fill_peer_args(odx_handle *h, PersistArgs &g) {
   g.rank = h->rank; g.nranks = h->nranks; g.epoch0 = h->epoch;
   g.mailbox = h->mail ? mail_box(h->mail) : nullptr; g.mailflag = h->mail ? mail_flag(h->mail) : nullptr;
@@ -533,6 +559,11 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   if (grid > (ring ? h->coop_blocks_tma : h->coop_blocks)) grid = ring ? h->coop_blocks_tma : h->coop_blocks;
   if (grid > PERSIST_MAX_CTAS) grid = PERSIST_MAX_CTAS;
   if (grid < 1) grid = 1;
+  if (h->nranks > 1 && h->peers_attached) {
+    k_peer_agree<<<1, 32, 0, h->stream>>>(h->rank, h->nranks, h->epoch, (double)nsteps, (double)nst * 4294967296.0 + (double)h->epoch, g.mailbox, g.mailflag, g);
+    ODX_TRY(launch_check(h));
+    h->epoch++; g.epoch0 = h->epoch;
+  }
   void *args[] = {(void *)&p, (void *)&g};
   ODX_CUDA(h, cudaLaunchCooperativeKernel(ring ? (const void *)k_chain_persist<TMA_ON> : (const void *)k_chain_persist<false>, dim3((unsigned)grid),
                                           dim3(pt), args, ring ? PF_BYTES : 0, h->stream));
@@ -930,6 +961,7 @@ int odx_sync(odx_handle *h) {
   if (h->mail) {
     int ab = 0;
     ODX_CUDA(h, cudaMemcpy(&ab, mail_abort(h->mail), sizeof ab, cudaMemcpyDeviceToHost));
+    if (ab == 2) { h->err = "ranks disagree on the steps of a persistent launch: every rank must request the same stepper, step count and history of exchanges (INTEGRATION.md)"; return ODX_EFAILED; }
     if (ab) { h->err = "peer exchange timed out: a rank did not reach the mean-field barrier"; return ODX_EFAILED; }
   }
   return ODX_SUCCESS;

@@ -126,6 +126,27 @@ for ssahmin, ps, res, T in [(1.0, 2000, 21, 2.0), (0.0, 60, 6, 1.0)]:
         solo.close()
     dist.barrier()
     pop.close()
+# ---- a rank that asks for another number of steps: every rank gets an error from odx_sync instead of a hung mean-field barrier
+lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "kuramoto.pop"))
+lo, hi = odist.shard_range(100003, rank, world)
+pop = capi.Population(lib, capacity=hi - lo + 64, device=local)
+odist.connect(pop)
+pop.init(hi - lo, replay=False, seed=77)
+pop.run_fixed("dde", 0.0, 0.01, 5); pop.sync()
+msg = ""
+try:
+    pop.run_fixed("dde", 0.05, 0.01, 3 if rank == 0 else 4)
+    pop.sync()
+except Exception as e:
+    msg = str(e)
+flags = [None] * world
+dist.all_gather_object(flags, "disagree" in msg)
+if rank == 0:
+    good = all(flags)
+    ok &= good
+    print("step-count mismatch between ranks: %s -> %s" % (msg[:60] or "no error", "OK" if good else "MISMATCH"), flush=True)
+dist.barrier()
+pop.close()
 if rank == 0:
     print("MGPU_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
