@@ -19,6 +19,7 @@
  *               (delete / clone / append, initial conditions) runs on the device.
  */
 #pragma once
+#include <cooperative_groups.h>
 
 namespace odx {
 
@@ -113,18 +114,22 @@ __global__ void __launch_bounds__(BLOCK) k_scan_add(int32_t *__restrict__ out, c
 
 /* ---- tau-leap kernels ----------------------------------------------------------------------------------------- */
 /* per-particle outcome for particles [first, first+count); flags3[i] = {replicates, rows, dies} for the scans */
+__device__ __forceinline__ int leap_outcome(const Pop &p, int64_t i, double dt, uint32_t stream) {
+  const double death = p.DEATH[i], repli = p.REPLI[i];
+  PhiloxStream rng; rng.k0 = p.k0; rng.k1 = p.k1; rng.id = (uint32_t)p.ID[i]; rng.stream = stream; rng.dom = DOM_LEAP; rng.slot = 0;
+  const double u1 = rng.rand01(), u2 = rng.rand01();
+  int o = OUT_NONE;
+  if ((u1 < death * dt) || (u2 < repli * dt)) {
+    const double u3 = rng.rand01();
+    o = (u3 < death / (death + repli)) ? OUT_DIE : OUT_REPL_DIE;
+  }
+  return o;
+}
 __global__ void __launch_bounds__(BLOCK) k_leap_flags(Pop p, int64_t first, int64_t count, double dt, uint32_t stream,
                                                        int32_t *__restrict__ outcome, int32_t *__restrict__ repl_flag) {
   for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
     const int64_t i = first + q;
-    const double death = p.DEATH[i], repli = p.REPLI[i];
-    PhiloxStream rng; rng.k0 = p.k0; rng.k1 = p.k1; rng.id = (uint32_t)p.ID[i]; rng.stream = stream; rng.dom = DOM_LEAP; rng.slot = 0;
-    const double u1 = rng.rand01(), u2 = rng.rand01();
-    int o = OUT_NONE;
-    if ((u1 < death * dt) || (u2 < repli * dt)) {
-      const double u3 = rng.rand01();
-      o = (u3 < death / (death + repli)) ? OUT_DIE : OUT_REPL_DIE;
-    }
+    const int o = leap_outcome(p, i, dt, stream);
     outcome[i] = o;
     repl_flag[q] = (o == OUT_REPL_DIE) ? 1 : 0;
   }
@@ -132,15 +137,10 @@ __global__ void __launch_bounds__(BLOCK) k_leap_flags(Pop p, int64_t first, int6
 
 /* clone + initial conditions for every replicating particle of [first, first+count): daughter slot = dst0 + off,
  * daughter id = id0 + off.  keep_mother: SSA replication (the mother stays, with her initial conditions re-run). */
-__global__ void __launch_bounds__(BLOCK) k_spawn(Pop p, int64_t first, int64_t count, const int32_t *__restrict__ outcome,
-                                                  const int32_t *__restrict__ off, int64_t dst0, int32_t id0, double t, uint32_t stream,
-                                                  int32_t *__restrict__ child_id) {
-  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
-    const int64_t i = first + q;
-    const int o = outcome[i];
-    if (o != OUT_REPL_DIE && o != OUT_REPL_KEEP) continue;
-    const int64_t j = dst0 + off[q];
-    const int32_t cid = id0 + off[q], mid = p.ID[i];
+__device__ __forceinline__ void spawn_one(const Pop &p, int64_t i, int o, int64_t j, int32_t cid, double t, uint32_t stream,
+                                          int32_t *__restrict__ child_id) {
+  {
+    const int32_t mid = p.ID[i];
     double my[A1(NVAR)], me[A1(NEXPR)], maux[A1(NAUX)], dy[A1(NVAR)], de[A1(NEXPR)];
     load_cols<NVAR>(p.Y, p.stride, i, my);
     load_cols<NEXPR>(p.E, p.stride, i, me);
@@ -166,11 +166,20 @@ __global__ void __launch_bounds__(BLOCK) k_spawn(Pop p, int64_t first, int64_t c
     if (o == OUT_REPL_KEEP) { store_cols<NVAR>(p.Y, p.stride, i, my); store_cols<NEXPR>(p.E, p.stride, i, me); }
   }
 }
+__global__ void __launch_bounds__(BLOCK) k_spawn(Pop p, int64_t first, int64_t count, const int32_t *__restrict__ outcome,
+                                                  const int32_t *__restrict__ off, int64_t dst0, int32_t id0, double t, uint32_t stream,
+                                                  int32_t *__restrict__ child_id) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
+    const int64_t i = first + q;
+    const int o = outcome[i];
+    if (o != OUT_REPL_DIE && o != OUT_REPL_KEEP) continue;
+    spawn_one(p, i, o, dst0 + off[q], id0 + off[q], t, stream, child_id);
+  }
+}
 
 /* de-novo births: slots [dst0, dst0+count), ids id0.. ; par_birth defaults then ode_init_conditions at birth */
-__global__ void __launch_bounds__(BLOCK) k_births(Pop p, int64_t dst0, int64_t count, int32_t id0, double t, uint32_t stream) {
-  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK) {
-    const int64_t j = dst0 + q;
+__device__ __forceinline__ void birth_one(const Pop &p, int64_t j, int32_t id, double t, uint32_t stream) {
+  {
     double y[A1(NVAR)], e[A1(NEXPR)], z[A1(NAUX)], zp[A1(NPSI)];
 #pragma unroll
     for (int v = 0; v < A1(NVAR); v++) y[v] = 0.0;
@@ -180,15 +189,19 @@ __global__ void __launch_bounds__(BLOCK) k_births(Pop p, int64_t dst0, int64_t c
     for (int v = 0; v < A1(NAUX); v++) z[v] = 0.0;
 #pragma unroll
     for (int v = 0; v < A1(NPSI); v++) zp[v] = 0.0;
-    DevCtx c = make_ctx(p, 0.0, stream, DOM_IC + 3, id0 + (int32_t)q);
+    DevCtx c = make_ctx(p, 0.0, stream, DOM_IC + 3, id);
     c.atbirth = 1;
     M::ic(c, t, y, e);
     store_cols<NVAR>(p.Y, p.stride, j, y);
     store_cols<NEXPR>(p.E, p.stride, j, e);
     store_cols<NAUX>(p.AUX, p.stride, j, z);
     store_cols<NPSI>(p.PSI, p.stride, j, zp);
-    p.DEATH[j] = 0.0; p.REPLI[j] = 0.0; p.ID[j] = id0 + (int32_t)q;
+    p.DEATH[j] = 0.0; p.REPLI[j] = 0.0; p.ID[j] = id;
   }
+}
+__global__ void __launch_bounds__(BLOCK) k_births(Pop p, int64_t dst0, int64_t count, int32_t id0, double t, uint32_t stream) {
+  for (int64_t q = (int64_t)blockIdx.x * BLOCK + threadIdx.x; q < count; q += (int64_t)gridDim.x * BLOCK)
+    birth_one(p, dst0 + q, id0 + (int32_t)q, t, stream);
 }
 
 /* scan inputs over the whole sweep: ch0 = keep, ch1 = rows written, ch2 = net deaths before (outcome DIE) */
@@ -241,6 +254,214 @@ __global__ void __launch_bounds__(BLOCK) k_compact(Pop p, AltBufs a, const int32
 #pragma unroll
     for (int c = 0; c < NPSI; c++) a.PSI[(int64_t)c * p.stride + j] = p.PSI[(int64_t)c * p.stride + i];
     a.DEATH[j] = p.DEATH[i]; a.REPLI[j] = p.REPLI[i]; a.ID[j] = p.ID[i];
+  }
+}
+/* ---- the whole tau-leaping sweep in ONE cooperative launch (single GPU) -----------------------------------------------------
+ * The per-generation kernels above cost ~30 launches and one host round trip per generation of daughters (0.86 ms at N = 2^22
+ * for ~0.1 ms of memory traffic).  Here every CTA owns a contiguous chunk of the range a phase walks, so that positions in list
+ * order are (sum over the CTAs in front) + (running offset inside the chunk) + (block scan inside a tile of LEAP_T items): a
+ * chunk total per CTA and one grid barrier replace the three-kernel scans, and the generation loop runs on the device.
+ *   generation g over [first, end):  outcomes (keyed draws) + replicators per chunk | barrier | daughters spawned at
+ *                                    end + position, ids max_id + position | barrier; next generation = the daughters
+ *   de-novo births behind the sweep; survivors / rows / deaths per chunk | barrier |
+ *   event rows in sweep order.  result[] = {survivors, rows, deaths, particles swept, max_id after the daughters, error}.
+ * The stable compaction into the alternate buffers is a plain launch behind it (k_leap_compact, same chunks), so that the rows can
+ * be copied to the host while it runs (written from the kernel straight into pinned host memory they cost 0.4 ms at 2 x 10^5 rows).
+ * Same draws, ids, rows and list order as the per-generation path (tests/test_gpu_events.py compares the two). */
+#ifndef LEAP_T_N
+#define LEAP_T_N 512
+#endif
+constexpr int LEAP_T = LEAP_T_N;
+constexpr int LEAP_MAX_CTAS = 1024;
+struct LeapArgs {
+  AltBufs a; double dt, t; uint32_t stream; int32_t n0, max_id0; int64_t nbirth;
+  int32_t *outcome, *child, *cta_cnt;            /* cta_cnt: [2][LEAP_MAX_CTAS] replicators per chunk (generation parity), [LEAP_MAX_CTAS][3] sweep totals */
+  odx_event_row *rows; int64_t rows_cap; long long *result;
+};
+__device__ __forceinline__ int leap_block_sum(int v, int *s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < LEAP_T / 32; w++) t += s_w[w];
+  return t;
+}
+/* exclusive scan of v over the block (thread order), total in `total` */
+__device__ __forceinline__ unsigned leap_block_scan(unsigned v, unsigned &total, unsigned *s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  __syncthreads();
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  unsigned woff = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < LEAP_T / 32; w++) { const unsigned q = s_w[w]; if (w < warp) woff += q; all += q; }
+  total = all;
+  return woff + x - v;
+}
+/* sum of cnt[0 .. nb) and of the entries in front of blockIdx.x (stride between entries) */
+__device__ __forceinline__ void leap_cta_prefix(const int32_t *cnt, int stride, int nb, int &before, int &all, int *s_w) {
+  int mine_b = 0, mine_a = 0;
+  for (int b = threadIdx.x; b < nb; b += LEAP_T) { const int c = cnt[(size_t)b * stride]; mine_a += c; if (b < (int)blockIdx.x) mine_b += c; }
+  before = leap_block_sum(mine_b, s_w);
+  all = leap_block_sum(mine_a, s_w);
+}
+__global__ void __launch_bounds__(LEAP_T) k_leap_sweep(Pop p, LeapArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int s_w[LEAP_T / 32];
+  const int ncta = (int)gridDim.x;
+  int64_t first = 0, end = p.n;
+  int32_t max_id = a.max_id0;
+  int gen = 0;
+#ifdef LEAP_TIMING
+  int mark = 8;
+#define LEAP_MARK() do { if (blockIdx.x == 0 && threadIdx.x == 0 && mark < 40) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); a.result[mark++] = (long long)tt; } } while (0)
+#else
+#define LEAP_MARK() do { } while (0)
+#endif
+  LEAP_MARK();
+  while (end > first) {
+    const int64_t count = end - first;
+    const int64_t chunk = ((count + ncta - 1) / ncta + LEAP_T - 1) / LEAP_T * LEAP_T;
+    int64_t c0 = first + (int64_t)blockIdx.x * chunk, c1 = c0 + chunk;
+    if (c0 > end) c0 = end;
+    if (c1 > end) c1 = end;
+    int32_t *cnt = a.cta_cnt + (size_t)(gen & 1) * LEAP_MAX_CTAS;
+    int mine = 0;
+    for (int64_t i = c0 + threadIdx.x; i < c1; i += LEAP_T) {
+      const int o = leap_outcome(p, i, a.dt, a.stream);
+      a.outcome[i] = o;
+      mine += (o == OUT_REPL_DIE);
+    }
+    mine = leap_block_sum(mine, s_w);
+    if (threadIdx.x == 0) cnt[blockIdx.x] = mine;
+    LEAP_MARK();
+    grid.sync();
+    LEAP_MARK();
+    int before, nd;
+    leap_cta_prefix(cnt, 1, ncta, before, nd, s_w);
+    if (end + nd > p.stride) { if (blockIdx.x == 0 && threadIdx.x == 0) a.result[5] = 1; return; }      /* the same decision in every CTA */
+    if (mine > 0) {
+      unsigned run = (unsigned)before;
+      for (int64_t t0 = c0; t0 < c1; t0 += LEAP_T) {
+        const int64_t i = t0 + threadIdx.x;
+        const int o = (i < c1) ? a.outcome[i] : OUT_NONE;
+        unsigned tot;
+        const unsigned ex = leap_block_scan(o == OUT_REPL_DIE ? 1u : 0u, tot, (unsigned *)s_w);
+        if (o == OUT_REPL_DIE) spawn_one(p, i, o, end + run + ex, max_id + (int32_t)(run + ex), a.t, a.stream, a.child);
+        run += tot;
+      }
+    }
+    LEAP_MARK();
+    first = end; end += nd; max_id += nd; gen++;
+    if (nd > 0) grid.sync();                       /* the daughters are the next generation */
+  }
+  const int64_t nsweep = end;
+  if (nsweep + a.nbirth > p.stride) { if (blockIdx.x == 0 && threadIdx.x == 0) a.result[5] = 1; return; }
+  for (int64_t q = (int64_t)blockIdx.x * LEAP_T + threadIdx.x; q < a.nbirth; q += (int64_t)ncta * LEAP_T)
+    birth_one(p, nsweep + q, max_id + (int32_t)q, a.t, a.stream);
+  /* survivors, rows and deaths per chunk of the whole sweep */
+  const int64_t chunk = ((nsweep + ncta - 1) / ncta + LEAP_T - 1) / LEAP_T * LEAP_T;
+  int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = c0 + chunk;
+  if (c0 > nsweep) c0 = nsweep;
+  if (c1 > nsweep) c1 = nsweep;
+  int32_t *cnt3 = a.cta_cnt + 2 * LEAP_MAX_CTAS;
+  {
+    int k = 0, r = 0, d = 0;
+    for (int64_t i = c0 + threadIdx.x; i < c1; i += LEAP_T) {
+      const int o = a.outcome[i];
+      k += (o == OUT_NONE); r += (o == OUT_DIE) ? 1 : (o == OUT_REPL_DIE ? 2 : 0); d += (o == OUT_DIE);
+    }
+    k = leap_block_sum(k, s_w); r = leap_block_sum(r, s_w); d = leap_block_sum(d, s_w);
+    if (threadIdx.x == 0) { cnt3[blockIdx.x * 3 + 0] = k; cnt3[blockIdx.x * 3 + 1] = r; cnt3[blockIdx.x * 3 + 2] = d; }
+  }
+  LEAP_MARK();
+  grid.sync();
+  LEAP_MARK();
+  int kb, ka, rb, ra, db, da;
+  leap_cta_prefix(cnt3 + 0, 3, ncta, kb, ka, s_w);
+  leap_cta_prefix(cnt3 + 1, 3, ncta, rb, ra, s_w);
+  leap_cta_prefix(cnt3 + 2, 3, ncta, db, da, s_w);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.result[0] = ka; a.result[1] = ra; a.result[2] = da; a.result[3] = nsweep; a.result[4] = max_id; a.result[5] = 0;
+  }
+  if (a.rows == nullptr) return;
+  /* event rows in sweep order (fwrite_SIM rows of tau_leaping_apply_birthdeath) */
+  int64_t rows_run = rb; int32_t dead_run = db;
+  for (int64_t t0 = c0; t0 < c1; t0 += LEAP_T) {
+    const int64_t i = t0 + threadIdx.x;
+    const int o = (i < c1) ? a.outcome[i] : -1;
+    const unsigned rf = (o == OUT_DIE) ? 1u : (o == OUT_REPL_DIE ? 2u : 0u), df = (o == OUT_DIE) ? 1u : 0u;
+    unsigned tot;
+    const unsigned ex = leap_block_scan(rf | (df << 16), tot, (unsigned *)s_w);
+    if (rf) {
+      const int64_t r = rows_run + (ex & 0xffffu);
+      const int32_t nbefore = a.n0 - (dead_run + (int32_t)(ex >> 16));
+      const int32_t id = p.ID[i];
+      if (o == OUT_DIE) {
+        if (r < a.rows_cap) { odx_event_row e = {nbefore - 1, ODX_STOP_DEATH, {id, -1, -1}}; a.rows[r] = e; }
+      } else {
+        if (r < a.rows_cap) { odx_event_row e = {nbefore + 1, ODX_STOP_REPLI, {id, 1, a.child[i]}}; a.rows[r] = e; }
+        if (r + 1 < a.rows_cap) { odx_event_row e = {nbefore, ODX_STOP_DEATH, {id, -1, -1}}; a.rows[r + 1] = e; }
+      }
+    }
+    rows_run += tot & 0xffffu; dead_run += (int32_t)(tot >> 16);
+  }
+  LEAP_MARK();
+}
+/* stable compaction of the swept list into the alternate buffers: same chunks as k_leap_sweep (same grid), survivors in front of
+ * a chunk from its per-chunk totals; a plain launch behind the cooperative one, so that the event rows can travel to the host
+ * while it runs */
+__global__ void __launch_bounds__(LEAP_T) k_leap_compact(Pop p, LeapArgs a) {
+  __shared__ int s_w[LEAP_T / 32];
+  if (a.result[5] != 0) return;
+  const int ncta = (int)gridDim.x;
+  const int64_t nsweep = a.result[3];
+  const int64_t chunk = ((nsweep + ncta - 1) / ncta + LEAP_T - 1) / LEAP_T * LEAP_T;
+  int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = c0 + chunk;
+  if (c0 > nsweep) c0 = nsweep;
+  if (c1 > nsweep) c1 = nsweep;
+  int kb, ka;
+  leap_cta_prefix(a.cta_cnt + 2 * LEAP_MAX_CTAS, 3, ncta, kb, ka, s_w);
+  int64_t keep_run = kb;
+  for (int64_t t0 = c0; t0 < c1; t0 += LEAP_T) {
+    const int64_t i = t0 + threadIdx.x;
+    const int o = (i < c1) ? a.outcome[i] : -1;
+    unsigned tot;
+    const unsigned ex = leap_block_scan(o == OUT_NONE ? 1u : 0u, tot, (unsigned *)s_w);
+    if (o == OUT_NONE) {
+      const int64_t j = keep_run + ex;
+#pragma unroll
+      for (int c = 0; c < NVAR; c++) a.a.Y[(int64_t)c * p.stride + j] = p.Y[(int64_t)c * p.stride + i];
+#pragma unroll
+      for (int c = 0; c < NEXPR; c++) a.a.E[(int64_t)c * p.stride + j] = p.E[(int64_t)c * p.stride + i];
+#pragma unroll
+      for (int c = 0; c < NAUX; c++) a.a.AUX[(int64_t)c * p.stride + j] = p.AUX[(int64_t)c * p.stride + i];
+#pragma unroll
+      for (int c = 0; c < NPSI; c++) a.a.PSI[(int64_t)c * p.stride + j] = p.PSI[(int64_t)c * p.stride + i];
+      a.a.DEATH[j] = p.DEATH[i]; a.a.REPLI[j] = p.REPLI[i]; a.a.ID[j] = p.ID[i];
+    }
+    keep_run += tot;
+  }
+  /* de-novo births stay behind the survivors of the sweep */
+  for (int64_t q = (int64_t)blockIdx.x * LEAP_T + threadIdx.x; q < a.nbirth; q += (int64_t)ncta * LEAP_T) {
+    const int64_t i = nsweep + q, j = (int64_t)ka + q;
+#pragma unroll
+    for (int c = 0; c < NVAR; c++) a.a.Y[(int64_t)c * p.stride + j] = p.Y[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NEXPR; c++) a.a.E[(int64_t)c * p.stride + j] = p.E[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NAUX; c++) a.a.AUX[(int64_t)c * p.stride + j] = p.AUX[(int64_t)c * p.stride + i];
+#pragma unroll
+    for (int c = 0; c < NPSI; c++) a.a.PSI[(int64_t)c * p.stride + j] = p.PSI[(int64_t)c * p.stride + i];
+    a.a.DEATH[j] = p.DEATH[i]; a.a.REPLI[j] = p.REPLI[i]; a.a.ID[j] = p.ID[i];
   }
 }
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
@@ -316,6 +537,8 @@ __global__ void __launch_bounds__(BLOCK) k_ssa_pick(const double *__restrict__ d
 struct EventBufs {
   double *ssa_tiles = nullptr; int64_t ssa_tiles_cap = 0; long long *ssa_out = nullptr;
   int32_t *xch = nullptr; void *xch_pin = nullptr;                  /* count exchanges of the sharded sweep */
+  int32_t *cta_cnt = nullptr; long long *leap_result = nullptr; int leap_grid = 0;      /* k_leap_sweep */
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_swept = nullptr;
   int32_t *outcome = nullptr, *flag = nullptr, *scan = nullptr, *tile = nullptr, *grand = nullptr, *child = nullptr, *f3 = nullptr, *s3 = nullptr;
   odx_event_row *rows = nullptr; int64_t rows_cap = 0;
   odx_event_row *rows_pin = nullptr; int64_t rows_pin_cap = 0;      /* pinned host copy of the event rows of the last sweep */
@@ -354,10 +577,12 @@ static void odx_events_free(odx_handle *h) {
   if (!h->ev_state) return;
   odx::EventBufs &b = h->ev_state->b;
   void *ptrs[] = {b.outcome, b.flag, b.scan, b.tile, b.grand, b.child, b.f3, b.s3, b.rows, b.alt.Y, b.alt.E, b.alt.AUX, b.alt.PSI,
-                  b.alt.DEATH, b.alt.REPLI, b.alt.ID, b.ssa_tiles, b.ssa_out, b.xch};
+                  b.alt.DEATH, b.alt.REPLI, b.alt.ID, b.ssa_tiles, b.ssa_out, b.xch, b.cta_cnt, b.leap_result};
   for (void *q : ptrs) if (q) cudaFree(q);
   if (b.rows_pin) cudaFreeHost(b.rows_pin);
   if (b.xch_pin) cudaFreeHost(b.xch_pin);
+  if (b.copy_stream) cudaStreamDestroy(b.copy_stream);
+  if (b.ev_swept) cudaEventDestroy(b.ev_swept);
   delete h->ev_state;
   h->ev_state = nullptr;
 }
@@ -776,6 +1001,106 @@ static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_ind
 
 extern "C" {
 
+/* the sweep as one cooperative launch (k_leap_sweep) + the compaction behind it (k_leap_compact); the host reads the counts as soon
+ * as the sweep kernel has ended and copies the event rows on a second stream while the compaction runs.  When the device row buffer
+ * turns out too small for this sweep (it holds a quarter of the capacity + 64 Ki rows at first), the rows are rebuilt afterwards from
+ * the outcomes by the scan kernels of the per-generation path. */
+static int tauleap_fused(odx_handle *h, odx_event_state *es, double t, double dt, uint32_t stream, int32_t n0, double birth_rate,
+                         odx_event_row *rows, int64_t max_rows, int64_t *nrows, const odx_event_row **view_out) {
+  EventBufs &b = es->b;
+  if (!b.cta_cnt) {
+    ODX_CUDA(h, cudaMalloc((void **)&b.cta_cnt, sizeof(int32_t) * 5 * LEAP_MAX_CTAS));
+    ODX_CUDA(h, cudaMalloc((void **)&b.leap_result, sizeof(long long) * 48));
+    ODX_CUDA(h, cudaMemset(b.leap_result, 0, sizeof(long long) * 48));
+    ODX_CUDA(h, cudaStreamCreateWithFlags(&b.copy_stream, cudaStreamNonBlocking));
+    ODX_CUDA(h, cudaEventCreateWithFlags(&b.ev_swept, cudaEventDisableTiming));
+    int occ = 0;
+    ODX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_leap_sweep, LEAP_T, 0));
+    if (occ < 1) { h->err = "k_leap_sweep does not fit on an SM"; return ODX_EFAILED; }
+    if (occ > 2) occ = 2;
+    b.leap_grid = occ * h->sm_count > LEAP_MAX_CTAS ? LEAP_MAX_CTAS : occ * h->sm_count;
+  }
+  long nnew = M::HAS_BIRTH ? odx_draw_poisson(h, birth_rate * dt, h->hr_seeded ? 1 : 0) : 0;     /* the only host draw of a sweep */
+  if (nnew < 0) nnew = 0;
+  const bool want = (rows && max_rows > 0) || view_out;
+  if (want && b.rows_cap < h->cap / 4 + 65536) {
+    if (b.rows) cudaFree(b.rows);
+    b.rows = nullptr; b.rows_cap = 0;
+    ODX_CUDA(h, cudaMalloc((void **)&b.rows, sizeof(odx_event_row) * (size_t)(h->cap / 4 + 65536)));
+    b.rows_cap = h->cap / 4 + 65536;
+  }
+  Pop p = pop_view(h);
+  LeapArgs a;
+  a.a = b.alt; a.dt = dt; a.t = t; a.stream = stream; a.n0 = n0; a.max_id0 = h->max_id; a.nbirth = nnew;
+  a.outcome = b.outcome; a.child = b.child; a.cta_cnt = b.cta_cnt; a.result = b.leap_result;
+  a.rows = want ? b.rows : nullptr; a.rows_cap = want ? b.rows_cap : 0;
+  void *args[] = {(void *)&p, (void *)&a};
+  ODX_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_leap_sweep, dim3((unsigned)b.leap_grid), dim3(LEAP_T), args, 0, h->stream));
+  ODX_CUDA(h, cudaEventRecord(b.ev_swept, h->stream));
+  k_leap_compact<<<b.leap_grid, LEAP_T, 0, h->stream>>>(p, a);
+  ODX_TRY(launch_check(h));
+  h->launches++;
+  /* counts first (behind the sweep, not behind the compaction), then the rows while the compaction runs */
+  long long *pin = reinterpret_cast<long long *>(h->h_pin + NSLOT * NRED);
+  ODX_CUDA(h, cudaStreamWaitEvent(b.copy_stream, b.ev_swept, 0));
+  ODX_CUDA(h, cudaMemcpyAsync(pin, b.leap_result, sizeof(long long) * 6, cudaMemcpyDeviceToHost, b.copy_stream));
+  ODX_CUDA(h, cudaStreamSynchronize(b.copy_stream));
+#ifdef LEAP_TIMING
+  { long long tm[40]; cudaMemcpy(tm, b.leap_result, sizeof tm, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "k_leap_sweep marks (us):"); for (int k = 9; k < 40 && tm[k] > tm[8]; k++) fprintf(stderr, " %.1f", (tm[k] - tm[k - 1]) * 1e-3); fprintf(stderr, "\n");
+    cudaMemset(b.leap_result, 0, sizeof tm); }
+#endif
+  if (pin[5] != 0) { cudaStreamSynchronize(h->stream); h->err = "odx_tauleap_apply: population exceeds the capacity given to odx_create"; return ODX_ENOMEM; }
+  const int64_t kept = pin[0], nr = pin[1], nsweep = pin[3];
+  const int32_t ndead = (int32_t)pin[2];
+  int64_t written = 0;
+  if (want) {
+    if (view_out) max_rows = nr + nnew;
+    written = nr < max_rows ? nr : max_rows;
+    if (b.rows_pin_cap < nr + nnew) {
+      if (b.rows_pin) cudaFreeHost(b.rows_pin);
+      b.rows_pin = nullptr; b.rows_pin_cap = 0;
+      const int64_t cap2 = 2 * (nr + nnew) + 1024;
+      ODX_CUDA(h, cudaMallocHost((void **)&b.rows_pin, sizeof(odx_event_row) * (size_t)cap2));
+      b.rows_pin_cap = cap2;
+    }
+    if (nr <= b.rows_cap) {
+      if (written > 0) ODX_CUDA(h, cudaMemcpyAsync(b.rows_pin, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, b.copy_stream));
+    } else {
+      /* more events than the row buffer held: rebuild the rows from the outcomes (the old columns are untouched until the swap) */
+      int32_t g3[4];
+      const int g = grid_for(h, nsweep);
+      k_sweep_flags<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.f3, nsweep); ODX_TRY(launch_check(h));
+      ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3));
+      cudaFree(b.rows); b.rows = nullptr; b.rows_cap = 0;
+      ODX_CUDA(h, cudaMalloc((void **)&b.rows, sizeof(odx_event_row) * (size_t)(2 * nr + 1024)));
+      b.rows_cap = 2 * nr + 1024;
+      k_event_rows<<<g, BLOCK, 0, h->stream>>>(b.outcome, b.s3, h->ID, b.child, nsweep, n0, b.rows, b.rows_cap); ODX_TRY(launch_check(h));
+      ODX_CUDA(h, cudaMemcpyAsync(b.rows_pin, b.rows, sizeof(odx_event_row) * (size_t)written, cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  ODX_CUDA(h, cudaStreamSynchronize(h->stream));
+  ODX_CUDA(h, cudaStreamSynchronize(b.copy_stream));
+  h->max_id = (int32_t)pin[4];
+  const int32_t n_after_sweep = n0 - ndead;
+  for (int64_t k = 0; k < nnew; k++) {
+    if (want && written < max_rows) {
+      odx_event_row e = {n_after_sweep + (int32_t)k + 1, ODX_STOP_BIRTH, {-1, 1, h->max_id + (int32_t)k}};
+      b.rows_pin[written++] = e;
+    }
+  }
+  h->max_id += (int32_t)nnew;
+  std::swap(h->Y, b.alt.Y); std::swap(h->E, b.alt.E); std::swap(h->AUX, b.alt.AUX); std::swap(h->PSI, b.alt.PSI);
+  std::swap(h->DEATH, b.alt.DEATH); std::swap(h->REPLI, b.alt.REPLI); std::swap(h->ID, b.alt.ID);
+  h->n = kept + nnew;
+  invalidate_state(h);
+  ODX_TRY(refresh_global_n(h));
+  if (rows && written > 0) memcpy(rows, b.rows_pin, sizeof(odx_event_row) * (size_t)written);
+  if (view_out) *view_out = b.rows_pin;
+  if (nrows) *nrows = written;
+  es->event_index++;
+  return ODX_SUCCESS;
+}
 static int tauleap_core(odx_handle *h, double t, double dt, uint64_t leap_index, odx_event_row *rows, int64_t max_rows, int64_t *nrows,
                         const odx_event_row **view_out) {
   ODX_CUDA(h, cudaSetDevice(h->device));
@@ -799,6 +1124,7 @@ static int tauleap_core(odx_handle *h, double t, double dt, uint64_t leap_index,
   const int32_t n0 = (int32_t)h->n;
   double birth_rate = 0.0;
   ODX_TRY(odx_rates(h, nullptr, &birth_rate));
+  if (h->coop_ok && h->leap_fused != 0) return tauleap_fused(h, es, t, dt, stream, n0, birth_rate, rows, max_rows, nrows, view_out);
   /* generations of the sweep: [first, end) -> daughters appended at [end, end + nd) */
   int64_t first = 0, end = h->n;
   int32_t g1[4];

@@ -75,6 +75,7 @@ struct odx_handle {
   uint32_t reinit_index = 0;               /* resets at stopping times so far (Philox stream of the re-drawn ICs) */
   double *stage_dev = nullptr; size_t stage_bytes = 0;   /* AoS staging for upload / download */
   double *gather = nullptr; int32_t *gather_id = nullptr; int64_t gather_cap = 0;   /* all-gathered j-particles (%C, multi-GPU) */
+  int leap_fused = 1;                                                                /* tau-leaping sweep as one cooperative launch (single GPU) */
   double *pair_sym_part = nullptr; size_t pair_sym_len = 0; int *pair_poison = nullptr; int pair_sym = -1;     /* k_pair_sym: [tile][other tile][npsi][PSYM_TILE], flag, option */
   double *pair_part = nullptr; size_t pair_part_len = 0;                             /* [segment][npsi][cap] raw partial sums of k_pair */
   int64_t all_n[MAX_RANKS] = {0, 0, 0, 0, 0, 0, 0, 0};                               /* particles per rank */
@@ -972,6 +973,7 @@ int odx_set_option(odx_handle *h, const char *name, double value) {
   if (strcmp(name, "tma") == 0) { h->tma_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "lean") == 0) { h->lean_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "pair_sym") == 0) { h->pair_sym = (int)value; return ODX_SUCCESS; }
+  if (strcmp(name, "leap_fused") == 0) { h->leap_fused = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "shard_events") == 0) { h->shard_events = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "ssa_device") == 0) { h->ssa_mode = (int)value; return ODX_SUCCESS; }
   if (strcmp(name, "reconstruct") == 0) { h->use_recon = value != 0.0; return ODX_SUCCESS; }

@@ -4,7 +4,8 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi
-lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
+from odexp_b200 import build as _b
+lib = capi.ModelLib(_b.lib_path("vdp_sde_timing")) if os.environ.get("LEAP_TIMING") else capi.ModelLib.from_pop(os.path.join(ROOT, "models", "vdp_sde.pop"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 nsw = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 pop = capi.Population(lib, capacity=2 * n + 8192)

@@ -260,3 +260,51 @@ def test_ssa_pick_device_equals_host(model_lib, n):
     np.testing.assert_array_equal(da["y"], db["y"])
     for p in pops:
         p.close()
+
+
+@pytest.mark.parametrize("model,n,dt,sweeps", [("vdp_sde", 5, 8.0, 4), ("vdp_sde", 70001, 2.0, 4), ("vdp_sde", 1 << 20, 1.0, 3),
+                                               ("vdp_sde", 300000, 40.0, 2), ("lineage", 3001, 4.0, 4)])
+def test_fused_sweep_equals_per_generation_sweep(model_lib, model, n, dt, sweeps):
+    """the tau-leaping sweep as one cooperative launch (k_leap_sweep: device-side generation loop, chunk totals + grid barrier
+    instead of the scan kernels, rows written into pinned host memory) against the per-generation kernels, which the oracle /
+    reference-binary parity tests pinned first (src/methods_odexp.c:1662-1762): identical event rows, ids, states and max_id
+    after every sweep.  dt = 40 makes nearly every particle an event: more rows than the pinned buffer holds at first (the rows
+    are then rebuilt by the scan kernels); lineage: SY / SE / SA and ISDAUGHTER in the daughters' initial conditions."""
+    from odexp_b200 import capi
+    res = []
+    for fused in (0, 1):
+        pop = capi.Population(model_lib(model), capacity=3 * n + 4096)
+        pop.set_option("leap_fused", fused)
+        pop.init(n, replay=False, seed=9)
+        t = pop.run_fixed("fe", 0.0, 0.01, 5)
+        got = []
+        for k in range(sweeps):
+            pop.rhs(t)
+            rows = pop.tauleap_apply(t, dt, k, as_array=True)
+            d = pop.download()
+            got.append((rows.tobytes(), d["id"].copy(), d["y"].copy(), d["expr"].copy(), pop.size()))
+        res.append(got)
+        pop.close()
+    for a, b in zip(*res):
+        assert a[4] == b[4]
+        assert a[0] == b[0]
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[3], b[3])
+    assert len(res[1][0][0]) > 0 or n < 10
+
+
+def test_fused_sweep_capacity_error(model_lib):
+    """daughters beyond the capacity given to odx_create: an error from the call, not a write past the buffers"""
+    from odexp_b200 import capi
+    n = 50000
+    lib = model_lib("vdp_sde")
+    pop = capi.Population(lib, capacity=n + 32)
+    mu = list(lib.par_defaults)                 # par mu, sigma, d, b (models/vdp_sde.pop): no deaths, replication rate 0.5 where x > 0
+    mu[2], mu[3] = 0.0, 0.5
+    pop.set_params(mu)
+    pop.init(n, replay=False, seed=9)
+    pop.rhs(0.0)
+    with pytest.raises(capi.OdxError, match="capacity"):
+        pop.tauleap_apply(0.0, 1.0, 0, as_array=True)
+    pop.close()
