@@ -266,7 +266,7 @@ def config_nbody(capi, odist, rank, world, local, no_peers, peak_hbm):
     pop.close()
     pairs = float(n) * n
     flops = 20.0 * pairs / (ms_eval * 1e-3) / world         # per GPU
-    sym = world == 1
+    sym = True                                               # 128 tiles of 1024 bodies: the symmetric kernel on any number of ranks
     inst = 9.0 if sym else 15.0                              # executed FP64 instructions per ordered pair
     return {"workload": "models/nbody.pop (from examples/Nbody.pop), N=%d bodies, O(N^2) %%C gravity" % n, "n_particles": n,
             "ms_per_rhs_eval": ms_eval, "ms_per_rhs_eval_ordered_kernel": ms_ordered, "pairs_per_s": pairs / (ms_eval * 1e-3),
@@ -275,7 +275,8 @@ def config_nbody(capi, odist, rank, world, local, no_peers, peak_hbm):
             "roofline": {"bound": "fp64", "achieved": flops / 1e12, "peak": FP64_PEAK_FLOPS / 1e12, "unit": "TFLOP/s", "frac": flops / FP64_PEAK_FLOPS,
                          "algorithmic_flops_per_pair": 20, "peak_source": "measured DFMA issue rate x 2 (profiles/r1_fp64_peak.txt); nominal 37.2",
                          "kernel": "k_pair_sym (every unordered pair once, added to both particles; 20 flop are credited per ORDERED pair, "
-                                   "the convention of SURVEY 8(d))" if sym else "k_pair (ordered: one launch per source rank over the allgathered columns)",
+                                   "the convention of SURVEY 8(d); sharded: allgather of the coupled columns, half of every cross-rank tile pair per rank, "
+                                   "the sums for the peers' bodies sent to their owners by ncclSend / ncclRecv)" if sym else "k_pair (ordered)",
                          "fp64_pipe_frac": inst * pairs / (ms_eval * 1e-3) / world / (FP64_PEAK_FLOPS / 2.0),
                          "executed_fp64_inst_per_ordered_pair": inst}}
 

@@ -1514,17 +1514,36 @@ constexpr int PSYM_NYC = psym_count_cols();                       /* dynamical v
 constexpr int psym_col(int c) { int k = 0; for (int v = 0; v < NVAR; v++) if ((M::CPL_SYM_YMASK >> v) & 1u) { if (k == c) return v; k++; } return 0; }
 constexpr size_t PSYM_SMEM = sizeof(double) * ((size_t)PSYM_W * PSYM_NYC * PSYM_SJ + (size_t)A1(NPSI) * PSYM_TILE);
 
+/* Sharded populations: the tiles of all ranks form one list of slots (rank order, tile_base[q] = first slot of rank q); a rank
+ * evaluates the pairs of its own tiles with each other as above, and HALF of the pairs (own tile a, tile b of rank q): those with
+ * a + b even when its rank is the lower one, odd when it is the higher one -- the other rank evaluates the rest, with the roles of
+ * the two tiles exchanged.  The j-side sums of such a pair belong to the other rank: they are written to `part_remote`, summed
+ * over the own tiles (k_pair_sym_remote_sum, ascending tile order) and sent to their owners by grouped ncclSend / ncclRecv
+ * (3 x N / G doubles per pair of ranks); k_pair_sym_finish adds, in ascending rank order, either the own partial blocks or what
+ * the peers sent.  Each rank does N^2 / (2 G) pair evaluations instead of N^2 / G. */
+struct PsymArgs {
+  const double *jsrc;            /* column c of rank q's particles at jsrc + q * jrank_stride + c * jcol_stride */
+  int64_t jcol_stride, jrank_stride;
+  int rank, nranks, nslots;      /* nslots = tiles of all ranks */
+  int tile_base[MAX_RANKS + 1];
+  int64_t all_n[MAX_RANKS];
+  double *part;                  /* [own tile][slot][NPSI][PSYM_TILE]: sums for the own tile from the tile in `slot` */
+  double *part_remote;           /* [slot][own tile][NPSI][PSYM_TILE]: sums for the (remote) tile in `slot` from the own tile */
+};
+__device__ __forceinline__ bool psym_mine(int rank, int q, int a, int b) {      /* which of the two owner ranks evaluates the pair of tiles */
+  return ((a + b) & 1) == (rank < q ? 0 : 1);
+}
 template <bool MASKED>
 __device__ __forceinline__ void psym_block(DevCtx &c, double t, const double (&yi)[PSYM_PI][A1(NVAR)], double (&ai)[PSYM_PI][A1(NPSI)],
                                            const double (&yj)[PSYM_PJ][A1(NVAR)], double (&aj)[PSYM_PJ][A1(NPSI)], int64_t gi0, int64_t gj0,
-                                           int64_t n) {
+                                           int64_t ni, int64_t nj, bool same_list) {
 #pragma unroll
   for (int u = 0; u < PSYM_PI; u++) {
 #pragma unroll
     for (int v = 0; v < PSYM_PJ; v++) {
       if (MASKED) {
         const int64_t gi = gi0 + 32 * u, gj = gj0 + 32 * v;
-        if (gi < n && gj < n && gi != gj) M::template cpl_terms_sym<false>(c, t, yi[u], yj[v], ai[u], aj[v]);
+        if (gi < ni && gj < nj && !(same_list && gi == gj)) M::template cpl_terms_sym<false>(c, t, yi[u], yj[v], ai[u], aj[v]);
       } else {
         M::template cpl_terms_sym<false>(c, t, yi[u], yj[v], ai[u], aj[v]);
       }
@@ -1534,7 +1553,7 @@ __device__ __forceinline__ void psym_block(DevCtx &c, double t, const double (&y
 template <bool MASKED>
 __device__ __forceinline__ void psym_rotate(DevCtx &c, double t, const double (&yi)[PSYM_PI][A1(NVAR)], double (&ai)[PSYM_PI][A1(NPSI)],
                                             double (&aj)[PSYM_PJ][A1(NPSI)], const double *__restrict__ s_pos, int lane, int64_t gi0,
-                                            int64_t jbase, int64_t n) {
+                                            int64_t jbase, int64_t ni, int64_t nj, bool same_list) {
 #pragma unroll 1
   for (int r = 0; r < 32; r++) {
     const int src = (lane + r) & 31;
@@ -1544,7 +1563,7 @@ __device__ __forceinline__ void psym_rotate(DevCtx &c, double t, const double (&
 #pragma unroll
       for (int cc = 0; cc < PSYM_NYC; cc++) yj[v][psym_col(cc)] = s_pos[cc * PSYM_SJ + src + 32 * v];
     }
-    psym_block<MASKED>(c, t, yi, ai, yj, aj, gi0, jbase + src, n);
+    psym_block<MASKED>(c, t, yi, ai, yj, aj, gi0, jbase + src, ni, nj, same_list);
     const int from = (lane + 1) & 31;
 #pragma unroll
     for (int v = 0; v < PSYM_PJ; v++) {
@@ -1553,20 +1572,24 @@ __device__ __forceinline__ void psym_rotate(DevCtx &c, double t, const double (&
     }
   }
 }
-__global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, const double *__restrict__ ysrc, double t,
-                                                                       double *__restrict__ part, int ntile) {
-  const int A = blockIdx.y, B = blockIdx.x;
-  if (B < A) return;
+__global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, const double *__restrict__ ysrc, double t, PsymArgs g) {
+  const int A = blockIdx.y, slot = blockIdx.x;
+  int q = 0;
+  while (q + 1 < g.nranks && slot >= g.tile_base[q + 1]) q++;
+  const int B = slot - g.tile_base[q];
+  const bool local = (q == g.rank);
+  if (local ? (B < A) : !psym_mine(g.rank, q, A, B)) return;
   extern __shared__ __align__(16) double s_psym[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double *s_pos = s_psym + (size_t)w * PSYM_NYC * PSYM_SJ;                    /* this warp's copy of the current j-superblock */
   double *s_acc = s_psym + (size_t)PSYM_W * PSYM_NYC * PSYM_SJ;               /* [NPSI][PSYM_TILE] j-side sums of tile B */
-  const int64_t n = p.n;
+  const int64_t ni = p.n, nj = g.all_n[q];
+  const double *__restrict__ jsrc = g.jsrc + (int64_t)q * g.jrank_stride;
   const int64_t ibase = (int64_t)A * PSYM_TILE + (int64_t)w * PSYM_SI;
   double yi[PSYM_PI][A1(NVAR)], ai[PSYM_PI][A1(NPSI)];
 #pragma unroll
   for (int u = 0; u < PSYM_PI; u++) {
-    int64_t gi = ibase + lane + 32 * u; if (gi > n - 1) gi = n - 1;
+    int64_t gi = ibase + lane + 32 * u; if (gi > ni - 1) gi = ni - 1;
 #pragma unroll
     for (int cc = 0; cc < PSYM_NYC; cc++) yi[u][psym_col(cc)] = ysrc[(int64_t)psym_col(cc) * p.stride + gi];
 #pragma unroll
@@ -1575,16 +1598,16 @@ __global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, con
   for (int idx = threadIdx.x; idx < A1(NPSI) * PSYM_TILE; idx += PSYM_THREADS) s_acc[idx] = 0.0;
   __syncthreads();
   DevCtx c = make_ctx(p, 0.0, 0, DOM_RHS, 0);
-  const bool diag = (A == B);
+  const bool diag = local && (A == B);
 #pragma unroll 1
   for (int s = 0; s < PSYM_NJ; s++) {
     const int jb = (w * (PSYM_NJ / PSYM_W) + s) % PSYM_NJ;
     const int64_t jbase = (int64_t)B * PSYM_TILE + (int64_t)jb * PSYM_SJ;
 #pragma unroll
     for (int v = 0; v < PSYM_PJ; v++) {
-      int64_t gj = jbase + lane + 32 * v; if (gj > n - 1) gj = n - 1;
+      int64_t gj = jbase + lane + 32 * v; if (gj > nj - 1) gj = nj - 1;
 #pragma unroll
-      for (int cc = 0; cc < PSYM_NYC; cc++) s_pos[cc * PSYM_SJ + lane + 32 * v] = ysrc[(int64_t)psym_col(cc) * p.stride + gj];
+      for (int cc = 0; cc < PSYM_NYC; cc++) s_pos[cc * PSYM_SJ + lane + 32 * v] = jsrc[(int64_t)psym_col(cc) * g.jcol_stride + gj];
     }
     __syncwarp();
     double aj[PSYM_PJ][A1(NPSI)];
@@ -1593,10 +1616,10 @@ __global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, con
 #pragma unroll
       for (int k = 0; k < A1(NPSI); k++) aj[v][k] = 0.0;
     }
-    const bool masked = (jbase + PSYM_SJ > n) || (ibase + PSYM_SI > n) || (diag && jbase < ibase + PSYM_SI && ibase < jbase + PSYM_SJ);
-    if (jbase < n && ibase < n) {
-      if (masked) psym_rotate<true>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, n);
-      else psym_rotate<false>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, n);
+    const bool masked = (jbase + PSYM_SJ > nj) || (ibase + PSYM_SI > ni) || (diag && jbase < ibase + PSYM_SI && ibase < jbase + PSYM_SJ);
+    if (jbase < nj && ibase < ni) {
+      if (masked) psym_rotate<true>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, ni, nj, local);
+      else psym_rotate<false>(c, t, yi, ai, aj, s_pos, lane, ibase + lane, jbase, ni, nj, local);
     }
     if (!diag) {
 #pragma unroll
@@ -1607,21 +1630,36 @@ __global__ void __launch_bounds__(PSYM_THREADS, PSYM_MINB) k_pair_sym(Pop p, con
     }
     __syncthreads();
   }
-  double *pa = part + ((size_t)A * ntile + B) * A1(NPSI) * PSYM_TILE;
+  double *pa = g.part + ((size_t)A * g.nslots + slot) * A1(NPSI) * PSYM_TILE;
 #pragma unroll
   for (int u = 0; u < PSYM_PI; u++) {
 #pragma unroll
     for (int k = 0; k < NPSI; k++) pa[(size_t)k * PSYM_TILE + w * PSYM_SI + lane + 32 * u] = ai[u][k];
   }
   if (!diag) {
-    double *pb = part + ((size_t)B * ntile + A) * A1(NPSI) * PSYM_TILE;
+    double *pb = local ? g.part + ((size_t)B * g.nslots + g.tile_base[g.rank] + A) * A1(NPSI) * PSYM_TILE
+                       : g.part_remote + ((size_t)slot * gridDim.y + A) * A1(NPSI) * PSYM_TILE;
     for (int idx = threadIdx.x; idx < NPSI * PSYM_TILE; idx += PSYM_THREADS) pb[idx] = s_acc[idx];
   }
 }
-/* psi_k(i) = scale_k(i) * (sum over the partial blocks of i's tile, ascending other tile) / POP_SIZE; a non-finite result
- * raises *poison (the ordered kernels then redo the evaluation with the exact forms) */
-__global__ void __launch_bounds__(BLOCK) k_pair_sym_finish(Pop p, const double *__restrict__ ysrc, double t, const double *__restrict__ part,
-                                                           int ntile, double *__restrict__ psi, int *__restrict__ poison) {
+/* sharded: out[slot] = sum over the own tiles a that evaluated the pair (a, tile in slot), ascending a; what is sent to the owner */
+__global__ void __launch_bounds__(BLOCK) k_pair_sym_remote_sum(PsymArgs g, int nown, double *__restrict__ out) {
+  const int slot = blockIdx.x;
+  int q = 0;
+  while (q + 1 < g.nranks && slot >= g.tile_base[q + 1]) q++;
+  if (q == g.rank) return;
+  const int B = slot - g.tile_base[q];
+  for (int idx = threadIdx.x; idx < NPSI * PSYM_TILE; idx += BLOCK) {
+    double a = 0.0;
+    for (int A = 0; A < nown; A++)
+      if (psym_mine(g.rank, q, A, B)) a += g.part_remote[((size_t)slot * nown + A) * A1(NPSI) * PSYM_TILE + idx];
+    out[(size_t)slot * A1(NPSI) * PSYM_TILE + idx] = a;
+  }
+}
+/* psi_k(i) = scale_k(i) * (own partial blocks and the peers' contributions, ascending rank and tile) / POP_SIZE; a non-finite
+ * result raises *poison (the ordered kernels then redo the evaluation with the exact forms).  recv: [rank][own tile][NPSI][PSYM_TILE] */
+__global__ void __launch_bounds__(BLOCK) k_pair_sym_finish(Pop p, const double *__restrict__ ysrc, double t, PsymArgs g, int nown,
+                                                           const double *__restrict__ recv, double *__restrict__ psi, int *__restrict__ poison) {
   for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * BLOCK) {
     const int64_t T = i / PSYM_TILE, il = i % PSYM_TILE;
     double sc[A1(NPSI)];
@@ -1637,8 +1675,13 @@ __global__ void __launch_bounds__(BLOCK) k_pair_sym_finish(Pop p, const double *
 #pragma unroll
     for (int k = 0; k < NPSI; k++) {
       double a = 0.0;
-      const double *src = part + ((size_t)T * ntile * A1(NPSI) + k) * PSYM_TILE + il;
-      for (int o = 0; o < ntile; o++) a += src[(size_t)o * A1(NPSI) * PSYM_TILE];
+      const double *src = g.part + ((size_t)T * g.nslots * A1(NPSI) + k) * PSYM_TILE + il;
+      for (int q = 0; q < g.nranks; q++) {
+        const int nb = g.tile_base[q + 1] - g.tile_base[q];
+        for (int b = 0; b < nb; b++)
+          if (q == g.rank || psym_mine(g.rank, q, (int)T, b)) a += src[(size_t)(g.tile_base[q] + b) * A1(NPSI) * PSYM_TILE];
+        if (q != g.rank && nb > 0) a += recv[(((size_t)q * nown + T) * A1(NPSI) + k) * PSYM_TILE + il];
+      }
       a = a * sc[k] / p.n_global;
       bad |= ((__double2hiint(a) & 0x7ff00000) == 0x7ff00000);
       psi[(int64_t)k * p.stride + i] = a;

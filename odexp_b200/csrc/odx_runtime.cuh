@@ -354,47 +354,13 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
     h->pair_part_len = need;
   }
   const int *only_if = nullptr;
-#ifdef ODX_MODEL_CPL_SYM
-  /* antisymmetric couplings on one GPU: every unordered pair once (k_pair_sym), then the ordered kernels below as a pass that
-   * returns at once unless the symmetric one met a non-finite term.  pair_sym: -1 automatic (populations of at least 16 tiles
-   * whose partial blocks fit in 8 GiB), 0 never, 1 always. */
-  {
-    const int64_t ntile = (h->n + PSYM_TILE - 1) / PSYM_TILE;
-    const size_t sym_need = (size_t)ntile * ntile * A1(NPSI) * PSYM_TILE;
-    const bool use_sym = h->nranks <= 1 && h->pair_sym != 0 && (h->pair_sym > 0 || (ntile >= 16 && sym_need * sizeof(double) <= ((size_t)8 << 30)));
-    if (use_sym) {
-      if (h->pair_sym_len < sym_need) {
-        if (h->pair_sym_part) cudaFree(h->pair_sym_part);
-        h->pair_sym_part = nullptr; h->pair_sym_len = 0;
-        ODX_CUDA(h, cudaMalloc((void **)&h->pair_sym_part, sizeof(double) * sym_need));
-        h->pair_sym_len = sym_need;
-      }
-      if (!h->pair_poison) ODX_CUDA(h, cudaMalloc((void **)&h->pair_poison, sizeof(int)));
-      static bool attr_set = false;
-      if (!attr_set) {
-        ODX_CUDA(h, cudaFuncSetAttribute(k_pair_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSYM_SMEM));
-        attr_set = true;
-      }
-      ODX_CUDA(h, cudaMemsetAsync(h->pair_poison, 0, sizeof(int), h->stream));
-      k_pair_sym<<<dim3((unsigned)ntile, (unsigned)ntile), PSYM_THREADS, PSYM_SMEM, h->stream>>>(p, ysrc, t, h->pair_sym_part, (int)ntile);
-      ODX_TRY(launch_check(h));
-      k_pair_sym_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, t, h->pair_sym_part, (int)ntile, h->PSI, h->pair_poison);
-      ODX_TRY(launch_check(h));
-      only_if = h->pair_poison;
-    }
-  }
-#endif
-  if (h->nranks <= 1) {
-    k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, ysrc, h->E, h->ID, h->cap, h->n, t, h->pair_part, 0, only_if);
-    ODX_TRY(launch_check(h));
-  } else {
+  int64_t nmax = 0;
+  const int ncol = PAIR_NCOL;
+  if (h->nranks > 1) {
 #ifdef ODX_HAVE_NCCL_H
-    /* allgather of the coupled columns (nvar[+nexpr] x N doubles per RHS evaluation) into [rank][col][nmax] + ids, then one
-     * launch per source rank in rank order = global list order */
+    /* allgather of the coupled columns (nvar[+nexpr] x N doubles per RHS evaluation) into [rank][col][nmax] + ids */
     if (!h->comm) { h->err = "multi-GPU %C needs odx_comm_init (NCCL allgather)"; return ODX_ENCCL; }
-    int64_t nmax = 0;
     for (int r = 0; r < h->nranks; r++) nmax = h->all_n[r] > nmax ? h->all_n[r] : nmax;
-    const int ncol = PAIR_NCOL;
     if (h->gather_cap < nmax) {
       if (h->gather) cudaFree(h->gather);
       if (h->gather_id) cudaFree(h->gather_id);
@@ -415,15 +381,87 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
     if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
     r = g_nccl.AllGather(sendid, h->gather_id, (size_t)nmax, ncclInt32, h->comm, h->stream);
     if (r != ncclSuccess) { h->err = std::string("ncclAllGather: ") + g_nccl.GetErrorString(r); return ODX_ENCCL; }
-    for (int src = 0; src < h->nranks; src++) {
-      const double *gy = h->gather + (size_t)src * ncol * nmax;
-      k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, gy, gy + (size_t)NVAR * nmax, h->gather_id + (size_t)src * nmax, nmax,
-                                                               h->all_n[src], t, h->pair_part, src * js, nullptr);
-      ODX_TRY(launch_check(h));
-    }
 #else
     h->err = "built without nccl.h"; return ODX_ENCCL;
 #endif
+  }
+#ifdef ODX_MODEL_CPL_SYM
+  /* antisymmetric couplings: every unordered pair once (k_pair_sym), then the ordered kernels below as a pass that returns at once
+   * unless the symmetric one met a non-finite term.  pair_sym: -1 automatic (populations of at least 16 tiles whose partial
+   * blocks fit in 8 GiB), 0 never, 1 always.  Sharded populations: every rank takes the same decision from the rank sizes. */
+  {
+    PsymArgs g; memset(&g, 0, sizeof g);
+    const int nrk = h->nranks > 1 ? h->nranks : 1;
+    g.rank = h->nranks > 1 ? h->rank : 0; g.nranks = nrk;
+    for (int r = 0; r < nrk; r++) {
+      g.all_n[r] = h->nranks > 1 ? h->all_n[r] : h->n;
+      g.tile_base[r + 1] = g.tile_base[r] + (int)((g.all_n[r] + PSYM_TILE - 1) / PSYM_TILE);
+    }
+    g.nslots = g.tile_base[nrk];
+    const int nown = g.tile_base[g.rank + 1] - g.tile_base[g.rank];
+    const size_t TS = (size_t)A1(NPSI) * PSYM_TILE;
+    int maxown = 0;
+    for (int r = 0; r < nrk; r++) maxown = std::max(maxown, g.tile_base[r + 1] - g.tile_base[r]);
+    /* [own][slot] blocks + (sharded) [slot][own] blocks for the peers, their sums per slot, and what the peers send */
+    const size_t sym_need = TS * ((size_t)maxown * g.nslots * (nrk > 1 ? 2 : 1) + (nrk > 1 ? (size_t)g.nslots + (size_t)nrk * maxown : 0));
+    const bool use_sym = h->pair_sym != 0 && (h->pair_sym > 0 || (g.nslots >= 16 && sym_need * sizeof(double) <= ((size_t)8 << 30)));
+    if (use_sym) {
+      if (h->pair_sym_len < sym_need) {
+        if (h->pair_sym_part) cudaFree(h->pair_sym_part);
+        h->pair_sym_part = nullptr; h->pair_sym_len = 0;
+        ODX_CUDA(h, cudaMalloc((void **)&h->pair_sym_part, sizeof(double) * sym_need));
+        h->pair_sym_len = sym_need;
+      }
+      if (!h->pair_poison) ODX_CUDA(h, cudaMalloc((void **)&h->pair_poison, sizeof(int)));
+      static bool attr_set = false;
+      if (!attr_set) {
+        ODX_CUDA(h, cudaFuncSetAttribute(k_pair_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSYM_SMEM));
+        attr_set = true;
+      }
+      g.part = h->pair_sym_part;
+      g.part_remote = g.part + TS * (size_t)maxown * g.nslots;
+      double *sendsum = g.part_remote + TS * (size_t)maxown * g.nslots, *recv = sendsum + TS * (size_t)g.nslots;
+      if (nrk > 1) { g.jsrc = h->gather; g.jcol_stride = nmax; g.jrank_stride = (int64_t)ncol * nmax; }
+      else { g.jsrc = ysrc; g.jcol_stride = h->cap; g.jrank_stride = 0; recv = nullptr; }
+      ODX_CUDA(h, cudaMemsetAsync(h->pair_poison, 0, sizeof(int), h->stream));
+      if (nown > 0) {
+        k_pair_sym<<<dim3((unsigned)g.nslots, (unsigned)nown), PSYM_THREADS, PSYM_SMEM, h->stream>>>(p, ysrc, t, g);
+        ODX_TRY(launch_check(h));
+      }
+#ifdef ODX_HAVE_NCCL_H
+      if (nrk > 1) {
+        if (nown > 0) { k_pair_sym_remote_sum<<<g.nslots, BLOCK, 0, h->stream>>>(g, nown, sendsum); ODX_TRY(launch_check(h)); }
+        /* the sums for the peers' tiles go to their owners, theirs for the own tiles come in: nown x NPSI x PSYM_TILE doubles per peer */
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int q = 0; q < nrk && r == ncclSuccess; q++) {
+          if (q == g.rank) continue;
+          const int nq = g.tile_base[q + 1] - g.tile_base[q];
+          if (nq > 0 && nown > 0) {
+            r = g_nccl.Send(sendsum + TS * (size_t)g.tile_base[q], TS * (size_t)nq, ncclDouble, q, h->comm, h->stream);
+            if (r == ncclSuccess) r = g_nccl.Recv(recv + TS * (size_t)q * nown, TS * (size_t)nown, ncclDouble, q, h->comm, h->stream);
+          }
+        }
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess) { h->err = std::string("ncclSend / ncclRecv (%C sums): ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2); return ODX_ENCCL; }
+      }
+#endif
+      k_pair_sym_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, t, g, nown, recv, h->PSI, h->pair_poison);
+      ODX_TRY(launch_check(h));
+      only_if = h->pair_poison;
+    }
+  }
+#endif
+  if (h->nranks <= 1) {
+    k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, ysrc, h->E, h->ID, h->cap, h->n, t, h->pair_part, 0, only_if);
+    ODX_TRY(launch_check(h));
+  } else {
+    /* one launch per source rank in rank order = global list order */
+    for (int src = 0; src < h->nranks; src++) {
+      const double *gy = h->gather + (size_t)src * ncol * nmax;
+      k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, gy, gy + (size_t)NVAR * nmax, h->gather_id + (size_t)src * nmax, nmax,
+                                                               h->all_n[src], t, h->pair_part, src * js, only_if);
+      ODX_TRY(launch_check(h));
+    }
   }
   k_pair_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, h->pair_part, nsrc * js, h->PSI, only_if);
   return launch_check(h);

@@ -16,6 +16,9 @@ ok = True
 CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 0}),
          ("kuramoto", 100003, "dde", 20, 1e-12, {"tma": 1, "lean": 1}),          # ring / lean step kernels with the NVLink exchange
          ("nbody", 3001, "dde", 2, 1e-12, {}), ("nbody", 2048, "rkf45", 3, 1e-9, {}),
+         # symmetric all-pairs kernel on a sharded population (half of every cross-rank tile pair per rank, sums sent to the owner):
+         # forced at a ragged size against the ordered single-GPU kernel, automatic at 40 tiles against the symmetric single-GPU one
+         ("nbody", 5003, "dde", 2, 1e-12, {"pair_sym": 1}), ("nbody", 40001, "rkf45", 2, 1e-9, {}),
          ("vdp_sde", 50001, "fe", 10, 1e-12, {}), ("vdp_sde", 50001, "fe", 10, 1e-12, {"tma": 1}), ("kuramoto_lowrank", 4097, "dde", 3, 1e-10, {}),
          ("kuramoto_lowrank64", 4099, "dde", 2, 1e-10, {}),
          # model-language coverage added late in round 1: MA()/OA() in %C, low-rank in an auxiliary variable, unweighted lrexp,
