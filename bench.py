@@ -341,8 +341,9 @@ def config_sde(capi, odist, rank, world, local, no_peers, peak_hbm):
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
                          "algorithmic_bytes_per_particle_step": 48, "kernel": "k_chain_persist (Euler-Maruyama)"},
             "tauleap_roofline": {"bound": "hbm", "algorithmic_bytes_per_particle": 72, "what": "read 2 state + 2 rate columns + id, write the compacted 2 state "
-                                 "+ 2 rate columns + id (36 + 36 B); the sweep is ~26 small launches + one host round trip per generation of daughters "
-                                 "(kernel time 0.45 ms of ~0.87 ms at N=2^22, profiles/r2m_tauleap_launches.txt): latency-bound, once per leap interval",
+                                 "+ 2 rate columns + id (36 + 36 B); one GPU: k_leap_sweep (one cooperative launch, device-side generation loop) + "
+                                 "k_leap_compact, event rows copied while the compaction runs (profiles/r2s_tauleap_fused_sweep.txt); sharded: "
+                                 "per-generation kernels + count allgathers + grouped send / recv rebalancing; once per leap interval",
                                  "frac": 72.0 * n / (best * 1e-3) / 1e9 / peak_hbm / world}}
 
 
@@ -403,10 +404,11 @@ def main():
         sampler.start()                                 # before the barrier: nothing is forked or initialised next to the timed launches
     t = 0.0
     # warm-up, device-timed: its rate fixes the length of the continuation BEFORE the timed region, identically on every rank
+    t = pop.run_fixed("dde", t, H_STEP, args.warmup)   # the warm-up proper: kernel loading, first exchanges, peer agreement
     pop.event_record(3)
-    t = pop.run_fixed("dde", t, H_STEP, args.warmup)
+    t = pop.run_fixed("dde", t, H_STEP, max(args.warmup, 5))
     pop.event_record(4)
-    warm_ms = _max_over_ranks(pop.event_elapsed_ms(3, 4) / args.warmup, world)
+    warm_ms = _max_over_ranks(pop.event_elapsed_ms(3, 4) / max(args.warmup, 5), world)      # rate of a warm launch, not of the first one
     extra = max(20, min(4000, int(400.0 / max(warm_ms, 1e-3))))          # ~0.4 s of the same workload
     extra = int(odist.agreed(extra, src=0))
     barrier()
