@@ -331,9 +331,9 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
   ODX_TRY(compute_lowrank(h, ysrc, t));
 #endif
   if (!M::HAS_PAIR) return ODX_SUCCESS;
-  if (h->n <= 0) return ODX_SUCCESS;
+  if (h->n <= 0 && h->nranks <= 1) return ODX_SUCCESS;      /* an empty shard still takes part in the collectives below */
   Pop p = pop_view(h);
-  const int itiles = (int)((h->n + PAIR_ITILE - 1) / PAIR_ITILE);
+  const int itiles = h->n > 0 ? (int)((h->n + PAIR_ITILE - 1) / PAIR_ITILE) : 1;
   /* split the j-range of every source segment until the grid is PAIR_WAVES waves of resident CTAs deep: with ~1.5 waves (the
    * first version at N = 2^17) the half-empty last wave idles a quarter of the GPU */
   static int resident = 0;
@@ -445,8 +445,10 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
         if (r != ncclSuccess || r2 != ncclSuccess) { h->err = std::string("ncclSend / ncclRecv (%C sums): ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2); return ODX_ENCCL; }
       }
 #endif
-      k_pair_sym_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, t, g, nown, recv, h->PSI, h->pair_poison);
-      ODX_TRY(launch_check(h));
+      if (h->n > 0) {
+        k_pair_sym_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, ysrc, t, g, nown, recv, h->PSI, h->pair_poison);
+        ODX_TRY(launch_check(h));
+      }
       only_if = h->pair_poison;
     }
   }
@@ -456,13 +458,14 @@ static int compute_psi(odx_handle *h, const double *ysrc, double t) {
     ODX_TRY(launch_check(h));
   } else {
     /* one launch per source rank in rank order = global list order */
-    for (int src = 0; src < h->nranks; src++) {
+    for (int src = 0; src < h->nranks && h->n > 0; src++) {
       const double *gy = h->gather + (size_t)src * ncol * nmax;
       k_pair<<<dim3(itiles, js), PAIR_THREADS, 0, h->stream>>>(p, ysrc, gy, gy + (size_t)NVAR * nmax, h->gather_id + (size_t)src * nmax, nmax,
                                                                h->all_n[src], t, h->pair_part, src * js, only_if);
       ODX_TRY(launch_check(h));
     }
   }
+  if (h->n <= 0) return ODX_SUCCESS;
   k_pair_finish<<<grid_for(h, h->n), BLOCK, 0, h->stream>>>(p, h->pair_part, nsrc * js, h->PSI, only_if);
   return launch_check(h);
 }

@@ -279,6 +279,34 @@ static void pa_ic(orc_ctx *c, double t, double *y, double *e) {
   y[1] = 0.0;
 }
 
+/* ---------------------------------------------------------------- repel2d.pop: softened antisymmetric all-pairs %C + two %M */
+static const double rp_pars[] = {0.5, 0.05, 0.3};
+static double rp_soft(double dx, double dy, double e) { return pow(dx*dx + dy*dy + e*e, 1.5); }
+static double rp_rep(double a, double b, double dx, double dy, double e) { return (a == b) ? 0.0 : (a - b)/rp_soft(dx, dy, e); }
+static void rp_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double gam = c->mu[2], x = y_[0], y = y_[1], u = y_[2], v = y_[3], FX = psi[0], FY = psi[1], CX = mfd[0], CY = mfd[1];
+  (void)t; (void)e; (void)aux; (void)death; (void)repli;
+  f[0] = u;
+  f[1] = v;
+  f[2] = FX - gam*u - 0.1*(x - CX);
+  f[3] = FY - gam*v - 0.1*(y - CY);
+}
+static void rp_cpl(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi) {
+  (void)e; (void)oe;
+  psi[0] += c->mu[0]*rp_rep(y[0], oy[0], y[0] - oy[0], y[1] - oy[1], c->mu[1]);
+  psi[1] += c->mu[0]*rp_rep(y[1], oy[1], y[0] - oy[0], y[1] - oy[1], c->mu[1]);
+}
+static double rp_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)e; (void)aux; (void)mfd;
+  return k == 0 ? y[0] : y[1];
+}
+static void rp_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t; (void)e;
+  y[0] = orc_rand01(c); y[1] = orc_rand01(c);
+  y[2] = 0.0; y[3] = 0.0;
+}
+
 /* ---------------------------------------------------------------- lineage.pop: SE / SA / SY, exprand / poisson in expressions */
 static const double ln_pars[] = {0.8, 0.05, 0.6};
 static void ln_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
@@ -542,6 +570,7 @@ static const orc_model MODELS[] = {
   {"table_drive", 1, 0, 1, 0, 1, 1, td_pars, td_rhs, td_mfd, NULL, NULL, td_ic, 0, 0, 0, 0, 0, NULL},
   {"lineage", 1, 4, 1, 0, 2, 3, ln_pars, ln_rhs, ln_mfd, ln_birth, NULL, ln_ic, 0, 0, 0, 0, 0, NULL},
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
+  {"repel2d", 4, 0, 0, 2, 2, 3, rp_pars, rp_rhs, rp_mfd, NULL, rp_cpl, rp_ic, 0, 0, 0, 0, 0, NULL},
   {"kuramoto_lrexp", 1, 1, 1, 1, 2, 1, kle_pars, kle_rhs, kle_mfd, NULL, NULL, kle_ic, 1, 0, 0, 0, 0, sin, NULL, NULL, 0, 1},
   {"fun_block", 3, 6, 5, 0, 1, 2, fb_pars, fb_rhs, fb_mfd, NULL, NULL, fb_ic, 0, 0, 0, 0, 0, NULL},
   {"helper_calls", 4, 6, 13, 0, 1, 2, hc_pars, hc_rhs, hc_mfd, NULL, NULL, hc_ic, 0, 0, 0, 0, 0, NULL},

@@ -25,6 +25,7 @@ DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict
         "delay_pop": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1),
         "kuramoto_lrexp": dict(nvar=1, naux=1, npsi=1, nmfd=2, nexpr=1),
         "pair_aux": dict(nvar=2, naux=3, npsi=2, nmfd=1, nexpr=1),
+        "repel2d": dict(nvar=4, naux=0, npsi=2, nmfd=2, nexpr=0),
         "lineage": dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=4),
         "table_drive": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=0),
         "lag_chain": dict(nvar=6, naux=1, npsi=0, nmfd=1, nexpr=0),

@@ -87,3 +87,25 @@ def test_symmetric_pairs_rkf45_trajectory(model_lib):
     assert res[0][2] == res[1][2]                                        # attempts, accepted, rejected
     assert abs(res[0][0] - res[1][0]) <= 1e-9 * res[0][0]                # the step size follows rmax continuously
     np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("meth,n,sym", [("dde", 2500, 0), ("dde", 2500, 1), ("rkf45", 1100, 1), ("fe", 17, 1)])
+def test_soft_repulsion_vs_oracle(model_lib, meth, n, sym):
+    """a second antisymmetric coupling (models/repel2d.pop: softened repulsion in the plane, two of four variables coupled, a
+    parameter inside the pair term, two %M mean fields next to it; restatement bit-identical to the reference binary,
+    tests/test_oracle_port.py) through the ordered and the symmetric kernel against the CPU restatement over several tiles"""
+    from odexp_b200 import capi
+    from oracle import port
+    opts = {"meth": meth, "h0": 0.05, "res": 3, "ps": n, "abstol": 1e-9, "reltol": 1e-9}
+    pop = capi.Population(model_lib("repel2d"), capacity=n + 8)
+    pop.set_option("pair_sym", sym)
+    out = capi.odesolver(pop, (0, 0.5), meth=meth, res=3, popsize=n, h0=0.05, abstol=1e-9, reltol=1e-9, replay_ic=True)
+    pop.close()
+    ref = port.run("repel2d", opts, (0, 0.5))
+    ta, tb = out["traj"], ref["traj"]
+    assert len(ta) == len(tb) and out["report"]["steps"] == ref["report"]["steps"]
+    np.testing.assert_array_equal(ta[ta["step"] == 0]["cols"][:, :4], tb[tb["step"] == 0]["cols"][:, :4])      # replayed ICs
+    np.testing.assert_allclose(ta["cols"][:, :4], tb["cols"][:, :4], rtol=1e-10, atol=1e-12)
+    scale = np.abs(tb["cols"][:, 4:6]).max()
+    assert np.abs(ta["cols"][:, 4:6] - tb["cols"][:, 4:6]).max() <= 1e-11 * scale                             # psi columns
+    np.testing.assert_allclose(out["stats"]["mfd"], ref["stats"]["mfd"], rtol=0, atol=1e-12)

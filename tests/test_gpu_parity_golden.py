@@ -288,6 +288,7 @@ def test_own_auxiliary_in_pairwise_coupling(model_lib, meth, n, ts):
                                             ("helper_calls_dde_n12", 1e-10, 1e-13), ("helper_calls_rkck_n9", 1e-9, 1e-12),
                                             ("delay_pop_dde_n8", 1e-10, 1e-13), ("delay_pop_dde_stop_n5", 1e-10, 1e-13),
                                             ("pair_aux_dde_n30", 1e-10, 1e-12), ("nbody_const_rkf45", 1e-8, 1e-10),
+                                            ("repel2d_dde_n50", 1e-10, 1e-12), ("repel2d_rkf45_n33", 1e-9, 1e-12),
                                             ("lowrank_aux_dde_n100", 1e-10, 1e-9), ("lrexp_dde_n200", 1e-10, 1e-9)])
 def test_model_language_fixtures_against_reference_outputs(model_lib, name, rtol, atol):
     """the model-language fixtures of DESIGN 1.1 against what the UNCHANGED reference binary wrote for them (tests/golden): stats

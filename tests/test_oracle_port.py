@@ -10,7 +10,7 @@ from conftest import load_golden
 
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
                 "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3",
-                "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "nbody_const_rkf45", "lowrank_aux_dde_n100",
+                "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "repel2d_dde_n50", "repel2d_rkf45_n33", "nbody_const_rkf45", "lowrank_aux_dde_n100",
                 "lrexp_dde_n200", "helper_calls_dde_n12", "helper_calls_rkck_n9", "delay_pop_dde_n8", "delay_pop_dde_stop_n5", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
 
 
@@ -77,6 +77,10 @@ REF_CASES = [
     ("pair_aux", {"meth": "dde", "h0": 0.05, "res": 3, "ps": 30}, (0, 2)),
     ("pair_aux", {"meth": "rkf45", "h0": 0.05, "res": 3, "ps": 41}, (0, 2)),
     ("pair_aux", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 7}, (0, 0.5)),
+    # softened antisymmetric all-pairs %C with parameters inside the pair term, next to two %M mean fields
+    ("repel2d", {"meth": "dde", "h0": 0.05, "res": 3, "ps": 50}, (0, 1)),
+    ("repel2d", {"meth": "rkf45", "h0": 0.05, "res": 3, "ps": 33, "abstol": 1e-9, "reltol": 1e-9}, (0, 1)),
+    ("repel2d", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 3}, (0, 0.3)),
     # inheritance at replication (SE / SA / SY, ISDAUGHTER), exprand / poisson inside expressions; tau-leaping and SSA
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 1.0}, (0, 6)),
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 0.0}, (0, 6)),
