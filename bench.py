@@ -37,7 +37,8 @@ H_STEP = 0.05
 ALG_BYTES_PER_PARTICLE_STEP = 72.0
 # measured with ncu --set full on k_chain_persist at N = 2^24 (profiles/, per particle-step): DRAM bytes and executed FP64
 # thread-instructions.  Constants because a number taken under a profiler must not be produced by the bench itself.
-NCU = {"ring-lean": {"dram_bytes": 96.4, "fp64_inst": 217.0, "file": "profiles/r1_k_chain_persist_lean_kuramoto_n16M.txt"}}
+NCU = {"ring-lean": {"dram_bytes": 99.3, "fp64_inst": 196.7, "file": "profiles/r2r_k_chain_persist_lean_kuramoto_n16M.txt (round 2: table sincos; "
+                     "8.33 GB of DRAM traffic and 515.6 M FP64 warp instructions for 5 steps of 2^24 particles)"}}
 FP64_PEAK_INST = 18.47e12                  # DFMA/s, reg,reg,const form, 64 warps/SM: profiles/r1_fp64_peak.txt (scripts/ubench/fp64_issue.cu)
 FP64_PEAK_FLOPS = 2 * FP64_PEAK_INST
 L2_BYTES = 132644864                       # cudaDeviceProp::l2CacheSize of the B200 (the library's variant thresholds use it)
