@@ -727,9 +727,17 @@ __device__ __forceinline__ void chain_sweep(const Pop &p, const ChainArgs &a, co
  * RHS.  While the population sits in L2 the stored scheme is faster (FP64-bound there) and stays in use.
  * ---------------------------------------------------------------------------------------------- */
 constexpr bool LEAN_OK = (NPSI == 0) && !M::RHS_RNG && !M::HAS_STOPIF && !M::HAS_PAIR && !M::HAS_LOWRANK && !M::USES_KY;
+/* ODX_LEAN_RECOMP_Y4 = 1: stage 3 does not store y4 either; stage 4 evaluates k3 = f(y3; M2) itself (M2 kept like M0) and forms y4
+ * from it: 16 + 24 + 24 + 32 = 96 B per particle-step, seven RHS evaluations.  Measured and NOT used (profiles/r2w_kbench_lean_recompute_y4.txt):
+ * 0.347 instead of 0.323 ms per step at 2^24 particles, 0.183 instead of 0.172 at 2^23 -- the stage-by-stage model of DESIGN 3.1 said
+ * -6 %, but the seventh evaluation takes stage 4 from 132 to 428 bytes of spill loads at 80 registers and makes it issue-bound. */
+#ifndef ODX_LEAN_RECOMP_Y4
+#define ODX_LEAN_RECOMP_Y4 0
+#endif
+constexpr bool LEAN_RECOMP_Y4 = ODX_LEAN_RECOMP_Y4 != 0;
 template <int LS, bool EXACT>
-__device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
-                                         int32_t id, const double (&y0)[A1(NVAR)], const double (&e)[A1(NEXPR)],
+__device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd2)[A1(NMFD)],
+                                         const double (&mfd)[A1(NMFD)], int32_t id, const double (&y0)[A1(NVAR)], const double (&e)[A1(NEXPR)],
                                          const double (&y3)[A1(NVAR)], const double (&y4)[A1(NVAR)], double (&yout)[A1(NVAR)],
                                          double (&aux)[A1(NAUX)], double &death, double &repli, double (&tm)[NRED]) {
   double psi[A1(NPSI)], f[A1(NVAR)], f2[A1(NVAR)];
@@ -763,14 +771,29 @@ __device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const
     t_next = t + h;
   } else {
     M::template rhs<EXACT>(c, t, y0, e, psi, mfd0, f, aux, death, repli, USE_HINTS ? &h0 : nullptr);
-    M::template rhs_inc<EXACT>(c, t + h, y4, e, psi, mfd, f2, aux, death, repli, h0, USE_HINTS ? &h1 : nullptr);
     const double r2 = 1.0 / half, r3 = 1.0 / h;
+    if (LEAN_RECOMP_Y4) {
+      double f3[A1(NVAR)], y4r[A1(NVAR)];
+      M::template rhs<EXACT>(c, t + half, y3, e, psi, mfd2, f3, aux, death, repli, nullptr);      /* k3 again: the same instructions as in stage 3 */
 #pragma unroll
-    for (int v = 0; v < NVAR; v++) {
-      double acc = f[v];                                  /* k1 + 2 k2 + 2 k3, then y += h/6 (acc + k4): the order of the stored scheme */
-      acc = acc + 2.0 * ((y3[v] - y0[v]) * r2);
-      acc = acc + 2.0 * ((y4[v] - y0[v]) * r3);
-      yout[v] = y0[v] + (h / 6.0) * (acc + f2[v]);
+      for (int v = 0; v < NVAR; v++) y4r[v] = y0[v] + h * f3[v];
+      M::template rhs_inc<EXACT>(c, t + h, y4r, e, psi, mfd, f2, aux, death, repli, h0, USE_HINTS ? &h1 : nullptr);
+#pragma unroll
+      for (int v = 0; v < NVAR; v++) {
+        double acc = f[v];
+        acc = acc + 2.0 * ((y3[v] - y0[v]) * r2);
+        acc = acc + 2.0 * f3[v];
+        yout[v] = y0[v] + (h / 6.0) * (acc + f2[v]);
+      }
+    } else {
+      M::template rhs_inc<EXACT>(c, t + h, y4, e, psi, mfd, f2, aux, death, repli, h0, USE_HINTS ? &h1 : nullptr);
+#pragma unroll
+      for (int v = 0; v < NVAR; v++) {
+        double acc = f[v];                                  /* k1 + 2 k2 + 2 k3, then y += h/6 (acc + k4): the order of the stored scheme */
+        acc = acc + 2.0 * ((y3[v] - y0[v]) * r2);
+        acc = acc + 2.0 * ((y4[v] - y0[v]) * r3);
+        yout[v] = y0[v] + (h / 6.0) * (acc + f2[v]);
+      }
     }
     tm[RED_RATES] = death + repli;
     hl = &h1; t_next = t + h;
@@ -785,24 +808,24 @@ __device__ __forceinline__ int lean_lane(const Pop &p, const ChainArgs &a, const
 }
 
 template <int LS, bool FULL>
-__device__ __forceinline__ void lean_pair(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
-                                          int64_t i, bool two_rt, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)],
+__device__ __forceinline__ void lean_pair(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd2)[A1(NMFD)],
+                                          const double (&mfd)[A1(NMFD)], int64_t i, bool two_rt, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)],
                                           double (&y3)[2][A1(NVAR)], double (&y4)[2][A1(NVAR)], double (&red)[NRED]) {
   const bool two = FULL ? true : two_rt;
   double yn[2][A1(NVAR)], aux[2][A1(NAUX)], tm[2][NRED];
   double death[2] = {0.0, 0.0}, repli[2] = {0.0, 0.0};
   int32_t id0 = 0, id1 = 0;
   if (M::NEEDS_ID) { id0 = p.ID[i]; id1 = two ? p.ID[i + 1] : id0; }
-  const int s0 = lean_lane<LS, false>(p, a, mfd0, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-  const int s1 = lean_lane<LS, false>(p, a, mfd0, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+  const int s0 = lean_lane<LS, false>(p, a, mfd0, mfd2, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+  const int s1 = lean_lane<LS, false>(p, a, mfd0, mfd2, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   if (s0 | s1) {          /* rare: a sincos argument outside the fast range, or a stage increment too large for angle addition */
-    lean_lane<LS, true>(p, a, mfd0, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
-    lean_lane<LS, true>(p, a, mfd0, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
+    lean_lane<LS, true>(p, a, mfd0, mfd2, mfd, id0, y0[0], e[0], y3[0], y4[0], yn[0], aux[0], death[0], repli[0], tm[0]);
+    lean_lane<LS, true>(p, a, mfd0, mfd2, mfd, id1, y0[1], e[1], y3[1], y4[1], yn[1], aux[1], death[1], repli[1], tm[1]);
   }
 #pragma unroll
   for (int k2 = 0; k2 < NRED; k2++) red[k2] += tm[0][k2] + (two ? tm[1][k2] : 0.0);
   if (LS == 1) store_cols2<NVAR>(p.YS, p.stride, i, two, yn[0], yn[1]);
-  if (LS == 2) store_cols2<NVAR>(p.ACC, p.stride, i, two, yn[0], yn[1]);
+  if (LS == 2 && !LEAN_RECOMP_Y4) store_cols2<NVAR>(p.ACC, p.stride, i, two, yn[0], yn[1]);
   if (LS == 3) {
     store_cols2<NVAR>(p.Y, p.stride, i, two, yn[0], yn[1]);
     if (a.want_out) {
@@ -815,14 +838,14 @@ __device__ __forceinline__ void lean_pair(const Pop &p, const ChainArgs &a, cons
 
 /* ring columns of lean stage LS: Y, E, [YS = y3], [ACC = y4] */
 __device__ __forceinline__ bool lean_has_ys(int ls) { return ls >= 2; }
-__device__ __forceinline__ bool lean_has_acc(int ls) { return ls == 3; }
+__device__ __forceinline__ bool lean_has_acc(int ls) { return ls == 3 && !LEAN_RECOMP_Y4; }
 template <int LS, bool TMA>
-__device__ __forceinline__ void lean_sweep(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd)[A1(NMFD)],
-                                           double (&red)[NRED], TmaRing &ring) {
-  tile_sweep<TMA>(p, a.reverse, LS >= 2, LS == 3, ring,
+__device__ __forceinline__ void lean_sweep(const Pop &p, const ChainArgs &a, const double (&mfd0)[A1(NMFD)], const double (&mfd2)[A1(NMFD)],
+                                           const double (&mfd)[A1(NMFD)], double (&red)[NRED], TmaRing &ring) {
+  tile_sweep<TMA>(p, a.reverse, LS >= 2, LS == 3 && !LEAN_RECOMP_Y4, ring,
                   [&](int64_t i, bool two, auto full, double (&y0)[2][A1(NVAR)], double (&e)[2][A1(NEXPR)], double (&psi)[2][A1(NPSI)],
                       double (&y3)[2][A1(NVAR)], double (&y4)[2][A1(NVAR)]) {
-                    lean_pair<LS, decltype(full)::value>(p, a, mfd0, mfd, i, two, y0, e, y3, y4, red);
+                    lean_pair<LS, decltype(full)::value>(p, a, mfd0, mfd2, mfd, i, two, y0, e, y3, y4, red);
                   });
 }
 
@@ -1100,9 +1123,9 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  double mfd[A1(NMFD)], mfd0[A1(NMFD)];
+  double mfd[A1(NMFD)], mfd0[A1(NMFD)], mfd2[A1(NMFD)];
 #pragma unroll
-  for (int k = 0; k < A1(NMFD); k++) mfd0[k] = 0.0;
+  for (int k = 0; k < A1(NMFD); k++) { mfd0[k] = 0.0; mfd2[k] = 0.0; }
   if (threadIdx.x < NRED) s_tot[threadIdx.x] = (g.sums_y != nullptr) ? g.sums_y[threadIdx.x] : 0.0;
   __shared__ unsigned long long *s_peer[MAX_RANKS];
   if (threadIdx.x == 0) {
@@ -1164,10 +1187,13 @@ __global__ void __launch_bounds__(PF_ON ? PT_TMA : PT_LD, PF_ON ? PERSIST_TMA_CT
         if (s == 0) {
 #pragma unroll
           for (int k = 0; k < A1(NMFD); k++) mfd0[k] = mfd[k];
-          lean_sweep<0, PF_ON>(p, a, mfd0, mfd, red, ring_);
-        } else if (s == 1) lean_sweep<1, PF_ON>(p, a, mfd0, mfd, red, ring_);
-        else if (s == 2) lean_sweep<2, PF_ON>(p, a, mfd0, mfd, red, ring_);
-        else lean_sweep<3, PF_ON>(p, a, mfd0, mfd, red, ring_);
+          lean_sweep<0, PF_ON>(p, a, mfd0, mfd2, mfd, red, ring_);
+        } else if (s == 1) lean_sweep<1, PF_ON>(p, a, mfd0, mfd2, mfd, red, ring_);
+        else if (s == 2) {
+#pragma unroll
+          for (int k = 0; k < A1(NMFD); k++) mfd2[k] = mfd[k];
+          lean_sweep<2, PF_ON>(p, a, mfd0, mfd2, mfd, red, ring_);
+        } else lean_sweep<3, PF_ON>(p, a, mfd0, mfd2, mfd, red, ring_);
       } else if (g.nst == 1) {                            /* Euler */
         a.t_eval = t; a.t_next = t + g.h; a.a = g.h; a.w = 1.0;
         chain_sweep<true, true, PF_ON, USE_SCTAB>(p, a, mfd, red, ring_);
