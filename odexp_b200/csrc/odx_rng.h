@@ -23,6 +23,10 @@
 #define ODX_HD inline
 #endif
 
+#ifndef ODX_FAST_NORMAL
+#define ODX_FAST_NORMAL 1
+#endif
+
 namespace odx {
 
 enum : uint32_t { DOM_RHS = 0x52485300u, DOM_IC = 0x49430000u, DOM_LEAP = 0x4c454150u };
@@ -59,7 +63,12 @@ struct PhiloxStream {
   ODX_HD double randN(double mu, double sigma) {
     uint32_t r[4]; draw4(r);
     const double u1 = u01_from_bits(r[0], r[1]), u2 = u01_from_bits(r[2], r[3]);
+#if defined(__CUDA_ARCH__) && ODX_FAST_NORMAL
+    /* the same two uniforms; cospi needs no range reduction of 2 pi u2 (cos of it costs a Cody-Waite reduction on top) */
+    return mu + sigma * (sqrt(-2.0 * log(u1)) * cospi(2.0 * u2));
+#else
     return mu + sigma * (sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2));
+#endif
   }
   ODX_HD double exprand(double r) { const double u = rand01(); return log(1.0 / (1.0 - u)) / r; }
   /* lambda < 30: Knuth's product method, as the reference composes it (src/rand_gen.c:37-46).  Above that the reference's form
