@@ -160,6 +160,7 @@ struct Pop {
   const double *mu;
   double muv[MUV_N];        /* the parameters by value: kernel-argument (constant bank) operands instead of a load per use */
   uint32_t k0, k1;          /* Philox key */
+  uint32_t rk[20];          /* its ten round keys (philox_round_keys): constant-bank operands of every draw */
   int *stop;                /* sticky STOPIF flag of the whole population (models with STOPIF only) */
   DelayView dl[A1(M::NDELAY)];      /* history stacks of the delay() call sites */
 };
@@ -252,6 +253,9 @@ __device__ __forceinline__ void load_mfd(const Pop &p, const double *__restrict_
 __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
   DevCtx c;
   c.mu = (NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu; c.pop_size = p.n_global; c.h = h;
+#pragma unroll
+  for (int r = 0; r < 20; r++) c.rng.rk[r] = p.rk[r];
+  c.rng.has_rk = 1;
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
   c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   c.ky_base = nullptr; c.ky_i = 0; c.ky_n = 1; c.ky_stride = 0;

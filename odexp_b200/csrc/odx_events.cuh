@@ -116,7 +116,11 @@ __global__ void __launch_bounds__(BLOCK) k_scan_add(int32_t *__restrict__ out, c
 /* per-particle outcome for particles [first, first+count); flags3[i] = {replicates, rows, dies} for the scans */
 __device__ __forceinline__ int leap_outcome(const Pop &p, int64_t i, double dt, uint32_t stream) {
   const double death = p.DEATH[i], repli = p.REPLI[i];
-  PhiloxStream rng; rng.k0 = p.k0; rng.k1 = p.k1; rng.id = (uint32_t)p.ID[i]; rng.stream = stream; rng.dom = DOM_LEAP; rng.slot = 0;
+  PhiloxStream rng;
+#pragma unroll
+  for (int r = 0; r < 20; r++) rng.rk[r] = p.rk[r];
+  rng.has_rk = 1;
+  rng.k0 = p.k0; rng.k1 = p.k1; rng.id = (uint32_t)p.ID[i]; rng.stream = stream; rng.dom = DOM_LEAP; rng.slot = 0;
   const double u1 = rng.rand01(), u2 = rng.rand01();
   int o = OUT_NONE;
   if ((u1 < death * dt) || (u2 < repli * dt)) {

@@ -43,6 +43,22 @@ ODX_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
+/* the same block function with the ten round keys given (rk[2r] = k0 + r W0, rk[2r + 1] = k1 + r W1): when they come from the kernel
+ * arguments they are constant-bank operands of the XORs, and the twenty per-thread additions of the key schedule leave the draw */
+ODX_HD void philox4x32_10_rk(uint32_t c[4], const uint32_t (&rk)[20]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ rk[2 * r], n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ rk[2 * r + 1], n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+}
+ODX_HD void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t (&rk)[20]) {
+  for (int r = 0; r < 10; r++) { rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+}
+
 /* 53-bit uniform in the open interval (0,1) from two 32-bit words */
 ODX_HD double u01_from_bits(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
@@ -54,9 +70,11 @@ struct PhiloxStream {
   uint32_t stream;      /* c[2]  = RHS-evaluation / leap / init index */
   uint32_t dom;         /* c[3]  = domain tag */
   uint32_t slot;        /* c[1]  = running draw index at this call site */
+  uint32_t rk[20];      /* round keys, valid when has_rk (set from the kernel arguments by the device contexts) */
+  int has_rk = 0;
   ODX_HD void draw4(uint32_t out[4]) {
     out[0] = id; out[1] = slot++; out[2] = stream; out[3] = dom;
-    philox4x32_10(out, k0, k1);
+    if (has_rk) philox4x32_10_rk(out, rk); else philox4x32_10(out, k0, k1);
   }
   ODX_HD double rand01() { uint32_t r[4]; draw4(r); return u01_from_bits(r[0], r[1]); }
   /* Box-Muller (cosine branch); one Philox block per normal keeps draws independently addressable */

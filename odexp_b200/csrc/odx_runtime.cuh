@@ -133,7 +133,7 @@ namespace odx {
 static inline Pop pop_view(const odx_handle *h) {
   Pop p;
   p.Y = h->Y; p.YS = h->YS; p.YS_OUT = h->YS; p.Y_OUT = h->Y; p.ACC = h->ACC; p.E = h->E; p.AUX = h->AUX; p.PSI = h->PSI; p.DEATH = h->DEATH; p.REPLI = h->REPLI;
-  p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1;
+  p.KS = h->KS; p.ID = h->ID; p.stride = h->cap; p.n = h->n; p.n_global = h->n_global; p.mu = h->d_mu; p.k0 = h->k0; p.k1 = h->k1; philox_round_keys(h->k0, h->k1, p.rk);
   p.stop = reinterpret_cast<int *>(h->counter + 8);
   for (int k = 0; k < MUV_N; k++) p.muv[k] = (k < NPAR) ? h->h_mu[k] : 0.0;
   for (int k = 0; k < A1(M::NDELAY); k++) { p.dl[k].T = h->dl_T[k]; p.dl[k].X = h->dl_X[k]; p.dl[k].pos = h->dl_pos[k]; p.dl[k].K = M::delay_count(k); }
@@ -593,7 +593,9 @@ static int chain_run_persist(odx_handle *h, int nst, double t0, double hh, int64
   /* TMA-ring variant for populations that stream from HBM, plain loads while the working set is L2-resident; the lean RK4
    * scheme once the working set is well beyond L2 (measured on Kuramoto, ms per step scaled to 2^24 particles: N = 2^21 plain
    * 0.446 / ring 0.461 / lean 0.481, 2^22: 0.437 / 0.403 / 0.422, 2^23: 0.446 / 0.413 / 0.386, 2^24: 0.443 / 0.400 / 0.337) */
-  const double wset = (double)h->n * TMA_NCOL_MAX * sizeof(double);
+  /* columns a step touches: Euler reads and writes Y in place (+ E, PSI); the chain methods also keep a stage state and an accumulator.
+   * vdP SDE at N = 2^22: 67 MB, L2-resident -- the plain variant runs 0.0465 ms per step there, the ring 0.0513 (profiles/r2x_sde_fast_normal.txt) */
+  const double wset = (double)h->n * (nst == 1 ? (NVAR + NEXPR + NPSI) : TMA_NCOL_MAX) * sizeof(double);
   const bool ring = TMA_ON && h->coop_blocks_tma > 0 && (h->tma_mode == 1 || (h->tma_mode < 0 && wset > 0.9 * h->l2_bytes));
   g.lean = (LEAN_OK && ring && nst == 4 && !iterate && (h->lean_mode == 1 || (h->lean_mode < 0 && wset > 1.5 * h->l2_bytes))) ? 1 : 0;   /* ring variant only */
   const int pt = ring ? PT_TMA : PT_LD, per_cta = ring ? TMA_TILE : 2 * PT_LD;
