@@ -551,7 +551,8 @@ struct EventBufs {
 };
 
 template <int NCH>
-static int exclusive_scan(odx_handle *h, const int32_t *in, int32_t *out, int64_t n, int32_t *tile, int32_t *grand, int32_t *grand_host) {
+static int exclusive_scan(odx_handle *h, const int32_t *in, int32_t *out, int64_t n, int32_t *tile, int32_t *grand, int32_t *grand_host,
+                          bool readback = true) {
   const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   if (n > 0) {
     k_scan_tiles<NCH><<<ntiles, BLOCK, 0, h->stream>>>(in, out, tile, n);
@@ -563,6 +564,7 @@ static int exclusive_scan(odx_handle *h, const int32_t *in, int32_t *out, int64_
     k_scan_add<NCH><<<ntiles, BLOCK, 0, h->stream>>>(out, tile, n);
     ODX_TRY(launch_check(h));
   }
+  if (!readback) return ODX_SUCCESS;      /* the totals stay in grand[] on the device (the sharded sweep allgathers them from there) */
   int32_t *pin = reinterpret_cast<int32_t *>(h->h_pin + NSLOT * NRED + 12);       /* pinned: a pageable target makes the copy a staged, blocking one */
   ODX_CUDA(h, cudaMemcpyAsync(pin, grand, sizeof(int32_t) * NCH, cudaMemcpyDeviceToHost, h->stream));
   ODX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -817,8 +819,7 @@ static int allgather_ints(odx_handle *h, EventBufs &b, const int32_t *dev_src, i
 struct Piece { int64_t gstart, cnt, lstart; };
 static int exchange_column(odx_handle *h, const char *src, char *dst, size_t elem, const std::vector<std::vector<Piece>> &pieces,
                            const std::vector<int64_t> &lo, const std::vector<int64_t> &hi) {
-  const int me = h->rank;
-  ODX_NCCL(h, g_nccl.GroupStart());
+  const int me = h->rank;      /* the caller brackets all columns of a redistribution with one ncclGroupStart / ncclGroupEnd */
   for (int q = 0; q < h->nranks; q++) {
     /* what I send to q: my pieces cut to [lo[q], hi[q]) */
     for (const Piece &pc : pieces[me]) {
@@ -839,7 +840,6 @@ static int exchange_column(odx_handle *h, const char *src, char *dst, size_t ele
       ODX_NCCL(h, g_nccl.Recv(dst + (size_t)(a - lo[me]) * elem, (size_t)(e - a) * elem, ncclChar, q, h->comm, h->stream));
     }
   }
-  ODX_NCCL(h, g_nccl.GroupEnd());
   return ODX_SUCCESS;
 }
 
@@ -871,15 +871,14 @@ static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_ind
     sg.first[g] = first;
     const int64_t count = end - first;
     Pop p = pop_view(h);
-    int32_t nd = 0;
     if (count > 0) {
       k_leap_flags<<<grid_for(h, count), BLOCK, 0, h->stream>>>(p, first, count, dt, stream, b.outcome, b.flag);
       ODX_TRY(launch_check(h));
-      ODX_TRY(exclusive_scan<1>(h, b.flag, b.scan, count, b.tile, b.grand, g1));
-      nd = g1[0];
     }
-    ODX_CUDA(h, cudaMemcpyAsync(xsend, &nd, sizeof nd, cudaMemcpyHostToDevice, h->stream));
-    ODX_TRY(allgather_ints(h, b, xsend, 1, all));
+    /* the number of daughters stays on the device: scan total -> allgather -> one host round trip per generation for all ranks' counts */
+    ODX_TRY(exclusive_scan<1>(h, b.flag, b.scan, count, b.tile, b.grand, g1, false));
+    ODX_TRY(allgather_ints(h, b, b.grand, 1, all));
+    const int32_t nd = all[me];
     cgen.push_back(all);
     int64_t ctot_ = 0, before = 0;
     for (int r = 0; r < nrk_; r++) { ctot_ += all[r]; if (r < me) before += all[r]; }
@@ -901,7 +900,7 @@ static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_ind
   /* ---- per-segment totals (survivors, rows, deaths) of every rank */
   int32_t g3[4] = {0, 0, 0, 0};
   if (nsweep > 0) { k_sweep_flags<<<grid_for(h, nsweep), BLOCK, 0, h->stream>>>(b.outcome, b.f3, nsweep); ODX_TRY(launch_check(h)); }
-  ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3));
+  ODX_TRY(exclusive_scan<3>(h, b.f3, b.s3, nsweep, b.tile, b.grand, g3, false));      /* totals read on the device by k_seg_totals */
   k_seg_totals<<<1, 3 * SHARD_MAXGEN, 0, h->stream>>>(b.s3, b.grand, sg, nsweep, xsend);
   ODX_TRY(launch_check(h));
   ODX_TRY(allgather_ints(h, b, xsend, 3 * ngen_, all));
@@ -964,6 +963,7 @@ static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_ind
   /* survivors occupy global positions [0, keep_run); de-novo births [keep_run, Nnew) are created in place by their new owners */
   std::vector<int64_t> hi_s(nrk_), lo_s(nrk_);
   for (int r = 0; r < nrk_; r++) { lo_s[r] = std::min(lo[r], keep_run); hi_s[r] = std::min(hi[r], keep_run); }
+  ODX_NCCL(h, g_nccl.GroupStart());
   for (int c = 0; c < NVAR; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.Y + (size_t)c * h->cap), (char *)(h->Y + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
   for (int c = 0; c < NEXPR; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.E + (size_t)c * h->cap), (char *)(h->E + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
   for (int c = 0; c < NAUX; c++) ODX_TRY(exchange_column(h, (const char *)(b.alt.AUX + (size_t)c * h->cap), (char *)(h->AUX + (size_t)c * h->cap), 8, pieces, lo_s, hi_s));
@@ -971,6 +971,7 @@ static int tauleap_sharded(odx_handle *h, double t, double dt, uint64_t leap_ind
   ODX_TRY(exchange_column(h, (const char *)b.alt.DEATH, (char *)h->DEATH, 8, pieces, lo_s, hi_s));
   ODX_TRY(exchange_column(h, (const char *)b.alt.REPLI, (char *)h->REPLI, 8, pieces, lo_s, hi_s));
   ODX_TRY(exchange_column(h, (const char *)b.alt.ID, (char *)h->ID, 4, pieces, lo_s, hi_s));
+  ODX_NCCL(h, g_nccl.GroupEnd());
   /* de-novo births that fall into my new shard */
   {
     const int64_t a = std::max(lo[me], keep_run), e = std::min(hi[me], Nnew);

@@ -25,9 +25,12 @@ CASES = [("kuramoto", 100003, "dde", 20, 1e-12, {}), ("kuramoto", 100003, "dde",
          # array variables + MA() in %M, {vect} mean fields
          ("pair_aux", 3001, "dde", 3, 1e-12, {}), ("kuramoto_lowrank_aux", 4097, "dde", 3, 1e-10, {}), ("kuramoto_lrexp", 4097, "dde", 3, 1e-10, {}),
          ("chain_array", 50001, "dde", 5, 1e-12, {}), ("vect_meanfield", 50001, "fe", 5, 1e-12, {})]
+ONLY = os.environ.get("MGPU_ONLY", "")               # "leap": only the tau-leaping sections (development runs)
 QUICK = bool(os.environ.get("MGPU_QUICK"))          # a subset for boxes where GPU time is dear (8 ranks): mean field, symmetric %C, one sweep set
 if QUICK:
     CASES = [c for c in CASES if (c[0], c[1]) in (("kuramoto", 100003), ("nbody", 40001), ("nbody", 5003), ("kuramoto_lowrank64", 4099))]
+if ONLY == "leap":
+    CASES = []
 for model, n, meth, nsteps, tol, opts in CASES:
     lib = capi.ModelLib.from_pop(os.path.join(ROOT, "models", model + ".pop"))
     lo, hi = odist.shard_range(n, rank, world)
