@@ -959,6 +959,9 @@ __device__ __forceinline__ unsigned long long ll_load_gpu(const unsigned long lo
 __device__ __forceinline__ void ll_load2_gpu(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+__device__ __forceinline__ void ll_load2_sys(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void ll_store_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1088,19 +1091,27 @@ __device__ __forceinline__ void stage_exchange(const double (&red)[NRED], const 
     a = warp_sum(a);
     if (g.nranks > 1) {
       a = __shfl_sync(0xffffffffu, a, 0);
-      const int r = lane >> 1, half = lane & 1;
-      uint32_t w32 = 0;
-      if (lane < 2 * g.nranks && r != g.rank) {
-        if (blockIdx.x == 0) ll_store_sys(g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + 2 * k + half, ll_pack(a, half, tag));
-        unsigned long long w; unsigned long long spins = 0;
-        while ((uint32_t)((w = ll_load_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + 2 * k + half)) >> 32) != tag) {
+      /* lane r < nranks handles peer r: CTA 0 stores this rank's total of value k as two LL words into the peer's mailbox, every CTA
+       * polls the peer's two words in its own GPU's mailbox with one 16-byte request (148 CTAs x nranks pollers share a few cache
+       * lines of the mailbox: half the requests of a poll per word) */
+      uint32_t wlo = 0, whi = 0;
+      if (lane < g.nranks && lane != g.rank) {
+        const int r = lane;
+        if (blockIdx.x == 0) {
+          unsigned long long *dst = g.peer_ll[r] + (par * MAX_RANKS + g.rank) * LLW + 2 * k;
+          ll_store_sys(dst, ll_pack(a, 0, tag)); ll_store_sys(dst + 1, ll_pack(a, 1, tag));
+        }
+        unsigned long long w0, w1; unsigned long long spins = 0;
+        for (;;) {
+          ll_load2_sys(g.mail_ll + (par * MAX_RANKS + r) * LLW + 2 * k, w0, w1);
+          if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
           if (spin_give_up(spins, g.abort_flag)) break;
         }
-        w32 = (uint32_t)w;
+        wlo = (uint32_t)w0; whi = (uint32_t)w1;
       }
       double tot = 0.0;
       for (int q = 0; q < g.nranks; q++) {
-        const uint32_t lo = __shfl_sync(0xffffffffu, w32, 2 * q), hi = __shfl_sync(0xffffffffu, w32, 2 * q + 1);
+        const uint32_t lo = __shfl_sync(0xffffffffu, wlo, q), hi = __shfl_sync(0xffffffffu, whi, q);
         tot += (q == g.rank) ? a : ll_unpack(lo, hi);
       }
       a = tot;
