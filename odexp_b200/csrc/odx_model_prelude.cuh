@@ -207,6 +207,19 @@ ODX_HD double odx_sel(bool c, double a, double b) { return c ? a : b; }
 /* STOPIF(cond): raise the stop flag, value is the condition (src/odexp.h:400-406) */
 template <class C> ODX_HD int odx_stopif(C &c, int cond) { if (cond) c.stop = 1; return cond; }
 
+/* interp(x, y, xi, nx, start) on user arrays (src/utils_odexp.c:173-203): piecewise-linear interpolation at xi in the table (x, y) whose
+ * abscissae increase circularly from `start`; dichotomy search with the reference's index arithmetic (the same code serves delay() through
+ * DevCtx::delay_lookup).  The reference prints a message when xi lies in front of the table and goes on: so does this, without the message. */
+ODX_HD double interp(const double *x, const double *y, double xi, int nx, int start) {
+  int i1 = 0, i9 = nx - 1;
+  while (i9 > i1 + 1) {
+    const int i5 = (i1 + i9 + 1) / 2;
+    if (x[(start + i5) % nx] > xi) i9 = i5; else i1 = i5;
+  }
+  if (i1 == i9) return y[(i1 + start) % nx];
+  return y[(i1 + start) % nx] + (y[(i9 + start) % nx] - y[(i1 + start) % nx]) * (xi - x[(i1 + start) % nx]) / (x[(i9 + start) % nx] - x[(i1 + start) % nx]);
+}
+
 /* device twins of the pure helpers a model expression may call (src/utils_odexp.c:11-107) */
 ODX_HD double sum(const double *array, long len) { double s = 0.0; for (long i = 0; i < len; i++) s += array[i]; return s; }
 ODX_HD double sumsub(const double *array, const long *ind, long len)      /* const: a `decl const long idx[]` array is the usual argument */ { double s = 0.0; for (long i = 0; i < len; i++) s += array[ind[i]]; return s; }

@@ -459,8 +459,6 @@ class Emitter:
             if not (where.startswith("aux ") or where.startswith("d") or where == "rhs") or exact:
                 raise PopError("delay() is only supported inside AUX / D/DT expressions (%s)" % where)
             e = e[:b] + "odx_c.delay_lookup(%d, (%s) - (%s), (long)(%s))" % self._delay_site(args, where) + e[en:]
-        if re.search(r"\binterp\s*\(", e):
-            raise PopError("interp() on user arrays is not supported on the device (%s)" % where)
         e = re.sub(r"\bDWDT\b", "odx_c.dwdt()", e)
         e = re.sub(r"\b(rand01|randN|exprand|poisson)\s*\(", lambda mm: "odx_c.%s(" % mm.group(1), e)
         e = re.sub(r"\bPOP_SIZE\b", "((int)odx_c.pop_size)", e)      # SIM->pop->size is an int in the reference (src/odexp.h): 1/POP_SIZE is 0

@@ -362,6 +362,38 @@ static void td_ic(orc_ctx *c, double t, double *y, double *e) {
   y[0] = td_tab[ID % 4][2] + 0.1*orc_rand01(c);
 }
 
+/* ---------------------------------------------------------------- interp_drive.pop: interp() on constant user arrays */
+static const double id_pars[] = {0.8};
+static const double id_tx[] = { 0.0, 0.5, 1.25, 2.0, 3.5, 4.0 }, id_ty[] = { 0.0, 1.0, 0.25, -0.5, 0.75, 0.0 };
+static const double id_rx[] = { 2.0, 3.5, 4.0, 0.0, 0.5, 1.25 }, id_ry[] = { -0.5, 0.75, 0.0, 0.0, 1.0, 0.25 };
+static double id_interp(const double *x, const double *y, double xi, int nx, int start) {      /* src/utils_odexp.c:173-203 */
+  int i1 = 0, i9 = nx - 1, i5;
+  while (i9 > i1 + 1) {
+    i5 = (i1 + i9 + 1)/2;
+    if (x[(start + i5) % nx] > xi) { i9 = i5; } else { i1 = i5; }
+  }
+  if (i1 == i9) return y[(i1 + start) % nx];
+  return y[(i1 + start) % nx] + (y[(i9 + start) % nx] - y[(i1 + start) % nx])*(xi - x[(i1 + start) % nx])/(x[(i9 + start) % nx] - x[(i1 + start) % nx]);
+}
+static void id_rhs(orc_ctx *c, double t, const double *y_, const double *e, const double *psi, const double *mfd, double *f,
+                   double *aux, double *death, double *repli) {
+  const double k = c->mu[0], ph = e[0], x = y_[0], XM = mfd[0];
+  const double drive = id_interp(id_tx, id_ty, fmod(t + ph, 4.0), 6, 0);
+  const double rot = id_interp(id_rx, id_ry, fmod(t + ph, 4.0), 6, 3);
+  (void)psi; (void)death; (void)repli;
+  f[0] = -k*x + drive + 0.5*rot - 0.1*XM;
+  aux[0] = drive; aux[1] = rot;
+}
+static double id_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  (void)c; (void)k; (void)e; (void)aux; (void)mfd;
+  return y[0];
+}
+static void id_ic(orc_ctx *c, double t, double *y, double *e) {
+  (void)t;
+  e[0] = 0.5*orc_rand01(c);
+  y[0] = 0.1*orc_rand01(c);
+}
+
 /* ---------------------------------------------------------------- lag_chain.pop (LET L 5): LAG -> linear chain of hidden variables */
 static const double lg_pars[] = {2.0, 1.0};
 static double lg_linchaindelay(const double root, const double *chain, const int link, const double delay, const int len) {
@@ -568,6 +600,7 @@ static void vm_ic(orc_ctx *c, double t, double *y, double *e) { (void)t; (void)e
 static const orc_model MODELS[] = {
   {"lag_chain", 6, 0, 1, 0, 1, 2, lg_pars, lg_rhs, lg_mfd, NULL, NULL, lg_ic, 0, 0, 0, 0, 0, NULL},
   {"table_drive", 1, 0, 1, 0, 1, 1, td_pars, td_rhs, td_mfd, NULL, NULL, td_ic, 0, 0, 0, 0, 0, NULL},
+  {"interp_drive", 1, 1, 2, 0, 1, 1, id_pars, id_rhs, id_mfd, NULL, NULL, id_ic, 0, 0, 0, 0, 0, NULL},
   {"lineage", 1, 4, 1, 0, 2, 3, ln_pars, ln_rhs, ln_mfd, ln_birth, NULL, ln_ic, 0, 0, 0, 0, 0, NULL},
   {"pair_aux", 2, 1, 3, 2, 1, 2, pa_pars, pa_rhs, pa_mfd, NULL, pa_cpl, pa_ic, 0, 0, 0, 0, 0, NULL},
   {"repel2d", 4, 0, 0, 2, 2, 3, rp_pars, rp_rhs, rp_mfd, NULL, rp_cpl, rp_ic, 0, 0, 0, 0, 0, NULL},

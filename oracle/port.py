@@ -28,6 +28,7 @@ DIMS = {"kuramoto": dict(nvar=1, naux=2, npsi=0, nmfd=3, nexpr=1), "nbody": dict
         "repel2d": dict(nvar=4, naux=0, npsi=2, nmfd=2, nexpr=0),
         "lineage": dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=4),
         "table_drive": dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=0),
+        "interp_drive": dict(nvar=1, naux=2, npsi=0, nmfd=1, nexpr=1),
         "lag_chain": dict(nvar=6, naux=1, npsi=0, nmfd=1, nexpr=0),
         "nbody_const": dict(nvar=6, naux=0, npsi=3, nmfd=0, nexpr=0),
         "kuramoto_lowrank_aux": dict(nvar=1, naux=2, npsi=1, nmfd=2, nexpr=7)}

@@ -41,6 +41,8 @@ CASES = {
     "delay_pop_dde_n8": ("delay_pop", dict(FULL, meth="dde", h0=0.05, res=5, ps=8), (0, 4), dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1)),
     "delay_pop_dde_stop_n5": ("delay_pop", dict(FULL, meth="dde", h0=0.05, res=4, ps=5), (0, 1.0, 2.5), dict(nvar=1, naux=1, npsi=0, nmfd=1, nexpr=1)),
     "pair_aux_dde_n30": ("pair_aux", dict(FULL, meth="dde", h0=0.05, res=3, ps=30), (0, 2), dict(nvar=2, naux=3, npsi=2, nmfd=1, nexpr=1)),
+    "interp_drive_dde_n12": ("interp_drive", dict(FULL, meth="dde", h0=0.05, res=5, ps=12), (0, 5), dict(nvar=1, naux=2, npsi=0, nmfd=1, nexpr=1)),
+    "interp_drive_rkck_n7": ("interp_drive", dict(FULL, meth="rkck", h0=0.05, res=5, ps=7), (0, 5), dict(nvar=1, naux=2, npsi=0, nmfd=1, nexpr=1)),
     "repel2d_dde_n50": ("repel2d", dict(FULL, meth="dde", h0=0.05, res=3, ps=50), (0, 1), dict(nvar=4, naux=0, npsi=2, nmfd=2, nexpr=0)),
     "repel2d_rkf45_n33": ("repel2d", dict(FULL, meth="rkf45", h0=0.05, res=3, ps=33, abstol=1e-9, reltol=1e-9), (0, 1), dict(nvar=4, naux=0, npsi=2, nmfd=2, nexpr=0)),
     "nbody_const_rkf45": ("nbody_const", dict(FULL, meth="rkf45", h0=0.1, res=11, ps=3, abstol=1e-8, reltol=1e-8, hmin=0), (0, 20),

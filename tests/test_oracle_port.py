@@ -10,7 +10,7 @@ from conftest import load_golden
 
 GOLDEN_CASES = ["kuramoto_shipped_rkck", "kuramoto_dde_n64", "kuramoto_dde_n1000", "kuramoto_dde_h003_n257", "kuramoto_fe_n100", "kuramoto_rkck_n200",
                 "kuramoto_rkf45_n200", "kuramoto_rk4_n50", "nbody_dde_n64", "nbody_rkf45_n96", "ring_dde_n50", "ring_fe_n3",
-                "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "repel2d_dde_n50", "repel2d_rkf45_n33", "nbody_const_rkf45", "lowrank_aux_dde_n100",
+                "chain_array_dde_n20", "fun_block_rkf45_n21", "pair_aux_dde_n30", "repel2d_dde_n50", "repel2d_rkf45_n33", "interp_drive_dde_n12", "interp_drive_rkck_n7", "nbody_const_rkf45", "lowrank_aux_dde_n100",
                 "lrexp_dde_n200", "helper_calls_dde_n12", "helper_calls_rkck_n9", "delay_pop_dde_n8", "delay_pop_dde_stop_n5", "vect_meanfield_tauleap", "lineage_tauleap_n20", "lineage_ssa_n20"]
 
 
@@ -85,6 +85,10 @@ REF_CASES = [
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 1.0}, (0, 6)),
     ("lineage", {"meth": "fe", "h0": 0.01, "res": 31, "ps": 20, "ssahmin": 0.0}, (0, 6)),
     ("lineage", {"meth": "rkck", "h0": 0.1, "res": 13, "ps": 50, "ssahmin": 1.0}, (0, 6)),
+    # interp() on constant user arrays, from the start of the table and from a rotated start
+    ("interp_drive", {"meth": "dde", "h0": 0.05, "res": 5, "ps": 12}, (0, 5)),
+    ("interp_drive", {"meth": "rkck", "h0": 0.05, "res": 5, "ps": 7}, (0, 5)),
+    ("interp_drive", {"meth": "fe", "h0": 0.01, "res": 3, "ps": 3}, (0, 1)),
     # FILE table (read from a text file at generation time) indexed by ID
     ("table_drive", {"meth": "dde", "h0": 0.05, "res": 4, "ps": 10}, (0, 3)),
     ("table_drive", {"meth": "rkf45", "h0": 0.05, "res": 4, "ps": 23}, (0, 3)),
