@@ -5,7 +5,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from odexp_b200 import capi, build
-VARIANTS = {"p44b2": (4, 4, 2), "p44b1": (4, 4, 1), "p82b1": (8, 2, 1), "p42b2": (4, 2, 2), "p84b1": (8, 4, 1), "p22b4": (2, 2, 4), "p81b2": (8, 1, 2)}
+VARIANTS = {"p82b1": (8, 2, 1), "p82b3": (8, 2, 3), "p81b3": (8, 1, 3), "p44b2": (4, 4, 2)}
+if os.environ.get("PSYM_ALL"):
+    VARIANTS.update({"p44b1": (4, 4, 1), "p42b2": (4, 2, 2), "p84b1": (8, 4, 1), "p22b4": (2, 2, 4), "p81b2": (8, 1, 2)})
 pop_path = os.path.join(ROOT, "models", "nbody.pop")
 if "--build" in sys.argv:
     for name, (pi, pj, mb) in VARIANTS.items():
@@ -19,7 +21,7 @@ for name in VARIANTS:
     lib = capi.ModelLib(so)
     pop = capi.Population(lib, capacity=n)
     pop.init(n, replay=False)
-    for sym in ((0, 1) if name == "p44b2" else (1,)):
+    for sym in ((0, 1) if name == "p82b1" else (1,)):
         pop.set_option("pair_sym", sym)
         pop.rhs(0.0); pop.sync()
         reps = 5
