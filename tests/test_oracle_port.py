@@ -216,7 +216,11 @@ int main(int argc, char **argv) {
   if (argc > 1 && strcmp(argv[1], "kat") == 0) {
     uint32_t c[4], k[2];
     while (scanf("%x %x %x %x %x %x", &c[0], &c[1], &c[2], &c[3], &k[0], &k[1]) == 6) {
+      uint32_t c2[4] = {c[0], c[1], c[2], c[3]}, rk[20];
       odx::philox4x32_10(c, k[0], k[1]);
+      odx::philox_round_keys(k[0], k[1], rk);           /* the form the device contexts use: round keys as kernel arguments */
+      odx::philox4x32_10_rk(c2, rk);
+      if (memcmp(c, c2, sizeof c) != 0) { printf("round-key form differs\n"); return 1; }
       printf("%08x %08x %08x %08x\n", c[0], c[1], c[2], c[3]);
     }
   } else if (argc > 4 && strcmp(argv[1], "poisson") == 0) {       /* poisson <lambda> <n> <first id>: one draw per particle id */
