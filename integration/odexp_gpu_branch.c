@@ -244,6 +244,8 @@ int odx_gpu_odesolver(int solver, double_array *tspan, int *status_out) {
   if (EVENT_TYPE != EVENT_ABORT) EVENT_TYPE = EVENT_NONE;
   else printf("\n  simulation aborted\n");
   if (getenv("ODEXP_CUDA_DUMP_POP")) dump_population(getenv("ODEXP_CUDA_DUMP_POP"));
+  if (rep.hmin_reached)      /* the reference's one-time warning (:604-612) */
+    ADD_MSG_TO_BUFF("  warning: hmin reached at t = %f (h=%f). Continuing with h = %e", rep.hmin_t, o.hmin, o.hmin);
   /* the reference's closing line (:736-741); `function` = time inside pop_rhs, which here is all device time */
   PRINTV("\n  total: %s%g msec%s,", T_VAL, rep.total_ms, T_NOR);
   PRINTV(" solver: %s%g msec%s,", T_VAL, rep.solver_ms, T_NOR);

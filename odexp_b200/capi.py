@@ -43,7 +43,7 @@ class SolverOpts(C.Structure):
 
 class SolverReport(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("solver_ms", C.c_double), ("steps", C.c_int64), ("particle_steps", C.c_double),
-                ("status", C.c_int), ("final_n", C.c_int64)]
+                ("status", C.c_int), ("final_n", C.c_int64), ("hmin_reached", C.c_int), ("hmin_t", C.c_double)]
 
 
 # every symbol include/odx.h declares (tests check that the library exports all of them)
@@ -373,7 +373,7 @@ def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, a
         raise OdxError("odx_odesolver: status %d: %s" % (st, pop.L.odx_last_error(pop.h).decode()))
     res_ = read_outputs(outdir, pop.lib.dims(), read_traj=read_traj)
     res_["report"] = dict(total_ms=rep.total_ms, solver_ms=rep.solver_ms, steps=rep.steps, particle_steps=rep.particle_steps,
-                          final_n=rep.final_n)
+                          final_n=rep.final_n, hmin_reached=int(rep.hmin_reached), hmin_t=rep.hmin_t)
     res_["outdir"] = outdir
     if own:
         import shutil

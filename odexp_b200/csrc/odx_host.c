@@ -163,6 +163,7 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
   const odx_model_info *mi = odx_model();
   const double t_start = now_ms();
   double tot_solver = 0.0;
+  int hmin_alert = 0; double hmin_t = 0.0;
   double t, t1, dt, tnext, dt_ssa, dt_leaping, dt_dyn, dt_next, sum_rates = 0.0, birth_rate = 0.0, expected_dt_ssa;
   double hstep = o->h0;
   int res = o->res;
@@ -291,7 +292,10 @@ int odx_odesolver(odx_handle *h, const odx_solver_opts *o, odx_solver_report *re
         }
         if (status != ODX_SUCCESS) { stop_flag = ODX_EVENT_GSL; break; }
         steps++; particle_steps += (double)n_step;
-        if (hstep < o->hmin) hstep = o->hmin;
+        if (hstep < o->hmin) {                 /* :604-612: continue with h = hmin, tell the user once */
+          hstep = o->hmin;
+          if (!hmin_alert && t < t1) { hmin_alert = 1; hmin_t = t; }
+        }
       }
       /* the interval's steps are queued: write the frames that have landed while the GPU works */
       if (status == ODX_SUCCESS && (status = flush_frames(h, &os)) != 0) stop_flag = ODX_EVENT_GSL;
@@ -349,7 +353,7 @@ done:
   free(os.mfd); free(os.y); free(os.e); free(os.aux); free(os.psi); free(os.ids);
   if (rep) {
     rep->total_ms = now_ms() - t_start; rep->solver_ms = tot_solver; rep->steps = steps; rep->particle_steps = particle_steps;
-    rep->status = status; rep->final_n = n;
+    rep->status = status; rep->final_n = n; rep->hmin_reached = hmin_alert; rep->hmin_t = hmin_t;
   }
   return status;
 }

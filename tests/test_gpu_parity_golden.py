@@ -381,3 +381,17 @@ def test_interp_forcing_adaptive(model_lib, meth, tol, bound):
     np.testing.assert_array_equal(a[a["step"] == 0]["cols"][:, 0], b[b["step"] == 0]["cols"][:, 0])
     assert np.abs(a["cols"][:, 0] - b["cols"][:, 0]).max() <= bound
     assert abs(out["report"]["steps"] - ref["report"]["steps"]) <= 0.15 * ref["report"]["steps"]
+
+
+def test_hmin_warning_is_reported(model_lib):
+    """`h < hmin` after an adaptive step: the run goes on with h = hmin and the driver reports the first time it happened, like the
+    reference's one-time "warning: hmin reached at t = ..." (src/methods_odexp.c:604-612); the drop-in branch prints it from the report"""
+    from odexp_b200 import capi
+    got = {}
+    for hmin in (1e-5, 2e-2):
+        pop = capi.Population(model_lib("interp_drive"), capacity=1024)
+        out = capi.odesolver(pop, (0, 5), meth="rkck", res=5, popsize=7, h0=0.05, hmin=hmin, abstol=1e-8, reltol=1e-8, replay_ic=True)
+        pop.close()
+        got[hmin] = out["report"]
+    assert got[1e-5]["hmin_reached"] == 0
+    assert got[2e-2]["hmin_reached"] == 1 and 0.0 < got[2e-2]["hmin_t"] < 5.0

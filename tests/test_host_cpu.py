@@ -173,12 +173,14 @@ def test_ctypes_mirror_matches_the_c_structs(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "odx.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", '
                    'sizeof(odx_solver_opts), offsetof(odx_solver_opts, outdir), offsetof(odx_solver_opts, mu), offsetof(odx_solver_opts, quick), '
-                   'offsetof(odx_solver_opts, particle), sizeof(odx_solver_report), offsetof(odx_solver_report, final_n)); return 0; }\n')
+                   'offsetof(odx_solver_opts, particle), sizeof(odx_solver_report), offsetof(odx_solver_report, final_n)); '
+                   'printf("%zu %zu\\n", offsetof(odx_solver_report, hmin_reached), offsetof(odx_solver_report, hmin_t)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout.split()]
     O, R = capi.SolverOpts, capi.SolverReport
-    assert got == [C.sizeof(O), O.outdir.offset, O.mu.offset, O.quick.offset, O.particle.offset, C.sizeof(R), R.final_n.offset]
+    assert got == [C.sizeof(O), O.outdir.offset, O.mu.offset, O.quick.offset, O.particle.offset, C.sizeof(R), R.final_n.offset,
+                   R.hmin_reached.offset, R.hmin_t.offset]
 
 
 def test_emit_rejects_unsupported():
