@@ -253,9 +253,15 @@ __device__ __forceinline__ void load_mfd(const Pop &p, const double *__restrict_
 __device__ __forceinline__ DevCtx make_ctx(const Pop &p, double h, uint32_t stream, uint32_t dom, int32_t id) {
   DevCtx c;
   c.mu = (NPAR >= 1 && NPAR <= MUV_MAX) ? p.muv : p.mu; c.pop_size = p.n_global; c.h = h;
+  /* round keys from the kernel arguments only where the RHS draws (DWDT, rand01 ... in AUX / D/DT / rates): in a model without them the
+   * twenty words would only add to the register pressure of the step kernels (Kuramoto ring kernel: 132 -> 332 bytes of spill loads) */
+  if (M::RHS_RNG) {
 #pragma unroll
-  for (int r = 0; r < 20; r++) c.rng.rk[r] = p.rk[r];
-  c.rng.has_rk = 1;
+    for (int r = 0; r < 20; r++) c.rng.rk[r] = p.rk[r];
+    c.rng.has_rk = 1;
+  } else {
+    c.rng.has_rk = 0;
+  }
   c.rng.k0 = p.k0; c.rng.k1 = p.k1; c.rng.id = (uint32_t)id; c.rng.stream = stream; c.rng.dom = dom; c.rng.slot = 0;
   c.id = id; c.oid = id; c.atbirth = 0; c.atrepli = 0; c.ist0 = 0; c.sis_y = c.sis_e = c.sis_aux = nullptr; c.has_sister = 0; c.stop = 0; c.slow = 0;
   c.ky_base = nullptr; c.ky_i = 0; c.ky_n = 1; c.ky_stride = 0;
