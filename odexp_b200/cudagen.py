@@ -120,6 +120,8 @@ def _ternary_to_select(expr: str) -> str:
     cond, a, b = e[:q].strip(), e[q + 1:c].strip(), e[c + 1:].strip()
     if re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF)\b", a + " " + b):
         return expr
+    if re.search(r"\[[^\]]*[A-Za-z_][^\]]*\]", a + " " + b):
+        return expr            # an arm indexes an array with a computed index (`(i == 0) ? a : X[i-1]`): the guard may be what keeps it in range
     return "odx_sel(%s, %s, %s)" % (cond, _ternary_to_select(a), _ternary_to_select(b))
 
 

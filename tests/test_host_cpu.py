@@ -266,3 +266,45 @@ def test_two_model_libraries_coexist(model_lib):
     a, b = model_lib("kuramoto"), model_lib("nbody")
     assert a.name == "kuramoto" and b.name == "nbody"
     assert (a.nvar, a.nmfd, a.npsi) == (1, 3, 0) and (b.nvar, b.nmfd, b.npsi) == (6, 0, 3)
+
+
+def test_antisymmetric_coupling_detection():
+    """OdxModel::CPL_SYM (the symmetric all-pairs kernel evaluates a term once and adds it to both particles) is claimed only when the
+    emitter can prove term(j, i) = -term(i, j) bit for bit: guarded difference times a factor that reads the particles through squares
+    of differences only.  Anything else keeps the ordered kernel."""
+    from odexp_b200 import popfile, cudagen
+    head = "par m 2.0\npar e 0.1\nexpr w rand01()\nfun nc(a,b) = pow(a*a+b*b+0.01,1.5);\n"
+    tail = "dx/dt = P\ndy/dt = -y\ninit x rand01()\ninit y rand01()\n"
+    yes = ["%C P MU(m)*((MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y)))",
+           "%C P -3.0*((MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/pow((MY(y)-OY(y))*(MY(y)-OY(y))+MU(e)*MU(e),1.5))",
+           "%C P ((MY(y) == OY(y)) ? 0.0 : (MY(y)-OY(y))/nc(OY(x)-MY(x),MY(y)-OY(y)))"]        # (oy - y)^2 is even as well
+    no = ["%C P OE(w)*((MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y)))",     # the other particle's weight
+          "%C P (MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y))",                   # not a function of the difference
+          "%C P (MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y))*(MY(y)-OY(y))",  # odd factor: symmetric, not antisymmetric
+          "%C P sin(OY(x)-MY(x))",                                                                # antisymmetric, but not in the proven form
+          # a guard that is the whole expression stays a C conditional (only guards inside functions / parentheses become selects: a bare
+          # `(i == 0) ? a : X[i-1]` must not evaluate its other arm), so it is not recognised either
+          "%C P (MY(y) == OY(y)) ? 0.0 : (MY(y)-OY(y))/nc(OY(x)-MY(x),MY(y)-OY(y))",
+          "%C P (MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y))*rand01()"]
+    for line in yes:
+        cu = cudagen.emit_cuda(popfile.parse(head + line + "\n" + tail, name="sym"))
+        assert "CPL_SYM = true" in cu and "#define ODX_MODEL_CPL_SYM 1" in cu, line
+    for line in no:
+        cu = cudagen.emit_cuda(popfile.parse(head + line + "\n" + tail, name="sym"))
+        assert "CPL_SYM = false" in cu and "ODX_MODEL_CPL_SYM" not in cu, line
+    # two couplings: both must qualify
+    two = "%C P (MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y))\n%C Q OY(y)-MY(y)\n"
+    cu = cudagen.emit_cuda(popfile.parse(head + two + "dx/dt = P + Q\ndy/dt = -y\ninit x rand01()\ninit y rand01()\n", name="sym"))
+    assert "CPL_SYM = false" in cu
+
+
+def test_guarded_array_access_stays_a_conditional():
+    """ternary -> select evaluates both arms; an arm that indexes an array with a computed index may rely on the guard to stay in range
+    (`(i == 0) ? a : X[i-1]`), so such a ternary is left alone even inside parentheses"""
+    from odexp_b200 import popfile, cudagen
+    txt = "par k 1\ndX[i=0:3]/dt = ((i == 0) ? -k*X[0] : k*(X[i-1] - X[i]))\ninit X[i=0:3] 1.0\n"
+    cu = cudagen.emit_cuda(popfile.parse(txt, name="g"))
+    line = [l for l in cu.splitlines() if "odx_f[" in l][0]
+    assert "?" in line and "odx_sel" not in line
+    txt = "par k 1\nfun pick(a,b) = (a > b) ? a : b;\naux m pick(x, k)\ndx/dt = -m\ninit x 1.0\n"
+    assert "odx_sel(" in cudagen.emit_cuda(popfile.parse(txt, name="g2"))         # pure arms: still a select
