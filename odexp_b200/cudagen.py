@@ -128,7 +128,7 @@ def _ternary_to_select(expr: str) -> str:
 def _ternary_to_select_nested(expr: str) -> str:
     """apply _ternary_to_select to every parenthesised sub-expression that is a whole ternary (after function inlining the
     guards of the model functions sit inside parentheses)"""
-    out, i = [], 0
+    out, i, brackets = [], 0, 0
     while i < len(expr):
         if expr[i] == "(":
             depth, j = 1, i + 1
@@ -137,24 +137,71 @@ def _ternary_to_select_nested(expr: str) -> str:
                 depth -= expr[j] == ")"
                 j += 1
             inner = _ternary_to_select_nested(expr[i + 1:j - 1])
-            conv = _ternary_to_select(inner)
+            conv = inner if brackets else _ternary_to_select(inner)      # inside an array subscript the value must stay an integer
             out.append("(" + conv + ")")
             i = j
         else:
+            brackets += expr[i] == "["
+            brackets -= expr[i] == "]"
             out.append(expr[i])
             i += 1
     return "".join(out)
 
 
-def _div_peephole(expr: str) -> str:
-    """`x / f(args)` -> `x * odx_rcp(f(args))` for divisions by a function call.
-    A double division costs ~20 instructions on the GPU; as a reciprocal it becomes a pure call the compiler can share
-    between terms that divide by the same quantity (the three force components of the N-body fixture divide by one r^3).
-    Result differs from the IEEE quotient by at most 1.5 ulp."""
+_DOUBLE_ATOM = re.compile(r"(?<![\w.])(\d+\.\d*|\.\d+|\d+[eE][-+]?\d+)|odx_o?(y|e|aux)\[|odx_(mfd|psi)\[|odx_c\.mu\[")
+
+
+def _is_double_valued(den: str, double_funs) -> bool:
+    """can the C type of this denominator (a call `f(...)` or a parenthesised expression) be shown to be double from its text?  A call
+    of a function known to return a double; or a parenthesised expression without comparison / logical / conditional / modulo operators
+    whose top level (plain parentheses, arguments of double-valued calls excluded from nothing, arguments of other calls ignored)
+    holds a floating-point literal, a double-valued call or a state / expression / mean-field / parameter reference."""
+    d = _strip_outer_parens(den.strip())
+    mm = re.match(r"^(%s)\s*\(" % IDENT, d)
+    if mm:
+        calls = list(_find_call(d, mm.group(1)))
+        if calls and calls[0][0] == 0 and calls[0][1] == len(d):
+            return mm.group(1) in _DOUBLE_FUNS or mm.group(1) in double_funs
+    if re.search(r"[<>=!&|?:%]", d):
+        return False
+    # blank out the argument lists of calls that are not known to return a double: what they read says nothing about their type
+    flat, i = [], 0
+    for mc in re.finditer(r"(%s)\s*\(" % IDENT, d):
+        if mc.start() < i:
+            continue
+        name = mc.group(1)
+        j, depth = mc.end(), 1
+        while j < len(d) and depth:
+            depth += d[j] == "("
+            depth -= d[j] == ")"
+            j += 1
+        if name in _DOUBLE_FUNS or name in double_funs:
+            return True
+        flat.append(d[i:mc.start()])
+        i = j
+    flat.append(d[i:])
+    rest = "".join(flat)
+    if _DOUBLE_ATOM.search(rest):
+        return True
+    names = getattr(double_funs, "double_names", ())
+    return any(tok in names for tok in re.findall(IDENT, re.sub(r"(?<![\w.])\d+[eE][-+]?\d+", "", rest)))
+
+
+_DOUBLE_FUNS = {"pow", "sqrt", "exp", "log", "fabs", "cosh", "sinh", "tanh", "hypot", "cbrt", "odx_pow05", "odx_pow15", "odx_pow2", "odx_pow3"}
+
+
+def _div_peephole(expr: str, double_funs=frozenset()) -> str:
+    """`x / f(args)` -> `x * odx_rcp(f(args))` for divisions by a call of a function that returns a double (libm, the pow peepholes,
+    one-line model functions).  A double division costs ~20 instructions on the GPU; as a reciprocal it becomes a pure call the
+    compiler can share between terms that divide by the same quantity (the three force components of the N-body fixture divide by
+    one r^3).  Result differs from the IEEE quotient by at most 1.5 ulp.  A division by a parenthesised expression or by anything else
+    is left alone: `1/POP_SIZE`, `ID/(2)`, `7/(ID+1)` are integer divisions in the reference's C (POP_SIZE and ID are ints), and a
+    reciprocal would silently turn them into floating-point ones."""
     out, pos = [], 0
     pat = re.compile(r"/\s*(%s)?\s*\(" % IDENT)
+    start = 0
     while True:
-        m = pat.search(expr, pos)
+        m = pat.search(expr, max(pos, start))
         if not m:
             out.append(expr[pos:])
             return "".join(out)
@@ -166,7 +213,10 @@ def _div_peephole(expr: str) -> str:
         if depth:
             out.append(expr[pos:])
             return "".join(out)
-        out.append(expr[pos:m.start()] + "* odx_rcp(" + (m.group(1) or "") + "(" + _div_peephole(expr[m.end():i - 1]) + "))")
+        if not _is_double_valued((m.group(1) or "") + "(" + expr[m.end():i - 1] + ")", double_funs):
+            start = m.end()                 # leave this division alone, look at the ones behind (and inside) it
+            continue
+        out.append(expr[pos:m.start()] + "* odx_rcp(" + (m.group(1) or "") + "(" + _div_peephole(expr[m.end():i - 1], double_funs) + "))")
         pos = i
 
 
@@ -378,6 +428,19 @@ class Emitter:
         self.psi_idx = {c.name: i for i, c in enumerate(m.cpls)}
         self.aux_idx = {e.name: m.index_of(m.auxs, e.name) for e in m.auxs}
         self.delay_sites = []
+        # model functions that return a double: one-liners always do, a block only without a `return (int|long|char|float)` cast
+        class _Names(frozenset):
+            pass
+        self.double_funs = _Names(f.name for f in m.funs if not (f.block and re.search(r"return\s*\((int|long|char|float)\)", f.body)))
+        # identifiers that are doubles in the generated code: dynamical variables, expressions, auxiliaries, parameters, mean fields,
+        # couplings (scalars: an array name alone is a pointer) and `decl const double` scalars; the arguments of the model functions
+        dn = {e.name for e in list(m.eqs) + list(m.exprs) + list(m.auxs) if not e.length}
+        dn |= {e.name for e in m.pars} | {e.name for e in m.mfds} | {c.name for c in m.cpls}
+        dn |= {n for t, n, d, init in m.consts if "double" in t and not d}
+        for f in m.funs:
+            dn |= {a.strip() for a in f.args if re.fullmatch(IDENT, a.strip())}
+        dn.add("t")
+        self.double_funs.double_names = frozenset(dn)
         self.expr_base = {}
         k = 0
         for e in m.exprs:
@@ -481,7 +544,7 @@ class Emitter:
         if self.fast_pow and not exact:
             e = _pow_peephole(e)
         if self.fast_div and not exact:
-            e = _rpow_peephole(_div_peephole(e))
+            e = _rpow_peephole(_div_peephole(e, self.double_funs))
             e = _ternary_to_select_nested(e)
             if zmul:
                 e = _zmul_peephole(e)
@@ -627,7 +690,7 @@ class Emitter:
                 w("ODX_HD %s %s(%s) { ODX_CONSTS %s }" % (rt.group(1) if rt else "double", mangle(f.name), args, _mangle_expr(f.body)))
                 continue
             body = _pow_peephole(f.body) if self.fast_pow else f.body
-            body = _div_peephole(body) if self.fast_div else body
+            body = _div_peephole(body, self.double_funs) if self.fast_div else body
             body = _mangle_expr(_ternary_to_select(body))
             w("ODX_HD double %s(%s) { ODX_CONSTS return %s; }" % (mangle(f.name), args, body))
         w("")

@@ -96,6 +96,11 @@ class Gen:
             e += self.r.choice(["+", "-", " + ", " - "]) + self.term(d)
         return e
 
+    def int_division(self):
+        """integer divisions of the reference's C (ID and POP_SIZE are ints): a reciprocal peephole must leave them alone"""
+        return self.r.choice(["ID/(2)", "7/(ID+1)", "1/POP_SIZE", "(ID+3)/(POP_SIZE)", "ID/(POP_SIZE-1)", "(2*ID+1)/(2)", "ID/(1+ID/(2))",
+                              "3/(2.0+ID)", "ID/(%s+1.5)" % self.r.choice(self.atoms), "POP_SIZE/(ID+1)*%s" % self.atom()])
+
     def gravity_like(self):
         """the exact shape the N-body example has: -c*MU(p)*gr(MY(v), OY(v), differences...)"""
         v = self.r.choice(["x", "y"])
@@ -113,7 +118,7 @@ def _model_text(seed):
         cexprs.append(e)
         L.append("%%C C%d %s" % (k, e))
     for k in range(NEXPR_A):
-        e = ga.expr(2)
+        e = ga.expr(2) if k % 6 else "%s*(%s) + %s" % (ga.atom(), ga.int_division(), ga.int_division())
         aexprs.append(e)
         L.append("aux A%d %s" % (k, e))
     L += ["dx/dt = -x + C0", "dy/dt = -y", "init x rand01()", "init y rand01()", "timespan 0 1", "opt popmode population", "opt popsize 4"]
@@ -148,7 +153,7 @@ int main() {
     if (it %% 5 == 2) { oy[0] = y[0]; oy[1] = y[1]; oe[0] = e[0]; }
     if (it %% 7 == 3) oy[1] = y[1];
     const double t = 0.37 * it;
-    Ctx c = {mu, 4.0, 0.1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    Ctx c = {mu, 4.0, 0.1, 3 + it %% 7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double pf[NC], pr[NC], sc[NC];
     for (int k = 0; k < NC; k++) { pf[k] = 0.0; pr[k] = 0.0; sc[k] = 1.0; }
     fastm::OdxModel::cpl_terms<true>(c, t, y, e, aux, oy, oe, oaux, pf);
