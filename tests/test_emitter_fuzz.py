@@ -56,7 +56,7 @@ class Gen:
         return "pow(%s+%s,0.5)" % (self.sq(d), self.num())
 
     def factor(self, d):
-        k = self.r.randrange(10) if d > 0 else self.r.randrange(3)
+        k = self.r.randrange(12) if d > 0 else self.r.randrange(3)
         if k <= 1:
             return self.atom()
         if k == 2:
@@ -74,6 +74,13 @@ class Gen:
             return "pow(%s,%s)" % (self.sq(d - 1) + "+0.5", self.r.choice(["2", "3", "1.5", "0.5", "2.7"]))
         if k == 8:
             return "h2(%s,%s)" % (self.expr(d - 1), self.expr(d - 1))
+        if k == 10:                                          # sin / cos of one argument: hoisted into one odx_sincos by the emitter
+            # arguments of moderate size: at 1e9 a rounding error of the argument alone is worth 1e-7 in the cosine
+            a = "%s*%s+%s" % (self.atom(), self.atom(), self.atom())
+            b = "%s-%s" % (self.atom(), self.atom())
+            return self.r.choice(["sin(%s)" % a, "cos(%s)" % a, "(sin(%s)*cos(%s))" % (a, a), "(cos(%s)-sin(%s))" % (a, b)])
+        if k == 11:
+            return "exp(-(%s))" % self.sq(d - 1)
         return "((%s > %s) ? %s : %s)" % (self.expr(d - 1), self.expr(d - 1), self.expr(d - 1), self.expr(d - 1))
 
     def term(self, d):
@@ -152,7 +159,7 @@ int main() {
     if (it %% 5 == 1) oy[0] = y[0];                  /* guards: equal coordinates, then the self pair */
     if (it %% 5 == 2) { oy[0] = y[0]; oy[1] = y[1]; oe[0] = e[0]; }
     if (it %% 7 == 3) oy[1] = y[1];
-    const double t = 0.37 * it;
+    const double t = 0.01 * it;
     Ctx c = {mu, 4.0, 0.1, 3 + it %% 7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double pf[NC], pr[NC], sc[NC];
     for (int k = 0; k < NC; k++) { pf[k] = 0.0; pr[k] = 0.0; sc[k] = 1.0; }
