@@ -308,3 +308,23 @@ def test_guarded_array_access_stays_a_conditional():
     assert "?" in line and "odx_sel" not in line
     txt = "par k 1\nfun pick(a,b) = (a > b) ? a : b;\naux m pick(x, k)\ndx/dt = -m\ninit x 1.0\n"
     assert "odx_sel(" in cudagen.emit_cuda(popfile.parse(txt, name="g2"))         # pure arms: still a select
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the unchanged reference binary on the host cores; needs no GPU): one JSON line with the same metric /
+    config as the GPU arm, `impl`, a `cpu_baseline` describing the sample and an `e2e` equal to the value"""
+    import json, subprocess, sys
+    from conftest import ROOT
+    from oracle import refrun
+    if not refrun.have("kuramoto"):
+        pytest.skip("oracle/_ref not built here")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"], capture_output=True,
+                       text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1, r.stderr[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("particle-steps/sec") and d["unit"] == "particle-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e5
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "n_particles" in d["config"] and "workload" in d["config"]
