@@ -100,6 +100,24 @@ def build(force=False, verbose=False):
     return True
 
 
+def build_one(name, pop_text):
+    """one more model.out under oracle/_ref/<name>/ from a .pop text (tests that generate models: tests/test_emitter_vs_reference.py);
+    the reference library must have been built (build())"""
+    objs = [os.path.join(OUT, "obj", s + ".o") for s in LIB_SRCS + ["stubs", "minigsl", "rand_hook"]]
+    if not available() or not all(os.path.exists(o) for o in objs):
+        return None
+    d = os.path.join(OUT, name)
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    local = os.path.join(d, name + ".pop")
+    open(local, "w").write(pop_text)
+    run(["perl", os.path.join(REF, "src", "odexp"), "-d", "-q", os.path.basename(local)], cwd=d)
+    exe = os.path.join(d, "model.out")
+    run(["gcc"] + CFLAGS + ["-I" + os.path.join(d, ".odexp"), os.path.join(d, ".odexp", "model.c")] + objs + ["-lm", "-o", exe])
+    os.remove(local)
+    return exe
+
+
 DROPIN_FIXTURES = ("kuramoto", "lineage", "nbody", "vdp_sde")
 ROOT = os.path.dirname(HERE)
 

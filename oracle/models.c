@@ -621,8 +621,12 @@ static const orc_model MODELS[] = {
   {"kuramoto_lowrank", 1, 1 + 2 * LR_R, 2, 1, 2, 1, klr_pars, klr_rhs, klr_mfd, NULL, NULL, klr_ic, LR_R, 0, 0, 1, 1 + LR_R, sin},
   {"kuramoto_lowrank64", 1, 1 + 2 * LR64_R, 2, 1, 2, 1, klr_pars, klr64_rhs, klr_mfd, NULL, NULL, klr64_ic, LR64_R, 0, 0, 1, 1 + LR64_R, sin},
 };
+/* a model registered from outside this file: tests/test_emitter_vs_reference.py compiles the PRODUCT's generated model code for the
+ * host and drives it through this checker's loop, against the reference binary built from the same .pop file */
+const orc_model *orc_extra_model = NULL;
 const orc_model *orc_find_model(const char *name) {
   unsigned i;
   for (i = 0; i < sizeof MODELS / sizeof MODELS[0]; i++) if (strcmp(MODELS[i].name, name) == 0) return &MODELS[i];
+  if (orc_extra_model != NULL && strcmp(orc_extra_model->name, name) == 0) return orc_extra_model;
   return NULL;
 }

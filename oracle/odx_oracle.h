@@ -102,6 +102,7 @@ double orc_interp(double *x, double *y, double xi, int nx, int start);
 double orc_delay(orc_ctx *c, const double t, const double x, const double tau, double (*ic)(double), orc_stack *xhist);
 
 const orc_model *orc_find_model(const char *name);
+extern const orc_model *orc_extra_model;
 int orc_pop_rhs(double t, const double *y, double *f, void *sim);
 int orc_odesolver(const char *model_name, const orc_opts *o, orc_report *rep);
 #endif

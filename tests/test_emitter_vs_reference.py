@@ -1,0 +1,218 @@
+"""Whole random MODELS through the product's parser + emitter against the unchanged reference binary, on the CPU.
+
+A seeded generator writes .pop files (parameters, a random parametric expression, one-line functions with guards, auxiliaries,
+%M mean fields incl. MA(), all-pairs %C couplings incl. the guarded-difference form, two coupled equations).  For each of them
+  (1) the reference's own generator (perl src/odexp) + gcc build model.out, which integrates the population (oracle/build_ref.build_one);
+  (2) the product's generated OdxModel -- the code the GPU compiles, `__host__ __device__` -- is compiled for the host behind a small
+      adapter and driven by the checker's solver loop (oracle/odx_oracle.c, itself bit-identical to the reference on every fixture):
+      so what is compared is the emitter's translation of the model file, not another hand-written model.
+Both consume the same replayed libc stream, so initial conditions must agree bit for bit (draw order of EXPR / INIT lines) and the
+trajectories, auxiliaries, couplings and mean fields to rounding -- with the peepholes off (the reference's expressions verbatim) to
+1e-12, with them on (what the GPU runs) to 1e-9.  Needs /root/reference (skipped where oracle/_ref cannot be built); no GPU."""
+import ctypes as C
+import os, random, subprocess
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+FUNS = """fun f1(u,v) = (u-v)/pow(u*u+v*v+0.3,1.5);
+fun g1(u) = u*u+1.0;
+fun nc(a,b) = pow(a*a+b*b+0.2,1.5);
+fun gr(p,q,a,b) = (p == q) ? 0.0 : (p-q)/nc(a,b);
+fun h2(u,v) = (u > v) ? u-v : v*0.5;
+"""
+
+ADAPTER = r"""
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "odx.h"
+#include "odx_rng.h"
+#include "odx_model_prelude.cuh"
+extern "C" {
+#include "odx_oracle.h"
+}
+%(model)s
+struct AdCtx {
+  const double *mu; double pop_size, h; int id, oid, atbirth, atrepli, ist0, has_sister, stop, slow;
+  const double *sis_y, *sis_e, *sis_aux; orc_ctx *o;
+  double rand01() { return orc_rand01(o); }
+  double randN(double m, double s) { return orc_randN(o, m, s); }
+  double exprand(double r) { return orc_exprand(o, r); }
+  long poisson(double l) { return orc_poisson(o, l); }
+  double dwdt() { return orc_dwdt(o); }
+  double ky(int v, long d) const { return orc_ky(o, v, (int)d); }
+  double delay_lookup(int, double, long) const { return 0.0; }
+};
+static AdCtx mk(orc_ctx *c) {
+  AdCtx a; memset(&a, 0, sizeof a);
+  a.mu = c->mu; a.pop_size = c->pop_size; a.h = c->h; a.id = c->id; a.oid = c->oid; a.atbirth = c->atbirth; a.atrepli = c->atrepli; a.ist0 = c->ist0;
+  if (c->sister) { a.has_sister = 1; a.sis_y = c->sister->y; a.sis_e = c->sister->expr; a.sis_aux = c->sister->aux; }
+  a.o = c;
+  return a;
+}
+typedef OdxModel M;
+static void ad_rhs(orc_ctx *c, double t, const double *y, const double *e, const double *psi, const double *mfd, double *f, double *aux,
+                   double *death, double *repli) {
+  AdCtx a = mk(c); double d = 0.0, r = 0.0;
+  M::rhs<true>(a, t, y, e, psi, mfd, f, aux, d, r);
+  *death = d; *repli = r;
+  if (a.stop) orc_stopif(c, 1);
+}
+static double ad_mfd(orc_ctx *c, int k, const double *y, const double *e, const double *aux, const double *mfd) {
+  AdCtx a = mk(c); double m[M::NMFD + 1];
+  (void)mfd;
+  M::mfd_terms<true>(a, 0.0, y, e, aux, m);
+  return m[k];
+}
+static void ad_cpl(orc_ctx *c, const double *y, const double *e, const double *oy, const double *oe, double *psi) {
+  AdCtx a = mk(c); double p[M::NPSI + 1], s[M::NPSI + 1];
+  for (int k = 0; k <= M::NPSI; k++) { p[k] = 0.0; s[k] = 1.0; }
+  M::cpl_terms<true>(a, 0.0, y, e, c->my_aux, oy, oe, c->other_aux, p);
+  M::cpl_scale<true>(a, 0.0, y, e, c->my_aux, s);
+  for (int k = 0; k < M::NPSI; k++) psi[k] += s[k] * p[k];
+}
+static void ad_ic(orc_ctx *c, double t, double *y, double *e) { AdCtx a = mk(c); M::ic(a, t, y, e); }
+static orc_model G;
+__attribute__((constructor)) static void ad_register(void) {
+  const odx_model_info &mi = M::info();
+  memset(&G, 0, sizeof G);
+  G.name = "generated"; G.nvar = M::NVAR; G.nexpr = M::NEXPR; G.naux = M::NAUX; G.npsi = M::NPSI; G.nmfd = M::NMFD; G.npar = M::NPAR;
+  G.par_defaults = mi.par_defaults;
+  G.rhs = ad_rhs; G.mfd_term = M::NMFD ? ad_mfd : NULL; G.birth_term = NULL; G.cpl_terms = M::NPSI ? ad_cpl : NULL; G.ic = ad_ic;
+  orc_extra_model = &G;
+}
+"""
+
+
+class Gen:
+    def __init__(self, rng, atoms):
+        self.r, self.atoms = rng, atoms
+
+    def num(self):
+        return self.r.choice(["0.5", "2.0", "1.25", "3", "0.1", "1e-1", "2.5e0"])
+
+    def atom(self):
+        return self.r.choice(self.atoms + [self.num()])
+
+    def sq(self):
+        a = self.atom()
+        return "(%s)*(%s)" % (a, a)
+
+    def posden(self):
+        return self.r.choice(["pow(%s+%s,1.5)" % (self.sq(), self.num()), "g1(%s)" % self.atom(), "(1.0+%s)" % self.sq(),
+                              "sqrt(%s+%s)" % (self.sq(), self.num()), "nc(%s,%s)" % (self.atom(), self.atom())])
+
+    def factor(self, d):
+        k = self.r.randrange(9) if d > 0 else self.r.randrange(3)
+        if k <= 1:
+            return self.atom()
+        if k == 2:
+            return "(-%s)" % self.atom()
+        if k == 3:
+            return "(%s)" % self.expr(d - 1)
+        if k == 4:
+            return "f1(%s,%s)" % (self.atom(), self.atom())
+        if k == 5:
+            a, b = self.atom(), self.atom()
+            return "((%s == %s) ? 0.0 : (%s-%s)/%s)" % (a, b, a, b, self.posden())
+        if k == 6:
+            return "h2(%s,%s)" % (self.atom(), self.expr(d - 1))
+        if k == 7:
+            return "sin(%s*%s+%s)" % (self.atom(), self.atom(), self.atom())
+        return "cos(%s-%s)" % (self.atom(), self.atom())
+
+    def term(self, d):
+        t = self.factor(d)
+        for _ in range(self.r.randrange(0, 3)):
+            t += self.r.choice(["*", " * "]) + self.factor(d)
+        if self.r.random() < 0.5:
+            t += "/" + self.posden()
+        return t
+
+    def expr(self, d):
+        e = ("-" if self.r.random() < 0.2 else "") + self.term(d)
+        for _ in range(self.r.randrange(0, 2)):
+            e += self.r.choice(["+", "-"]) + self.term(d)
+        return e
+
+
+def model_text(seed):
+    rng = random.Random(seed)
+    ga = Gen(rng, ["x", "y", "p", "q", "w", "t"])
+    gm = Gen(rng, ["MY(x)", "MY(y)", "ME(w)", "MU(p)", "MA(A0)"])
+    gc = Gen(rng, ["MY(x)", "OY(x)", "MY(y)", "OY(y)", "MU(p)", "MU(q)", "ME(w)", "OE(w)"])
+    gd = Gen(rng, ["x", "y", "p", "q", "w", "A0", "A1", "M0", "M1", "C0", "C1"])
+    v = rng.choice(["x", "y"])
+    L = ["par p 0.7", "par q 1.3", FUNS.rstrip(), "expr w 0.5+rand01()",
+         "aux A0 " + ga.expr(2), "aux A1 " + ga.expr(2),
+         "%M M0 MY(x)", "%M M1 " + gm.expr(1),
+         "%C C0 " + gc.expr(2),
+         "%%C C1 -MU(q)*gr(MY(%s),OY(%s),MY(x)-OY(x),MY(y)-OY(y))" % (v, v),
+         "dx/dt = -x + 0.2*(%s)" % gd.expr(2), "dy/dt = -0.5*y + 0.2*(%s)" % gd.expr(2),
+         "init x rand01()", "init y rand01()-0.5", "timespan 0 0.3", "opt popmode population", "opt popsize 9", "opt meth dde", "opt h0 0.05", "opt res 4"]
+    return "\n".join(L) + "\n"
+
+
+def _oracle_objects(tmp):
+    objs = []
+    for f in ("odx_oracle.c", "models.c", "minigsl.c", "lowrank.c"):
+        o = os.path.join(tmp, f[:-2] + ".o")
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-fPIC", "-w", "-I" + os.path.join(ROOT, "oracle", "stubinc"), "-I" + os.path.join(ROOT, "oracle"),
+                        "-c", os.path.join(ROOT, "oracle", f), "-o", o], check=True)
+        objs.append(o)
+    return objs
+
+
+def _run_generated(so, dims, opts, ts, outdir):
+    from oracle import port
+    L = C.CDLL(so)
+    L.orc_odesolver.argtypes = [C.c_char_p, C.POINTER(port.Opts), C.POINTER(port.Report)]
+    tsa = np.ascontiguousarray(ts, dtype=np.float64)
+    op = port.Opts(port.METHODS[opts["meth"]], int(opts["res"]), 1e-5, float(opts["h0"]), 1e-6, 1e-6, 0.0, 0.01, int(opts["ps"]), 3141592, 0, 1,
+                   outdir.encode(), tsa.ctypes.data_as(C.POINTER(C.c_double)), len(tsa), None, -1, 0, 1, 0)
+    rep = port.Report()
+    assert L.orc_odesolver(b"generated", C.byref(op), C.byref(rep)) == 0
+    nc = dims["nvar"] + dims["naux"] + dims["npsi"] + dims["nmfd"] + dims["nexpr"]
+    tdt = np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (nc,))])
+    return np.fromfile(os.path.join(outdir, "traj.dat"), dtype=tdt)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_generated_model_code_matches_the_reference_binary(tmp_path, seed):
+    from oracle import build_ref, refrun
+    from odexp_b200 import popfile, cudagen
+    if not build_ref.available() or not build_ref.build():
+        pytest.skip("needs /root/reference to build oracle/_ref")
+    text = model_text(seed)
+    name = "fuzzmodel_%d" % seed
+    assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
+    model = popfile.parse(text, name=name)
+    dims = dict(nvar=2, naux=2, npsi=2, nmfd=2, nexpr=1)
+    objs = _oracle_objects(str(tmp_path))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
+           "-I" + os.path.join(ROOT, "oracle", "stubinc")]
+    for meth in ("dde", "fe"):
+        opts = {"meth": meth, "h0": 0.05, "res": 4, "ps": 9}
+        ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), (0, 0.3), dims=dims)["traj"]
+        for fast, rtol in ((False, 1e-12), (True, 1e-9)):
+            cu = cudagen.Emitter(model, fast_pow=fast, fast_div=fast).emit()
+            src = tmp_path / ("ad_%d.cpp" % fast)
+            src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+            so = str(tmp_path / ("libgen_%s_%d.so" % (meth, fast)))
+            r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + inc + [str(src)] + objs + ["-lm", "-o", so],
+                               capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            out = tmp_path / ("out_%s_%d" % (meth, fast)); out.mkdir()
+            got = _run_generated(so, dims, opts, (0, 0.3), str(out))
+            assert len(got) == len(ref)
+            np.testing.assert_array_equal(got["id"], ref["id"])
+            first = got["step"] == 0
+            np.testing.assert_array_equal(got["cols"][first][:, :2], ref["cols"][first][:, :2])          # y: replayed draws, in file order
+            np.testing.assert_array_equal(got["cols"][first][:, -1], ref["cols"][first][:, -1])          # expr w
+            scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
+            err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
+            assert np.all(err <= rtol), (meth, fast, err, text)
