@@ -182,7 +182,7 @@ def _run_generated(so, dims, opts, ts, outdir):
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
-def test_generated_model_code_matches_the_reference_binary(tmp_path, seed):
+def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, request):
     from oracle import build_ref, refrun
     from odexp_b200 import popfile, cudagen
     if not build_ref.available() or not build_ref.build():
@@ -190,6 +190,7 @@ def test_generated_model_code_matches_the_reference_binary(tmp_path, seed):
     text = model_text(seed)
     name = "fuzzmodel_%d" % seed
     assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
+    request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
     model = popfile.parse(text, name=name)
     dims = dict(nvar=2, naux=2, npsi=2, nmfd=2, nexpr=1)
     objs = _oracle_objects(str(tmp_path))
