@@ -76,16 +76,23 @@ static void ad_cpl(orc_ctx *c, const double *y, const double *e, const double *o
   for (int k = 0; k < M::NPSI; k++) psi[k] += s[k] * p[k];
 }
 static void ad_ic(orc_ctx *c, double t, double *y, double *e) { AdCtx a = mk(c); M::ic(a, t, y, e); }
+static double ad_birth(orc_ctx *c, const double *y, const double *e, const double *aux) { AdCtx a = mk(c); return M::birth_term<true>(a, 0.0, y, e, aux); }
 static orc_model G;
 __attribute__((constructor)) static void ad_register(void) {
   const odx_model_info &mi = M::info();
   memset(&G, 0, sizeof G);
   G.name = "generated"; G.nvar = M::NVAR; G.nexpr = M::NEXPR; G.naux = M::NAUX; G.npsi = M::NPSI; G.nmfd = M::NMFD; G.npar = M::NPAR;
   G.par_defaults = mi.par_defaults;
-  G.rhs = ad_rhs; G.mfd_term = M::NMFD ? ad_mfd : NULL; G.birth_term = NULL; G.cpl_terms = M::NPSI ? ad_cpl : NULL; G.ic = ad_ic;
+  G.rhs = ad_rhs; G.mfd_term = M::NMFD ? ad_mfd : NULL; G.birth_term = M::HAS_BIRTH ? ad_birth : NULL; G.cpl_terms = M::NPSI ? ad_cpl : NULL; G.ic = ad_ic;
   orc_extra_model = &G;
 }
 """
+
+
+# several generated libraries live in one test process: without these the static locals of the generated inline functions (the parameter
+# defaults inside OdxModel::info()) are STB_GNU_UNIQUE and every library after the first would read the first one's -- the product's
+# own build uses the same flags for the same reason (odexp_b200/build.py)
+ISOLATE = ["-fvisibility=hidden", "-fno-gnu-unique", "-Wl,-Bsymbolic"]
 
 
 class Gen:
@@ -167,18 +174,22 @@ def _oracle_objects(tmp):
     return objs
 
 
-def _run_generated(so, dims, opts, ts, outdir):
+def _run_generated(so, dims, opts, ts, outdir, want_stats=False):
     from oracle import port
     L = C.CDLL(so)
     L.orc_odesolver.argtypes = [C.c_char_p, C.POINTER(port.Opts), C.POINTER(port.Report)]
     tsa = np.ascontiguousarray(ts, dtype=np.float64)
-    op = port.Opts(port.METHODS[opts["meth"]], int(opts["res"]), 1e-5, float(opts["h0"]), 1e-6, 1e-6, 0.0, 0.01, int(opts["ps"]), 3141592, 0, 1,
+    op = port.Opts(port.METHODS[opts["meth"]], int(opts["res"]), 1e-5, float(opts["h0"]), 1e-6, 1e-6, float(opts.get("ssahmin", 0.0)), 0.01, int(opts["ps"]), 3141592, 0, 1,
                    outdir.encode(), tsa.ctypes.data_as(C.POINTER(C.c_double)), len(tsa), None, -1, 0, 1, 0)
     rep = port.Report()
     assert L.orc_odesolver(b"generated", C.byref(op), C.byref(rep)) == 0
     nc = dims["nvar"] + dims["naux"] + dims["npsi"] + dims["nmfd"] + dims["nexpr"]
     tdt = np.dtype([("step", "<u4"), ("id", "<i4"), ("t", "<f8"), ("cols", "<f8", (nc,))])
-    return np.fromfile(os.path.join(outdir, "traj.dat"), dtype=tdt)
+    traj = np.fromfile(os.path.join(outdir, "traj.dat"), dtype=tdt)
+    if not want_stats:
+        return traj
+    sdt = np.dtype([("t", "<f8"), ("mfd", "<f8", (dims["nmfd"],)), ("n", "<i4"), ("stop_flag", "<i4"), ("event", "<i4", (3,))])
+    return traj, np.fromfile(os.path.join(outdir, "stats.dat"), dtype=sdt)
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14])
@@ -204,7 +215,7 @@ def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, reque
             src = tmp_path / ("ad_%d.cpp" % fast)
             src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
             so = str(tmp_path / ("libgen_%s_%d.so" % (meth, fast)))
-            r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + inc + [str(src)] + objs + ["-lm", "-o", so],
+            r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
                                capture_output=True, text=True)
             assert r.returncode == 0, r.stderr[-3000:]
             out = tmp_path / ("out_%s_%d" % (meth, fast)); out.mkdir()
@@ -217,3 +228,61 @@ def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, reque
             scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
             err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
             assert np.all(err <= rtol), (meth, fast, err, text)
+
+
+def lineage_text(seed):
+    """a birth / death population with inheritance at replication: random (positive) rate expressions, initial conditions that read the
+    mother through SY / SE / SA and tell births from replications through BR / ISDAUGHTER / ATBIRTH"""
+    rng = random.Random(seed)
+    g = Gen(rng, ["x", "p", "q", "gen"])
+    pos = lambda: "(%s)*(%s)" % (g.atom(), g.atom())
+    gb = Gen(rng, ["MU(p)", "MU(q)", "MY(x)", "ME(gen)"])          # %BIRTH is summed in pop_rhs, outside ode_rhs: macros only
+    posb = lambda: "(%s)*(%s)" % (gb.atom(), gb.atom())
+    L = ["par p 0.7", "par q 1.3", "par d %s {impl}" % rng.choice(["0.05", "0.1"]), FUNS.rstrip(),
+         "expr life exprand(2.0)", "expr gen BR(0.0, SE(gen) + 1)", "expr tag ISDAUGHTER*10 + ATBIRTH + poisson(2.0)",
+         "aux size x*(1 + 0.1*gen) + 0.01*(%s)" % g.expr(1),
+         "dx/dt = q*x*(1 - x) - 0.01*life*x + 0.01*(%s)" % g.expr(1),
+         "init x BR(0.1 + 0.05*rand01(), 0.5*SA(size)/(1 + 0.1*gen) + 0.25*SY(x))",
+         "%%BIRTH 0.3 + 0.01*%s" % posb(), "%%DEATH MU(d)*(1.0 + 0.1*%s)" % pos(), "%%REPLI %s*(x > %s)" % (rng.choice(["0.6", "0.4", "MU(p)"]), rng.choice(["0.5", "0.3"])),
+         "%M XM MY(x)", "%M GM ME(gen)", "timespan 0 4", "opt popmode population", "opt popsize 20", "opt meth fe", "opt h0 0.01", "opt res 21", "opt ssahmin 1.0"]
+    return "\n".join(L) + "\n"
+
+
+@pytest.mark.parametrize("seed,ssahmin", [(21, 1.0), (22, 1.0), (23, 0.0)])
+def test_generated_birth_death_model_matches_the_reference_binary(tmp_path, seed, ssahmin, request):
+    """the same end-to-end comparison for stochastic birth / death (tau-leaping and SSA) on the replayed libc stream: identical event
+    rows (N, flag, parent, +-1, child), identical ids in every frame, states to 1e-12 -- the draw order of the generated initial
+    conditions (mother first, then the daughter with the mother as sister: src/methods_odexp.c:1697-1717) and of the rates is the reference's"""
+    from oracle import build_ref, refrun
+    from odexp_b200 import popfile, cudagen
+    if not build_ref.available() or not build_ref.build():
+        pytest.skip("needs /root/reference to build oracle/_ref")
+    text = lineage_text(seed)
+    name = "fuzzlineage_%d" % seed
+    assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
+    request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
+    model = popfile.parse(text, name=name)
+    dims = dict(nvar=1, naux=1, npsi=0, nmfd=2, nexpr=3)
+    opts = {"meth": "fe", "h0": 0.01, "res": 21, "ps": 20, "ssahmin": ssahmin}
+    r = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, aleap=0.01, seed=3141592), (0, 4), dims=dims)
+    objs = _oracle_objects(str(tmp_path))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
+           "-I" + os.path.join(ROOT, "oracle", "stubinc")]
+    cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
+    src = tmp_path / "ad.cpp"
+    src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+    so = str(tmp_path / "libgen.so")
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    out = tmp_path / "out"; out.mkdir()
+    traj, stats = _run_generated(so, dims, opts, (0, 4), str(out), want_stats=True)
+    ev = r["stats"]["event"][:, 1]
+    assert (ev == 1).sum() > 20 and (ev == -1).sum() > 0                      # births / replications beyond the initial rows, and deaths
+    assert len(stats) == len(r["stats"])
+    np.testing.assert_array_equal(stats["n"], r["stats"]["n"])
+    np.testing.assert_array_equal(stats["stop_flag"], r["stats"]["stop_flag"])
+    np.testing.assert_array_equal(stats["event"], r["stats"]["event"])
+    assert len(traj) == len(r["traj"])
+    np.testing.assert_array_equal(traj["id"], r["traj"]["id"])
+    np.testing.assert_allclose(traj["cols"], r["traj"]["cols"], rtol=1e-12, atol=1e-13)
