@@ -1008,6 +1008,13 @@ class Emitter:
             w("#define ODX_MODEL_HAS_LOWRANK 1")
         if getattr(self, "cpl_sym", False):
             w("#define ODX_MODEL_CPL_SYM 1")
+        if m.macros:
+            # the model's MACRO lines are #defines, as in the reference's model.c -- but there they live in a translation unit of their own.
+            # Here the engine follows in the same one: a model's `macro T 1.0`, `macro h ...` or `macro n ...` would rewrite the engine's own
+            # identifiers.  The generated functions above are already preprocessed text, so the macros can end here.
+            w("/* end of the model's macros (the engine below must not see them) */")
+            for name, _ in m.macros:
+                w("#undef %s" % mangle(name))
         w('#include "odx_engine.cuh"')
         return "\n".join(L) + "\n"
 

@@ -328,3 +328,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "n_particles" in d["config"] and "workload" in d["config"]
+
+
+def test_model_macros_do_not_reach_the_engine(tmp_path):
+    """MACRO lines are #defines (as in the reference's model.c); the engine is compiled in the same translation unit, so a model that
+    names a macro T, h or n must not rewrite the engine's identifiers: the generated file #undefs them in front of the engine"""
+    import shutil
+    from odexp_b200 import popfile, cudagen
+    txt = open(fixture_path("kuramoto")).read() + "\nmacro T 1.0\nmacro h 0.5\nmacro n 3\n"
+    cu = cudagen.emit_cuda(popfile.parse(txt, name="mac"))
+    tail = cu[cu.index("end of the model's macros"):]
+    for name in ("PI", "T", "h", "n"):
+        assert "#undef %s\n" % name in tail
+    assert tail.rstrip().endswith('#include "odx_engine.cuh"')
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not here")
+    src = tmp_path / "mac.cu"
+    src.write_text(cu)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O0", "-std=c++17", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361",
+                        "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "mac.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
