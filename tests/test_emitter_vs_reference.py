@@ -77,13 +77,27 @@ static void ad_cpl(orc_ctx *c, const double *y, const double *e, const double *o
 }
 static void ad_ic(orc_ctx *c, double t, double *y, double *e) { OdxAdCtx a = mk(c); OdxAdM::ic(a, t, y, e); }
 static double ad_birth(orc_ctx *c, const double *y, const double *e, const double *aux) { OdxAdCtx a = mk(c); return OdxAdM::birth_term<true>(a, 0.0, y, e, aux); }
+/* {vect} mean fields: which ones they are comes from the parser (%(vect)s), their values from the generated mfd_vect */
+static const int odx_ad_vect[] = {%(vect)s 0};
+static double ad_vect_eval(int k, const double *mu, double pop_size, const double *mfd) {
+  double m[OdxAdM::NMFD + 1];
+  for (int q = 0; q < OdxAdM::NMFD; q++) m[q] = mfd[q];
+  OdxAdM::mfd_vect(mu, pop_size, m);
+  return m[k];
+}
 static orc_model odx_ad_model;
 __attribute__((constructor)) static void ad_register(void) {
   const odx_model_info &mi = OdxAdM::info();
   memset(&odx_ad_model, 0, sizeof odx_ad_model);
   odx_ad_model.name = "generated"; odx_ad_model.nvar = OdxAdM::NVAR; odx_ad_model.nexpr = OdxAdM::NEXPR; odx_ad_model.naux = OdxAdM::NAUX; odx_ad_model.npsi = OdxAdM::NPSI; odx_ad_model.nmfd = OdxAdM::NMFD; odx_ad_model.npar = OdxAdM::NPAR;
   odx_ad_model.par_defaults = mi.par_defaults;
-  odx_ad_model.rhs = ad_rhs; odx_ad_model.mfd_term = OdxAdM::NMFD ? ad_mfd : NULL; odx_ad_model.birth_term = OdxAdM::HAS_BIRTH ? ad_birth : NULL; odx_ad_model.cpl_terms = OdxAdM::NPSI ? ad_cpl : NULL; odx_ad_model.ic = ad_ic;
+  odx_ad_model.rhs = ad_rhs; odx_ad_model.mfd_term = OdxAdM::NMFD ? ad_mfd : NULL; odx_ad_model.birth_term = OdxAdM::HAS_BIRTH ? ad_birth : NULL; odx_ad_model.cpl_terms = OdxAdM::HAS_PAIR ? ad_cpl : NULL; odx_ad_model.ic = ad_ic;
+  if (OdxAdM::HAS_VECT_MFD) { odx_ad_model.mfd_vect = odx_ad_vect; odx_ad_model.mfd_vect_eval = ad_vect_eval; }
+#ifdef ODX_MODEL_HAS_LOWRANK
+  odx_ad_model.lr_rank = OdxAdM::LR0_UNWEIGHTED ? 1 : OdxAdM::LR0_RANK; odx_ad_model.lr_psi = OdxAdM::LR0_PSI; odx_ad_model.lr_var = OdxAdM::LR0_VAR;
+  odx_ad_model.lr_iu = OdxAdM::LR0_U; odx_ad_model.lr_iv = OdxAdM::LR0_V; odx_ad_model.lr_fun = OdxAdM::lr0_fun;
+  odx_ad_model.lr_var_kind = OdxAdM::LR0_VAR_KIND; odx_ad_model.lr_unweighted = OdxAdM::LR0_UNWEIGHTED ? 1 : 0;
+#endif
   orc_extra_model = &odx_ad_model;
 }
 """
@@ -164,6 +178,13 @@ def model_text(seed):
     return "\n".join(L) + "\n"
 
 
+def _adapter(cu, parsed):
+    """the adapter source around one generated model (its #include lines dropped: the adapter includes the headers itself)"""
+    from odexp_b200 import cudagen
+    vect = "".join("%d, " % (1 if cudagen.is_vect(e) else 0) for e in parsed.mfds)
+    return ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include")), vect=vect)
+
+
 def _oracle_objects(tmp):
     objs = []
     for f in ("odx_oracle.c", "models.c", "minigsl.c", "lowrank.c"):
@@ -213,7 +234,7 @@ def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, reque
         for fast, rtol in ((False, 1e-12), (True, 1e-9)):
             cu = cudagen.Emitter(model, fast_pow=fast, fast_div=fast).emit()
             src = tmp_path / ("ad_%d.cpp" % fast)
-            src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+            src.write_text(_adapter(cu, model))
             so = str(tmp_path / ("libgen_%s_%d.so" % (meth, fast)))
             r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
                                capture_output=True, text=True)
@@ -270,7 +291,7 @@ def test_generated_birth_death_model_matches_the_reference_binary(tmp_path, seed
            "-I" + os.path.join(ROOT, "oracle", "stubinc")]
     cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
     src = tmp_path / "ad.cpp"
-    src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+    src.write_text(_adapter(cu, model))
     so = str(tmp_path / "libgen.so")
     cc = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
                         capture_output=True, text=True)
@@ -288,18 +309,18 @@ def test_generated_birth_death_model_matches_the_reference_binary(tmp_path, seed
     np.testing.assert_allclose(traj["cols"], r["traj"]["cols"], rtol=1e-12, atol=1e-13)
 
 
-# fixtures whose constructs the adapter above can carry (no low-rank coupling, {vect} mean field or delay() stack: those need the checker's
-# special hooks).  The hand-written restatement of every fixture is bit-identical to the reference binary (tests/test_oracle_port.py), so it
+# every fixture but delay_pop (its history stacks live in the engine / the checker, not in the generated model code).  The hand-written restatement of every fixture is bit-identical to the reference binary (tests/test_oracle_port.py), so it
 # stands in for it here and the test also runs where /root/reference is absent.
 _FIXTURE_CASES = [c for c in __import__("test_oracle_port").REF_CASES
                   if c[0] in ("kuramoto", "nbody", "nbody_const", "vdp_sde", "pair_aux", "repel2d", "chain_array", "fun_block", "helper_calls", "table_drive",
-                              "interp_drive", "lag_chain", "logistic_map", "reset_decay", "ring_diffusion", "lineage")
+                              "interp_drive", "lag_chain", "logistic_map", "reset_decay", "ring_diffusion", "lineage", "vect_meanfield",
+                              "kuramoto_lowrank", "kuramoto_lowrank64", "kuramoto_lowrank_aux", "kuramoto_lrexp")
                   and c[1]["meth"] in ("dde", "fe", "iteration", "rkck", "rkf45")]
 
 
 @pytest.mark.parametrize("model", sorted({c[0] for c in _FIXTURE_CASES}))
 def test_generated_code_of_every_fixture_matches_the_restatement(tmp_path, model):
-    """the code the emitter generates for the shipped fixtures (arrays, function blocks, const arrays, FILE tables, LAG chains, helper
+    """the code the emitter generates for 21 of the 22 fixtures (arrays, function blocks, const arrays, FILE tables, LAG chains, helper
     calls, interp(), KY() neighbours, STOPIF and stopping times, MA() / OA() in %C, birth / death with sister macros, DWDT), compiled for
     the host and driven by the checker's loop, against the checker's hand-written model of the same fixture: the emitter alone, without
     the GPU engine around it.  Replayed libc stream on both sides: bit-identical initial conditions, identical event rows and ids."""
@@ -308,7 +329,7 @@ def test_generated_code_of_every_fixture_matches_the_restatement(tmp_path, model
     pm = popfile.parse_file(os.path.join(ROOT, "models", model + ".pop"))
     cu = cudagen.Emitter(pm, fast_pow=True, fast_div=True).emit()
     src = tmp_path / "ad.cpp"
-    src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+    src.write_text(_adapter(cu, pm))
     objs = _oracle_objects(str(tmp_path))
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
            "-I" + os.path.join(ROOT, "oracle", "stubinc")]
@@ -401,7 +422,7 @@ def test_generated_array_model_matches_the_reference_binary(tmp_path, seed, requ
             pytest.skip("the reference binary itself aborts on this model file")
         cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
         src = tmp_path / ("ad_%s.cpp" % meth)
-        src.write_text(ADAPTER % dict(model="\n".join(ln for ln in cu.splitlines() if not ln.startswith("#include"))))
+        src.write_text(_adapter(cu, model))
         so = str(tmp_path / ("libgen_%s.so" % meth))
         r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
                            capture_output=True, text=True)
