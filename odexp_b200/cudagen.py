@@ -435,7 +435,8 @@ class Emitter:
         # identifiers that are doubles in the generated code: dynamical variables, expressions, auxiliaries, parameters, mean fields,
         # couplings (scalars: an array name alone is a pointer) and `decl const double` scalars; the arguments of the model functions
         dn = {e.name for e in list(m.eqs) + list(m.exprs) + list(m.auxs) if not e.length}
-        dn |= {e.name for e in m.pars} | {e.name for e in m.mfds} | {c.name for c in m.cpls}
+        dn |= {e.name for e in m.pars if not re.search(r"\b(int|long)\b", e.attr or "")}      # `par n 3 {int}` is an int in the generated code
+        dn |= {e.name for e in m.mfds} | {c.name for c in m.cpls}
         dn |= {n for t, n, d, init in m.consts if "double" in t and not d}
         for f in m.funs:
             dn |= {a.strip() for a in f.args if re.fullmatch(IDENT, a.strip())}

@@ -106,6 +106,7 @@ class Gen:
     def int_division(self):
         """integer divisions of the reference's C (ID and POP_SIZE are ints): a reciprocal peephole must leave them alone"""
         return self.r.choice(["ID/(2)", "7/(ID+1)", "1/POP_SIZE", "(ID+3)/(POP_SIZE)", "ID/(POP_SIZE-1)", "(2*ID+1)/(2)", "ID/(1+ID/(2))",
+                              "7/(n)", "(ID+1)/(n)", "(n+4)/(2)", "7/(n+p)",          # `par n 3 {int}` is an int in the generated code, p a double
                               "3/(2.0+ID)", "ID/(%s+1.5)" % self.r.choice(self.atoms), "POP_SIZE/(ID+1)*%s" % self.atom()])
 
     def gravity_like(self):
@@ -118,7 +119,7 @@ def _model_text(seed):
     rng = random.Random(seed)
     gc = Gen(rng, ["MY(x)", "OY(x)", "MY(y)", "OY(y)", "MU(p)", "MU(q)", "ME(w)", "OE(w)"])
     ga = Gen(rng, ["x", "y", "p", "q", "w", "t"])
-    L = ["par p 0.7", "par q 1.3", FUNS, "expr w 0.5+rand01()"]
+    L = ["par p 0.7", "par q 1.3", "par n 3 {int}", FUNS, "expr w 0.5+rand01()"]
     cexprs, aexprs = [], []
     for k in range(NEXPR_C):
         e = gc.gravity_like() if k % 8 == 0 else gc.expr(2)
@@ -150,7 +151,7 @@ namespace refm {
 }
 int main() {
   const int NC = %(nc)d, NA = %(na)d, NPT = 240;
-  double mu[2] = {0.7, 1.3};
+  double mu[3] = {0.7, 1.3, 3.0};
   srand(12345);
   for (int it = 0; it < NPT; it++) {
     double y[2], oy[2], e[1], oe[1], aux[NA + 1], oaux[NA + 1];
