@@ -88,7 +88,7 @@ def _strip_outer_parens(e):
     return e
 
 
-def _ternary_to_select(expr: str) -> str:
+def _ternary_to_select(expr: str, double_funs=None) -> str:
     """`c ? a : b` (whole expression) -> odx_sel(c, a, b): both arms are evaluated, the result is a select.
     On the GPU this removes a divergent branch per use and lets the compiler share sub-expressions between several
     guarded terms (the N-body fixture guards each force component separately around the same r^3).  Only applied when
@@ -122,10 +122,12 @@ def _ternary_to_select(expr: str) -> str:
         return expr
     if re.search(r"\[[^\]]*[A-Za-z_][^\]]*\]", a + " " + b):
         return expr            # an arm indexes an array with a computed index (`(i == 0) ? a : X[i-1]`): the guard may be what keeps it in range
-    return "odx_sel(%s, %s, %s)" % (cond, _ternary_to_select(a), _ternary_to_select(b))
+    if double_funs is not None and not (_is_double_valued("(" + a + ")", double_funs) or _is_double_valued("(" + b + ")", double_funs)):
+        return expr            # `(ID > 2) ? 3 : 1` is an int in C (its quotient by 2 an integer division); odx_sel would make it a double
+    return "odx_sel(%s, %s, %s)" % (cond, _ternary_to_select(a, double_funs), _ternary_to_select(b, double_funs))
 
 
-def _ternary_to_select_nested(expr: str) -> str:
+def _ternary_to_select_nested(expr: str, double_funs=None) -> str:
     """apply _ternary_to_select to every parenthesised sub-expression that is a whole ternary (after function inlining the
     guards of the model functions sit inside parentheses)"""
     out, i, brackets = [], 0, 0
@@ -136,8 +138,8 @@ def _ternary_to_select_nested(expr: str) -> str:
                 depth += expr[j] == "("
                 depth -= expr[j] == ")"
                 j += 1
-            inner = _ternary_to_select_nested(expr[i + 1:j - 1])
-            conv = inner if brackets else _ternary_to_select(inner)      # inside an array subscript the value must stay an integer
+            inner = _ternary_to_select_nested(expr[i + 1:j - 1], double_funs)
+            conv = inner if brackets else _ternary_to_select(inner, double_funs)      # inside an array subscript the value must stay an integer
             out.append("(" + conv + ")")
             i = j
         else:
@@ -546,7 +548,7 @@ class Emitter:
             e = _pow_peephole(e)
         if self.fast_div and not exact:
             e = _rpow_peephole(_div_peephole(e, self.double_funs))
-            e = _ternary_to_select_nested(e)
+            e = _ternary_to_select_nested(e, self.double_funs)
             if zmul:
                 e = _zmul_peephole(e)
         return _mangle_expr(e)
@@ -692,7 +694,7 @@ class Emitter:
                 continue
             body = _pow_peephole(f.body) if self.fast_pow else f.body
             body = _div_peephole(body, self.double_funs) if self.fast_div else body
-            body = _mangle_expr(_ternary_to_select(body))
+            body = _mangle_expr(_ternary_to_select(body, self.double_funs))
             w("ODX_HD double %s(%s) { ODX_CONSTS return %s; }" % (mangle(f.name), args, body))
         w("")
         # sincos arguments shared by the RHS and the %M terms: candidates for the stage-to-stage increment

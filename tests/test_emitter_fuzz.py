@@ -106,7 +106,8 @@ class Gen:
     def int_division(self):
         """integer divisions of the reference's C (ID and POP_SIZE are ints): a reciprocal peephole must leave them alone"""
         return self.r.choice(["ID/(2)", "7/(ID+1)", "1/POP_SIZE", "(ID+3)/(POP_SIZE)", "ID/(POP_SIZE-1)", "(2*ID+1)/(2)", "ID/(1+ID/(2))",
-                              "7/(n)", "(ID+1)/(n)", "(n+4)/(2)", "7/(n+p)",          # `par n 3 {int}` is an int in the generated code, p a double
+                              "7/(n)", "(ID+1)/(n)", "(n+4)/(2)", "7/(n+p)",
+                              "((ID > 2) ? 3 : 1)/2", "((ID > 4) ? ID : 1)/(2)", "((n > 2) ? 7 : p)/2",      # a conditional of two ints is an int          # `par n 3 {int}` is an int in the generated code, p a double
                               "3/(2.0+ID)", "ID/(%s+1.5)" % self.r.choice(self.atoms), "POP_SIZE/(ID+1)*%s" % self.atom()])
 
     def gravity_like(self):
