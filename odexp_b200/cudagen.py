@@ -413,6 +413,33 @@ def _antisymmetric_pair_term(term: str):
     return int(ma.group(1)), R, used
 
 
+def _nd(e):
+    """an array entry with more than one index (`name[i=a:b][j=c:d]`)"""
+    return len(getattr(e, "dims", ())) > 1
+
+
+def _arr_decl(e):
+    return mangle(e.name) + "".join("[%d]" % b for _, a, b in e.dims)
+
+
+def _arr_loops(e):
+    return " ".join("for (size_t %s = %d; %s < %d; ++%s)" % (mangle(it), a, mangle(it), b, mangle(it)) for it, a, b in e.dims)
+
+
+def _arr_ref(e):
+    return mangle(e.name) + "".join("[%s]" % mangle(it) for it, _, _ in e.dims)
+
+
+def _arr_flat(e):
+    """position of entry [i][j].. among the stored entries: row-major over the iterated ranges, the order of the reference's nested loops
+    (`*(aux_++) = a[i][j];`, src/odexp:1381-1436)"""
+    s = ""
+    for k, (it, a, b) in enumerate(e.dims):
+        term = "(%s - %d)" % (mangle(it), a)
+        s = term if k == 0 else "(%s*%d + %s)" % (s, b - a, term)
+    return s
+
+
 def is_vect(e):
     """%M name rhs {vect} / {noloop}"""
     return bool(re.search(r"\b(vect|noloop)\b", getattr(e, "attr", "") or ""))
@@ -489,6 +516,11 @@ class Emitter:
             return d[name]
         if kind == "MU":
             return "(odx_c.mu[%d])" % need(self.par_idx, "parameter")
+        if kind in ("MF", "MC") and (where.startswith("%C") or where.startswith("%BIRTH") or (where.startswith("%M") and "{vect}" not in where)):
+            # in the reference MF() is SIM->meanfield[k] (src/odexp.h:357-364): inside the %M / %C loops of pop_rhs it reads whatever the
+            # loop before it left there, a dependence on the evaluation order the population kernels do not reproduce
+            raise PopError("%s(%s) in %s: mean fields / couplings cannot be read inside %%M, %%C or %%BIRTH expressions "
+                           "(read them in an AUX or D/DT expression instead)" % (kind, name, where))
         if kind == "MF":
             return "(odx_mfd[%d])" % need(self.mfd_idx, "mean field")
         if kind == "MC":
@@ -701,7 +733,7 @@ class Emitter:
         hint_slots = {}
         if not terms_use_aux and not rhs_rng:
             shared = self.sincos_args([e.rhs for e in m.auxs if not e.length] + [e.rhs for e in m.eqs if not e.length], "rhs") & \
-                     self.sincos_args([e.rhs for e in m.mfds], "%M")
+                     self.sincos_args([e.rhs for e in m.mfds if not is_vect(e)], "%M")
             hint_slots = {a: i for i, a in enumerate(sorted(shared))}
         self.hint_slots = hint_slots
         w("/* (argument, sin, cos) of the sincos arguments the RHS shares with the %M terms */")
@@ -741,13 +773,17 @@ class Emitter:
                     w("    const %s %s = (%s)odx_c.mu[%d];" % (ctype, mangle(p.name), ctype, i))
             for e in m.exprs:
                 b = self.expr_base[e.name]
-                if e.length:
+                if _nd(e):
+                    w("    double %s; %s %s = odx_e[%d + %s];" % (_arr_decl(e), _arr_loops(e), _arr_ref(e), b, _arr_flat(e)))
+                elif e.length:
                     w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
                       (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
                 else:
                     w("    const double %s = odx_e[%d];" % (mangle(e.name), b))
             for e in m.eqs:
-                if e.length:
+                if _nd(e):
+                    w("    double %s; %s %s = odx_y[%d + %s];" % (_arr_decl(e), _arr_loops(e), _arr_ref(e), self.var_idx[e.name], _arr_flat(e)))
+                elif e.length:
                     w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_y[%d + odx_i];" %
                       (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, self.var_idx[e.name]))
                 else:
@@ -760,7 +796,11 @@ class Emitter:
             # arrays: one loop per entry with the reference's `size_t` iterator (src/odexp:1381-1436, 1439-1506); no common-subexpression
             # hoisting across the loop
             for e in m.auxs:
-                if e.length and is_vect(e):        # filled by a function: the rhs is evaluated once, as a statement (src/odexp:1394-1397)
+                if _nd(e) and is_vect(e):
+                    w("    double %s; %s;" % (_arr_decl(e), self.tr(e.rhs, "aux " + e.name)))
+                elif _nd(e):
+                    w("    double %s; %s %s = %s;" % (_arr_decl(e), _arr_loops(e), _arr_ref(e), self.tr(e.rhs, "aux " + e.name)))
+                elif e.length and is_vect(e):        # filled by a function: the rhs is evaluated once, as a statement (src/odexp:1394-1397)
                     w("    double %s[%d]; %s;" % (mangle(e.name), e.start + e.length, self.tr(e.rhs, "aux " + e.name)))
                 elif e.length:
                     it = mangle(e.iterator)
@@ -769,14 +809,18 @@ class Emitter:
                 else:
                     w("    const double %s = %s;" % (mangle(e.name), self.cse(self.tr(e.rhs, "aux " + e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
             for e in m.eqs:
-                if e.length:
+                if _nd(e):
+                    w("    %s odx_f[%d + %s] = %s;" % (_arr_loops(e), self.var_idx[e.name], _arr_flat(e), self.tr(e.rhs, "d%s/dt" % e.name)))
+                elif e.length:
                     it = mangle(e.iterator)
                     w("    for (size_t %s = %d; %s < %d; ++%s) odx_f[%d + %s - %d] = %s;" % (it, e.start, it, e.start + e.length, it,
                       self.var_idx[e.name], it, e.start, self.tr(e.rhs, "d%s/dt" % e.name)))
                 else:
                     w("    odx_f[%d] = %s;" % (self.var_idx[e.name], self.cse(self.tr(e.rhs, "d%s/dt" % e.name), tc, w, record=hint_slots, hinted=(hint_slots if inc else None), hin="odx_hi")))
             for e in m.auxs:
-                if e.length:
+                if _nd(e):
+                    w("    %s odx_aux[%d + %s] = %s;" % (_arr_loops(e), self.aux_idx[e.name], _arr_flat(e), _arr_ref(e)))
+                elif e.length:
                     w("    for (int odx_i = 0; odx_i < %d; odx_i++) odx_aux[%d + odx_i] = %s[%d + odx_i];" % (e.length, self.aux_idx[e.name], mangle(e.name), e.start))
                 else:
                     w("    odx_aux[%d] = %s;" % (self.aux_idx[e.name], mangle(e.name)))
@@ -906,13 +950,17 @@ class Emitter:
                     w("    const %s %s = (%s)odx_c.mu[%d]; (void)%s;" % (ctype, mangle(p.name), ctype, i, mangle(p.name)))
             for e in m.exprs:
                 b = self.expr_base[e.name]
-                if e.length:
+                if _nd(e):
+                    w("    double %s; %s %s = odx_e[%d + %s];" % (_arr_decl(e), _arr_loops(e), _arr_ref(e), b, _arr_flat(e)))
+                elif e.length:
                     w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_e[%d + odx_i];" %
                       (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, b))
                 else:
                     w("    const double %s = odx_e[%d]; (void)%s;" % (mangle(e.name), b, mangle(e.name)))
             for e in m.eqs:
-                if e.length:
+                if _nd(e):
+                    w("    double %s; %s %s = odx_y[%d + %s];" % (_arr_decl(e), _arr_loops(e), _arr_ref(e), self.var_idx[e.name], _arr_flat(e)))
+                elif e.length:
                     w("    double %s[%d]; for (int odx_i = 0; odx_i < %d; odx_i++) %s[%d + odx_i] = odx_y[%d + odx_i];" %
                       (mangle(e.name), e.start + e.length, e.length, mangle(e.name), e.start, self.var_idx[e.name]))
                 else:
@@ -936,7 +984,13 @@ class Emitter:
                 w("    const double %s = odx_c.mu[%d];" % (mangle(p.name), i))
         for e in m.exprs:
             b = self.expr_base[e.name]
-            if e.length and is_vect(e):
+            if _nd(e) and is_vect(e):
+                w("    double %s; %s;" % (_arr_decl(e), self.tr(e.rhs, "expr " + e.name, exact=True)))
+                w("    %s odx_e[%d + %s] = %s;" % (_arr_loops(e), b, _arr_flat(e), _arr_ref(e)))
+            elif _nd(e):
+                w("    double %s;" % _arr_decl(e))
+                w("    %s { %s = %s; odx_e[%d + %s] = %s; }" % (_arr_loops(e), _arr_ref(e), self.tr(e.rhs, "expr " + e.name, exact=True), b, _arr_flat(e), _arr_ref(e)))
+            elif e.length and is_vect(e):
                 w("    double %s[%d]; %s;" % (mangle(e.name), e.start + e.length, self.tr(e.rhs, "expr " + e.name, exact=True)))
                 w("    for (int odx_i = 0; odx_i < %d; odx_i++) odx_e[%d + odx_i] = %s[%d + odx_i];" % (e.length, b, mangle(e.name), e.start))
             elif e.length:
@@ -948,7 +1002,9 @@ class Emitter:
             else:
                 w("    const double %s = %s; odx_e[%d] = %s;" % (mangle(e.name), self.tr(e.rhs, "expr " + e.name, exact=True), b, mangle(e.name)))
         for e in m.inits:
-            if e.length:
+            if _nd(e):
+                w("    %s odx_y[%d + %s] = %s;" % (_arr_loops(e), self.var_idx[e.name], _arr_flat(e), self.tr(e.rhs, "init " + e.name, exact=True)))
+            elif e.length:
                 it = mangle(e.iterator)
                 w("    for (size_t %s = %d; %s < %d; ++%s) odx_y[%d + %s - %d] = %s;" % (it, e.start, it, e.start + e.length, it, self.var_idx[e.name],
                   it, e.start, self.tr(e.rhs, "init " + e.name, exact=True)))

@@ -6,9 +6,9 @@ case-insensitively by prefix (PAR, EXPR, AUX, D<var>/DT, INIT, LET, MACRO, TIMES
 %BIRTH, %DEATH, %REPLI), `#` starts a comment, `{...}` carries attributes, LET constants are substituted
 textually, `;` separates several PAR / OPT entries on one line, a bare `name value` line is a parameter.
 
-Accepted beyond the basic keywords: `decl const` / `const` arrays, FILE tables, LAG chains, one-dimensional array
-entries `name[i=a:b]`, multi-line `FUN ... end` blocks.  Constructs outside the population path (iterators with more
-than one index, `decl` of anything but constants, the TIMESPAN array mini-language) raise PopError with the line.
+Accepted beyond the basic keywords: `decl const` / `const` arrays, FILE tables, LAG chains, array entries with one or
+more indices `name[i=a:b][j=c:d]`, multi-line `FUN ... end` blocks.  Constructs outside the population path (`decl`
+of anything but constants and delay stacks, the TIMESPAN array mini-language) raise PopError with the line.
 """
 import re
 from dataclasses import dataclass, field
@@ -29,6 +29,8 @@ class Entry:
     length: int = 0          # 0 = scalar, >0 = 1-D array of that many elements
     iterator: str = ""       # iterator name of an array entry
     start: int = 0
+    dims: List[Tuple[str, int, int]] = field(default_factory=list)      # (iterator, first, end) of every index of `name[i=a:b][j=c:d]`;
+                                                                        # length = number of entries, iterator / start = the first index
 
 
 @dataclass
@@ -89,7 +91,10 @@ class PopModel:
     def flat_names(self, entries):
         out = []
         for e in entries:
-            if e.length:
+            if len(e.dims) > 1:
+                import itertools
+                out += [e.name + "".join("[%d]" % k for k in idx) for idx in itertools.product(*[range(a, b) for _, a, b in e.dims])]
+            elif e.length:
                 out += ["%s[%d]" % (e.name, e.start + k) for k in range(e.length)]
             else:
                 out.append(e.name)
@@ -113,6 +118,23 @@ OPT_DEFAULTS = {"res": "201", "hmin": "1e-5", "h0": "1e-1", "abstol": "1e-6", "r
                 "ssahmin": "0.0", "aleap": "0.01", "seed": "3141592", "reseed": "1", "init": "0"}
 
 _RE_ARRAY = re.compile(r"^(%s)\s*\[\s*(\w+)\s*=\s*(\d+)\s*:\s*(\d+)\s*\]$" % IDENT)
+_RE_INDEX = re.compile(r"\[\s*(\w+)\s*=\s*(\d+)\s*:\s*(\d+)\s*\]")
+
+
+def _array_entry(name, brackets, rhs, attr, lineno, raw):
+    """`name[i=a:b]` or `name[i=a:b][j=c:d]...` (declare_scalar_or_array, src/odexp:1288-1340: `double name[b][d]`, nested loops in the
+    order of the indices, entries stored row-major over the iterated ranges)"""
+    dims = [(mm.group(1), int(mm.group(2)), int(mm.group(3))) for mm in _RE_INDEX.finditer(brackets)]
+    if not dims or _RE_INDEX.sub("", brackets).strip():
+        raise PopError("line %d: unsupported index expression in '%s'" % (lineno, raw.strip()))
+    if any(b <= a for _, a, b in dims):
+        raise PopError("line %d: empty iterator range in '%s'" % (lineno, raw.strip()))
+    if len({it for it, _, _ in dims}) != len(dims):
+        raise PopError("line %d: the indices of '%s' need distinct iterators" % (lineno, raw.strip()))
+    n = 1
+    for _, a, b in dims:
+        n *= b - a
+    return Entry(name, rhs, attr, length=n if len(dims) > 1 else dims[0][2] - dims[0][1], iterator=dims[0][0], start=dims[0][1], dims=dims)
 
 
 def _strip_comment(line):
@@ -131,18 +153,12 @@ def _split_attr(s):
 def _name_and_rhs(rest, lineno, raw):
     """`name[iter=a:b] rhs {attr}` -> Entry"""
     rest, attr = _split_attr(rest)
-    m = re.match(r"^(%s(?:\s*\[[^\]]*\])?)\s+(.*)$" % IDENT, rest, flags=re.S)
+    m = re.match(r"^(%s(?:\s*\[[^\]]*\])*)\s+(.*)$" % IDENT, rest, flags=re.S)
     if not m:
         raise PopError("line %d: cannot parse '%s'" % (lineno, raw.strip()))
     lhs, rhs = m.group(1).replace(" ", ""), m.group(2).strip()
-    ma = _RE_ARRAY.match(lhs)
-    if ma:
-        a, b = int(ma.group(3)), int(ma.group(4))
-        if b <= a:
-            raise PopError("line %d: empty iterator range in '%s'" % (lineno, raw.strip()))
-        return Entry(ma.group(1), rhs, attr, length=b - a, iterator=ma.group(2), start=a)
     if "[" in lhs:
-        raise PopError("line %d: unsupported index expression '%s'" % (lineno, lhs))
+        return _array_entry(lhs[:lhs.index("[")], lhs[lhs.index("["):], rhs, attr, lineno, raw)
     return Entry(lhs, rhs, attr)
 
 
@@ -217,7 +233,15 @@ def parse(text: str, name: str = "model", base_dir: str = ".") -> PopModel:
         kwl = kw.lower()
         rest = s[len(kw):].strip()
         if kwl.startswith("par") or kwl.startswith("opt"):
-            parts = [p.strip() for p in rest.split(";") if p.strip()]
+            # the reference breaks PAR / OPT lines at every ';' before it looks for comments (src/odexp:397), so a comment ends at the
+            # next ';' and what follows is another entry: `PAR a 1 {int} # an integer; b 2.3` declares a and b
+            full = raw.strip()
+            i = full.find("#")
+            if i >= 0 and ";" in full[i:] and full.lower().startswith(kwl):
+                for k, v in lets:
+                    full = re.sub(r"\b%s\b" % re.escape(k), v, full)
+                rest = full[len(kw):]
+            parts = [p for p in (_strip_comment(p).strip() for p in rest.split(";")) if p]
         else:
             parts = [rest]
         for rest in parts:
@@ -334,18 +358,15 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.consts.append(("double", f[0], "[%d][%d]" % (nrow, ncol), init))
     elif kwl.startswith("cmd") or kwl.startswith("end"):
         return
-    elif re.match(r"^d%s\s*\[" % IDENT, kw + " " + rest, flags=re.I) and re.match(r"^d(%s)\s*\[([^\]]*)\]\s*/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S):
+    elif re.match(r"^d%s\s*\[" % IDENT, kw + " " + rest, flags=re.I) and re.match(r"^d(%s)\s*((?:\[[^\]]*\]\s*)+)/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S):
         # array of dynamical variables `dX[i=0:5]/dt = rhs`: one equation per index, the iterator is visible in the rhs (src/odexp:1439-1506)
-        mm = re.match(r"^d(%s)\s*\[([^\]]*)\]\s*/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S)
+        mm = re.match(r"^d(%s)\s*((?:\[[^\]]*\]\s*)+)/dt\s*=?\s*(.*)$" % IDENT, kw + " " + rest, flags=re.I | re.S)
         rhs, attr = _split_attr(mm.group(3))
-        ma = _RE_ARRAY.match("%s[%s]" % (mm.group(1), mm.group(2).replace(" ", "")))
-        if not ma or int(ma.group(4)) <= int(ma.group(3)):
-            raise PopError("line %d: unsupported index expression in '%s'" % (lineno, raw.strip()))
-        a, b = int(ma.group(3)), int(ma.group(4))
-        m.eqs.append(Entry(mm.group(1), rhs.strip(), attr, length=b - a, iterator=ma.group(2), start=a))
+        e = _array_entry(mm.group(1), mm.group(2).replace(" ", ""), rhs.strip(), attr, lineno, raw)
+        m.eqs.append(e)
         mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)               # {init = value}: `INIT name[i=a:b] value` (src/odexp:377-382)
         if mi:
-            m.inits.append(Entry(mm.group(1), mi.group(1).strip(), "", length=b - a, iterator=ma.group(2), start=a))
+            m.inits.append(Entry(e.name, mi.group(1).strip(), "", length=e.length, iterator=e.iterator, start=e.start, dims=list(e.dims)))
     elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):
         var = re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I).group(1)
         rhs, attr = _split_attr(rest)
@@ -371,7 +392,7 @@ def _validate(m):
     if dyn != ini:
         raise PopError("initial conditions must be declared for, and in the order of, the dynamical variables: %s vs %s" % (dyn, ini))
     for e, i in zip(m.eqs, m.inits):
-        if (e.length, e.start) != (i.length, i.start):
+        if (e.length, e.start, [d[1:] for d in e.dims]) != (i.length, i.start, [d[1:] for d in i.dims]):
             raise PopError("initial condition of %s does not cover the same index range as its equation" % e.name)
     for k, v in OPT_DEFAULTS.items():
         m.options.setdefault(k, v)

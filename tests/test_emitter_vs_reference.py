@@ -436,3 +436,131 @@ def test_generated_array_model_matches_the_reference_binary(tmp_path, seed, requ
         scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
         err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
         assert np.all(err <= 1e-9), (meth, err, text)
+
+
+# the syntax forms of the manual's "Dynamical system keywords" section (src/odexp.mdoc:383-740) in the spelling the generator accepts today
+# (the manual's `CONST`, `rand01[i]`, one-line FUN without `;` and implicit `var_0` initial conditions are rejected by src/odexp itself)
+SYNTAX_MODELS = {
+    "manual_1": (r"""## man-page syntax forms (in the spelling the generator accepts)
+PAR a 0.1 {every}; b 0.2
+PAR n 3 {int} # n is an int; c 2.3
+PAR d 0.4 {every}
+LET N 5
+decl const double MY_ARRAY[2][3] = { {1.1, 1.2, 1.3}, {2.1, 2.2, 2.3} };
+FUN my_fun_name (x, y, z) = x*x+y+z;
+FUN mean(*x) = sum(x,N)/N;
+FUN myatan( x, *p)
+  double a = *p;
+  return atan(a*x);
+end
+EXPR cc a*a
+EXPR rand_array[i=0:N] -1 + 2*rand01()
+EXPR is_ancestor ATBIRTH*1 + ATREPLI*0
+AUX dd sqrt(x*x+cc)
+AUX sq[i=0:N] X[i]*X[i]
+AUX norm_x sqrt(sum(sq,N))
+AUX norm_x2 dotprod(X,X,N)
+AUX mm mean(X) + myatan(x, rand_array) + my_fun_name(x, a, MY_ARRAY[1][2])
+dx/dt = -a*x + MU(b)*MFX {init = 0.5}
+dX[i=0:N]/dt = -X[i] + n*c*0.01 {init = 0.3}
+dz/dt = -d*z {init = 1.5}
+%M MFX MY(x)
+%M TOTAL POP_SIZE {vect}
+%C PSI cos(OY(x) - MY(x))
+TIMES 0 10
+OPT reltol 1e-3
+OPT popsize 7
+""", dict(nvar=7, naux=9, npsi=1, nmfd=2, nexpr=7), 1e-13),
+    "manual_2": (r"""# second set: long keyword spellings, naked parameters, continuation lines, vect arrays, tags
+PARAMETERS k 1.5 {ever} # rate; s 0.25
+PAR r 0.8 {init}
+delta 2 {int}   # a naked parameter (its name starts like a keyword, so the syntax check lets it through)
+LET NN 4
+MACRO HALF 0.5
+FUNCTION fill(*v)
+  for (int j = 0; j < NN; j++) { v[j] = 0.1*(j+1); }
+  return 0.0;
+end
+FUN wsum(*v, *w) = dotprod(v,w,NN);
+EXPRESSION wgt[i=0:NN] fill(wgt) {vect}
+EXPR e0 r*HALF + ...
+        0.1*rand01()
+AUXILIARY sqv[i=0:NN] fill(sqv) {vect}
+AUX tot wsum(Y, wgt) + sum(sqv,NN) \
+        + delta
+AUX mfread MF(YB)*HALF
+dY[i=0:NN]/dt = -k*Y[i] + s*YB + 0.01*delta {tag = why, init = 0.2*(i+1)}
+dw/dt = -w + tot*0.01 {hidden, init = e0}
+%MEAN YB MY(w)
+%COUPLING PS sin(OY(w) - MY(w))*ME(e0)*OE(e0)
+TIMESPAN 0 1
+OPTIONS popsize 6; meth dde
+OPT h0 0.05 # step; res 3
+""", dict(nvar=5, naux=6, npsi=1, nmfd=1, nexpr=5), 1e-13),
+    "multi_index": (r"""PAR k 1.5
+PAR g 0.2 {init}
+LET NA 2
+LET NB 3
+FUN fill2(*v)
+  for (int q = 0; q < NA*NB; q++) { v[q] = 0.05*(q+1); }
+  return 0.0;
+end
+EXPR w[i=0:NA][j=0:NB] 0.1*(i+1) + 0.01*j + g*rand01()
+EXPR c3[a=1:3][b=0:2][c=2:4] a + 0.1*b + 0.01*c
+EXPR ev[i=0:NA][j=0:NB] fill2(&ev[0][0]) {vect}
+AUX a2[i=0:NA][j=1:NB] w[i][j]*x + U[i][j] + ev[i][j]
+AUX av[i=0:NA][j=0:NB] fill2(&av[0][0]) {vect}
+AUX s a2[1][2] + w[0][1] + c3[2][1][3] + av[1][1]
+dx/dt = -k*x + 0.1*s
+dU[i=0:NA][j=0:NB]/dt = -U[i][j] + ((j > 0) ? U[i][j-1] : x) + 0.01*XB*c3[i+1][0][2]
+dz/dt = -z + U[1][2]
+INIT x 1.0
+INIT U[i=0:NA][j=0:NB] 0.1*i + j + 0.1*rand01()
+INIT z 0.5
+%M XB MY(x)
+TIMES 0 1
+OPT popsize 3
+""", dict(nvar=8, naux=11, npsi=0, nmfd=1, nexpr=20), 0.0),
+}
+
+
+@pytest.mark.parametrize("which", sorted(SYNTAX_MODELS))
+def test_documented_syntax_forms_match_the_reference_binary(tmp_path, which, request):
+    """manual_1: `PAR a 0.1 {every}; b 0.2`, a comment that ends at the next `;` (`PAR n 3 {int} # ...; c 2.3`, src/odexp:397), `decl const
+    double M[2][3]`, one-line / pointer-argument / multi-line FUN, array EXPR / AUX / D/DT, sum / dotprod, `{init = value}` on D/DT,
+    `%M TOTAL POP_SIZE {vect}`, MU() / MF() in the RHS.  manual_2: the long keyword spellings (PARAMETERS, EXPRESSION, AUXILIARY, FUNCTION,
+    %MEAN, %COUPLING, TIMESPAN, OPTIONS), a naked parameter, `...` and `\\` continuation lines, MACRO, `{vect}` arrays filled by a function,
+    `{tag = .., init = ..}` / `{hidden, init = ..}`, `OPT a 1 # comment; b 2`.  multi_index: arrays with two and three indices
+    (`w[i=0:2][j=0:3]`, ranges that do not start at 0, `{vect}` fills through `&a[0][0]`, a guarded neighbour access `U[i][j-1]`),
+    declare_scalar_or_array / define_array_functions (src/odexp:1288-1340, 1381-1506).  The generated code is driven by the checker's loop and
+    compared with the unchanged reference binary on the replayed libc stream; manual_2's coupling sum hoists a factor (1e-13), the rest is bit-identical."""
+    from oracle import build_ref, refrun
+    from odexp_b200 import popfile, cudagen
+    if not build_ref.available() or not build_ref.build():
+        pytest.skip("needs /root/reference to build oracle/_ref")
+    text, dims, rtol = SYNTAX_MODELS[which]
+    name = "syntax_%s" % which
+    assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
+    request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
+    model = popfile.parse(text, name=name)
+    assert (model.nvar, model.naux, model.npsi, model.nmfd, model.nexpr) == tuple(dims[k] for k in ("nvar", "naux", "npsi", "nmfd", "nexpr"))
+    objs = _oracle_objects(str(tmp_path))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
+           "-I" + os.path.join(ROOT, "oracle", "stubinc")]
+    cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
+    src = tmp_path / "ad.cpp"
+    src.write_text(_adapter(cu, model))
+    so = str(tmp_path / "libgen.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for meth in ("dde", "fe"):
+        opts = {"meth": meth, "h0": 0.05, "res": 4, "ps": 7}
+        ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), (0, 0.5), dims=dims)["traj"]
+        out = tmp_path / ("out_" + meth); out.mkdir()
+        got = _run_generated(so, dims, opts, (0, 0.5), str(out))
+        assert len(got) == len(ref) == 7 * 4
+        np.testing.assert_array_equal(got["id"], ref["id"])
+        scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
+        err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
+        assert np.all(err <= rtol), (which, meth, err)

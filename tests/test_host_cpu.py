@@ -350,3 +350,58 @@ def test_model_macros_do_not_reach_the_engine(tmp_path):
                         "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "mac.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_comment_on_a_parameter_line_ends_at_the_next_semicolon():
+    """src/odexp:397 breaks PAR / OPT lines at every ';' before comments are looked at (the manual: "this comment ends at the semi-colon: b is
+    another parameter!"); on every other keyword a comment runs to the end of the line"""
+    from odexp_b200 import popfile
+    m = popfile.parse("let K 4\npar a 1 {int} # an integer; b 2.3; c K # the LET is substituted; d 5\n"
+                      "opt h0 0.05 # step; res 3\naux z x # no; split here\ndx/dt = -a*x # neither; here\ninit x 1\n")
+    assert [(p.name, p.rhs, p.attr) for p in m.pars] == [("a", "1", "int"), ("b", "2.3", ""), ("c", "4", ""), ("d", "5", "")]
+    assert m.options["h0"] == "0.05" and m.options["res"] == "3"
+    assert m.auxs[0].rhs == "x" and m.eqs[0].rhs == "-a*x"
+
+
+def test_mean_fields_cannot_be_read_inside_population_sums():
+    """MF() is SIM->meanfield[k] in the reference (src/odexp.h:357-364): inside %M / %C / %BIRTH it would read the state of pop_rhs's own
+    loops; rejected with a message.  {vect} mean fields (evaluated once, after the loops, in file order) may read the ones before them."""
+    from odexp_b200 import popfile, cudagen
+    for line in ("%C P cos(OY(x) - MY(x)) + MF(XM)", "%M X2 MY(x)*MF(XM)", "%BIRTH 0.1*MF(XM)"):
+        with pytest.raises(popfile.PopError, match="cannot be read inside"):
+            cudagen.emit_cuda(popfile.parse("%M XM MY(x)\n" + line + "\ndx/dt = -x\ninit x 1\n"))
+    cu = cudagen.emit_cuda(popfile.parse("%M XM MY(x)\n%M TWICE 2*MF(XM) {vect}\naux a MF(TWICE)\ndx/dt = -x\ninit x 1\n"))
+    assert "odx_mfd[1] = 2*(odx_mfd[0]);" in cu
+
+
+def test_multi_index_arrays(tmp_path):
+    """`name[i=a:b][j=c:d]`: stored row-major over the iterated ranges, declared with the end of every range (src/odexp:1288-1340), column
+    names `name[i][j]`; the generated file compiles for sm_100a (its results are pinned to the reference binary in
+    tests/test_emitter_vs_reference.py::test_documented_syntax_forms_match_the_reference_binary[multi_index])"""
+    import shutil
+    from odexp_b200 import popfile, cudagen
+    txt = ("expr w[i=0:2][j=1:3] 0.1*i + j\naux a[p=1:3][q=0:2][r=0:2] w[p-1][1]*U[p-1][q] + r\ndx/dt = -x + a[2][1][0]\n"
+           "dU[i=0:2][j=0:3]/dt = -U[i][j] + ((j > 0) ? U[i][j-1] : x) {init = 0.1*i + j}\ninit x 1\n")
+    with pytest.raises(popfile.PopError, match="order of"):
+        popfile.parse(txt)                                        # {init = ..} appends in file order: x must come first, as in the reference
+    txt = txt.replace("dx/dt = -x + a[2][1][0]\n", "dx/dt = -x + a[2][1][0] {init = 1}\n").replace("init x 1\n", "")
+    m = popfile.parse(txt, name="nd")
+    assert (m.nvar, m.naux, m.nexpr) == (7, 8, 4)
+    assert m.flat_names(m.exprs) == ["w[0][1]", "w[0][2]", "w[1][1]", "w[1][2]"]
+    assert m.flat_names(m.eqs)[:4] == ["x", "U[0][0]", "U[0][1]", "U[0][2]"]
+    cu = cudagen.emit_cuda(m)
+    assert "double w[2][3]; for (size_t i = 0; i < 2; ++i) for (size_t j = 1; j < 3; ++j) w[i][j] = odx_e[0 + ((i - 0)*2 + (j - 1))];" in cu
+    assert "odx_aux[0 + (((p - 1)*2 + (q - 0))*2 + (r - 0))] = a[p][q][r];" in cu
+    assert "? U[i][j-1] : x" in cu                               # the guard of a computed index stays a conditional
+    for bad in ("expr w[i=0:2][i=0:3] 1\ndx/dt = -x\ninit x 1\n", "expr w[i=0:2][3] 1\ndx/dt = -x\ninit x 1\n", "expr w[i=0:2][j=3:3] 1\ndx/dt = -x\ninit x 1\n"):
+        with pytest.raises(popfile.PopError):
+            popfile.parse(bad)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not here")
+    src = tmp_path / "nd.cu"
+    src.write_text(cu)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O0", "-std=c++17", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361",
+                        "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "nd.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
