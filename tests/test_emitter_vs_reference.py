@@ -521,6 +521,24 @@ INIT z 0.5
 TIMES 0 1
 OPT popsize 3
 """, dict(nvar=8, naux=11, npsi=0, nmfd=1, nexpr=20), 0.0),
+    # the manual's EXAMPLES section (src/odexp.mdoc:1119-1140), as printed
+    "manual_lotka": (r"""## file lotka.pop
+## a simple nonlinear ODE system
+#  all lines starting with ## are printed with the command ld
+ 
+PAR a 0.2
+PAR b 0.3
+ 
+dx/dt = x*(y - a) # equation on x
+dy/dt = y*(b - x) # equation on y
+ 
+INIT x 0.1 # initial condition for x
+INIT y 0.2 # initial condition for y
+ 
+TIMESPAN 0 10 # timespan is 0 to 10
+
+# end of file
+""", dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0), 0.0),
 }
 
 
@@ -554,12 +572,14 @@ def test_documented_syntax_forms_match_the_reference_binary(tmp_path, which, req
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    for meth in ("dde", "fe"):
-        opts = {"meth": meth, "h0": 0.05, "res": 4, "ps": 7}
-        ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), (0, 0.5), dims=dims)["traj"]
+    lotka = which == "manual_lotka"           # one trajectory under the adaptive steppers (the checker's GSL restatement on both sides)
+    ts = (0, 10) if lotka else (0, 0.5)
+    for meth in (("rkck", "rk8pd", "rk4") if lotka else ("dde", "fe")):
+        opts = {"meth": meth, "h0": 0.1, "res": 11, "ps": 1} if lotka else {"meth": meth, "h0": 0.05, "res": 4, "ps": 7}
+        ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), ts, dims=dims)["traj"]
         out = tmp_path / ("out_" + meth); out.mkdir()
-        got = _run_generated(so, dims, opts, (0, 0.5), str(out))
-        assert len(got) == len(ref) == 7 * 4
+        got = _run_generated(so, dims, opts, ts, str(out))
+        assert len(got) == len(ref) == opts["ps"] * opts["res"]
         np.testing.assert_array_equal(got["id"], ref["id"])
         scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
         err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
