@@ -18,17 +18,45 @@ from .popfile import PopModel, PopError, IDENT
 _C_KEYWORDS = {"double", "int", "float", "long", "return", "if", "else", "for", "while", "const", "static", "void", "char"}
 
 
+# identifiers a C model may use freely (the reference compiles model.c as C) that the generated C++ / CUDA cannot: the template
+# parameter of the generated functions and the C++-only keywords
+_CXX_RESERVED = {"C", "alignas", "alignof", "and", "and_eq", "bitand", "bitor", "catch", "class", "compl", "const_cast", "constexpr",
+                 "decltype", "delete", "dynamic_cast", "explicit", "export", "friend", "mutable", "namespace", "new", "noexcept", "not", "not_eq",
+                 "nullptr", "operator", "or", "or_eq", "private", "protected", "public", "reinterpret_cast", "static_assert", "static_cast",
+                 "template", "this", "thread_local", "throw", "try", "typeid", "typename", "using", "virtual", "wchar_t", "xor", "xor_eq"}
+# functions of the CUDA math API that live in the global namespace and are not part of C's libm: a model FUN of that name would redefine them
+_CUDA_MATH = {"max", "min", "rsqrt", "rcbrt", "sinpi", "cospi", "sincospi", "sincos", "exp10", "erfinv", "erfcinv", "erfcx", "normcdf",
+              "normcdfinv", "cyl_bessel_i0", "cyl_bessel_i1", "norm3d", "norm4d", "rnorm3d", "rnorm4d", "rhypot", "norm", "rnorm", "saturate",
+              "umin", "umax", "llmin", "llmax", "ullmin", "ullmax", "fdivide", "signbit", "clock", "clock64"}
+_fun_renames = set()          # the FUN names of the model being emitted that collide with _CUDA_MATH (set by Emitter.__init__)
+
+
 def mangle(name: str) -> str:
-    """ASCII-safe identifier (nvcc device code does not take the UTF-8 identifiers gcc accepts)"""
+    """ASCII-safe identifier (nvcc device code does not take the UTF-8 identifiers gcc accepts) that is neither a C++ keyword, the
+    generated functions' template parameter, nor a model function named like a CUDA builtin"""
     out = []
     for ch in name:
         out.append(ch if (ch.isascii() and (ch.isalnum() or ch == "_")) else "_u%04x" % ord(ch))
     s = "".join(out)
+    if s in _CXX_RESERVED or s in _fun_renames:
+        s = "odx_v_" + s
     return s
 
 
 def _mangle_expr(expr: str) -> str:
-    return re.sub(IDENT, lambda m: mangle(m.group(0)), expr)
+    def rep(m):
+        name = m.group(0)
+        if name in ("max", "min") and name not in _fun_renames and re.match(r"\s*\(", expr[m.end():]):
+            return "odx_" + name          # the reference's type-generic max(a,b) / min(a,b) macros (src/odexp.h:204-212), see _MINMAX
+        return mangle(name)
+    return re.sub(IDENT, rep, expr)
+
+
+# max(a,b) / min(a,b) of src/odexp.h:204-212 (`_a > _b ? _a : _b` on the arguments' own types: the usual arithmetic conversions, a NaN in
+# the first argument gives the second, unlike fmax / CUDA's max; `+ 0` makes the return type a value, not a reference to an argument); printed into the generated file only when the model calls them
+_MINMAX = """template <class OdxA, class OdxB> ODX_HD auto odx_max(OdxA a, OdxB b) -> decltype((a > b ? a : b) + 0) { return a > b ? a : b; }
+template <class OdxA, class OdxB> ODX_HD auto odx_min(OdxA a, OdxB b) -> decltype((a < b ? a : b) + 0) { return a < b ? a : b; }
+"""
 
 
 def _find_call(expr, fname, start=0):
@@ -450,6 +478,8 @@ class Emitter:
         self.m = m
         self.fast_pow = fast_pow
         self.fast_div = fast_div
+        _fun_renames.clear()
+        _fun_renames.update(f.name for f in m.funs if f.name in _CUDA_MATH)
         self.var_idx = {e.name: m.index_of(m.eqs, e.name) for e in m.eqs}       # flattened base index (arrays count element-wise)
         self.arrays = {e.name for e in list(m.eqs) + list(m.auxs) if e.length}
         self.par_idx = {e.name: i for i, e in enumerate(m.pars)}
@@ -542,6 +572,11 @@ class Emitter:
         """translate one model expression to C++.  exact = True (initial conditions): no arithmetic peepholes, so that replayed
         initial conditions stay bit-identical to the reference's"""
         e = expr.strip().rstrip(";")
+        bad = re.search(r"\b(FIRST|LAST|NEXT|PREVIOUS|NEXTCIRC|PREVIOUSCIRC|EVENT_TYPE|DELAY_FIRST_EVAL|SIM|myself_|other_|PRINT)\b", e)
+        if bad:
+            # src/odexp.h:366-412: pointers into the reference's particle list and its global simulation record
+            raise PopError("%s in %s: the reference's list pointers / simulation record do not exist on the device "
+                           "(neighbours: KY(name, degree); stopping: STOPIF(condition))" % (bad.group(1), where))
         if self.fast_div and self.m.funs and not exact:
             e = _inline_funs(e, self.m.funs)
         e = re.sub(r"\b(MU|MF|MC|MY|OY|SY|ME|OE|SE|MA|OA|SA)\(\s*(%s)\s*\)" % IDENT,
@@ -1075,7 +1110,10 @@ class Emitter:
             for name, _ in m.macros:
                 w("#undef %s" % mangle(name))
         w('#include "odx_engine.cuh"')
-        return "\n".join(L) + "\n"
+        text = "\n".join(L) + "\n"
+        if re.search(r"\bodx_(max|min)\(", text):
+            text = text.replace('#include "odx_model_prelude.cuh"\n', '#include "odx_model_prelude.cuh"\n' + _MINMAX, 1)
+        return text
 
 
 def emit_cuda(model: PopModel, fast_pow: bool = True, fast_div: bool = True) -> str:

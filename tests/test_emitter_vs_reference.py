@@ -539,6 +539,35 @@ TIMESPAN 0 10 # timespan is 0 to 10
 
 # end of file
 """, dict(nvar=2, naux=0, npsi=0, nmfd=0, nexpr=0), 0.0),
+    # names that are fine in the reference's C but not in the generated C++ / CUDA (the template parameter C, C++ keywords, a FUN named
+    # like a CUDA builtin), a variable called min next to calls of the reference's max() / min() macros (src/odexp.h:204-212)
+    "reserved_names": (r"""PAR beta 0.3
+PAR gamma 0.1
+PAR N 1000 {int}
+PAR C 2.0
+PAR new 0.5
+PAR class 2
+PAR min 0.25
+FUN rsqrt(a) = 1.0/sqrt(a);
+FUN clip(v, lo, hi) = max(lo, min(v, hi));
+FUN mix(C, this)
+  double or = C*this;
+  return max(or, 1) + 1.0;
+end
+EXPR E 0.1*rand01()
+AUX A S + I + R
+AUX T2 C*E + mix(E, C) + min
+AUX mx max(S, I)*new + rsqrt(1.0 + R)*class + max (ID, 1)/2 + min(3, 2.5) + clip(I, 2.0, 50)
+dS/dt = -beta*S*I/N
+dI/dt = beta*S*I/N - gamma*I
+dR/dt = gamma*I + 1e-3*T2*mx/A
+INIT S 999 - rand01()
+INIT I 1
+INIT R 0
+%M MI max(MY(I), 2)*MU(C)
+TIMES 0 10
+OPT popsize 3
+""", dict(nvar=3, naux=3, npsi=0, nmfd=1, nexpr=1), 0.0),
 }
 
 

@@ -405,3 +405,33 @@ def test_multi_index_arrays(tmp_path):
                         "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "nd.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_reserved_names_and_minmax_macros(tmp_path):
+    """identifiers that are legal in the reference's C model but not in generated C++ / CUDA are renamed consistently (`C` is the template
+    parameter of the generated functions; `new`, `class`, `this`, `or` are C++ keywords; a FUN called rsqrt would redefine CUDA's); max(a,b) /
+    min(a,b) are the reference's type-generic macros (src/odexp.h:204-212) -- a value-returning template here, a variable called `min` stays
+    a variable; the list-pointer macros are refused by name.  Results vs the reference binary: test_documented_syntax_forms...[reserved_names]"""
+    import shutil
+    from odexp_b200 import popfile, cudagen
+    txt = ("par C 2\npar new 0.5\npar class 2\npar min 0.25\nfun rsqrt(a) = 1.0/sqrt(a);\nfun mix(C, this)\n  double or = C*this;\n  return max(or, 1) + 1.0;\nend\n"
+           "aux a max(x, C)*new + rsqrt(1.0 + x)*class + max (ID, 1)/2 + min + mix(x, C)\ndx/dt = -x + a\ninit x 1\n%M XM min(MY(x), 2)\n")
+    cu = cudagen.emit_cuda(popfile.parse(txt, name="resv"))
+    assert "const double odx_v_C = (double)odx_c.mu[0];" in cu and "odx_v_new" in cu and "odx_v_class" in cu
+    assert "ODX_HD double odx_v_rsqrt(double a)" in cu and "double odx_v_or = odx_v_C*odx_v_this; return odx_max(odx_v_or, 1) + 1.0;" in cu
+    assert "odx_max ((odx_c.id), 1)/2 + min + " in cu and "odx_min((odx_y[0]), 2)" in cu
+    assert "-> decltype((a > b ? a : b) + 0)" in cu                       # a value: decltype of the bare conditional is a reference to an argument
+    assert '"C", "new", "class", "min"' in cu                              # the names a user sees stay the model's
+    assert "odx_max" not in cudagen.emit_cuda(popfile.parse("dx/dt = -x\ninit x 1\n"))
+    for macro in ("NEXT", "FIRST", "EVENT_TYPE", "PRINT"):
+        with pytest.raises(popfile.PopError, match="do not exist on the device"):
+            cudagen.emit_cuda(popfile.parse("aux a %s\ndx/dt = -x\ninit x 1\n" % (macro + ("(\"x\")" if macro == "PRINT" else ""))))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not here")
+    src = tmp_path / "resv.cu"
+    src.write_text(cu)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O0", "-std=c++17", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361",
+                        "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "resv.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
