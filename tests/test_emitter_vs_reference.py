@@ -161,18 +161,20 @@ class Gen:
         return e
 
 
-def model_text(seed):
+def model_text(seed, aux_macros=False):
+    """aux_macros: the couplings also read auxiliaries through MA() (the particle's own pass-1 values) and OA() (the other particle's;
+    the auxiliaries read no mean field, so the list order does not matter: src/odexp:905-954)"""
     rng = random.Random(seed)
     ga = Gen(rng, ["x", "y", "p", "q", "w", "t"])
     gm = Gen(rng, ["MY(x)", "MY(y)", "ME(w)", "MU(p)", "MA(A0)"])
-    gc = Gen(rng, ["MY(x)", "OY(x)", "MY(y)", "OY(y)", "MU(p)", "MU(q)", "ME(w)", "OE(w)"])
+    gc = Gen(rng, ["MY(x)", "OY(x)", "MY(y)", "OY(y)", "MU(p)", "MU(q)", "ME(w)", "OE(w)"] + (["MA(A0)", "OA(A0)", "OA(A1)", "MA(A1)"] if aux_macros else []))
     gd = Gen(rng, ["x", "y", "p", "q", "w", "A0", "A1", "M0", "M1", "C0", "C1"])
     v = rng.choice(["x", "y"])
     L = ["par p 0.7", "par q 1.3", FUNS.rstrip(), "expr w 0.5+rand01()",
-         "aux A0 " + ga.expr(2), "aux A1 " + ga.expr(2),
+         "aux A0 " + ga.expr(2), "aux A1 " + (ga.expr(1) + " + 0.1*A0" if aux_macros else ga.expr(2)),
          "%M M0 MY(x)", "%M M1 " + gm.expr(1),
          "%C C0 " + gc.expr(2),
-         "%%C C1 -MU(q)*gr(MY(%s),OY(%s),MY(x)-OY(x),MY(y)-OY(y))" % (v, v),
+         "%%C C1 -MU(q)*gr(MY(%s),OY(%s),MY(x)-OY(x),MY(y)-OY(y))" % (v, v) + (" + 0.1*OA(A0)*MA(A1)" if aux_macros else ""),
          "dx/dt = -x + 0.2*(%s)" % gd.expr(2), "dy/dt = -0.5*y + 0.2*(%s)" % gd.expr(2),
          "init x rand01()", "init y rand01()-0.5", "timespan 0 0.3", "opt popmode population", "opt popsize 9", "opt meth dde", "opt h0 0.05", "opt res 4"]
     return "\n".join(L) + "\n"
@@ -213,13 +215,13 @@ def _run_generated(so, dims, opts, ts, outdir, want_stats=False):
     return traj, np.fromfile(os.path.join(outdir, "stats.dat"), dtype=sdt)
 
 
-@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 51, 53])
 def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, request):
     from oracle import build_ref, refrun
     from odexp_b200 import popfile, cudagen
     if not build_ref.available() or not build_ref.build():
         pytest.skip("needs /root/reference to build oracle/_ref")
-    text = model_text(seed)
+    text = model_text(seed, aux_macros=seed > 50)
     name = "fuzzmodel_%d" % seed
     assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
     request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
