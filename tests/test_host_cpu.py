@@ -435,3 +435,19 @@ def test_reserved_names_and_minmax_macros(tmp_path):
                         "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "resv.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_fast_sincos_error_bounds(tmp_path):
+    """the two fast sincos forms of the step kernels (csrc/odx_model_prelude.cuh) over their whole range |x| < 105615, against long-double
+    libm: the polynomial form (host branch of the same function) and the table-assisted form of the persistent kernels, whose device
+    branch tests/aux/sincos_bounds.cpp restates operation for operation on the product's own constants (fma = DFMA; table nodes correctly
+    rounded, the device's sincospi gives them to <= 1 ulp).  3 million arguments: small, spread over the range, and next to multiples of
+    pi/2 where the reduction cancels.  Both stay below 1 ulp of 1 in absolute error."""
+    exe = tmp_path / "sc"
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"),
+                        os.path.join(ROOT, "tests", "aux", "sincos_bounds.cpp"), "-o", str(exe), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe), "3000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    table, poly = (float(v) for v in out.stdout.split())
+    assert table <= 2.22e-16 and poly <= 2.22e-16, (table, poly)
