@@ -451,3 +451,16 @@ def test_fast_sincos_error_bounds(tmp_path):
     assert out.returncode == 0, out.stdout
     table, poly = (float(v) for v in out.stdout.split())
     assert table <= 2.22e-16 and poly <= 2.22e-16, (table, poly)
+
+
+def test_fast_inverse_cube_error_bound(tmp_path):
+    """odx_rpow15_fast (x^(-3/2) of the pair kernels' guarded product, csrc/odx_model_prelude.cuh): one approximate reciprocal square root and a
+    second-order correction.  The device branch restated on the CPU (tests/aux/rpow15_bounds.cpp) with the hardware seed replaced by
+    x^(-1/2) (1 + d): for any |d| <= 2^-20 the result is within 3e-16 relative (1.4 ulp) of the long-double value over 36 decades of x;
+    the bound degrades gracefully (1.3e-15 at 18 bits), so the parity tolerances of the N-body tests do not hinge on the exact seed quality."""
+    exe = tmp_path / "rp"
+    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", os.path.join(ROOT, "tests", "aux", "rpow15_bounds.cpp"), "-o", str(exe), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    e20 = float(subprocess.run([str(exe), "20", "1000000"], capture_output=True, text=True, check=True).stdout)
+    e18 = float(subprocess.run([str(exe), "18", "1000000"], capture_output=True, text=True, check=True).stdout)
+    assert e20 <= 3.0e-16 and e18 <= 1.5e-15, (e20, e18)
