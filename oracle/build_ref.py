@@ -65,16 +65,25 @@ def build(force=False, verbose=False):
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
             run(["gcc", "-std=gnu99", "-O3", "-Wall", "-I" + os.path.join(HERE, "stubinc"), "-c", src, "-o", obj])
         objs.append(obj)
-    if os.path.exists(lib):
-        os.remove(lib)
-    run(["ar", "rcs", lib] + objs)
+    newest_obj = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < newest_obj:
+        if os.path.exists(lib):
+            os.remove(lib)
+        run(["ar", "rcs", lib] + objs)
+    gobjs = dropin_objects(force)
     for name, pop in fixtures().items():
         d = os.path.join(OUT, name)
         exe = os.path.join(d, "model.out")
-        if not force and os.path.exists(exe) and os.path.getmtime(exe) > os.path.getmtime(pop) \
-                and os.path.getmtime(exe) > os.path.getmtime(lib) - 1e9:
-            # relink is cheap, but keep incremental builds quick
-            pass
+        # incremental: a fixture is regenerated when its model file (or a data file next to it), the reference's generator, an object
+        # of the library or this recipe is newer than its binaries
+        deps = [pop, os.path.join(REF, "src", "odexp"), os.path.abspath(__file__)] + \
+               [os.path.join(os.path.dirname(pop), x) for x in os.listdir(os.path.dirname(pop)) if x.startswith(name + ".") and not x.endswith(".pop")]
+        stamp = max([newest_obj] + [os.path.getmtime(f) for f in deps])
+        outs = [exe] + ([os.path.join(d, "model_gpu.out")] if name in DROPIN_FIXTURES else [])
+        gstamp = max([stamp] + [os.path.getmtime(o) for o in gobjs]) if name in DROPIN_FIXTURES else stamp
+        if not force and all(os.path.exists(o) for o in outs) and os.path.getmtime(exe) > stamp and os.path.getmtime(outs[-1]) > gstamp \
+                and os.path.isdir(os.path.join(d, ".odexp")):
+            continue
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         local = os.path.join(d, os.path.basename(pop))
@@ -94,7 +103,6 @@ def build(force=False, verbose=False):
         # methods_odexp.c (integration/apply_gpu_branch.py) + integration/odexp_gpu_branch.c -> model_gpu.out.  It runs the GPU
         # branch when ODEXP_CUDA_MODEL names the model library, and the unchanged CPU path otherwise.
         if name in DROPIN_FIXTURES:
-            gobjs = dropin_objects(force)
             run(["gcc"] + CFLAGS + ["-I" + os.path.join(d, ".odexp"), os.path.join(d, ".odexp", "model.c")]
                 + [o for o in objs if not o.endswith(os.sep + "methods_odexp.o")] + gobjs + ["-lm", "-ldl", "-o", os.path.join(d, "model_gpu.out")])
     return True

@@ -180,6 +180,17 @@ def model_text(seed, aux_macros=False):
     return "\n".join(L) + "\n"
 
 
+def _rel_err(got, ref):
+    """largest error per column relative to the column's largest finite magnitude; a random right-hand side may blow up (a quotient by a
+    difference that vanishes): then both sides must turn non-finite in the same entries, with the same infinities"""
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN in different entries"
+    inf = np.isinf(ref) | np.isinf(got)
+    assert np.array_equal(got[inf], ref[inf]), "infinities differ"
+    skip = inf | np.isnan(ref)
+    g, r = np.where(skip, 0.0, got), np.where(skip, 0.0, ref)
+    return (np.abs(g - r) / np.maximum(np.abs(r).max(axis=0), 1e-3)).max(axis=0)
+
+
 def _adapter(cu, parsed):
     """the adapter source around one generated model (its #include lines dropped: the adapter includes the headers itself)"""
     from odexp_b200 import cudagen
@@ -248,8 +259,7 @@ def test_generated_model_code_matches_the_reference_binary(tmp_path, seed, reque
             first = got["step"] == 0
             np.testing.assert_array_equal(got["cols"][first][:, :2], ref["cols"][first][:, :2])          # y: replayed draws, in file order
             np.testing.assert_array_equal(got["cols"][first][:, -1], ref["cols"][first][:, -1])          # expr w
-            scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
-            err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
+            err = _rel_err(got["cols"], ref["cols"])
             assert np.all(err <= rtol), (meth, fast, err, text)
 
 
@@ -435,8 +445,7 @@ def test_generated_array_model_matches_the_reference_binary(tmp_path, seed, requ
         np.testing.assert_array_equal(got["id"], ref["id"])
         first = got["step"] == 0
         np.testing.assert_array_equal(got["cols"][first][:, :nc + 2], ref["cols"][first][:, :nc + 2])
-        scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
-        err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
+        err = _rel_err(got["cols"], ref["cols"])
         assert np.all(err <= 1e-9), (meth, err, text)
 
 
@@ -612,6 +621,5 @@ def test_documented_syntax_forms_match_the_reference_binary(tmp_path, which, req
         got = _run_generated(so, dims, opts, ts, str(out))
         assert len(got) == len(ref) == opts["ps"] * opts["res"]
         np.testing.assert_array_equal(got["id"], ref["id"])
-        scale = np.maximum(np.abs(ref["cols"]).max(axis=0), 1e-3)
-        err = (np.abs(got["cols"] - ref["cols"]) / scale).max(axis=0)
+        err = _rel_err(got["cols"], ref["cols"])
         assert np.all(err <= rtol), (which, meth, err)
