@@ -623,3 +623,58 @@ def test_documented_syntax_forms_match_the_reference_binary(tmp_path, which, req
         np.testing.assert_array_equal(got["id"], ref["id"])
         err = _rel_err(got["cols"], ref["cols"])
         assert np.all(err <= rtol), (which, meth, err)
+
+
+def sde_model_text(seed):
+    """random draws inside the right-hand side (DWDT, randN, rand01, exprand: one per statement, C leaves the order inside one expression
+    open), in scalar and array auxiliaries and equations, inside a hoisted sincos argument, next to a mean field of a noisy auxiliary"""
+    r = random.Random(seed)
+    g = Gen(r, ["x", "y", "s", "q", "w"])
+    draw = lambda: r.choice(["DWDT", "randN(0.0,1.0)", "rand01()", "exprand(2.0)", "DWDT*0.5"])
+    n = r.choice([2, 3])
+    L = ["let NZ %d" % n, "par s 0.3", "par q 1.1", FUNS.rstrip(), "expr w 0.5+rand01()",
+         "aux n1 0.1*%s + 0.01*(%s)" % (draw(), g.expr(1)),
+         "aux zz[i=0:NZ] Z[i]*0.5 + 0.01*%s" % draw(),
+         "aux n2 sin(x + 0.01*%s)*cos(y)" % draw(),
+         "%M XM MY(x)", "%M NM MA(n1)",
+         "dx/dt = -x + s*%s + 0.01*(%s)" % (draw(), g.expr(1)),
+         "dy/dt = -y + 0.1*n1 + 0.1*n2 + 0.01*XM",
+         "dZ[i=0:NZ]/dt = -Z[i] + s*%s + 0.01*zz[i]" % draw(),
+         "init x rand01()", "init y randN(0.0,0.1)", "init Z[i=0:NZ] 0.1*i + 0.01*rand01()",
+         "timespan 0 0.5", "opt popmode population", "opt popsize 5", "opt meth fe", "opt h0 0.01", "opt res 6"]
+    return "\n".join(L) + "\n", n
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_generated_sde_model_matches_the_reference_binary(tmp_path, seed, request):
+    """Euler-Maruyama on the replayed libc stream: the generated code must consume the draws in the reference's order (both passes of
+    pop_rhs evaluate ode_rhs, src/odexp:801-858; auxiliaries then equations, array loops entry by entry) -- one misplaced draw shifts the
+    whole stream, so agreement to 1e-13 over 50 steps means the order is the reference's"""
+    from oracle import build_ref, refrun
+    from odexp_b200 import popfile, cudagen
+    if not build_ref.available() or not build_ref.build():
+        pytest.skip("needs /root/reference to build oracle/_ref")
+    text, n = sde_model_text(seed)
+    name = "fuzzsde_%d" % seed
+    assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
+    request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
+    model = popfile.parse(text, name=name)
+    dims = dict(nvar=2 + n, naux=2 + n, npsi=0, nmfd=2, nexpr=1)
+    opts = {"meth": "fe", "h0": 0.01, "res": 6, "ps": 5}
+    ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), (0, 0.5), dims=dims)["traj"]
+    objs = _oracle_objects(str(tmp_path))
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
+           "-I" + os.path.join(ROOT, "oracle", "stubinc")]
+    cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
+    src = tmp_path / "ad.cpp"
+    src.write_text(_adapter(cu, model))
+    so = str(tmp_path / "libgen.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-w", "-shared"] + ISOLATE + inc + [str(src)] + objs + ["-lm", "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = tmp_path / "out"; out.mkdir()
+    got = _run_generated(so, dims, opts, (0, 0.5), str(out))
+    assert len(got) == len(ref) == 5 * 6
+    np.testing.assert_array_equal(got["id"], ref["id"])
+    err = _rel_err(got["cols"], ref["cols"])
+    assert np.all(err <= 1e-13), (err, text)
