@@ -286,8 +286,17 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         if body.startswith("\x01"):
             m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body[1:].strip() + ";", block=True))
             return
-        if re.search(r"\b(for|while|if|return)\b", body) or ";" in body:
-            raise PopError("line %d: function bodies with statements are not supported" % lineno)
+        # the reference's prescan (src/odexp:356-363) rewrites FUN lines before its generator and its loader read them back from
+        # .odexp/equations.pop: `fun f(a) = return expr;` for a one-liner, `fun f(a) = stmt;stmt;return x;` (the lines of the block glued
+        # together, `end` dropped) for a multi-line function.  Both spellings are accepted, so the device model can be built from that file.
+        one = re.match(r"^return\b\s*(.*)$", body, flags=re.S)
+        if one and ";" not in one.group(1) and not re.search(r"\b(for|while|if|return)\b", one.group(1)):
+            body = one.group(1).strip()
+        elif re.search(r"\b(for|while|if|return)\b", body) or ";" in body:
+            glued = re.sub(r"([;{}])(?=\S)", r"\1 ", body)          # the spacing of the multi-line spelling: one statement per line, joined by blanks
+            glued = re.sub(r";\s+\)", ";)", glued)
+            m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], glued.strip() + ";", block=True))
+            return
         m.funs.append(Fun(mm.group(1), [a.strip() for a in mm.group(2).split(",") if a.strip()], body))
     elif kwl == "%m" or kwl.startswith("%m"):
         e = _name_and_rhs(rest, lineno, raw)
@@ -346,6 +355,9 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
             return default if not mo else (mo.group(2) if mo.group(2) is not None else int(mo.group(1)))
         sep, skip = opt("sep", " "), opt("skip", 0)
         path = fname if os.path.isabs(fname) else os.path.join(m.base_dir, fname)
+        if not os.path.exists(path) and os.path.exists(fname):
+            path = fname              # the reference's generator opens the file relative to the working directory (src/odexp:581-641): the
+                                      # case of a model built from its prescanned copy .odexp/equations.pop
         try:
             lines_ = open(path).read().splitlines()[skip:]
         except OSError as ex:

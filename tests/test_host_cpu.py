@@ -464,3 +464,30 @@ def test_fast_inverse_cube_error_bound(tmp_path):
     e20 = float(subprocess.run([str(exe), "20", "1000000"], capture_output=True, text=True, check=True).stdout)
     e18 = float(subprocess.run([str(exe), "18", "1000000"], capture_output=True, text=True, check=True).stdout)
     assert e20 <= 3.0e-16 and e18 <= 1.5e-15, (e20, e18)
+
+
+def test_device_model_builds_from_the_prescanned_file():
+    """INTEGRATION.md section 1 builds the device model from .odexp/equations.pop, the copy of the model file the reference's prescan writes
+    (src/odexp:311-402: LET values substituted, PAR / OPT lines broken at ';', LAG lines expanded, `{init = ..}` turned into INIT lines,
+    `fun f(a) = return expr;`, multi-line functions glued into one line without `end`).  For every fixture that file must give the same
+    generated code as the model file itself (oracle/_ref/<fixture>/.odexp/ is written by the reference's own generator)."""
+    import glob
+    from odexp_b200 import popfile, cudagen
+    dirs = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "*", ".odexp")))
+    if not dirs:
+        pytest.skip("oracle/_ref not built")
+    seen = 0
+    for d in dirs:
+        name = os.path.basename(os.path.dirname(d))
+        src = fixture_path(name) if os.path.exists(os.path.join(ROOT, "models", name + ".pop")) else None
+        if src is None:
+            continue
+        pre = popfile.parse(open(os.path.join(d, "equations.pop")).read(), name=name, base_dir=os.path.join(ROOT, "models"))
+        assert cudagen.emit_cuda(pre) == cudagen.emit_cuda(popfile.parse_file(src)), name
+        seen += 1
+    assert seen >= 20
+    # the two prescanned FUN spellings on their own
+    m = popfile.parse("fun f(a,b) = return (a > b) ? a : b;\nfun g(*v, n) = int j;double s = 0;for (j = 0; j < n; j++) { s += v[j]; }return s;\n"
+                      "dx/dt = -f(x, 1)\ninit x 1\n")
+    assert (m.funs[0].body, m.funs[0].block) == ("(a > b) ? a : b", False)
+    assert m.funs[1].block and m.funs[1].body == "int j; double s = 0; for (j = 0; j < n; j++) { s += v[j]; } return s;"
