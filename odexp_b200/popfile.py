@@ -378,7 +378,7 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.eqs.append(e)
         mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)               # {init = value}: `INIT name[i=a:b] value` (src/odexp:377-382)
         if mi:
-            m.inits.append(Entry(e.name, mi.group(1).strip(), "", length=e.length, iterator=e.iterator, start=e.start, dims=list(e.dims)))
+            m.inits.append(Entry(e.name, mi.group(1).strip(), "from {init = ..}", length=e.length, iterator=e.iterator, start=e.start, dims=list(e.dims)))
     elif re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I):
         var = re.match(r"^d(%s)/dt$" % IDENT, kw, flags=re.I).group(1)
         rhs, attr = _split_attr(rest)
@@ -386,7 +386,7 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
         m.eqs.append(Entry(var, rhs, attr))
         mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)
         if mi:
-            m.inits.append(Entry(var, mi.group(1).strip()))
+            m.inits.append(Entry(var, mi.group(1).strip(), "from {init = ..}"))
     else:
         mm = re.match(r"^d(%s)/dt\s*=?\s*(.*)$" % IDENT, (kw + " " + rest), flags=re.I | re.S)
         if mm:
@@ -399,6 +399,10 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
 def _validate(m):
     if not m.eqs:
         raise PopError("model has no dynamical variable (d<name>/dt = ...)")
+    # the prescanned copy of a model file (.odexp/equations.pop) carries both the `{init = ..}` attribute and the INIT line the reference's
+    # prescan made of it (src/odexp:377-382): the explicit line stands
+    explicit = {e.name for e in m.inits if e.attr != "from {init = ..}"}
+    m.inits = [e for e in m.inits if not (e.attr == "from {init = ..}" and e.name in explicit)]
     dyn = [e.name for e in m.eqs]
     ini = [e.name for e in m.inits]
     if dyn != ini:

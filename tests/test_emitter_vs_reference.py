@@ -606,6 +606,11 @@ def test_documented_syntax_forms_match_the_reference_binary(tmp_path, which, req
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
            "-I" + os.path.join(ROOT, "oracle", "stubinc")]
     cu = cudagen.Emitter(model, fast_pow=True, fast_div=True).emit()
+    # the prescanned copy the reference's generator wrote (INTEGRATION.md section 1 builds the device model from it) gives the same code, up to
+    # the blanks of the continuation lines
+    pre = popfile.parse(open(os.path.join(build_ref.OUT, name, ".odexp", "equations.pop")).read(), name=name)
+    squeeze = lambda s: __import__("re").sub(r"\s+", " ", s)
+    assert squeeze(cudagen.Emitter(pre, fast_pow=True, fast_div=True).emit()) == squeeze(cu)
     src = tmp_path / "ad.cpp"
     src.write_text(_adapter(cu, model))
     so = str(tmp_path / "libgen.so")
