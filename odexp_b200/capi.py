@@ -19,6 +19,16 @@ class OdxError(RuntimeError):
     pass
 
 
+def method_code(meth):
+    """`opt meth` -> ODX_METH_* (include/odx.h); the implicit GSL steppers of src/methods_odexp.c:154-208 are not built (DESIGN.md section 6:
+    the drop-in binary keeps them on the reference's CPU path)"""
+    try:
+        return METHODS[meth]
+    except KeyError:
+        raise OdxError("meth %s: not a stepping method of the CUDA path (%s); bsimp and the other implicit GSL methods stay on the "
+                       "reference's CPU path" % (meth, ", ".join(sorted(METHODS)))) from None
+
+
 class ModelInfo(C.Structure):
     _fields_ = [("name", C.c_char_p), ("nvar", C.c_int), ("nexpr", C.c_int), ("naux", C.c_int), ("npsi", C.c_int),
                 ("nmfd", C.c_int), ("npar", C.c_int), ("has_birth", C.c_int), ("has_death", C.c_int), ("has_repli", C.c_int),
@@ -267,7 +277,7 @@ class Population:
 
     def evolve_apply(self, method, t, t1, h):
         tt, hh = C.c_double(t), C.c_double(h)
-        self._ck(self.L.odx_evolve_apply(self.h, METHODS[method], C.byref(tt), t1, C.byref(hh)), "odx_evolve_apply")
+        self._ck(self.L.odx_evolve_apply(self.h, method_code(method), C.byref(tt), t1, C.byref(hh)), "odx_evolve_apply")
         return tt.value, hh.value
 
     def evolve_reset(self):
@@ -280,7 +290,7 @@ class Population:
 
     def run_fixed(self, method, t, h, nsteps):
         tt = C.c_double(t)
-        self._ck(self.L.odx_run_fixed(self.h, METHODS[method], C.byref(tt), h, int(nsteps)), "odx_run_fixed")
+        self._ck(self.L.odx_run_fixed(self.h, method_code(method), C.byref(tt), h, int(nsteps)), "odx_run_fixed")
         return tt.value
 
     def event_record(self, slot):
@@ -364,7 +374,7 @@ def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, a
     os.makedirs(outdir, exist_ok=True)
     ts = np.ascontiguousarray(tspan, dtype=np.float64)
     muarr = np.ascontiguousarray(mu, dtype=np.float64) if mu is not None else None
-    o = SolverOpts(METHODS[meth], int(res), hmin, h0, abstol, reltol, ssahmin, aleap, int(popsize), int(seed), 1 if replay_ic else 0,
+    o = SolverOpts(method_code(meth), int(res), hmin, h0, abstol, reltol, ssahmin, aleap, int(popsize), int(seed), 1 if replay_ic else 0,
                    int(traj_stride), outdir.encode(), _dp(ts), len(ts), _dp(muarr), 1 if quick else 0, int(plot[0]), int(plot[1]),
                    int(plot[2]), int(particle), int(init_mode))
     rep = SolverReport()
