@@ -389,9 +389,12 @@ def _dispatch(m, kwl, kw, rest, lineno, raw):
             m.inits.append(Entry(var, mi.group(1).strip(), "from {init = ..}"))
     else:
         mm = re.match(r"^d(%s)/dt\s*=?\s*(.*)$" % IDENT, (kw + " " + rest), flags=re.I | re.S)
-        if mm:
+        if mm:                                                   # `dx/dt=-x`: no blank before the `=`
             rhs, attr = _split_attr(mm.group(2))
             m.eqs.append(Entry(mm.group(1), rhs.strip(), attr))
+            mi = re.search(r"\binit\s*=\s*([^,}]+)", attr)
+            if mi:
+                m.inits.append(Entry(mm.group(1), mi.group(1).strip(), "from {init = ..}"))
             return
         raise PopError("line %d: unknown or unsupported keyword '%s' in '%s'" % (lineno, kw, raw.strip()))
 
