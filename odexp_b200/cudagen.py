@@ -626,10 +626,13 @@ class Emitter:
         (the RHS side of the stage-to-stage increment); hinted: the same map on the %M side, where sincos(A') is then formed
         from the recorded triple and the small difference A' - A"""
         while True:
-            found = None
+            found, skip = None, set()
             for fn in ("sin", "cos"):
                 for b, en, args in _find_call(e, fn):
-                    if len(args) == 1 and not re.search(r"\b(sin|cos)\s*\(", args[0]):
+                    if len(args) == 1 and not re.search(r"\b(sin|cos)\s*\(", args[0]) and not (b, en) in skip:
+                        if re.search(r"odx_c\.(rand01|randN|exprand|poisson|dwdt)\(", args[0]):
+                            skip.add((b, en))        # a draw inside the argument: hoisting it out of a conditional arm would consume the draw
+                            continue                 # even when the reference does not evaluate that arm; the call stays where it is
                         found = (b, en, fn, args[0])
                         break
                 if found:

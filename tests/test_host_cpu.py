@@ -491,3 +491,14 @@ def test_device_model_builds_from_the_prescanned_file():
                       "dx/dt = -f(x, 1)\ninit x 1\n")
     assert (m.funs[0].body, m.funs[0].block) == ("(a > b) ? a : b", False)
     assert m.funs[1].block and m.funs[1].body == "int j; double s = 0; for (j = 0; j < n; j++) { s += v[j]; } return s;"
+
+
+def test_sincos_with_a_draw_in_its_argument_is_not_hoisted():
+    """sin(A) / cos(A) are hoisted into one odx_sincos(A) in front of the statement; not when A draws a random number: out of a conditional
+    arm the draw would be consumed even when the reference does not evaluate the arm, and sin(randN(..))*cos(randN(..)) are two draws"""
+    from odexp_b200 import popfile, cudagen
+    cu = cudagen.emit_cuda(popfile.parse("aux a (x > 0.5) ? sin(rand01()) : 0.0\naux b cos(x)*sin(x) + sin(randN(0,1))*cos(randN(0,1))\n"
+                                         "dx/dt = -x + a + b + sin(DWDT)\ninit x 1\n"))
+    assert "const double a = (x > 0.5) ? sin(odx_c.rand01()) : 0.0;" in cu
+    assert "const double b = odx_cs0*odx_sn0 + sin(odx_c.randN(0,1))*cos(odx_c.randN(0,1));" in cu
+    assert "sin(odx_c.dwdt())" in cu and cu.count("odx_sincos<ODX_EXACT>(odx_c, x,") == 2          # rhs and rhs_inc
