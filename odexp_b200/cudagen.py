@@ -261,6 +261,8 @@ def _inline_funs(expr: str, funs) -> str:
             for b, e, args in _find_call(expr, f.name):
                 if len(args) != len(f.args):
                     continue
+                if any(re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF|delay)\b", a) for a in args):
+                    continue                # call by value evaluates a draw once; substituted text would draw once per use of the parameter
                 body = f.body
                 # two-phase substitution so that an argument text cannot be captured by a later parameter name
                 for k, a in enumerate(f.args):

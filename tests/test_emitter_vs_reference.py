@@ -641,9 +641,11 @@ def sde_model_text(seed):
          "aux n1 0.1*%s + 0.01*(%s)" % (draw(), g.expr(1)),
          "aux zz[i=0:NZ] Z[i]*0.5 + 0.01*%s" % draw(),
          "aux n2 sin(x + 0.01*%s)*cos(y)" % draw(),
+         # a draw as the argument of a one-line function that uses its parameter twice / inside a guard: evaluated once (call by value)
+         "aux n3 0.1*h2(%s, x)" % draw(), "aux n4 0.1*f1(y, %s)" % draw(),
          "%M XM MY(x)", "%M NM MA(n1)",
          "dx/dt = -x + s*%s + 0.01*(%s)" % (draw(), g.expr(1)),
-         "dy/dt = -y + 0.1*n1 + 0.1*n2 + 0.01*XM",
+         "dy/dt = -y + 0.1*n1 + 0.1*n2 + 0.01*XM + 0.1*n3 + 0.1*n4",
          "dZ[i=0:NZ]/dt = -Z[i] + s*%s + 0.01*zz[i]" % draw(),
          "init x rand01()", "init y randN(0.0,0.1)", "init Z[i=0:NZ] 0.1*i + 0.01*rand01()",
          "timespan 0 0.5", "opt popmode population", "opt popsize 5", "opt meth fe", "opt h0 0.01", "opt res 6"]
@@ -664,7 +666,7 @@ def test_generated_sde_model_matches_the_reference_binary(tmp_path, seed, reques
     assert build_ref.build_one(name, text), "the reference's own generator must accept the model"
     request.addfinalizer(lambda: __import__("shutil").rmtree(os.path.join(build_ref.OUT, name), ignore_errors=True))
     model = popfile.parse(text, name=name)
-    dims = dict(nvar=2 + n, naux=2 + n, npsi=0, nmfd=2, nexpr=1)
+    dims = dict(nvar=2 + n, naux=4 + n, npsi=0, nmfd=2, nexpr=1)
     opts = {"meth": "fe", "h0": 0.01, "res": 6, "ps": 5}
     ref = refrun.run(name, dict(opts, hmin=1e-5, abstol=1e-6, reltol=1e-6, ssahmin=0.0, aleap=0.01, seed=3141592), (0, 0.5), dims=dims)["traj"]
     objs = _oracle_objects(str(tmp_path))

@@ -502,3 +502,13 @@ def test_sincos_with_a_draw_in_its_argument_is_not_hoisted():
     assert "const double a = (x > 0.5) ? sin(odx_c.rand01()) : 0.0;" in cu
     assert "const double b = odx_cs0*odx_sn0 + sin(odx_c.randN(0,1))*cos(odx_c.randN(0,1));" in cu
     assert "sin(odx_c.dwdt())" in cu and cu.count("odx_sincos<ODX_EXACT>(odx_c, x,") == 2          # rhs and rhs_inc
+
+
+def test_function_calls_with_draws_are_not_inlined():
+    """one-line model functions are substituted textually so that the peepholes see through them -- not when an argument draws a random
+    number: `sq(rand01())` is u*u of ONE draw (call by value), the substituted text would be the product of two"""
+    from odexp_b200 import popfile, cudagen
+    cu = cudagen.emit_cuda(popfile.parse("fun sq(u) = u*u;\nfun g(p,q) = (p == q) ? 0.0 : (p-q)/sq(q);\n"
+                                         "aux a sq(rand01()) + sq(x) + g(x, DWDT) + g(x, 2.0)\ndx/dt = -x + a\ninit x 1\n"))
+    line = next(ln for ln in cu.splitlines() if "const double a" in ln)
+    assert "sq(odx_c.rand01())" in line and "g(x, odx_c.dwdt())" in line and "((x)*(x))" in line and line.count("rand01") == 1
