@@ -732,6 +732,11 @@ class Emitter:
         cpl_uses_aux = self.uses(cpl_exprs, r"\bMA\(")       # the particle's own pass-1 auxiliary values (src/odexp:820-833, 905-954)
         if self.uses(term_exprs, r"\b(OY|OE)\("):
             raise PopError("OY()/OE() are only meaningful inside %C")
+        if self.uses(term_exprs + cpl_exprs, r"\b(rand01|randN|exprand|poisson|DWDT)\b"):
+            # the reference draws from the serial libc stream once per particle (%M, %BIRTH) or per ordered pair (%C) in list order; the
+            # population sums here run in parallel in another order, and their contexts carry no random stream
+            raise PopError("random numbers inside %M, %C or %BIRTH expressions are not supported (draw them in an EXPR, AUX or D/DT "
+                           "expression and read that through ME() / MA())")
         terms_use_aux = self.uses(term_exprs, r"\bMA\(")
         uses_ky = self.uses(rhs_exprs, r"\bKY\s*\(")
         if self.uses(term_exprs + cpl_exprs + [x.rhs for x in m.exprs] + [x.rhs for x in m.inits], r"\bKY\s*\("):

@@ -194,6 +194,11 @@ def test_emit_rejects_unsupported():
                 "aux a x\n%C P SA(a)\ndx/dt = P\ninit x 0\n"):
         with pytest.raises(popfile.PopError):
             cudagen.emit_cuda(popfile.parse(txt))
+    # draws inside the population sums: serial libc draws in list order in the reference, no random stream in the parallel sums here
+    for txt in ("%C P rand01()*sin(OY(x)-MY(x))\ndx/dt = P\ninit x 0\n", "%M XM MY(x)*randN(0,1)\ndx/dt = XM\ninit x 0\n",
+                "%BIRTH 0.1*exprand(1.0)\ndx/dt = -x\ninit x 0\n"):
+        with pytest.raises(popfile.PopError, match="random numbers inside"):
+            cudagen.emit_cuda(popfile.parse(txt))
     ok = cudagen.emit_cuda(popfile.parse("expr q 1\naux a q*x\n%C P OA(a)*MA(a)\ndx/dt = P\ninit x 0\n"))
     assert "CPL_USES_OAUX = true" in ok and "CPL_USES_AUX = true" in ok and "CPL_USES_EXPR = true" in ok
 
