@@ -25,7 +25,7 @@ _CXX_RESERVED = {"C", "alignas", "alignof", "and", "and_eq", "bitand", "bitor", 
                  "nullptr", "operator", "or", "or_eq", "private", "protected", "public", "reinterpret_cast", "static_assert", "static_cast",
                  "template", "this", "thread_local", "throw", "try", "typeid", "typename", "using", "virtual", "wchar_t", "xor", "xor_eq"}
 # functions of the CUDA math API that live in the global namespace and are not part of C's libm: a model FUN of that name would redefine them
-_CUDA_MATH = {"max", "min", "rsqrt", "rcbrt", "sinpi", "cospi", "sincospi", "sincos", "exp10", "erfinv", "erfcinv", "erfcx", "normcdf",
+_CUDA_MATH = {"max", "min", "abs", "rsqrt", "rcbrt", "sinpi", "cospi", "sincospi", "sincos", "exp10", "erfinv", "erfcinv", "erfcx", "normcdf",
               "normcdfinv", "cyl_bessel_i0", "cyl_bessel_i1", "norm3d", "norm4d", "rnorm3d", "rnorm4d", "rhypot", "norm", "rnorm", "saturate",
               "umin", "umax", "llmin", "llmax", "ullmin", "ullmax", "fdivide", "signbit", "clock", "clock64"}
 _fun_renames = set()          # the FUN names of the model being emitted that collide with _CUDA_MATH (set by Emitter.__init__)
@@ -48,6 +48,8 @@ def _mangle_expr(expr: str) -> str:
         name = m.group(0)
         if name in ("max", "min") and name not in _fun_renames and re.match(r"\s*\(", expr[m.end():]):
             return "odx_" + name          # the reference's type-generic max(a,b) / min(a,b) macros (src/odexp.h:204-212), see _MINMAX
+        if name == "abs" and name not in _fun_renames and re.match(r"\s*\(", expr[m.end():]):
+            return "odx_iabs"             # C's abs() is int abs(int): abs(-0.5) is 0 in the reference's model.c; C++ would pick fabs
         return mangle(name)
     return re.sub(IDENT, rep, expr)
 
@@ -1121,8 +1123,11 @@ class Emitter:
                 w("#undef %s" % mangle(name))
         w('#include "odx_engine.cuh"')
         text = "\n".join(L) + "\n"
-        if re.search(r"\bodx_(max|min)\(", text):
+        if re.search(r"\bodx_(max|min)\s*\(", text):
             text = text.replace('#include "odx_model_prelude.cuh"\n', '#include "odx_model_prelude.cuh"\n' + _MINMAX, 1)
+        if re.search(r"\bodx_iabs\s*\(", text):
+            text = text.replace('#include "odx_model_prelude.cuh"\n', '#include "odx_model_prelude.cuh"\n'
+                                'ODX_HD int odx_iabs(int v) { return v < 0 ? -v : v; }      /* C\'s abs(): the argument converts to int */\n', 1)
         return text
 
 

@@ -569,16 +569,17 @@ EXPR E 0.1*rand01()
 AUX A S + I + R
 AUX T2 C*E + mix(E, C) + min
 AUX mx max(S, I)*new + rsqrt(1.0 + R)*class + max (ID, 1)/2 + min(3, 2.5) + clip(I, 2.0, 50)
+AUX ab abs(I - 3.6) + abs(-3) + fabs(-0.5) + 0.25*abs (R - 0.5)
 dS/dt = -beta*S*I/N
 dI/dt = beta*S*I/N - gamma*I
-dR/dt = gamma*I + 1e-3*T2*mx/A
+dR/dt = gamma*I + 1e-3*T2*mx/A + 1e-3*ab
 INIT S 999 - rand01()
 INIT I 1
 INIT R 0
 %M MI max(MY(I), 2)*MU(C)
 TIMES 0 10
 OPT popsize 3
-""", dict(nvar=3, naux=3, npsi=0, nmfd=1, nexpr=1), 0.0),
+""", dict(nvar=3, naux=4, npsi=0, nmfd=1, nexpr=1), 0.0),
 }
 
 

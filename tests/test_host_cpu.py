@@ -420,11 +420,12 @@ def test_reserved_names_and_minmax_macros(tmp_path):
     import shutil
     from odexp_b200 import popfile, cudagen
     txt = ("par C 2\npar new 0.5\npar class 2\npar min 0.25\nfun rsqrt(a) = 1.0/sqrt(a);\nfun mix(C, this)\n  double or = C*this;\n  return max(or, 1) + 1.0;\nend\n"
-           "aux a max(x, C)*new + rsqrt(1.0 + x)*class + max (ID, 1)/2 + min + mix(x, C)\ndx/dt = -x + a\ninit x 1\n%M XM min(MY(x), 2)\n")
+           "aux a max(x, C)*new + rsqrt(1.0 + x)*class + max (ID, 1)/2 + min + mix(x, C) + abs(x - 2.6)\ndx/dt = -x + a\ninit x 1\n%M XM min(MY(x), 2)\n")
     cu = cudagen.emit_cuda(popfile.parse(txt, name="resv"))
     assert "const double odx_v_C = (double)odx_c.mu[0];" in cu and "odx_v_new" in cu and "odx_v_class" in cu
     assert "ODX_HD double odx_v_rsqrt(double a)" in cu and "double odx_v_or = odx_v_C*odx_v_this; return odx_max(odx_v_or, 1) + 1.0;" in cu
     assert "odx_max ((odx_c.id), 1)/2 + min + " in cu and "odx_min((odx_y[0]), 2)" in cu
+    assert "odx_iabs(x - 2.6)" in cu and "int odx_iabs(int v)" in cu       # C's abs(): abs(-1.6) is 1 in the reference's model.c
     assert "-> decltype((a > b ? a : b) + 0)" in cu                       # a value: decltype of the bare conditional is a reference to an argument
     assert '"C", "new", "class", "min"' in cu                              # the names a user sees stay the model's
     assert "odx_max" not in cudagen.emit_cuda(popfile.parse("dx/dt = -x\ninit x 1\n"))
