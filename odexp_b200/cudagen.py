@@ -27,8 +27,16 @@ _CXX_RESERVED = {"C", "alignas", "alignof", "and", "and_eq", "bitand", "bitor", 
 # functions of the CUDA math API that live in the global namespace and are not part of C's libm: a model FUN of that name would redefine them
 _CUDA_MATH = {"max", "min", "abs", "rsqrt", "rcbrt", "sinpi", "cospi", "sincospi", "sincos", "exp10", "erfinv", "erfcinv", "erfcx", "normcdf",
               "normcdfinv", "cyl_bessel_i0", "cyl_bessel_i1", "norm3d", "norm4d", "rnorm3d", "rnorm4d", "rhypot", "norm", "rnorm", "saturate",
-              "umin", "umax", "llmin", "llmax", "ullmin", "ullmax", "fdivide", "signbit", "clock", "clock64"}
-_fun_renames = set()          # the FUN names of the model being emitted that collide with _CUDA_MATH (set by Emitter.__init__)
+              "umin", "umax", "llmin", "llmax", "ullmin", "ullmax", "fdivide", "signbit", "clock", "clock64",
+              # libm: math.h declares them extern "C"; a model FUN of the same name defines (and in C overrides) the function, in C++ the
+              # definition clashes with the declaration
+              "gamma", "lgamma", "tgamma", "j0", "j1", "jn", "y0", "y1", "yn", "erf", "erfc", "expm1", "log1p", "logb", "ilogb", "cbrt", "hypot",
+              "fdim", "fmax", "fmin", "fma", "fmod", "round", "lround", "trunc", "rint", "lrint", "nearbyint", "remainder", "remquo", "copysign",
+              "nan", "exp2", "log2", "log10", "scalbn", "scalbln", "ldexp", "frexp", "modf", "significand", "drem", "finite", "isinf", "isnan",
+              "sin", "cos", "tan", "asin", "acos", "atan", "atan2", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "log", "pow",
+              "sqrt", "ceil", "floor", "fabs", "nextafter", "div", "labs", "rand", "srand", "exit", "abort", "index", "time", "select", "link",
+              "signal", "pause", "sleep", "read", "write", "open", "close", "pipe", "dup", "sync", "nice", "access", "alarm", "truncate"}
+_fun_renames = set()          # the FUN names of the model being emitted that collide with _CUDA_MATH / libc (set by Emitter.__init__)
 
 
 def mangle(name: str) -> str:
