@@ -289,8 +289,9 @@ def test_antisymmetric_coupling_detection():
           "%C P sin(OY(x)-MY(x))",                                                                # antisymmetric, but not in the proven form
           # a guard that is the whole expression stays a C conditional (only guards inside functions / parentheses become selects: a bare
           # `(i == 0) ? a : X[i-1]` must not evaluate its other arm), so it is not recognised either
-          "%C P (MY(y) == OY(y)) ? 0.0 : (MY(y)-OY(y))/nc(OY(x)-MY(x),MY(y)-OY(y))",
-          "%C P (MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y))*rand01()"]
+          "%C P (MY(y) == OY(y)) ? 0.0 : (MY(y)-OY(y))/nc(OY(x)-MY(x),MY(y)-OY(y))"]
+    with pytest.raises(popfile.PopError, match="random numbers inside"):       # a draw per ordered pair: refused altogether
+        cudagen.emit_cuda(popfile.parse(head + "%C P ((MY(x) == OY(x)) ? 0.0 : (MY(x)-OY(x))/nc(MY(x)-OY(x),MY(y)-OY(y)))*rand01()\n" + tail, name="sym"))
     for line in yes:
         cu = cudagen.emit_cuda(popfile.parse(head + line + "\n" + tail, name="sym"))
         assert "CPL_SYM = true" in cu and "#define ODX_MODEL_CPL_SYM 1" in cu, line
