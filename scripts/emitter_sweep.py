@@ -5,9 +5,11 @@ compare with the reference binary).  One class at a time -- the classes share or
     python scripts/emitter_sweep.py model   20  44      # random %M / %C models vs the reference binary (seeds > 50: couplings read MA() / OA())
     python scripts/emitter_sweep.py array   100 124     # array expressions / auxiliaries / equations
     python scripts/emitter_sweep.py lineage 100 118     # birth / death with inheritance: event rows, ids, states
+    python scripts/emitter_sweep.py sde     100 130     # Euler-Maruyama: order of the random draws
 
-Round-2 record: expr 100-159, model 20-43 and 100-115, array 100-123 (5 skipped: the reference binary aborts in its loader), lineage 100-117:
-no failure."""
+Round-2 record: expr 100-159 and 200-299, model 20-43, 100-115 and 200-239, array 100-123 and 200-239 (15 skipped: the reference binary
+aborts in its loader; 4 random right-hand sides diverge -- `z * (-i)` with the size_t iterator is 1.8e19 on both sides -- and are compared up
+to the first diverged frame), lineage 100-117 and 200-229, sde 100-139: no failure."""
 import os
 import pathlib
 import shutil
@@ -43,6 +45,8 @@ for seed in range(lo, hi):
             T.test_generated_array_model_matches_the_reference_binary(tmp, seed, rq)
         elif which == "lineage":
             T.test_generated_birth_death_model_matches_the_reference_binary(tmp, seed, 1.0 if seed % 2 else 0.0, rq)
+        elif which == "sde":
+            T.test_generated_sde_model_matches_the_reference_binary(tmp, seed, rq)
         else:
             sys.exit("unknown class " + which)
         print("ok", seed, flush=True)

