@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_emitter_vs_reference import SYNTAX_MODELS      # noqa: E402
 from odexp_b200 import build, capi                         # noqa: E402
 
-CASES = [(k, m) for k in ("multi_index", "reserved_names") for m in ("dde", "fe")]
+from test_gpu_syntax import CASES                         # noqa: E402
 OPTS = dict(h0=0.05, res=4, ps=7)
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -27,7 +27,7 @@ if "--make" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "syntax_%s_%s.npz" % (k, meth)), traj=ref["traj"], mfd=ref["stats"]["mfd"])
         build.build_model(text=text, name="syntax_" + k)          # the device library travels to the GPU box prebuilt
     import shutil
-    for k in ("multi_index", "reserved_names"):
+    for k in sorted({c[0] for c in CASES}):
         shutil.rmtree(os.path.join(build_ref.OUT, "syntax_" + k), ignore_errors=True)
     print("goldens and libraries written")
     sys.exit(0)

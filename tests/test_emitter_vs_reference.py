@@ -586,6 +586,21 @@ INIT R 0
 TIMES 0 10
 OPT popsize 3
 """, dict(nvar=3, naux=4, npsi=0, nmfd=1, nexpr=1), 0.0),
+    # ID / OID (int, src/odexp.h:370-371) inside mean fields and couplings, integer arithmetic on them, POP_SIZE as an int
+    "oid_coupling": (r"""PAR k 0.8
+EXPR w 0.5 + rand01()
+AUX par2 (ID % 2)*1.0
+dx/dt = -x + k*P + 0.1*Q + 0.01*R2
+dy/dt = -y + 0.1*par2
+INIT x rand01()
+INIT y 0.1*ID
+%M XM MY(x)*(ID > 2)
+%C P (ID != OID) * sin(OY(x)-MY(x))
+%C Q (OID > ID) ? OE(w)*OY(y) : -ME(w)*MY(y)
+%C R2 (OID - ID)*1.0/(1 + POP_SIZE)
+TIMES 0 1
+OPT popsize 6
+""", dict(nvar=2, naux=1, npsi=3, nmfd=1, nexpr=1), 0.0),
 }
 
 

@@ -9,7 +9,7 @@ import pytest
 
 from conftest import ROOT
 
-CASES = [(k, m) for k in ("multi_index", "reserved_names") for m in ("dde", "fe")]
+CASES = [(k, m) for k in ("multi_index", "reserved_names", "oid_coupling") for m in ("dde", "fe")]
 OPTS = dict(h0=0.05, res=4, ps=7)
 
 
