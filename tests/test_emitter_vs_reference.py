@@ -601,6 +601,22 @@ INIT y 0.1*ID
 TIMES 0 1
 OPT popsize 6
 """, dict(nvar=2, naux=1, npsi=3, nmfd=1, nexpr=1), 0.0),
+    # KY(name, degree): list neighbours at any distance, circular in both directions (src/odexp.h:329-353), degrees beyond the population
+    # size, an int parameter and ID arithmetic as degree
+    "ky_degrees": (r"""PAR D 0.4
+PAR s 2 {int}
+EXPR w 0.5 + rand01()
+AUX lap KY(x, 1) + KY(x, -1) - 2*x
+AUX far KY(x, s) - KY(x, -3) + 0.1*KY(y, 7) + 0.01*KY(y, -8)
+AUX idd KY(y, ID % 3)
+dx/dt = D*lap + 0.01*far
+dy/dt = -y + 0.1*idd + 0.05*KY(x, 2*s)
+INIT x rand01()
+INIT y 0.1*ID
+%M XM MY(x)
+TIMES 0 1
+OPT popsize 6
+""", dict(nvar=2, naux=3, npsi=0, nmfd=1, nexpr=1), 0.0),
 }
 
 
