@@ -617,6 +617,27 @@ INIT y 0.1*ID
 TIMES 0 1
 OPT popsize 6
 """, dict(nvar=2, naux=3, npsi=0, nmfd=1, nexpr=1), 0.0),
+    # low-rank coupling in an auxiliary variable with a multi-line, one-argument model function as kernel (coupling_function is
+    # double (*)(double), src/lrexp.h:13), rank 2 weights, next to a mean field of an expression
+    "lowrank_user_fun": (r"""let R 2
+par K 0.3
+par sc 1.5 {impl}
+expr om 0.5 + rand01()
+expr U[i=0:R] rand01()
+expr V[i=0:R] 0.5 + rand01()
+fun cpf(x)
+  double s = 0.7;
+  x *= s;
+  return sin(x) + 0.25*cos(2*x);
+end
+aux wr th - ( (int) (th/2/3.141592) * 2 * 3.141592 )
+%M OM ME(om)
+%C CPL lrwexp {var = wr, fun = cpf, U = U, V = V, rank = R}
+dth/dt = om + K*CPL
+init th 6.283*rand01()
+timespan 0 1
+opt popsize 40
+""", dict(nvar=1, naux=1, npsi=1, nmfd=1, nexpr=5), 1e-13),
 }
 
 
