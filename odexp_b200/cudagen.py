@@ -490,8 +490,8 @@ class Emitter:
         self.m = m
         self.fast_pow = fast_pow
         self.fast_div = fast_div
-        _fun_renames.clear()
-        _fun_renames.update(f.name for f in m.funs if f.name in _CUDA_MATH)
+        self._renames = {f.name for f in m.funs if f.name in _CUDA_MATH}
+        self._activate()
         self.var_idx = {e.name: m.index_of(m.eqs, e.name) for e in m.eqs}       # flattened base index (arrays count element-wise)
         self.arrays = {e.name for e in list(m.eqs) + list(m.auxs) if e.length}
         self.par_idx = {e.name: i for i, e in enumerate(m.pars)}
@@ -518,6 +518,12 @@ class Emitter:
         for e in m.exprs:
             self.expr_base[e.name] = k
             k += max(1, e.length)
+
+    def _activate(self):
+        """mangle() is a module function: point it at this model's renamed functions (several emitters may be alive at once)"""
+        if _fun_renames != self._renames:
+            _fun_renames.clear()
+            _fun_renames.update(self._renames)
 
     # ---- delay() call sites ----------------------------------------------------------------------
     def _delay_site(self, args, where):
@@ -583,6 +589,7 @@ class Emitter:
     def tr(self, expr: str, where: str, exact: bool = False, zmul: bool = False) -> str:
         """translate one model expression to C++.  exact = True (initial conditions): no arithmetic peepholes, so that replayed
         initial conditions stay bit-identical to the reference's"""
+        self._activate()
         e = expr.strip().rstrip(";")
         bad = re.search(r"\b(FIRST|LAST|NEXT|PREVIOUS|NEXTCIRC|PREVIOUSCIRC|EVENT_TYPE|DELAY_FIRST_EVAL|SIM|myself_|other_|PRINT)\b", e)
         if bad:
@@ -716,6 +723,7 @@ class Emitter:
     # ---- emit ------------------------------------------------------------------------------------
     def emit(self) -> str:
         m = self.m
+        self._activate()
         pair_cpls = [c for c in m.cpls if c.lowrank is None]
         lr_cpls = [c for c in m.cpls if c.lowrank is not None]
         term_exprs = [e.rhs for e in m.mfds] + ([m.birth] if m.birth else [])
