@@ -581,6 +581,11 @@ class Emitter:
         if kind in ("ME", "OE", "SE"):
             i = need(self.expr_base, "parametric expression")
             return {"ME": "(odx_e[%d])", "OE": "(odx_oe[%d])", "SE": "(odx_c.has_sister ? odx_c.sis_e[%d] : 0.0)"}[kind] % i
+        if kind == "MA" and (where.startswith("aux ") or re.match(r"^d.*/dt$", where)):
+            # myself_->aux[] inside ode_rhs is what the PREVIOUS evaluation left there (the array is rewritten at the end of ode_rhs,
+            # src/odexp:1030-1040): a lagged value the stage kernels do not keep
+            raise PopError("MA(%s) in %s: inside AUX / D/DT expressions an auxiliary variable is read by its name (MA() there is the value "
+                           "of the previous evaluation in the reference; not supported)" % (name, where))
         if kind in ("MA", "OA", "SA"):
             i = need(self.aux_idx, "auxiliary variable")
             return {"MA": "(odx_aux[%d])", "OA": "(odx_oaux[%d])", "SA": "(odx_c.has_sister ? odx_c.sis_aux[%d] : 0.0)"}[kind] % i

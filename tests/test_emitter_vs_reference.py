@@ -638,6 +638,20 @@ init th 6.283*rand01()
 timespan 0 1
 opt popsize 40
 """, dict(nvar=1, naux=1, npsi=1, nmfd=1, nexpr=5), 1e-13),
+    # MC() / MF() / MU() read inside AUX and D/DT expressions (the values of the current evaluation), MA() / ME() inside %M
+    "macros_in_rhs": (r"""PAR k 0.8
+EXPR w 0.5 + rand01()
+AUX a0 x*w
+AUX a1 MC(P)*2 + MF(XM) + MU(k) + a0
+dx/dt = -x + k*MC(P) + 0.1*MF(XM)*MC(Q) + 0.01*a1
+INIT x rand01()
+%M XM MY(x)
+%M AM MA(a0) + ME(w)
+%C P sin(OY(x)-MY(x))
+%C Q OE(w)*cos(OY(x)-MY(x))*MU(k)
+TIMES 0 1
+OPT popsize 6
+""", dict(nvar=1, naux=2, npsi=2, nmfd=2, nexpr=1), 1e-13),
 }
 
 

@@ -199,6 +199,11 @@ def test_emit_rejects_unsupported():
                 "%BIRTH 0.1*exprand(1.0)\ndx/dt = -x\ninit x 0\n"):
         with pytest.raises(popfile.PopError, match="random numbers inside"):
             cudagen.emit_cuda(popfile.parse(txt))
+    # MA() inside AUX / D/DT: the previous evaluation's value in the reference (myself_->aux[] is rewritten at the end of ode_rhs)
+    for txt in ("aux a0 x\naux a1 MA(a0)\ndx/dt = -x\ninit x 1\n", "aux a0 x\ndx/dt = -x + MA(a0)\ninit x 1\n"):
+        with pytest.raises(popfile.PopError, match="read by its name"):
+            cudagen.emit_cuda(popfile.parse(txt))
+    cudagen.emit_cuda(popfile.parse("aux a0 x\ndx/dt = -x\ninit x 1\n%DEATH 0.1*MA(a0)\n%M AM MA(a0)\n"))      # rates and sums: the current values
     ok = cudagen.emit_cuda(popfile.parse("expr q 1\naux a q*x\n%C P OA(a)*MA(a)\ndx/dt = P\ninit x 0\n"))
     assert "CPL_USES_OAUX = true" in ok and "CPL_USES_AUX = true" in ok and "CPL_USES_EXPR = true" in ok
 
