@@ -15,5 +15,15 @@ for name in g.MODELS:
     stamp = os.path.join(build.BUILD, "model_%s.stamp" % name)
     if not os.path.exists(stamp) or open(stamp).read().strip() != build._digest(cu):
         stale.append(name)
-print("unchanged: %d of %d" % (len(g.MODELS) - len(stale), len(g.MODELS)) + ("; would rebuild: " + " ".join(stale) if stale else ""))
+# the model-language test models that run on the GPU (tests/test_gpu_syntax.py)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_emitter_vs_reference import SYNTAX_MODELS   # noqa: E402
+from test_gpu_syntax import CASES                      # noqa: E402
+extra = sorted({c[0] for c in CASES})
+for k in extra:
+    cu = cudagen.emit_cuda(popfile.parse(SYNTAX_MODELS[k][0], name="syntax_" + k))
+    stamp = os.path.join(build.BUILD, "model_syntax_%s.stamp" % k)
+    if not os.path.exists(stamp) or open(stamp).read().strip() != build._digest(cu):
+        stale.append("syntax_" + k)
+print("unchanged: %d of %d" % (len(g.MODELS) + len(extra) - len(stale), len(g.MODELS) + len(extra)) + ("; would rebuild: " + " ".join(stale) if stale else ""))
 sys.exit(1 if stale else 0)
