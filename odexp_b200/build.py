@@ -38,7 +38,10 @@ def build_model(pop_path=None, text=None, name=None, force=False, verbose=False,
     if name is None:
         name = os.path.splitext(os.path.basename(pop_path))[0]
     model = popfile.parse(text, name=name, base_dir=os.path.dirname(os.path.abspath(pop_path)) if pop_path else ".")
-    cu = cudagen.emit_cuda(model)
+    # ODX_EMIT_PLAIN=1: the model expressions as written (no reciprocal / pow / select / zero-product rewrites, cudagen.py): the escape hatch
+    # when a rewrite is suspected; the library is cached under its own digest
+    plain = os.environ.get("ODX_EMIT_PLAIN", "0") == "1"
+    cu = cudagen.emit_cuda(model, fast_pow=not plain, fast_div=not plain)
     os.makedirs(BUILD, exist_ok=True)
     so, cu_path, stamp = lib_path(name), os.path.join(BUILD, "model_%s.cu" % name), os.path.join(BUILD, "model_%s.stamp" % name)
     dg = _digest(cu + " ".join(extra_flags))
