@@ -156,7 +156,7 @@ def _ternary_to_select(expr: str, double_funs=None) -> str:
     if c < 0:
         return expr
     cond, a, b = e[:q].strip(), e[q + 1:c].strip(), e[c + 1:].strip()
-    if re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF)\b", a + " " + b):
+    if re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF%s)\b" % "".join("|" + re.escape(n) for n in getattr(double_funs, "rng_names", ())), a + " " + b):
         return expr
     if re.search(r"\[[^\]]*[A-Za-z_][^\]]*\]", a + " " + b):
         return expr            # an arm indexes an array with a computed index (`(i == 0) ? a : X[i-1]`): the guard may be what keeps it in range
@@ -260,7 +260,7 @@ def _div_peephole(expr: str, double_funs=frozenset()) -> str:
         pos = i
 
 
-def _inline_funs(expr: str, funs) -> str:
+def _inline_funs(expr: str, funs, rng=()) -> str:
     """substitute one-line model functions textually (arguments parenthesised), innermost definitions last, so that the
     peepholes below see through `grav(...)` / `normCube(...)`; the functions are still emitted for host use"""
     for _ in range(8):                      # bounded nesting depth
@@ -271,7 +271,7 @@ def _inline_funs(expr: str, funs) -> str:
             for b, e, args in _find_call(expr, f.name):
                 if len(args) != len(f.args):
                     continue
-                if any(re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF|delay)\b", a) for a in args):
+                if any(re.search(r"\b(rand01|randN|exprand|poisson|DWDT|STOPIF|delay%s)\b" % "".join("|" + re.escape(n) for n in rng), a) for a in args):
                     continue                # call by value evaluates a draw once; substituted text would draw once per use of the parameter
                 body = f.body
                 # two-phase substitution so that an argument text cannot be captured by a later parameter name
@@ -492,6 +492,23 @@ class Emitter:
         self.fast_div = fast_div
         self._renames = {f.name for f in m.funs if f.name in _CUDA_MATH}
         self._activate()
+        # model functions that reach the simulation through the reference's global SIM (MU(par), POP_SIZE) or draw random numbers
+        # (rand01() ... are plain C functions there): here they take the evaluation context as their first argument.  rng_funs: the ones
+        # that draw, directly or through another function (a call of one makes the expression a drawing one).
+        self.ctx_funs, self.rng_funs = set(), set()
+        for _ in range(len(m.funs) + 1):
+            for f in m.funs:
+                calls = set(re.findall(IDENT, f.body))
+                if re.search(r"\b(rand01|randN|exprand|poisson|DWDT)\b", f.body) or calls & self.rng_funs:
+                    self.rng_funs.add(f.name)
+                if re.search(r"\b(MU|POP_SIZE)\b", f.body) or f.name in self.rng_funs or calls & self.ctx_funs:
+                    self.ctx_funs.add(f.name)
+        for f in m.funs:
+            bad = re.search(r"\b(MY|ME|MA|MC|MF|OY|OE|OA|SY|SE|SA|KY|ID|MID|OID|STOPIF|ATBIRTH|ATREPLI|ISDAUGHTER|ISMOTHER|delay)\b", f.body)
+            if bad:
+                raise PopError("FUN %s: %s is not available inside a model function (in the reference it needs the particle in scope); "
+                               "pass the value as an argument" % (f.name, bad.group(1)))
+        self.draw_pat = r"\b(DWDT|rand01|randN|exprand|poisson%s)\b" % "".join("|" + re.escape(n) for n in sorted(self.rng_funs))
         self.var_idx = {e.name: m.index_of(m.eqs, e.name) for e in m.eqs}       # flattened base index (arrays count element-wise)
         self.arrays = {e.name for e in list(m.eqs) + list(m.auxs) if e.length}
         self.par_idx = {e.name: i for i, e in enumerate(m.pars)}
@@ -513,6 +530,7 @@ class Emitter:
             dn |= {a.strip() for a in f.args if re.fullmatch(IDENT, a.strip())}
         dn.add("t")
         self.double_funs.double_names = frozenset(dn)
+        self.double_funs.rng_names = tuple(sorted(self.rng_funs))
         self.expr_base = {}
         k = 0
         for e in m.exprs:
@@ -524,6 +542,24 @@ class Emitter:
         if _fun_renames != self._renames:
             _fun_renames.clear()
             _fun_renames.update(self._renames)
+
+    def _ctx_calls(self, e):
+        """calls of context-taking model functions get the context as first argument"""
+        for name in self.ctx_funs:
+            for b, en, args in list(_find_call(e, name))[::-1]:
+                inner = e[b:en]
+                k = inner.index("(")
+                rest = inner[k + 1:].lstrip()
+                e = e[:b] + inner[:k + 1] + ("odx_c)" if rest.startswith(")") else "odx_c, " + inner[k + 1:]) + e[en:]
+        return e
+
+    def _fun_body(self, f, body):
+        """the body of a context-taking model function: MU(par), POP_SIZE and the draws go through the context"""
+        body = self._ctx_calls(body)
+        body = re.sub(r"\bMU\(\s*(%s)\s*\)" % IDENT, lambda mm: self._macro("MU", mm.group(1), "FUN " + f.name), body)
+        body = re.sub(r"\bPOP_SIZE\b", "((int)odx_c.pop_size)", body)
+        body = re.sub(r"\bDWDT\b", "odx_c.dwdt()", body)
+        return re.sub(r"(?<![\w.])(rand01|randN|exprand|poisson)\s*\(", r"odx_c.\1(", body)
 
     # ---- delay() call sites ----------------------------------------------------------------------
     def _delay_site(self, args, where):
@@ -602,7 +638,9 @@ class Emitter:
             raise PopError("%s in %s: the reference's list pointers / simulation record do not exist on the device "
                            "(neighbours: KY(name, degree); stopping: STOPIF(condition))" % (bad.group(1), where))
         if self.fast_div and self.m.funs and not exact:
-            e = _inline_funs(e, self.m.funs)
+            e = _inline_funs(e, [f for f in self.m.funs if f.name not in self.ctx_funs], rng=sorted(self.rng_funs))
+        if self.ctx_funs:
+            e = self._ctx_calls(e)
         e = re.sub(r"\b(MU|MF|MC|MY|OY|SY|ME|OE|SE|MA|OA|SA)\(\s*(%s)\s*\)" % IDENT,
                    lambda mm: self._macro(mm.group(1), mm.group(2), where), e)
         for b, en, args in list(_find_call(e, "KY"))[::-1]:       # KY(name, degree): the degree-th neighbour in list order, ring
@@ -654,7 +692,8 @@ class Emitter:
             for fn in ("sin", "cos"):
                 for b, en, args in _find_call(e, fn):
                     if len(args) == 1 and not re.search(r"\b(sin|cos)\s*\(", args[0]) and not (b, en) in skip:
-                        if re.search(r"odx_c\.(rand01|randN|exprand|poisson|dwdt)\(", args[0]):
+                        if re.search(r"odx_c\.(rand01|randN|exprand|poisson|dwdt)\(", args[0]) or \
+                                any(re.search(r"\b%s\s*\(" % re.escape(mangle(n)), args[0]) for n in self.rng_funs):
                             skip.add((b, en))        # a draw inside the argument: hoisting it out of a conditional arm would consume the draw
                             continue                 # even when the reference does not evaluate that arm; the call stays where it is
                         found = (b, en, fn, args[0])
@@ -745,7 +784,7 @@ class Emitter:
             dirty = set()
             for a in m.auxs:                                   # file order: an auxiliary can only read the ones before it
                 ids = set(re.findall(IDENT, a.rhs))
-                if ids & (tainted | dirty) or re.search(r"\b(MF|MC|KY|rand01|randN|exprand|poisson|DWDT)\b", a.rhs):
+                if ids & (tainted | dirty) or re.search(r"\b(MF|MC|KY)\b", a.rhs) or re.search(self.draw_pat, a.rhs):
                     dirty.add(a.name)
             for ex in cpl_exprs:
                 for nm in re.findall(r"\bOA\(\s*(%s)\s*\)" % IDENT, ex or ""):
@@ -755,7 +794,7 @@ class Emitter:
         cpl_uses_aux = self.uses(cpl_exprs, r"\bMA\(")       # the particle's own pass-1 auxiliary values (src/odexp:820-833, 905-954)
         if self.uses(term_exprs, r"\b(OY|OE)\("):
             raise PopError("OY()/OE() are only meaningful inside %C")
-        if self.uses(term_exprs + cpl_exprs, r"\b(rand01|randN|exprand|poisson|DWDT)\b"):
+        if self.uses(term_exprs + cpl_exprs, self.draw_pat):
             # the reference draws from the serial libc stream once per particle (%M, %BIRTH) or per ordered pair (%C) in list order; the
             # population sums here run in parallel in another order, and their contexts carry no random stream
             raise PopError("random numbers inside %M, %C or %BIRTH expressions are not supported (draw them in an EXPR, AUX or D/DT "
@@ -767,7 +806,7 @@ class Emitter:
         if uses_ky and terms_use_aux:
             raise PopError("KY() together with MA() inside %M is not supported (the reference's first pass sees a half-updated list)")
         cpl_uses_expr = self.uses(cpl_exprs, r"\bOE\(") or (cpl_uses_oaux and m.nexpr > 0)      # the other particle's aux may read its expressions
-        rhs_rng = self.uses(rhs_exprs, r"\b(DWDT|rand01|randN|exprand|poisson)\b")
+        rhs_rng = self.uses(rhs_exprs, self.draw_pat)
         if cpl_uses_aux and rhs_rng:
             raise PopError("MA() inside %C in a model with random numbers in its RHS is not supported (the pass-1 evaluation would consume draws)")
         has_stopif = self.uses(rhs_exprs, r"\bSTOPIF\s*\(")
@@ -788,6 +827,14 @@ class Emitter:
             # arguments are doubles unless they carry a type; `*x` passes an array (src/odexp:694-707)
             args = ", ".join(_mangle_expr(a) if re.search(r"\b(void|int|long|char|float|const)\b", a) else
                              "double " + _mangle_expr(a) for a in f.args)
+            if f.name in self.ctx_funs:
+                # MU(par) / POP_SIZE / random draws inside the function (the reference reaches them through globals): the evaluation
+                # context comes in as the first argument, every call site passes its own (tr / _ctx_calls); no arithmetic rewrites
+                rt = re.search(r"return\s*\((int|long|char|float)\)", f.body) if f.block else None
+                inner = _mangle_expr(self._fun_body(f, f.body))
+                w("template <class OdxC> ODX_HD %s %s(OdxC &odx_c%s) { (void)odx_c; ODX_CONSTS %s }" %
+                  (rt.group(1) if rt else "double", mangle(f.name), ", " + args if args else "", inner if f.block else "return %s;" % inner))
+                continue
             if f.block:
                 rt = re.search(r"return\s*\((int|long|char|float)\)", f.body)
                 w("ODX_HD %s %s(%s) { ODX_CONSTS %s }" % (rt.group(1) if rt else "double", mangle(f.name), args, _mangle_expr(f.body)))

@@ -652,6 +652,27 @@ INIT x rand01()
 TIMES 0 1
 OPT popsize 6
 """, dict(nvar=1, naux=2, npsi=2, nmfd=2, nexpr=1), 1e-13),
+    # model functions that reach the simulation the way the reference's C does -- MU(par) (the manual: attribute impl "for parameters only
+    # accessed through MU() in ... user-defined functions"), POP_SIZE, random draws (plain C functions there) -- directly and through one
+    # another, called from EXPR / INIT / AUX / D/DT / %M / %C, a drawing function inside a guarded arm and inside a sincos argument
+    "context_functions": (r"""PAR k 2 {impl}
+PAR s 0.3
+FUN scaled(u) = u*MU(k)/POP_SIZE;
+FUN noise(a) = a*randN(0.0,1.0);
+FUN two(u)
+  double a = noise(u);
+  return a + scaled(u);
+end
+EXPR e0 scaled(1.0) + rand01()
+AUX a1 (x > 0.3) ? noise(x) : 0.0
+AUX a2 sin(noise(0.1) + x) + scaled(x)
+dx/dt = -x + s*two(x)*0.1 + 0.1*a1 + 0.1*a2 + 0.01*e0
+INIT x scaled(3.0) + rand01()
+%M XM MY(x)*scaled(2.0)
+%C PC sin(OY(x) - MY(x))*scaled(1.0)
+TIMES 0 1
+OPT popsize 5
+""", dict(nvar=1, naux=2, npsi=1, nmfd=1, nexpr=1), 0.0),
 }
 
 

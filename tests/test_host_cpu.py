@@ -524,3 +524,32 @@ def test_function_calls_with_draws_are_not_inlined():
                                          "aux a sq(rand01()) + sq(x) + g(x, DWDT) + g(x, 2.0)\ndx/dt = -x + a\ninit x 1\n"))
     line = next(ln for ln in cu.splitlines() if "const double a" in ln)
     assert "sq(odx_c.rand01())" in line and "g(x, odx_c.dwdt())" in line and "((x)*(x))" in line and line.count("rand01") == 1
+
+
+def test_model_functions_that_read_parameters_or_draw(tmp_path):
+    """MU(par), POP_SIZE and rand01() ... inside a FUN: globals / plain C functions in the reference, the evaluation context here -- such a
+    function takes the context as its first argument and every call site passes its own; a function that draws (directly or through
+    another) makes the model's RHS a drawing one (RHS_RNG), is neither inlined nor evaluated eagerly inside a guard, and stays out of the
+    population sums.  Results vs the reference binary: test_documented_syntax_forms...[context_functions]; compiles for sm_100a."""
+    import shutil
+    from odexp_b200 import popfile, cudagen
+    txt = ("par k 2 {impl}\nfun f(u) = u*MU(k)/POP_SIZE;\nfun noise(s) = s*randN(0.0,1.0);\nfun two(u)\n  double a = noise(u);\n  return a + f(u);\nend\n"
+           "fun plain(u) = u*u;\naux a (x > 0) ? noise(x) : 0.0\naux b sin(noise(x)) + plain(x)\ndx/dt = -f(x) + two(x) + a + b\ninit x f(1.0)\n%M XM MY(x)*f(2.0)\n")
+    cu = cudagen.emit_cuda(popfile.parse(txt, name="ctxf"))
+    assert "template <class OdxC> ODX_HD double f(OdxC &odx_c, double u) { (void)odx_c; ODX_CONSTS return u*(odx_c.mu[0])/((int)odx_c.pop_size); }" in cu
+    assert "double a = noise(odx_c, u); return a + f(odx_c, u);" in cu and "ODX_HD double plain(double u)" in cu
+    assert "const double a = (x > 0) ? noise(odx_c, x) : 0.0;" in cu and "const double b = sin(noise(odx_c, x)) + ((x)*(x));" in cu
+    assert "RHS_RNG = true" in cu and "odx_y[0] = f(odx_c, 1.0);" in cu and "(odx_y[0])*f(odx_c, 2.0)" in cu
+    with pytest.raises(popfile.PopError, match="random numbers inside"):
+        cudagen.emit_cuda(popfile.parse(txt + "%C P noise(1.0)*sin(OY(x)-MY(x))\n"))
+    with pytest.raises(popfile.PopError, match="not available inside a model function"):
+        cudagen.emit_cuda(popfile.parse("fun g(u) = u*MY(x);\ndx/dt = -g(x)\ninit x 1\n"))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not here")
+    src = tmp_path / "ctxf.cu"
+    src.write_text(cu)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O0", "-std=c++17", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361",
+                        "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "ctxf.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
