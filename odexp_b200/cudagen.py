@@ -637,6 +637,8 @@ class Emitter:
             # src/odexp.h:366-412: pointers into the reference's particle list and its global simulation record
             raise PopError("%s in %s: the reference's list pointers / simulation record do not exist on the device "
                            "(neighbours: KY(name, degree); stopping: STOPIF(condition))" % (bad.group(1), where))
+        if re.search(r"\brandIntMax\b", e):
+            raise PopError("randIntMax() in %s: not built (src/rand_gen.c:46-63); (long)(rand01()*n) draws the same distribution" % where)
         if self.fast_div and self.m.funs and not exact:
             e = _inline_funs(e, [f for f in self.m.funs if f.name not in self.ctx_funs], rng=sorted(self.rng_funs))
         if self.ctx_funs:
