@@ -389,3 +389,30 @@ def odesolver(pop: Population, tspan, meth="rkck", res=201, hmin=1e-5, h0=0.1, a
         import shutil
         shutil.rmtree(outdir, ignore_errors=True)
     return res_
+
+
+def solver_args(model, **overrides):
+    """keyword arguments of odesolver() from the OPT / TIMESPAN lines of a parsed model file, the way the reference starts a run from them
+    (GOPTS, src/options.c:6-79; `-a key=value` on the command line = `overrides`, with the same abbreviations: ps, meth, r)"""
+    o = dict(model.options)
+    for k, v in overrides.items():
+        o[popfile.OPT_ABBREV.get(k, k)] = str(v)
+    if o.get("popmode", "population")[:3] == "sin":
+        raise OdxError("popmode single: one trajectory, no population -- stays on the reference's CPU path")
+    return dict(tspan=tuple(model.timespan), meth=o["solver"], res=int(float(o["res"])), hmin=float(o["hmin"]), h0=float(o["h0"]),
+                abstol=float(o["abstol"]), reltol=float(o["reltol"]), popsize=int(float(o["popsize"])), ssahmin=float(o["ssahmin"]),
+                aleap=float(o["aleap"]), seed=int(float(o["seed"])), init_mode=int(float(o.get("init", "0"))),
+                particle=int(float(o.get("particle", "0"))))
+
+
+def run_pop(pop_path, capacity=None, device=0, replay_ic=True, **overrides):
+    """`odexp model.pop` for the population path: build (or reuse) the model library, size the population from `opt popsize`
+    (with room for births), integrate over the file's TIMESPAN with its OPT values; overrides as in solver_args()"""
+    lib = ModelLib.from_pop(pop_path)
+    kw = solver_args(lib.model, **overrides)
+    births = bool(lib.model.birth or lib.model.repli)
+    pop = Population(lib, capacity=capacity or (max(4 * kw["popsize"], 1024) if births else kw["popsize"] + 8), device=device)
+    try:
+        return odesolver(pop, kw.pop("tspan"), replay_ic=replay_ic, **kw)
+    finally:
+        pop.close()

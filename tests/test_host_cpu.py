@@ -553,3 +553,21 @@ def test_model_functions_that_read_parameters_or_draw(tmp_path):
                         "-I" + os.path.join(ROOT, "odexp_b200", "csrc"), "-I" + os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "ctxf.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_run_arguments_from_the_model_file(model_lib):
+    """capi.solver_args / run_pop: a run started from the OPT and TIMESPAN lines of the model file, like `odexp model.pop -a key=value`
+    (defaults of src/options.c:6-79, abbreviations ps / meth / r); without a GPU run_pop gets as far as odx_create and fails loudly"""
+    from odexp_b200 import capi, popfile
+    m = popfile.parse_file(fixture_path("reset_decay"))
+    a = capi.solver_args(m)
+    assert (a["tspan"], a["meth"], a["res"], a["h0"], a["popsize"], a["abstol"], a["seed"]) == ((0.0, 1.5, 3.25, 6.0), "dde", 25, 0.05, 20, 1e-6, 3141592)
+    b = capi.solver_args(m, ps=50, meth="fe", r=11, reltol=1e-9)
+    assert (b["popsize"], b["meth"], b["res"], b["reltol"]) == (50, "fe", 11, 1e-9)
+    assert capi.solver_args(popfile.parse("dx/dt = -x\ninit x 1\n"))["meth"] == "rkck"            # the reference's default stepper
+    with pytest.raises(capi.OdxError, match="popmode single"):
+        capi.solver_args(m, popmode="single")
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.OdxError, match="odx_create"):
+            capi.run_pop(fixture_path("reset_decay"), ps=8)
