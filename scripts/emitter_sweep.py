@@ -7,10 +7,10 @@ compare with the reference binary).  One class at a time -- the classes share or
     python scripts/emitter_sweep.py lineage 100 118     # birth / death with inheritance: event rows, ids, states
     python scripts/emitter_sweep.py sde     100 130     # Euler-Maruyama: order of the random draws
 
-Round-2 record: expr 100-159 and 200-299, model 20-43, 100-115 and 200-299, array 100-123 and 200-239 (15 skipped: the reference binary
-aborts in its loader; 4 random right-hand sides diverge -- `z * (-i)` with the size_t iterator is 1.8e19 on both sides -- and are compared up
-to the first diverged frame), lineage 100-117 and 200-244 (245: the population of the random model explodes, the reference binary itself
-does not finish), sde 100-199: no failure."""
+Round-2 record: expr 100-159 and 200-299, model 20-43, 100-115 and 200-299, array 32-41, 100-123 and 200-299 (about a quarter skipped: the
+reference binary aborts in its loader on long array lines), lineage 100-117 and 200-244 (245: the population of the random model explodes,
+the reference binary itself does not finish), sde 100-259: no failure.  Frames from the first one in which the reference solution holds a
+value beyond 1e12 (a random right-hand side that blows up) are not compared."""
 import os
 import pathlib
 import shutil
